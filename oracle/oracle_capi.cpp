@@ -1,0 +1,337 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.
+// Flat C entry points over the CPU restatement so that tests/ and bench.py's cpu_baseline /
+// --impl reference legs can drive it through ctypes.  Never linked into the product library.
+#include <chrono>
+#include <cstring>
+#include <memory>
+
+#include "compression_oracle.h"
+#include "deform_oracle.h"
+
+using namespace pgmo_oracle;
+
+namespace {
+
+struct ControlTable {
+  std::vector<Point3d> pos;
+  std::vector<Timestamp> stamps;
+  std::vector<uint8_t> valid;
+  std::vector<Pose3> poses;
+  void fill(uint64_t n_c, const double* xyz, const uint64_t* st, const uint8_t* v,
+            const double* poses12) {
+    pos.resize(n_c);
+    stamps.assign(n_c, 0);
+    valid.assign(n_c, 1);
+    poses.resize(n_c);
+    for (uint64_t j = 0; j < n_c; ++j) {
+      pos[j] = {xyz[3 * j], xyz[3 * j + 1], xyz[3 * j + 2]};
+      if (st) stamps[j] = st[j];
+      if (v) valid[j] = v[j];
+      if (poses12) {
+        std::memcpy(poses[j].R, poses12 + 12 * j, 9 * sizeof(double));
+        std::memcpy(poses[j].t, poses12 + 12 * j + 9, 3 * sizeof(double));
+      }
+    }
+  }
+  ValuesView view() const { return {valid.data(), poses.data(), poses.size()}; }
+};
+
+void exportTrace(const DeformTrace& trace, uint64_t n_pos, double* out_f64, int32_t* assoc,
+                 uint32_t assoc_stride, int32_t* assoc_cnt, uint8_t* processed) {
+  if (processed) std::memset(processed, 0, n_pos);
+  if (assoc_cnt) std::memset(assoc_cnt, 0, n_pos * sizeof(int32_t));
+  if (assoc) {
+    for (uint64_t i = 0; i < n_pos * assoc_stride; ++i) assoc[i] = -1;
+  }
+  for (size_t e = 0; e < trace.position.size(); ++e) {
+    const size_t pos = trace.position[e];
+    if (processed) processed[pos] = 1;
+    if (assoc_cnt) assoc_cnt[pos] = static_cast<int32_t>(trace.order[e].size());
+    if (assoc) {
+      for (size_t j = 0; j < trace.order[e].size() && j < assoc_stride; ++j) {
+        assoc[pos * assoc_stride + j] = trace.order[e][j];
+      }
+    }
+    if (out_f64) {
+      out_f64[3 * pos + 0] = trace.pre_cast[3 * e + 0];
+      out_f64[3 * pos + 1] = trace.pre_cast[3 * e + 1];
+      out_f64[3 * pos + 2] = trace.pre_cast[3 * e + 2];
+    }
+  }
+}
+
+struct GraphHandle {
+  DeformationGraphMeshPath graph;
+  std::map<char, ControlTable> tables;
+};
+
+struct CompHandle {
+  std::unique_ptr<MeshCompression> comp;
+  VoxelClearingCompression* vcc = nullptr;
+  HashedIndexMapping remapping;  // the caller-owned persistent map of the reference
+  std::vector<PointXYZRGBA> new_vertices;
+  std::vector<Face> new_triangles;
+  std::vector<size_t> new_indices;
+};
+
+FlatBlockMesh makeMesh(uint32_t n_blocks, const int32_t* block_idx, const uint64_t* offsets,
+                       const float* xyz, const uint32_t* rgba) {
+  FlatBlockMesh mesh;
+  mesh.blocks.resize(n_blocks);
+  mesh.offsets.resize(n_blocks + 1);
+  for (uint32_t b = 0; b < n_blocks; ++b) {
+    mesh.blocks[b] = {block_idx[3 * b], block_idx[3 * b + 1], block_idx[3 * b + 2]};
+  }
+  for (uint32_t b = 0; b <= n_blocks; ++b) mesh.offsets[b] = offsets[b];
+  const uint64_t n = offsets[n_blocks];
+  mesh.vertices.resize(n);
+  for (uint64_t i = 0; i < n; ++i) {
+    mesh.vertices[i].x = xyz[3 * i];
+    mesh.vertices[i].y = xyz[3 * i + 1];
+    mesh.vertices[i].z = xyz[3 * i + 2];
+    mesh.vertices[i].rgba = rgba ? rgba[i] : 0;
+  }
+  return mesh;
+}
+
+}  // namespace
+
+extern "C" {
+
+// deformation::deformPoints (mesh_deformation.h:63-213).  out_* must be pre-filled by the
+// caller (the reference leaves skipped vertices untouched); in-place (out == in) is allowed.
+// Returns 0 = ran, 1 = reference early return.  elapsed_s (optional) = time inside the call.
+int oracle_deform_points(uint64_t n_v, const float* x, const float* y, const float* z,
+                         const uint64_t* stamps, uint64_t n_c, const double* ctrl_xyz,
+                         const uint64_t* ctrl_stamps, const uint8_t* valid,
+                         const double* poses12, uint32_t k, double tol_t,
+                         const uint64_t* indices, uint64_t n_indices, int want_trace,
+                         float* out_x, float* out_y, float* out_z, double* out_f64,
+                         int32_t* assoc, uint32_t assoc_stride, int32_t* assoc_cnt,
+                         uint8_t* processed, double* elapsed_s) {
+  ControlTable table;
+  table.fill(n_c, ctrl_xyz, ctrl_stamps, valid, poses12);
+  DeformIO io;
+  io.num_vertices = n_v;
+  io.in_x = x;
+  io.in_y = y;
+  io.in_z = z;
+  io.stamps = stamps;
+  io.out_x = out_x;
+  io.out_y = out_y;
+  io.out_z = out_z;
+  std::vector<size_t> idx;
+  if (indices) idx.assign(indices, indices + n_indices);
+  std::vector<std::set<size_t>> map;
+  DeformTrace trace;
+  const auto t0 = std::chrono::steady_clock::now();
+  const int rc = deformPoints(io, map, table.pos, table.stamps, table.view(), k, tol_t,
+                              indices ? &idx : nullptr, want_trace ? &trace : nullptr);
+  const auto t1 = std::chrono::steady_clock::now();
+  if (elapsed_s) *elapsed_s = std::chrono::duration<double>(t1 - t0).count();
+  if (want_trace) {
+    exportTrace(trace, indices ? n_indices : n_v, out_f64, assoc, assoc_stride, assoc_cnt,
+                processed);
+  }
+  return rc;
+}
+
+// DeformationGraph mesh path (deformation_graph.h:715-870)
+void* oracle_dgraph_create() { return new GraphHandle(); }
+void oracle_dgraph_destroy(void* h) { delete static_cast<GraphHandle*>(h); }
+void oracle_dgraph_set_controls(void* h, char prefix, uint64_t n_c, const double* ctrl_xyz,
+                                const uint64_t* ctrl_stamps, const uint8_t* valid,
+                                const double* poses12) {
+  auto* g = static_cast<GraphHandle*>(h);
+  auto& t = g->tables[prefix];
+  t.fill(n_c, ctrl_xyz, ctrl_stamps, valid, poses12);
+  g->graph.setControlPoints(prefix, t.pos, t.stamps);
+}
+void oracle_dgraph_set_recalculate(void* h, int v) {
+  static_cast<GraphHandle*>(h)->graph.setRecalculate(v != 0);
+}
+// returns the start index used, or -1 when the prefix is unknown (reference: silent return)
+int64_t oracle_dgraph_deform(void* h, char prefix, uint64_t n_v, const float* x, const float* y,
+                             const float* z, const uint64_t* stamps, uint32_t k, double tol_t,
+                             const int32_t* graph_indices, int start_index_hint, float* out_x,
+                             float* out_y, float* out_z, int32_t* assoc, uint32_t assoc_stride,
+                             int32_t* assoc_cnt) {
+  auto* g = static_cast<GraphHandle*>(h);
+  const auto it = g->tables.find(prefix);
+  if (it == g->tables.end()) return -1;
+  DeformIO io;
+  io.num_vertices = n_v;
+  io.in_x = x;
+  io.in_y = y;
+  io.in_z = z;
+  io.stamps = stamps;
+  io.out_x = out_x;
+  io.out_y = out_y;
+  io.out_z = out_z;
+  std::vector<int> gi;
+  if (graph_indices) gi.assign(graph_indices, graph_indices + n_v);
+  std::vector<std::set<size_t>> vgm;
+  DeformTrace trace;
+  const size_t start = g->graph.deformPoints(io, prefix, it->second.view(), k, tol_t,
+                                             graph_indices ? &gi : nullptr, start_index_hint,
+                                             assoc ? &vgm : nullptr, &trace);
+  if (assoc) {
+    // vertex_graph_map as the reference builds it (deformation_graph.h:857-866), in blend order
+    for (uint64_t i = 0; i < n_v * assoc_stride; ++i) assoc[i] = -1;
+    if (assoc_cnt) std::memset(assoc_cnt, 0, n_v * sizeof(int32_t));
+    for (size_t e = 0; e < trace.vertex.size(); ++e) {
+      // start == 0: entry e of the map; start != 0: scattered to the vertex index
+      const size_t slot = start == 0 ? e : trace.vertex[e];
+      if (assoc_cnt) assoc_cnt[slot] = static_cast<int32_t>(trace.order[e].size());
+      for (size_t j = 0; j < trace.order[e].size() && j < assoc_stride; ++j) {
+        assoc[slot * assoc_stride + j] = trace.order[e][j];
+      }
+    }
+  }
+  return static_cast<int64_t>(start);
+}
+
+// MeshCompression family.  kind: 0 = VoxelClearingCompression, 1 = OctreeCompression
+void* oracle_comp_create(int kind, double resolution) {
+  auto* h = new CompHandle();
+  if (kind == 0) {
+    h->vcc = new VoxelClearingCompression(resolution);
+    h->comp.reset(h->vcc);
+  } else {
+    h->comp.reset(new OctreeCompression(resolution));
+  }
+  return h;
+}
+void oracle_comp_destroy(void* h) { delete static_cast<CompHandle*>(h); }
+
+// compressAndIntegrate with the handle's persistent remapping.  remap_index/remap_kind: dense
+// per-input-vertex record (see RemapRecord); keys: 3 int64 per input vertex (voxel clearing).
+void oracle_comp_integrate(void* hv, uint32_t n_blocks, const int32_t* block_idx,
+                           const uint64_t* offsets, const float* xyz, const uint32_t* rgba,
+                           double stamp_s, int64_t* remap_index, uint8_t* remap_kind,
+                           int64_t* keys, double* elapsed_s) {
+  auto* h = static_cast<CompHandle*>(hv);
+  const FlatBlockMesh mesh = makeMesh(n_blocks, block_idx, offsets, xyz, rgba);
+  RemapRecord rec;
+  const auto t0 = std::chrono::steady_clock::now();
+  h->comp->compressAndIntegrate(mesh, h->new_vertices, h->new_triangles, h->new_indices,
+                                h->remapping, stamp_s, &rec);
+  const auto t1 = std::chrono::steady_clock::now();
+  if (elapsed_s) *elapsed_s = std::chrono::duration<double>(t1 - t0).count();
+  const uint64_t n = offsets[n_blocks];
+  for (uint64_t i = 0; i < n && i < rec.index.size(); ++i) {
+    if (remap_index) remap_index[i] = rec.index[i];
+    if (remap_kind) remap_kind[i] = rec.kind[i];
+  }
+  if (keys && h->vcc) {
+    const auto& k = h->vcc->lastKeys();
+    for (uint64_t i = 0; i < n && i < k.size(); ++i) {
+      keys[3 * i] = k[i].x;
+      keys[3 * i + 1] = k[i].y;
+      keys[3 * i + 2] = k[i].z;
+    }
+  }
+}
+void oracle_comp_prune(void* h, double earliest_s) {
+  static_cast<CompHandle*>(h)->comp->pruneStoredMesh(earliest_s);
+}
+void oracle_comp_clear_blocks(void* hv, uint32_t n_blocks, const int32_t* block_idx) {
+  BlockIndices b(n_blocks);
+  for (uint32_t i = 0; i < n_blocks; ++i) b[i] = {block_idx[3 * i], block_idx[3 * i + 1], block_idx[3 * i + 2]};
+  static_cast<CompHandle*>(hv)->comp->clearArchivedBlocks(b);
+}
+
+// sizes: [num_vertices, num_polygons, num_active, num_invalid, num_new_vertices,
+//         num_new_triangles, num_new_indices, num_active_xyz]
+void oracle_comp_sizes(void* hv, uint64_t* sizes) {
+  auto* h = static_cast<CompHandle*>(hv);
+  sizes[0] = h->comp->getVertices().size();
+  sizes[1] = h->comp->getStoredPolygons().size();
+  sizes[2] = h->comp->getActiveVerticesIndex().size();
+  sizes[3] = h->comp->getInvalidIndices().size();
+  sizes[4] = h->new_vertices.size();
+  sizes[5] = h->new_triangles.size();
+  sizes[6] = h->new_indices.size();
+  sizes[7] = h->comp->getActiveVertices().size();
+}
+// any pointer may be null; buffers sized from oracle_comp_sizes
+void oracle_comp_snapshot(void* hv, float* vertices_xyz, uint32_t* vertices_rgba,
+                          uint64_t* stamps, uint32_t* polygons, uint64_t* active,
+                          uint64_t* invalid, float* new_vertices_xyz, uint32_t* new_triangles,
+                          uint64_t* new_indices, float* active_xyz, double* active_stamps) {
+  auto* h = static_cast<CompHandle*>(hv);
+  const auto& v = h->comp->getVertices();
+  for (size_t i = 0; i < v.size(); ++i) {
+    if (vertices_xyz) {
+      vertices_xyz[3 * i] = v[i].x;
+      vertices_xyz[3 * i + 1] = v[i].y;
+      vertices_xyz[3 * i + 2] = v[i].z;
+    }
+    if (vertices_rgba) vertices_rgba[i] = v[i].rgba;
+    if (stamps) stamps[i] = h->comp->getTimestamps()[i];
+  }
+  const auto& p = h->comp->getStoredPolygons();
+  if (polygons) {
+    for (size_t i = 0; i < p.size(); ++i) {
+      polygons[3 * i] = p[i][0];
+      polygons[3 * i + 1] = p[i][1];
+      polygons[3 * i + 2] = p[i][2];
+    }
+  }
+  const auto& a = h->comp->getActiveVerticesIndex();
+  if (active) {
+    for (size_t i = 0; i < a.size(); ++i) active[i] = a[i];
+  }
+  const auto inv = h->comp->getInvalidIndices();
+  if (invalid) {
+    for (size_t i = 0; i < inv.size(); ++i) invalid[i] = inv[i];
+  }
+  if (new_vertices_xyz) {
+    for (size_t i = 0; i < h->new_vertices.size(); ++i) {
+      new_vertices_xyz[3 * i] = h->new_vertices[i].x;
+      new_vertices_xyz[3 * i + 1] = h->new_vertices[i].y;
+      new_vertices_xyz[3 * i + 2] = h->new_vertices[i].z;
+    }
+  }
+  if (new_triangles) {
+    for (size_t i = 0; i < h->new_triangles.size(); ++i) {
+      new_triangles[3 * i] = h->new_triangles[i][0];
+      new_triangles[3 * i + 1] = h->new_triangles[i][1];
+      new_triangles[3 * i + 2] = h->new_triangles[i][2];
+    }
+  }
+  if (new_indices) {
+    for (size_t i = 0; i < h->new_indices.size(); ++i) new_indices[i] = h->new_indices[i];
+  }
+  const auto& ax = h->comp->getActiveVertices();
+  if (active_xyz) {
+    for (size_t i = 0; i < ax.size(); ++i) {
+      active_xyz[3 * i] = ax[i].x;
+      active_xyz[3 * i + 1] = ax[i].y;
+      active_xyz[3 * i + 2] = ax[i].z;
+    }
+  }
+  if (active_stamps) {
+    const auto& as = h->comp->getActiveVerticesTimestamps();
+    for (size_t i = 0; i < as.size(); ++i) active_stamps[i] = as[i];
+  }
+}
+// persistent remapping lookup: -1 if the block or the local index has no entry
+int64_t oracle_comp_remap_lookup(void* hv, int32_t bx, int32_t by, int32_t bz, uint64_t local) {
+  auto* h = static_cast<CompHandle*>(hv);
+  const auto b = h->remapping.find(BlockIndex{bx, by, bz});
+  if (b == h->remapping.end()) return -1;
+  const auto e = b->second.find(local);
+  if (e == b->second.end()) return -1;
+  return static_cast<int64_t>(e->second);
+}
+int64_t oracle_comp_remap_block_size(void* hv, int32_t bx, int32_t by, int32_t bz) {
+  auto* h = static_cast<CompHandle*>(hv);
+  const auto b = h->remapping.find(BlockIndex{bx, by, bz});
+  if (b == h->remapping.end()) return -1;
+  return static_cast<int64_t>(b->second.size());
+}
+
+uint64_t oracle_stamp_from_sec(double sec) { return stampFromSec(sec); }
+
+}  // extern "C"
