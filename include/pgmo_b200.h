@@ -1,0 +1,233 @@
+/* pgmo_b200.h — C ABI of the B200-native Kimera-PGMO mesh path (libpgmo_b200.so).
+ *
+ * Plain pointers and sizes only; no C++ / torch / PCL / GTSAM types cross this boundary.
+ * The header-only C++ shim under include/kimera_pgmo_b200/ re-creates the reference's C++
+ * API (same namespaces, names and argument meaning) on top of these entry points; see
+ * INTEGRATION.md for the binding a Kimera-PGMO maintainer would add.
+ *
+ * Reference interfaces replaced (paths relative to the Kimera-PGMO tree):
+ *   pgmo_deform_points*      kimera_pgmo/include/kimera_pgmo/mesh_deformation.h:63-75 (unstamped
+ *                            deformPoints), :129-141 (stamped deformPoints) incl. interpPoint
+ *                            (src/mesh_deformation.cpp:73-106) and SearchTree (:22-70)
+ *   pgmo_deform_predeform*   include/kimera_pgmo/deformation_graph.h:779-806 (predeformPoints)
+ *   pgmo_vcc_*               include/kimera_pgmo/compression/voxel_clearing_compression.h:14-97,
+ *                            src/compression/voxel_clearing_compression.cpp:34-210
+ *   pgmo_oct_*               include/kimera_pgmo/compression/octree_compression.h:29-66 +
+ *                            mesh_compression.h:85-96 (compressAndIntegrate / pruneStoredMesh of
+ *                            the base class, src/compression/mesh_compression.cpp:216-464)
+ *   pgmo_stamp_from_sec      src/utils/common_structs.cpp:21-24
+ *
+ * Conventions
+ *   - Return value: 0 = done; > 0 = the reference would have returned early and left the
+ *     outputs untouched (so do we); < 0 = error, message via pgmo_last_error().
+ *   - Nothing throws across the boundary.  Where the reference would raise
+ *     std::out_of_range (.at()), the call returns PGMO_ERR_OUT_OF_RANGE and the shim re-raises.
+ *   - Host entry points take host pointers, copy them in, and do not retain them.
+ *     *_device entry points take device pointers valid on the handle's device and enqueue on
+ *     the given CUDA stream (cudaStream_t passed as void*; NULL = the handle's own stream).
+ *   - Handles are independent: no global state, one CUDA stream each, never the default
+ *     stream; two handles may be driven from two host threads concurrently (the reference
+ *     runs two compressors on two std::threads, mesh_frontend_interface.cpp:100-110).  A single
+ *     handle is not thread-safe (the reference serialises deformMesh under
+ *     KimeraPgmo::interface_mutex_, kimera_pgmo_ros/src/kimera_pgmo.cpp:296-306).
+ *   - There is no CPU fallback: every entry point that computes fails with
+ *     PGMO_ERR_NO_DEVICE when no CUDA device is usable.
+ */
+#ifndef PGMO_B200_H_
+#define PGMO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PGMO_OK 0
+#define PGMO_NOOP 1               /* reference early return: outputs untouched */
+#define PGMO_ERR_INVALID (-1)     /* bad argument */
+#define PGMO_ERR_CUDA (-2)        /* CUDA runtime failure */
+#define PGMO_ERR_NO_DEVICE (-3)   /* no usable GPU (there is no CPU fallback) */
+#define PGMO_ERR_UNSUPPORTED (-4)
+#define PGMO_ERR_OUT_OF_RANGE (-5) /* reference would throw std::out_of_range */
+
+#define PGMO_PRECISION_FP64 0 /* reference arithmetic: f32 distances, f64 weights + blend */
+#define PGMO_PRECISION_FP32 1 /* f32 distances (identical associations), f32 weights + blend */
+
+const char* pgmo_last_error(void); /* thread-local, valid until the next call on this thread */
+const char* pgmo_version(void);
+int pgmo_device_count(void);
+uint64_t pgmo_stamp_from_sec(double sec);
+
+/* ------------------------------------------------------------------------------------------
+ * Deformation: deformation::deformPoints behind one handle per (DeformationGraph, prefix).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct pgmo_deform pgmo_deform_t;
+
+int pgmo_deform_create(int device, pgmo_deform_t** out);
+void pgmo_deform_destroy(pgmo_deform_t* h);
+
+/* Control table = what the hot path reads from DeformationGraph::vertex_positions_[prefix],
+ * vertex_stamps_[prefix] (deformation_graph.h:678-679) and from `values`:
+ *   pos_xyz   n_c x 3 f64 (control_points[j])
+ *   stamps_ns n_c u64, may be NULL for the unstamped overload
+ *   valid     n_c u8: values.exists(gtsam::Symbol(prefix, j)); NULL = all valid
+ *   poses12   n_c x 12 f64: values.at<Pose3>(Symbol(prefix, j)) as row-major R (9) then t (3);
+ *             entries with valid[j] == 0 are never read
+ * Copies; may be called again after every solve. */
+int pgmo_deform_set_controls(pgmo_deform_t* h, uint64_t n_c, const double* pos_xyz,
+                             const uint64_t* stamps_ns, const uint8_t* valid,
+                             const double* poses12);
+/* Same from device memory (e.g. after an NCCL broadcast); stream-ordered on `stream`. */
+int pgmo_deform_set_controls_device(pgmo_deform_t* h, uint64_t n_c, const double* d_pos_xyz,
+                                    const uint64_t* d_stamps_ns, const uint8_t* d_valid,
+                                    const double* d_poses12, void* stream);
+
+/* Replace only the poses (what changes after every solve when no node was added); n_c x 12 f64.
+ * The cached window schedule stays valid: it depends on position / stamp / validity only. */
+int pgmo_deform_update_poses(pgmo_deform_t* h, const double* poses12);
+int pgmo_deform_update_poses_device(pgmo_deform_t* h, const double* d_poses12, void* stream);
+
+/* Optional kernel timing for roofline reporting: when enabled, pgmo_deform_run_device brackets
+ * its kernels with CUDA events on the launching stream.  pgmo_deform_last_timings waits for the
+ * last run and returns ms2 = [knn+blend kernel, tie resolver kernel] in milliseconds, plus the
+ * number of times the window schedule has been (re)built on this handle. */
+int pgmo_deform_set_profiling(pgmo_deform_t* h, int enabled);
+int pgmo_deform_last_timings(pgmo_deform_t* h, float* ms2, uint64_t* schedule_builds);
+
+/* deformation::deformPoints, host buffers, whole job.
+ *   x,y,z        n_v f32 each (SoA vertex stream)
+ *   stamps_ns    n_v u64; NULL selects the unstamped overload (mesh_deformation.h:63-113)
+ *   subset_idx   optional `indices` argument (n_subset entries, processed in this order)
+ *   k, tol_t     as in the reference (k+1 neighbours are blended, the (k+2)-th sets d_max)
+ *   out_x/y/z    n_v f32; written only at processed vertices (others keep the caller's data)
+ * Optional outputs, one slot per *processing position* p (p < n_subset, or p < n_v):
+ *   out_xyz_f64  3 f64: blended point before the final cast<float>() (FP64 mode only)
+ *   assoc        assoc_stride u32: neighbour control indices in blend order, 0xFFFFFFFF padded
+ *   assoc_cnt    u8: number of blended neighbours (= entries of the reference's std::set,
+ *                before set de-duplication)
+ *   processed    u8: 1 = vertex deformed (owns one control_point_map entry), 0 = skipped
+ *                (mesh_deformation.h:184-186) */
+int pgmo_deform_points(pgmo_deform_t* h, uint64_t n_v, const float* x, const float* y,
+                       const float* z, const uint64_t* stamps_ns, const uint64_t* subset_idx,
+                       uint64_t n_subset, uint32_t k, double tol_t, int precision, float* out_x,
+                       float* out_y, float* out_z, double* out_xyz_f64, uint32_t* assoc,
+                       uint32_t assoc_stride, uint8_t* assoc_cnt, uint8_t* processed);
+
+/* --- device-resident / sharded path (what bench.py and a multi-GPU caller drive) ---------
+ * 1. every rank: pgmo_deform_stamp_stretches_device over its slab of the stamp stream
+ * 2. ranks exchange the stretch lists (a few KB) and concatenate them in rank order
+ * 3. every rank: pgmo_deform_build_schedule over the global list (identical on all ranks)
+ * 4. every rank: pgmo_deform_run_device on its slab [first_position, first_position + n_local)
+ */
+
+/* Maximal stretches of equal stamps, in order.  Writes up to `capacity` (stamp, length) pairs
+ * to host arrays and the total count to *n_stretches (may exceed capacity: call again). */
+int pgmo_deform_stamp_stretches_device(pgmo_deform_t* h, uint64_t n_local,
+                                       const uint64_t* d_stamps_ns, uint64_t capacity,
+                                       uint64_t* stretch_stamp, uint64_t* stretch_len,
+                                       uint64_t* n_stretches, void* stream);
+
+/* Replays the reference's add/remove window state machine (mesh_deformation.h:159-212) over the
+ * stamp stretches and uploads the resulting schedule.  stretch_stamp == NULL selects the
+ * unstamped overload for `total_positions` vertices.  Returns PGMO_NOOP for the reference's
+ * early returns (:78-80, :83-86, :96-99, :143-152). */
+int pgmo_deform_build_schedule(pgmo_deform_t* h, uint64_t n_stretches,
+                               const uint64_t* stretch_stamp, const uint64_t* stretch_len,
+                               uint64_t total_positions, uint32_t k, double tol_t);
+
+/* Deforms positions [first_position, first_position + n_local).  All vertex arrays are local
+ * to the slab (element 0 = position first_position); d_subset_idx (optional) holds local
+ * vertex indices.  Optional outputs as in pgmo_deform_points (d_assoc/d_assoc_cnt/d_processed/
+ * d_out_xyz_f64 may be NULL).  *n_resolved (optional, host) receives the number of vertices
+ * that went through the exact tie-order resolver; requesting it synchronises the stream. */
+int pgmo_deform_run_device(pgmo_deform_t* h, uint64_t first_position, uint64_t n_local,
+                           const float* d_x, const float* d_y, const float* d_z,
+                           const uint64_t* d_subset_idx, int precision, float* d_out_x,
+                           float* d_out_y, float* d_out_z, double* d_out_xyz_f64,
+                           uint32_t* d_assoc, uint32_t assoc_stride, uint8_t* d_assoc_cnt,
+                           uint8_t* d_processed, uint64_t* n_resolved, void* stream);
+
+/* Schedule introspection (tests / diagnostics): number of runs, and per run
+ * [first_position, lo, hi, k, skip] as u64 x 5. */
+int pgmo_deform_schedule_info(pgmo_deform_t* h, uint64_t* n_runs, uint64_t capacity,
+                              uint64_t* runs5);
+
+/* DeformationGraph::predeformPoints (deformation_graph.h:779-806): for i >= start_idx with
+ * graph_indices[i] >= 0 and a valid pose: out[i] = float(R * (double(v_i) - g) + t); every other
+ * i >= start_idx is appended to to_deform (ascending).  Host buffers.
+ * Returns PGMO_ERR_OUT_OF_RANGE if a valid pose index is >= n_c (vertex_positions_.at()). */
+int pgmo_deform_predeform(pgmo_deform_t* h, uint64_t n_v, const float* x, const float* y,
+                          const float* z, const int32_t* graph_indices, uint64_t start_idx,
+                          float* out_x, float* out_y, float* out_z, uint64_t* to_deform,
+                          uint64_t* n_to_deform);
+
+/* ------------------------------------------------------------------------------------------
+ * VoxelClearingCompression: one handle per compressor object.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct pgmo_vcc pgmo_vcc_t;
+
+int pgmo_vcc_create(double resolution, int device, pgmo_vcc_t** out);
+void pgmo_vcc_destroy(pgmo_vcc_t* h);
+
+/* compressAndIntegrate (voxel_clearing_compression.cpp:34-47).  The MeshInterface is passed
+ * flattened in blockIndices() order: block b = vertices [block_offsets[b], block_offsets[b+1]),
+ * 3 consecutive vertices = 1 face.
+ *   block_idx_xyz  n_blocks x 3 i32
+ *   xyz            N x 3 f32 (x,y,z interleaved), rgba N u32 (pcl::PointXYZRGBA::rgba)
+ *   remap_out      N u64: remapping[block][local] for every input vertex (always overwritten,
+ *                  :154)
+ *   keys_out       optional N x 3 i64: the voxel keys round(p / resolution) (:134-136) */
+int pgmo_vcc_integrate(pgmo_vcc_t* h, uint32_t n_blocks, const int32_t* block_idx_xyz,
+                       const uint64_t* block_offsets, const float* xyz, const uint32_t* rgba,
+                       double stamp_s, uint64_t* remap_out, int64_t* keys_out);
+/* pruneStoredMesh (:57-66) and clearArchivedBlocks (:68-70) */
+int pgmo_vcc_prune(pgmo_vcc_t* h, double earliest_s);
+int pgmo_vcc_clear_blocks(pgmo_vcc_t* h, uint32_t n_blocks, const int32_t* block_idx_xyz);
+/* sizes4 = [num_vertices, num_polygons, num_active, num_invalid] */
+int pgmo_vcc_sizes(pgmo_vcc_t* h, uint64_t* sizes4);
+/* getVertices / getTimestamps / getStoredPolygons / getActiveVerticesIndex / getInvalidIndices;
+ * any pointer may be NULL.  polygons: num_polygons x 3 u32.  invalid is returned ascending
+ * (the reference's order follows unordered_set iteration and is not pinned). */
+int pgmo_vcc_snapshot(pgmo_vcc_t* h, float* vertices_xyz, uint32_t* vertices_rgba,
+                      uint64_t* stamps_ns, uint32_t* polygons, uint64_t* active,
+                      uint64_t* invalid);
+
+/* Device-resident integrate for throughput measurement: inputs already in HBM, remap written to
+ * HBM, stream-ordered, no host synchronisation.  Single-block or multi-block as above;
+ * block_offsets / block_idx_xyz stay host arrays (they are tiny). */
+int pgmo_vcc_integrate_device(pgmo_vcc_t* h, uint32_t n_blocks, const int32_t* block_idx_xyz,
+                              const uint64_t* block_offsets, const float* d_xyz,
+                              const uint32_t* d_rgba, double stamp_s, uint64_t* d_remap_out,
+                              void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * OctreeCompression (MeshCompression base flow + PCL-octree uniqueness tests).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct pgmo_oct pgmo_oct_t;
+
+int pgmo_oct_create(double resolution, int device, pgmo_oct_t** out);
+void pgmo_oct_destroy(pgmo_oct_t* h);
+
+/* MeshCompression::compressAndIntegrate (mesh_compression.cpp:216-417).  Inputs as for
+ * pgmo_vcc_integrate.  remap_index/remap_kind: dense record of what the reference does to the
+ * caller's persistent `remapping` for each input vertex: kind 0 = no write, 1 = overwrite
+ * (remapping.at(block)[i] = index, :288), 2 = insert-if-absent (:366-372).  The lists
+ * new_indices / new_vertices / new_triangles are fetched with pgmo_oct_last_outputs. */
+int pgmo_oct_integrate(pgmo_oct_t* h, uint32_t n_blocks, const int32_t* block_idx_xyz,
+                       const uint64_t* block_offsets, const float* xyz, const uint32_t* rgba,
+                       double stamp_s, int64_t* remap_index, uint8_t* remap_kind);
+int pgmo_oct_prune(pgmo_oct_t* h, double earliest_s);
+/* sizes8 = [num_vertices, num_polygons, num_active, 0, num_new_vertices, num_new_triangles,
+ *           num_new_indices, num_active] */
+int pgmo_oct_sizes(pgmo_oct_t* h, uint64_t* sizes8);
+int pgmo_oct_snapshot(pgmo_oct_t* h, float* vertices_xyz, uint32_t* vertices_rgba,
+                      uint64_t* stamps_ns, uint32_t* polygons, uint64_t* active_index,
+                      float* active_xyz, double* active_stamps_s);
+int pgmo_oct_last_outputs(pgmo_oct_t* h, float* new_vertices_xyz, uint32_t* new_vertices_rgba,
+                          uint32_t* new_triangles, uint64_t* new_indices);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PGMO_B200_H_ */

@@ -1,0 +1,380 @@
+"""ctypes binding of libpgmo_b200.so (include/pgmo_b200.h).
+
+Test / bench plumbing only: the product's host side is the C++ shim under
+include/kimera_pgmo_b200/.  Everything here goes through the C ABI; there is no Python or CPU
+implementation behind it, and loading fails loudly when the CUDA library has not been built.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libpgmo_b200.so")
+
+PGMO_OK = 0
+PGMO_NOOP = 1
+PGMO_ERR_INVALID = -1
+PGMO_ERR_CUDA = -2
+PGMO_ERR_NO_DEVICE = -3
+PGMO_ERR_UNSUPPORTED = -4
+PGMO_ERR_OUT_OF_RANGE = -5
+FP64 = 0
+FP32 = 1
+
+_u64p = C.POINTER(C.c_uint64)
+_i64p = C.POINTER(C.c_int64)
+_u32p = C.POINTER(C.c_uint32)
+_i32p = C.POINTER(C.c_int32)
+_u8p = C.POINTER(C.c_uint8)
+_f32p = C.POINTER(C.c_float)
+_f64p = C.POINTER(C.c_double)
+_vp = C.c_void_p
+
+# name -> (restype, argtypes); kept in one table so tests can check it against the header
+SIGNATURES = {
+    "pgmo_last_error": (C.c_char_p, []),
+    "pgmo_version": (C.c_char_p, []),
+    "pgmo_device_count": (C.c_int, []),
+    "pgmo_stamp_from_sec": (C.c_uint64, [C.c_double]),
+    "pgmo_deform_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
+    "pgmo_deform_destroy": (None, [_vp]),
+    "pgmo_deform_set_controls": (C.c_int, [_vp, C.c_uint64, _vp, _vp, _vp, _vp]),
+    "pgmo_deform_set_controls_device": (C.c_int, [_vp, C.c_uint64, _vp, _vp, _vp, _vp, _vp]),
+    "pgmo_deform_update_poses": (C.c_int, [_vp, _vp]),
+    "pgmo_deform_update_poses_device": (C.c_int, [_vp, _vp, _vp]),
+    "pgmo_deform_set_profiling": (C.c_int, [_vp, C.c_int]),
+    "pgmo_deform_last_timings": (C.c_int, [_vp, _vp, _u64p]),
+    "pgmo_deform_points": (C.c_int, [_vp, C.c_uint64, _vp, _vp, _vp, _vp, _vp, C.c_uint64,
+                                     C.c_uint32, C.c_double, C.c_int, _vp, _vp, _vp, _vp, _vp,
+                                     C.c_uint32, _vp, _vp]),
+    "pgmo_deform_stamp_stretches_device": (C.c_int, [_vp, C.c_uint64, _vp, C.c_uint64, _vp, _vp,
+                                                     _u64p, _vp]),
+    "pgmo_deform_build_schedule": (C.c_int, [_vp, C.c_uint64, _vp, _vp, C.c_uint64, C.c_uint32,
+                                             C.c_double]),
+    "pgmo_deform_run_device": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _vp, _vp, _vp, _vp, C.c_int,
+                                         _vp, _vp, _vp, _vp, _vp, C.c_uint32, _vp, _vp, _vp, _vp]),
+    "pgmo_deform_schedule_info": (C.c_int, [_vp, _u64p, C.c_uint64, _vp]),
+    "pgmo_deform_predeform": (C.c_int, [_vp, C.c_uint64, _vp, _vp, _vp, _vp, C.c_uint64, _vp, _vp,
+                                        _vp, _vp, _u64p]),
+    "pgmo_vcc_create": (C.c_int, [C.c_double, C.c_int, C.POINTER(_vp)]),
+    "pgmo_vcc_destroy": (None, [_vp]),
+    "pgmo_vcc_integrate": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, C.c_double, _vp, _vp]),
+    "pgmo_vcc_prune": (C.c_int, [_vp, C.c_double]),
+    "pgmo_vcc_clear_blocks": (C.c_int, [_vp, C.c_uint32, _vp]),
+    "pgmo_vcc_sizes": (C.c_int, [_vp, _vp]),
+    "pgmo_vcc_snapshot": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pgmo_vcc_integrate_device": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, C.c_double, _vp,
+                                            _vp]),
+    "pgmo_oct_create": (C.c_int, [C.c_double, C.c_int, C.POINTER(_vp)]),
+    "pgmo_oct_destroy": (None, [_vp]),
+    "pgmo_oct_integrate": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, C.c_double, _vp, _vp]),
+    "pgmo_oct_prune": (C.c_int, [_vp, C.c_double]),
+    "pgmo_oct_sizes": (C.c_int, [_vp, _vp]),
+    "pgmo_oct_snapshot": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pgmo_oct_last_outputs": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+}
+
+_lib = None
+
+
+class PgmoError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"pgmo_b200 error {code}: {message}")
+        self.code = code
+
+
+def load():
+    """Loads libpgmo_b200.so; raises if it has not been built (no fallback of any kind)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; "
+            "g.build()'` (nvcc, sm_100a).  There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _check(rc):
+    if rc < 0:
+        raise PgmoError(rc, load().pgmo_last_error().decode())
+    return rc
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"], "array must be contiguous"
+        return a.ctypes.data_as(_vp)
+    if isinstance(a, int):
+        return _vp(a)
+    if hasattr(a, "data_ptr"):  # torch tensor
+        return _vp(a.data_ptr())
+    raise TypeError(type(a))
+
+
+def stamp_from_sec(sec: float) -> int:
+    return int(load().pgmo_stamp_from_sec(float(sec)))
+
+
+class DeformHandle:
+    """pgmo_deform_t: deformation::deformPoints for one control table (one prefix)."""
+
+    def __init__(self, device: int = 0):
+        self._lib = load()
+        h = _vp()
+        _check(self._lib.pgmo_deform_create(device, C.byref(h)))
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.pgmo_deform_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def set_controls(self, pos_xyz, stamps_ns, valid, poses12):
+        pos = np.ascontiguousarray(pos_xyz, dtype=np.float64).reshape(-1, 3)
+        n_c = pos.shape[0]
+        st = None if stamps_ns is None else np.ascontiguousarray(stamps_ns, dtype=np.uint64)
+        va = None if valid is None else np.ascontiguousarray(valid, dtype=np.uint8)
+        po = None if poses12 is None else np.ascontiguousarray(poses12, dtype=np.float64).reshape(-1, 12)
+        _check(self._lib.pgmo_deform_set_controls(self._h, n_c, _ptr(pos), _ptr(st), _ptr(va), _ptr(po)))
+
+    def set_controls_device(self, n_c, d_pos, d_stamps, d_valid, d_poses, stream=0):
+        _check(self._lib.pgmo_deform_set_controls_device(
+            self._h, n_c, _ptr(d_pos), _ptr(d_stamps), _ptr(d_valid), _ptr(d_poses), _vp(stream)))
+
+    def update_poses(self, poses12):
+        po = np.ascontiguousarray(poses12, dtype=np.float64).reshape(-1, 12)
+        _check(self._lib.pgmo_deform_update_poses(self._h, _ptr(po)))
+
+    def update_poses_device(self, d_poses, stream=0):
+        _check(self._lib.pgmo_deform_update_poses_device(self._h, _ptr(d_poses), _vp(stream)))
+
+    def set_profiling(self, enabled=True):
+        _check(self._lib.pgmo_deform_set_profiling(self._h, 1 if enabled else 0))
+
+    def last_timings(self):
+        """(knn_blend_ms, resolver_ms, schedule_builds) of the last run_device."""
+        ms = np.zeros(2, dtype=np.float32)
+        builds = C.c_uint64(0)
+        _check(self._lib.pgmo_deform_last_timings(self._h, _ptr(ms), C.byref(builds)))
+        return float(ms[0]), float(ms[1]), int(builds.value)
+
+    def deform_points(self, x, y, z, stamps_ns, k=4, tol_t=10.0, precision=FP64, subset=None,
+                      out=None, want_f64=False, want_assoc=False, assoc_stride=8):
+        """Host-buffer call.  Returns dict(rc, x, y, z, f64, assoc, assoc_cnt, processed)."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        y = np.ascontiguousarray(y, dtype=np.float32)
+        z = np.ascontiguousarray(z, dtype=np.float32)
+        n_v = x.shape[0]
+        st = None if stamps_ns is None else np.ascontiguousarray(stamps_ns, dtype=np.uint64)
+        sub = None if subset is None else np.ascontiguousarray(subset, dtype=np.uint64)
+        n_pos = n_v if sub is None else sub.shape[0]
+        if out is None:
+            ox, oy, oz = x.copy(), y.copy(), z.copy()
+        else:
+            ox, oy, oz = out
+        f64 = np.full((n_pos, 3), np.nan, dtype=np.float64) if want_f64 else None
+        assoc = np.full((n_pos, assoc_stride), 0xFFFFFFFF, dtype=np.uint32) if want_assoc else None
+        cnt = np.zeros(n_pos, dtype=np.uint8) if want_assoc else None
+        processed = np.zeros(n_pos, dtype=np.uint8)
+        rc = _check(self._lib.pgmo_deform_points(
+            self._h, n_v, _ptr(x), _ptr(y), _ptr(z), _ptr(st), _ptr(sub),
+            0 if sub is None else sub.shape[0], k, float(tol_t), precision, _ptr(ox), _ptr(oy),
+            _ptr(oz), _ptr(f64), _ptr(assoc), assoc_stride, _ptr(cnt), _ptr(processed)))
+        return dict(rc=rc, x=ox, y=oy, z=oz, f64=f64, assoc=assoc, assoc_cnt=cnt,
+                    processed=processed)
+
+    # --- device-resident path -------------------------------------------------------------
+    def stamp_stretches_device(self, d_stamps, n_local, stream=0):
+        n = C.c_uint64(0)
+        cap = 1 << 16
+        while True:
+            stamps = np.zeros(cap, dtype=np.uint64)
+            lens = np.zeros(cap, dtype=np.uint64)
+            _check(self._lib.pgmo_deform_stamp_stretches_device(
+                self._h, n_local, _ptr(d_stamps), cap, _ptr(stamps), _ptr(lens), C.byref(n),
+                _vp(stream)))
+            if n.value <= cap:
+                return stamps[: n.value].copy(), lens[: n.value].copy()
+            cap = int(n.value)
+
+    def build_schedule(self, stretch_stamp, stretch_len, total_positions, k, tol_t):
+        if stretch_stamp is None:
+            return _check(self._lib.pgmo_deform_build_schedule(
+                self._h, 0, None, None, total_positions, k, float(tol_t)))
+        ss = np.ascontiguousarray(stretch_stamp, dtype=np.uint64)
+        sl = np.ascontiguousarray(stretch_len, dtype=np.uint64)
+        return _check(self._lib.pgmo_deform_build_schedule(
+            self._h, ss.shape[0], _ptr(ss), _ptr(sl), total_positions, k, float(tol_t)))
+
+    def schedule_info(self):
+        n = C.c_uint64(0)
+        _check(self._lib.pgmo_deform_schedule_info(self._h, C.byref(n), 0, None))
+        runs = np.zeros((max(int(n.value), 1), 5), dtype=np.uint64)
+        _check(self._lib.pgmo_deform_schedule_info(self._h, C.byref(n), runs.shape[0], _ptr(runs)))
+        return runs[: n.value]
+
+    def run_device(self, first_position, n_local, d_x, d_y, d_z, d_ox, d_oy, d_oz,
+                   precision=FP64, d_subset=None, d_f64=None, d_assoc=None, assoc_stride=0,
+                   d_assoc_cnt=None, d_processed=None, want_resolved=False, stream=0):
+        resolved = C.c_uint64(0)
+        _check(self._lib.pgmo_deform_run_device(
+            self._h, first_position, n_local, _ptr(d_x), _ptr(d_y), _ptr(d_z), _ptr(d_subset),
+            precision, _ptr(d_ox), _ptr(d_oy), _ptr(d_oz), _ptr(d_f64), _ptr(d_assoc),
+            assoc_stride, _ptr(d_assoc_cnt), _ptr(d_processed),
+            C.cast(C.byref(resolved), _vp) if want_resolved else None, _vp(stream)))
+        return int(resolved.value)
+
+    def predeform(self, x, y, z, graph_indices, start_idx, out):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        y = np.ascontiguousarray(y, dtype=np.float32)
+        z = np.ascontiguousarray(z, dtype=np.float32)
+        gi = np.ascontiguousarray(graph_indices, dtype=np.int32)
+        n_v = x.shape[0]
+        to_deform = np.zeros(max(n_v - start_idx, 1), dtype=np.uint64)
+        n_to = C.c_uint64(0)
+        ox, oy, oz = out
+        _check(self._lib.pgmo_deform_predeform(self._h, n_v, _ptr(x), _ptr(y), _ptr(z), _ptr(gi),
+                                               start_idx, _ptr(ox), _ptr(oy), _ptr(oz),
+                                               _ptr(to_deform), C.byref(n_to)))
+        return to_deform[: n_to.value].copy()
+
+
+def _flatten_blocks(block_idx, offsets, xyz, rgba):
+    bi = np.ascontiguousarray(block_idx, dtype=np.int32).reshape(-1, 3)
+    off = np.ascontiguousarray(offsets, dtype=np.uint64)
+    pts = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+    col = None if rgba is None else np.ascontiguousarray(rgba, dtype=np.uint32)
+    assert off.shape[0] == bi.shape[0] + 1 and int(off[-1]) == pts.shape[0]
+    return bi, off, pts, col
+
+
+class VccHandle:
+    """pgmo_vcc_t: VoxelClearingCompression."""
+
+    def __init__(self, resolution: float, device: int = 0):
+        self._lib = load()
+        h = _vp()
+        _check(self._lib.pgmo_vcc_create(float(resolution), device, C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.pgmo_vcc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def integrate(self, block_idx, offsets, xyz, rgba, stamp_s, want_keys=False):
+        bi, off, pts, col = _flatten_blocks(block_idx, offsets, xyz, rgba)
+        n = pts.shape[0]
+        remap = np.zeros(n, dtype=np.uint64)
+        keys = np.zeros((n, 3), dtype=np.int64) if want_keys else None
+        _check(self._lib.pgmo_vcc_integrate(self._h, bi.shape[0], _ptr(bi), _ptr(off), _ptr(pts),
+                                            _ptr(col), float(stamp_s), _ptr(remap), _ptr(keys)))
+        return remap, keys
+
+    def integrate_device(self, block_idx, offsets, d_xyz, d_rgba, stamp_s, d_remap, stream=0):
+        bi = np.ascontiguousarray(block_idx, dtype=np.int32).reshape(-1, 3)
+        off = np.ascontiguousarray(offsets, dtype=np.uint64)
+        _check(self._lib.pgmo_vcc_integrate_device(self._h, bi.shape[0], _ptr(bi), _ptr(off),
+                                                   _ptr(d_xyz), _ptr(d_rgba), float(stamp_s),
+                                                   _ptr(d_remap), _vp(stream)))
+
+    def prune(self, earliest_s):
+        _check(self._lib.pgmo_vcc_prune(self._h, float(earliest_s)))
+
+    def clear_blocks(self, block_idx):
+        bi = np.ascontiguousarray(block_idx, dtype=np.int32).reshape(-1, 3)
+        _check(self._lib.pgmo_vcc_clear_blocks(self._h, bi.shape[0], _ptr(bi)))
+
+    def sizes(self):
+        s = np.zeros(4, dtype=np.uint64)
+        _check(self._lib.pgmo_vcc_sizes(self._h, _ptr(s)))
+        return [int(v) for v in s]
+
+    def snapshot(self):
+        nv, npoly, nact, ninv = self.sizes()
+        out = dict(
+            vertices=np.zeros((nv, 3), dtype=np.float32), rgba=np.zeros(nv, dtype=np.uint32),
+            stamps=np.zeros(nv, dtype=np.uint64), polygons=np.zeros((npoly, 3), dtype=np.uint32),
+            active=np.zeros(nact, dtype=np.uint64), invalid=np.zeros(ninv, dtype=np.uint64))
+        _check(self._lib.pgmo_vcc_snapshot(self._h, _ptr(out["vertices"]), _ptr(out["rgba"]),
+                                           _ptr(out["stamps"]), _ptr(out["polygons"]),
+                                           _ptr(out["active"]), _ptr(out["invalid"])))
+        return out
+
+
+class OctHandle:
+    """pgmo_oct_t: OctreeCompression."""
+
+    def __init__(self, resolution: float, device: int = 0):
+        self._lib = load()
+        h = _vp()
+        _check(self._lib.pgmo_oct_create(float(resolution), device, C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.pgmo_oct_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def integrate(self, block_idx, offsets, xyz, rgba, stamp_s):
+        bi, off, pts, col = _flatten_blocks(block_idx, offsets, xyz, rgba)
+        n = pts.shape[0]
+        idx = np.full(n, -1, dtype=np.int64)
+        kind = np.zeros(n, dtype=np.uint8)
+        _check(self._lib.pgmo_oct_integrate(self._h, bi.shape[0], _ptr(bi), _ptr(off), _ptr(pts),
+                                            _ptr(col), float(stamp_s), _ptr(idx), _ptr(kind)))
+        return idx, kind
+
+    def prune(self, earliest_s):
+        _check(self._lib.pgmo_oct_prune(self._h, float(earliest_s)))
+
+    def sizes(self):
+        s = np.zeros(8, dtype=np.uint64)
+        _check(self._lib.pgmo_oct_sizes(self._h, _ptr(s)))
+        return [int(v) for v in s]
+
+    def snapshot(self):
+        s = self.sizes()
+        out = dict(
+            vertices=np.zeros((s[0], 3), dtype=np.float32), rgba=np.zeros(s[0], dtype=np.uint32),
+            stamps=np.zeros(s[0], dtype=np.uint64), polygons=np.zeros((s[1], 3), dtype=np.uint32),
+            active=np.zeros(s[2], dtype=np.uint64), active_xyz=np.zeros((s[2], 3), dtype=np.float32),
+            active_stamps=np.zeros(s[2], dtype=np.float64))
+        _check(self._lib.pgmo_oct_snapshot(self._h, _ptr(out["vertices"]), _ptr(out["rgba"]),
+                                           _ptr(out["stamps"]), _ptr(out["polygons"]),
+                                           _ptr(out["active"]), _ptr(out["active_xyz"]),
+                                           _ptr(out["active_stamps"])))
+        return out
+
+    def last_outputs(self):
+        s = self.sizes()
+        out = dict(new_vertices=np.zeros((s[4], 3), dtype=np.float32),
+                   new_rgba=np.zeros(s[4], dtype=np.uint32),
+                   new_triangles=np.zeros((s[5], 3), dtype=np.uint32),
+                   new_indices=np.zeros(s[6], dtype=np.uint64))
+        _check(self._lib.pgmo_oct_last_outputs(self._h, _ptr(out["new_vertices"]),
+                                               _ptr(out["new_rgba"]), _ptr(out["new_triangles"]),
+                                               _ptr(out["new_indices"])))
+        return out

@@ -1,0 +1,102 @@
+// Shared plumbing for libpgmo_b200: error reporting, device buffers, launch helpers.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "pgmo_b200.h"
+
+namespace pgmo {
+
+void setLastError(const char* fmt, ...);
+const char* lastError();
+
+// Selects the device and verifies that a kernel image for it exists (sm_100a only).
+int ensureDevice(int device);
+
+#define PGMO_CUDA(expr)                                                                   \
+  do {                                                                                    \
+    cudaError_t err__ = (expr);                                                           \
+    if (err__ != cudaSuccess) {                                                           \
+      ::pgmo::setLastError("%s:%d %s -> %s", __FILE__, __LINE__, #expr,                   \
+                           cudaGetErrorString(err__));                                    \
+      return PGMO_ERR_CUDA;                                                               \
+    }                                                                                     \
+  } while (0)
+
+#define PGMO_CHECK_ARG(cond)                                                              \
+  do {                                                                                    \
+    if (!(cond)) {                                                                        \
+      ::pgmo::setLastError("%s:%d invalid argument: %s", __FILE__, __LINE__, #cond);       \
+      return PGMO_ERR_INVALID;                                                            \
+    }                                                                                     \
+  } while (0)
+
+#define PGMO_TRY(expr)                   \
+  do {                                   \
+    const int rc__ = (expr);             \
+    if (rc__ < 0) return rc__;           \
+  } while (0)
+
+// Grow-only device buffer (never shrinks: handles are long-lived and re-used per message).
+template <typename T>
+struct DevBuf {
+  T* ptr = nullptr;
+  size_t cap = 0;
+  ~DevBuf() { release(); }
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  void release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+  }
+  // keep == true preserves the first `keep_n` elements across a growth
+  int reserve(size_t n, cudaStream_t stream = nullptr, size_t keep_n = 0) {
+    if (n <= cap) return PGMO_OK;
+    size_t new_cap = cap ? cap : 256;
+    while (new_cap < n) new_cap += new_cap / 2 + 256;
+    T* fresh = nullptr;
+    PGMO_CUDA(cudaMalloc(&fresh, new_cap * sizeof(T)));
+    if (ptr && keep_n) {
+      PGMO_CUDA(cudaMemcpyAsync(fresh, ptr, keep_n * sizeof(T), cudaMemcpyDeviceToDevice, stream));
+      PGMO_CUDA(cudaStreamSynchronize(stream));
+    }
+    if (ptr) cudaFree(ptr);
+    ptr = fresh;
+    cap = new_cap;
+    return PGMO_OK;
+  }
+};
+
+// Pinned host staging buffer.
+template <typename T>
+struct PinnedBuf {
+  T* ptr = nullptr;
+  size_t cap = 0;
+  ~PinnedBuf() {
+    if (ptr) cudaFreeHost(ptr);
+  }
+  PinnedBuf() = default;
+  PinnedBuf(const PinnedBuf&) = delete;
+  PinnedBuf& operator=(const PinnedBuf&) = delete;
+  int reserve(size_t n) {
+    if (n <= cap) return PGMO_OK;
+    if (ptr) cudaFreeHost(ptr);
+    ptr = nullptr;
+    cap = 0;
+    size_t new_cap = n + n / 4 + 64;
+    PGMO_CUDA(cudaMallocHost(&ptr, new_cap * sizeof(T)));
+    cap = new_cap;
+    return PGMO_OK;
+  }
+};
+
+inline unsigned divUp(uint64_t a, uint64_t b) { return static_cast<unsigned>((a + b - 1) / b); }
+
+}  // namespace pgmo

@@ -1,0 +1,691 @@
+// C ABI of the deformation path (see include/pgmo_b200.h).
+#include <algorithm>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+#include "deform_kernels.cuh"
+#include "deform_schedule.h"
+
+using namespace pgmo;
+
+struct pgmo_deform {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+
+  // control table
+  uint64_t n_c = 0;
+  bool has_stamps = false;
+  bool has_valid = false;
+  bool has_poses = false;
+  std::vector<double> h_pos;
+  std::vector<uint64_t> h_stamps;
+  std::vector<uint8_t> h_valid;
+  DevBuf<double> d_pos, d_poses;
+  DevBuf<uint8_t> d_valid;
+  DevBuf<float4> d_ctrl_f4;
+  DevBuf<float> d_pose_f32;
+  DevBuf<int4> d_ctrl_key;
+  DevBuf<int32_t> d_del_run, d_stable_key;
+
+  // schedule (cached: it depends on control position / stamp / validity, on the vertex stamp
+  // stretches, k and tol_t — not on the poses — so a re-solve does not rebuild it)
+  Schedule sched;
+  bool sched_ready = false;
+  uint64_t control_version = 1;  // bumped when position / stamp / validity change
+  uint64_t sched_control_version = 0;
+  std::vector<uint64_t> sched_stretch_stamp, sched_stretch_len;
+  uint64_t sched_total = 0;
+  uint32_t sched_k = 0;
+  double sched_tol = 0.0;
+  bool sched_stamped = false;
+  uint64_t sched_builds = 0;
+  DevBuf<uint64_t> d_run_start;
+  DevBuf<uint4> d_run_info;
+  DevBuf<RunFrameDev> d_run_frame;
+
+  // optional kernel timing (bench / roofline): events on the launching stream
+  bool profiling = false;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool ev_recorded = false;
+
+  // work buffers
+  DevBuf<ulonglong2> d_bounds;
+  DevBuf<unsigned long long> d_counters;
+  DevBuf<uint8_t> d_status;
+  DevBuf<CandEntry> d_scratch;
+  PinnedBuf<unsigned long long> h_counters;
+  PinnedBuf<ulonglong2> h_bounds;
+
+  // staging for the host-buffer entry points
+  DevBuf<float> d_x, d_y, d_z, d_ox, d_oy, d_oz;
+  DevBuf<uint64_t> d_vstamps, d_subset;
+  DevBuf<double> d_of64;
+  DevBuf<uint32_t> d_assoc;
+  DevBuf<uint8_t> d_assoc_cnt;
+  DevBuf<int32_t> d_graph_idx;
+  DevBuf<uint8_t> d_needs;
+};
+
+namespace {
+
+cudaStream_t pick(pgmo_deform_t* h, void* stream) {
+  return stream ? static_cast<cudaStream_t>(stream) : h->stream;
+}
+
+int uploadSchedule(pgmo_deform_t* h, cudaStream_t st) {
+  const Schedule& s = h->sched;
+  const size_t n_runs = s.runs.size();
+  std::vector<uint64_t> run_start(n_runs + 1);
+  std::vector<uint4> run_info(n_runs);
+  std::vector<RunFrameDev> run_frame(n_runs);
+  for (size_t r = 0; r < n_runs; ++r) {
+    const ScheduleRun& run = s.runs[r];
+    run_start[r] = run.first_position;
+    run_info[r] = make_uint4(run.lo, run.hi, run.k, run.skip);
+    for (int a = 0; a < 3; ++a) {
+      run_frame[r].min_xyz[a] = run.min_xyz[a];
+      run_frame[r].shift[a] = run.shift[a];
+    }
+    run_frame[r].depth = run.depth;
+    if (!run.skip && run.depth > static_cast<uint32_t>(kResolverMaxDepth)) {
+      setLastError("control-point octree depth %u exceeds the supported %d", run.depth,
+                   kResolverMaxDepth);
+      return PGMO_ERR_UNSUPPORTED;
+    }
+  }
+  run_start[n_runs] = s.total_positions;
+  PGMO_TRY(h->d_run_start.reserve(n_runs + 1));
+  PGMO_TRY(h->d_run_info.reserve(n_runs + 1));
+  PGMO_TRY(h->d_run_frame.reserve(n_runs + 1));
+  PGMO_TRY(h->d_del_run.reserve(h->n_c + 1));
+  PGMO_TRY(h->d_stable_key.reserve(3 * h->n_c + 1));
+  PGMO_CUDA(cudaMemcpyAsync(h->d_run_start.ptr, run_start.data(), (n_runs + 1) * sizeof(uint64_t),
+                            cudaMemcpyHostToDevice, st));
+  PGMO_CUDA(cudaMemcpyAsync(h->d_run_info.ptr, run_info.data(), n_runs * sizeof(uint4),
+                            cudaMemcpyHostToDevice, st));
+  PGMO_CUDA(cudaMemcpyAsync(h->d_run_frame.ptr, run_frame.data(), n_runs * sizeof(RunFrameDev),
+                            cudaMemcpyHostToDevice, st));
+  PGMO_CUDA(cudaMemcpyAsync(h->d_del_run.ptr, s.del_run.data(), h->n_c * sizeof(int32_t),
+                            cudaMemcpyHostToDevice, st));
+  PGMO_CUDA(cudaMemcpyAsync(h->d_stable_key.ptr, s.stable_key.data(),
+                            3 * h->n_c * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  PGMO_CUDA(launchApplySchedule(h->n_c, h->d_del_run.ptr, h->d_stable_key.ptr, h->d_ctrl_f4.ptr,
+                                h->d_ctrl_key.ptr, st));
+  // the host vectors above die at scope exit: make sure the copies have been consumed
+  PGMO_CUDA(cudaStreamSynchronize(st));
+  return PGMO_OK;
+}
+
+// (Re)builds the derived device tables after d_pos / d_poses changed.
+int finishControls(pgmo_deform_t* h, bool positions_changed, cudaStream_t st) {
+  PGMO_TRY(h->d_ctrl_f4.reserve(h->n_c + 1));
+  PGMO_TRY(h->d_pose_f32.reserve(16 * h->n_c + 16));
+  PGMO_TRY(h->d_ctrl_key.reserve(h->n_c + 1));
+  PGMO_CUDA(launchBuildControlTables(h->n_c, h->d_pos.ptr, h->has_poses ? h->d_poses.ptr : nullptr,
+                                     h->d_ctrl_f4.ptr, h->d_pose_f32.ptr, positions_changed, st));
+  if (positions_changed) {
+    ++h->control_version;
+    h->sched_ready = false;
+  }
+  return PGMO_OK;
+}
+
+template <typename T>
+bool sameArray(const std::vector<T>& have, const T* fresh, uint64_t n) {
+  if (!fresh) return have.empty();
+  return have.size() == n && (n == 0 || std::memcmp(have.data(), fresh, n * sizeof(T)) == 0);
+}
+
+// K1 + host sort: stretches of equal stamps over positions [0, n_pos).
+int stampStretches(pgmo_deform_t* h, const uint64_t* d_stamps, const uint64_t* d_subset,
+                   uint64_t n_pos, std::vector<uint64_t>* s_stamp, std::vector<uint64_t>* s_len,
+                   cudaStream_t st) {
+  s_stamp->clear();
+  s_len->clear();
+  if (n_pos == 0) return PGMO_OK;
+  PGMO_TRY(h->d_counters.reserve(8));
+  PGMO_TRY(h->h_counters.reserve(8));
+  uint64_t cap = std::max<uint64_t>(h->d_bounds.cap, 1u << 16);
+  uint64_t found = 0;
+  while (true) {
+    PGMO_TRY(h->d_bounds.reserve(cap));
+    PGMO_CUDA(cudaMemsetAsync(h->d_counters.ptr, 0, 8 * sizeof(unsigned long long), st));
+    PGMO_CUDA(launchStampStretches(d_stamps, d_subset, n_pos, h->d_bounds.ptr, h->d_bounds.cap,
+                                   h->d_counters.ptr, st));
+    PGMO_CUDA(cudaMemcpyAsync(h->h_counters.ptr, h->d_counters.ptr, sizeof(unsigned long long),
+                              cudaMemcpyDeviceToHost, st));
+    PGMO_CUDA(cudaStreamSynchronize(st));
+    found = h->h_counters.ptr[0];
+    if (found <= h->d_bounds.cap) break;
+    cap = found;  // rare: more stretches than expected, run again with room for all
+  }
+  PGMO_TRY(h->h_bounds.reserve(found));
+  PGMO_CUDA(cudaMemcpyAsync(h->h_bounds.ptr, h->d_bounds.ptr, found * sizeof(ulonglong2),
+                            cudaMemcpyDeviceToHost, st));
+  PGMO_CUDA(cudaStreamSynchronize(st));
+  ulonglong2* b = h->h_bounds.ptr;
+  std::sort(b, b + found, [](const ulonglong2& l, const ulonglong2& r) { return l.x < r.x; });
+  s_stamp->resize(found);
+  s_len->resize(found);
+  for (uint64_t i = 0; i < found; ++i) {
+    (*s_stamp)[i] = b[i].y;
+    (*s_len)[i] = (i + 1 < found ? b[i + 1].x : n_pos) - b[i].x;
+  }
+  return PGMO_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pgmo_deform_create(int device, pgmo_deform_t** out) {
+  PGMO_CHECK_ARG(out != nullptr);
+  *out = nullptr;
+  PGMO_TRY(ensureDevice(device));
+  pgmo_deform_t* h = new (std::nothrow) pgmo_deform();
+  PGMO_CHECK_ARG(h != nullptr);
+  h->device = device;
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete h;
+    setLastError("cudaStreamCreateWithFlags failed");
+    return PGMO_ERR_CUDA;
+  }
+  for (auto& e : h->ev) {
+    if (cudaEventCreate(&e) != cudaSuccess) {
+      setLastError("cudaEventCreate failed");
+      pgmo_deform_destroy(h);
+      return PGMO_ERR_CUDA;
+    }
+  }
+  *out = h;
+  return PGMO_OK;
+}
+
+void pgmo_deform_destroy(pgmo_deform_t* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) {
+    cudaStreamSynchronize(h->stream);
+    cudaStreamDestroy(h->stream);
+  }
+  for (auto& e : h->ev) {
+    if (e) cudaEventDestroy(e);
+  }
+  delete h;
+}
+
+int pgmo_deform_set_controls(pgmo_deform_t* h, uint64_t n_c, const double* pos_xyz,
+                             const uint64_t* stamps_ns, const uint8_t* valid,
+                             const double* poses12) {
+  PGMO_CHECK_ARG(h != nullptr);
+  PGMO_CHECK_ARG(n_c == 0 || pos_xyz != nullptr);
+  PGMO_CHECK_ARG(n_c < 0x7FFFFFFFull);
+  PGMO_TRY(ensureDevice(h->device));
+  const bool changed = h->n_c != n_c || !sameArray(h->h_pos, pos_xyz, 3 * n_c) ||
+                       !sameArray(h->h_stamps, stamps_ns, n_c) ||
+                       !sameArray(h->h_valid, valid, n_c);
+  h->n_c = n_c;
+  h->has_stamps = stamps_ns != nullptr;
+  h->has_valid = valid != nullptr;
+  h->has_poses = poses12 != nullptr;
+  cudaStream_t st = h->stream;
+  PGMO_TRY(h->d_pos.reserve(3 * n_c + 3));
+  PGMO_TRY(h->d_poses.reserve(12 * n_c + 12));
+  PGMO_TRY(h->d_valid.reserve(n_c + 1));
+  if (changed) {
+    h->h_pos.assign(pos_xyz, pos_xyz + 3 * n_c);
+    if (stamps_ns) h->h_stamps.assign(stamps_ns, stamps_ns + n_c);
+    else h->h_stamps.clear();
+    if (valid) h->h_valid.assign(valid, valid + n_c);
+    else h->h_valid.clear();
+    PGMO_CUDA(cudaMemcpyAsync(h->d_pos.ptr, pos_xyz, 3 * n_c * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (valid) {
+      PGMO_CUDA(cudaMemcpyAsync(h->d_valid.ptr, valid, n_c, cudaMemcpyHostToDevice, st));
+    }
+  }
+  if (poses12) {
+    PGMO_CUDA(cudaMemcpyAsync(h->d_poses.ptr, poses12, 12 * n_c * sizeof(double), cudaMemcpyHostToDevice, st));
+  }
+  PGMO_TRY(finishControls(h, changed, st));
+  PGMO_CUDA(cudaStreamSynchronize(st));
+  return PGMO_OK;
+}
+
+int pgmo_deform_set_controls_device(pgmo_deform_t* h, uint64_t n_c, const double* d_pos_xyz,
+                                    const uint64_t* d_stamps_ns, const uint8_t* d_valid,
+                                    const double* d_poses12, void* stream) {
+  PGMO_CHECK_ARG(h != nullptr);
+  PGMO_CHECK_ARG(n_c == 0 || d_pos_xyz != nullptr);
+  PGMO_CHECK_ARG(n_c < 0x7FFFFFFFull);
+  PGMO_TRY(ensureDevice(h->device));
+  cudaStream_t st = pick(h, stream);
+  // the window schedule is host logic: it needs position / stamp / validity (33 B per control)
+  std::vector<double> pos(3 * n_c);
+  std::vector<uint64_t> stamps(d_stamps_ns ? n_c : 0);
+  std::vector<uint8_t> valid(d_valid ? n_c : 0);
+  PGMO_CUDA(cudaMemcpyAsync(pos.data(), d_pos_xyz, 3 * n_c * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (d_stamps_ns) {
+    PGMO_CUDA(cudaMemcpyAsync(stamps.data(), d_stamps_ns, n_c * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  }
+  if (d_valid) {
+    PGMO_CUDA(cudaMemcpyAsync(valid.data(), d_valid, n_c, cudaMemcpyDeviceToHost, st));
+  }
+  PGMO_CUDA(cudaStreamSynchronize(st));
+  const bool changed = h->n_c != n_c || h->h_pos != pos || h->h_stamps != stamps || h->h_valid != valid;
+  h->n_c = n_c;
+  h->has_stamps = d_stamps_ns != nullptr;
+  h->has_valid = d_valid != nullptr;
+  h->has_poses = d_poses12 != nullptr;
+  PGMO_TRY(h->d_pos.reserve(3 * n_c + 3));
+  PGMO_TRY(h->d_poses.reserve(12 * n_c + 12));
+  PGMO_TRY(h->d_valid.reserve(n_c + 1));
+  if (changed) {
+    h->h_pos.swap(pos);
+    h->h_stamps.swap(stamps);
+    h->h_valid.swap(valid);
+    PGMO_CUDA(cudaMemcpyAsync(h->d_pos.ptr, d_pos_xyz, 3 * n_c * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (d_valid) {
+      PGMO_CUDA(cudaMemcpyAsync(h->d_valid.ptr, d_valid, n_c, cudaMemcpyDeviceToDevice, st));
+    }
+  }
+  if (d_poses12) {
+    PGMO_CUDA(cudaMemcpyAsync(h->d_poses.ptr, d_poses12, 12 * n_c * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  }
+  PGMO_TRY(finishControls(h, changed, st));
+  return PGMO_OK;
+}
+
+int pgmo_deform_update_poses(pgmo_deform_t* h, const double* poses12) {
+  PGMO_CHECK_ARG(h != nullptr && poses12 != nullptr);
+  PGMO_TRY(ensureDevice(h->device));
+  cudaStream_t st = h->stream;
+  h->has_poses = true;
+  PGMO_TRY(h->d_poses.reserve(12 * h->n_c + 12));
+  PGMO_CUDA(cudaMemcpyAsync(h->d_poses.ptr, poses12, 12 * h->n_c * sizeof(double), cudaMemcpyHostToDevice, st));
+  PGMO_TRY(finishControls(h, false, st));
+  PGMO_CUDA(cudaStreamSynchronize(st));
+  return PGMO_OK;
+}
+
+int pgmo_deform_update_poses_device(pgmo_deform_t* h, const double* d_poses12, void* stream) {
+  PGMO_CHECK_ARG(h != nullptr && d_poses12 != nullptr);
+  PGMO_TRY(ensureDevice(h->device));
+  cudaStream_t st = pick(h, stream);
+  h->has_poses = true;
+  PGMO_TRY(h->d_poses.reserve(12 * h->n_c + 12));
+  PGMO_CUDA(cudaMemcpyAsync(h->d_poses.ptr, d_poses12, 12 * h->n_c * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  PGMO_TRY(finishControls(h, false, st));
+  return PGMO_OK;
+}
+
+int pgmo_deform_stamp_stretches_device(pgmo_deform_t* h, uint64_t n_local,
+                                       const uint64_t* d_stamps_ns, uint64_t capacity,
+                                       uint64_t* stretch_stamp, uint64_t* stretch_len,
+                                       uint64_t* n_stretches, void* stream) {
+  PGMO_CHECK_ARG(h != nullptr && n_stretches != nullptr);
+  PGMO_CHECK_ARG(n_local == 0 || d_stamps_ns != nullptr);
+  PGMO_TRY(ensureDevice(h->device));
+  cudaStream_t st = pick(h, stream);
+  *n_stretches = 0;
+  std::vector<uint64_t> s_stamp, s_len;
+  PGMO_TRY(stampStretches(h, d_stamps_ns, nullptr, n_local, &s_stamp, &s_len, st));
+  *n_stretches = s_stamp.size();
+  for (uint64_t i = 0; i < s_stamp.size() && i < capacity; ++i) {
+    if (stretch_stamp) stretch_stamp[i] = s_stamp[i];
+    if (stretch_len) stretch_len[i] = s_len[i];
+  }
+  return PGMO_OK;
+}
+
+int pgmo_deform_build_schedule(pgmo_deform_t* h, uint64_t n_stretches,
+                               const uint64_t* stretch_stamp, const uint64_t* stretch_len,
+                               uint64_t total_positions, uint32_t k, double tol_t) {
+  PGMO_CHECK_ARG(h != nullptr);
+  PGMO_TRY(ensureDevice(h->device));
+  const bool stamped = stretch_stamp != nullptr;
+  if (stamped) {
+    PGMO_CHECK_ARG(stretch_len != nullptr);
+    if (!h->has_stamps && h->n_c > 0) {
+      setLastError("stamped deformation needs control-point stamps (set_controls stamps_ns)");
+      return PGMO_ERR_INVALID;
+    }
+  }
+  // cache hit: same control table (position / stamp / validity), same stretches, k and tol_t
+  if (h->sched_ready && h->sched_control_version == h->control_version && h->sched_k == k &&
+      h->sched_tol == tol_t && h->sched_stamped == stamped &&
+      (stamped ? (sameArray(h->sched_stretch_stamp, stretch_stamp, n_stretches) &&
+                  sameArray(h->sched_stretch_len, stretch_len, n_stretches))
+               : h->sched_total == total_positions)) {
+    return PGMO_OK;
+  }
+  ControlTableHost ctrl;
+  ctrl.n = h->n_c;
+  ctrl.pos_xyz = h->h_pos.data();
+  ctrl.stamps = h->has_stamps ? h->h_stamps.data() : nullptr;
+  ctrl.valid = h->has_valid ? h->h_valid.data() : nullptr;
+  h->sched_ready = false;
+  if (stamped) {
+    buildStampedSchedule(ctrl, n_stretches, stretch_stamp, stretch_len, k, tol_t, 1.0, &h->sched);
+  } else {
+    buildUnstampedSchedule(ctrl, total_positions, k, 1.0, &h->sched);
+  }
+  ++h->sched_builds;
+  if (h->sched.noop) return PGMO_NOOP;
+  if (h->sched.degenerate) {
+    setLastError("a vertex would query an empty control-point tree (undefined in the reference)");
+    return PGMO_ERR_INVALID;
+  }
+  if (!h->has_poses) {
+    setLastError("set_controls was called without poses");
+    return PGMO_ERR_INVALID;
+  }
+  PGMO_TRY(uploadSchedule(h, h->stream));
+  h->sched_ready = true;
+  h->sched_control_version = h->control_version;
+  h->sched_k = k;
+  h->sched_tol = tol_t;
+  h->sched_stamped = stamped;
+  h->sched_total = h->sched.total_positions;
+  if (stamped) {
+    h->sched_stretch_stamp.assign(stretch_stamp, stretch_stamp + n_stretches);
+    h->sched_stretch_len.assign(stretch_len, stretch_len + n_stretches);
+  } else {
+    h->sched_stretch_stamp.clear();
+    h->sched_stretch_len.clear();
+  }
+  return PGMO_OK;
+}
+
+int pgmo_deform_schedule_info(pgmo_deform_t* h, uint64_t* n_runs, uint64_t capacity,
+                              uint64_t* runs5) {
+  PGMO_CHECK_ARG(h != nullptr && n_runs != nullptr);
+  *n_runs = h->sched.runs.size();
+  for (uint64_t r = 0; r < *n_runs && r < capacity && runs5; ++r) {
+    const ScheduleRun& run = h->sched.runs[r];
+    runs5[5 * r + 0] = run.first_position;
+    runs5[5 * r + 1] = run.lo;
+    runs5[5 * r + 2] = run.hi;
+    runs5[5 * r + 3] = run.k;
+    runs5[5 * r + 4] = run.skip;
+  }
+  return PGMO_OK;
+}
+
+int pgmo_deform_run_device(pgmo_deform_t* h, uint64_t first_position, uint64_t n_local,
+                           const float* d_x, const float* d_y, const float* d_z,
+                           const uint64_t* d_subset_idx, int precision, float* d_out_x,
+                           float* d_out_y, float* d_out_z, double* d_out_xyz_f64,
+                           uint32_t* d_assoc, uint32_t assoc_stride, uint8_t* d_assoc_cnt,
+                           uint8_t* d_processed, uint64_t* n_resolved, void* stream) {
+  PGMO_CHECK_ARG(h != nullptr);
+  PGMO_CHECK_ARG(precision == PGMO_PRECISION_FP64 || precision == PGMO_PRECISION_FP32);
+  PGMO_TRY(ensureDevice(h->device));
+  if (!h->sched_ready) {
+    setLastError("pgmo_deform_run_device: no schedule (call pgmo_deform_build_schedule)");
+    return PGMO_ERR_INVALID;
+  }
+  PGMO_CHECK_ARG(first_position + n_local <= h->sched.total_positions);
+  if (n_resolved) *n_resolved = 0;
+  if (n_local == 0) return PGMO_OK;
+  PGMO_CHECK_ARG(d_x && d_y && d_z && d_out_x && d_out_y && d_out_z);
+  PGMO_CHECK_ARG(d_assoc == nullptr || assoc_stride > 0);
+  cudaStream_t st = pick(h, stream);
+
+  uint8_t* status = d_processed;
+  if (!status) {
+    PGMO_TRY(h->d_status.reserve(n_local));
+    status = h->d_status.ptr;
+  }
+  PGMO_TRY(h->d_counters.reserve(8));
+  PGMO_CUDA(cudaMemsetAsync(h->d_counters.ptr, 0, 8 * sizeof(unsigned long long), st));
+
+  DeformArgs a;
+  a.first_position = first_position;
+  a.n_local = n_local;
+  a.x = d_x;
+  a.y = d_y;
+  a.z = d_z;
+  a.subset = d_subset_idx;
+  a.run_start = h->d_run_start.ptr;
+  a.n_runs = static_cast<uint32_t>(h->sched.runs.size());
+  a.run_info = h->d_run_info.ptr;
+  a.run_frame = h->d_run_frame.ptr;
+  a.ctrl_f4 = h->d_ctrl_f4.ptr;
+  a.ctrl_key = h->d_ctrl_key.ptr;
+  a.ctrl_pos = h->d_pos.ptr;
+  a.poses = h->d_poses.ptr;
+  a.ctrl_pose_f32 = h->d_pose_f32.ptr;
+  a.resolution = 1.0;  // SearchTree default resolution (mesh_deformation.h:24)
+  a.ox = d_out_x;
+  a.oy = d_out_y;
+  a.oz = d_out_z;
+  a.of64 = d_out_xyz_f64;
+  a.assoc = d_assoc;
+  a.assoc_stride = assoc_stride;
+  a.assoc_cnt = d_assoc_cnt;
+  a.status = status;
+  a.counters = h->d_counters.ptr;
+
+  ResolveArgs ra;
+  ra.n_warps = resolverResidentWarps(h->device);
+  ra.cand_cap = h->sched.max_k + 2 + h->sched.max_leaf_points + 1;
+  PGMO_TRY(h->d_scratch.reserve(static_cast<size_t>(ra.n_warps) * ra.cand_cap * 2));
+  ra.scratch = h->d_scratch.ptr;
+
+  if (h->profiling) PGMO_CUDA(cudaEventRecord(h->ev[0], st));
+  PGMO_CUDA(launchDeformKnnBlend(a, precision, h->sched.max_k, st));
+  if (h->profiling) PGMO_CUDA(cudaEventRecord(h->ev[1], st));
+  PGMO_CUDA(launchDeformResolve(a, ra, precision, st));
+  if (h->profiling) {
+    PGMO_CUDA(cudaEventRecord(h->ev[2], st));
+    h->ev_recorded = true;
+  }
+
+  if (n_resolved) {
+    PGMO_TRY(h->h_counters.reserve(8));
+    PGMO_CUDA(cudaMemcpyAsync(h->h_counters.ptr, h->d_counters.ptr, sizeof(unsigned long long),
+                              cudaMemcpyDeviceToHost, st));
+    PGMO_CUDA(cudaStreamSynchronize(st));
+    *n_resolved = h->h_counters.ptr[0];
+  }
+  return PGMO_OK;
+}
+
+int pgmo_deform_set_profiling(pgmo_deform_t* h, int enabled) {
+  PGMO_CHECK_ARG(h != nullptr);
+  h->profiling = enabled != 0;
+  h->ev_recorded = false;
+  return PGMO_OK;
+}
+
+int pgmo_deform_last_timings(pgmo_deform_t* h, float* ms2, uint64_t* schedule_builds) {
+  PGMO_CHECK_ARG(h != nullptr);
+  if (schedule_builds) *schedule_builds = h->sched_builds;
+  if (ms2) {
+    ms2[0] = ms2[1] = 0.f;
+    if (h->profiling && h->ev_recorded) {
+      PGMO_CUDA(cudaEventSynchronize(h->ev[2]));
+      PGMO_CUDA(cudaEventElapsedTime(&ms2[0], h->ev[0], h->ev[1]));
+      PGMO_CUDA(cudaEventElapsedTime(&ms2[1], h->ev[1], h->ev[2]));
+    }
+  }
+  return PGMO_OK;
+}
+
+int pgmo_deform_points(pgmo_deform_t* h, uint64_t n_v, const float* x, const float* y,
+                       const float* z, const uint64_t* stamps_ns, const uint64_t* subset_idx,
+                       uint64_t n_subset, uint32_t k, double tol_t, int precision, float* out_x,
+                       float* out_y, float* out_z, double* out_xyz_f64, uint32_t* assoc,
+                       uint32_t assoc_stride, uint8_t* assoc_cnt, uint8_t* processed) {
+  PGMO_CHECK_ARG(h != nullptr);
+  PGMO_TRY(ensureDevice(h->device));
+  const uint64_t n_pos = subset_idx ? n_subset : n_v;
+  // reference early returns before anything is touched
+  if (n_pos == 0) return PGMO_NOOP;
+  PGMO_CHECK_ARG(x && y && z && out_x && out_y && out_z);
+  if (subset_idx) {
+    for (uint64_t p = 0; p < n_subset; ++p) {
+      if (subset_idx[p] >= n_v) {
+        setLastError("indices[%llu] = %llu out of range", (unsigned long long)p,
+                     (unsigned long long)subset_idx[p]);
+        return PGMO_ERR_OUT_OF_RANGE;  // indices->at() / cloud .at()
+      }
+    }
+  }
+  cudaStream_t st = h->stream;
+  PGMO_TRY(h->d_x.reserve(n_v));
+  PGMO_TRY(h->d_y.reserve(n_v));
+  PGMO_TRY(h->d_z.reserve(n_v));
+  PGMO_TRY(h->d_ox.reserve(n_v));
+  PGMO_TRY(h->d_oy.reserve(n_v));
+  PGMO_TRY(h->d_oz.reserve(n_v));
+  const uint64_t* d_subset = nullptr;
+  if (subset_idx) {
+    PGMO_TRY(h->d_subset.reserve(n_subset));
+    PGMO_CUDA(cudaMemcpyAsync(h->d_subset.ptr, subset_idx, n_subset * sizeof(uint64_t),
+                              cudaMemcpyHostToDevice, st));
+    d_subset = h->d_subset.ptr;
+  }
+
+  int rc;
+  if (stamps_ns) {
+    // stamps first: K1 and the host-side schedule overlap with the x/y/z upload below
+    PGMO_TRY(h->d_vstamps.reserve(n_v));
+    PGMO_CUDA(cudaMemcpyAsync(h->d_vstamps.ptr, stamps_ns, n_v * sizeof(uint64_t),
+                              cudaMemcpyHostToDevice, st));
+    std::vector<uint64_t> s_stamp, s_len;
+    PGMO_TRY(stampStretches(h, h->d_vstamps.ptr, d_subset, n_pos, &s_stamp, &s_len, st));
+    PGMO_CUDA(cudaMemcpyAsync(h->d_x.ptr, x, n_v * sizeof(float), cudaMemcpyHostToDevice, st));
+    PGMO_CUDA(cudaMemcpyAsync(h->d_y.ptr, y, n_v * sizeof(float), cudaMemcpyHostToDevice, st));
+    PGMO_CUDA(cudaMemcpyAsync(h->d_z.ptr, z, n_v * sizeof(float), cudaMemcpyHostToDevice, st));
+    rc = pgmo_deform_build_schedule(h, s_stamp.size(), s_stamp.data(), s_len.data(), n_pos, k,
+                                    tol_t);
+  } else {
+    PGMO_CUDA(cudaMemcpyAsync(h->d_x.ptr, x, n_v * sizeof(float), cudaMemcpyHostToDevice, st));
+    PGMO_CUDA(cudaMemcpyAsync(h->d_y.ptr, y, n_v * sizeof(float), cudaMemcpyHostToDevice, st));
+    PGMO_CUDA(cudaMemcpyAsync(h->d_z.ptr, z, n_v * sizeof(float), cudaMemcpyHostToDevice, st));
+    rc = pgmo_deform_build_schedule(h, 0, nullptr, nullptr, n_pos, k, tol_t);
+  }
+  if (rc != PGMO_OK) {
+    cudaStreamSynchronize(st);
+    return rc;
+  }
+
+  double* d_f64 = nullptr;
+  uint32_t* d_assoc = nullptr;
+  uint8_t* d_cnt = nullptr;
+  if (out_xyz_f64) {
+    PGMO_TRY(h->d_of64.reserve(3 * n_pos));
+    d_f64 = h->d_of64.ptr;
+  }
+  if (assoc) {
+    PGMO_CHECK_ARG(assoc_stride > 0);
+    PGMO_TRY(h->d_assoc.reserve(n_pos * assoc_stride));
+    d_assoc = h->d_assoc.ptr;
+  }
+  if (assoc_cnt) {
+    PGMO_TRY(h->d_assoc_cnt.reserve(n_pos));
+    d_cnt = h->d_assoc_cnt.ptr;
+  }
+  PGMO_TRY(h->d_status.reserve(n_pos));
+  PGMO_TRY(pgmo_deform_run_device(h, 0, n_pos, h->d_x.ptr, h->d_y.ptr, h->d_z.ptr, d_subset,
+                                  precision, h->d_ox.ptr, h->d_oy.ptr, h->d_oz.ptr, d_f64, d_assoc,
+                                  assoc_stride, d_cnt, h->d_status.ptr, nullptr, st));
+
+  bool any_skip = false;
+  for (const ScheduleRun& run : h->sched.runs) any_skip = any_skip || run.skip;
+  if (!subset_idx && !any_skip) {
+    PGMO_CUDA(cudaMemcpyAsync(out_x, h->d_ox.ptr, n_v * sizeof(float), cudaMemcpyDeviceToHost, st));
+    PGMO_CUDA(cudaMemcpyAsync(out_y, h->d_oy.ptr, n_v * sizeof(float), cudaMemcpyDeviceToHost, st));
+    PGMO_CUDA(cudaMemcpyAsync(out_z, h->d_oz.ptr, n_v * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (processed) {
+      PGMO_CUDA(cudaMemcpyAsync(processed, h->d_status.ptr, n_pos, cudaMemcpyDeviceToHost, st));
+    }
+  } else {
+    // only processed vertices may be written: stage and scatter
+    std::vector<float> tx(n_v), ty(n_v), tz(n_v);
+    std::vector<uint8_t> status(n_pos);
+    PGMO_CUDA(cudaMemcpyAsync(tx.data(), h->d_ox.ptr, n_v * sizeof(float), cudaMemcpyDeviceToHost, st));
+    PGMO_CUDA(cudaMemcpyAsync(ty.data(), h->d_oy.ptr, n_v * sizeof(float), cudaMemcpyDeviceToHost, st));
+    PGMO_CUDA(cudaMemcpyAsync(tz.data(), h->d_oz.ptr, n_v * sizeof(float), cudaMemcpyDeviceToHost, st));
+    PGMO_CUDA(cudaMemcpyAsync(status.data(), h->d_status.ptr, n_pos, cudaMemcpyDeviceToHost, st));
+    PGMO_CUDA(cudaStreamSynchronize(st));
+    for (uint64_t p = 0; p < n_pos; ++p) {
+      if (status[p] != kStatusDone) continue;
+      const uint64_t ii = subset_idx ? subset_idx[p] : p;
+      out_x[ii] = tx[ii];
+      out_y[ii] = ty[ii];
+      out_z[ii] = tz[ii];
+    }
+    if (processed) std::memcpy(processed, status.data(), n_pos);
+  }
+  if (out_xyz_f64) {
+    PGMO_CUDA(cudaMemcpyAsync(out_xyz_f64, d_f64, 3 * n_pos * sizeof(double), cudaMemcpyDeviceToHost, st));
+  }
+  if (assoc) {
+    PGMO_CUDA(cudaMemcpyAsync(assoc, d_assoc, n_pos * assoc_stride * sizeof(uint32_t),
+                              cudaMemcpyDeviceToHost, st));
+  }
+  if (assoc_cnt) {
+    PGMO_CUDA(cudaMemcpyAsync(assoc_cnt, d_cnt, n_pos, cudaMemcpyDeviceToHost, st));
+  }
+  PGMO_CUDA(cudaStreamSynchronize(st));
+  return PGMO_OK;
+}
+
+int pgmo_deform_predeform(pgmo_deform_t* h, uint64_t n_v, const float* x, const float* y,
+                          const float* z, const int32_t* graph_indices, uint64_t start_idx,
+                          float* out_x, float* out_y, float* out_z, uint64_t* to_deform,
+                          uint64_t* n_to_deform) {
+  PGMO_CHECK_ARG(h != nullptr && n_to_deform != nullptr);
+  PGMO_TRY(ensureDevice(h->device));
+  *n_to_deform = 0;
+  if (start_idx >= n_v) return PGMO_OK;
+  PGMO_CHECK_ARG(x && y && z && graph_indices && out_x && out_y && out_z && to_deform);
+  if (!h->has_poses) {
+    setLastError("set_controls was called without poses");
+    return PGMO_ERR_INVALID;
+  }
+  cudaStream_t st = h->stream;
+  const uint64_t n = n_v - start_idx;
+  PGMO_TRY(h->d_x.reserve(n_v));
+  PGMO_TRY(h->d_y.reserve(n_v));
+  PGMO_TRY(h->d_z.reserve(n_v));
+  PGMO_TRY(h->d_ox.reserve(n_v));
+  PGMO_TRY(h->d_oy.reserve(n_v));
+  PGMO_TRY(h->d_oz.reserve(n_v));
+  PGMO_TRY(h->d_graph_idx.reserve(n_v));
+  PGMO_TRY(h->d_needs.reserve(n_v));
+  PGMO_CUDA(cudaMemcpyAsync(h->d_x.ptr + start_idx, x + start_idx, n * sizeof(float), cudaMemcpyHostToDevice, st));
+  PGMO_CUDA(cudaMemcpyAsync(h->d_y.ptr + start_idx, y + start_idx, n * sizeof(float), cudaMemcpyHostToDevice, st));
+  PGMO_CUDA(cudaMemcpyAsync(h->d_z.ptr + start_idx, z + start_idx, n * sizeof(float), cudaMemcpyHostToDevice, st));
+  PGMO_CUDA(cudaMemcpyAsync(h->d_graph_idx.ptr + start_idx, graph_indices + start_idx,
+                            n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  PGMO_CUDA(launchPredeform(n_v, start_idx, h->d_x.ptr, h->d_y.ptr, h->d_z.ptr, h->d_graph_idx.ptr,
+                            h->n_c, nullptr, h->has_valid ? h->d_valid.ptr : nullptr, h->d_pos.ptr,
+                            h->d_poses.ptr, h->d_ox.ptr, h->d_oy.ptr, h->d_oz.ptr, h->d_needs.ptr,
+                            nullptr, st));
+  std::vector<float> tx(n), ty(n), tz(n);
+  std::vector<uint8_t> needs(n);
+  PGMO_CUDA(cudaMemcpyAsync(tx.data(), h->d_ox.ptr + start_idx, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  PGMO_CUDA(cudaMemcpyAsync(ty.data(), h->d_oy.ptr + start_idx, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  PGMO_CUDA(cudaMemcpyAsync(tz.data(), h->d_oz.ptr + start_idx, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  PGMO_CUDA(cudaMemcpyAsync(needs.data(), h->d_needs.ptr + start_idx, n, cudaMemcpyDeviceToHost, st));
+  PGMO_CUDA(cudaStreamSynchronize(st));
+  uint64_t m = 0;
+  for (uint64_t i = 0; i < n; ++i) {
+    if (needs[i]) {
+      to_deform[m++] = start_idx + i;
+    } else {
+      out_x[start_idx + i] = tx[i];
+      out_y[start_idx + i] = ty[i];
+      out_z[start_idx + i] = tz[i];
+    }
+  }
+  *n_to_deform = m;
+  return PGMO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,98 @@
+// Device-side data layout and launchers of the deformation path (sm_100a).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace pgmo {
+
+// status byte per processing position
+constexpr uint8_t kStatusSkipped = 0;    // reference `continue`d: no control_point_map entry
+constexpr uint8_t kStatusDone = 1;       // deformed
+constexpr uint8_t kStatusNeedsTie = 2;   // exact float-distance tie (or k too large for the
+                                         // register path): finished by the resolver kernel
+
+constexpr int kResolverMaxDepth = 26;    // octree depth the resolver's DFS stack can hold
+
+struct RunFrameDev {
+  double min_xyz[3];
+  uint32_t depth;
+  int32_t shift[3];
+};
+
+struct DeformArgs {
+  uint64_t first_position;
+  uint64_t n_local;
+  const float* x;
+  const float* y;
+  const float* z;
+  const uint64_t* subset;     // local vertex index per local position, or null
+  // schedule
+  const uint64_t* run_start;  // n_runs + 1 entries, run_start[n_runs] = total positions
+  uint32_t n_runs;
+  const uint4* run_info;      // {lo, hi, k, skip}
+  const RunFrameDev* run_frame;
+  // control table
+  const float4* ctrl_f4;      // float(x), float(y), float(z), del_run (int bits)
+  const int4* ctrl_key;       // stable voxel key xyz
+  const double* ctrl_pos;     // n_c x 3 (f64 control point)
+  const double* poses;        // n_c x 12 (row-major R, t)
+  const float* ctrl_pose_f32; // n_c x 16: R(9) t(3) g(3) pad — FP32 mode
+  double resolution;
+  // outputs
+  float* ox;
+  float* oy;
+  float* oz;
+  double* of64;               // 3 per position, or null
+  uint32_t* assoc;            // assoc_stride per position, or null
+  uint32_t assoc_stride;
+  uint8_t* assoc_cnt;         // or null
+  uint8_t* status;            // per position (always present)
+  unsigned long long* counters;  // [0] = vertices sent to the resolver
+};
+
+struct CandEntry {
+  float dist;
+  int idx;
+};
+
+struct ResolveArgs {
+  CandEntry* scratch;        // one slab of cand_cap entries per resident warp
+  uint32_t cand_cap;
+  uint32_t n_warps;          // resident warps (grid is persistent)
+};
+
+// K1: boundaries of equal-stamp stretches.  Appends (position, stamp) of every position whose
+// stamp differs from its predecessor's (position 0 always) to `out`, unordered; *count is the
+// number appended (may exceed capacity: entries beyond it are dropped).
+cudaError_t launchStampStretches(const uint64_t* stamps, const uint64_t* subset, uint64_t n,
+                                 ulonglong2* out, uint64_t capacity,
+                                 unsigned long long* count, cudaStream_t stream);
+
+// K3: windowed exact top-(k+2) + blend.  precision: 0 = FP64 blend, 1 = FP32 blend.
+cudaError_t launchDeformKnnBlend(const DeformArgs& args, int precision, uint32_t max_k,
+                                 cudaStream_t stream);
+
+// K4: PCL-order resolution of the vertices flagged kStatusNeedsTie.
+cudaError_t launchDeformResolve(const DeformArgs& args, const ResolveArgs& rargs, int precision,
+                                cudaStream_t stream);
+uint32_t resolverResidentWarps(int device);
+
+// K5: rigid predeform by graph index.
+cudaError_t launchPredeform(uint64_t n_v, uint64_t start_idx, const float* x, const float* y,
+                            const float* z, const int32_t* graph_indices, uint64_t n_c,
+                            const float4* ctrl_f4_valid, const uint8_t* valid,
+                            const double* ctrl_pos, const double* poses, float* ox, float* oy,
+                            float* oz, uint8_t* needs_deform, int* out_of_range,
+                            cudaStream_t stream);
+
+// builds ctrl_f4 (only when positions changed) / ctrl_pose_f32 from the f64 tables
+cudaError_t launchBuildControlTables(uint64_t n_c, const double* ctrl_pos, const double* poses,
+                                     float4* ctrl_f4, float* ctrl_pose_f32, bool positions_changed,
+                                     cudaStream_t stream);
+// writes del_run into ctrl_f4[].w and the stable keys (after build_schedule)
+cudaError_t launchApplySchedule(uint64_t n_c, const int32_t* del_run, const int32_t* stable_key3,
+                                float4* ctrl_f4, int4* ctrl_key, cudaStream_t stream);
+
+}  // namespace pgmo

@@ -1,0 +1,286 @@
+// Host-side window schedule builder.  See deform_schedule.h for the idea; the arithmetic that
+// decides voxel membership follows PCL's OctreePointCloud (adoptBoundingBoxToPoint,
+// getKeyBitSize, genOctreeKeyforPoint, deleteVoxelAtPoint) because the reference counts and
+// deletes *1 m voxels*, not points (mesh_deformation.cpp:31,40).
+#include "deform_schedule.h"
+
+#include <algorithm>
+#include <cfloat>
+#include <climits>
+#include <cmath>
+#include <limits>
+#include <unordered_map>
+
+namespace pgmo {
+
+uint64_t stampFromSec(double sec) {
+  // kimera_pgmo/src/utils/common_structs.cpp:21-24
+  return static_cast<uint64_t>(static_cast<int64_t>(sec * 1e9));
+}
+
+namespace {
+
+struct VoxelKey {
+  int32_t x, y, z;
+  bool operator==(const VoxelKey& o) const { return x == o.x && y == o.y && z == o.z; }
+};
+struct VoxelKeyHash {
+  size_t operator()(const VoxelKey& k) const {
+    uint64_t h = static_cast<uint32_t>(k.x) * 0x9E3779B97F4A7C15ull;
+    h ^= (static_cast<uint64_t>(static_cast<uint32_t>(k.y)) + 0x7F4A7C15ull) * 0xC2B2AE3D27D4EB4Full;
+    h ^= (static_cast<uint64_t>(static_cast<uint32_t>(k.z)) + 0x165667B1ull) * 0xD6E8FEB86659FD93ull;
+    return static_cast<size_t>(h ^ (h >> 29));
+  }
+};
+
+// Leaf bookkeeping of the search octree: which voxels are occupied and by which control points.
+// No search structure is kept here — only what getLeafCount / deleteVoxelAtPoint observe.
+class LeafBook {
+ public:
+  explicit LeafBook(double resolution) : res_(resolution) {}
+
+  size_t leafCount() const { return leaves_.size(); }
+  uint32_t maxLeafPoints() const { return max_leaf_points_; }
+
+  void frame(ScheduleRun* run) const {
+    run->min_xyz[0] = min_[0];
+    run->min_xyz[1] = min_[1];
+    run->min_xyz[2] = min_[2];
+    run->depth = depth_;
+    run->shift[0] = shift_[0];
+    run->shift[1] = shift_[1];
+    run->shift[2] = shift_[2];
+  }
+
+  // addPointFromCloud for control point j at float position p; returns its stable key
+  VoxelKey add(uint32_t j, const float p[3]) {
+    growToFit(p);
+    const VoxelKey stable = stableKey(p);
+    auto& pts = leaves_[stable];
+    pts.push_back(j);
+    max_leaf_points_ = std::max<uint32_t>(max_leaf_points_, static_cast<uint32_t>(pts.size()));
+    return stable;
+  }
+
+  // deleteVoxelAtPoint: removes the whole leaf; `killed` receives the control points in it
+  void removeVoxelAt(const float p[3], std::vector<uint32_t>* killed) {
+    killed->clear();
+    if (!box_defined_) return;
+    for (int a = 0; a < 3; ++a) {
+      if (p[a] < min_[a] || p[a] >= max_[a]) return;  // isPointWithinBoundingBox
+    }
+    const auto it = leaves_.find(stableKey(p));
+    if (it == leaves_.end()) return;
+    killed->swap(it->second);
+    leaves_.erase(it);
+  }
+
+ private:
+  VoxelKey stableKey(const float p[3]) const {
+    // genOctreeKeyforPoint: unsigned((p - min) / resolution), float promoted to double
+    const uint32_t kx = static_cast<uint32_t>((p[0] - min_[0]) / res_);
+    const uint32_t ky = static_cast<uint32_t>((p[1] - min_[1]) / res_);
+    const uint32_t kz = static_cast<uint32_t>((p[2] - min_[2]) / res_);
+    return {static_cast<int32_t>(kx) - shift_[0], static_cast<int32_t>(ky) - shift_[1],
+            static_cast<int32_t>(kz) - shift_[2]};
+  }
+
+  void growToFit(const float p[3]) {
+    const float eps = std::numeric_limits<float>::epsilon();
+    while (true) {
+      bool lower = false, upper[3];
+      for (int a = 0; a < 3; ++a) {
+        lower = lower || (p[a] < min_[a]);
+        upper[a] = p[a] >= max_[a];
+      }
+      if (!(lower || upper[0] || upper[1] || upper[2] || !box_defined_)) break;
+      if (box_defined_) {
+        // one more level: the old root becomes a child of the new root
+        double side = static_cast<double>(1u << depth_) * res_;
+        for (int a = 0; a < 3; ++a) {
+          if (!upper[a]) {
+            min_[a] -= side;
+            shift_[a] += static_cast<int32_t>(1u << depth_);
+          }
+        }
+        ++depth_;
+        side = static_cast<double>(1u << depth_) * res_ - eps;
+        for (int a = 0; a < 3; ++a) max_[a] = min_[a] + side;
+      } else {
+        for (int a = 0; a < 3; ++a) {
+          min_[a] = p[a] - res_ / 2;
+          max_[a] = p[a] + res_ / 2;
+        }
+        // getKeyBitSize on an empty tree
+        uint32_t max_voxels = 2;
+        for (int a = 0; a < 3; ++a) {
+          max_voxels = std::max(
+              max_voxels, static_cast<uint32_t>(std::ceil((max_[a] - min_[a] - eps) / res_)));
+        }
+        depth_ = static_cast<uint32_t>(
+            std::max(std::min(32.0, std::ceil(std::log2(max_voxels) - eps)), 0.0));
+        const double side = static_cast<double>(1u << depth_) * res_;
+        for (int a = 0; a < 3; ++a) {
+          const double oversize = (side - (max_[a] - min_[a])) / 2.0;
+          if (oversize > eps) {
+            min_[a] -= oversize;
+            max_[a] += oversize;
+          }
+        }
+        box_defined_ = true;
+      }
+    }
+  }
+
+  double res_;
+  bool box_defined_ = false;
+  double min_[3] = {0, 0, 0};
+  double max_[3] = {0, 0, 0};
+  uint32_t depth_ = 1;
+  int32_t shift_[3] = {0, 0, 0};
+  std::unordered_map<VoxelKey, std::vector<uint32_t>, VoxelKeyHash> leaves_;
+  uint32_t max_leaf_points_ = 0;
+};
+
+struct Builder {
+  const ControlTableHost& ctrl;
+  Schedule* out;
+  LeafBook book;
+  Builder(const ControlTableHost& c, double resolution, Schedule* o)
+      : ctrl(c), out(o), book(resolution) {
+    out->runs.clear();
+    out->del_run.assign(c.n, 0);
+    out->stable_key.assign(3 * c.n, 0);
+    out->max_leaf_points = 0;
+    out->max_k = 0;
+    out->noop = false;
+    out->degenerate = false;
+    for (uint64_t j = 0; j < c.n; ++j) out->del_run[j] = isValid(j) ? INT32_MAX : 0;
+  }
+  bool isValid(uint64_t j) const { return !ctrl.valid || ctrl.valid[j]; }
+  void floatPos(uint64_t j, float p[3]) const {
+    // SearchTree::Impl::addPoint -> eigenToPcl: double -> float (mesh_deformation.cpp:16-20,34)
+    p[0] = static_cast<float>(ctrl.pos_xyz[3 * j + 0]);
+    p[1] = static_cast<float>(ctrl.pos_xyz[3 * j + 1]);
+    p[2] = static_cast<float>(ctrl.pos_xyz[3 * j + 2]);
+  }
+  void addPoint(uint64_t j) {
+    float p[3];
+    floatPos(j, p);
+    const VoxelKey key = book.add(static_cast<uint32_t>(j), p);
+    out->stable_key[3 * j + 0] = key.x;
+    out->stable_key[3 * j + 1] = key.y;
+    out->stable_key[3 * j + 2] = key.z;
+  }
+  void emitRun(uint64_t position, uint32_t lo, uint32_t hi, uint32_t k, bool skip) {
+    ScheduleRun run;
+    run.first_position = position;
+    run.lo = lo;
+    run.hi = hi;
+    run.k = k;
+    run.skip = skip ? 1u : 0u;
+    book.frame(&run);
+    out->runs.push_back(run);
+    out->max_k = std::max(out->max_k, k);
+  }
+};
+
+}  // namespace
+
+void buildStampedSchedule(const ControlTableHost& ctrl, uint64_t n_stretches,
+                          const uint64_t* stretch_stamp, const uint64_t* stretch_len,
+                          uint32_t k_in, double tol_t, double resolution, Schedule* out) {
+  Builder b(ctrl, resolution, out);
+  uint64_t total = 0;
+  for (uint64_t s = 0; s < n_stretches; ++s) total += stretch_len[s];
+  out->total_positions = total;
+  // mesh_deformation.h:143-152
+  if (total == 0 || ctrl.n < k_in) {
+    out->noop = true;
+    return;
+  }
+
+  const uint64_t tol = stampFromSec(tol_t);
+  const uint64_t n_c = ctrl.n;
+  size_t k = k_in;           // mutated mid-sweep (:183) and stays changed
+  uint64_t hi = 0, lo = 0;   // ctrl_pt_idx / lower_ctrl_pt_idx
+  bool dirty = true;         // search state changed since the last emitted run
+  uint64_t position = 0;
+  std::vector<uint32_t> killed;
+
+  for (uint64_t s = 0; s < n_stretches; ++s) {
+    const uint64_t stamp = stretch_stamp[s];
+    const uint64_t len = stretch_len[s];
+    for (uint64_t v = 0; v < len; ++v) {
+      bool step_changed = false;
+      size_t num_ctrl_pts = b.book.leafCount();  // :164
+      while (hi < n_c && (ctrl.stamps[hi] <= stamp + tol || num_ctrl_pts < k + 1)) {  // :167-169
+        const bool valid = b.isValid(hi);
+        if (valid) b.addPoint(hi);
+        ++hi;
+        step_changed = true;
+        if (!valid) continue;
+        ++num_ctrl_pts;
+      }
+      bool skip = false;
+      if (b.book.leafCount() < k + 1) {  // :180
+        if (num_ctrl_pts > 1) {
+          if (k != num_ctrl_pts - 1) step_changed = true;
+          k = num_ctrl_pts - 1;
+        } else {
+          skip = true;
+        }
+      }
+      dirty = dirty || step_changed;
+      if (out->runs.empty() || dirty || (out->runs.back().skip != 0) != skip) {
+        b.emitRun(position + v, static_cast<uint32_t>(lo), static_cast<uint32_t>(hi),
+                  static_cast<uint32_t>(k), skip);
+        dirty = false;
+      }
+      if (!skip) {
+        if (b.book.leafCount() == 0) out->degenerate = true;
+        size_t num_leaves = b.book.leafCount();  // :200
+        while (lo < n_c && num_leaves > k + 1 && ctrl.stamps[lo] < stamp - tol) {  // :201-202
+          step_changed = true;
+          dirty = true;
+          if (!b.isValid(lo)) {
+            ++lo;
+            continue;
+          }
+          float p[3];
+          b.floatPos(lo, p);
+          b.book.removeVoxelAt(p, &killed);  // whole voxel; no-op when already gone
+          for (uint32_t j : killed) out->del_run[j] = static_cast<int32_t>(out->runs.size());
+          --num_leaves;
+          ++lo;
+        }
+      }
+      if (!step_changed) break;  // fixed point: the rest of the stretch sees this very state
+    }
+    position += len;
+  }
+  out->max_leaf_points = b.book.maxLeafPoints();
+}
+
+void buildUnstampedSchedule(const ControlTableHost& ctrl, uint64_t total_positions, uint32_t k,
+                            double resolution, Schedule* out) {
+  Builder b(ctrl, resolution, out);
+  out->total_positions = total_positions;
+  // mesh_deformation.h:78-86
+  if (total_positions == 0 || ctrl.n == 0) {
+    out->noop = true;
+    return;
+  }
+  for (uint64_t j = 0; j < ctrl.n; ++j) {
+    if (b.isValid(j)) b.addPoint(j);
+  }
+  if (b.book.leafCount() < k) {  // :96-99
+    out->noop = true;
+    return;
+  }
+  if (b.book.leafCount() == 0) out->degenerate = true;
+  b.emitRun(0, 0, static_cast<uint32_t>(ctrl.n), k, false);
+  out->max_leaf_points = b.book.maxLeafPoints();
+}
+
+}  // namespace pgmo

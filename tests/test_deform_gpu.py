@@ -1,0 +1,235 @@
+"""GPU parity: pgmo_deform_* (through the C ABI) against the CPU oracle on the same inputs.
+
+Bar (BASELINE.json north_star): vertex->control associations bit-exact in reference order,
+FP64-mode positions within 1e-9 m (we assert bit-identical pre-cast doubles and bit-identical
+floats), FP32-mode positions within 1e-4 m.
+"""
+import numpy as np
+import pytest
+
+from kimera_pgmo_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+FP64_TOL = 1e-9  # metres, north_star
+FP32_TOL = 1e-4  # metres, north_star
+
+
+def _set(handle, case):
+    handle.set_controls(case["ctrl_xyz"], case["ctrl_stamps"], case["valid"], case["poses"])
+
+
+def _compare(gpu, ref, exact_positions=True, tol=FP64_TOL):
+    assert gpu["rc"] == ref["rc"]
+    if ref["rc"] != 0:
+        return
+    np.testing.assert_array_equal(gpu["processed"], ref["processed"])
+    done = ref["processed"].astype(bool)
+    np.testing.assert_array_equal(gpu["assoc_cnt"][done].astype(np.int32), ref["assoc_cnt"][done])
+    ga = gpu["assoc"].astype(np.int64)
+    ga[ga == 0xFFFFFFFF] = -1
+    np.testing.assert_array_equal(ga[done], ref["assoc"][done].astype(np.int64))
+    if exact_positions:
+        np.testing.assert_array_equal(gpu["f64"][done], ref["f64"][done])  # bit-identical doubles
+        for ax in "xyz":
+            np.testing.assert_array_equal(gpu[ax], ref[ax])
+    for ax in "xyz":
+        np.testing.assert_allclose(gpu[ax].astype(np.float64), ref[ax].astype(np.float64), rtol=0,
+                                   atol=tol)
+
+
+def _run_both(capi, oracle, case, k, tol_t, precision=0, subset=None, stamped=True, stride=8):
+    h = capi.DeformHandle(0)
+    _set(h, case)
+    st = case["stamps"] if stamped else None
+    gpu = h.deform_points(case["x"], case["y"], case["z"], st, k=k, tol_t=tol_t,
+                          precision=precision, subset=subset, want_f64=True, want_assoc=True,
+                          assoc_stride=stride)
+    ref = oracle.deform_points(case["x"], case["y"], case["z"], st, case["ctrl_xyz"],
+                               case["ctrl_stamps"], case["valid"], case["poses"], k=k, tol_t=tol_t,
+                               subset=subset, assoc_stride=stride)
+    h.close()
+    return gpu, ref
+
+
+def test_reference_unit_test_deform_points(capi):
+    # kimera_pgmo/test/test_mesh_deformation.cpp:16-50 through the C ABI
+    xs = np.arange(100, dtype=np.float32)
+    zeros = np.zeros(100, dtype=np.float32)
+    ctrl = np.array([[i, 0, 0] for i in range(0, 100, 10)], dtype=np.float64)
+    poses = np.zeros((10, 12))
+    poses[:, [0, 4, 8]] = 1.0
+    poses[:, 9] = ctrl[:, 0]
+    poses[:, 10] = 1.0
+    h = capi.DeformHandle(0)
+    h.set_controls(ctrl, None, None, poses)
+    r = h.deform_points(xs, zeros, zeros, None, k=4)
+    assert r["rc"] == 0
+    np.testing.assert_allclose(r["x"], xs, atol=1e-9)
+    np.testing.assert_allclose(r["y"], 1.0, atol=1e-9)
+    np.testing.assert_allclose(r["z"], 0.0, atol=1e-9)
+
+
+def test_reference_unit_test_time_check(capi, oracle):
+    # test_mesh_deformation.cpp:52-112: k = 3, tol 10 s, stamps 0 / 20 s (uint64 wrap quirk)
+    xs = np.arange(100, dtype=np.float32)
+    zeros = np.zeros(100, dtype=np.float32)
+    ctrl = np.array([[i, 0, 0] for i in range(0, 100, 10)], dtype=np.float64)
+    poses = np.zeros((10, 12))
+    poses[:, [0, 4, 8]] = 1.0
+    poses[:, 9] = ctrl[:, 0]
+    poses[:, 10] = np.where(ctrl[:, 0] > 50, 1.0, -1.0)
+    t20 = capi.stamp_from_sec(20.0)
+    cst = np.where(ctrl[:, 0] > 50, t20, 0).astype(np.uint64)
+    stamps = np.where(np.arange(100) < 50, 0, t20).astype(np.uint64)
+    case = dict(x=xs, y=zeros, z=zeros, stamps=stamps, ctrl_xyz=ctrl, ctrl_stamps=cst,
+                valid=np.ones(10, np.uint8), poses=poses)
+    gpu, ref = _run_both(capi, oracle, case, 3, 10.0)
+    _compare(gpu, ref)
+    np.testing.assert_array_equal(gpu["y"][:50], -1.0)
+    np.testing.assert_array_equal(gpu["y"][51:], 1.0)
+    np.testing.assert_array_equal(gpu["x"], xs)
+
+
+def test_cube_known_answer(capi):
+    # test_deformation_graph.cpp:250-309 second phase: pins the LINEAR weight (1.273)
+    cube = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1], [1, 1, 0], [1, 0, 1], [0, 1, 1],
+                     [1, 1, 1]], dtype=np.float32)
+    ctrl = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], dtype=np.float64)
+    poses = np.zeros((3, 12))
+    poses[:, [0, 4, 8]] = 1.0
+    poses[:, 9:] = [[-0.5, 0, 0], [1.5, 0, 0], [0.5, 1, 0]]
+    h = capi.DeformHandle(0)
+    h.set_controls(ctrl, np.zeros(3, np.uint64), None, poses)
+    r = h.deform_points(cube[:, 0].copy(), cube[:, 1].copy(), cube[:, 2].copy(),
+                        np.zeros(8, np.uint64), k=2, tol_t=10.0)
+    assert abs(r["x"][0] + 0.5) < 1e-3
+    assert abs(r["x"][1] - 1.273) < 1e-3
+
+
+@pytest.mark.parametrize("tol_t", [10.0, 20.0])
+@pytest.mark.parametrize("invalid", [0.0, 0.01])
+def test_config_a_parity(capi, oracle, tol_t, invalid):
+    # configs[0]: 200k vertices, 2k control points, k = 4
+    case = synth.deformation_case(200_000, 2_000, invalid_fraction=invalid)
+    gpu, ref = _run_both(capi, oracle, case, 4, tol_t)
+    _compare(gpu, ref)
+    assert ref["processed"].all()
+
+
+def test_fp32_mode(capi, oracle):
+    case = synth.deformation_case(200_000, 2_000)
+    gpu, ref = _run_both(capi, oracle, case, 4, 10.0, precision=1)
+    _compare(gpu, ref, exact_positions=False, tol=FP32_TOL)
+
+
+def test_unsigned_wrap_epoch_zero(capi, oracle):
+    # stamps starting at 0: `stamp - tol` wraps (mesh_deformation.h:202)
+    case = synth.deformation_case(50_000, 1_000, t0_ns=0)
+    gpu, ref = _run_both(capi, oracle, case, 4, 10.0)
+    _compare(gpu, ref)
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 6, 9])
+def test_k_sweep(capi, oracle, k):
+    case = synth.deformation_case(20_000, 500, seed=3)
+    gpu, ref = _run_both(capi, oracle, case, k, 10.0, stride=12)
+    _compare(gpu, ref)
+
+
+def test_unstamped(capi, oracle):
+    case = synth.deformation_case(20_000, 300, seed=5)
+    gpu, ref = _run_both(capi, oracle, case, 4, 10.0, stamped=False)
+    _compare(gpu, ref)
+
+
+def test_subset_indices(capi, oracle):
+    case = synth.deformation_case(30_000, 600, seed=9)
+    rng = np.random.default_rng(1)
+    subset = np.sort(rng.choice(30_000, 7_000, replace=False)).astype(np.uint64)
+    subset = subset[subset >= 12_000]  # incremental mode: tail of the mesh
+    gpu, ref = _run_both(capi, oracle, case, 4, 10.0, subset=subset)
+    _compare(gpu, ref)
+
+
+@pytest.mark.parametrize("ppv", [1, 3])
+def test_lattice_ties_follow_pcl_order(capi, oracle, ppv):
+    # exact float-distance ties everywhere: associations must follow PCL's traversal order
+    case = synth.lattice_case(n_side=12, points_per_voxel=ppv)
+    gpu, ref = _run_both(capi, oracle, case, 4, 6.0, stride=12)
+    _compare(gpu, ref)
+    gpu, ref = _run_both(capi, oracle, case, 2, 100.0, stamped=False)
+    _compare(gpu, ref)
+
+
+def test_many_points_per_voxel_unstable_sort(capi, oracle):
+    # > 16 candidates inside one voxel with ties: PCL's std::sort is not stable there
+    rng = np.random.default_rng(11)
+    n_c = 60
+    cpos = np.zeros((n_c, 3))
+    cpos[:, 0] = 0.125 * rng.integers(0, 4, n_c)
+    cpos[:, 1] = 0.125 * rng.integers(0, 4, n_c)
+    cpos[:, 2] = 0.125 * rng.integers(0, 2, n_c)
+    cpos[40:] += [3.0, 0, 0]
+    poses = np.zeros((n_c, 12))
+    poses[:, [0, 4, 8]] = 1.0
+    poses[:, 9:] = cpos + rng.uniform(-0.2, 0.2, (n_c, 3))
+    g = 0.125 * np.arange(0, 32, dtype=np.float32)
+    vx, vy = np.meshgrid(g, g[:8], indexing="ij")
+    case = dict(x=vx.ravel().copy(), y=vy.ravel().copy(), z=np.zeros(vx.size, np.float32),
+                stamps=np.zeros(vx.size, np.uint64), ctrl_xyz=cpos,
+                ctrl_stamps=np.zeros(n_c, np.uint64), valid=np.ones(n_c, np.uint8), poses=poses)
+    for k in (4, 12):
+        gpu, ref = _run_both(capi, oracle, case, k, 10.0, stamped=False, stride=16)
+        _compare(gpu, ref)
+
+
+def test_too_few_controls_skip_and_k_shrink(capi, oracle):
+    # first stretches see < k + 1 voxels: k shrinks (:183), single-point windows skip (:185)
+    case = synth.deformation_case(3_000, 30, ctrl_per_kf=1, seed=2)
+    case["valid"][1:4] = 0
+    gpu, ref = _run_both(capi, oracle, case, 4, 0.4)
+    _compare(gpu, ref)
+
+
+def test_early_returns(capi, oracle):
+    case = synth.deformation_case(100, 3, ctrl_per_kf=1)
+    gpu, ref = _run_both(capi, oracle, case, 4, 10.0)  # control_points.size() < k
+    assert gpu["rc"] == ref["rc"] == 1
+    np.testing.assert_array_equal(gpu["x"], case["x"])
+    assert not gpu["processed"].any()
+
+
+def test_shard_invariance_single_gpu(capi):
+    """Vertex-range slabs deformed independently give bitwise the same result as one pass."""
+    import torch
+    case = synth.deformation_case(100_000, 2_000)
+    dev = torch.device("cuda:0")
+    h = capi.DeformHandle(0)
+    _set(h, case)
+    t = {k: torch.from_numpy(case[k]).to(dev) for k in ("x", "y", "z")}
+    st = torch.from_numpy(case["stamps"].view(np.int64)).to(dev)
+    n = case["x"].shape[0]
+
+    def run(n_shards):
+        out = [torch.zeros(n, dtype=torch.float32, device=dev) for _ in range(3)]
+        bounds = [n * i // n_shards for i in range(n_shards + 1)]
+        stamps, lens = [], []
+        for s in range(n_shards):
+            a, b = bounds[s], bounds[s + 1]
+            ss, ll = h.stamp_stretches_device(st[a:b], b - a)
+            stamps.append(ss)
+            lens.append(ll)
+        h.build_schedule(np.concatenate(stamps), np.concatenate(lens), n, 4, 10.0)
+        for s in range(n_shards):
+            a, b = bounds[s], bounds[s + 1]
+            h.run_device(a, b - a, t["x"][a:b], t["y"][a:b], t["z"][a:b], out[0][a:b],
+                         out[1][a:b], out[2][a:b])
+        torch.cuda.synchronize()
+        return [o.cpu().numpy() for o in out]
+
+    one = run(1)
+    for shards in (2, 3, 8):
+        many = run(shards)
+        for a, b in zip(one, many):
+            np.testing.assert_array_equal(a, b)
