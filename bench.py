@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""bench.py — headline metric of BASELINE.json: mesh vertices deformed / s (k = 4).
+
+  python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun)
+  python bench.py --impl reference ...                      (CPU restatement of the reference)
+
+One *step* = one full deformMesh-style pass of the hot path over the synthetic mesh:
+pose update (a new solve result) -> stamp-stretch scan (K1) -> window schedule (cached on the
+host when control positions/stamps and mesh stamps are unchanged) -> windowed knn + blend (K3)
+-> PCL tie-order resolver (K4).  N = 1 is BASELINE configs[2] (10M vertices, 50k control points,
+k = 4, FP64 mode = the reference's arithmetic); N > 1 is weak scaling of the same mesh family
+(10M vertices and 50k control points per GPU, one prefix, vertex-range slabs, control table and
+poses replicated by NCCL broadcast, stamp-stretch lists exchanged by all_gather).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+K_NEIGHBOURS = 4
+TOL_T = 10.0
+CTRL_PER_GPU = 50_000
+BYTES_K3_PER_VERTEX = 24   # 12 B read (x, y, z f32) + 12 B write; DESIGN.md "algorithmic bytes"
+BYTES_STEP_PER_VERTEX = 32  # + 8 B stamp read by K1
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--vertices-per-gpu", type=int, default=10_000_000)
+    ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32"])
+    ap.add_argument("--cpu-sample", type=int, default=1_500_000,
+                    help="vertices of the workload the CPU baseline is timed on")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._thread = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(
+                    ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
+                     "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                if out.returncode == 0 and out.stdout.strip():
+                    self.samples.append([f.strip() for f in out.stdout.strip().split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._thread.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names)
+                   if any(len(s) > 3 + i and s[3 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": float(self.samples[0][1]) if self.samples[0][1].replace(".", "").isdigit() else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+def cpu_baseline(case_fn, n_sample):
+    """Times the CPU restatement (oracle, the reference's single-threaded algorithm) on the
+    first n_sample vertices of the workload with the full control table."""
+    from oracle import ffi
+    case = case_fn(n_sample)
+    r = ffi.deform_points(case["x"], case["y"], case["z"], case["stamps"], case["ctrl_xyz"],
+                          case["ctrl_stamps"], case["valid"], case["poses"], k=K_NEIGHBOURS,
+                          tol_t=TOL_T, want_trace=False)
+    assert r["rc"] == 0
+    return n_sample / r["elapsed_s"], r["elapsed_s"]
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (the oracle port; the real reference needs
+    PCL/GTSAM/... and cannot be built here) on the box's host cores.  The reference path is
+    single-threaded (no OpenMP/TBB/std::thread inside deformMesh), so cores = 1."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from kimera_pgmo_b200 import synth
+    n_total = args.vertices_per_gpu * args.gpus
+    n_ctrl = CTRL_PER_GPU * args.gpus
+    sample = min(400_000, n_total)
+
+    def case_fn(n):
+        return synth.deformation_slab(n_total, n_ctrl, 0, n)
+
+    times = []
+    for i in range(args.warmup + args.steps):
+        _, el = cpu_baseline(case_fn, sample)
+        if i >= args.warmup:
+            times.append(el)
+    ms = 1e3 * sum(times) / len(times)
+    value = sample / (ms * 1e-3)
+    line = {
+        "impl": "reference", "metric": "mesh vertices deformed/sec (k=4)", "value": value,
+        "unit": "vertices/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, n_total, n_ctrl),
+        "cpu_baseline": {"value": value, "unit": "vertices/s", "cores": 1, "kind": "port",
+                         "sample": f"first {sample} vertices of the workload, full control table, "
+                                   "oracle/liboracle.so (g++ -O2, single thread like the reference)"},
+        "e2e": {"value": value, "unit": "vertices/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, n_total, n_ctrl):
+    return {
+        "workload": (f"{n_total}-vertex synthetic building-scale mesh, {n_ctrl} control points, "
+                     f"k={K_NEIGHBOURS}, tol_t={TOL_T}s, full deformMesh (start index 0) "
+                     "after a pose update"),
+        "baseline_config": "configs[2]: 10M-vertex building-scale mesh, 50k control points, k=4, 1 B200"
+        if args.gpus == 1 else
+        "weak scaling of configs[2]/[3]: 10M vertices + 50k control points per GPU, vertex-range slabs",
+        "precision_mode": args.precision,
+        "cache": "inputs larger than L2 (>= 200 MB of vertex streams per step vs 126 MB L2)",
+        "parallelism": f"vertex-range x{args.gpus}",
+    }
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from kimera_pgmo_b200 import capi, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    n_local = args.vertices_per_gpu
+    n_total = n_local * world
+    n_ctrl = CTRL_PER_GPU * world
+    first = rank * n_local
+    precision = capi.FP64 if args.precision == "fp64" else capi.FP32
+
+    case = synth.deformation_slab(n_total, n_ctrl, first, n_local)
+    # host-side (pinned) copies of this rank's inputs: what an end-to-end caller owns
+    h_in = {k: torch.from_numpy(case[k]).pin_memory() for k in ("x", "y", "z")}
+    h_stamps = torch.from_numpy(case["stamps"].view(np.int64)).pin_memory()
+    h_poses = torch.from_numpy(case["poses"]).pin_memory()
+    h_out = [torch.empty(n_local, dtype=torch.float32).pin_memory() for _ in range(3)]
+
+    d = {k: h_in[k].to(dev) for k in h_in}
+    d_stamps = h_stamps.to(dev)
+    d_out = [torch.empty(n_local, dtype=torch.float32, device=dev) for _ in range(3)]
+
+    # control table: rank 0 owns it, everybody else receives it over NCCL
+    d_cpos = torch.from_numpy(case["ctrl_xyz"]).to(dev)
+    d_cst = torch.from_numpy(case["ctrl_stamps"].view(np.int64)).to(dev)
+    d_cvalid = torch.from_numpy(case["valid"]).to(dev)
+    d_poses = h_poses.to(dev)
+    if world > 1:
+        if rank != 0:
+            for t in (d_cpos, d_cst, d_cvalid, d_poses):
+                t.zero_()
+        for t in (d_cpos, d_cst, d_cvalid, d_poses):
+            dist.broadcast(t, src=0)
+    torch.cuda.synchronize()
+
+    h = capi.DeformHandle(local_rank)
+    stream = torch.cuda.current_stream().cuda_stream
+    h.set_controls_device(n_ctrl, d_cpos, d_cst, d_cvalid, d_poses, stream)
+    h.set_profiling(True)
+    cap = 1 << 15
+    gather_buf = torch.zeros((world, 2 * cap + 1), dtype=torch.int64, device=dev) if world > 1 else None
+
+    def exchange_stretches(ss, sl):
+        if world == 1:
+            return ss, sl
+        n = ss.shape[0]
+        assert n <= cap, "stretch list larger than the exchange buffer"
+        mine = torch.zeros(2 * cap + 1, dtype=torch.int64)
+        mine[0] = n
+        mine[1:1 + n] = torch.from_numpy(ss.view(np.int64))
+        mine[1 + cap:1 + cap + n] = torch.from_numpy(sl.view(np.int64))
+        dist.all_gather_into_tensor(gather_buf, mine.to(dev, non_blocking=True))
+        g = gather_buf.cpu().numpy()
+        stamps, lens = [], []
+        for r in range(world):
+            m = int(g[r, 0])
+            stamps.append(g[r, 1:1 + m].view(np.uint64))
+            lens.append(g[r, 1 + cap:1 + cap + m].view(np.uint64))
+        return np.concatenate(stamps), np.concatenate(lens)
+
+    knn_ms, res_ms = [], []
+
+    def step(record=False):
+        # 1. a new solve result: poses replicated to every GPU
+        if world > 1:
+            dist.broadcast(d_poses, src=0)
+        h.update_poses_device(d_poses, stream)
+        # 2. stamp stretches of the local slab, exchanged so that every rank replays the same
+        #    window state machine (cached when nothing changed)
+        ss, sl = h.stamp_stretches_device(d_stamps, n_local, stream)
+        ss, sl = exchange_stretches(ss, sl)
+        rc = h.build_schedule(ss, sl, n_total, K_NEIGHBOURS, TOL_T)
+        assert rc == 0
+        # 3. deform this rank's slab
+        h.run_device(first, n_local, d["x"], d["y"], d["z"], d_out[0], d_out[1], d_out[2],
+                     precision=precision, stream=stream)
+        if record:
+            a, b, _ = h.last_timings()
+            knn_ms.append(a)
+            res_ms.append(b)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        start.record()
+        for _ in range(args.steps):
+            step(record=True)
+        stop.record()
+        barrier()
+    elapsed_ms = start.elapsed_time(stop)
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / args.steps
+    value = n_total / (ms_per_step * 1e-3)
+    n_resolved = h.run_device(first, n_local, d["x"], d["y"], d["z"], d_out[0], d_out[1], d_out[2],
+                              precision=precision, want_resolved=True, stream=stream)
+    _, _, sched_builds = h.last_timings()
+
+    # ---- end to end: host buffers in, host buffers out ------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        h2d = n_local * (12 + 8) + n_ctrl * 96
+        d2h = n_local * 12
+        if world == 1:
+            he = capi.DeformHandle(local_rank)
+            he.set_controls(case["ctrl_xyz"], case["ctrl_stamps"], case["valid"], case["poses"])
+
+            def e2e_step():
+                # the reference-facing C-ABI call: pinned host pointers, copies inside
+                he.update_poses(h_poses.numpy())
+                rc2 = capi._check(he._lib.pgmo_deform_points(
+                    he._h, n_local, capi._ptr(h_in["x"]), capi._ptr(h_in["y"]), capi._ptr(h_in["z"]),
+                    capi._ptr(h_stamps), None, 0, K_NEIGHBOURS, TOL_T, precision,
+                    capi._ptr(h_out[0]), capi._ptr(h_out[1]), capi._ptr(h_out[2]), None, None, 0,
+                    None, None))
+                assert rc2 == 0
+        else:
+            def e2e_step():
+                if rank == 0:
+                    d_poses.copy_(h_poses, non_blocking=True)
+                for k2 in ("x", "y", "z"):
+                    d[k2].copy_(h_in[k2], non_blocking=True)
+                d_stamps.copy_(h_stamps, non_blocking=True)
+                step()
+                for o, ho in zip(d_out, h_out):
+                    ho.copy_(o, non_blocking=True)
+                torch.cuda.synchronize()
+
+        for _ in range(3):
+            e2e_step()
+        barrier()
+        e2e_steps = max(3, min(args.steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        barrier()
+        e2e_ms = 1e3 * (time.perf_counter() - t0) / e2e_steps
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+        e2e = {"value": n_total / (e2e_ms * 1e-3), "unit": "vertices/s", "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "api": "pgmo_deform_update_poses + pgmo_deform_points (host pointers)" if world == 1
+               else "pinned H2D + pgmo_deform_*_device + pinned D2H per rank"}
+
+    if rank == 0:
+        peak, peak_kind = measured_peak_gbs()
+        knn = float(np.mean(knn_ms))
+        achieved = BYTES_K3_PER_VERTEX * n_local / (knn * 1e-3) / 1e9
+        line = {
+            "metric": "mesh vertices deformed/sec (k=4)", "value": value, "unit": "vertices/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64" if args.precision == "fp64" else "f32",
+            "data": "synthetic", "config": workload_config(args, n_total, n_ctrl),
+            "roofline": {
+                "bound": "hbm", "kernel": "deformKnnBlendKernel", "achieved": achieved,
+                "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": load_ncu_traffic(), "kernel_ms": knn,
+                "resolver_ms": float(np.mean(res_ms)),
+                "bytes_per_vertex": BYTES_K3_PER_VERTEX,
+                "step_bytes_per_vertex": BYTES_STEP_PER_VERTEX,
+                "step_frac": BYTES_STEP_PER_VERTEX * n_local / (ms_per_step * 1e-3) / 1e9 / peak,
+            },
+            "clocks": clocks.summary(),
+            "e2e": e2e,
+            "gpu_launches": 4 * args.steps,
+            "resolved_by_tie_kernel": int(n_resolved),
+            "schedule_builds": int(sched_builds),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            v, el = cpu_baseline(lambda n: synth.deformation_slab(n_total, n_ctrl, 0, n),
+                                 min(args.cpu_sample, n_total))
+            line["cpu_baseline"] = {
+                "value": v, "unit": "vertices/s", "cores": 1, "kind": "port",
+                "sample": f"first {min(args.cpu_sample, n_total)} vertices of the workload with the "
+                          f"full control table, {el:.1f} s, oracle/liboracle.so single thread "
+                          "(the reference path is single-threaded)"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def load_ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+    path = os.path.join(ROOT, "profiles", "knn_traffic.json")
+    if os.path.exists(path):
+        try:
+            return json.load(open(path)).get("dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -80,6 +80,29 @@ def deformation_case(n_vertices: int, n_controls: int, ctrl_per_kf: int = 10, se
                 valid=valid, poses=poses)
 
 
+def deformation_slab(n_vertices_total: int, n_controls: int, first: int, count: int,
+                     ctrl_per_kf: int = 10, seed: int = 42, t0_ns: int = T0_NS,
+                     vertex_spread: float = 6.0, ctrl_spread: float = 5.0):
+    """Same workload family as deformation_case, but only vertices [first, first + count) are
+    materialised (multi-GPU ranks generate their own slab); the control table is global."""
+    ctrl = deformation_case(0, n_controls, ctrl_per_kf, seed, t0_ns, 0.0, vertex_spread,
+                            ctrl_spread)
+    n_kf = max(n_controls // ctrl_per_kf, 1)
+    kf = _trajectory(n_kf)
+    kf_stamp = (np.uint64(t0_ns) + np.arange(n_kf, dtype=np.uint64) * np.uint64(1_000_000_000))
+    per_kf = -(-n_vertices_total // n_kf)
+    idx = np.arange(first, first + count, dtype=np.int64)
+    v_kf = np.minimum(idx // per_kf, n_kf - 1)
+    rng = np.random.default_rng([seed, first, count])
+    base = kf[v_kf].astype(np.float32)
+    x = base[:, 0] + rng.uniform(-vertex_spread, vertex_spread, count).astype(np.float32)
+    y = base[:, 1] + rng.uniform(-vertex_spread, vertex_spread, count).astype(np.float32)
+    z = rng.uniform(0.0, 3.0, count).astype(np.float32)
+    ctrl.update(x=np.ascontiguousarray(x), y=np.ascontiguousarray(y), z=np.ascontiguousarray(z),
+                stamps=np.ascontiguousarray(kf_stamp[v_kf]))
+    return ctrl
+
+
 def lattice_case(n_side: int = 12, seed: int = 7, t0_ns: int = T0_NS, n_groups: int = 4,
                  points_per_voxel: int = 1):
     """Tie-heavy case: vertices and control points on a 0.5 m lattice, so exact float-distance
