@@ -1,0 +1,380 @@
+// Drop-in for Kimera-PGMO's mesh-frontend compressors:
+//   MeshInterface / PclMeshInterface   include/kimera_pgmo/utils/mesh_interface.h:17-37,
+//                                      utils/pcl_mesh_interface.h:17-45
+//   MeshCompression (public surface)   include/kimera_pgmo/compression/mesh_compression.h:25-148
+//   VoxelClearingCompression           include/.../voxel_clearing_compression.h:14-97
+//   OctreeCompression                  include/.../octree_compression.h:29-66
+// Same class names, constructor (double resolution), compressAndIntegrate / pruneStoredMesh /
+// clearArchivedBlocks / getters; state lives in HBM behind pgmo_vcc_t / pgmo_oct_t handles.
+#pragma once
+
+#include <memory>
+#include <optional>
+#include <stdexcept>
+#include <vector>
+
+#include "kimera_pgmo_b200/mesh_deformation.h"
+
+namespace kimera_pgmo_b200 {
+
+// utils/mesh_interface.h:17-37
+struct MeshInterface {
+  using Ptr = std::shared_ptr<MeshInterface>;
+  virtual ~MeshInterface() = default;
+  virtual const BlockIndices& blockIndices() const = 0;
+  virtual void markBlockActive(const BlockIndex& block) const = 0;
+  virtual size_t activeBlockSize() const = 0;
+  virtual pcl::PointXYZRGBA getActiveVertex(size_t i) const = 0;
+  virtual bool hasSemantics() const { return false; }
+  virtual std::optional<uint32_t> getActiveSemantics(size_t /* index */) const {
+    return std::nullopt;
+  }
+  virtual Ptr clone() const = 0;
+};
+
+// utils/pcl_mesh_interface.h:17-45: one block (0,0,0) of 3 * faces unindexed vertices
+class PclMeshInterface : public MeshInterface {
+ public:
+  explicit PclMeshInterface(const pcl::PolygonMesh& mesh)
+      : cloud_(new pcl::PointCloud<pcl::PointXYZRGBA>()), faces_(mesh.polygons) {
+    pcl::fromPCLPointCloud2(mesh.cloud, *cloud_);
+    indices_.push_back(BlockIndex::Zero());
+  }
+  const BlockIndices& blockIndices() const override { return indices_; }
+  void markBlockActive(const BlockIndex&) const override {}
+  size_t activeBlockSize() const override { return 3 * faces_.size(); }
+  pcl::PointXYZRGBA getActiveVertex(size_t i) const override {
+    return cloud_->at(faces_.at(i / 3).vertices.at(i % 3));
+  }
+  MeshInterface::Ptr clone() const override { return std::make_shared<PclMeshInterface>(*this); }
+
+ protected:
+  pcl::PointCloud<pcl::PointXYZRGBA>::Ptr cloud_;
+  std::vector<pcl::Vertices> faces_;
+  BlockIndices indices_;
+};
+
+namespace detail {
+// MeshInterface -> the flat arrays of the C ABI (blockIndices() order, cursor protocol kept)
+struct FlatMesh {
+  std::vector<int32_t> block_idx;
+  std::vector<uint64_t> offsets;
+  std::vector<float> xyz;
+  std::vector<uint32_t> rgba;
+  explicit FlatMesh(const MeshInterface& mesh) {
+    offsets.push_back(0);
+    for (const auto& block : mesh.blockIndices()) {
+      block_idx.push_back(block.x());
+      block_idx.push_back(block.y());
+      block_idx.push_back(block.z());
+      mesh.markBlockActive(block);
+      const size_t n = mesh.activeBlockSize();
+      for (size_t i = 0; i < n; ++i) {
+        const pcl::PointXYZRGBA p = mesh.getActiveVertex(i);
+        xyz.push_back(p.x);
+        xyz.push_back(p.y);
+        xyz.push_back(p.z);
+        rgba.push_back(p.rgba);
+      }
+      offsets.push_back(rgba.size());
+    }
+  }
+  uint32_t numBlocks() const { return static_cast<uint32_t>(offsets.size() - 1); }
+};
+
+inline pcl::PointXYZRGBA makePoint(const float* xyz, uint32_t rgba) {
+  pcl::PointXYZRGBA p;
+  p.x = xyz[0];
+  p.y = xyz[1];
+  p.z = xyz[2];
+  p.rgba = rgba;
+  return p;
+}
+inline void fillPolygons(const std::vector<uint32_t>& flat, std::vector<pcl::Vertices>* out) {
+  out->clear();
+  out->resize(flat.size() / 3);
+  for (size_t f = 0; f < out->size(); ++f) {
+    (*out)[f].vertices = {flat[3 * f], flat[3 * f + 1], flat[3 * f + 2]};
+  }
+}
+}  // namespace detail
+
+// mesh_compression.h:25-148 — the public surface shared by the compressors
+class MeshCompression {
+ public:
+  using PointCloud = pcl::PointCloud<pcl::PointXYZRGBA>;
+  using PointCloudXYZ = pcl::PointCloud<pcl::PointXYZ>;
+
+  explicit MeshCompression(double resolution) : resolution_(resolution) {}
+  virtual ~MeshCompression() = default;
+
+  virtual void compressAndIntegrate(const MeshInterface& mesh, PointCloud& new_vertices,
+                                    std::vector<pcl::Vertices>& new_triangles,
+                                    std::vector<size_t>& new_indices,
+                                    HashedIndexMapping& remapping, double stamp_in_sec) = 0;
+  virtual void pruneStoredMesh(double earliest_time_sec) = 0;
+  virtual std::vector<size_t> getInvalidIndices() const { return {}; }
+  virtual void clearArchivedBlocks(const BlockIndices& /* blocks */) {}
+
+  virtual void getVertices(PointCloud::Ptr vertices) = 0;
+  virtual void getTimestamps(std::shared_ptr<std::vector<Timestamp>> vertex_stamps) = 0;
+  virtual void getStoredPolygons(std::shared_ptr<std::vector<pcl::Vertices>> polygons) = 0;
+  virtual size_t getNumVertices() const = 0;
+  virtual const std::vector<size_t>& getActiveVerticesIndex() const = 0;
+
+ protected:
+  double resolution_;
+};
+using MeshCompressionPtr = std::shared_ptr<MeshCompression>;
+
+class VoxelClearingCompression : public MeshCompression {
+ public:
+  explicit VoxelClearingCompression(double resolution, int device = 0)
+      : MeshCompression(resolution) {
+    pgmo_vcc_t* h = nullptr;
+    detail::throwOnError(pgmo_vcc_create(resolution, device, &h));
+    handle_.reset(h, [](pgmo_vcc_t* p) { pgmo_vcc_destroy(p); });
+  }
+
+  // voxel_clearing_compression.cpp:34-47: outputs are `remapping` and the getters; the three
+  // new_* arguments are cleared and left empty, as in the reference
+  void compressAndIntegrate(const MeshInterface& mesh, PointCloud& new_vertices,
+                            std::vector<pcl::Vertices>& new_triangles,
+                            std::vector<size_t>& new_indices, HashedIndexMapping& remapping,
+                            double stamp_in_sec) override {
+    new_vertices.clear();
+    new_triangles.clear();
+    new_indices.clear();
+    const detail::FlatMesh flat(mesh);
+    std::vector<uint64_t> remap(flat.rgba.size());
+    detail::throwOnError(pgmo_vcc_integrate(handle_.get(), flat.numBlocks(), flat.block_idx.data(),
+                                            flat.offsets.data(), flat.xyz.data(), flat.rgba.data(),
+                                            stamp_in_sec, remap.data(), nullptr));
+    size_t b = 0;
+    for (const auto& block : mesh.blockIndices()) {
+      remapping.insert({block, IndexMapping()});  // :123
+      auto& map = remapping.at(block);
+      for (uint64_t i = flat.offsets[b]; i < flat.offsets[b + 1]; ++i) {
+        map[i - flat.offsets[b]] = remap[i];  // :154 operator[] (overwrite)
+      }
+      ++b;
+    }
+    refreshActive();
+  }
+
+  void pruneStoredMesh(double earliest_time_sec) override {
+    detail::throwOnError(pgmo_vcc_prune(handle_.get(), earliest_time_sec));
+    refreshActive();
+  }
+
+  void clearArchivedBlocks(const BlockIndices& blocks) override {
+    std::vector<int32_t> idx;
+    for (const auto& b : blocks) {
+      idx.push_back(b.x());
+      idx.push_back(b.y());
+      idx.push_back(b.z());
+    }
+    detail::throwOnError(
+        pgmo_vcc_clear_blocks(handle_.get(), static_cast<uint32_t>(blocks.size()), idx.data()));
+    refreshActive();
+  }
+
+  std::vector<size_t> getInvalidIndices() const override {
+    uint64_t sizes[4];
+    detail::throwOnError(pgmo_vcc_sizes(handle_.get(), sizes));
+    std::vector<uint64_t> inv(sizes[3]);
+    detail::throwOnError(pgmo_vcc_snapshot(handle_.get(), nullptr, nullptr, nullptr, nullptr,
+                                           nullptr, inv.data()));
+    return std::vector<size_t>(inv.begin(), inv.end());
+  }
+
+  void getVertices(PointCloud::Ptr vertices) override {
+    uint64_t sizes[4];
+    detail::throwOnError(pgmo_vcc_sizes(handle_.get(), sizes));
+    std::vector<float> xyz(3 * sizes[0]);
+    std::vector<uint32_t> rgba(sizes[0]);
+    detail::throwOnError(pgmo_vcc_snapshot(handle_.get(), xyz.data(), rgba.data(), nullptr,
+                                           nullptr, nullptr, nullptr));
+    vertices->clear();
+    for (uint64_t i = 0; i < sizes[0]; ++i) {
+      vertices->push_back(detail::makePoint(xyz.data() + 3 * i, rgba[i]));
+    }
+  }
+
+  void getTimestamps(std::shared_ptr<std::vector<Timestamp>> vertex_stamps) override {
+    uint64_t sizes[4];
+    detail::throwOnError(pgmo_vcc_sizes(handle_.get(), sizes));
+    vertex_stamps->assign(sizes[0], 0);
+    detail::throwOnError(pgmo_vcc_snapshot(handle_.get(), nullptr, nullptr, vertex_stamps->data(),
+                                           nullptr, nullptr, nullptr));
+  }
+
+  void getStoredPolygons(std::shared_ptr<std::vector<pcl::Vertices>> polygons) override {
+    uint64_t sizes[4];
+    detail::throwOnError(pgmo_vcc_sizes(handle_.get(), sizes));
+    std::vector<uint32_t> flat(3 * sizes[1]);
+    detail::throwOnError(pgmo_vcc_snapshot(handle_.get(), nullptr, nullptr, nullptr, flat.data(),
+                                           nullptr, nullptr));
+    detail::fillPolygons(flat, polygons.get());
+  }
+
+  size_t getNumVertices() const override {
+    uint64_t sizes[4];
+    detail::throwOnError(pgmo_vcc_sizes(handle_.get(), sizes));
+    return sizes[0];
+  }
+
+  const std::vector<size_t>& getActiveVerticesIndex() const override {
+    return active_vertices_index_;
+  }
+
+ protected:
+  void refreshActive() {
+    uint64_t sizes[4];
+    detail::throwOnError(pgmo_vcc_sizes(handle_.get(), sizes));
+    std::vector<uint64_t> act(sizes[2]);
+    detail::throwOnError(pgmo_vcc_snapshot(handle_.get(), nullptr, nullptr, nullptr, nullptr,
+                                           act.data(), nullptr));
+    active_vertices_index_.assign(act.begin(), act.end());
+  }
+
+  std::shared_ptr<pgmo_vcc_t> handle_;
+  std::vector<size_t> active_vertices_index_;
+};
+using VoxelClearingCompressionPtr = std::shared_ptr<VoxelClearingCompression>;
+
+class OctreeCompression : public MeshCompression {
+ public:
+  explicit OctreeCompression(double resolution, int device = 0) : MeshCompression(resolution) {
+    pgmo_oct_t* h = nullptr;
+    detail::throwOnError(pgmo_oct_create(resolution, device, &h));
+    handle_.reset(h, [](pgmo_oct_t* p) { pgmo_oct_destroy(p); });
+  }
+
+  // mesh_compression.cpp:216-417.  The dense per-vertex record from the GPU is replayed onto the
+  // caller's persistent `remapping` with the reference's exact container operations:
+  // reobservations overwrite (:288), new / converged vertices insert-if-absent (:366-372),
+  // potential vertices that failed the face check get no entry.
+  void compressAndIntegrate(const MeshInterface& mesh, PointCloud& new_vertices,
+                            std::vector<pcl::Vertices>& new_triangles,
+                            std::vector<size_t>& new_indices, HashedIndexMapping& remapping,
+                            double stamp_in_sec) override {
+    new_vertices.clear();
+    new_triangles.clear();
+    new_indices.clear();
+    const detail::FlatMesh flat(mesh);
+    std::vector<int64_t> idx(flat.rgba.size());
+    std::vector<uint8_t> kind(flat.rgba.size());
+    detail::throwOnError(pgmo_oct_integrate(handle_.get(), flat.numBlocks(), flat.block_idx.data(),
+                                            flat.offsets.data(), flat.xyz.data(), flat.rgba.data(),
+                                            stamp_in_sec, idx.data(), kind.data()));
+    size_t b = 0;
+    for (const auto& block : mesh.blockIndices()) {
+      remapping.insert({block, IndexMapping()});  // :256
+      ++b;
+    }
+    // pass 1: reobservations, in input order; pass 2: inserts.  (Overwrites and inserts touch
+    // different keys within one message, so the relative order between the passes is free.)
+    b = 0;
+    for (const auto& block : mesh.blockIndices()) {
+      auto& map = remapping.at(block);
+      for (uint64_t i = flat.offsets[b]; i < flat.offsets[b + 1]; ++i) {
+        if (kind[i] == 1) map[i - flat.offsets[b]] = static_cast<size_t>(idx[i]);
+      }
+      ++b;
+    }
+    b = 0;
+    for (const auto& block : mesh.blockIndices()) {
+      auto& map = remapping.at(block);
+      for (uint64_t i = flat.offsets[b]; i < flat.offsets[b + 1]; ++i) {
+        if (kind[i] == 2) map.insert({i - flat.offsets[b], static_cast<size_t>(idx[i])});
+      }
+      ++b;
+    }
+    uint64_t sizes[8];
+    detail::throwOnError(pgmo_oct_sizes(handle_.get(), sizes));
+    std::vector<float> nv(3 * sizes[4]);
+    std::vector<uint32_t> nc(sizes[4]), nt(3 * sizes[5]);
+    std::vector<uint64_t> ni(sizes[6]);
+    detail::throwOnError(pgmo_oct_last_outputs(handle_.get(), nv.data(), nc.data(), nt.data(), ni.data()));
+    for (uint64_t i = 0; i < sizes[4]; ++i) new_vertices.push_back(detail::makePoint(nv.data() + 3 * i, nc[i]));
+    detail::fillPolygons(nt, &new_triangles);
+    new_indices.assign(ni.begin(), ni.end());
+    refreshActive();
+  }
+
+  void pruneStoredMesh(double earliest_time_sec) override {
+    detail::throwOnError(pgmo_oct_prune(handle_.get(), earliest_time_sec));
+    refreshActive();
+  }
+
+  void getVertices(PointCloud::Ptr vertices) override {
+    uint64_t sizes[8];
+    detail::throwOnError(pgmo_oct_sizes(handle_.get(), sizes));
+    std::vector<float> xyz(3 * sizes[0]);
+    std::vector<uint32_t> rgba(sizes[0]);
+    detail::throwOnError(pgmo_oct_snapshot(handle_.get(), xyz.data(), rgba.data(), nullptr, nullptr,
+                                           nullptr, nullptr, nullptr));
+    vertices->clear();
+    for (uint64_t i = 0; i < sizes[0]; ++i) {
+      vertices->push_back(detail::makePoint(xyz.data() + 3 * i, rgba[i]));
+    }
+  }
+  void getTimestamps(std::shared_ptr<std::vector<Timestamp>> vertex_stamps) override {
+    uint64_t sizes[8];
+    detail::throwOnError(pgmo_oct_sizes(handle_.get(), sizes));
+    vertex_stamps->assign(sizes[0], 0);
+    detail::throwOnError(pgmo_oct_snapshot(handle_.get(), nullptr, nullptr, vertex_stamps->data(),
+                                           nullptr, nullptr, nullptr, nullptr));
+  }
+  void getStoredPolygons(std::shared_ptr<std::vector<pcl::Vertices>> polygons) override {
+    uint64_t sizes[8];
+    detail::throwOnError(pgmo_oct_sizes(handle_.get(), sizes));
+    std::vector<uint32_t> flat(3 * sizes[1]);
+    detail::throwOnError(pgmo_oct_snapshot(handle_.get(), nullptr, nullptr, nullptr, flat.data(),
+                                           nullptr, nullptr, nullptr));
+    detail::fillPolygons(flat, polygons.get());
+  }
+  void getActiveVertices(PointCloudXYZ::Ptr vertices) {
+    uint64_t sizes[8];
+    detail::throwOnError(pgmo_oct_sizes(handle_.get(), sizes));
+    std::vector<float> xyz(3 * sizes[2]);
+    detail::throwOnError(pgmo_oct_snapshot(handle_.get(), nullptr, nullptr, nullptr, nullptr,
+                                           nullptr, xyz.data(), nullptr));
+    vertices->clear();
+    for (uint64_t i = 0; i < sizes[2]; ++i) {
+      vertices->push_back(pcl::PointXYZ(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]));
+    }
+  }
+  void getActiveVerticesTimestamps(std::shared_ptr<std::vector<double>> timestamps) {
+    uint64_t sizes[8];
+    detail::throwOnError(pgmo_oct_sizes(handle_.get(), sizes));
+    timestamps->assign(sizes[2], 0.0);
+    detail::throwOnError(pgmo_oct_snapshot(handle_.get(), nullptr, nullptr, nullptr, nullptr,
+                                           nullptr, nullptr, timestamps->data()));
+  }
+  size_t getNumVertices() const override {
+    uint64_t sizes[8];
+    detail::throwOnError(pgmo_oct_sizes(handle_.get(), sizes));
+    return sizes[0];
+  }
+  const std::vector<size_t>& getActiveVerticesIndex() const override {
+    return active_vertices_index_;
+  }
+
+ protected:
+  void refreshActive() {
+    uint64_t sizes[8];
+    detail::throwOnError(pgmo_oct_sizes(handle_.get(), sizes));
+    std::vector<uint64_t> act(sizes[2]);
+    detail::throwOnError(pgmo_oct_snapshot(handle_.get(), nullptr, nullptr, nullptr, nullptr,
+                                           act.data(), nullptr, nullptr));
+    active_vertices_index_.assign(act.begin(), act.end());
+  }
+
+  std::shared_ptr<pgmo_oct_t> handle_;
+  std::vector<size_t> active_vertices_index_;
+};
+using OctreeCompressionPtr = std::shared_ptr<OctreeCompression>;
+
+}  // namespace kimera_pgmo_b200

@@ -1,0 +1,209 @@
+// Drop-in for the mesh path of kimera_pgmo::DeformationGraph:
+//   deformMesh x2            src/deformation_graph.cpp:523-559
+//   deformPoints (XYZRGBA)   src/deformation_graph.cpp:561-581
+//   deformPoints<In,Out>     include/kimera_pgmo/deformation_graph.h:808-870
+//   findStartIndex / fillPreviousPoints / cacheNewPoints / predeformPoints   :715-806
+// Everything that belongs to the solver (factors, optimize(), values_) stays upstream: this class
+// only holds what the mesh path reads — vertex_positions_, vertex_stamps_, the cache of the
+// last deformed vertices and the recalculate flag — and forwards the heavy lifting to the GPU.
+//
+// Integration: DeformationGraph keeps a DeformationGraphMeshPath member, mirrors
+// addNewMeshNode() into addControlPoint(), sets setRecalculateVertices() where it sets
+// recalculate_vertices_, and its deformMesh/deformPoints bodies become one-line forwards
+// (INTEGRATION.md).
+#pragma once
+
+#include <algorithm>
+#include <map>
+#include <numeric>
+
+#include "kimera_pgmo_b200/mesh_deformation.h"
+
+namespace kimera_pgmo_b200 {
+
+class DeformationGraphMeshPath {
+ public:
+  explicit DeformationGraphMeshPath(int device = 0) : device_(device) {}
+
+  // DeformationGraph::addNewMeshNode (deformation_graph.cpp:362-378) appends in index order
+  void addControlPoint(char prefix, const gtsam::Point3& position, Timestamp stamp) {
+    vertex_positions_[prefix].push_back(position);
+    vertex_stamps_[prefix].push_back(stamp);
+  }
+  void setControlPoints(char prefix, const std::vector<gtsam::Point3>& positions,
+                        const std::vector<Timestamp>& stamps) {
+    vertex_positions_[prefix] = positions;
+    vertex_stamps_[prefix] = stamps;
+  }
+  void setRecalculateVertices(bool v = true) { recalculate_vertices_ = v; }
+  bool recalculateVertices() const { return recalculate_vertices_; }
+  size_t getNumVertices(char prefix) const {
+    const auto it = vertex_positions_.find(prefix);
+    return it == vertex_positions_.end() ? 0 : it->second.size();
+  }
+
+  // deformation_graph.cpp:532-559
+  pcl::PolygonMesh deformMesh(const pcl::PolygonMesh& original_mesh,
+                              const std::vector<Timestamp>& stamps,
+                              const std::vector<int>& graph_indices, const char& prefix,
+                              const gtsam::Values& optimized_values, size_t k = 4,
+                              double tol_t = 10.0) {
+    pcl::PointCloud<pcl::PointXYZRGBA> new_vertices;
+    pcl::fromPCLPointCloud2(original_mesh.cloud, new_vertices);
+    deformPoints(new_vertices, new_vertices, stamps, prefix, optimized_values, k, tol_t,
+                 &graph_indices);
+    pcl::PolygonMesh new_mesh;
+    new_mesh.polygons = original_mesh.polygons;
+    pcl::toPCLPointCloud2(new_vertices, new_mesh.cloud);
+    return new_mesh;
+  }
+
+  // deformation_graph.cpp:561-581
+  void deformPoints(pcl::PointCloud<pcl::PointXYZRGBA>& vertices,
+                    const pcl::PointCloud<pcl::PointXYZRGBA>& old_vertices,
+                    const std::vector<Timestamp>& stamps, char prefix,
+                    const gtsam::Values& optimized_values, size_t k = 4, double tol_t = 10.0,
+                    const std::vector<int>* graph_indices = nullptr, int start_index_hint = -1,
+                    std::vector<std::set<size_t>>* vertex_graph_map = nullptr) {
+    deformPoints(vertices, ConstStampedCloud<pcl::PointXYZRGBA>{old_vertices, stamps}, prefix,
+                 optimized_values, k, tol_t, graph_indices, start_index_hint, vertex_graph_map);
+  }
+
+  // deformation_graph.h:808-870
+  template <typename CloudIn, typename CloudOut>
+  void deformPoints(CloudOut& vertices, const CloudIn& old_vertices, char prefix,
+                    const gtsam::Values& optimized_values, size_t k = 4, double tol_t = 10.0,
+                    const std::vector<int>* graph_indices = nullptr, int start_index_hint = -1,
+                    std::vector<std::set<size_t>>* vertex_graph_map = nullptr) {
+    if (vertex_positions_.find(prefix) == vertex_positions_.end()) return;  // :819-823
+
+    const size_t start_idx = findStartIndex(prefix, start_index_hint, old_vertices, tol_t);
+    fillPreviousPoints(vertices, prefix, start_idx);
+
+    deformation::Backend& b = backend(prefix);
+    std::vector<size_t> to_deform;
+    if (start_idx != 0) {
+      if (graph_indices) {
+        b.setControls(prefix, vertex_positions_.at(prefix), &vertex_stamps_.at(prefix),
+                      optimized_values);
+        predeformPoints(b, vertices, old_vertices, *graph_indices, to_deform, start_idx);
+      } else {
+        to_deform.resize(traits::num_vertices(vertices) - start_idx);
+        std::iota(to_deform.begin(), to_deform.end(), start_idx);
+      }
+    }
+
+    const std::vector<size_t>* indices_ptr = start_idx == 0 ? nullptr : &to_deform;
+    std::vector<std::set<size_t>> vertex_graph_map_deformed;
+    deformation::deformPoints(vertices, vertex_graph_map_deformed, old_vertices, prefix,
+                              vertex_positions_.at(prefix), vertex_stamps_.at(prefix),
+                              optimized_values, k, tol_t, indices_ptr, &b);
+
+    if (vertex_graph_map) {  // :857-866
+      if (start_idx == 0) {
+        *vertex_graph_map = vertex_graph_map_deformed;
+      } else {
+        vertex_graph_map->resize(traits::num_vertices(vertices));
+        for (size_t i = 0; i < indices_ptr->size(); i++) {
+          vertex_graph_map->at(indices_ptr->at(i)) = vertex_graph_map_deformed.at(i);
+        }
+      }
+    }
+
+    cacheNewPoints(vertices, prefix, start_idx);
+    recalculate_vertices_ = false;
+  }
+
+  // deformation_graph.h:715-746
+  template <typename Cloud>
+  size_t findStartIndex(char prefix, int start_index_hint, const Cloud& cloud,
+                        double tol_t) const {
+    const auto cache = last_calculated_vertices_.find(prefix);
+    if (cache == last_calculated_vertices_.end()) return 0;
+    if (recalculate_vertices_) return 0;
+    if (start_index_hint >= 0) return static_cast<size_t>(start_index_hint);
+    // unsigned arithmetic like the reference: the subtraction wraps for small stamps
+    const Timestamp min_stamp = std::max(static_cast<Timestamp>(0),
+                                         vertex_stamps_.at(prefix).back() - stampFromSec(tol_t));
+    size_t lo = 0, count = traits::num_vertices(cloud);
+    while (count > 0) {  // std::upper_bound(gen, min_stamp, v < stamp(i))
+      const size_t step = count / 2;
+      if (!(min_stamp < traits::get_timestamp(cloud, lo + step))) {
+        lo += step + 1;
+        count -= step + 1;
+      } else {
+        count = step;
+      }
+    }
+    return std::min(lo, cache->second.size());
+  }
+
+ private:
+  deformation::Backend& backend(char prefix) {
+    auto it = backends_.find(prefix);
+    if (it == backends_.end()) it = backends_.emplace(prefix, deformation::Backend(device_)).first;
+    return it->second;
+  }
+
+  // :748-760
+  template <typename Cloud>
+  void fillPreviousPoints(Cloud& vertices, char prefix, size_t start_idx) const {
+    const auto iter = last_calculated_vertices_.find(prefix);
+    if (iter == last_calculated_vertices_.end()) return;
+    for (size_t i = 0; i < start_idx; i++) {
+      traits::set_vertex(vertices, i, traits::get_vertex(iter->second, i));
+    }
+  }
+
+  // :762-777
+  template <typename Cloud>
+  void cacheNewPoints(const Cloud& vertices, char prefix, size_t start_idx) {
+    auto& cache = last_calculated_vertices_[prefix];
+    const size_t total_vertices = traits::num_vertices(vertices);
+    cache.resize(total_vertices);
+    for (size_t i = start_idx; i < total_vertices; i++) {
+      traits::set_vertex(cache, i, traits::get_vertex(vertices, i));
+    }
+  }
+
+  // :779-806 on the GPU (pgmo_deform_predeform)
+  template <typename CloudIn, typename CloudOut>
+  void predeformPoints(deformation::Backend& b, CloudOut& new_vertices, const CloudIn& vertices,
+                       const std::vector<int>& graph_indices,
+                       std::vector<size_t>& indices_to_deform, size_t start_idx) {
+    const size_t n_v = traits::num_vertices(vertices);
+    if (start_idx >= n_v) return;
+    if (graph_indices.size() < n_v) throw std::out_of_range("graph_indices.at()");
+    std::vector<float> x(n_v), y(n_v), z(n_v), ox(n_v), oy(n_v), oz(n_v);
+    for (size_t i = start_idx; i < n_v; ++i) {
+      const traits::Pos p = traits::get_vertex(vertices, i);
+      x[i] = p.x();
+      y[i] = p.y();
+      z[i] = p.z();
+    }
+    std::vector<int32_t> gi(graph_indices.begin(), graph_indices.begin() + n_v);
+    std::vector<uint64_t> to_deform(n_v - start_idx);
+    uint64_t n_to = 0;
+    detail::throwOnError(pgmo_deform_predeform(b.get(), n_v, x.data(), y.data(), z.data(),
+                                               gi.data(), start_idx, ox.data(), oy.data(),
+                                               oz.data(), to_deform.data(), &n_to));
+    size_t next = 0;
+    for (size_t i = start_idx; i < n_v; ++i) {
+      if (next < n_to && to_deform[next] == i) {
+        indices_to_deform.push_back(i);
+        ++next;
+      } else {
+        traits::set_vertex(new_vertices, i, traits::Pos(ox[i], oy[i], oz[i]));
+      }
+    }
+  }
+
+  int device_;
+  std::map<char, std::vector<gtsam::Point3>> vertex_positions_;
+  std::map<char, std::vector<Timestamp>> vertex_stamps_;
+  bool recalculate_vertices_ = false;
+  std::map<char, pcl::PointCloud<pcl::PointXYZ>> last_calculated_vertices_;
+  std::map<char, deformation::Backend> backends_;
+};
+
+}  // namespace kimera_pgmo_b200

@@ -1,0 +1,492 @@
+// The reference's own unit tests, re-typed against the drop-in C++ shim
+// (include/kimera_pgmo_b200/*.h) with the stand-in PCL / GTSAM types.  Scenario and expected
+// values of every test come from the reference:
+//   kimera_pgmo/test/test_mesh_deformation.cpp:16-112
+//   kimera_pgmo/test/test_deformation_graph.cpp:163-309 (solver outputs set by hand)
+//   kimera_pgmo/test/test_voxel_clearing_compression.cpp:106-356
+//   kimera_pgmo/test/test_octree_compression.cpp:58-364, test_mesh_frontend_interface.cpp:523-607
+// Needs a GPU (runs under `pytest -m gpu`); compiled (not run) by the CPU test-suite.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <iostream>
+
+#include "kimera_pgmo_b200/compression.h"
+#include "kimera_pgmo_b200/deformation_graph.h"
+
+using namespace kimera_pgmo_b200;
+
+static int g_failures = 0, g_checks = 0;
+#define EXPECT_TRUE(a)                                                             \
+  do {                                                                             \
+    ++g_checks;                                                                    \
+    if (!(a)) {                                                                    \
+      ++g_failures;                                                                \
+      std::cerr << __FILE__ << ":" << __LINE__ << " EXPECT_TRUE(" #a ") failed\n"; \
+    }                                                                              \
+  } while (0)
+#define EXPECT_EQ(a, b)                                                                      \
+  do {                                                                                       \
+    ++g_checks;                                                                              \
+    if (!((a) == (b))) {                                                                     \
+      ++g_failures;                                                                          \
+      std::cerr << __FILE__ << ":" << __LINE__ << " EXPECT_EQ(" #a ", " #b "): " << (a)      \
+                << " vs " << (b) << "\n";                                                    \
+    }                                                                                        \
+  } while (0)
+#define EXPECT_NEAR(a, b, tol)                                                               \
+  do {                                                                                       \
+    ++g_checks;                                                                              \
+    if (!(std::fabs(double(a) - double(b)) <= (tol))) {                                      \
+      ++g_failures;                                                                          \
+      std::cerr << __FILE__ << ":" << __LINE__ << " EXPECT_NEAR(" #a ", " #b "): " << (a)    \
+                << " vs " << (b) << "\n";                                                    \
+    }                                                                                        \
+  } while (0)
+
+// ------------------------------------------------------------------ TestMeshDeformation
+static void testDeformPoints() {
+  typedef pcl::PointXYZ Point;
+  pcl::PointCloud<Point> original_points;
+  std::vector<gtsam::Point3> control_points;
+  gtsam::Values optimized_values;
+  char prefix = 'a';
+  for (size_t i = 0; i < 100; i++) {
+    original_points.push_back(Point(static_cast<float>(i), 0.0, 0.0));
+    if (i % 10 == 0) {
+      control_points.push_back(gtsam::Point3(static_cast<double>(i), 0.0, 0.0));
+      optimized_values.insert(
+          gtsam::Symbol(prefix, i / 10),
+          gtsam::Pose3(gtsam::Rot3(), gtsam::Point3(static_cast<double>(i), 1.0, 0.0)));
+    }
+  }
+  std::vector<std::set<size_t>> control_point_map;
+  deformation::deformPoints(original_points, control_point_map, original_points, prefix,
+                            control_points, {}, optimized_values);
+  EXPECT_EQ(size_t(100), original_points.size());
+  EXPECT_EQ(size_t(100), control_point_map.size());
+  for (size_t i = 0; i < 100; i++) {
+    EXPECT_NEAR(static_cast<double>(i), original_points.points[i].x, 1.0e-9);
+    EXPECT_NEAR(1.0, original_points.points[i].y, 1.0e-9);
+    EXPECT_NEAR(0.0, original_points.points[i].z, 1.0e-9);
+  }
+}
+
+static void testDeformPointsWithTimeCheck() {
+  typedef pcl::PointXYZ Point;
+  pcl::PointCloud<Point> original_points;
+  std::vector<Timestamp> stamps;
+  std::vector<gtsam::Point3> control_points;
+  std::vector<Timestamp> control_point_stamps;
+  gtsam::Values optimized_values;
+  char prefix = 'a';
+  for (size_t i = 0; i < 100; i++) {
+    original_points.push_back(Point(static_cast<float>(i), 0.0, 0.0));
+    if (i % 10 == 0) {
+      control_points.push_back(gtsam::Point3(static_cast<double>(i), 0.0, 0.0));
+      if (i > 50) {
+        optimized_values.insert(
+            gtsam::Symbol(prefix, i / 10),
+            gtsam::Pose3(gtsam::Rot3(), gtsam::Point3(static_cast<double>(i), 1.0, 0.0)));
+        control_point_stamps.push_back(stampFromSec(20.0));
+      } else {
+        optimized_values.insert(
+            gtsam::Symbol(prefix, i / 10),
+            gtsam::Pose3(gtsam::Rot3(), gtsam::Point3(static_cast<double>(i), -1.0, 0.0)));
+        control_point_stamps.push_back(0);
+      }
+    }
+    stamps.push_back(i < 50 ? 0 : stampFromSec(20.0));
+  }
+  std::vector<std::set<size_t>> control_point_map;
+  const ConstStampedCloud<pcl::PointXYZ> cloud{original_points, stamps};
+  deformation::deformPoints(original_points, control_point_map, cloud, prefix, control_points,
+                            control_point_stamps, optimized_values, 3, 10.0);
+  EXPECT_EQ(size_t(100), original_points.size());
+  for (size_t i = 0; i < 50; i++) {
+    EXPECT_EQ(static_cast<double>(i), double(original_points.points[i].x));
+    EXPECT_EQ(-1.0, double(original_points.points[i].y));
+    EXPECT_EQ(0.0, double(original_points.points[i].z));
+  }
+  for (size_t i = 51; i < 100; i++) {
+    EXPECT_EQ(static_cast<double>(i), double(original_points.points[i].x));
+    EXPECT_EQ(1.0, double(original_points.points[i].y));
+    EXPECT_EQ(0.0, double(original_points.points[i].z));
+  }
+}
+
+// ------------------------------------------------------------------ TestDeformationGraph
+static pcl::PointXYZRGBA colored(float x, float y, float z, uint8_t r, uint8_t g, uint8_t b) {
+  pcl::PointXYZRGBA p;
+  p.x = x;
+  p.y = y;
+  p.z = z;
+  p.r = r;
+  p.g = g;
+  p.b = b;
+  p.a = 255;
+  return p;
+}
+
+// pgmo_fixtures.cpp:97-158
+static pcl::PolygonMesh createSimpleMesh(double scale = 1.0) {
+  const float s = static_cast<float>(scale);
+  pcl::PointCloud<pcl::PointXYZRGBA> ptcld;
+  ptcld.push_back(colored(0, 0, 0, 23, 24, 122));
+  ptcld.push_back(colored(s, 0, 0, 33, 34, 52));
+  ptcld.push_back(colored(0, s, 0, 12, 144, 22));
+  ptcld.push_back(colored(s, s, 0, 0, 14, 0));
+  ptcld.push_back(colored(0, 0, s, 144, 0, 12));
+  pcl::PolygonMesh mesh;
+  pcl::toPCLPointCloud2(ptcld, mesh.cloud);
+  const uint32_t tris[4][3] = {{0, 1, 2}, {1, 3, 2}, {0, 1, 4}, {0, 4, 2}};
+  for (auto& t : tris) {
+    pcl::Vertices v;
+    v.vertices = {t[0], t[1], t[2]};
+    mesh.polygons.push_back(v);
+  }
+  return mesh;
+}
+
+// SetUpDeformationGraph (test_deformation_graph.cpp:98-130): nodes of createMeshTriangle
+static void setUpGraph(DeformationGraphMeshPath* graph, gtsam::Values* values, double shift_x) {
+  const double tri[3][3] = {{0, 0, 0}, {1, 0, 0}, {0, 1, 0}};
+  for (size_t j = 0; j < 3; ++j) {
+    graph->addControlPoint('v', gtsam::Point3(tri[j][0], tri[j][1], tri[j][2]), 0);
+    values->insert(gtsam::Symbol('v', j),
+                   gtsam::Pose3(gtsam::Rot3(),
+                                gtsam::Point3(tri[j][0] + shift_x, tri[j][1], tri[j][2])));
+  }
+}
+
+static void testReconstructAndTranslate() {
+  for (int scenario = 0; scenario < 2; ++scenario) {
+    const double shift = scenario == 0 ? 0.0 : 0.5;
+    DeformationGraphMeshPath graph;
+    gtsam::Values values;
+    setUpGraph(&graph, &values, shift);
+    pcl::PolygonMesh original_mesh = createSimpleMesh();
+    std::vector<Timestamp> stamps(5, 0);
+    std::vector<int> inds = {-1, 0, -1, 0, -1};
+    for (size_t k : {size_t(1), size_t(2)}) {
+      graph.setRecalculateVertices(true);
+      pcl::PolygonMesh new_mesh = graph.deformMesh(original_mesh, stamps, inds, 'v', values, k);
+      pcl::PointCloud<pcl::PointXYZRGBA> deformed, orig;
+      pcl::fromPCLPointCloud2(new_mesh.cloud, deformed);
+      pcl::fromPCLPointCloud2(original_mesh.cloud, orig);
+      EXPECT_EQ(size_t(5), deformed.points.size());
+      for (size_t i = 0; i < 5; ++i) {
+        EXPECT_NEAR(orig.points[i].x + shift, deformed.points[i].x, 1e-6);
+        EXPECT_NEAR(orig.points[i].y, deformed.points[i].y, 1e-6);
+        EXPECT_NEAR(orig.points[i].z, deformed.points[i].z, 1e-6);
+        EXPECT_EQ(orig.points[i].rgba, deformed.points[i].rgba);
+      }
+      EXPECT_EQ(33, int(deformed.points[1].r));
+      EXPECT_EQ(144, int(deformed.points[2].g));
+      EXPECT_EQ(255, int(deformed.points[3].a));
+      EXPECT_EQ(144, int(deformed.points[4].r));
+      EXPECT_TRUE(original_mesh.polygons[0].vertices == new_mesh.polygons[0].vertices);
+      EXPECT_TRUE(original_mesh.polygons[3].vertices == new_mesh.polygons[3].vertices);
+    }
+    // second call without a new solve: served from the cache (findStartIndex -> all cached)
+    pcl::PolygonMesh again = graph.deformMesh(original_mesh, stamps, inds, 'v', values, 2);
+    pcl::PointCloud<pcl::PointXYZRGBA> deformed;
+    pcl::fromPCLPointCloud2(again.cloud, deformed);
+    EXPECT_NEAR(1.0 + shift, deformed.points[1].x, 1e-6);
+  }
+}
+
+static void testDeformMeshCube() {
+  const float cube[8][3] = {{0, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1},
+                            {1, 1, 0}, {1, 0, 1}, {0, 1, 1}, {1, 1, 1}};
+  pcl::PointCloud<pcl::PointXYZRGBA> verts;
+  for (auto& v : cube) verts.push_back(colored(v[0], v[1], v[2], 100, 0, 0));
+  pcl::PolygonMesh cube_mesh;
+  pcl::toPCLPointCloud2(verts, cube_mesh.cloud);
+  pcl::Vertices f;
+  f.vertices = {0, 2, 1};
+  cube_mesh.polygons.push_back(f);
+  std::vector<Timestamp> stamps(8, 0);
+  std::vector<int> inds(8, -1);
+
+  DeformationGraphMeshPath graph;
+  gtsam::Values values;
+  setUpGraph(&graph, &values, -0.5);
+  graph.setRecalculateVertices(true);
+  auto new_mesh = graph.deformMesh(cube_mesh, stamps, inds, 'v', values, 3);
+  pcl::PointCloud<pcl::PointXYZRGBA> actual;
+  pcl::fromPCLPointCloud2(new_mesh.cloud, actual);
+  for (size_t i = 0; i < 8; ++i) {
+    EXPECT_NEAR(cube[i][0] - 0.5, actual.points[i].x, 1e-6);
+    EXPECT_NEAR(cube[i][1], actual.points[i].y, 1e-6);
+    EXPECT_NEAR(cube[i][2], actual.points[i].z, 1e-6);
+  }
+  // second phase: node 0 at (-0.5,0,0), node 1 at (1.5,0,0) -> 1.273 (test :305-306)
+  gtsam::Values values2;
+  values2.insert(gtsam::Symbol('v', 0), gtsam::Pose3(gtsam::Rot3(), gtsam::Point3(-0.5, 0, 0)));
+  values2.insert(gtsam::Symbol('v', 1), gtsam::Pose3(gtsam::Rot3(), gtsam::Point3(1.5, 0, 0)));
+  values2.insert(gtsam::Symbol('v', 2), gtsam::Pose3(gtsam::Rot3(), gtsam::Point3(0.5, 1, 0)));
+  graph.setRecalculateVertices(true);
+  new_mesh = graph.deformMesh(cube_mesh, stamps, inds, 'v', values2, 2);
+  pcl::fromPCLPointCloud2(new_mesh.cloud, actual);
+  EXPECT_NEAR(-0.5, actual.points[0].x, 0.001);
+  EXPECT_NEAR(1.273, actual.points[1].x, 0.001);
+}
+
+static void testIncrementalWithPredeform() {
+  // incremental mode: cache + start index + rigid predeform by graph index
+  DeformationGraphMeshPath graph;
+  gtsam::Values values;
+  for (size_t j = 0; j < 8; ++j) {
+    graph.addControlPoint('v', gtsam::Point3(double(j), 0, 0), Timestamp(j) * 1000000000ull);
+    values.insert(gtsam::Symbol('v', j),
+                  gtsam::Pose3(gtsam::Rot3::Rz(0.01 * j), gtsam::Point3(double(j), 0.1 * j, 0)));
+  }
+  pcl::PointCloud<pcl::PointXYZRGBA> verts;
+  std::vector<Timestamp> stamps;
+  std::vector<int> inds;
+  for (size_t i = 0; i < 80; ++i) {
+    verts.push_back(colored(0.1f * i, 0.2f, 0.1f, 1, 2, 3));
+    stamps.push_back(Timestamp(i / 10) * 1000000000ull);
+    inds.push_back(i % 3 == 0 ? int(i / 10) : -1);
+  }
+  pcl::PointCloud<pcl::PointXYZRGBA> full = verts, incr = verts;
+  graph.setRecalculateVertices(true);
+  graph.deformPoints(full, verts, stamps, 'v', values, 2, 3.0, &inds);
+  // no loop closure since: only vertices newer than last_ctrl_stamp - tol are recomputed
+  std::vector<std::set<size_t>> vgm;
+  graph.deformPoints(incr, verts, stamps, 'v', values, 2, 3.0, &inds, -1, &vgm);
+  EXPECT_EQ(size_t(80), vgm.size());
+  for (size_t i = 0; i < 40; ++i) {  // stamps <= 7 s - 3 s: served from the cache
+    EXPECT_EQ(full.points[i].x, incr.points[i].x);
+    EXPECT_EQ(full.points[i].y, incr.points[i].y);
+  }
+  for (size_t i = 50; i < 80; ++i) {
+    if (inds[i] >= 0) {  // rigidly predeformed by its graph node: R * (v - g) + t
+      const double c = std::cos(0.01 * inds[i]), s = std::sin(0.01 * inds[i]);
+      const double px = double(verts.points[i].x) - inds[i], py = double(verts.points[i].y);
+      EXPECT_NEAR(c * px - s * py + inds[i], incr.points[i].x, 1e-6);
+      EXPECT_NEAR(s * px + c * py + 0.1 * inds[i], incr.points[i].y, 1e-6);
+      EXPECT_TRUE(vgm[i].empty());
+    } else {
+      EXPECT_TRUE(!vgm[i].empty());
+    }
+  }
+}
+
+// ------------------------------------------------------ TestVoxelClearingCompression
+struct OrderedBlockMesh : MeshInterface {  // pgmo_fixtures.h:28-48
+  BlockIndices order;
+  std::vector<std::vector<pcl::PointXYZRGBA>> blocks;
+  mutable size_t active = 0;
+  const BlockIndices& blockIndices() const override { return order; }
+  void markBlockActive(const BlockIndex& block) const override {
+    for (size_t b = 0; b < order.size(); ++b) {
+      if (order[b] == block) active = b;
+    }
+  }
+  size_t activeBlockSize() const override { return blocks[active].size(); }
+  pcl::PointXYZRGBA getActiveVertex(size_t i) const override { return blocks[active][i]; }
+  Ptr clone() const override { return std::make_shared<OrderedBlockMesh>(*this); }
+};
+
+using FaceCoords = std::array<std::array<float, 3>, 3>;
+struct BlockConfig {
+  std::array<int, 3> index;
+  std::vector<FaceCoords> faces;
+};
+static const BlockConfig block1_empty{{0, 0, 0}, {}};
+static const BlockConfig block1_test1{{0, 0, 0},
+                                      {{{{0.5, 0.5, 0.5}, {0.5, 0.75, 0.75}, {0.5, 0.75, 0.5}}},
+                                       {{{0.5, 0.5, 0.5}, {0.5, 0.75, 0.75}, {0.5, 0.75, 0.5}}},
+                                       {{{0.0, 0.0, 0.0}, {0.0, 0.5, 0.5}, {0.0, 0.0, 0.5}}}}};
+static const BlockConfig block2_empty{{-1, 0, 0}, {}};
+static const BlockConfig block2_test1{{-1, 0, 0},
+                                      {{{{-0.5, 0.5, 0.5}, {-0.5, 0.75, 0.75}, {-0.5, 0.75, 0.5}}},
+                                       {{{0.0, 0.0, 0.0}, {0.0, 0.5, 0.5}, {0.0, 0.0, 0.5}}}}};
+
+static OrderedBlockMesh createMesh(const std::vector<BlockConfig>& configs) {
+  OrderedBlockMesh mesh;
+  uint8_t point_index = 0;
+  for (const auto& c : configs) {
+    mesh.order.push_back(BlockIndex(c.index[0], c.index[1], c.index[2]));
+    mesh.blocks.emplace_back();
+    for (const auto& f : c.faces) {
+      for (const auto& v : f) {
+        mesh.blocks.back().push_back(colored(v[0], v[1], v[2], point_index, point_index, point_index));
+        ++point_index;
+      }
+    }
+  }
+  return mesh;
+}
+
+struct CompressionOutput {
+  explicit CompressionOutput(VoxelClearingCompression& c)
+      : vertices(new pcl::PointCloud<pcl::PointXYZRGBA>()),
+        triangles(new std::vector<pcl::Vertices>()),
+        timestamps(new std::vector<Timestamp>()) {
+    c.getVertices(vertices);
+    c.getStoredPolygons(triangles);
+    invalidated = c.getInvalidIndices();
+    active_indices = c.getActiveVerticesIndex();
+    c.getTimestamps(timestamps);
+  }
+  pcl::PointCloud<pcl::PointXYZRGBA>::Ptr vertices;
+  std::shared_ptr<std::vector<pcl::Vertices>> triangles;
+  std::vector<size_t> invalidated;
+  std::vector<size_t> active_indices;
+  std::shared_ptr<std::vector<Timestamp>> timestamps;
+};
+
+static bool checkTriangles(const std::vector<std::vector<uint32_t>>& expected,
+                           const std::vector<pcl::Vertices>& result) {
+  std::vector<std::vector<uint32_t>> filtered;
+  for (const auto& r : result) {
+    bool seen = false;
+    for (const auto& t : filtered) seen |= (t == r.vertices);
+    if (!seen) filtered.push_back(r.vertices);
+  }
+  if (expected.size() != filtered.size()) return false;
+  for (size_t i = 0; i < expected.size(); ++i) {
+    std::set<uint32_t> e(expected[i].begin(), expected[i].end());
+    std::set<uint32_t> r(filtered[i].begin(), filtered[i].end());
+    if (e != r) return false;
+  }
+  return true;
+}
+
+static void integrate(VoxelClearingCompression& c, const OrderedBlockMesh& mesh, double t) {
+  pcl::PointCloud<pcl::PointXYZRGBA> v;
+  std::vector<pcl::Vertices> tri;
+  std::vector<size_t> ind;
+  HashedIndexMapping remap;
+  c.compressAndIntegrate(mesh, v, tri, ind, remap, t);
+}
+
+static void testVoxelClearing() {
+  using V = std::vector<size_t>;
+  {  // clearingCorrectBasic
+    VoxelClearingCompression c(1.0e-3);
+    integrate(c, createMesh({block1_test1}), 100.0);
+    CompressionOutput o(c);
+    EXPECT_EQ(6u, o.vertices->points.size());
+    EXPECT_EQ(0u, o.invalidated.size());
+    EXPECT_EQ(o.vertices->size(), o.timestamps->size());
+    EXPECT_TRUE(o.active_indices == (V{0, 1, 2, 3, 4, 5}));
+    EXPECT_TRUE(checkTriangles({{0, 1, 2}, {3, 4, 5}}, *o.triangles));
+    integrate(c, createMesh({block1_empty}), 100.0);
+    CompressionOutput o2(c);
+    EXPECT_EQ(6u, o2.vertices->points.size());
+    EXPECT_EQ(6u, o2.invalidated.size());
+    EXPECT_EQ(0u, o2.triangles->size());
+    EXPECT_EQ(0u, o2.active_indices.size());
+  }
+  {  // clearingCorrectMultiblock
+    VoxelClearingCompression c(1.0e-3);
+    integrate(c, createMesh({block1_test1, block2_test1}), 100.0);
+    {
+      CompressionOutput o(c);
+      EXPECT_EQ(9u, o.vertices->points.size());
+      EXPECT_EQ(0u, o.invalidated.size());
+      EXPECT_TRUE(checkTriangles({{6, 7, 8}, {3, 4, 5}, {0, 1, 2}}, *o.triangles));
+    }
+    integrate(c, createMesh({block1_empty, block2_test1}), 100.0);
+    {
+      CompressionOutput o(c);
+      EXPECT_EQ(9u, o.vertices->points.size());
+      EXPECT_EQ(3u, o.invalidated.size());
+      EXPECT_TRUE(checkTriangles({{6, 7, 8}, {3, 4, 5}}, *o.triangles));
+    }
+    integrate(c, createMesh({block1_test1, block2_test1}), 100.0);
+    {
+      CompressionOutput o(c);
+      EXPECT_EQ(12u, o.vertices->points.size());
+      EXPECT_EQ(3u, o.invalidated.size());
+      EXPECT_TRUE(checkTriangles({{6, 7, 8}, {3, 4, 5}, {9, 10, 11}}, *o.triangles));
+    }
+    integrate(c, createMesh({block1_test1, block2_empty}), 100.0);
+    {
+      CompressionOutput o(c);
+      EXPECT_EQ(12u, o.vertices->points.size());
+      EXPECT_EQ(6u, o.invalidated.size());
+      EXPECT_TRUE(checkTriangles({{9, 10, 11}, {3, 4, 5}}, *o.triangles));
+    }
+  }
+  {  // pruningCorrectMultiblock
+    VoxelClearingCompression c(1.0e-3);
+    integrate(c, createMesh({block1_test1}), 100.0);
+    integrate(c, createMesh({block2_test1}), 102.0);
+    c.pruneStoredMesh(101.0);
+    integrate(c, createMesh({block1_empty, block2_empty}), 105.0);
+    {
+      CompressionOutput o(c);
+      EXPECT_EQ(9u, o.vertices->points.size());
+      EXPECT_EQ(3u, o.invalidated.size());
+      EXPECT_TRUE(checkTriangles({{0, 1, 2}, {3, 4, 5}}, *o.triangles));
+    }
+    integrate(c, createMesh({block1_test1}), 105.0);
+    {
+      CompressionOutput o(c);
+      EXPECT_EQ(15u, o.vertices->points.size());
+      EXPECT_EQ(3u, o.invalidated.size());
+      EXPECT_EQ(o.vertices->size(), o.timestamps->size());
+      EXPECT_TRUE(checkTriangles({{0, 1, 2}, {3, 4, 5}, {9, 10, 11}, {12, 13, 14}}, *o.triangles));
+    }
+  }
+}
+
+// ------------------------------------------------------------- TestOctreeCompression
+static void testOctreeCompression() {
+  using V = std::vector<size_t>;
+  OctreeCompression compression(0.1);
+  pcl::PointCloud<pcl::PointXYZRGBA> new_vertices;
+  std::vector<pcl::Vertices> new_triangles;
+  std::vector<size_t> new_indices;
+  HashedIndexMapping remaps;
+  PclMeshInterface mesh1(createSimpleMesh(1.0));
+  compression.compressAndIntegrate(mesh1, new_vertices, new_triangles, new_indices, remaps, 100.0);
+  EXPECT_EQ(5u, new_vertices.size());
+  EXPECT_EQ(4u, new_triangles.size());
+  EXPECT_TRUE(new_indices == (V{0, 1, 2, 3, 4}));
+  EXPECT_EQ(1, new_vertices.points[1].x);
+  EXPECT_EQ(1, new_vertices.points[2].y);
+  EXPECT_EQ(1, new_vertices.points[4].z);
+  EXPECT_EQ(0u, new_triangles.at(0).vertices[0]);
+  EXPECT_EQ(2u, new_triangles.at(3).vertices[2]);
+  PclMeshInterface mesh2(createSimpleMesh(2.0));
+  remaps.clear();
+  compression.compressAndIntegrate(mesh2, new_vertices, new_triangles, new_indices, remaps, 101.0);
+  EXPECT_EQ(4u, new_vertices.size());
+  EXPECT_EQ(4u, new_triangles.size());
+  EXPECT_TRUE(new_indices == (V{0, 5, 6, 7, 8}));
+  EXPECT_EQ(2, new_vertices.points[0].x);
+  EXPECT_EQ(6u, new_triangles.at(3).vertices[2]);
+  compression.pruneStoredMesh(100.5);
+  pcl::PointCloud<pcl::PointXYZ>::Ptr active(new pcl::PointCloud<pcl::PointXYZ>());
+  compression.getActiveVertices(active);
+  EXPECT_EQ(5u, active->size());
+  EXPECT_EQ(2, active->points[1].x);
+  PclMeshInterface mesh3(createSimpleMesh(1.0));
+  remaps.clear();
+  compression.compressAndIntegrate(mesh3, new_vertices, new_triangles, new_indices, remaps, 102.0);
+  EXPECT_TRUE(new_indices == (V{0, 9, 10, 11, 12}));
+  EXPECT_EQ(13u, compression.getNumVertices());
+}
+
+int main(int argc, char** argv) {
+  const bool with_octree = argc > 1 && std::strcmp(argv[1], "--octree") == 0;
+  if (pgmo_device_count() <= 0) {
+    std::printf("no CUDA device: the shim has no CPU fallback\n");
+    return 77;
+  }
+  testDeformPoints();
+  testDeformPointsWithTimeCheck();
+  testReconstructAndTranslate();
+  testDeformMeshCube();
+  testIncrementalWithPredeform();
+  testVoxelClearing();
+  if (with_octree) testOctreeCompression();
+  std::printf("shim tests: %d checks, %d failures\n", g_checks, g_failures);
+  return g_failures ? 1 : 0;
+}
