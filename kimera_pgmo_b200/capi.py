@@ -46,6 +46,7 @@ SIGNATURES = {
     "pgmo_deform_update_poses": (C.c_int, [_vp, _vp]),
     "pgmo_deform_update_poses_device": (C.c_int, [_vp, _vp, _vp]),
     "pgmo_deform_set_profiling": (C.c_int, [_vp, C.c_int]),
+    "pgmo_deform_set_search_mode": (C.c_int, [_vp, C.c_int]),
     "pgmo_deform_last_timings": (C.c_int, [_vp, _vp, _u64p]),
     "pgmo_deform_points": (C.c_int, [_vp, C.c_uint64, _vp, _vp, _vp, _vp, _vp, C.c_uint64,
                                      C.c_uint32, C.c_double, C.c_int, _vp, _vp, _vp, _vp, _vp,
@@ -163,6 +164,9 @@ class DeformHandle:
 
     def update_poses_device(self, d_poses, stream=0):
         _check(self._lib.pgmo_deform_update_poses_device(self._h, _ptr(d_poses), _vp(stream)))
+
+    def set_search_mode(self, mode):
+        _check(self._lib.pgmo_deform_set_search_mode(self._h, int(mode)))
 
     def set_profiling(self, enabled=True):
         _check(self._lib.pgmo_deform_set_profiling(self._h, 1 if enabled else 0))

@@ -1,5 +1,6 @@
 // C ABI of the deformation path (see include/pgmo_b200.h).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -44,6 +45,17 @@ struct pgmo_deform {
   DevBuf<uint64_t> d_run_start;
   DevBuf<uint4> d_run_info;
   DevBuf<RunFrameDev> d_run_frame;
+  // per-run spatial grids over the alive control points (built with the schedule)
+  bool use_grid = false;
+  int grid_mode = 1;  // 0 = brute force over the window, 1 = per-run grids
+  DevBuf<RunGridDev> d_grids;
+  DevBuf<float4> d_grid_points;
+  DevBuf<uint32_t> d_grid_cells;
+  DevBuf<uint32_t> d_grid_offsets;
+  DevBuf<WorkItem> d_items;
+  float r_scale = 1.0f, r_grow_mul = 1.5f, r_grow_add = 1.0f;
+  uint32_t n_items = 0;
+  uint64_t items_first = ~0ull, items_n = 0, items_sched_builds = ~0ull;
 
   // optional kernel timing (bench / roofline): events on the launching stream
   bool profiling = false;
@@ -113,6 +125,31 @@ int uploadSchedule(pgmo_deform_t* h, cudaStream_t st) {
                             3 * h->n_c * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   PGMO_CUDA(launchApplySchedule(h->n_c, h->d_del_run.ptr, h->d_stable_key.ptr, h->d_ctrl_f4.ptr,
                                 h->d_ctrl_key.ptr, st));
+  // per-run grids: one slab of (hi - lo) point slots per run; skipped when the slabs would not
+  // pay off (tiny windows) or would be unreasonably large (window ~ whole table for every run)
+  h->use_grid = false;
+  std::vector<uint32_t> offsets(n_runs + 1, 0);
+  uint64_t total_slots = 0, widest = 0;
+  for (size_t r = 0; r < n_runs; ++r) {
+    offsets[r] = static_cast<uint32_t>(total_slots);
+    if (!s.runs[r].skip) {
+      total_slots += s.runs[r].hi - s.runs[r].lo;
+      widest = std::max<uint64_t>(widest, s.runs[r].hi - s.runs[r].lo);
+    }
+  }
+  offsets[n_runs] = static_cast<uint32_t>(total_slots);
+  if (h->grid_mode == 1 && n_runs > 0 && widest > 48 && total_slots < (1ull << 28)) {
+    PGMO_TRY(h->d_grids.reserve(n_runs));
+    PGMO_TRY(h->d_grid_points.reserve(total_slots + 1));
+    PGMO_TRY(h->d_grid_cells.reserve(n_runs * static_cast<size_t>(kGridMaxCells + 1)));
+    PGMO_TRY(h->d_grid_offsets.reserve(n_runs + 1));
+    PGMO_CUDA(cudaMemcpyAsync(h->d_grid_offsets.ptr, offsets.data(), (n_runs + 1) * sizeof(uint32_t),
+                              cudaMemcpyHostToDevice, st));
+    PGMO_CUDA(launchBuildRunGrids(static_cast<uint32_t>(n_runs), h->d_run_info.ptr, h->d_ctrl_f4.ptr,
+                                  h->d_grid_offsets.ptr, h->d_grids.ptr, h->d_grid_points.ptr,
+                                  h->d_grid_cells.ptr, st));
+    h->use_grid = true;
+  }
   // the host vectors above die at scope exit: make sure the copies have been consumed
   PGMO_CUDA(cudaStreamSynchronize(st));
   return PGMO_OK;
@@ -192,6 +229,10 @@ int pgmo_deform_create(int device, pgmo_deform_t** out) {
     setLastError("cudaStreamCreateWithFlags failed");
     return PGMO_ERR_CUDA;
   }
+  // tuning knobs of the search-box schedule (results do not depend on them)
+  if (const char* e = std::getenv("PGMO_R_SCALE")) h->r_scale = static_cast<float>(atof(e));
+  if (const char* e = std::getenv("PGMO_R_GROW_MUL")) h->r_grow_mul = static_cast<float>(atof(e));
+  if (const char* e = std::getenv("PGMO_R_GROW_ADD")) h->r_grow_add = static_cast<float>(atof(e));
   for (auto& e : h->ev) {
     if (cudaEventCreate(&e) != cudaSuccess) {
       setLastError("cudaEventCreate failed");
@@ -475,7 +516,58 @@ int pgmo_deform_run_device(pgmo_deform_t* h, uint64_t first_position, uint64_t n
   ra.scratch = h->d_scratch.ptr;
 
   if (h->profiling) PGMO_CUDA(cudaEventRecord(h->ev[0], st));
-  PGMO_CUDA(launchDeformKnnBlend(a, precision, h->sched.max_k, st));
+  if (h->use_grid) {
+    // work items: <= kDeformChunk consecutive positions of one run each (cached per slab)
+    if (h->items_first != first_position || h->items_n != n_local ||
+        h->items_sched_builds != h->sched_builds) {
+      std::vector<WorkItem> items;
+      const auto& runs = h->sched.runs;
+      size_t r = 0;
+      {
+        size_t lo = 0, hi = runs.size();
+        while (hi - lo > 1) {
+          const size_t mid = (lo + hi) / 2;
+          if (runs[mid].first_position <= first_position) lo = mid;
+          else hi = mid;
+        }
+        r = lo;
+      }
+      const uint64_t slab_end = first_position + n_local;
+      for (; r < runs.size() && runs[r].first_position < slab_end; ++r) {
+        const uint64_t run_end =
+            r + 1 < runs.size() ? runs[r + 1].first_position : h->sched.total_positions;
+        uint64_t b = std::max<uint64_t>(runs[r].first_position, first_position);
+        const uint64_t e = std::min<uint64_t>(run_end, slab_end);
+        for (; b < e; b += kDeformChunk) {
+          WorkItem it;
+          it.start = b - first_position;
+          it.run = static_cast<uint32_t>(r);
+          it.count = static_cast<uint32_t>(std::min<uint64_t>(kDeformChunk, e - b));
+          items.push_back(it);
+        }
+      }
+      PGMO_TRY(h->d_items.reserve(items.size() + 1));
+      PGMO_CUDA(cudaMemcpyAsync(h->d_items.ptr, items.data(), items.size() * sizeof(WorkItem),
+                                cudaMemcpyHostToDevice, st));
+      PGMO_CUDA(cudaStreamSynchronize(st));  // `items` dies at scope exit
+      h->n_items = static_cast<uint32_t>(items.size());
+      h->items_first = first_position;
+      h->items_n = n_local;
+      h->items_sched_builds = h->sched_builds;
+    }
+    GridArgs ga;
+    ga.grids = h->d_grids.ptr;
+    ga.points = h->d_grid_points.ptr;
+    ga.cells = h->d_grid_cells.ptr;
+    ga.r_scale = h->r_scale;
+    ga.r_grow_mul = h->r_grow_mul;
+    ga.r_grow_add = h->r_grow_add;
+    if (h->profiling) PGMO_CUDA(cudaEventRecord(h->ev[0], st));
+    PGMO_CUDA(launchDeformKnnBlendGrid(a, ga, h->d_items.ptr, h->n_items, precision,
+                                       h->sched.max_k, st));
+  } else {
+    PGMO_CUDA(launchDeformKnnBlend(a, precision, h->sched.max_k, st));
+  }
   if (h->profiling) PGMO_CUDA(cudaEventRecord(h->ev[1], st));
   PGMO_CUDA(launchDeformResolve(a, ra, precision, st));
   if (h->profiling) {
@@ -490,6 +582,14 @@ int pgmo_deform_run_device(pgmo_deform_t* h, uint64_t first_position, uint64_t n
     PGMO_CUDA(cudaStreamSynchronize(st));
     *n_resolved = h->h_counters.ptr[0];
   }
+  return PGMO_OK;
+}
+
+int pgmo_deform_set_search_mode(pgmo_deform_t* h, int mode) {
+  PGMO_CHECK_ARG(h != nullptr);
+  PGMO_CHECK_ARG(mode == 0 || mode == 1);
+  if (h->grid_mode != mode) h->sched_ready = false;  // rebuild (or drop) the grids
+  h->grid_mode = mode;
   return PGMO_OK;
 }
 

@@ -1,0 +1,219 @@
+// Device helpers shared by the deformation kernels: the reference's arithmetic, bit for bit.
+#pragma once
+
+#include <cfloat>
+
+#include "deform_kernels.cuh"
+
+namespace pgmo {
+namespace dev {
+
+__device__ __forceinline__ float dist2Exact(float ax, float ay, float az, float bx, float by,
+                                            float bz) {
+  const float dx = __fsub_rn(ax, bx);
+  const float dy = __fsub_rn(ay, by);
+  const float dz = __fsub_rn(az, bz);
+  return __fadd_rn(__fmul_rn(dx, dx), __fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dz, dz)));
+}
+
+__device__ __forceinline__ uint32_t findRun(const uint64_t* __restrict__ run_start,
+                                            uint32_t n_runs, uint64_t position) {
+  // last r with run_start[r] <= position
+  uint32_t lo = 0, hi = n_runs;
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(run_start + mid) <= position) lo = mid;
+    else hi = mid;
+  }
+  return lo;
+}
+
+// interpPoint's blend in the reference's arithmetic.  nbr_d2 / nbr_idx: n neighbours ascending.
+__device__ __forceinline__ void blendFp64(const DeformArgs& a, float qx, float qy, float qz,
+                                          const float* nbr_d2, const int* nbr_idx, int n,
+                                          double out[3]) {
+  const float d_max_f = __fsqrt_rn(nbr_d2[n - 1]);
+  const double d_max = static_cast<double>(d_max_f);
+  const bool const_w = (__fsqrt_rn(nbr_d2[0]) == d_max_f) || d_max == 0.0;
+  double wsum = 0.0, acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
+  const double v0 = static_cast<double>(qx), v1 = static_cast<double>(qy),
+               v2 = static_cast<double>(qz);
+  for (int j = 0; j < n - 1; ++j) {
+    const int c = nbr_idx[j];
+    const double w =
+        const_w ? 1.0
+                : __dsub_rn(1.0, __ddiv_rn(static_cast<double>(__fsqrt_rn(nbr_d2[j])), d_max));
+    wsum = __dadd_rn(wsum, w);
+    const double* g = a.ctrl_pos + 3ull * c;
+    const double* T = a.poses + 12ull * c;
+    const double p0 = __dsub_rn(v0, g[0]);
+    const double p1 = __dsub_rn(v1, g[1]);
+    const double p2 = __dsub_rn(v2, g[2]);
+    const double r0 = __dadd_rn(__dadd_rn(__dmul_rn(T[0], p0), __dmul_rn(T[1], p1)), __dmul_rn(T[2], p2));
+    const double r1 = __dadd_rn(__dadd_rn(__dmul_rn(T[3], p0), __dmul_rn(T[4], p1)), __dmul_rn(T[5], p2));
+    const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(T[6], p0), __dmul_rn(T[7], p1)), __dmul_rn(T[8], p2));
+    acc0 = __dadd_rn(acc0, __dmul_rn(w, __dadd_rn(r0, T[9])));
+    acc1 = __dadd_rn(acc1, __dmul_rn(w, __dadd_rn(r1, T[10])));
+    acc2 = __dadd_rn(acc2, __dmul_rn(w, __dadd_rn(r2, T[11])));
+  }
+  out[0] = __ddiv_rn(acc0, wsum);
+  out[1] = __ddiv_rn(acc1, wsum);
+  out[2] = __ddiv_rn(acc2, wsum);
+}
+
+// FP32 mode: same neighbours, same weight formula, float arithmetic (FMA allowed).
+__device__ __forceinline__ void blendFp32(const DeformArgs& a, float qx, float qy, float qz,
+                                          const float* nbr_d2, const int* nbr_idx, int n,
+                                          float out[3]) {
+  const float d_max = __fsqrt_rn(nbr_d2[n - 1]);
+  const bool const_w = (__fsqrt_rn(nbr_d2[0]) == d_max) || d_max == 0.0f;
+  const float inv_dmax = const_w ? 0.0f : __frcp_rn(d_max);
+  float wsum = 0.f, acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
+  for (int j = 0; j < n - 1; ++j) {
+    const int c = nbr_idx[j];
+    const float w = const_w ? 1.0f : 1.0f - __fsqrt_rn(nbr_d2[j]) * inv_dmax;
+    wsum += w;
+    const float4* T = reinterpret_cast<const float4*>(a.ctrl_pose_f32 + 16ull * c);
+    const float4 t0 = __ldg(T), t1 = __ldg(T + 1), t2 = __ldg(T + 2), t3 = __ldg(T + 3);
+    // layout: R0..R8, t0..t2, g0..g2, pad
+    const float p0 = qx - t3.x, p1 = qy - t3.y, p2 = qz - t3.z;
+    const float r0 = t0.x * p0 + t0.y * p1 + t0.z * p2 + t2.y;
+    const float r1 = t0.w * p0 + t1.x * p1 + t1.y * p2 + t2.z;
+    const float r2 = t1.z * p0 + t1.w * p1 + t2.x * p2 + t2.w;
+    acc0 += w * r0;
+    acc1 += w * r1;
+    acc2 += w * r2;
+  }
+  out[0] = acc0 / wsum;
+  out[1] = acc1 / wsum;
+  out[2] = acc2 / wsum;
+}
+
+__device__ __forceinline__ void writeResult(const DeformArgs& a, uint64_t p, uint64_t ii,
+                                            int precision, float qx, float qy, float qz,
+                                            const float* nbr_d2, const int* nbr_idx, int n) {
+  if (precision == 0) {
+    double o[3];
+    blendFp64(a, qx, qy, qz, nbr_d2, nbr_idx, n, o);
+    a.ox[ii] = __double2float_rn(o[0]);
+    a.oy[ii] = __double2float_rn(o[1]);
+    a.oz[ii] = __double2float_rn(o[2]);
+    if (a.of64) {
+      a.of64[3 * p + 0] = o[0];
+      a.of64[3 * p + 1] = o[1];
+      a.of64[3 * p + 2] = o[2];
+    }
+  } else {
+    float o[3];
+    blendFp32(a, qx, qy, qz, nbr_d2, nbr_idx, n, o);
+    a.ox[ii] = o[0];
+    a.oy[ii] = o[1];
+    a.oz[ii] = o[2];
+    if (a.of64) {
+      a.of64[3 * p + 0] = o[0];
+      a.of64[3 * p + 1] = o[1];
+      a.of64[3 * p + 2] = o[2];
+    }
+  }
+  if (a.assoc) {
+    for (uint32_t j = 0; j < a.assoc_stride; ++j) {
+      a.assoc[p * a.assoc_stride + j] = (static_cast<int>(j) < n - 1) ? nbr_idx[j] : 0xFFFFFFFFu;
+    }
+  }
+  if (a.assoc_cnt) a.assoc_cnt[p] = static_cast<uint8_t>(n - 1 > 255 ? 255 : n - 1);
+}
+
+// Register-resident variants for the K3 kernels: every loop is fully unrolled over the
+// compile-time capacity and guarded by the runtime neighbour count, so that the neighbour
+// arrays are never indexed dynamically (dynamic indexing would push them to local memory).
+template <int KCAP>
+__device__ __forceinline__ void writeResultReg(const DeformArgs& a, uint64_t p, uint64_t ii,
+                                               int precision, float qx, float qy, float qz,
+                                               const float (&nbr_d2)[KCAP],
+                                               const int (&nbr_idx)[KCAP], int n) {
+  // nbr_d2[n - 1] without dynamic indexing: distances ascend, so it is the max of the first n
+  float last_d2 = nbr_d2[0];
+#pragma unroll
+  for (int j = 1; j < KCAP; ++j) {
+    last_d2 = j < n ? fmaxf(last_d2, nbr_d2[j]) : last_d2;
+  }
+  if (precision == 0) {
+    const float d_max_f = __fsqrt_rn(last_d2);
+    const double d_max = static_cast<double>(d_max_f);
+    const bool const_w = (__fsqrt_rn(nbr_d2[0]) == d_max_f) || d_max == 0.0;
+    double wsum = 0.0, acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
+    const double v0 = static_cast<double>(qx), v1 = static_cast<double>(qy),
+                 v2 = static_cast<double>(qz);
+#pragma unroll
+    for (int j = 0; j < KCAP; ++j) {
+      if (j < n - 1) {
+        const int c = nbr_idx[j];
+        const double w =
+            const_w ? 1.0
+                    : __dsub_rn(1.0, __ddiv_rn(static_cast<double>(__fsqrt_rn(nbr_d2[j])), d_max));
+        wsum = __dadd_rn(wsum, w);
+        const double* g = a.ctrl_pos + 3ull * c;
+        const double* T = a.poses + 12ull * c;
+        const double p0 = __dsub_rn(v0, g[0]);
+        const double p1 = __dsub_rn(v1, g[1]);
+        const double p2 = __dsub_rn(v2, g[2]);
+        const double r0 = __dadd_rn(__dadd_rn(__dmul_rn(T[0], p0), __dmul_rn(T[1], p1)), __dmul_rn(T[2], p2));
+        const double r1 = __dadd_rn(__dadd_rn(__dmul_rn(T[3], p0), __dmul_rn(T[4], p1)), __dmul_rn(T[5], p2));
+        const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(T[6], p0), __dmul_rn(T[7], p1)), __dmul_rn(T[8], p2));
+        acc0 = __dadd_rn(acc0, __dmul_rn(w, __dadd_rn(r0, T[9])));
+        acc1 = __dadd_rn(acc1, __dmul_rn(w, __dadd_rn(r1, T[10])));
+        acc2 = __dadd_rn(acc2, __dmul_rn(w, __dadd_rn(r2, T[11])));
+      }
+    }
+    const double o0 = __ddiv_rn(acc0, wsum), o1 = __ddiv_rn(acc1, wsum), o2 = __ddiv_rn(acc2, wsum);
+    a.ox[ii] = __double2float_rn(o0);
+    a.oy[ii] = __double2float_rn(o1);
+    a.oz[ii] = __double2float_rn(o2);
+    if (a.of64) {
+      a.of64[3 * p + 0] = o0;
+      a.of64[3 * p + 1] = o1;
+      a.of64[3 * p + 2] = o2;
+    }
+  } else {
+    const float d_max = __fsqrt_rn(last_d2);
+    const bool const_w = (__fsqrt_rn(nbr_d2[0]) == d_max) || d_max == 0.0f;
+    const float inv_dmax = const_w ? 0.0f : __frcp_rn(d_max);
+    float wsum = 0.f, acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < KCAP; ++j) {
+      if (j < n - 1) {
+        const int c = nbr_idx[j];
+        const float w = const_w ? 1.0f : 1.0f - __fsqrt_rn(nbr_d2[j]) * inv_dmax;
+        wsum += w;
+        const float4* T = reinterpret_cast<const float4*>(a.ctrl_pose_f32 + 16ull * c);
+        const float4 t0 = __ldg(T), t1 = __ldg(T + 1), t2 = __ldg(T + 2), t3 = __ldg(T + 3);
+        const float p0 = qx - t3.x, p1 = qy - t3.y, p2 = qz - t3.z;
+        acc0 += w * (t0.x * p0 + t0.y * p1 + t0.z * p2 + t2.y);
+        acc1 += w * (t0.w * p0 + t1.x * p1 + t1.y * p2 + t2.z);
+        acc2 += w * (t1.z * p0 + t1.w * p1 + t2.x * p2 + t2.w);
+      }
+    }
+    const float o0 = acc0 / wsum, o1 = acc1 / wsum, o2 = acc2 / wsum;
+    a.ox[ii] = o0;
+    a.oy[ii] = o1;
+    a.oz[ii] = o2;
+    if (a.of64) {
+      a.of64[3 * p + 0] = o0;
+      a.of64[3 * p + 1] = o1;
+      a.of64[3 * p + 2] = o2;
+    }
+  }
+  if (a.assoc) {
+#pragma unroll
+    for (int j = 0; j < KCAP; ++j) {
+      if (static_cast<uint32_t>(j) < a.assoc_stride) {
+        a.assoc[p * a.assoc_stride + j] = (j < n - 1) ? static_cast<uint32_t>(nbr_idx[j]) : 0xFFFFFFFFu;
+      }
+    }
+    for (uint32_t j = KCAP; j < a.assoc_stride; ++j) a.assoc[p * a.assoc_stride + j] = 0xFFFFFFFFu;
+  }
+  if (a.assoc_cnt) a.assoc_cnt[p] = static_cast<uint8_t>(n - 1 > 255 ? 255 : n - 1);
+}
+
+}  // namespace dev
+}  // namespace pgmo

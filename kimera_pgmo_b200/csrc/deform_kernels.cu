@@ -13,126 +13,14 @@
 
 #include <cfloat>
 
+#include "deform_device.cuh"
 #include "stdsort_restated.cuh"
 
 namespace pgmo {
 
 namespace {
 
-__device__ __forceinline__ float dist2Exact(float ax, float ay, float az, float bx, float by,
-                                            float bz) {
-  const float dx = __fsub_rn(ax, bx);
-  const float dy = __fsub_rn(ay, by);
-  const float dz = __fsub_rn(az, bz);
-  return __fadd_rn(__fmul_rn(dx, dx), __fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dz, dz)));
-}
-
-__device__ __forceinline__ uint32_t findRun(const uint64_t* __restrict__ run_start,
-                                            uint32_t n_runs, uint64_t position) {
-  // last r with run_start[r] <= position
-  uint32_t lo = 0, hi = n_runs;
-  while (hi - lo > 1) {
-    const uint32_t mid = (lo + hi) >> 1;
-    if (__ldg(run_start + mid) <= position) lo = mid;
-    else hi = mid;
-  }
-  return lo;
-}
-
-// interpPoint's blend in the reference's arithmetic.  nbr_d2 / nbr_idx: n neighbours ascending.
-__device__ __forceinline__ void blendFp64(const DeformArgs& a, float qx, float qy, float qz,
-                                          const float* nbr_d2, const int* nbr_idx, int n,
-                                          double out[3]) {
-  const float d_max_f = __fsqrt_rn(nbr_d2[n - 1]);
-  const double d_max = static_cast<double>(d_max_f);
-  const bool const_w = (__fsqrt_rn(nbr_d2[0]) == d_max_f) || d_max == 0.0;
-  double wsum = 0.0, acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
-  const double v0 = static_cast<double>(qx), v1 = static_cast<double>(qy),
-               v2 = static_cast<double>(qz);
-  for (int j = 0; j < n - 1; ++j) {
-    const int c = nbr_idx[j];
-    const double w =
-        const_w ? 1.0
-                : __dsub_rn(1.0, __ddiv_rn(static_cast<double>(__fsqrt_rn(nbr_d2[j])), d_max));
-    wsum = __dadd_rn(wsum, w);
-    const double* g = a.ctrl_pos + 3ull * c;
-    const double* T = a.poses + 12ull * c;
-    const double p0 = __dsub_rn(v0, g[0]);
-    const double p1 = __dsub_rn(v1, g[1]);
-    const double p2 = __dsub_rn(v2, g[2]);
-    const double r0 = __dadd_rn(__dadd_rn(__dmul_rn(T[0], p0), __dmul_rn(T[1], p1)), __dmul_rn(T[2], p2));
-    const double r1 = __dadd_rn(__dadd_rn(__dmul_rn(T[3], p0), __dmul_rn(T[4], p1)), __dmul_rn(T[5], p2));
-    const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(T[6], p0), __dmul_rn(T[7], p1)), __dmul_rn(T[8], p2));
-    acc0 = __dadd_rn(acc0, __dmul_rn(w, __dadd_rn(r0, T[9])));
-    acc1 = __dadd_rn(acc1, __dmul_rn(w, __dadd_rn(r1, T[10])));
-    acc2 = __dadd_rn(acc2, __dmul_rn(w, __dadd_rn(r2, T[11])));
-  }
-  out[0] = __ddiv_rn(acc0, wsum);
-  out[1] = __ddiv_rn(acc1, wsum);
-  out[2] = __ddiv_rn(acc2, wsum);
-}
-
-// FP32 mode: same neighbours, same weight formula, float arithmetic (FMA allowed).
-__device__ __forceinline__ void blendFp32(const DeformArgs& a, float qx, float qy, float qz,
-                                          const float* nbr_d2, const int* nbr_idx, int n,
-                                          float out[3]) {
-  const float d_max = __fsqrt_rn(nbr_d2[n - 1]);
-  const bool const_w = (__fsqrt_rn(nbr_d2[0]) == d_max) || d_max == 0.0f;
-  const float inv_dmax = const_w ? 0.0f : __frcp_rn(d_max);
-  float wsum = 0.f, acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
-  for (int j = 0; j < n - 1; ++j) {
-    const int c = nbr_idx[j];
-    const float w = const_w ? 1.0f : 1.0f - __fsqrt_rn(nbr_d2[j]) * inv_dmax;
-    wsum += w;
-    const float4* T = reinterpret_cast<const float4*>(a.ctrl_pose_f32 + 16ull * c);
-    const float4 t0 = __ldg(T), t1 = __ldg(T + 1), t2 = __ldg(T + 2), t3 = __ldg(T + 3);
-    // layout: R0..R8, t0..t2, g0..g2, pad
-    const float p0 = qx - t3.x, p1 = qy - t3.y, p2 = qz - t3.z;
-    const float r0 = t0.x * p0 + t0.y * p1 + t0.z * p2 + t2.y;
-    const float r1 = t0.w * p0 + t1.x * p1 + t1.y * p2 + t2.z;
-    const float r2 = t1.z * p0 + t1.w * p1 + t2.x * p2 + t2.w;
-    acc0 += w * r0;
-    acc1 += w * r1;
-    acc2 += w * r2;
-  }
-  out[0] = acc0 / wsum;
-  out[1] = acc1 / wsum;
-  out[2] = acc2 / wsum;
-}
-
-__device__ __forceinline__ void writeResult(const DeformArgs& a, uint64_t p, uint64_t ii,
-                                            int precision, float qx, float qy, float qz,
-                                            const float* nbr_d2, const int* nbr_idx, int n) {
-  if (precision == 0) {
-    double o[3];
-    blendFp64(a, qx, qy, qz, nbr_d2, nbr_idx, n, o);
-    a.ox[ii] = __double2float_rn(o[0]);
-    a.oy[ii] = __double2float_rn(o[1]);
-    a.oz[ii] = __double2float_rn(o[2]);
-    if (a.of64) {
-      a.of64[3 * p + 0] = o[0];
-      a.of64[3 * p + 1] = o[1];
-      a.of64[3 * p + 2] = o[2];
-    }
-  } else {
-    float o[3];
-    blendFp32(a, qx, qy, qz, nbr_d2, nbr_idx, n, o);
-    a.ox[ii] = o[0];
-    a.oy[ii] = o[1];
-    a.oz[ii] = o[2];
-    if (a.of64) {
-      a.of64[3 * p + 0] = o[0];
-      a.of64[3 * p + 1] = o[1];
-      a.of64[3 * p + 2] = o[2];
-    }
-  }
-  if (a.assoc) {
-    for (uint32_t j = 0; j < a.assoc_stride; ++j) {
-      a.assoc[p * a.assoc_stride + j] = (static_cast<int>(j) < n - 1) ? nbr_idx[j] : 0xFFFFFFFFu;
-    }
-  }
-  if (a.assoc_cnt) a.assoc_cnt[p] = static_cast<uint8_t>(n - 1 > 255 ? 255 : n - 1);
-}
+using namespace dev;
 
 // ------------------------------------------------------------------------------------------
 // K1
@@ -221,7 +109,7 @@ deformKnnBlendKernel(const DeformArgs a, const int precision) {
     atomicAdd(a.counters, 1ull);
     return;
   }
-  writeResult(a, p, ii, precision, qx, qy, qz, best_d, best_i, n);
+  writeResultReg<KCAP>(a, p, ii, precision, qx, qy, qz, best_d, best_i, n);
   a.status[p] = kStatusDone;
 }
 
@@ -448,15 +336,39 @@ deformResolveKernel(const DeformArgs a, const ResolveArgs ra, const int precisio
   const uint32_t warp = blockIdx.x * kResolveWarpsPerBlock + warp_in_block;
   // slab per warp: cand_cap entries + room for the split views used by large k
   CandEntry* cand = ra.scratch + static_cast<uint64_t>(warp) * ra.cand_cap * 2;
-  const uint64_t n_chunks = (a.n_local + 31) / 32;
+  // scan the status bytes 16 per lane (512 positions per warp step); status is 16-byte aligned
+  // when the caller's buffer is (cudaMalloc / torch allocations are), else fall back to bytes
+  const bool aligned = (reinterpret_cast<uintptr_t>(a.status) & 15) == 0;
+  const uint64_t n_chunks = (a.n_local + 511) / 512;
   for (uint64_t chunk = warp; chunk < n_chunks; chunk += ra.n_warps) {
-    const uint64_t p = chunk * 32 + lane;
-    const uint8_t st = p < a.n_local ? a.status[p] : kStatusSkipped;
-    unsigned todo = __ballot_sync(0xFFFFFFFFu, st == kStatusNeedsTie);
+    const uint64_t p0 = chunk * 512 + static_cast<uint64_t>(lane) * 16;
+    uint32_t flags = 0;  // bit i: position p0 + i needs the resolver
+    if (aligned && p0 + 16 <= a.n_local) {
+      const uint4 v = *reinterpret_cast<const uint4*>(a.status + p0);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          if (((w[q] >> (8 * b)) & 0xFFu) == kStatusNeedsTie) flags |= 1u << (4 * q + b);
+        }
+      }
+    } else {
+      for (int i = 0; i < 16; ++i) {
+        if (p0 + i < a.n_local && a.status[p0 + i] == kStatusNeedsTie) flags |= 1u << i;
+      }
+    }
+    unsigned todo = __ballot_sync(0xFFFFFFFFu, flags != 0);
     while (todo) {
-      const int b = __ffs(todo) - 1;
+      const int src = __ffs(todo) - 1;
       todo &= todo - 1;
-      resolveOne(a, ra, s_levels[warp_in_block], cand, chunk * 32 + b, precision, lane);
+      uint32_t f = __shfl_sync(0xFFFFFFFFu, flags, src);
+      while (f) {
+        const int i = __ffs(f) - 1;
+        f &= f - 1;
+        resolveOne(a, ra, s_levels[warp_in_block], cand,
+                   chunk * 512 + static_cast<uint64_t>(src) * 16 + i, precision, lane);
+      }
     }
   }
 }

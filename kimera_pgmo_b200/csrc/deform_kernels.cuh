@@ -52,6 +52,31 @@ struct DeformArgs {
   unsigned long long* counters;  // [0] = vertices sent to the resolver
 };
 
+// per-run uniform grid over the run's alive control points (deform_grid.cu)
+constexpr int kGridMaxCells = 1024;
+struct RunGridDev {
+  float ox, oy, oz;       // grid origin = bounding-box minimum of the alive set
+  float cell, inv_cell;   // cell edge
+  int nx, ny, nz;         // nx * ny * nz <= kGridMaxCells, x fastest
+  uint32_t point_offset;  // first slot of this run in GridArgs::points
+  uint32_t n_alive;
+  float r0;               // first search radius: ~1.25 x expected (K+1)-th neighbour distance
+};
+// up to kDeformChunk consecutive local positions of one run (one CTA of the grid kernel)
+constexpr uint32_t kDeformChunk = 2048;
+struct WorkItem {
+  uint64_t start;  // local position
+  uint32_t run;
+  uint32_t count;
+};
+struct GridArgs {
+  const RunGridDev* grids;  // n_runs
+  const float4* points;     // alive points sorted by cell: x, y, z, control index (int bits)
+  const uint32_t* cells;    // n_runs x (kGridMaxCells + 1) cell starts
+  // search-box schedule, in units of the run's r0 / cell: first radius, then growth per round
+  float r_scale, r_grow_mul, r_grow_add;
+};
+
 struct CandEntry {
   float dist;
   int idx;
@@ -73,6 +98,16 @@ cudaError_t launchStampStretches(const uint64_t* stamps, const uint64_t* subset,
 // K3: windowed exact top-(k+2) + blend.  precision: 0 = FP64 blend, 1 = FP32 blend.
 cudaError_t launchDeformKnnBlend(const DeformArgs& args, int precision, uint32_t max_k,
                                  cudaStream_t stream);
+
+// K2b: one CTA per run buckets the run's alive control points into its grid.  point_offset[r] =
+// first slot of run r (prefix sum of the window sizes hi - lo).
+cudaError_t launchBuildRunGrids(uint32_t n_runs, const uint4* run_info, const float4* ctrl_f4,
+                                const uint32_t* point_offset, RunGridDev* grids,
+                                float4* grid_points, uint32_t* grid_cells, cudaStream_t stream);
+// K3 over the per-run grids: same result as launchDeformKnnBlend, ~8x fewer candidates.
+cudaError_t launchDeformKnnBlendGrid(const DeformArgs& args, const GridArgs& gargs,
+                                     const WorkItem* items, uint32_t n_items, int precision,
+                                     uint32_t max_k, cudaStream_t stream);
 
 // K4: PCL-order resolution of the vertices flagged kStatusNeedsTie.
 cudaError_t launchDeformResolve(const DeformArgs& args, const ResolveArgs& rargs, int precision,

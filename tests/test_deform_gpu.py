@@ -117,6 +117,27 @@ def test_config_a_parity(capi, oracle, tol_t, invalid):
     assert ref["processed"].all()
 
 
+@pytest.mark.parametrize("spread", [(6.0, 5.0), (40.0, 2.0), (0.5, 30.0)])
+def test_search_modes_agree(capi, oracle, spread):
+    """Per-run spatial grids (default) and brute force over the window are bit-identical, also
+    when vertices lie far outside / deep inside the control-point cloud."""
+    case = synth.deformation_case(150_000, 3_000, vertex_spread=spread[0], ctrl_spread=spread[1],
+                                  seed=17)
+    outs = []
+    for mode in (0, 1):
+        h = capi.DeformHandle(0)
+        h.set_search_mode(mode)
+        _set(h, case)
+        outs.append(h.deform_points(case["x"], case["y"], case["z"], case["stamps"], k=4,
+                                    tol_t=10.0, want_f64=True, want_assoc=True))
+        h.close()
+    for key in ("x", "y", "z", "f64", "assoc", "assoc_cnt", "processed"):
+        np.testing.assert_array_equal(outs[0][key], outs[1][key])
+    ref = oracle.deform_points(case["x"], case["y"], case["z"], case["stamps"], case["ctrl_xyz"],
+                               case["ctrl_stamps"], case["valid"], case["poses"], k=4, tol_t=10.0)
+    _compare(outs[1], ref)
+
+
 def test_fp32_mode(capi, oracle):
     case = synth.deformation_case(200_000, 2_000)
     gpu, ref = _run_both(capi, oracle, case, 4, 10.0, precision=1)
