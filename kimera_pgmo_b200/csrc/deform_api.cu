@@ -53,6 +53,10 @@ struct pgmo_deform {
   DevBuf<uint32_t> d_grid_cells;
   DevBuf<uint32_t> d_grid_offsets;
   DevBuf<WorkItem> d_items;
+  std::vector<WorkItem> h_items;
+  cudaStream_t s_in = nullptr, s_out = nullptr;  // copy streams of the pipelined host entry point
+  static constexpr int kPipe = 8;
+  cudaEvent_t ev_in[kPipe] = {}, ev_done[kPipe] = {};
   float r_scale = 1.0f, r_grow_mul = 1.5f, r_grow_add = 1.0f;
   uint32_t n_items = 0;
   uint64_t items_first = ~0ull, items_n = 0, items_sched_builds = ~0ull;
@@ -233,6 +237,12 @@ int pgmo_deform_create(int device, pgmo_deform_t** out) {
   if (const char* e = std::getenv("PGMO_R_SCALE")) h->r_scale = static_cast<float>(atof(e));
   if (const char* e = std::getenv("PGMO_R_GROW_MUL")) h->r_grow_mul = static_cast<float>(atof(e));
   if (const char* e = std::getenv("PGMO_R_GROW_ADD")) h->r_grow_add = static_cast<float>(atof(e));
+  cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking);
+  for (int i = 0; i < pgmo_deform::kPipe; ++i) {
+    cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming);
+  }
   for (auto& e : h->ev) {
     if (cudaEventCreate(&e) != cudaSuccess) {
       setLastError("cudaEventCreate failed");
@@ -254,6 +264,12 @@ void pgmo_deform_destroy(pgmo_deform_t* h) {
   for (auto& e : h->ev) {
     if (e) cudaEventDestroy(e);
   }
+  for (int i = 0; i < pgmo_deform::kPipe; ++i) {
+    if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
+    if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
+  }
+  if (h->s_in) cudaStreamDestroy(h->s_in);
+  if (h->s_out) cudaStreamDestroy(h->s_out);
   delete h;
 }
 
@@ -454,12 +470,60 @@ int pgmo_deform_schedule_info(pgmo_deform_t* h, uint64_t* n_runs, uint64_t capac
   return PGMO_OK;
 }
 
-int pgmo_deform_run_device(pgmo_deform_t* h, uint64_t first_position, uint64_t n_local,
+}  // extern "C"
+
+// Work items of the grid kernel for the slab [first_position, first_position + n_local):
+// <= kDeformChunk consecutive positions of one run each, cached per slab.
+static int ensureItems(pgmo_deform_t* h, uint64_t first_position, uint64_t n_local,
+                     cudaStream_t st) {
+  if (h->items_first != first_position || h->items_n != n_local ||
+      h->items_sched_builds != h->sched_builds) {
+    std::vector<WorkItem> items;
+    const auto& runs = h->sched.runs;
+    size_t r = 0;
+    {
+      size_t lo = 0, hi = runs.size();
+      while (hi - lo > 1) {
+        const size_t mid = (lo + hi) / 2;
+        if (runs[mid].first_position <= first_position) lo = mid;
+        else hi = mid;
+      }
+      r = lo;
+    }
+    const uint64_t slab_end = first_position + n_local;
+    for (; r < runs.size() && runs[r].first_position < slab_end; ++r) {
+      const uint64_t run_end =
+          r + 1 < runs.size() ? runs[r + 1].first_position : h->sched.total_positions;
+      uint64_t b = std::max<uint64_t>(runs[r].first_position, first_position);
+      const uint64_t e = std::min<uint64_t>(run_end, slab_end);
+      for (; b < e; b += kDeformChunk) {
+        WorkItem it;
+        it.start = b - first_position;
+        it.run = static_cast<uint32_t>(r);
+        it.count = static_cast<uint32_t>(std::min<uint64_t>(kDeformChunk, e - b));
+        items.push_back(it);
+      }
+    }
+    PGMO_TRY(h->d_items.reserve(items.size() + 1));
+    PGMO_CUDA(cudaMemcpyAsync(h->d_items.ptr, items.data(), items.size() * sizeof(WorkItem),
+                              cudaMemcpyHostToDevice, st));
+    PGMO_CUDA(cudaStreamSynchronize(st));
+    h->n_items = static_cast<uint32_t>(items.size());
+    h->h_items.swap(items);
+    h->items_first = first_position;
+    h->items_n = n_local;
+    h->items_sched_builds = h->sched_builds;
+  }
+  return PGMO_OK;
+}
+
+static int runDeviceRange(pgmo_deform_t* h, uint64_t first_position, uint64_t n_local,
                            const float* d_x, const float* d_y, const float* d_z,
                            const uint64_t* d_subset_idx, int precision, float* d_out_x,
                            float* d_out_y, float* d_out_z, double* d_out_xyz_f64,
                            uint32_t* d_assoc, uint32_t assoc_stride, uint8_t* d_assoc_cnt,
-                           uint8_t* d_processed, uint64_t* n_resolved, void* stream) {
+                           uint8_t* d_processed, uint64_t* n_resolved, void* stream,
+                          uint64_t range_begin, uint64_t range_end) {
   PGMO_CHECK_ARG(h != nullptr);
   PGMO_CHECK_ARG(precision == PGMO_PRECISION_FP64 || precision == PGMO_PRECISION_FP32);
   PGMO_TRY(ensureDevice(h->device));
@@ -480,7 +544,9 @@ int pgmo_deform_run_device(pgmo_deform_t* h, uint64_t first_position, uint64_t n
     status = h->d_status.ptr;
   }
   PGMO_TRY(h->d_counters.reserve(8));
-  PGMO_CUDA(cudaMemsetAsync(h->d_counters.ptr, 0, 8 * sizeof(unsigned long long), st));
+  if (range_begin == 0) {
+    PGMO_CUDA(cudaMemsetAsync(h->d_counters.ptr, 0, 8 * sizeof(unsigned long long), st));
+  }
 
   DeformArgs a;
   a.first_position = first_position;
@@ -514,47 +580,12 @@ int pgmo_deform_run_device(pgmo_deform_t* h, uint64_t first_position, uint64_t n
   ra.cand_cap = h->sched.max_k + 2 + h->sched.max_leaf_points + 1;
   PGMO_TRY(h->d_scratch.reserve(static_cast<size_t>(ra.n_warps) * ra.cand_cap * 2));
   ra.scratch = h->d_scratch.ptr;
+  ra.scan_begin = range_begin;
+  ra.scan_end = range_end;
 
   if (h->profiling) PGMO_CUDA(cudaEventRecord(h->ev[0], st));
   if (h->use_grid) {
-    // work items: <= kDeformChunk consecutive positions of one run each (cached per slab)
-    if (h->items_first != first_position || h->items_n != n_local ||
-        h->items_sched_builds != h->sched_builds) {
-      std::vector<WorkItem> items;
-      const auto& runs = h->sched.runs;
-      size_t r = 0;
-      {
-        size_t lo = 0, hi = runs.size();
-        while (hi - lo > 1) {
-          const size_t mid = (lo + hi) / 2;
-          if (runs[mid].first_position <= first_position) lo = mid;
-          else hi = mid;
-        }
-        r = lo;
-      }
-      const uint64_t slab_end = first_position + n_local;
-      for (; r < runs.size() && runs[r].first_position < slab_end; ++r) {
-        const uint64_t run_end =
-            r + 1 < runs.size() ? runs[r + 1].first_position : h->sched.total_positions;
-        uint64_t b = std::max<uint64_t>(runs[r].first_position, first_position);
-        const uint64_t e = std::min<uint64_t>(run_end, slab_end);
-        for (; b < e; b += kDeformChunk) {
-          WorkItem it;
-          it.start = b - first_position;
-          it.run = static_cast<uint32_t>(r);
-          it.count = static_cast<uint32_t>(std::min<uint64_t>(kDeformChunk, e - b));
-          items.push_back(it);
-        }
-      }
-      PGMO_TRY(h->d_items.reserve(items.size() + 1));
-      PGMO_CUDA(cudaMemcpyAsync(h->d_items.ptr, items.data(), items.size() * sizeof(WorkItem),
-                                cudaMemcpyHostToDevice, st));
-      PGMO_CUDA(cudaStreamSynchronize(st));  // `items` dies at scope exit
-      h->n_items = static_cast<uint32_t>(items.size());
-      h->items_first = first_position;
-      h->items_n = n_local;
-      h->items_sched_builds = h->sched_builds;
-    }
+    PGMO_TRY(ensureItems(h, first_position, n_local, st));
     GridArgs ga;
     ga.grids = h->d_grids.ptr;
     ga.points = h->d_grid_points.ptr;
@@ -563,7 +594,16 @@ int pgmo_deform_run_device(pgmo_deform_t* h, uint64_t first_position, uint64_t n
     ga.r_grow_mul = h->r_grow_mul;
     ga.r_grow_add = h->r_grow_add;
     if (h->profiling) PGMO_CUDA(cudaEventRecord(h->ev[0], st));
-    PGMO_CUDA(launchDeformKnnBlendGrid(a, ga, h->d_items.ptr, h->n_items, precision,
+    // the requested range must start and end on work-item boundaries
+    uint32_t i0 = 0, i1 = h->n_items;
+    if (range_begin != 0 || range_end != n_local) {
+      const auto& it = h->h_items;
+      i0 = static_cast<uint32_t>(std::lower_bound(it.begin(), it.end(), range_begin,
+               [](const WorkItem& w, uint64_t v) { return w.start < v; }) - it.begin());
+      i1 = static_cast<uint32_t>(std::lower_bound(it.begin(), it.end(), range_end,
+               [](const WorkItem& w, uint64_t v) { return w.start < v; }) - it.begin());
+    }
+    PGMO_CUDA(launchDeformKnnBlendGrid(a, ga, h->d_items.ptr + i0, i1 - i0, precision,
                                        h->sched.max_k, st));
   } else {
     PGMO_CUDA(launchDeformKnnBlend(a, precision, h->sched.max_k, st));
@@ -583,6 +623,19 @@ int pgmo_deform_run_device(pgmo_deform_t* h, uint64_t first_position, uint64_t n
     *n_resolved = h->h_counters.ptr[0];
   }
   return PGMO_OK;
+}
+
+extern "C" {
+
+int pgmo_deform_run_device(pgmo_deform_t* h, uint64_t first_position, uint64_t n_local,
+                           const float* d_x, const float* d_y, const float* d_z,
+                           const uint64_t* d_subset_idx, int precision, float* d_out_x,
+                           float* d_out_y, float* d_out_z, double* d_out_xyz_f64,
+                           uint32_t* d_assoc, uint32_t assoc_stride, uint8_t* d_assoc_cnt,
+                           uint8_t* d_processed, uint64_t* n_resolved, void* stream) {
+  return runDeviceRange(h, first_position, n_local, d_x, d_y, d_z, d_subset_idx, precision,
+                        d_out_x, d_out_y, d_out_z, d_out_xyz_f64, d_assoc, assoc_stride,
+                        d_assoc_cnt, d_processed, n_resolved, stream, 0, n_local);
 }
 
 int pgmo_deform_set_search_mode(pgmo_deform_t* h, int mode) {
@@ -650,27 +703,72 @@ int pgmo_deform_points(pgmo_deform_t* h, uint64_t n_v, const float* x, const flo
   }
 
   int rc;
+  bool xyz_uploaded = false;
   if (stamps_ns) {
-    // stamps first: K1 and the host-side schedule overlap with the x/y/z upload below
+    // stamps first: K1 and the host-side window schedule only need them
     PGMO_TRY(h->d_vstamps.reserve(n_v));
     PGMO_CUDA(cudaMemcpyAsync(h->d_vstamps.ptr, stamps_ns, n_v * sizeof(uint64_t),
                               cudaMemcpyHostToDevice, st));
     std::vector<uint64_t> s_stamp, s_len;
     PGMO_TRY(stampStretches(h, h->d_vstamps.ptr, d_subset, n_pos, &s_stamp, &s_len, st));
-    PGMO_CUDA(cudaMemcpyAsync(h->d_x.ptr, x, n_v * sizeof(float), cudaMemcpyHostToDevice, st));
-    PGMO_CUDA(cudaMemcpyAsync(h->d_y.ptr, y, n_v * sizeof(float), cudaMemcpyHostToDevice, st));
-    PGMO_CUDA(cudaMemcpyAsync(h->d_z.ptr, z, n_v * sizeof(float), cudaMemcpyHostToDevice, st));
     rc = pgmo_deform_build_schedule(h, s_stamp.size(), s_stamp.data(), s_len.data(), n_pos, k,
                                     tol_t);
   } else {
-    PGMO_CUDA(cudaMemcpyAsync(h->d_x.ptr, x, n_v * sizeof(float), cudaMemcpyHostToDevice, st));
-    PGMO_CUDA(cudaMemcpyAsync(h->d_y.ptr, y, n_v * sizeof(float), cudaMemcpyHostToDevice, st));
-    PGMO_CUDA(cudaMemcpyAsync(h->d_z.ptr, z, n_v * sizeof(float), cudaMemcpyHostToDevice, st));
     rc = pgmo_deform_build_schedule(h, 0, nullptr, nullptr, n_pos, k, tol_t);
   }
   if (rc != PGMO_OK) {
     cudaStreamSynchronize(st);
     return rc;
+  }
+  bool any_skip = false;
+  for (const ScheduleRun& run : h->sched.runs) any_skip = any_skip || run.skip;
+
+  // Pipelined path (the common full-mesh case): vertex slabs are uploaded on one copy stream,
+  // deformed on the compute stream and downloaded on a second copy stream, so that H2D, kernels
+  // and D2H overlap (PCIe is full duplex).  Slab boundaries are work-item boundaries.
+  if (!subset_idx && !any_skip && h->use_grid && !out_xyz_f64 && !assoc && !assoc_cnt &&
+      n_pos >= (1u << 18) && h->s_in && h->s_out) {
+    PGMO_TRY(h->d_status.reserve(n_pos));
+    PGMO_TRY(ensureItems(h, 0, n_pos, st));
+    const int n_slabs = pgmo_deform::kPipe;
+    uint64_t begin = 0;
+    for (int sl = 0; sl < n_slabs && begin < n_pos; ++sl) {
+      uint64_t end = n_pos;
+      if (sl + 1 < n_slabs) {
+        // first item starting at or after the ideal cut
+        const uint64_t want = n_pos * static_cast<uint64_t>(sl + 1) / n_slabs;
+        const auto it = std::lower_bound(h->h_items.begin(), h->h_items.end(), want,
+                                         [](const WorkItem& w, uint64_t v) { return w.start < v; });
+        end = it == h->h_items.end() ? n_pos : it->start;
+      }
+      if (end <= begin) continue;
+      const uint64_t cnt = end - begin;
+      PGMO_CUDA(cudaMemcpyAsync(h->d_x.ptr + begin, x + begin, cnt * sizeof(float), cudaMemcpyHostToDevice, h->s_in));
+      PGMO_CUDA(cudaMemcpyAsync(h->d_y.ptr + begin, y + begin, cnt * sizeof(float), cudaMemcpyHostToDevice, h->s_in));
+      PGMO_CUDA(cudaMemcpyAsync(h->d_z.ptr + begin, z + begin, cnt * sizeof(float), cudaMemcpyHostToDevice, h->s_in));
+      PGMO_CUDA(cudaEventRecord(h->ev_in[sl], h->s_in));
+      PGMO_CUDA(cudaStreamWaitEvent(st, h->ev_in[sl], 0));
+      PGMO_TRY(runDeviceRange(h, 0, n_pos, h->d_x.ptr, h->d_y.ptr, h->d_z.ptr, nullptr, precision,
+                              h->d_ox.ptr, h->d_oy.ptr, h->d_oz.ptr, nullptr, nullptr, 0, nullptr,
+                              h->d_status.ptr, nullptr, st, begin, end));
+      PGMO_CUDA(cudaEventRecord(h->ev_done[sl], st));
+      PGMO_CUDA(cudaStreamWaitEvent(h->s_out, h->ev_done[sl], 0));
+      PGMO_CUDA(cudaMemcpyAsync(out_x + begin, h->d_ox.ptr + begin, cnt * sizeof(float), cudaMemcpyDeviceToHost, h->s_out));
+      PGMO_CUDA(cudaMemcpyAsync(out_y + begin, h->d_oy.ptr + begin, cnt * sizeof(float), cudaMemcpyDeviceToHost, h->s_out));
+      PGMO_CUDA(cudaMemcpyAsync(out_z + begin, h->d_oz.ptr + begin, cnt * sizeof(float), cudaMemcpyDeviceToHost, h->s_out));
+      if (processed) {
+        PGMO_CUDA(cudaMemcpyAsync(processed + begin, h->d_status.ptr + begin, cnt, cudaMemcpyDeviceToHost, h->s_out));
+      }
+      begin = end;
+    }
+    PGMO_CUDA(cudaStreamSynchronize(h->s_out));
+    PGMO_CUDA(cudaStreamSynchronize(st));
+    return PGMO_OK;
+  }
+  if (!xyz_uploaded) {
+    PGMO_CUDA(cudaMemcpyAsync(h->d_x.ptr, x, n_v * sizeof(float), cudaMemcpyHostToDevice, st));
+    PGMO_CUDA(cudaMemcpyAsync(h->d_y.ptr, y, n_v * sizeof(float), cudaMemcpyHostToDevice, st));
+    PGMO_CUDA(cudaMemcpyAsync(h->d_z.ptr, z, n_v * sizeof(float), cudaMemcpyHostToDevice, st));
   }
 
   double* d_f64 = nullptr;
@@ -694,8 +792,6 @@ int pgmo_deform_points(pgmo_deform_t* h, uint64_t n_v, const float* x, const flo
                                   precision, h->d_ox.ptr, h->d_oy.ptr, h->d_oz.ptr, d_f64, d_assoc,
                                   assoc_stride, d_cnt, h->d_status.ptr, nullptr, st));
 
-  bool any_skip = false;
-  for (const ScheduleRun& run : h->sched.runs) any_skip = any_skip || run.skip;
   if (!subset_idx && !any_skip) {
     PGMO_CUDA(cudaMemcpyAsync(out_x, h->d_ox.ptr, n_v * sizeof(float), cudaMemcpyDeviceToHost, st));
     PGMO_CUDA(cudaMemcpyAsync(out_y, h->d_oy.ptr, n_v * sizeof(float), cudaMemcpyDeviceToHost, st));

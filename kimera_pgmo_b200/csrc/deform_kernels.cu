@@ -339,11 +339,12 @@ deformResolveKernel(const DeformArgs a, const ResolveArgs ra, const int precisio
   // scan the status bytes 16 per lane (512 positions per warp step); status is 16-byte aligned
   // when the caller's buffer is (cudaMalloc / torch allocations are), else fall back to bytes
   const bool aligned = (reinterpret_cast<uintptr_t>(a.status) & 15) == 0;
-  const uint64_t n_chunks = (a.n_local + 511) / 512;
-  for (uint64_t chunk = warp; chunk < n_chunks; chunk += ra.n_warps) {
+  const uint64_t first_chunk = ra.scan_begin / 512;
+  const uint64_t n_chunks = (ra.scan_end + 511) / 512;
+  for (uint64_t chunk = first_chunk + warp; chunk < n_chunks; chunk += ra.n_warps) {
     const uint64_t p0 = chunk * 512 + static_cast<uint64_t>(lane) * 16;
     uint32_t flags = 0;  // bit i: position p0 + i needs the resolver
-    if (aligned && p0 + 16 <= a.n_local) {
+    if (aligned && p0 >= ra.scan_begin && p0 + 16 <= ra.scan_end) {
       const uint4 v = *reinterpret_cast<const uint4*>(a.status + p0);
       const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -355,7 +356,10 @@ deformResolveKernel(const DeformArgs a, const ResolveArgs ra, const int precisio
       }
     } else {
       for (int i = 0; i < 16; ++i) {
-        if (p0 + i < a.n_local && a.status[p0 + i] == kStatusNeedsTie) flags |= 1u << i;
+        if (p0 + i >= ra.scan_begin && p0 + i < ra.scan_end &&
+            a.status[p0 + i] == kStatusNeedsTie) {
+          flags |= 1u << i;
+        }
       }
     }
     unsigned todo = __ballot_sync(0xFFFFFFFFu, flags != 0);

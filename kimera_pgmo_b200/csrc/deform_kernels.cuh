@@ -86,6 +86,8 @@ struct ResolveArgs {
   CandEntry* scratch;        // one slab of cand_cap entries per resident warp
   uint32_t cand_cap;
   uint32_t n_warps;          // resident warps (grid is persistent)
+  uint64_t scan_begin;       // local positions [scan_begin, scan_end) are scanned for flags
+  uint64_t scan_end;
 };
 
 // K1: boundaries of equal-stamp stretches.  Appends (position, stamp) of every position whose
