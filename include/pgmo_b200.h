@@ -88,9 +88,10 @@ int pgmo_deform_set_controls_device(pgmo_deform_t* h, uint64_t n_c, const double
 int pgmo_deform_update_poses(pgmo_deform_t* h, const double* poses12);
 int pgmo_deform_update_poses_device(pgmo_deform_t* h, const double* d_poses12, void* stream);
 
-/* Candidate search of the knn kernel: 1 (default) = per-run spatial grids over the alive control
- * points, built once per cached window schedule; 0 = brute force over the whole time window.
- * Both give bit-identical results (tests/test_deform_gpu.py::test_search_modes_agree). */
+/* Candidate search of the knn kernel: 1 (default) = bucket-ordered candidate lists over each
+ * run's alive control points (grid walk for alive sets > 512); 2 = grid walk only (per-run uniform
+ * grids, built once per cached window schedule); 0 = brute force over the whole time window.
+ * All give bit-identical results (tests/test_deform_gpu.py::test_search_modes_agree). */
 int pgmo_deform_set_search_mode(pgmo_deform_t* h, int mode);
 
 /* Optional kernel timing for roofline reporting: when enabled, pgmo_deform_run_device brackets

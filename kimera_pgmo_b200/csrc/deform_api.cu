@@ -47,7 +47,9 @@ struct pgmo_deform {
   DevBuf<RunFrameDev> d_run_frame;
   // per-run spatial grids over the alive control points (built with the schedule)
   bool use_grid = false;
-  int grid_mode = 1;  // 0 = brute force over the window, 1 = per-run grids
+  int grid_mode = 1;  // 0 = brute force over the window, 1 = bucket-ordered lists (+ grid walk
+                      // for alive sets > kSortedMaxPoints), 2 = grid walk only
+  uint64_t widest_window = 0;
   DevBuf<RunGridDev> d_grids;
   DevBuf<float4> d_grid_points;
   DevBuf<uint32_t> d_grid_cells;
@@ -142,7 +144,8 @@ int uploadSchedule(pgmo_deform_t* h, cudaStream_t st) {
     }
   }
   offsets[n_runs] = static_cast<uint32_t>(total_slots);
-  if (h->grid_mode == 1 && n_runs > 0 && widest > 48 && total_slots < (1ull << 28)) {
+  h->widest_window = widest;
+  if (h->grid_mode != 0 && n_runs > 0 && widest > 48 && total_slots < (1ull << 28)) {
     PGMO_TRY(h->d_grids.reserve(n_runs));
     PGMO_TRY(h->d_grid_points.reserve(total_slots + 1));
     PGMO_TRY(h->d_grid_cells.reserve(n_runs * static_cast<size_t>(kGridMaxCells + 1)));
@@ -603,8 +606,17 @@ static int runDeviceRange(pgmo_deform_t* h, uint64_t first_position, uint64_t n_
       i1 = static_cast<uint32_t>(std::lower_bound(it.begin(), it.end(), range_end,
                [](const WorkItem& w, uint64_t v) { return w.start < v; }) - it.begin());
     }
-    PGMO_CUDA(launchDeformKnnBlendGrid(a, ga, h->d_items.ptr + i0, i1 - i0, precision,
-                                       h->sched.max_k, st));
+    if (h->grid_mode == 1) {
+      PGMO_CUDA(launchDeformKnnBlendSorted(a, ga, h->d_items.ptr + i0, i1 - i0, precision,
+                                           h->sched.max_k, st));
+      if (h->widest_window > static_cast<uint64_t>(kSortedMaxPoints)) {
+        PGMO_CUDA(launchDeformKnnBlendGrid(a, ga, h->d_items.ptr + i0, i1 - i0, precision,
+                                           h->sched.max_k, kSortedMaxPoints, st));
+      }
+    } else {
+      PGMO_CUDA(launchDeformKnnBlendGrid(a, ga, h->d_items.ptr + i0, i1 - i0, precision,
+                                         h->sched.max_k, 0, st));
+    }
   } else {
     PGMO_CUDA(launchDeformKnnBlend(a, precision, h->sched.max_k, st));
   }
@@ -617,10 +629,14 @@ static int runDeviceRange(pgmo_deform_t* h, uint64_t first_position, uint64_t n_
 
   if (n_resolved) {
     PGMO_TRY(h->h_counters.reserve(8));
-    PGMO_CUDA(cudaMemcpyAsync(h->h_counters.ptr, h->d_counters.ptr, sizeof(unsigned long long),
+    PGMO_CUDA(cudaMemcpyAsync(h->h_counters.ptr, h->d_counters.ptr, 8 * sizeof(unsigned long long),
                               cudaMemcpyDeviceToHost, st));
     PGMO_CUDA(cudaStreamSynchronize(st));
     *n_resolved = h->h_counters.ptr[0];
+    if (std::getenv("PGMO_DEBUG")) {
+      fprintf(stderr, "pgmo debug counters: resolved %llu groups %llu scanned %llu boxvol_l %llu\n",
+              h->h_counters.ptr[0], h->h_counters.ptr[1], h->h_counters.ptr[2], h->h_counters.ptr[3]);
+    }
   }
   return PGMO_OK;
 }
@@ -640,7 +656,7 @@ int pgmo_deform_run_device(pgmo_deform_t* h, uint64_t first_position, uint64_t n
 
 int pgmo_deform_set_search_mode(pgmo_deform_t* h, int mode) {
   PGMO_CHECK_ARG(h != nullptr);
-  PGMO_CHECK_ARG(mode == 0 || mode == 1);
+  PGMO_CHECK_ARG(mode >= 0 && mode <= 2);
   if (h->grid_mode != mode) h->sched_ready = false;  // rebuild (or drop) the grids
   h->grid_mode = mode;
   return PGMO_OK;

@@ -236,7 +236,7 @@ struct BinnedSmem {
 template <int KCAP>
 __global__ void __launch_bounds__(kThreads, 3)
 deformKnnBlendBinnedKernel(const DeformArgs a, const GridArgs ga, const WorkItem* __restrict__ items,
-                           const int precision) {
+                           const int precision, const uint32_t skip_alive_le) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BinnedSmem& S = *reinterpret_cast<BinnedSmem*>(smem_raw);
 
@@ -251,13 +251,14 @@ deformKnnBlendBinnedKernel(const DeformArgs a, const GridArgs ga, const WorkItem
     for (int i = t; i < count; i += kThreads) a.status[p_base + i] = kStatusSkipped;
     return;
   }
+  const RunGridDev g = ga.grids[r];
+  if (g.n_alive <= skip_alive_le) return;  // the bucket-ordered kernel's item
   const int K = static_cast<int>(info.z) + 2;
   if (K + 1 > KCAP) {
     for (int i = t; i < count; i += kThreads) a.status[p_base + i] = kStatusNeedsTie;
     if (t == 0) atomicAdd(a.counters, static_cast<unsigned long long>(count));
     return;
   }
-  const RunGridDev g = ga.grids[r];
   const int n_cells = g.nx * g.ny * g.nz;
   const int tiles_x = (g.nx + 1) >> 1, tiles_y = (g.ny + 1) >> 1;
   const int n_tiles = tiles_x * tiles_y;  // <= kGridMaxCells
@@ -474,7 +475,7 @@ cudaError_t launchBuildRunGrids(uint32_t n_runs, const uint4* run_info, const fl
 
 cudaError_t launchDeformKnnBlendGrid(const DeformArgs& args, const GridArgs& gargs,
                                      const WorkItem* items, uint32_t n_items, int precision,
-                                     uint32_t max_k, cudaStream_t stream) {
+                                     uint32_t max_k, uint32_t skip_alive_le, cudaStream_t stream) {
   if (n_items == 0) return cudaSuccess;
   const size_t smem = sizeof(BinnedSmem);
   static thread_local int configured_device = -1;
@@ -491,9 +492,11 @@ cudaError_t launchDeformKnnBlendGrid(const DeformArgs& args, const GridArgs& gar
     configured_device = device;
   }
   if (max_k + 3 <= 8) {
-    deformKnnBlendBinnedKernel<8><<<n_items, kThreads, smem, stream>>>(args, gargs, items, precision);
+    deformKnnBlendBinnedKernel<8><<<n_items, kThreads, smem, stream>>>(args, gargs, items, precision,
+                                                                       skip_alive_le);
   } else {
-    deformKnnBlendBinnedKernel<16><<<n_items, kThreads, smem, stream>>>(args, gargs, items, precision);
+    deformKnnBlendBinnedKernel<16><<<n_items, kThreads, smem, stream>>>(args, gargs, items, precision,
+                                                                        skip_alive_le);
   }
   return cudaGetLastError();
 }

@@ -62,8 +62,11 @@ struct RunGridDev {
   uint32_t n_alive;
   float r0;               // first search radius: ~1.25 x expected (K+1)-th neighbour distance
 };
-// up to kDeformChunk consecutive local positions of one run (one CTA of the grid kernel)
+// up to kDeformChunk consecutive local positions of one run (one CTA of the grid kernels)
 constexpr uint32_t kDeformChunk = 2048;
+// runs with at most this many alive control points go through the bucket-ordered kernel
+// (deform_sorted.cu); larger alive sets stay on the grid-walk kernel (deform_grid.cu)
+constexpr int kSortedMaxPoints = 512;
 struct WorkItem {
   uint64_t start;  // local position
   uint32_t run;
@@ -107,9 +110,16 @@ cudaError_t launchBuildRunGrids(uint32_t n_runs, const uint4* run_info, const fl
                                 const uint32_t* point_offset, RunGridDev* grids,
                                 float4* grid_points, uint32_t* grid_cells, cudaStream_t stream);
 // K3 over the per-run grids: same result as launchDeformKnnBlend, ~8x fewer candidates.
+// Items whose run has <= skip_alive_le alive points are left untouched (they belong to the
+// bucket-ordered kernel); pass 0 to process everything.
 cudaError_t launchDeformKnnBlendGrid(const DeformArgs& args, const GridArgs& gargs,
                                      const WorkItem* items, uint32_t n_items, int precision,
-                                     uint32_t max_k, cudaStream_t stream);
+                                     uint32_t max_k, uint32_t skip_alive_le, cudaStream_t stream);
+// K3, bucket-ordered candidate lists: processes the items whose run has <= kSortedMaxPoints
+// alive points and leaves the others untouched.  Same result as the other two K3 kernels.
+cudaError_t launchDeformKnnBlendSorted(const DeformArgs& args, const GridArgs& gargs,
+                                       const WorkItem* items, uint32_t n_items, int precision,
+                                       uint32_t max_k, cudaStream_t stream);
 
 // K4: PCL-order resolution of the vertices flagged kStatusNeedsTie.
 cudaError_t launchDeformResolve(const DeformArgs& args, const ResolveArgs& rargs, int precision,

@@ -1,0 +1,466 @@
+// K3, bucket-ordered candidate lists (sm_100a): the main knn + blend kernel.
+//
+// deformation::interpPoint (kimera_pgmo/src/mesh_deformation.cpp:73-106) needs, per vertex, the
+// K = k + 2 nearest alive control points in ascending float-d^2 order.  The profile of the
+// grid-walk kernel (profiles/r01b_*) showed the search to be ALU-issue-bound: ~6000 warp
+// instructions per 32 vertices, almost all of them 64-bit compare/select chains and cell-loop
+// bookkeeping.  This kernel removes both:
+//
+//   * One CTA = one work item (<= 2048 consecutive positions of ONE run, i.e. one alive set of
+//     a few hundred control points, staged in shared memory).  The vertices are counting-sorted
+//     in shared memory by 2x2x2-cell tile of a grid over their own bounding box, so that every
+//     group of 32 consecutive sorted vertices (= one warp pass) is a compact blob B.
+//   * Per group, the warp buckets ALL alive points by a lower bound of their squared distance
+//     to B's bounding box (32 buckets of width r0^2/8) and walks the buckets outwards.  Lanes
+//     keep their (K+1) smallest keys in registers; the walk stops as soon as every lane's
+//     (K+1)-th key is below the lower bound of the next bucket, i.e. nothing unscanned can
+//     enter (or tie with) anybody's list.  Every candidate read is one broadcast LDS.128.
+//   * Keys are 32 bits: the exact float d^2 bit pattern with the low `ord_bits` mantissa bits
+//     replaced by the candidate's position in the warp's list, so that the sorted insert is a
+//     branch-free chain of integer min/max pairs (2 VIMNMX per slot instead of the 6-7
+//     instructions of a 64-bit compare + payload select).  The winners' exact d^2 and control
+//     index are recomputed from the list afterwards.  Two winners whose keys agree above the
+//     ordinal bits are "near ties" (|delta d^2| < 2^ord_bits ulp, ~3e-4 of the vertices):
+//     they are re-ordered on their exact d^2 in registers; exact ties (and near ties that
+//     touch the last tracked slot) are handed to the PCL-order resolver (K4), which is exact.
+//
+// The result is bit-identical to the brute-force and grid-walk kernels (tests/test_deform_gpu.py
+// ::test_search_modes_agree).  Runs with more than kSMaxPts alive points stay on the grid-walk
+// kernel (deform_grid.cu).
+#include <cfloat>
+
+#include "deform_device.cuh"
+
+namespace pgmo {
+
+namespace {
+
+using namespace dev;
+
+constexpr int kSThreads = 256;
+constexpr int kSWarps = kSThreads / 32;
+constexpr int kSChunk = kDeformChunk;  // positions per work item
+constexpr int kSMaxPts = kSortedMaxPoints;
+constexpr int kSBuckets = 32;
+constexpr int kSMaxCells = 1024;       // sort bins (8 per tile)
+constexpr int kSlotBits = 9;           // kSMaxPts = 512
+static_assert((1 << kSlotBits) == kSMaxPts, "slot bits");
+
+struct SortedSmem {
+  float4 pts[kSMaxPts];                     // alive control points: x, y, z, index (int bits)
+  float vx[kSChunk], vy[kSChunk], vz[kSChunk];
+  uint16_t perm[kSChunk];                   // sorted position -> vertex of the item
+  union alignas(16) {
+    uint32_t hist[kSMaxCells + 1];          // vertex sort only
+    struct {
+      uint16_t tmp[kSWarps][kSMaxPts];      // per point: bucket << 9 | rank inside the bucket
+      uint16_t list[kSWarps][kSMaxPts + 8]; // bucket-ordered: bucket << 9 | point slot
+    } w;
+  } u;
+  uint32_t bcnt[kSWarps][kSBuckets];
+  float red[6][kSWarps];
+  uint32_t warp_tot[kSWarps];
+  float grid[8];                            // origin xyz, inv cell, nx, ny, nz (as float bits)
+};
+
+template <int KCAP>
+__device__ __forceinline__ void chainInsert(uint32_t (&best)[KCAP], uint32_t x) {
+#pragma unroll
+  for (int i = 0; i < KCAP; ++i) {
+    const uint32_t lo = min(best[i], x);
+    x = max(best[i], x);
+    best[i] = lo;
+  }
+}
+
+__device__ __forceinline__ float warpMinF(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warpMaxF(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ int clampCell(float p, float origin, float inv_cell, int n) {
+  int c = static_cast<int>((p - origin) * inv_cell);
+  c = c < 0 ? 0 : c;
+  return c >= n ? n - 1 : c;
+}
+
+template <int KCAP, int PREC>
+__global__ void __launch_bounds__(kSThreads, 3)
+deformKnnBlendSortedKernel(const DeformArgs a, const GridArgs ga,
+                           const WorkItem* __restrict__ items) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SortedSmem& S = *reinterpret_cast<SortedSmem*>(smem_raw);
+
+  const WorkItem item = items[blockIdx.x];
+  const uint32_t r = item.run;
+  const uint4 info = __ldg(a.run_info + r);
+  const uint64_t p_base = item.start;
+  const int t = threadIdx.x;
+  const int lane = t & 31, warp = t >> 5;
+  const int count = static_cast<int>(item.count);
+  if (info.w) {
+    for (int i = t; i < count; i += kSThreads) a.status[p_base + i] = kStatusSkipped;
+    return;
+  }
+  const RunGridDev g = ga.grids[r];
+  const int n_alive = static_cast<int>(g.n_alive);
+  if (n_alive > kSMaxPts) return;  // grid-walk kernel's item
+  const int K = static_cast<int>(info.z) + 2;
+  if (K + 1 > KCAP) {
+    for (int i = t; i < count; i += kSThreads) a.status[p_base + i] = kStatusNeedsTie;
+    if (t == 0) atomicAdd(a.counters, static_cast<unsigned long long>(count));
+    return;
+  }
+
+  // ---- stage the run's alive points; load the item's vertices and their bounding box
+  {
+    const float4* src = ga.points + g.point_offset;
+    for (int i = t; i < n_alive; i += kSThreads) S.pts[i] = __ldg(src + i);
+  }
+  float mn0 = FLT_MAX, mn1 = FLT_MAX, mn2 = FLT_MAX, mx0 = -FLT_MAX, mx1 = -FLT_MAX,
+        mx2 = -FLT_MAX;
+  for (int i = t; i < count; i += kSThreads) {
+    const uint64_t ii = a.subset ? a.subset[p_base + i] : p_base + i;
+    const float x = a.x[ii], y = a.y[ii], z = a.z[ii];
+    S.vx[i] = x;
+    S.vy[i] = y;
+    S.vz[i] = z;
+    mn0 = fminf(mn0, x);
+    mx0 = fmaxf(mx0, x);
+    mn1 = fminf(mn1, y);
+    mx1 = fmaxf(mx1, y);
+    mn2 = fminf(mn2, z);
+    mx2 = fmaxf(mx2, z);
+  }
+  mn0 = warpMinF(mn0);
+  mn1 = warpMinF(mn1);
+  mn2 = warpMinF(mn2);
+  mx0 = warpMaxF(mx0);
+  mx1 = warpMaxF(mx1);
+  mx2 = warpMaxF(mx2);
+  if (lane == 0) {
+    S.red[0][warp] = mn0;
+    S.red[1][warp] = mn1;
+    S.red[2][warp] = mn2;
+    S.red[3][warp] = mx0;
+    S.red[4][warp] = mx1;
+    S.red[5][warp] = mx2;
+  }
+  for (int i = t; i <= kSMaxCells; i += kSThreads) S.u.hist[i] = 0;
+  __syncthreads();
+  if (t == 0) {
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (int w = 0; w < kSWarps; ++w) {
+      for (int ax = 0; ax < 3; ++ax) {
+        lo[ax] = fminf(lo[ax], S.red[ax][w]);
+        hi[ax] = fmaxf(hi[ax], S.red[3 + ax][w]);
+      }
+    }
+    // sort grid over the vertices' box: ~4 vertices per cell, 2x2x2 cells per tile, so that 32
+    // consecutive sorted vertices fill about one tile.  NaN / inf coordinates degrade the
+    // ordering only (cells are clamped), never the result.
+    float ext[3];
+    for (int ax = 0; ax < 3; ++ax) {
+      ext[ax] = hi[ax] - lo[ax];
+      if (!(ext[ax] >= 0.f) || ext[ax] > 1e30f) ext[ax] = 0.f;
+    }
+    const float target = fmaxf(static_cast<float>(count) * 0.25f, 1.f);
+    const float longest = fmaxf(fmaxf(ext[0], ext[1]), ext[2]);
+    float cell = 1.f;
+    if (longest > 0.f) {
+      // cell edge s with prod(max(ext / s, 1)) ~ target: thin extents count as one cell
+      float s = longest / target;  // 1-d answer: the smallest candidate
+      for (int it = 0; it < 3; ++it) {
+        float vol = 1.f;
+        int dims = 0;
+        for (int ax = 0; ax < 3; ++ax) {
+          if (ext[ax] > s) {
+            vol *= ext[ax];
+            ++dims;
+          }
+        }
+        if (dims == 0) break;
+        const float per = vol / target;
+        s = dims == 3 ? cbrtf(per) : (dims == 2 ? sqrtf(per) : per);
+      }
+      cell = fmaxf(s, longest * (1.f / 512.f));
+    }
+    int nx, ny, nz;
+    while (true) {
+      nx = static_cast<int>(ext[0] / cell) + 1;
+      ny = static_cast<int>(ext[1] / cell) + 1;
+      nz = static_cast<int>(ext[2] / cell) + 1;
+      const long long bins = 8ll * ((nx + 1) >> 1) * ((ny + 1) >> 1) * ((nz + 1) >> 1);
+      if (bins <= kSMaxCells) break;
+      cell *= 1.26f;
+    }
+    S.grid[0] = lo[0];
+    S.grid[1] = lo[1];
+    S.grid[2] = lo[2];
+    S.grid[3] = 1.f / cell;
+    S.grid[4] = __int_as_float(nx);
+    S.grid[5] = __int_as_float(ny);
+    S.grid[6] = __int_as_float(nz);
+  }
+  __syncthreads();
+  const float gox = S.grid[0], goy = S.grid[1], goz = S.grid[2], ginv = S.grid[3];
+  const int nx = __float_as_int(S.grid[4]), ny = __float_as_int(S.grid[5]),
+            nz = __float_as_int(S.grid[6]);
+  const int txs = (nx + 1) >> 1, tys = (ny + 1) >> 1, tzs = (nz + 1) >> 1;
+  const int n_bins = 8 * txs * tys * tzs;
+
+  // ---- counting sort of the vertices by bin (tile-major, 8 cells per tile)
+  auto binOf = [&](int i) {
+    const int ix = clampCell(S.vx[i], gox, ginv, nx);
+    const int iy = clampCell(S.vy[i], goy, ginv, ny);
+    const int iz = clampCell(S.vz[i], goz, ginv, nz);
+    return ((((iz >> 1) * tys + (iy >> 1)) * txs + (ix >> 1)) << 3) | ((iz & 1) << 2) |
+           ((iy & 1) << 1) | (ix & 1);
+  };
+  for (int i = t; i < count; i += kSThreads) atomicAdd(&S.u.hist[binOf(i) + 1], 1u);
+  __syncthreads();
+  {
+    constexpr int per = (kSMaxCells + kSThreads - 1) / kSThreads;
+    uint32_t local[per];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int e = 0; e < per; ++e) {
+      const int i = 1 + t * per + e;
+      local[e] = i <= n_bins ? S.u.hist[i] : 0;
+      sum += local[e];
+    }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if (lane >= o) incl += up;
+    }
+    if (lane == 31) S.warp_tot[warp] = incl;
+    __syncthreads();
+    uint32_t run_sum = incl - sum;
+    for (int w = 0; w < warp; ++w) run_sum += S.warp_tot[w];
+#pragma unroll
+    for (int e = 0; e < per; ++e) {
+      const int i = 1 + t * per + e;
+      run_sum += local[e];
+      if (i <= n_bins) S.u.hist[i] = run_sum;  // hist[i] = #vertices in bins < i
+    }
+  }
+  __syncthreads();
+  for (int i = t; i < count; i += kSThreads) {
+    const uint32_t at = atomicAdd(&S.u.hist[binOf(i)], 1u);
+    S.perm[at] = static_cast<uint16_t>(i);
+  }
+  __syncthreads();  // hist is dead from here on: tmp / list alias it
+
+  // ---- per group of 32 sorted vertices: bucket the alive points around the group's box, walk
+  const unsigned full = 0xFFFFFFFFu;
+  uint16_t* tmp = S.u.w.tmp[warp];
+  uint16_t* list = S.u.w.list[warp];
+  uint32_t* bcnt = S.bcnt[warp];
+  const int n_groups = (count + 31) >> 5;
+  const int n_need = n_alive < K + 1 ? n_alive : K + 1;
+  const int n = n_alive < K ? n_alive : K;
+  // ordinal bits: enough for every list position of this run
+  const int ord_bits = n_alive <= 128 ? 7 : (n_alive <= 256 ? 8 : 9);
+  const uint32_t ord_mask = (1u << ord_bits) - 1u;
+  const float bw = fmaxf(g.r0 * g.r0 * 0.125f, 1e-20f);  // bucket width in d^2
+  const float inv_bw = 1.f / bw;
+  const float bw_lb = bw * 0.9999f;
+
+  for (int group = warp; group < n_groups; group += kSWarps) {
+    const int slot = group * 32 + lane;
+    const bool active = slot < count;
+    const int v = S.perm[active ? slot : group * 32];  // idle lanes shadow the group's first vertex
+    const float qx = S.vx[v], qy = S.vy[v], qz = S.vz[v];
+    const float lox = warpMinF(qx), hix = warpMaxF(qx);
+    const float loy = warpMinF(qy), hiy = warpMaxF(qy);
+    const float loz = warpMinF(qz), hiz = warpMaxF(qz);
+
+    // pass 1: bucket = floor(lower bound of d^2(point, box) / bw); rank inside the bucket
+    bcnt[lane] = 0;
+    __syncwarp();
+    for (int i = lane; i < n_alive; i += 32) {
+      const float4 c = S.pts[i];
+      const float ax = fmaxf(fmaxf(lox - c.x, c.x - hix), 0.f);
+      const float ay = fmaxf(fmaxf(loy - c.y, c.y - hiy), 0.f);
+      const float az = fmaxf(fmaxf(loz - c.z, c.z - hiz), 0.f);
+      // 0.9999: the bound must hold against the separately rounded exact d^2 of every lane
+      const float m = (ax * ax + ay * ay + az * az) * 0.9999f;
+      int b = static_cast<int>(fminf(m * inv_bw, static_cast<float>(kSBuckets - 1)));
+      b = b < 0 ? 0 : b;  // NaN coordinates
+      const uint32_t rank = atomicAdd(&bcnt[b], 1u);
+      tmp[i] = static_cast<uint16_t>((b << kSlotBits) | rank);
+    }
+    __syncwarp();
+    {
+      const uint32_t c = bcnt[lane];
+      uint32_t incl = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t up = __shfl_up_sync(full, incl, o);
+        if (lane >= o) incl += up;
+      }
+      __syncwarp();
+      bcnt[lane] = incl - c;
+    }
+    __syncwarp();
+    for (int i = lane; i < n_alive; i += 32) {
+      const uint32_t e = tmp[i];
+      const uint32_t pos = bcnt[e >> kSlotBits] + (e & (kSMaxPts - 1));
+      list[pos] = static_cast<uint16_t>((e & ~static_cast<uint32_t>(kSMaxPts - 1)) | i);
+    }
+    __syncwarp();
+
+    // pass 2: walk the list, 4 entries per step
+    uint32_t best[KCAP];
+#pragma unroll
+    for (int i = 0; i < KCAP; ++i) best[i] = 0xFFFFFFFFu;
+    for (int c = 0; c < n_alive; c += 4) {
+      const uint2 ee = *reinterpret_cast<const uint2*>(list + c);
+      uint32_t e[4] = {ee.x & 0xFFFFu, ee.x >> 16, ee.y & 0xFFFFu, ee.y >> 16};
+      if (c >= 8) {
+        // every unscanned point has d^2 >= lb for every lane; stop when nobody can use that
+        const float lb = static_cast<float>(e[0] >> kSlotBits) * bw_lb;
+        uint32_t kth = 0u;  // best[n_need - 1] = max of the first n_need (ascending) entries
+#pragma unroll
+        for (int i = 0; i < KCAP; ++i) kth = i < n_need ? max(kth, best[i]) : kth;
+        // (key | ord_mask) >= the entry's exact d^2 bits; unfilled slots are NaN: never "<"
+        const bool ok = __uint_as_float(kth | ord_mask) < lb;
+        if (__all_sync(full, ok)) break;
+      }
+#ifdef PGMO_DEBUG_COUNTERS
+      if (lane == 0) atomicAdd(a.counters + 2, 4ull);
+#endif
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (c + u < n_alive) {
+          const float4 p = S.pts[e[u] & (kSMaxPts - 1)];  // same address in all lanes: broadcast
+          const float d2 = dist2Exact(p.x, p.y, p.z, qx, qy, qz);
+          chainInsert<KCAP>(best, (__float_as_uint(d2) & ~ord_mask) | static_cast<uint32_t>(c + u));
+        }
+      }
+    }
+#ifdef PGMO_DEBUG_COUNTERS
+    if (lane == 0) {
+      atomicAdd(a.counters + 1, 1ull);
+      atomicAdd(a.counters + 3, static_cast<unsigned long long>((hix - lox) * (hiy - loy) * (hiz - loz) * 1000.f));
+    }
+#endif
+    if (!active) continue;
+
+    // winners: exact d^2 and control index back from the list
+    const uint64_t p = p_base + v;
+    const uint64_t ii = a.subset ? a.subset[p] : p;
+    float nbr_d2[KCAP];
+    int nbr_idx[KCAP];
+    bool near = false;       // two winners agree above the ordinal bits
+    bool near_last = false;  // ... and one of them is the last tracked slot
+#pragma unroll
+    for (int i = 0; i < KCAP; ++i) {
+      nbr_d2[i] = FLT_MAX;
+      nbr_idx[i] = -1;
+      if (i < n_need) {
+        const float4 c = S.pts[list[best[i] & ord_mask] & (kSMaxPts - 1)];
+        nbr_d2[i] = dist2Exact(c.x, c.y, c.z, qx, qy, qz);
+        nbr_idx[i] = __float_as_int(c.w);
+      }
+      if (i > 0 && i < n_need && (best[i] >> ord_bits) == (best[i - 1] >> ord_bits)) {
+        near = true;
+        near_last = near_last || (i == n_need - 1);
+      }
+    }
+    bool tie = false;
+    if (near) {
+      // Keys that agree above the ordinal bits were ordered by list position, not by d^2.
+      // Every point sharing that prefix is tracked unless the group reaches the last slot
+      // (untracked points have keys >= the last slot's), so below the last slot the exact
+      // order is recovered by sorting the winners on their exact d^2; what remains equal is an
+      // exact tie.  A group touching the last slot is checked for untracked members first.
+      // Exact ties, groups with untracked members and anything two bubble passes do not sort
+      // (>= 4 near-equal winners) go to the resolver.
+      if (near_last && n_alive > n_need) {
+        // does an untracked point share the last slot's prefix?  Count all of them (rare path:
+        // ~1e-4 of the vertices) and compare with the number of tracked ones.
+        uint32_t last_key = 0u;  // best[n_need - 1] without dynamic indexing (ascending keys)
+#pragma unroll
+        for (int i = 0; i < KCAP; ++i) last_key = i < n_need ? max(last_key, best[i]) : last_key;
+        const uint32_t prefix = last_key >> ord_bits;
+        int tracked = 0;
+#pragma unroll
+        for (int i = 0; i < KCAP; ++i) tracked += (i < n_need && (best[i] >> ord_bits) == prefix) ? 1 : 0;
+        int all = 0;
+        for (int j = 0; j < n_alive; ++j) {
+          const float4 c = S.pts[j];
+          all += ((__float_as_uint(dist2Exact(c.x, c.y, c.z, qx, qy, qz)) >> ord_bits) == prefix) ? 1 : 0;
+        }
+        tie = all != tracked;
+      }
+#pragma unroll
+      for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+        for (int i = 1; i < KCAP; ++i) {
+          if (i < n_need && nbr_d2[i] < nbr_d2[i - 1]) {
+            const float td = nbr_d2[i];
+            nbr_d2[i] = nbr_d2[i - 1];
+            nbr_d2[i - 1] = td;
+            const int ti = nbr_idx[i];
+            nbr_idx[i] = nbr_idx[i - 1];
+            nbr_idx[i - 1] = ti;
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 1; i < KCAP; ++i) {
+        if (i < n_need && nbr_d2[i] <= nbr_d2[i - 1]) tie = true;
+      }
+    }
+    if (tie) {  // exact tie (or an unresolvable near tie): the resolver is exact for both
+      a.status[p] = kStatusNeedsTie;
+      atomicAdd(a.counters, 1ull);
+      continue;
+    }
+    writeResultReg<KCAP>(a, p, ii, PREC, qx, qy, qz, nbr_d2, nbr_idx, n);
+    a.status[p] = kStatusDone;
+  }
+}
+
+template <int KCAP, int PREC>
+cudaError_t launchOne(const DeformArgs& args, const GridArgs& gargs, const WorkItem* items,
+                      uint32_t n_items, cudaStream_t stream) {
+  const size_t smem = sizeof(SortedSmem);
+  static thread_local int configured_device = -1;
+  int device = 0;
+  cudaGetDevice(&device);
+  if (configured_device != device) {
+    const cudaError_t e =
+        cudaFuncSetAttribute(deformKnnBlendSortedKernel<KCAP, PREC>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    configured_device = device;
+  }
+  deformKnnBlendSortedKernel<KCAP, PREC><<<n_items, kSThreads, smem, stream>>>(args, gargs, items);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launchDeformKnnBlendSorted(const DeformArgs& args, const GridArgs& gargs,
+                                       const WorkItem* items, uint32_t n_items, int precision,
+                                       uint32_t max_k, cudaStream_t stream) {
+  if (n_items == 0) return cudaSuccess;
+  if (max_k + 3 <= 7) {
+    return precision == 0 ? launchOne<7, 0>(args, gargs, items, n_items, stream)
+                          : launchOne<7, 1>(args, gargs, items, n_items, stream);
+  }
+  return precision == 0 ? launchOne<16, 0>(args, gargs, items, n_items, stream)
+                        : launchOne<16, 1>(args, gargs, items, n_items, stream);
+}
+
+}  // namespace pgmo

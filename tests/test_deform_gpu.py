@@ -117,14 +117,17 @@ def test_config_a_parity(capi, oracle, tol_t, invalid):
     assert ref["processed"].all()
 
 
-@pytest.mark.parametrize("spread", [(6.0, 5.0), (40.0, 2.0), (0.5, 30.0)])
+@pytest.mark.parametrize("spread", [(6.0, 5.0, 10), (40.0, 2.0, 10), (0.5, 30.0, 10),
+                                    (6.0, 5.0, 40), (3.0, 0.0, 10)])
 def test_search_modes_agree(capi, oracle, spread):
-    """Per-run spatial grids (default) and brute force over the window are bit-identical, also
-    when vertices lie far outside / deep inside the control-point cloud."""
-    case = synth.deformation_case(150_000, 3_000, vertex_spread=spread[0], ctrl_spread=spread[1],
-                                  seed=17)
+    """Bucket-ordered lists (default), grid walk and brute force over the window are
+    bit-identical, also when vertices lie far outside / deep inside the control-point cloud,
+    when the alive set exceeds the bucket kernel's capacity (40 control points per keyframe:
+    ~840 alive) and when all control points of a keyframe coincide."""
+    case = synth.deformation_case(150_000, 300 * spread[2], ctrl_per_kf=spread[2],
+                                  vertex_spread=spread[0], ctrl_spread=spread[1], seed=17)
     outs = []
-    for mode in (0, 1):
+    for mode in (0, 1, 2):
         h = capi.DeformHandle(0)
         h.set_search_mode(mode)
         _set(h, case)
@@ -133,6 +136,7 @@ def test_search_modes_agree(capi, oracle, spread):
         h.close()
     for key in ("x", "y", "z", "f64", "assoc", "assoc_cnt", "processed"):
         np.testing.assert_array_equal(outs[0][key], outs[1][key])
+        np.testing.assert_array_equal(outs[0][key], outs[2][key])
     ref = oracle.deform_points(case["x"], case["y"], case["z"], case["stamps"], case["ctrl_xyz"],
                                case["ctrl_stamps"], case["valid"], case["poses"], k=4, tol_t=10.0)
     _compare(outs[1], ref)
