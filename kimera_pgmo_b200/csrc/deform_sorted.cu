@@ -47,7 +47,8 @@ constexpr int kSlotBits = 9;           // kSMaxPts = 512
 static_assert((1 << kSlotBits) == kSMaxPts, "slot bits");
 
 struct SortedSmem {
-  float4 pts[kSMaxPts];                     // alive control points: x, y, z, index (int bits)
+  float4 pts[kSMaxPts];                     // alive control points: x, y, z, index (int bits);
+                                            // pts[n_alive] = a point at infinity when n_alive % 4 != 0
   float vx[kSChunk], vy[kSChunk], vz[kSChunk];
   uint16_t perm[kSChunk];                   // sorted position -> vertex of the item
   union alignas(16) {
@@ -122,6 +123,8 @@ deformKnnBlendSortedKernel(const DeformArgs a, const GridArgs ga,
   {
     const float4* src = ga.points + g.point_offset;
     for (int i = t; i < n_alive; i += kSThreads) S.pts[i] = __ldg(src + i);
+    // list padding (see the walk): d^2 to this point is +inf for every finite query
+    if (t == 0 && (n_alive & 3)) S.pts[n_alive] = make_float4(3e30f, 3e30f, 3e30f, __int_as_float(-1));
   }
   float mn0 = FLT_MAX, mn1 = FLT_MAX, mn2 = FLT_MAX, mx0 = -FLT_MAX, mx1 = -FLT_MAX,
         mx2 = -FLT_MAX;
@@ -273,6 +276,7 @@ deformKnnBlendSortedKernel(const DeformArgs a, const GridArgs ga,
   const float bw = fmaxf(g.r0 * g.r0 * 0.125f, 1e-20f);  // bucket width in d^2
   const float inv_bw = 1.f / bw;
   const float bw_lb = bw * 0.9999f;
+  const bool full_k = n_need == KCAP;
 
   for (int group = warp; group < n_groups; group += kSWarps) {
     const int slot = group * 32 + lane;
@@ -316,6 +320,10 @@ deformKnnBlendSortedKernel(const DeformArgs a, const GridArgs ga,
       const uint32_t pos = bcnt[e >> kSlotBits] + (e & (kSMaxPts - 1));
       list[pos] = static_cast<uint16_t>((e & ~static_cast<uint32_t>(kSMaxPts - 1)) | i);
     }
+    // pad to a multiple of 4 with the point at infinity (last bucket): the walk needs no guards
+    if (lane < ((4 - (n_alive & 3)) & 3)) {
+      list[n_alive + lane] = static_cast<uint16_t>(((kSBuckets - 1) << kSlotBits) | n_alive);
+    }
     __syncwarp();
 
     // pass 2: walk the list, 4 entries per step
@@ -328,31 +336,25 @@ deformKnnBlendSortedKernel(const DeformArgs a, const GridArgs ga,
       if (c >= 8) {
         // every unscanned point has d^2 >= lb for every lane; stop when nobody can use that
         const float lb = static_cast<float>(e[0] >> kSlotBits) * bw_lb;
-        uint32_t kth = 0u;  // best[n_need - 1] = max of the first n_need (ascending) entries
+        uint32_t kth;  // best[n_need - 1]: the maximum of the first n_need (ascending) entries
+        if (full_k) {
+          kth = best[KCAP - 1];
+        } else {
+          kth = 0u;
 #pragma unroll
-        for (int i = 0; i < KCAP; ++i) kth = i < n_need ? max(kth, best[i]) : kth;
+          for (int i = 0; i < KCAP; ++i) kth = i < n_need ? max(kth, best[i]) : kth;
+        }
         // (key | ord_mask) >= the entry's exact d^2 bits; unfilled slots are NaN: never "<"
         const bool ok = __uint_as_float(kth | ord_mask) < lb;
         if (__all_sync(full, ok)) break;
       }
-#ifdef PGMO_DEBUG_COUNTERS
-      if (lane == 0) atomicAdd(a.counters + 2, 4ull);
-#endif
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        if (c + u < n_alive) {
-          const float4 p = S.pts[e[u] & (kSMaxPts - 1)];  // same address in all lanes: broadcast
-          const float d2 = dist2Exact(p.x, p.y, p.z, qx, qy, qz);
-          chainInsert<KCAP>(best, (__float_as_uint(d2) & ~ord_mask) | static_cast<uint32_t>(c + u));
-        }
+        const float4 p = S.pts[e[u] & (kSMaxPts - 1)];  // same address in all lanes: broadcast
+        const float d2 = dist2Exact(p.x, p.y, p.z, qx, qy, qz);
+        chainInsert<KCAP>(best, (__float_as_uint(d2) & ~ord_mask) | static_cast<uint32_t>(c + u));
       }
     }
-#ifdef PGMO_DEBUG_COUNTERS
-    if (lane == 0) {
-      atomicAdd(a.counters + 1, 1ull);
-      atomicAdd(a.counters + 3, static_cast<unsigned long long>((hix - lox) * (hiy - loy) * (hiz - loz) * 1000.f));
-    }
-#endif
     if (!active) continue;
 
     // winners: exact d^2 and control index back from the list
