@@ -92,7 +92,7 @@ __device__ __forceinline__ int clampCell(float p, float origin, float inv_cell, 
 }
 
 template <int KCAP, int PREC>
-__global__ void __launch_bounds__(kSThreads, 3)
+__global__ void __launch_bounds__(kSThreads, 4)
 deformKnnBlendSortedKernel(const DeformArgs a, const GridArgs ga,
                            const WorkItem* __restrict__ items) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
