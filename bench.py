@@ -47,6 +47,7 @@ def parse_args():
                     help="vertices of the workload the CPU baseline is timed on")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-compression", action="store_true")
     return ap.parse_args()
 
 
@@ -174,7 +175,7 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
 
-    from kimera_pgmo_b200 import capi, synth
+    from kimera_pgmo_b200 import capi, sharding, synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -214,34 +215,14 @@ def run_b200(args):
         if rank != 0:
             for t in (d_cpos, d_cst, d_cvalid, d_poses):
                 t.zero_()
-        for t in (d_cpos, d_cst, d_cvalid, d_poses):
-            dist.broadcast(t, src=0)
+        sharding.broadcast_controls((d_cpos, d_cst, d_cvalid, d_poses), src=0)
     torch.cuda.synchronize()
 
     h = capi.DeformHandle(local_rank)
     stream = torch.cuda.current_stream().cuda_stream
     h.set_controls_device(n_ctrl, d_cpos, d_cst, d_cvalid, d_poses, stream)
     h.set_profiling(True)
-    cap = 1 << 15
-    gather_buf = torch.zeros((world, 2 * cap + 1), dtype=torch.int64, device=dev) if world > 1 else None
-
-    def exchange_stretches(ss, sl):
-        if world == 1:
-            return ss, sl
-        n = ss.shape[0]
-        assert n <= cap, "stretch list larger than the exchange buffer"
-        mine = torch.zeros(2 * cap + 1, dtype=torch.int64)
-        mine[0] = n
-        mine[1:1 + n] = torch.from_numpy(ss.view(np.int64))
-        mine[1 + cap:1 + cap + n] = torch.from_numpy(sl.view(np.int64))
-        dist.all_gather_into_tensor(gather_buf, mine.to(dev, non_blocking=True))
-        g = gather_buf.cpu().numpy()
-        stamps, lens = [], []
-        for r in range(world):
-            m = int(g[r, 0])
-            stamps.append(g[r, 1:1 + m].view(np.uint64))
-            lens.append(g[r, 1 + cap:1 + cap + m].view(np.uint64))
-        return np.concatenate(stamps), np.concatenate(lens)
+    exchange_stretches = sharding.StretchExchange(world, dev)
 
     knn_ms, res_ms = [], []
 
@@ -350,7 +331,7 @@ def run_b200(args):
             "vs_baseline": None, "dtype": "f64" if args.precision == "fp64" else "f32",
             "data": "synthetic", "config": workload_config(args, n_total, n_ctrl),
             "roofline": {
-                "bound": "hbm", "kernel": "deformKnnBlendKernel", "achieved": achieved,
+                "bound": "hbm", "kernel": "deformKnnBlendSortedKernel", "achieved": achieved,
                 "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": load_ncu_traffic(), "kernel_ms": knn,
                 "resolver_ms": float(np.mean(res_ms)),
@@ -372,10 +353,82 @@ def run_b200(args):
                 "sample": f"first {min(args.cpu_sample, n_total)} vertices of the workload with the "
                           f"full control table, {el:.1f} s, oracle/liboracle.so single thread "
                           "(the reference path is single-threaded)"}
+        if world == 1 and not args.no_compression:
+            line["compression"] = bench_compression(local_rank, with_cpu=not args.no_cpu_baseline)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def bench_compression(dev_index, n_messages=60, verts=50_000, with_cpu=True):
+    """configs[1]: VoxelClearingCompression of streamed 50k-vertex mesh blocks at 0.05 m on one GPU.
+    Three numbers: device-resident throughput (inputs in HBM, pgmo_vcc_integrate_device, CUDA
+    events), end to end through pgmo_vcc_prune + pgmo_vcc_integrate with host buffers, and the
+    oracle (the reference's single-threaded algorithm) on the same messages."""
+    import torch
+
+    from kimera_pgmo_b200 import capi, synth
+    dev = torch.device("cuda", dev_index)
+    msgs = list(synth.compression_stream(n_messages, verts, n_blocks=1))
+    bytes_per_vertex = 24  # 16 B read (xyz + rgba) + 8 B remap written (SURVEY.md 8d)
+
+    # device resident
+    d_msgs = [(torch.from_numpy(x).to(dev), torch.from_numpy(c.view(np.int32)).to(dev)) for _, _, x, c, _ in msgs]
+    d_remap = torch.empty(verts, dtype=torch.int64, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    warm = 10
+    vcc = capi.VccHandle(0.05, dev_index)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for m, (blocks, offsets, _, _, t) in enumerate(msgs):
+        if m == warm:
+            torch.cuda.synchronize()
+            ev0.record()
+        vcc.prune(t - 10.0)
+        vcc.integrate_device(blocks, offsets, d_msgs[m][0], d_msgs[m][1], t, d_remap, stream)
+    ev1.record()
+    torch.cuda.synchronize()
+    dev_ms = ev0.elapsed_time(ev1) / (n_messages - warm)
+    vcc.close()
+
+    # end to end (host buffers in, remap out)
+    vcc = capi.VccHandle(0.05, dev_index)
+    t0 = None
+    for m, (blocks, offsets, xyz, rgba, t) in enumerate(msgs):
+        if m == warm:
+            t0 = time.perf_counter()
+        vcc.prune(t - 10.0)
+        vcc.integrate(blocks, offsets, xyz, rgba, t)
+    e2e_ms = 1e3 * (time.perf_counter() - t0) / (n_messages - warm)
+    n_vertices_stored = vcc.sizes()[0]
+    vcc.close()
+
+    out = {
+        "workload": f"VoxelClearingCompression, {n_messages} messages x {verts} vertices (1 block), "
+                    "res 0.05 m, prune(t - 10 s) before each message; configs[1]",
+        "value": verts / (dev_ms * 1e-3), "unit": "vertices/s", "ms_per_message": dev_ms,
+        "roofline": {"bound": "hbm", "bytes_per_vertex": bytes_per_vertex,
+                     "achieved": bytes_per_vertex * verts / (dev_ms * 1e-3) / 1e9, "unit": "GB/s",
+                     "note": "a 50k-vertex message is 1.2 MB: launch-latency-bound, not HBM-bound"},
+        "e2e": {"value": verts / (e2e_ms * 1e-3), "unit": "vertices/s", "ms_per_message": e2e_ms,
+                "h2d_bytes_per_step": verts * 16, "d2h_bytes_per_step": verts * 8},
+        "stored_vertices": int(n_vertices_stored),
+    }
+    if with_cpu:
+        from oracle import ffi
+        ora = ffi.Compression("voxel_clearing", 0.05)
+        total = 0.0
+        for m, (blocks, offsets, xyz, rgba, t) in enumerate(msgs):
+            t1 = time.perf_counter()
+            ora.prune(t - 10.0)
+            ora.integrate(blocks, offsets, xyz, rgba, t)
+            if m >= warm:
+                total += time.perf_counter() - t1
+        cpu_ms = 1e3 * total / (n_messages - warm)
+        out["cpu_baseline"] = {"value": verts / (cpu_ms * 1e-3), "unit": "vertices/s", "cores": 1,
+                               "kind": "port", "ms_per_message": cpu_ms,
+                               "sample": f"the same {n_messages - warm} messages, oracle/liboracle.so"}
+    return out
 
 
 def load_ncu_traffic():

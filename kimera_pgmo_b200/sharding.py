@@ -1,0 +1,89 @@
+"""Host-side plumbing of the vertex-range sharded deformation.
+
+One process per GPU.  Nothing here touches vertex data: ranks own contiguous slabs of the
+processing order, the control table / poses are replicated by a broadcast, and the only exchange
+is the list of equal-stamp stretches of every slab (a few KB), all-gathered and concatenated in
+rank order so that every rank replays the identical window state machine
+(pgmo_deform_build_schedule).  torch.distributed is plumbing: NCCL on the GPU box, gloo in the
+CPU tests (tests/test_multi_rank_cpu.py).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def slab_bounds(n_total: int, world: int, rank: int):
+    """Contiguous vertex range [first, first + count) of `rank`."""
+    first = n_total * rank // world
+    last = n_total * (rank + 1) // world
+    return first, last - first
+
+
+def stretches_of(stamps: np.ndarray):
+    """(stamp, length) of the maximal equal-stamp stretches — what K1
+    (pgmo_deform_stamp_stretches_device) computes on the GPU."""
+    stamps = np.ascontiguousarray(stamps, dtype=np.uint64)
+    if stamps.shape[0] == 0:
+        return np.zeros(0, np.uint64), np.zeros(0, np.uint64)
+    b = np.flatnonzero(np.concatenate([[True], stamps[1:] != stamps[:-1]]))
+    lens = np.diff(np.concatenate([b, [stamps.shape[0]]]))
+    return stamps[b].copy(), lens.astype(np.uint64)
+
+
+def merge_stretch_lists(lists):
+    """Concatenates per-rank (stamps, lens) in rank order, fusing a stretch that continues across
+    a slab boundary (the same stamp at the end of rank r and the start of rank r + 1), so that
+    the result equals the stretch list of the unsharded stamp stream."""
+    stamps, lens = [], []
+    for ss, sl in lists:
+        for s, l in zip(ss.tolist(), sl.tolist()):
+            if l == 0:
+                continue
+            if stamps and stamps[-1] == s:
+                lens[-1] += l
+            else:
+                stamps.append(s)
+                lens.append(l)
+    return np.array(stamps, dtype=np.uint64), np.array(lens, dtype=np.uint64)
+
+
+class StretchExchange:
+    """all_gather of variable-length stretch lists through one fixed-size int64 tensor
+    (count, stamps[cap], lens[cap]) per rank; works on any torch.distributed backend."""
+
+    def __init__(self, world: int, device, cap: int = 1 << 15):
+        import torch
+        self.world = world
+        self.cap = cap
+        self.device = device
+        self._torch = torch
+        self._buf = (torch.zeros(world * (2 * cap + 1), dtype=torch.int64, device=device)
+                     if world > 1 else None)
+
+    def __call__(self, ss: np.ndarray, sl: np.ndarray):
+        if self.world == 1:
+            return ss, sl
+        import torch.distributed as dist
+        torch = self._torch
+        n = ss.shape[0]
+        if n > self.cap:
+            raise ValueError(f"{n} stretches exceed the exchange capacity {self.cap}")
+        mine = torch.zeros(2 * self.cap + 1, dtype=torch.int64)
+        mine[0] = n
+        mine[1:1 + n] = torch.from_numpy(ss.view(np.int64))
+        mine[1 + self.cap:1 + self.cap + n] = torch.from_numpy(sl.view(np.int64))
+        dist.all_gather_into_tensor(self._buf, mine.to(self.device, non_blocking=True))
+        g = self._buf.cpu().numpy().reshape(self.world, 2 * self.cap + 1)
+        lists = []
+        for r in range(self.world):
+            m = int(g[r, 0])
+            lists.append((g[r, 1:1 + m].view(np.uint64), g[r, 1 + self.cap:1 + self.cap + m].view(np.uint64)))
+        return merge_stretch_lists(lists)
+
+
+def broadcast_controls(tensors, src: int = 0):
+    """Replicates the control table / poses (device or CPU tensors) from `src` to every rank."""
+    import torch.distributed as dist
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        for t in tensors:
+            dist.broadcast(t, src=src)
