@@ -1,0 +1,393 @@
+// Implicit-octree kernels of OctreeCompression (see oct_kernels.cuh for the design).
+#include "oct_kernels.cuh"
+
+#include <cfloat>
+
+#include "deform_device.cuh"  // dist2Exact: (a - b).squaredNorm() as PCL / Eigen evaluate it
+
+namespace pgmo {
+
+namespace {
+
+using dev::dist2Exact;
+
+constexpr long long kCoordOffset = 1ll << (kOctCoordBits - 1);
+constexpr long long kCoordLimit = 1ll << kOctCoordBits;
+
+__device__ __forceinline__ bool packKey(int h, long long x, long long y, long long z,
+                                        unsigned long long* key) {
+  x += kCoordOffset;
+  y += kCoordOffset;
+  z += kCoordOffset;
+  if (x < 0 || y < 0 || z < 0 || x >= kCoordLimit || y >= kCoordLimit || z >= kCoordLimit) {
+    return false;
+  }
+  *key = (static_cast<unsigned long long>(h) << (3 * kOctCoordBits)) |
+         (static_cast<unsigned long long>(x) << (2 * kOctCoordBits)) |
+         (static_cast<unsigned long long>(y) << kOctCoordBits) | static_cast<unsigned long long>(z);
+  return true;
+}
+
+__device__ __forceinline__ uint32_t hashKey(unsigned long long k) {
+  k ^= k >> 30;
+  k *= 0xbf58476d1ce4e5b9ull;
+  k ^= k >> 27;
+  k *= 0x94d049bb133111ebull;
+  k ^= k >> 31;
+  return static_cast<uint32_t>(k);
+}
+
+__device__ __forceinline__ uint32_t tableInsert(const OctTable& t, unsigned long long key,
+                                                uint32_t seq) {
+  uint32_t slot = hashKey(key) & t.mask;
+  for (uint32_t probe = 0; probe <= t.mask; ++probe) {
+    const unsigned long long old = atomicCAS(t.keys + slot, kOctEmptyKey, key);
+    if (old == kOctEmptyKey || old == key) {
+      atomicMin(t.minseq + slot, seq);
+      return slot;
+    }
+    slot = (slot + 1) & t.mask;
+  }
+  return kOctNone;
+}
+
+__device__ __forceinline__ uint32_t tableFind(const OctTable& t, unsigned long long key) {
+  uint32_t slot = hashKey(key) & t.mask;
+  for (uint32_t probe = 0; probe <= t.mask; ++probe) {
+    const unsigned long long k = t.keys[slot];
+    if (k == key) return slot;
+    if (k == kOctEmptyKey) return kOctNone;
+    slot = (slot + 1) & t.mask;
+  }
+  return kOctNone;
+}
+
+// OctreePointCloud::adoptBoundingBoxToPoint's test: lower bounds inclusive, upper exclusive
+__device__ __forceinline__ bool outsideBox(const OctFrame& f, float x, float y, float z) {
+  const double px = x, py = y, pz = z;
+  return px < f.min[0] || py < f.min[1] || pz < f.min[2] || px >= f.max[0] || py >= f.max[1] ||
+         pz >= f.max[2];
+}
+
+__device__ __forceinline__ uint32_t ceilLog2(uint32_t v) {  // v >= 1
+  return v <= 1 ? 0u : 32u - __clz(v - 1);
+}
+
+// One point's adoptBoundingBoxToPoint (+ getKeyBitSize for the very first point); appends one
+// event per doubling.  Single thread.
+__device__ void growForPoint(OctFrames* F, float x, float y, float z, uint32_t seq, double res) {
+  const double eps = static_cast<double>(FLT_EPSILON);
+  const double p[3] = {static_cast<double>(x), static_cast<double>(y), static_cast<double>(z)};
+  if (F->n == 0) {
+    OctFrame f;
+    for (int a = 0; a < 3; ++a) {
+      f.min[a] = p[a] - res / 2;
+      f.max[a] = p[a] + res / 2;
+      f.shift[a] = 0;
+    }
+    uint32_t max_voxels = 2;
+    for (int a = 0; a < 3; ++a) {
+      const uint32_t mk = static_cast<uint32_t>(ceil((f.max[a] - f.min[a] - eps) / res));
+      max_voxels = mk > max_voxels ? mk : max_voxels;
+    }
+    // ceil(log2(max_voxels) - eps) of the reference: max_voxels is 2 for a single point
+    uint32_t depth = ceilLog2(max_voxels);
+    depth = depth > 32 ? 32 : depth;
+    const double side = static_cast<double>(1u << depth) * res;
+    for (int a = 0; a < 3; ++a) {
+      const double over = (side - (f.max[a] - f.min[a])) / 2.0;
+      if (over > eps) {
+        f.min[a] -= over;
+        f.max[a] += over;
+      }
+    }
+    f.depth = depth;
+    f.seq = seq;
+    F->f[0] = f;
+    for (int h = 0; h < 32; ++h) {
+      F->base[h][0] = F->base[h][1] = F->base[h][2] = 0;
+    }
+    for (int a = 0; a < 3; ++a) {
+      F->anchor_sigma[a] = static_cast<long long>(static_cast<uint32_t>((p[a] - f.min[a]) / res));
+    }
+    F->n = 1;
+    return;
+  }
+  OctFrame f = F->f[F->n - 1];
+  while (outsideBox(f, x, y, z)) {
+    if (F->n >= kOctMaxFrames || f.depth >= kOctMaxDepth) {
+      F->error |= 1u;
+      return;
+    }
+    const bool up[3] = {p[0] >= f.max[0], p[1] >= f.max[1], p[2] >= f.max[2]};
+    double side = static_cast<double>(1u << f.depth) * res;
+    for (int a = 0; a < 3; ++a) {
+      if (!up[a]) {
+        f.min[a] -= side;
+        f.shift[a] += 1ll << f.depth;
+      }
+      // height f.depth comes into existence: its partition is fixed from now on
+      F->base[f.depth][a] = f.shift[a] & ((1ll << f.depth) - 1);
+    }
+    ++f.depth;
+    side = static_cast<double>(1u << f.depth) * res - eps;
+    for (int a = 0; a < 3; ++a) f.max[a] = f.min[a] + side;
+    f.seq = seq;
+    F->f[F->n] = f;
+    F->n += 1;
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+octGrowKernel(OctFrames* F, const float4* __restrict__ xyz, const uint8_t* __restrict__ member,
+              uint32_t first, uint32_t n, double res) {
+  __shared__ uint32_t s_min;
+  __shared__ OctFrame s_frame;
+  __shared__ uint32_t s_events;
+  uint32_t cursor = first;
+  while (true) {
+    if (threadIdx.x == 0) {
+      s_min = kOctNone;
+      s_events = F->n;
+      if (F->n > 0) s_frame = F->f[F->n - 1];
+    }
+    __syncthreads();
+    const bool defined = s_events > 0;
+    for (uint32_t i = cursor + threadIdx.x; i < n; i += blockDim.x) {
+      if (member && !member[i]) continue;
+      const float4 p = xyz[i];
+      if (!defined || outsideBox(s_frame, p.x, p.y, p.z)) {
+        atomicMin(&s_min, i);
+        break;  // this thread's indices ascend: the first hit is its minimum
+      }
+    }
+    __syncthreads();
+    const uint32_t m = s_min;
+    if (m == kOctNone) break;
+    if (threadIdx.x == 0) {
+      const float4 p = xyz[m];
+      growForPoint(F, p.x, p.y, p.z, m, res);
+    }
+    __syncthreads();
+    if (F->error) break;
+    cursor = m + 1;
+  }
+}
+
+// frame in force when point `seq` is inserted: the last event with f.seq <= seq
+__device__ __forceinline__ int insertionFrame(const OctFrames* F, uint32_t seq) {
+  int e = -1;
+  for (uint32_t i = 0; i < F->n; ++i) {
+    if (F->f[i].seq <= seq) e = static_cast<int>(i);
+  }
+  return e;
+}
+// frame in force when point `seq` is examined: the last event caused by an earlier point
+__device__ __forceinline__ int queryFrame(const OctFrames* F, uint32_t seq) {
+  int e = -1;
+  for (uint32_t i = 0; i < F->n; ++i) {
+    if (F->f[i].seq < seq) e = static_cast<int>(i);
+  }
+  return e;
+}
+
+__global__ void __launch_bounds__(256)
+octInsertKernel(OctFrames* F, const OctTable t, const OctPoints pts,
+                const uint8_t* __restrict__ member, uint32_t first, uint32_t n, double res) {
+  const uint32_t i = first + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (member && !member[i]) return;
+  const int e = insertionFrame(F, i);
+  if (e < 0) return;  // unreachable: growth ran over the same members
+  const OctFrame& fi = F->f[e];
+  const float4 p = pts.xyz[i];
+  // OctreePointCloud::genOctreeKeyforPoint at insertion time, then made stable
+  const long long sx = static_cast<long long>(static_cast<uint32_t>((static_cast<double>(p.x) - fi.min[0]) / res)) - fi.shift[0];
+  const long long sy = static_cast<long long>(static_cast<uint32_t>((static_cast<double>(p.y) - fi.min[1]) / res)) - fi.shift[1];
+  const long long sz = static_cast<long long>(static_cast<uint32_t>((static_cast<double>(p.z) - fi.min[2]) / res)) - fi.shift[2];
+  pts.sigma[i] = make_int4(static_cast<int>(sx), static_cast<int>(sy), static_cast<int>(sz), 0);
+  const int depth = static_cast<int>(F->f[F->n - 1].depth);
+  for (int h = 0; h < depth; ++h) {
+    unsigned long long key;
+    if (!packKey(h, (sx + F->base[h][0]) >> h, (sy + F->base[h][1]) >> h,
+                 (sz + F->base[h][2]) >> h, &key)) {
+      atomicOr(&F->error, 2u);
+      return;
+    }
+    const uint32_t slot = tableInsert(t, key, i);
+    if (slot == kOctNone) {
+      atomicOr(&F->error, 4u);
+      return;
+    }
+    if (h == 0) pts.next[i] = atomicExch(t.head + slot, i);
+  }
+}
+
+__global__ void octRootChainKernel(OctFrames* F, const OctTable t) {
+  if (threadIdx.x != 0 || blockIdx.x != 0 || F->n == 0) return;
+  const int depth = static_cast<int>(F->f[F->n - 1].depth);
+  const uint32_t seq = F->f[0].seq;
+  for (int h = static_cast<int>(F->f[0].depth); h < depth; ++h) {
+    unsigned long long key;
+    if (!packKey(h, (F->anchor_sigma[0] + F->base[h][0]) >> h,
+                 (F->anchor_sigma[1] + F->base[h][1]) >> h,
+                 (F->anchor_sigma[2] + F->base[h][2]) >> h, &key)) {
+      F->error |= 2u;
+      return;
+    }
+    if (tableInsert(t, key, seq) == kOctNone) {
+      F->error |= 4u;
+      return;
+    }
+  }
+}
+
+// OctreePointCloudSearch::approxNearestSearchRecursive on the implicit tree as of `limit_seq`:
+// per level the existing child with the strictly smallest voxel-centre distance (first child
+// index wins ties), at the leaf the point with the strictly smallest d^2 in insertion order.
+__device__ int approxNearest(const OctFrames* F, const OctFrame& fr, const OctTable& t,
+                             const float4* __restrict__ pts, const uint32_t* __restrict__ next,
+                             float qx, float qy, float qz, uint32_t limit_seq, double res,
+                             float* out_d2) {
+  long long kx = 0, ky = 0, kz = 0;
+  const int depth = static_cast<int>(fr.depth);
+  uint32_t leaf_slot = kOctNone;
+  for (int td = 1; td <= depth; ++td) {
+    const int h = depth - td;
+    const double side = __dmul_rn(res, static_cast<double>(1u << h));
+    const long long ox = (fr.shift[0] - F->base[h][0]) >> h;
+    const long long oy = (fr.shift[1] - F->base[h][1]) >> h;
+    const long long oz = (fr.shift[2] - F->base[h][2]) >> h;
+    double best = DBL_MAX;
+    int best_c = -1;
+    uint32_t best_slot = kOctNone;
+    for (int c = 0; c < 8; ++c) {
+      const long long nx = (kx << 1) + ((c >> 2) & 1);
+      const long long ny = (ky << 1) + ((c >> 1) & 1);
+      const long long nz = (kz << 1) + (c & 1);
+      unsigned long long key;
+      if (!packKey(h, nx - ox, ny - oy, nz - oz, &key)) continue;
+      const uint32_t slot = tableFind(t, key);
+      if (slot == kOctNone || t.minseq[slot] >= limit_seq) continue;
+      // genVoxelCenterFromOctreeKey: double arithmetic, float result
+      const float cx = __double2float_rn(__dadd_rn(__dmul_rn(__dadd_rn(static_cast<double>(nx), 0.5), side), fr.min[0]));
+      const float cy = __double2float_rn(__dadd_rn(__dmul_rn(__dadd_rn(static_cast<double>(ny), 0.5), side), fr.min[1]));
+      const float cz = __double2float_rn(__dadd_rn(__dmul_rn(__dadd_rn(static_cast<double>(nz), 0.5), side), fr.min[2]));
+      const double d = static_cast<double>(dist2Exact(cx, cy, cz, qx, qy, qz));
+      if (d >= best) continue;
+      best = d;
+      best_c = c;
+      best_slot = slot;
+    }
+    if (best_c < 0) return -1;  // PCL asserts; unreachable below an existing root
+    kx = (kx << 1) + ((best_c >> 2) & 1);
+    ky = (ky << 1) + ((best_c >> 1) & 1);
+    kz = (kz << 1) + (best_c & 1);
+    leaf_slot = best_slot;
+  }
+  if (leaf_slot == kOctNone) return -1;
+  float smallest = FLT_MAX;
+  uint32_t result = kOctNone;
+  for (uint32_t j = t.head[leaf_slot]; j != kOctNone; j = next[j]) {
+    if (j >= limit_seq) continue;
+    const float4 p = pts[j];
+    const float d2 = dist2Exact(p.x, p.y, p.z, qx, qy, qz);
+    // `if (d2 >= smallest) continue` in insertion order == argmin over (d2, insertion order)
+    if (d2 < smallest || (d2 == smallest && j < result)) {
+      smallest = d2;
+      result = j;
+    }
+  }
+  if (result == kOctNone) return -1;
+  *out_d2 = smallest;
+  return static_cast<int>(result);
+}
+
+// OctreeCompression::inOctree (octree_compression.cpp:17-40)
+__device__ int inOctree(const OctFrames* F, int frame, const OctTable& t,
+                        const float4* __restrict__ pts, const uint32_t* __restrict__ next, float qx,
+                        float qy, float qz, uint32_t limit_seq, double res) {
+  if (frame < 0) return -1;  // getLeafCount() == 0
+  const OctFrame& fr = F->f[frame];
+  const double px = qx, py = qy, pz = qz;
+  const bool in_box = (px >= fr.min[0] && px <= fr.max[0]) && (py >= fr.min[1] && py <= fr.max[1]) &&
+                      (pz >= fr.min[2] && pz <= fr.max[2]);
+  if (!in_box) return -1;
+  const double threshold = __dmul_rn(res, res);
+  float sqr_distance = static_cast<float>(threshold + 1.0);
+  float d2 = 0.f;
+  const int idx = approxNearest(F, fr, t, pts, next, qx, qy, qz, limit_seq, res, &d2);
+  if (idx >= 0) sqr_distance = d2;
+  if (static_cast<double>(sqr_distance) >= threshold) return -1;
+  return idx;
+}
+
+__global__ void __launch_bounds__(128)
+octQueryPersistentKernel(const OctFrames* F, const OctTable t, const float4* __restrict__ act_xyz,
+                         const uint32_t* __restrict__ next, const float* __restrict__ xyz,
+                         uint32_t n, double res, int32_t* __restrict__ result) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int frame = static_cast<int>(F->n) - 1;
+  result[i] = inOctree(F, frame, t, act_xyz, next, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2],
+                       kOctNone, res);
+}
+
+__global__ void __launch_bounds__(128)
+octDecideTempKernel(const OctFrames* F, const OctTable t, const float4* __restrict__ cand_xyz,
+                    const uint32_t* __restrict__ next, uint32_t n_cand, double res,
+                    const uint8_t* __restrict__ member_in, uint8_t* __restrict__ member_out,
+                    int32_t* __restrict__ decision, uint32_t* __restrict__ changed) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_cand) return;
+  const float4 q = cand_xyz[c];
+  const int d = inOctree(F, queryFrame(F, c), t, cand_xyz, next, q.x, q.y, q.z, c, res);
+  decision[c] = d;
+  const uint8_t m = d < 0 ? 1 : 0;
+  member_out[c] = m;
+  if (m != member_in[c]) atomicOr(changed, 1u);
+}
+
+}  // namespace
+
+cudaError_t launchOctGrow(OctFrames* frames, const float4* xyz, const uint8_t* member,
+                          uint32_t first, uint32_t n, double resolution, cudaStream_t stream) {
+  if (first >= n) return cudaSuccess;
+  octGrowKernel<<<1, 1024, 0, stream>>>(frames, xyz, member, first, n, resolution);
+  return cudaGetLastError();
+}
+
+cudaError_t launchOctInsert(OctFrames* frames, OctTable table, OctPoints pts,
+                            const uint8_t* member, uint32_t first, uint32_t n, double resolution,
+                            cudaStream_t stream) {
+  if (first >= n) return cudaSuccess;
+  octInsertKernel<<<(n - first + 255) / 256, 256, 0, stream>>>(frames, table, pts, member, first, n,
+                                                               resolution);
+  return cudaGetLastError();
+}
+
+cudaError_t launchOctInsertRootChain(OctFrames* frames, OctTable table, cudaStream_t stream) {
+  octRootChainKernel<<<1, 32, 0, stream>>>(frames, table);
+  return cudaGetLastError();
+}
+
+cudaError_t launchOctQueryPersistent(const OctFrames* frames, OctTable table, const float4* act_xyz,
+                                     const uint32_t* next, const float* xyz, uint32_t n,
+                                     double resolution, int32_t* result, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  octQueryPersistentKernel<<<(n + 127) / 128, 128, 0, stream>>>(frames, table, act_xyz, next, xyz, n,
+                                                               resolution, result);
+  return cudaGetLastError();
+}
+
+cudaError_t launchOctDecideTemp(const OctFrames* frames, OctTable table, const float4* cand_xyz,
+                                const uint32_t* next, uint32_t n_cand, double resolution,
+                                const uint8_t* member_in, uint8_t* member_out, int32_t* decision,
+                                uint32_t* changed, cudaStream_t stream) {
+  if (n_cand == 0) return cudaSuccess;
+  octDecideTempKernel<<<(n_cand + 127) / 128, 128, 0, stream>>>(
+      frames, table, cand_xyz, next, n_cand, resolution, member_in, member_out, decision, changed);
+  return cudaGetLastError();
+}
+
+}  // namespace pgmo

@@ -34,31 +34,33 @@ def merge_stretch_lists(lists):
     """Concatenates per-rank (stamps, lens) in rank order, fusing a stretch that continues across
     a slab boundary (the same stamp at the end of rank r and the start of rank r + 1), so that
     the result equals the stretch list of the unsharded stamp stream."""
-    stamps, lens = [], []
-    for ss, sl in lists:
-        for s, l in zip(ss.tolist(), sl.tolist()):
-            if l == 0:
-                continue
-            if stamps and stamps[-1] == s:
-                lens[-1] += l
-            else:
-                stamps.append(s)
-                lens.append(l)
-    return np.array(stamps, dtype=np.uint64), np.array(lens, dtype=np.uint64)
+    ss = np.concatenate([np.asarray(a, dtype=np.uint64) for a, _ in lists]) if lists else np.zeros(0, np.uint64)
+    sl = np.concatenate([np.asarray(b, dtype=np.uint64) for _, b in lists]) if lists else np.zeros(0, np.uint64)
+    keep = sl > 0
+    ss, sl = ss[keep], sl[keep]
+    if ss.shape[0] == 0:
+        return ss, sl
+    head = np.concatenate([[True], ss[1:] != ss[:-1]])
+    starts = np.flatnonzero(head)
+    return ss[starts].copy(), np.add.reduceat(sl, starts).astype(np.uint64)
 
 
 class StretchExchange:
     """all_gather of variable-length stretch lists through one fixed-size int64 tensor
-    (count, stamps[cap], lens[cap]) per rank; works on any torch.distributed backend."""
+    (count, stamps[cap], lens[cap]) per rank; works on any torch.distributed backend.  The
+    result is cached: when no rank's local list changed since the last call (one 1-element
+    all_reduce), the cached global list is returned without moving anything."""
 
-    def __init__(self, world: int, device, cap: int = 1 << 15):
+    def __init__(self, world: int, device, cap: int = 1 << 13):
         import torch
         self.world = world
         self.cap = cap
         self.device = device
         self._torch = torch
-        self._buf = (torch.zeros(world * (2 * cap + 1), dtype=torch.int64, device=device)
-                     if world > 1 else None)
+        self._buf = None
+        self._last_local = None
+        self._last_global = None
+        self._flag = torch.zeros(1, dtype=torch.int64, device=device) if world > 1 else None
 
     def __call__(self, ss: np.ndarray, sl: np.ndarray):
         if self.world == 1:
@@ -66,19 +68,34 @@ class StretchExchange:
         import torch.distributed as dist
         torch = self._torch
         n = ss.shape[0]
-        if n > self.cap:
-            raise ValueError(f"{n} stretches exceed the exchange capacity {self.cap}")
+        same = (self._last_local is not None and np.array_equal(self._last_local[0], ss)
+                and np.array_equal(self._last_local[1], sl))
+        # value = 0 if unchanged, else the capacity this rank needs
+        self._flag[0] = 0 if same else max(n, 1)
+        dist.all_reduce(self._flag, op=dist.ReduceOp.MAX)
+        need = int(self._flag.item())
+        if need == 0:
+            return self._last_global
+        while self.cap < need:
+            self.cap *= 2
+            self._buf = None
+        if self._buf is None:
+            self._buf = torch.zeros(self.world * (2 * self.cap + 1), dtype=torch.int64,
+                                    device=self.device)
         mine = torch.zeros(2 * self.cap + 1, dtype=torch.int64)
         mine[0] = n
         mine[1:1 + n] = torch.from_numpy(ss.view(np.int64))
         mine[1 + self.cap:1 + self.cap + n] = torch.from_numpy(sl.view(np.int64))
-        dist.all_gather_into_tensor(self._buf, mine.to(self.device, non_blocking=True))
+        dist.all_gather_into_tensor(self._buf, mine.to(self.device))
         g = self._buf.cpu().numpy().reshape(self.world, 2 * self.cap + 1)
         lists = []
         for r in range(self.world):
             m = int(g[r, 0])
-            lists.append((g[r, 1:1 + m].view(np.uint64), g[r, 1 + self.cap:1 + self.cap + m].view(np.uint64)))
-        return merge_stretch_lists(lists)
+            lists.append((g[r, 1:1 + m].view(np.uint64),
+                          g[r, 1 + self.cap:1 + self.cap + m].view(np.uint64)))
+        self._last_local = (ss.copy(), sl.copy())
+        self._last_global = merge_stretch_lists(lists)
+        return self._last_global
 
 
 def broadcast_controls(tensors, src: int = 0):
