@@ -226,20 +226,35 @@ def run_b200(args):
 
     knn_ms, res_ms = [], []
 
+    phases = os.environ.get("PGMO_BENCH_PHASES") == "1"
+    phase_ms = {}
+
+    def _mark(name, t0):
+        if phases:
+            torch.cuda.synchronize()
+            phase_ms[name] = phase_ms.get(name, 0.0) + 1e3 * (time.perf_counter() - t0)
+        return time.perf_counter()
+
     def step(record=False):
+        t0 = time.perf_counter()
         # 1. a new solve result: poses replicated to every GPU
         if world > 1:
             dist.broadcast(d_poses, src=0)
         h.update_poses_device(d_poses, stream)
+        t0 = _mark("poses", t0)
         # 2. stamp stretches of the local slab, exchanged so that every rank replays the same
         #    window state machine (cached when nothing changed)
         ss, sl = h.stamp_stretches_device(d_stamps, n_local, stream)
+        t0 = _mark("stretches", t0)
         ss, sl = exchange_stretches(ss, sl)
+        t0 = _mark("exchange", t0)
         rc = h.build_schedule(ss, sl, n_total, K_NEIGHBOURS, TOL_T)
         assert rc == 0
+        t0 = _mark("schedule", t0)
         # 3. deform this rank's slab
         h.run_device(first, n_local, d["x"], d["y"], d["z"], d_out[0], d_out[1], d_out[2],
                      precision=precision, stream=stream)
+        t0 = _mark("run", t0)
         if record:
             a, b, _ = h.last_timings()
             knn_ms.append(a)
@@ -320,6 +335,9 @@ def run_b200(args):
                "api": "pgmo_deform_update_poses + pgmo_deform_points (host pointers)" if world == 1
                else "pinned H2D + pgmo_deform_*_device + pinned D2H per rank"}
 
+    if phases and rank == 0:
+        print("phase ms per step:", {k: v / (args.steps + max(args.warmup, 3) + 1) for k, v in phase_ms.items()},
+              file=sys.stderr)
     if rank == 0:
         peak, peak_kind = measured_peak_gbs()
         knn = float(np.mean(knn_ms))
