@@ -608,7 +608,7 @@ static int runDeviceRange(pgmo_deform_t* h, uint64_t first_position, uint64_t n_
     }
     if (h->grid_mode == 1) {
       PGMO_CUDA(launchDeformKnnBlendSorted(a, ga, h->d_items.ptr + i0, i1 - i0, precision,
-                                           h->sched.max_k, st));
+                                           h->sched.max_k, h->widest_window, st));
       if (h->widest_window > static_cast<uint64_t>(kSortedMaxPoints)) {
         PGMO_CUDA(launchDeformKnnBlendGrid(a, ga, h->d_items.ptr + i0, i1 - i0, precision,
                                            h->sched.max_k, kSortedMaxPoints, st));

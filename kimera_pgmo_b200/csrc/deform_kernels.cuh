@@ -119,7 +119,7 @@ cudaError_t launchDeformKnnBlendGrid(const DeformArgs& args, const GridArgs& gar
 // alive points and leaves the others untouched.  Same result as the other two K3 kernels.
 cudaError_t launchDeformKnnBlendSorted(const DeformArgs& args, const GridArgs& gargs,
                                        const WorkItem* items, uint32_t n_items, int precision,
-                                       uint32_t max_k, cudaStream_t stream);
+                                       uint32_t max_k, uint64_t widest_window, cudaStream_t stream);
 
 // K4: PCL-order resolution of the vertices flagged kStatusNeedsTie.
 cudaError_t launchDeformResolve(const DeformArgs& args, const ResolveArgs& rargs, int precision,

@@ -24,10 +24,16 @@
 //     they are re-ordered on their exact d^2 in registers; exact ties (and near ties that
 //     touch the last tracked slot) are handed to the PCL-order resolver (K4), which is exact.
 //
+//   * The pose table rows of the run's alive points (R, t, g: 15 doubles, or floats in FP32
+//     mode) are staged in shared memory as SoA when the alive set has <= 256 points, so that
+//     the blend's 75 gathered loads per vertex are conflict-free LDS instead of L2 round trips
+//     (profiles/r01e: the gathers were 1/3 of all stall samples and most of the LSU traffic).
+//
 // The result is bit-identical to the brute-force and grid-walk kernels (tests/test_deform_gpu.py
 // ::test_search_modes_agree).  Runs with more than kSMaxPts alive points stay on the grid-walk
 // kernel (deform_grid.cu).
 #include <cfloat>
+#include <type_traits>
 
 #include "deform_device.cuh"
 
@@ -40,28 +46,41 @@ using namespace dev;
 constexpr int kSThreads = 256;
 constexpr int kSWarps = kSThreads / 32;
 constexpr int kSChunk = kDeformChunk;  // positions per work item
-constexpr int kSMaxPts = kSortedMaxPoints;
 constexpr int kSBuckets = 32;
 constexpr int kSMaxCells = 1024;       // sort bins (8 per tile)
-constexpr int kSlotBits = 9;           // kSMaxPts = 512
-static_assert((1 << kSlotBits) == kSMaxPts, "slot bits");
+constexpr int kStagedMaxPts = 256;     // alive-set size up to which the pose rows are staged
 
+template <int MAXPTS>
+struct SlotBits {
+  static constexpr int value = MAXPTS == 512 ? 9 : 8;
+};
+static_assert(kSortedMaxPoints == 512, "slot bits");
+
+// pose rows of the alive points, SoA: component c of slot s at row[c][s]
+template <typename T, int MAXPTS>
+struct PoseRows {
+  T row[15][MAXPTS];  // R0..R8, t0..t2, g0..g2
+};
+struct NoPoseRows {};
+
+template <int MAXPTS, typename POSE>
 struct SortedSmem {
-  float4 pts[kSMaxPts];                     // alive control points: x, y, z, index (int bits);
+  float4 pts[MAXPTS];                       // alive control points: x, y, z, index (int bits);
                                             // pts[n_alive] = a point at infinity when n_alive % 4 != 0
   float vx[kSChunk], vy[kSChunk], vz[kSChunk];
   uint16_t perm[kSChunk];                   // sorted position -> vertex of the item
   union alignas(16) {
     uint32_t hist[kSMaxCells + 1];          // vertex sort only
     struct {
-      uint16_t tmp[kSWarps][kSMaxPts];      // per point: bucket << 9 | rank inside the bucket
-      uint16_t list[kSWarps][kSMaxPts + 8]; // bucket-ordered: bucket << 9 | point slot
+      uint16_t tmp[kSWarps][MAXPTS];        // per point: bucket << slot bits | rank in the bucket
+      uint16_t list[kSWarps][MAXPTS + 8];   // bucket-ordered: bucket << slot bits | point slot
     } w;
   } u;
   uint32_t bcnt[kSWarps][kSBuckets];
   float red[6][kSWarps];
   uint32_t warp_tot[kSWarps];
   float grid[8];                            // origin xyz, inv cell, nx, ny, nz (as float bits)
+  alignas(16) POSE pose;
 };
 
 template <int KCAP>
@@ -91,12 +110,109 @@ __device__ __forceinline__ int clampCell(float p, float origin, float inv_cell, 
   return c >= n ? n - 1 : c;
 }
 
-template <int KCAP, int PREC>
-__global__ void __launch_bounds__(kSThreads, 4)
+// interpPoint's blend with the pose rows read from shared memory (same arithmetic, operation
+// for operation, as dev::writeResultReg).  nbr_slot: slots of the neighbours in S.pts / S.pose.
+template <int KCAP, int PREC, typename Smem>
+__device__ __forceinline__ void writeResultStaged(const DeformArgs& a, const Smem& S, uint64_t p,
+                                                  uint64_t ii, float qx, float qy, float qz,
+                                                  const float (&nbr_d2)[KCAP],
+                                                  const int (&nbr_slot)[KCAP], int n) {
+  float last_d2 = nbr_d2[0];
+#pragma unroll
+  for (int j = 1; j < KCAP; ++j) last_d2 = j < n ? fmaxf(last_d2, nbr_d2[j]) : last_d2;
+  if constexpr (PREC == 0) {
+    const float d_max_f = __fsqrt_rn(last_d2);
+    const double d_max = static_cast<double>(d_max_f);
+    const bool const_w = (__fsqrt_rn(nbr_d2[0]) == d_max_f) || d_max == 0.0;
+    double wsum = 0.0, acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
+    const double v0 = static_cast<double>(qx), v1 = static_cast<double>(qy),
+                 v2 = static_cast<double>(qz);
+#pragma unroll
+    for (int j = 0; j < KCAP; ++j) {
+      if (j < n - 1) {
+        const int s = nbr_slot[j];
+        const double w =
+            const_w ? 1.0
+                    : __dsub_rn(1.0, __ddiv_rn(static_cast<double>(__fsqrt_rn(nbr_d2[j])), d_max));
+        wsum = __dadd_rn(wsum, w);
+        const double p0 = __dsub_rn(v0, S.pose.row[12][s]);
+        const double p1 = __dsub_rn(v1, S.pose.row[13][s]);
+        const double p2 = __dsub_rn(v2, S.pose.row[14][s]);
+        const double r0 = __dadd_rn(__dadd_rn(__dmul_rn(S.pose.row[0][s], p0), __dmul_rn(S.pose.row[1][s], p1)), __dmul_rn(S.pose.row[2][s], p2));
+        const double r1 = __dadd_rn(__dadd_rn(__dmul_rn(S.pose.row[3][s], p0), __dmul_rn(S.pose.row[4][s], p1)), __dmul_rn(S.pose.row[5][s], p2));
+        const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(S.pose.row[6][s], p0), __dmul_rn(S.pose.row[7][s], p1)), __dmul_rn(S.pose.row[8][s], p2));
+        acc0 = __dadd_rn(acc0, __dmul_rn(w, __dadd_rn(r0, S.pose.row[9][s])));
+        acc1 = __dadd_rn(acc1, __dmul_rn(w, __dadd_rn(r1, S.pose.row[10][s])));
+        acc2 = __dadd_rn(acc2, __dmul_rn(w, __dadd_rn(r2, S.pose.row[11][s])));
+      }
+    }
+    const double o0 = __ddiv_rn(acc0, wsum), o1 = __ddiv_rn(acc1, wsum), o2 = __ddiv_rn(acc2, wsum);
+    a.ox[ii] = __double2float_rn(o0);
+    a.oy[ii] = __double2float_rn(o1);
+    a.oz[ii] = __double2float_rn(o2);
+    if (a.of64) {
+      a.of64[3 * p + 0] = o0;
+      a.of64[3 * p + 1] = o1;
+      a.of64[3 * p + 2] = o2;
+    }
+  } else {
+    const float d_max = __fsqrt_rn(last_d2);
+    const bool const_w = (__fsqrt_rn(nbr_d2[0]) == d_max) || d_max == 0.0f;
+    const float inv_dmax = const_w ? 0.0f : __frcp_rn(d_max);
+    float wsum = 0.f, acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < KCAP; ++j) {
+      if (j < n - 1) {
+        const int s = nbr_slot[j];
+        const float w = const_w ? 1.0f : 1.0f - __fsqrt_rn(nbr_d2[j]) * inv_dmax;
+        wsum += w;
+        const float p0 = qx - S.pose.row[12][s], p1 = qy - S.pose.row[13][s],
+                    p2 = qz - S.pose.row[14][s];
+        acc0 += w * (S.pose.row[0][s] * p0 + S.pose.row[1][s] * p1 + S.pose.row[2][s] * p2 + S.pose.row[9][s]);
+        acc1 += w * (S.pose.row[3][s] * p0 + S.pose.row[4][s] * p1 + S.pose.row[5][s] * p2 + S.pose.row[10][s]);
+        acc2 += w * (S.pose.row[6][s] * p0 + S.pose.row[7][s] * p1 + S.pose.row[8][s] * p2 + S.pose.row[11][s]);
+      }
+    }
+    const float o0 = acc0 / wsum, o1 = acc1 / wsum, o2 = acc2 / wsum;
+    a.ox[ii] = o0;
+    a.oy[ii] = o1;
+    a.oz[ii] = o2;
+    if (a.of64) {
+      a.of64[3 * p + 0] = o0;
+      a.of64[3 * p + 1] = o1;
+      a.of64[3 * p + 2] = o2;
+    }
+  }
+  if (a.assoc) {
+#pragma unroll
+    for (int j = 0; j < KCAP; ++j) {
+      if (static_cast<uint32_t>(j) < a.assoc_stride) {
+        a.assoc[p * a.assoc_stride + j] =
+            (j < n - 1) ? static_cast<uint32_t>(__float_as_int(S.pts[nbr_slot[j]].w)) : 0xFFFFFFFFu;
+      }
+    }
+    for (uint32_t j = KCAP; j < a.assoc_stride; ++j) a.assoc[p * a.assoc_stride + j] = 0xFFFFFFFFu;
+  }
+  if (a.assoc_cnt) a.assoc_cnt[p] = static_cast<uint8_t>(n - 1 > 255 ? 255 : n - 1);
+}
+
+template <int PREC, int MAXPTS, bool STAGE>
+struct SmemOf {
+  using Pose = typename std::conditional<
+      STAGE, typename std::conditional<PREC == 0, PoseRows<double, MAXPTS>, PoseRows<float, MAXPTS>>::type,
+      NoPoseRows>::type;
+  using type = SortedSmem<MAXPTS, Pose>;
+};
+
+template <int KCAP, int PREC, int MAXPTS, bool STAGE>
+__global__ void __launch_bounds__(kSThreads, STAGE ? 3 : 4)
 deformKnnBlendSortedKernel(const DeformArgs a, const GridArgs ga,
                            const WorkItem* __restrict__ items) {
+  using Smem = typename SmemOf<PREC, MAXPTS, STAGE>::type;
+  constexpr int kSMaxPts = MAXPTS;
+  constexpr int kSlotBits = SlotBits<MAXPTS>::value;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  SortedSmem& S = *reinterpret_cast<SortedSmem*>(smem_raw);
+  Smem& S = *reinterpret_cast<Smem*>(smem_raw);
 
   const WorkItem item = items[blockIdx.x];
   const uint32_t r = item.run;
@@ -111,7 +227,7 @@ deformKnnBlendSortedKernel(const DeformArgs a, const GridArgs ga,
   }
   const RunGridDev g = ga.grids[r];
   const int n_alive = static_cast<int>(g.n_alive);
-  if (n_alive > kSMaxPts) return;  // grid-walk kernel's item
+  if (n_alive > kSMaxPts) return;  // another kernel's item
   const int K = static_cast<int>(info.z) + 2;
   if (K + 1 > KCAP) {
     for (int i = t; i < count; i += kSThreads) a.status[p_base + i] = kStatusNeedsTie;
@@ -125,6 +241,19 @@ deformKnnBlendSortedKernel(const DeformArgs a, const GridArgs ga,
     for (int i = t; i < n_alive; i += kSThreads) S.pts[i] = __ldg(src + i);
     // list padding (see the walk): d^2 to this point is +inf for every finite query
     if (t == 0 && (n_alive & 3)) S.pts[n_alive] = make_float4(3e30f, 3e30f, 3e30f, __int_as_float(-1));
+    if constexpr (STAGE) {
+      // pose rows of the alive points: component-major so that lanes reading one component of
+      // different slots never collide on a bank
+      for (int e = t; e < n_alive * 15; e += kSThreads) {
+        const int s_ = e / 15, c = e - s_ * 15;
+        const int j = __float_as_int(__ldg(src + s_).w);
+        if constexpr (PREC == 0) {
+          S.pose.row[c][s_] = c < 12 ? a.poses[12ull * j + c] : a.ctrl_pos[3ull * j + (c - 12)];
+        } else {
+          S.pose.row[c][s_] = a.ctrl_pose_f32[16ull * j + c];  // R(9) t(3) g(3)
+        }
+      }
+    }
   }
   float mn0 = FLT_MAX, mn1 = FLT_MAX, mn2 = FLT_MAX, mx0 = -FLT_MAX, mx1 = -FLT_MAX,
         mx2 = -FLT_MAX;
@@ -290,17 +419,35 @@ deformKnnBlendSortedKernel(const DeformArgs a, const GridArgs ga,
     // pass 1: bucket = floor(lower bound of d^2(point, box) / bw); rank inside the bucket
     bcnt[lane] = 0;
     __syncwarp();
-    for (int i = lane; i < n_alive; i += 32) {
-      const float4 c = S.pts[i];
-      const float ax = fmaxf(fmaxf(lox - c.x, c.x - hix), 0.f);
-      const float ay = fmaxf(fmaxf(loy - c.y, c.y - hiy), 0.f);
-      const float az = fmaxf(fmaxf(loz - c.z, c.z - hiz), 0.f);
-      // 0.9999: the bound must hold against the separately rounded exact d^2 of every lane
-      const float m = (ax * ax + ay * ay + az * az) * 0.9999f;
-      int b = static_cast<int>(fminf(m * inv_bw, static_cast<float>(kSBuckets - 1)));
-      b = b < 0 ? 0 : b;  // NaN coordinates
-      const uint32_t rank = atomicAdd(&bcnt[b], 1u);
-      tmp[i] = static_cast<uint16_t>((b << kSlotBits) | rank);
+    for (int i0 = 0; i0 < n_alive; i0 += 32) {
+      const int i = i0 + lane;
+      const bool valid = i < n_alive;
+      int b = kSBuckets + lane;  // idle lanes: a key nobody shares
+      if (valid) {
+        const float4 c = S.pts[i];
+        const float ax = fmaxf(fmaxf(lox - c.x, c.x - hix), 0.f);
+        const float ay = fmaxf(fmaxf(loy - c.y, c.y - hiy), 0.f);
+        const float az = fmaxf(fmaxf(loz - c.z, c.z - hiz), 0.f);
+        // 0.9999: the bound must hold against the separately rounded exact d^2 of every lane
+        const float m = (ax * ax + ay * ay + az * az) * 0.9999f;
+        b = static_cast<int>(fminf(m * inv_bw, static_cast<float>(kSBuckets - 1)));
+        b = b < 0 ? 0 : b;  // NaN coordinates
+      }
+      // rank inside the bucket: lanes of this round that share b are ranked by lane; the lowest
+      // of them advances the bucket's counter for everybody (no shared-memory atomics)
+      const unsigned peers = __match_any_sync(full, b);
+      const int leader = __ffs(peers) - 1;
+      uint32_t base = 0;
+      if (valid && lane == leader) {
+        base = bcnt[b];
+        bcnt[b] = base + __popc(peers);
+      }
+      base = __shfl_sync(full, base, leader);
+      if (valid) {
+        const uint32_t rank = base + __popc(peers & ((1u << lane) - 1u));
+        tmp[i] = static_cast<uint16_t>((b << kSlotBits) | rank);
+      }
+      __syncwarp();
     }
     __syncwarp();
     {
@@ -369,9 +516,10 @@ deformKnnBlendSortedKernel(const DeformArgs a, const GridArgs ga,
       nbr_d2[i] = FLT_MAX;
       nbr_idx[i] = -1;
       if (i < n_need) {
-        const float4 c = S.pts[list[best[i] & ord_mask] & (kSMaxPts - 1)];
+        const int slot_i = list[best[i] & ord_mask] & (kSMaxPts - 1);
+        const float4 c = S.pts[slot_i];
         nbr_d2[i] = dist2Exact(c.x, c.y, c.z, qx, qy, qz);
-        nbr_idx[i] = __float_as_int(c.w);
+        nbr_idx[i] = STAGE ? slot_i : __float_as_int(c.w);  // staged: the slot, resolved at the end
       }
       if (i > 0 && i < n_need && (best[i] >> ord_bits) == (best[i - 1] >> ord_bits)) {
         near = true;
@@ -428,41 +576,55 @@ deformKnnBlendSortedKernel(const DeformArgs a, const GridArgs ga,
       atomicAdd(a.counters, 1ull);
       continue;
     }
-    writeResultReg<KCAP>(a, p, ii, PREC, qx, qy, qz, nbr_d2, nbr_idx, n);
+    if constexpr (STAGE) {
+      writeResultStaged<KCAP, PREC>(a, S, p, ii, qx, qy, qz, nbr_d2, nbr_idx, n);
+    } else {
+      writeResultReg<KCAP>(a, p, ii, PREC, qx, qy, qz, nbr_d2, nbr_idx, n);
+    }
     a.status[p] = kStatusDone;
   }
 }
 
-template <int KCAP, int PREC>
+template <int KCAP, int PREC, int MAXPTS, bool STAGE>
 cudaError_t launchOne(const DeformArgs& args, const GridArgs& gargs, const WorkItem* items,
                       uint32_t n_items, cudaStream_t stream) {
-  const size_t smem = sizeof(SortedSmem);
+  const size_t smem = sizeof(typename SmemOf<PREC, MAXPTS, STAGE>::type);
   static thread_local int configured_device = -1;
   int device = 0;
   cudaGetDevice(&device);
   if (configured_device != device) {
     const cudaError_t e =
-        cudaFuncSetAttribute(deformKnnBlendSortedKernel<KCAP, PREC>,
+        cudaFuncSetAttribute(deformKnnBlendSortedKernel<KCAP, PREC, MAXPTS, STAGE>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
     configured_device = device;
   }
-  deformKnnBlendSortedKernel<KCAP, PREC><<<n_items, kSThreads, smem, stream>>>(args, gargs, items);
+  deformKnnBlendSortedKernel<KCAP, PREC, MAXPTS, STAGE>
+      <<<n_items, kSThreads, smem, stream>>>(args, gargs, items);
   return cudaGetLastError();
+}
+
+template <int KCAP, int PREC>
+cudaError_t launchVariant(const DeformArgs& args, const GridArgs& gargs, const WorkItem* items,
+                          uint32_t n_items, bool staged, cudaStream_t stream) {
+  return staged ? launchOne<KCAP, PREC, kStagedMaxPts, true>(args, gargs, items, n_items, stream)
+                : launchOne<KCAP, PREC, kSortedMaxPoints, false>(args, gargs, items, n_items, stream);
 }
 
 }  // namespace
 
 cudaError_t launchDeformKnnBlendSorted(const DeformArgs& args, const GridArgs& gargs,
                                        const WorkItem* items, uint32_t n_items, int precision,
-                                       uint32_t max_k, cudaStream_t stream) {
+                                       uint32_t max_k, uint64_t widest_window, cudaStream_t stream) {
   if (n_items == 0) return cudaSuccess;
+  // every alive set fits the staged variant (pose rows in shared memory) iff the widest window does
+  const bool staged = widest_window <= static_cast<uint64_t>(kStagedMaxPts);
   if (max_k + 3 <= 7) {
-    return precision == 0 ? launchOne<7, 0>(args, gargs, items, n_items, stream)
-                          : launchOne<7, 1>(args, gargs, items, n_items, stream);
+    return precision == 0 ? launchVariant<7, 0>(args, gargs, items, n_items, staged, stream)
+                          : launchVariant<7, 1>(args, gargs, items, n_items, staged, stream);
   }
-  return precision == 0 ? launchOne<16, 0>(args, gargs, items, n_items, stream)
-                        : launchOne<16, 1>(args, gargs, items, n_items, stream);
+  return precision == 0 ? launchVariant<16, 0>(args, gargs, items, n_items, staged, stream)
+                        : launchVariant<16, 1>(args, gargs, items, n_items, staged, stream);
 }
 
 }  // namespace pgmo

@@ -118,12 +118,13 @@ def test_config_a_parity(capi, oracle, tol_t, invalid):
 
 
 @pytest.mark.parametrize("spread", [(6.0, 5.0, 10), (40.0, 2.0, 10), (0.5, 30.0, 10),
-                                    (6.0, 5.0, 40), (3.0, 0.0, 10)])
+                                    (6.0, 5.0, 40), (3.0, 0.0, 10), (6.0, 5.0, 20)])
 def test_search_modes_agree(capi, oracle, spread):
     """Bucket-ordered lists (default), grid walk and brute force over the window are
     bit-identical, also when vertices lie far outside / deep inside the control-point cloud,
     when the alive set exceeds the bucket kernel's capacity (40 control points per keyframe:
-    ~840 alive) and when all control points of a keyframe coincide."""
+    ~840 alive: grid walk; 20: ~420 alive: the non-staged bucket kernel) and when all control
+    points of a keyframe coincide."""
     case = synth.deformation_case(150_000, 300 * spread[2], ctrl_per_kf=spread[2],
                                   vertex_spread=spread[0], ctrl_spread=spread[1], seed=17)
     outs = []
