@@ -59,6 +59,7 @@ struct pgmo_deform {
   cudaStream_t s_in = nullptr, s_out = nullptr;  // copy streams of the pipelined host entry point
   static constexpr int kPipe = 8;
   cudaEvent_t ev_in[kPipe] = {}, ev_done[kPipe] = {};
+  cudaEvent_t ev_stamps = nullptr;
   float r_scale = 1.0f, r_grow_mul = 1.5f, r_grow_add = 1.0f;
   uint32_t n_items = 0;
   uint64_t items_first = ~0ull, items_n = 0, items_sched_builds = ~0ull;
@@ -242,6 +243,7 @@ int pgmo_deform_create(int device, pgmo_deform_t** out) {
   if (const char* e = std::getenv("PGMO_R_GROW_ADD")) h->r_grow_add = static_cast<float>(atof(e));
   cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&h->ev_stamps, cudaEventDisableTiming);
   for (int i = 0; i < pgmo_deform::kPipe; ++i) {
     cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming);
@@ -271,6 +273,7 @@ void pgmo_deform_destroy(pgmo_deform_t* h) {
     if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
     if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
   }
+  if (h->ev_stamps) cudaEventDestroy(h->ev_stamps);
   if (h->s_in) cudaStreamDestroy(h->s_in);
   if (h->s_out) cudaStreamDestroy(h->s_out);
   delete h;
@@ -718,13 +721,36 @@ int pgmo_deform_points(pgmo_deform_t* h, uint64_t n_v, const float* x, const flo
     d_subset = h->d_subset.ptr;
   }
 
-  int rc;
-  bool xyz_uploaded = false;
+  // Every upload is queued on the copy stream right away — stamps first (K1 and the host-side
+  // window schedule only need them), then the vertex streams in kPipe chunks, one event each —
+  // so that the H2D engine never idles while the schedule is looked up / built on the host.
+  const int n_chunks = pgmo_deform::kPipe;
+  const bool copy_stream = h->s_in != nullptr && h->s_out != nullptr;
+  cudaStream_t up = copy_stream ? h->s_in : st;
   if (stamps_ns) {
-    // stamps first: K1 and the host-side window schedule only need them
     PGMO_TRY(h->d_vstamps.reserve(n_v));
     PGMO_CUDA(cudaMemcpyAsync(h->d_vstamps.ptr, stamps_ns, n_v * sizeof(uint64_t),
-                              cudaMemcpyHostToDevice, st));
+                              cudaMemcpyHostToDevice, up));
+    if (copy_stream) {
+      PGMO_CUDA(cudaEventRecord(h->ev_stamps, up));
+      PGMO_CUDA(cudaStreamWaitEvent(st, h->ev_stamps, 0));
+    }
+  }
+  uint64_t chunk_end[pgmo_deform::kPipe];
+  for (int c = 0; c < n_chunks; ++c) {
+    const uint64_t b = n_v * static_cast<uint64_t>(c) / n_chunks;
+    const uint64_t e = n_v * static_cast<uint64_t>(c + 1) / n_chunks;
+    chunk_end[c] = e;
+    if (e > b) {
+      PGMO_CUDA(cudaMemcpyAsync(h->d_x.ptr + b, x + b, (e - b) * sizeof(float), cudaMemcpyHostToDevice, up));
+      PGMO_CUDA(cudaMemcpyAsync(h->d_y.ptr + b, y + b, (e - b) * sizeof(float), cudaMemcpyHostToDevice, up));
+      PGMO_CUDA(cudaMemcpyAsync(h->d_z.ptr + b, z + b, (e - b) * sizeof(float), cudaMemcpyHostToDevice, up));
+    }
+    if (copy_stream) PGMO_CUDA(cudaEventRecord(h->ev_in[c], up));
+  }
+
+  int rc;
+  if (stamps_ns) {
     std::vector<uint64_t> s_stamp, s_len;
     PGMO_TRY(stampStretches(h, h->d_vstamps.ptr, d_subset, n_pos, &s_stamp, &s_len, st));
     rc = pgmo_deform_build_schedule(h, s_stamp.size(), s_stamp.data(), s_len.data(), n_pos, k,
@@ -733,21 +759,24 @@ int pgmo_deform_points(pgmo_deform_t* h, uint64_t n_v, const float* x, const flo
     rc = pgmo_deform_build_schedule(h, 0, nullptr, nullptr, n_pos, k, tol_t);
   }
   if (rc != PGMO_OK) {
+    if (copy_stream) cudaStreamSynchronize(up);  // the caller's buffers must not be read any more
     cudaStreamSynchronize(st);
     return rc;
   }
   bool any_skip = false;
   for (const ScheduleRun& run : h->sched.runs) any_skip = any_skip || run.skip;
 
-  // Pipelined path (the common full-mesh case): vertex slabs are uploaded on one copy stream,
-  // deformed on the compute stream and downloaded on a second copy stream, so that H2D, kernels
-  // and D2H overlap (PCIe is full duplex).  Slab boundaries are work-item boundaries.
+  // Pipelined path (the common full-mesh case): vertex chunks arrive on the copy stream, slabs
+  // are deformed on the compute stream as soon as their last chunk is in and downloaded on a
+  // second copy stream, so that H2D, kernels and D2H overlap (PCIe is full duplex).  Slab
+  // boundaries are work-item boundaries.
   if (!subset_idx && !any_skip && h->use_grid && !out_xyz_f64 && !assoc && !assoc_cnt &&
-      n_pos >= (1u << 18) && h->s_in && h->s_out) {
+      n_pos >= (1u << 18) && copy_stream) {
     PGMO_TRY(h->d_status.reserve(n_pos));
     PGMO_TRY(ensureItems(h, 0, n_pos, st));
     const int n_slabs = pgmo_deform::kPipe;
     uint64_t begin = 0;
+    int waited = -1;  // chunks [0, waited] are known to the compute stream
     for (int sl = 0; sl < n_slabs && begin < n_pos; ++sl) {
       uint64_t end = n_pos;
       if (sl + 1 < n_slabs) {
@@ -759,11 +788,12 @@ int pgmo_deform_points(pgmo_deform_t* h, uint64_t n_v, const float* x, const flo
       }
       if (end <= begin) continue;
       const uint64_t cnt = end - begin;
-      PGMO_CUDA(cudaMemcpyAsync(h->d_x.ptr + begin, x + begin, cnt * sizeof(float), cudaMemcpyHostToDevice, h->s_in));
-      PGMO_CUDA(cudaMemcpyAsync(h->d_y.ptr + begin, y + begin, cnt * sizeof(float), cudaMemcpyHostToDevice, h->s_in));
-      PGMO_CUDA(cudaMemcpyAsync(h->d_z.ptr + begin, z + begin, cnt * sizeof(float), cudaMemcpyHostToDevice, h->s_in));
-      PGMO_CUDA(cudaEventRecord(h->ev_in[sl], h->s_in));
-      PGMO_CUDA(cudaStreamWaitEvent(st, h->ev_in[sl], 0));
+      int need = 0;
+      while (need + 1 < n_chunks && chunk_end[need] < end) ++need;
+      if (need > waited) {
+        PGMO_CUDA(cudaStreamWaitEvent(st, h->ev_in[need], 0));  // in-order stream: covers <= need
+        waited = need;
+      }
       PGMO_TRY(runDeviceRange(h, 0, n_pos, h->d_x.ptr, h->d_y.ptr, h->d_z.ptr, nullptr, precision,
                               h->d_ox.ptr, h->d_oy.ptr, h->d_oz.ptr, nullptr, nullptr, 0, nullptr,
                               h->d_status.ptr, nullptr, st, begin, end));
@@ -781,11 +811,8 @@ int pgmo_deform_points(pgmo_deform_t* h, uint64_t n_v, const float* x, const flo
     PGMO_CUDA(cudaStreamSynchronize(st));
     return PGMO_OK;
   }
-  if (!xyz_uploaded) {
-    PGMO_CUDA(cudaMemcpyAsync(h->d_x.ptr, x, n_v * sizeof(float), cudaMemcpyHostToDevice, st));
-    PGMO_CUDA(cudaMemcpyAsync(h->d_y.ptr, y, n_v * sizeof(float), cudaMemcpyHostToDevice, st));
-    PGMO_CUDA(cudaMemcpyAsync(h->d_z.ptr, z, n_v * sizeof(float), cudaMemcpyHostToDevice, st));
-  }
+  // everything else: wait for the whole upload, then one pass on the compute stream
+  if (copy_stream) PGMO_CUDA(cudaStreamWaitEvent(st, h->ev_in[n_chunks - 1], 0));
 
   double* d_f64 = nullptr;
   uint32_t* d_assoc = nullptr;
