@@ -71,8 +71,12 @@ struct pgmo_deform {
 
   // work buffers
   DevBuf<ulonglong2> d_bounds;
+  // last stretch list downloaded (count, fingerprint, positions) and its contents
+  uint64_t sc_count = ~0ull, sc_sum = 0, sc_n_pos = 0;
+  std::vector<uint64_t> sc_stamp, sc_len;
   DevBuf<unsigned long long> d_counters;
   DevBuf<uint8_t> d_status;
+  DevBuf<uint32_t> d_tie_list;
   DevBuf<CandEntry> d_scratch;
   PinnedBuf<unsigned long long> h_counters;
   PinnedBuf<ulonglong2> h_bounds;
@@ -199,12 +203,17 @@ int stampStretches(pgmo_deform_t* h, const uint64_t* d_stamps, const uint64_t* d
     PGMO_CUDA(cudaMemsetAsync(h->d_counters.ptr, 0, 8 * sizeof(unsigned long long), st));
     PGMO_CUDA(launchStampStretches(d_stamps, d_subset, n_pos, h->d_bounds.ptr, h->d_bounds.cap,
                                    h->d_counters.ptr, st));
-    PGMO_CUDA(cudaMemcpyAsync(h->h_counters.ptr, h->d_counters.ptr, sizeof(unsigned long long),
+    PGMO_CUDA(cudaMemcpyAsync(h->h_counters.ptr, h->d_counters.ptr, 2 * sizeof(unsigned long long),
                               cudaMemcpyDeviceToHost, st));
     PGMO_CUDA(cudaStreamSynchronize(st));
     found = h->h_counters.ptr[0];
     if (found <= h->d_bounds.cap) break;
     cap = found;  // rare: more stretches than expected, run again with room for all
+  }
+  if (found == h->sc_count && h->h_counters.ptr[1] == h->sc_sum && n_pos == h->sc_n_pos) {
+    *s_stamp = h->sc_stamp;  // same boundary set as last time: nothing to download
+    *s_len = h->sc_len;
+    return PGMO_OK;
   }
   PGMO_TRY(h->h_bounds.reserve(found));
   PGMO_CUDA(cudaMemcpyAsync(h->h_bounds.ptr, h->d_bounds.ptr, found * sizeof(ulonglong2),
@@ -218,6 +227,11 @@ int stampStretches(pgmo_deform_t* h, const uint64_t* d_stamps, const uint64_t* d
     (*s_stamp)[i] = b[i].y;
     (*s_len)[i] = (i + 1 < found ? b[i + 1].x : n_pos) - b[i].x;
   }
+  h->sc_count = found;
+  h->sc_sum = h->h_counters.ptr[1];
+  h->sc_n_pos = n_pos;
+  h->sc_stamp = *s_stamp;
+  h->sc_len = *s_len;
   return PGMO_OK;
 }
 
@@ -580,14 +594,14 @@ static int runDeviceRange(pgmo_deform_t* h, uint64_t first_position, uint64_t n_
   a.assoc_cnt = d_assoc_cnt;
   a.status = status;
   a.counters = h->d_counters.ptr;
+  PGMO_TRY(h->d_tie_list.reserve(n_local));
+  a.tie_list = h->d_tie_list.ptr;
 
   ResolveArgs ra;
   ra.n_warps = resolverResidentWarps(h->device);
   ra.cand_cap = h->sched.max_k + 2 + h->sched.max_leaf_points + 1;
   PGMO_TRY(h->d_scratch.reserve(static_cast<size_t>(ra.n_warps) * ra.cand_cap * 2));
   ra.scratch = h->d_scratch.ptr;
-  ra.scan_begin = range_begin;
-  ra.scan_end = range_end;
 
   if (h->profiling) PGMO_CUDA(cudaEventRecord(h->ev[0], st));
   if (h->use_grid) {

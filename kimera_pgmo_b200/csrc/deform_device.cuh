@@ -16,6 +16,13 @@ __device__ __forceinline__ float dist2Exact(float ax, float ay, float az, float 
   return __fadd_rn(__fmul_rn(dx, dx), __fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dz, dz)));
 }
 
+// hands local position p to the PCL-order resolver (K4)
+__device__ __forceinline__ void sendToResolver(const DeformArgs& a, uint64_t p) {
+  a.status[p] = kStatusNeedsTie;
+  const unsigned long long at = atomicAdd(a.counters, 1ull);
+  a.tie_list[at] = static_cast<uint32_t>(p);
+}
+
 __device__ __forceinline__ uint32_t findRun(const uint64_t* __restrict__ run_start,
                                             uint32_t n_runs, uint64_t position) {
   // last r with run_start[r] <= position

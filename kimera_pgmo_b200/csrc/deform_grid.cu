@@ -255,8 +255,7 @@ deformKnnBlendBinnedKernel(const DeformArgs a, const GridArgs ga, const WorkItem
   if (g.n_alive <= skip_alive_le) return;  // the bucket-ordered kernel's item
   const int K = static_cast<int>(info.z) + 2;
   if (K + 1 > KCAP) {
-    for (int i = t; i < count; i += kThreads) a.status[p_base + i] = kStatusNeedsTie;
-    if (t == 0) atomicAdd(a.counters, static_cast<unsigned long long>(count));
+    for (int i = t; i < count; i += kThreads) sendToResolver(a, p_base + i);
     return;
   }
   const int n_cells = g.nx * g.ny * g.nz;
@@ -453,8 +452,7 @@ deformKnnBlendBinnedKernel(const DeformArgs a, const GridArgs ga, const WorkItem
       if (i + 1 < n_check && nbr_d2[i] == nbr_d2[i + 1]) tie = true;
     }
     if (tie) {
-      a.status[p] = kStatusNeedsTie;
-      atomicAdd(a.counters, 1ull);
+      sendToResolver(a, p);
       continue;
     }
     writeResultReg<KCAP>(a, p, ii, precision, qx, qy, qz, nbr_d2, nbr_idx, n);

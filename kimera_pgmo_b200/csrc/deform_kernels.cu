@@ -40,6 +40,13 @@ __global__ void stampStretchKernel(const uint64_t* __restrict__ stamps,
     if (boundary) {
       const unsigned long long slot = atomicAdd(count, 1ull);
       if (slot < capacity) out[slot] = make_ulonglong2(p, s);
+      // order-independent fingerprint of the boundary set (count[1]): lets the host skip the
+      // download + sort when the stretches are the ones it already holds
+      unsigned long long m = (p + 0x9e3779b97f4a7c15ull) * 0xbf58476d1ce4e5b9ull;
+      m ^= m >> 29;
+      m = (m ^ s) * 0x94d049bb133111ebull;
+      m ^= m >> 32;
+      atomicAdd(count + 1, m);
     }
   }
 }
@@ -59,8 +66,7 @@ deformKnnBlendKernel(const DeformArgs a, const int precision) {
   }
   const int K = static_cast<int>(info.z) + 2;
   if (K + 1 > KCAP) {
-    a.status[p] = kStatusNeedsTie;
-    atomicAdd(a.counters, 1ull);
+    sendToResolver(a, p);
     return;
   }
   const uint64_t ii = a.subset ? a.subset[p] : p;
@@ -105,8 +111,7 @@ deformKnnBlendKernel(const DeformArgs a, const int precision) {
     if (i + 1 < n_check && best_d[i] == best_d[i + 1]) tie = true;
   }
   if (tie) {
-    a.status[p] = kStatusNeedsTie;
-    atomicAdd(a.counters, 1ull);
+    sendToResolver(a, p);
     return;
   }
   writeResultReg<KCAP>(a, p, ii, precision, qx, qy, qz, best_d, best_i, n);
@@ -128,13 +133,20 @@ struct DfsLevel {
 };
 
 constexpr int kResolveWarpsPerBlock = 4;
+constexpr int kResolveStage = 320;  // alive points of the vertex's run staged per warp
+
+struct ResolveStage {
+  float4 pts[kResolveStage];    // x, y, z, control index (int bits), ascending control index
+  uint32_t key[kResolveStage][3];  // leaf key in the run's octree frame
+};
 
 __device__ __forceinline__ bool aliveInRun(const float4& c, int run) {
   return __float_as_int(c.w) > run;
 }
 
 __device__ void resolveOne(const DeformArgs& a, const ResolveArgs& ra, DfsLevel* levels,
-                           CandEntry* cand, uint64_t p, int precision, int lane) {
+                           ResolveStage& stage, CandEntry* cand, uint64_t p, int precision,
+                           int lane) {
   const uint32_t r = findRun(a.run_start, a.n_runs, a.first_position + p);
   const uint4 info = a.run_info[r];
   const RunFrameDev frame = a.run_frame[r];
@@ -144,6 +156,32 @@ __device__ void resolveOne(const DeformArgs& a, const ResolveArgs& ra, DfsLevel*
   const uint32_t K = info.z + 2;
   const int depth = static_cast<int>(frame.depth);
   const unsigned full = 0xFFFFFFFFu;
+
+  // stage the run's alive points (ascending control index, like the PCL leaves hold them) with
+  // their leaf keys: every later pass of the DFS then runs out of shared memory
+  int n_staged = 0;
+  bool staged = true;
+  for (uint32_t base = info.x; base < info.y; base += 32) {
+    const uint32_t j = base + lane;
+    float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool alive = false;
+    if (j < info.y) {
+      c = __ldg(a.ctrl_f4 + j);
+      alive = aliveInRun(c, run);
+    }
+    const unsigned m = __ballot_sync(full, alive);
+    const int at = n_staged + __popc(m & ((1u << lane) - 1u));
+    if (alive && at < kResolveStage) {
+      const int4 sk = __ldg(a.ctrl_key + j);
+      stage.pts[at] = make_float4(c.x, c.y, c.z, __int_as_float(static_cast<int>(j)));
+      stage.key[at][0] = static_cast<uint32_t>(sk.x + frame.shift[0]);
+      stage.key[at][1] = static_cast<uint32_t>(sk.y + frame.shift[1]);
+      stage.key[at][2] = static_cast<uint32_t>(sk.z + frame.shift[2]);
+    }
+    n_staged += __popc(m);
+  }
+  if (n_staged > kResolveStage) staged = false;  // large alive set: scan the window in place
+  __syncwarp();
 
   uint32_t n_cand = 0;
   double best = DBL_MAX;
@@ -161,7 +199,16 @@ __device__ void resolveOne(const DeformArgs& a, const ResolveArgs& ra, DfsLevel*
       const uint32_t kx = L.key[0], ky = L.key[1], kz = L.key[2];
       const int up = depth - level;  // leaf key >> up == node key
       unsigned mask = 0;
-      for (uint32_t j = info.x + lane; j < info.y; j += 32) {
+      if (staged) {
+        for (int i = lane; i < n_staged; i += 32) {
+          const uint32_t x = stage.key[i][0], y = stage.key[i][1], z = stage.key[i][2];
+          const bool in_node = up >= 32 || ((x >> up) == kx && (y >> up) == ky && (z >> up) == kz);
+          if (!in_node) continue;
+          const int bit = up - 1;
+          mask |= 1u << ((((x >> bit) & 1) << 2) | (((y >> bit) & 1) << 1) | ((z >> bit) & 1));
+        }
+      }
+      for (uint32_t j = info.x + lane; !staged && j < info.y; j += 32) {
         const float4 c = __ldg(a.ctrl_f4 + j);
         if (!aliveInRun(c, run)) continue;
         const int4 sk = __ldg(a.ctrl_key + j);
@@ -258,7 +305,28 @@ __device__ void resolveOne(const DeformArgs& a, const ResolveArgs& ra, DfsLevel*
       continue;
     }
     // leaf: append its points (ascending index) that beat the current K-th distance
-    for (uint32_t base = info.x; base < info.y; base += 32) {
+    for (int base = 0; staged && base < n_staged; base += 32) {
+      const int i = base + lane;
+      bool accept = false;
+      float d2 = 0.f;
+      int j = 0;
+      if (i < n_staged && stage.key[i][0] == cx && stage.key[i][1] == cy && stage.key[i][2] == cz) {
+        const float4 cp = stage.pts[i];
+        j = __float_as_int(cp.w);
+        d2 = dist2Exact(cp.x, cp.y, cp.z, qx, qy, qz);
+        accept = static_cast<double>(d2) < best;
+      }
+      const unsigned m = __ballot_sync(full, accept);
+      if (accept) {
+        const uint32_t slot = n_cand + __popc(m & ((1u << lane) - 1));
+        if (slot < ra.cand_cap) {
+          cand[slot].dist = d2;
+          cand[slot].idx = j;
+        }
+      }
+      n_cand += __popc(m);
+    }
+    for (uint32_t base = info.x; !staged && base < info.y; base += 32) {
       const uint32_t j = base + lane;
       bool accept = false;
       float d2 = 0.f;
@@ -331,50 +399,22 @@ __device__ void resolveOne(const DeformArgs& a, const ResolveArgs& ra, DfsLevel*
 __global__ void __launch_bounds__(kResolveWarpsPerBlock * 32)
 deformResolveKernel(const DeformArgs a, const ResolveArgs ra, const int precision) {
   __shared__ DfsLevel s_levels[kResolveWarpsPerBlock][kResolverMaxDepth + 1];
+  __shared__ ResolveStage s_stage[kResolveWarpsPerBlock];
   const int lane = threadIdx.x & 31;
   const int warp_in_block = threadIdx.x >> 5;
   const uint32_t warp = blockIdx.x * kResolveWarpsPerBlock + warp_in_block;
   // slab per warp: cand_cap entries + room for the split views used by large k
   CandEntry* cand = ra.scratch + static_cast<uint64_t>(warp) * ra.cand_cap * 2;
-  // scan the status bytes 16 per lane (512 positions per warp step); status is 16-byte aligned
-  // when the caller's buffer is (cudaMalloc / torch allocations are), else fall back to bytes
-  const bool aligned = (reinterpret_cast<uintptr_t>(a.status) & 15) == 0;
-  const uint64_t first_chunk = ra.scan_begin / 512;
-  const uint64_t n_chunks = (ra.scan_end + 511) / 512;
-  for (uint64_t chunk = first_chunk + warp; chunk < n_chunks; chunk += ra.n_warps) {
-    const uint64_t p0 = chunk * 512 + static_cast<uint64_t>(lane) * 16;
-    uint32_t flags = 0;  // bit i: position p0 + i needs the resolver
-    if (aligned && p0 >= ra.scan_begin && p0 + 16 <= ra.scan_end) {
-      const uint4 v = *reinterpret_cast<const uint4*>(a.status + p0);
-      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          if (((w[q] >> (8 * b)) & 0xFFu) == kStatusNeedsTie) flags |= 1u << (4 * q + b);
-        }
-      }
-    } else {
-      for (int i = 0; i < 16; ++i) {
-        if (p0 + i >= ra.scan_begin && p0 + i < ra.scan_end &&
-            a.status[p0 + i] == kStatusNeedsTie) {
-          flags |= 1u << i;
-        }
-      }
-    }
-    unsigned todo = __ballot_sync(0xFFFFFFFFu, flags != 0);
-    while (todo) {
-      const int src = __ffs(todo) - 1;
-      todo &= todo - 1;
-      uint32_t f = __shfl_sync(0xFFFFFFFFu, flags, src);
-      while (f) {
-        const int i = __ffs(f) - 1;
-        f &= f - 1;
-        resolveOne(a, ra, s_levels[warp_in_block], cand,
-                   chunk * 512 + static_cast<uint64_t>(src) * 16 + i, precision, lane);
-      }
-    }
+  // work list filled by the K3 kernels: entries [counters[1], counters[0]) are new
+  const unsigned long long begin = a.counters[1], end = a.counters[0];
+  for (unsigned long long i = begin + warp; i < end; i += ra.n_warps) {
+    resolveOne(a, ra, s_levels[warp_in_block], s_stage[warp_in_block], cand, a.tie_list[i], precision,
+               lane);
   }
+}
+
+__global__ void deformResolveDoneKernel(unsigned long long* counters) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) counters[1] = counters[0];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -476,6 +516,7 @@ cudaError_t launchDeformResolve(const DeformArgs& args, const ResolveArgs& rargs
   if (args.n_local == 0) return cudaSuccess;
   const unsigned blocks = rargs.n_warps / kResolveWarpsPerBlock;
   deformResolveKernel<<<blocks, kResolveWarpsPerBlock * 32, 0, stream>>>(args, rargs, precision);
+  deformResolveDoneKernel<<<1, 32, 0, stream>>>(args.counters);
   return cudaGetLastError();
 }
 

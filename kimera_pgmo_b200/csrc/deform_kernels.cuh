@@ -49,7 +49,8 @@ struct DeformArgs {
   uint32_t assoc_stride;
   uint8_t* assoc_cnt;         // or null
   uint8_t* status;            // per position (always present)
-  unsigned long long* counters;  // [0] = vertices sent to the resolver
+  unsigned long long* counters;  // [0] = vertices sent to the resolver, [1] = already resolved
+  uint32_t* tie_list;            // local positions sent to the resolver (capacity n_local)
 };
 
 // per-run uniform grid over the run's alive control points (deform_grid.cu)
@@ -89,8 +90,6 @@ struct ResolveArgs {
   CandEntry* scratch;        // one slab of cand_cap entries per resident warp
   uint32_t cand_cap;
   uint32_t n_warps;          // resident warps (grid is persistent)
-  uint64_t scan_begin;       // local positions [scan_begin, scan_end) are scanned for flags
-  uint64_t scan_end;
 };
 
 // K1: boundaries of equal-stamp stretches.  Appends (position, stamp) of every position whose

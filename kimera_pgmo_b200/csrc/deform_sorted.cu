@@ -230,8 +230,7 @@ deformKnnBlendSortedKernel(const DeformArgs a, const GridArgs ga,
   if (n_alive > kSMaxPts) return;  // another kernel's item
   const int K = static_cast<int>(info.z) + 2;
   if (K + 1 > KCAP) {
-    for (int i = t; i < count; i += kSThreads) a.status[p_base + i] = kStatusNeedsTie;
-    if (t == 0) atomicAdd(a.counters, static_cast<unsigned long long>(count));
+    for (int i = t; i < count; i += kSThreads) sendToResolver(a, p_base + i);
     return;
   }
 
@@ -572,8 +571,7 @@ deformKnnBlendSortedKernel(const DeformArgs a, const GridArgs ga,
       }
     }
     if (tie) {  // exact tie (or an unresolvable near tie): the resolver is exact for both
-      a.status[p] = kStatusNeedsTie;
-      atomicAdd(a.counters, 1ull);
+      sendToResolver(a, p);
       continue;
     }
     if constexpr (STAGE) {
