@@ -379,7 +379,7 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
-def bench_compression(dev_index, n_messages=60, verts=50_000, with_cpu=True):
+def bench_compression(dev_index, n_messages=200, verts=50_000, with_cpu=True, n_octree=40):
     """configs[1]: VoxelClearingCompression of streamed 50k-vertex mesh blocks at 0.05 m on one GPU.
     Three numbers: device-resident throughput (inputs in HBM, pgmo_vcc_integrate_device, CUDA
     events), end to end through pgmo_vcc_prune + pgmo_vcc_integrate with host buffers, and the
@@ -446,6 +446,36 @@ def bench_compression(dev_index, n_messages=60, verts=50_000, with_cpu=True):
         out["cpu_baseline"] = {"value": verts / (cpu_ms * 1e-3), "unit": "vertices/s", "cores": 1,
                                "kind": "port", "ms_per_message": cpu_ms,
                                "sample": f"the same {n_messages - warm} messages, oracle/liboracle.so"}
+
+    # OctreeCompression (the other MeshCompression variant of the north star) on the first
+    # n_octree messages, host buffers in / remap record out, prune(t - 10 s) before each
+    if n_octree > 0:
+        oc = capi.OctHandle(0.05, dev_index)
+        t0 = None
+        w2 = min(5, n_octree - 1)
+        for m, (blocks, offsets, xyz, rgba, t) in enumerate(msgs[:n_octree]):
+            if m == w2:
+                t0 = time.perf_counter()
+            oc.prune(t - 10.0)
+            oc.integrate(blocks, offsets, xyz, rgba, t)
+        oct_ms = 1e3 * (time.perf_counter() - t0) / (n_octree - w2)
+        out["octree"] = {"value": verts / (oct_ms * 1e-3), "unit": "vertices/s", "ms_per_message": oct_ms,
+                         "api": "pgmo_oct_prune + pgmo_oct_integrate (host buffers)",
+                         "stored_vertices": int(oc.sizes()[0])}
+        oc.close()
+        if with_cpu:
+            from oracle import ffi
+            ora = ffi.Compression("octree", 0.05)
+            total = 0.0
+            for m, (blocks, offsets, xyz, rgba, t) in enumerate(msgs[:n_octree]):
+                t1 = time.perf_counter()
+                ora.prune(t - 10.0)
+                ora.integrate(blocks, offsets, xyz, rgba, t)
+                if m >= w2:
+                    total += time.perf_counter() - t1
+            cpu_ms = 1e3 * total / (n_octree - w2)
+            out["octree"]["cpu_baseline"] = {"value": verts / (cpu_ms * 1e-3), "unit": "vertices/s",
+                                             "cores": 1, "kind": "port", "ms_per_message": cpu_ms}
     return out
 
 

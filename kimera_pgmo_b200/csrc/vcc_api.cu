@@ -55,6 +55,9 @@ struct pgmo_vcc {
   DevBuf<uint64_t> t_keys;
   DevBuf<uint32_t> t_vals;
   DevBuf<unsigned long long> t_seq_min, t_seq_max;
+  DevBuf<uint64_t> spare_keys;  // second table buffer set (rebuild target, then swapped)
+  DevBuf<uint32_t> spare_vals;
+  DevBuf<unsigned long long> spare_seq_min, spare_seq_max;
   uint64_t table_cap = 0;
   DevBuf<int32_t> active, inactive;
   DevBuf<uint8_t> live;
@@ -148,15 +151,20 @@ int ensureTable(pgmo_vcc_t* h, uint64_t extra, cudaStream_t st) {
   const uint64_t needed = h->used_upper + extra;
   if (h->table_cap && 2 * needed <= h->table_cap) return PGMO_OK;
   if (h->pending) PGMO_TRY(syncCounters(h, st));
-  uint64_t cap = 1024;
-  while (cap < 4 * (h->n_live + extra) + 16) cap <<= 1;
+  // Sized with head room (load <= 1/8 right after a rebuild) so that rebuilds are rare: the
+  // stream of 50k-vertex messages is launch-latency-bound and a rebuild costs allocations.  The
+  // spare buffer set is kept on the handle: a tombstone-only rebuild of the same size allocates
+  // nothing.
+  uint64_t cap = std::max<uint64_t>(h->table_cap, 1024);
+  while (cap < 8 * (h->n_live + extra) + 16) cap <<= 1;
   if (cap > (1ull << 31)) {
     setLastError("voxel table would exceed 2^31 slots");
     return PGMO_ERR_UNSUPPORTED;
   }
-  DevBuf<uint64_t> keys;
-  DevBuf<uint32_t> vals;
-  DevBuf<unsigned long long> smin, smax;
+  DevBuf<uint64_t>& keys = h->spare_keys;
+  DevBuf<uint32_t>& vals = h->spare_vals;
+  DevBuf<unsigned long long>& smin = h->spare_seq_min;
+  DevBuf<unsigned long long>& smax = h->spare_seq_max;
   PGMO_TRY(keys.reserve(cap));
   PGMO_TRY(vals.reserve(cap));
   PGMO_TRY(smin.reserve(cap));
