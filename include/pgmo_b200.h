@@ -232,6 +232,10 @@ int pgmo_oct_snapshot(pgmo_oct_t* h, float* vertices_xyz, uint32_t* vertices_rgb
                       float* active_xyz, double* active_stamps_s);
 int pgmo_oct_last_outputs(pgmo_oct_t* h, float* new_vertices_xyz, uint32_t* new_vertices_rgba,
                           uint32_t* new_triangles, uint64_t* new_indices);
+/* Diagnostics of the last pgmo_oct_integrate: stats4 = [fixed-point rounds of the temp-structure
+ * pass, vertices that failed the persistent-structure test (candidates), temp vertices created,
+ * vertices accepted into the mesh]. */
+int pgmo_oct_last_stats(pgmo_oct_t* h, uint64_t* stats4);
 
 #ifdef __cplusplus
 }

@@ -76,6 +76,7 @@ SIGNATURES = {
     "pgmo_oct_sizes": (C.c_int, [_vp, _vp]),
     "pgmo_oct_snapshot": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pgmo_oct_last_outputs": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "pgmo_oct_last_stats": (C.c_int, [_vp, _vp]),
 }
 
 _lib = None
@@ -371,6 +372,12 @@ class OctHandle:
                                            _ptr(out["active"]), _ptr(out["active_xyz"]),
                                            _ptr(out["active_stamps"])))
         return out
+
+    def last_stats(self):
+        """[fixed-point rounds, candidates, temp vertices, accepted] of the last integrate."""
+        st = np.zeros(4, dtype=np.uint64)
+        _check(self._lib.pgmo_oct_last_stats(self._h, _ptr(st)))
+        return [int(v) for v in st]
 
     def last_outputs(self):
         s = self.sizes()

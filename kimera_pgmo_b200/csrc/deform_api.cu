@@ -269,6 +269,7 @@ int pgmo_deform_create(int device, pgmo_deform_t** out) {
       return PGMO_ERR_CUDA;
     }
   }
+  preloadDeformSortedKernels();
   *out = h;
   return PGMO_OK;
 }

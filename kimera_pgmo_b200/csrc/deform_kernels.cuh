@@ -120,6 +120,9 @@ cudaError_t launchDeformKnnBlendSorted(const DeformArgs& args, const GridArgs& g
                                        const WorkItem* items, uint32_t n_items, int precision,
                                        uint32_t max_k, uint64_t widest_window, cudaStream_t stream);
 
+// forces the lazy loading of the default K3 kernels (handle creation)
+void preloadDeformSortedKernels();
+
 // K4: PCL-order resolution of the vertices flagged kStatusNeedsTie.
 cudaError_t launchDeformResolve(const DeformArgs& args, const ResolveArgs& rargs, int precision,
                                 cudaStream_t stream);

@@ -609,7 +609,21 @@ cudaError_t launchVariant(const DeformArgs& args, const GridArgs& gargs, const W
                 : launchOne<KCAP, PREC, kSortedMaxPoints, false>(args, gargs, items, n_items, stream);
 }
 
+template <int KCAP, int PREC>
+void preloadVariants() {
+  cudaFuncAttributes attr;
+  cudaFuncGetAttributes(&attr, deformKnnBlendSortedKernel<KCAP, PREC, kStagedMaxPts, true>);
+  cudaFuncGetAttributes(&attr, deformKnnBlendSortedKernel<KCAP, PREC, kSortedMaxPoints, false>);
+}
+
 }  // namespace
+
+// CUDA loads kernels lazily at their first launch (hundreds of ms for the large K3 variants):
+// pull the common ones in when the handle is created instead of inside the first deformMesh.
+void preloadDeformSortedKernels() {
+  preloadVariants<7, 0>();
+  preloadVariants<7, 1>();
+}
 
 cudaError_t launchDeformKnnBlendSorted(const DeformArgs& args, const GridArgs& gargs,
                                        const WorkItem* items, uint32_t n_items, int precision,

@@ -395,7 +395,7 @@ struct pgmo_oct {
   PinnedBuf<unsigned long long> h_counts;
   PinnedBuf<uint32_t> h_flags;
   PinnedBuf<OctFrames> h_frames;
-  uint64_t last_rounds = 0;
+  uint64_t last_rounds = 0, last_cand = 0, last_pot = 0;
 };
 
 namespace {
@@ -763,6 +763,8 @@ int pgmo_oct_integrate(pgmo_oct_t* h, uint32_t n_blocks, const int32_t* block_id
   PGMO_CUDA(cudaMemcpyAsync(h->h_flags.ptr, h->flags32.ptr, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   PGMO_CUDA(cudaStreamSynchronize(st));
   PGMO_TRY(treeErrorToRc(h->h_flags.ptr[1]));
+  h->last_cand = n_cand;
+  h->last_pot = n_pot;
   const uint64_t first_new = h->n_act;
   h->n_all = n_orig + n_acc;
   h->n_act += n_acc;
@@ -863,6 +865,15 @@ int pgmo_oct_snapshot(pgmo_oct_t* h, float* vertices_xyz, uint32_t* vertices_rgb
     active_xyz[3 * i + 1] = ax[i].y;
     active_xyz[3 * i + 2] = ax[i].z;
   }
+  return PGMO_OK;
+}
+
+int pgmo_oct_last_stats(pgmo_oct_t* h, uint64_t* stats4) {
+  PGMO_CHECK_ARG(h != nullptr && stats4 != nullptr);
+  stats4[0] = h->last_rounds;
+  stats4[1] = h->last_cand;
+  stats4[2] = h->last_pot;
+  stats4[3] = h->n_new_vertices;
   return PGMO_OK;
 }
 

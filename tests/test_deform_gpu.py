@@ -259,3 +259,27 @@ def test_shard_invariance_single_gpu(capi):
         many = run(shards)
         for a, b in zip(one, many):
             np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+def test_config_c_slice_parity(capi, oracle, precision):
+    """configs[2] at 1/5 scale (2M vertices, 10k control points, same density as the 10M / 50k
+    benchmark workload): full oracle parity through the pipelined host entry point.  The full
+    10M-vertex comparison is scripts/full_parity.py (profiles/r01_full_parity.txt)."""
+    case = synth.deformation_case(2_000_000, 10_000)
+    h = capi.DeformHandle(0)
+    _set(h, case)
+    gpu = h.deform_points(case["x"], case["y"], case["z"], case["stamps"], k=4, tol_t=10.0,
+                          precision=precision)
+    ref = oracle.deform_points(case["x"], case["y"], case["z"], case["stamps"], case["ctrl_xyz"],
+                               case["ctrl_stamps"], case["valid"], case["poses"], k=4, tol_t=10.0,
+                               want_trace=False)
+    h.close()
+    assert gpu["rc"] == ref["rc"] == 0
+    assert gpu["processed"].all()
+    for ax in "xyz":
+        if precision == 0:
+            np.testing.assert_array_equal(gpu[ax], ref[ax])
+        else:
+            np.testing.assert_allclose(gpu[ax].astype(np.float64), ref[ax].astype(np.float64),
+                                       rtol=0, atol=FP32_TOL)
