@@ -222,43 +222,39 @@ __device__ void resolveOne(const DeformArgs& a, const ResolveArgs& ra, DfsLevel*
         mask |= 1u << child;
       }
       mask = __reduce_or_sync(full, mask);
-      if (lane == 0) {
+      {
+        // lanes 0..7 each take one child: voxel centre (genVoxelCenterFromOctreeKey: double
+        // arithmetic, float result), float distance, then its rank in the visiting order —
+        // ascending distance, ties -> higher child index first
         const int tree_depth = level + 1;
         const double side = a.resolution * static_cast<double>(1u << (depth - tree_depth));
-        int cnt = 0;
-        for (int c = 0; c < 8; ++c) {
-          if (!(mask & (1u << c))) continue;
-          const uint32_t cx = (kx << 1) + ((c >> 2) & 1);
-          const uint32_t cy = (ky << 1) + ((c >> 1) & 1);
-          const uint32_t cz = (kz << 1) + (c & 1);
-          // genVoxelCenterFromOctreeKey: double arithmetic, float result
-          const float vx = __double2float_rn(
-              __dadd_rn(__dmul_rn(__dadd_rn(static_cast<double>(cx), 0.5), side), frame.min_xyz[0]));
-          const float vy = __double2float_rn(
-              __dadd_rn(__dmul_rn(__dadd_rn(static_cast<double>(cy), 0.5), side), frame.min_xyz[1]));
-          const float vz = __double2float_rn(
-              __dadd_rn(__dmul_rn(__dadd_rn(static_cast<double>(cz), 0.5), side), frame.min_xyz[2]));
-          const float d = dist2Exact(vx, vy, vz, qx, qy, qz);
-          // visiting order: ascending distance, ties -> higher child index first
-          int at = cnt;
-          while (at > 0 && (d < L.dist[at - 1])) {
-            L.dist[at] = L.dist[at - 1];
-            L.child[at] = L.child[at - 1];
-            --at;
-          }
-          // children arrive in ascending index: on equal distance the newcomer (higher index)
-          // must be visited first, so it also passes equal entries
-          while (at > 0 && d == L.dist[at - 1]) {
-            L.dist[at] = L.dist[at - 1];
-            L.child[at] = L.child[at - 1];
-            --at;
-          }
-          L.dist[at] = d;
-          L.child[at] = static_cast<uint8_t>(c);
-          ++cnt;
+        const int c = lane & 7;
+        const bool exists = lane < 8 && (mask & (1u << c));
+        const uint32_t ccx = (kx << 1) + ((c >> 2) & 1);
+        const uint32_t ccy = (ky << 1) + ((c >> 1) & 1);
+        const uint32_t ccz = (kz << 1) + (c & 1);
+        const float vx = __double2float_rn(
+            __dadd_rn(__dmul_rn(__dadd_rn(static_cast<double>(ccx), 0.5), side), frame.min_xyz[0]));
+        const float vy = __double2float_rn(
+            __dadd_rn(__dmul_rn(__dadd_rn(static_cast<double>(ccy), 0.5), side), frame.min_xyz[1]));
+        const float vz = __double2float_rn(
+            __dadd_rn(__dmul_rn(__dadd_rn(static_cast<double>(ccz), 0.5), side), frame.min_xyz[2]));
+        const float d = dist2Exact(vx, vy, vz, qx, qy, qz);
+        int rank = 0;
+#pragma unroll
+        for (int o = 0; o < 8; ++o) {
+          const float od = __shfl_sync(full, d, o);
+          const bool other = (mask >> o) & 1u;
+          rank += (other && (od < d || (od == d && o > c))) ? 1 : 0;
         }
-        L.cnt = cnt;
-        L.pos = 0;
+        if (exists) {
+          L.dist[rank] = d;
+          L.child[rank] = static_cast<uint8_t>(c);
+        }
+        if (lane == 0) {
+          L.cnt = __popc(mask & 0xFFu);
+          L.pos = 0;
+        }
       }
       __syncwarp();
       entering = false;
