@@ -52,29 +52,75 @@ def parse_args():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    """Samples SM clocks / throttle reasons during the timed region: NVML (nvidia_ml_py, ~2 ms
+    period, so that even a 30 ms region gets several samples) with nvidia-smi as the fallback."""
 
     QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         self.index = index
-        self.samples = []
+        self.samples = []   # (sm_mhz, [reason flags])
+        self.sm_max = None
+        self.source = None
         self._stop = threading.Event()
         self._thread = None
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES remapping
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                ids = [v for v in vis.split(",") if v.strip() != ""]
+                if index < len(ids) and ids[index].strip().isdigit():
+                    phys = int(ids[index])
+            self._handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self._handle, pynvml.NVML_CLOCK_SM))
+            self._nvml = pynvml
+            self.source = "nvml"
+        except Exception:
+            self._nvml = None
+            self.source = "nvidia-smi"
+
+    def _sample_nvml(self):
+        n = self._nvml
+        sm = float(n.nvmlDeviceGetClockInfo(self._handle, n.NVML_CLOCK_SM))
+        try:
+            mask = n.nvmlDeviceGetCurrentClocksEventReasons(self._handle)
+        except Exception:
+            mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self._handle)
+        flags = [bool(mask & n.nvmlClocksThrottleReasonHwSlowdown),
+                 bool(mask & n.nvmlClocksThrottleReasonHwThermalSlowdown),
+                 bool(mask & n.nvmlClocksThrottleReasonSwThermalSlowdown),
+                 bool(mask & n.nvmlClocksThrottleReasonSwPowerCap)]
+        self.samples.append((sm, flags))
+
+    def _sample_smi(self):
+        out = subprocess.run(
+            ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
+             "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+        if out.returncode == 0 and out.stdout.strip():
+            f = [v.strip() for v in out.stdout.strip().split(",")]
+            if f[0].replace(".", "").isdigit():
+                if f[1].replace(".", "").isdigit():
+                    self.sm_max = float(f[1])
+                self.samples.append((float(f[0]), [len(f) > 3 + i and f[3 + i].lower().startswith("active")
+                                                   for i in range(4)]))
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(
-                    ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
-                     "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
-                if out.returncode == 0 and out.stdout.strip():
-                    self.samples.append([f.strip() for f in out.stdout.strip().split(",")])
+                if self._nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.002 if self._nvml is not None else 0.1)
 
     def __enter__(self):
         self._thread = threading.Thread(target=self._run, daemon=True)
@@ -87,14 +133,11 @@ class ClockSampler:
 
     def summary(self):
         if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names)
-                   if any(len(s) > 3 + i and s[3 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
-                "sm_max_mhz": float(self.samples[0][1]) if self.samples[0][1].replace(".", "").isdigit() else None,
-                "reasons": reasons, "samples": len(self.samples)}
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["unsampled"]}
+        sm = sorted(s[0] for s in self.samples)
+        reasons = [n for i, n in enumerate(self.NAMES) if any(s[1][i] for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": self.sm_max,
+                "reasons": reasons, "samples": len(self.samples), "source": self.source}
 
 
 def measured_peak_gbs():
@@ -359,7 +402,7 @@ def run_b200(args):
             },
             "clocks": clocks.summary(),
             "e2e": e2e,
-            "gpu_launches": 4 * args.steps,
+            "gpu_launches": 5 * args.steps,  # buildControlTables, K1, K3, K4, K4-done per step
             "resolved_by_tie_kernel": int(n_resolved),
             "schedule_builds": int(sched_builds),
         }
