@@ -88,6 +88,12 @@ int pgmo_deform_set_controls_device(pgmo_deform_t* h, uint64_t n_c, const double
 int pgmo_deform_update_poses(pgmo_deform_t* h, const double* poses12);
 int pgmo_deform_update_poses_device(pgmo_deform_t* h, const double* d_poses12, void* stream);
 
+/* Forgets the cached window schedule (and the per-run tables built from it), so that the next
+ * pgmo_deform_build_schedule / pgmo_deform_points rebuilds it even if nothing changed.  What a
+ * caller gets implicitly whenever control positions / stamps / validity or the mesh stamps
+ * change; exposed so that the rebuild can be measured (bench.py "cold" step). */
+int pgmo_deform_drop_schedule(pgmo_deform_t* h);
+
 /* Candidate search of the knn kernel: 1 (default) = bucket-ordered candidate lists over each
  * run's alive control points (grid walk for alive sets > 512); 2 = grid walk only (per-run uniform
  * grids, built once per cached window schedule); 0 = brute force over the whole time window.

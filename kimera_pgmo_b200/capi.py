@@ -47,6 +47,7 @@ SIGNATURES = {
     "pgmo_deform_update_poses_device": (C.c_int, [_vp, _vp, _vp]),
     "pgmo_deform_set_profiling": (C.c_int, [_vp, C.c_int]),
     "pgmo_deform_set_search_mode": (C.c_int, [_vp, C.c_int]),
+    "pgmo_deform_drop_schedule": (C.c_int, [_vp]),
     "pgmo_deform_last_timings": (C.c_int, [_vp, _vp, _u64p]),
     "pgmo_deform_points": (C.c_int, [_vp, C.c_uint64, _vp, _vp, _vp, _vp, _vp, C.c_uint64,
                                      C.c_uint32, C.c_double, C.c_int, _vp, _vp, _vp, _vp, _vp,
@@ -165,6 +166,9 @@ class DeformHandle:
 
     def update_poses_device(self, d_poses, stream=0):
         _check(self._lib.pgmo_deform_update_poses_device(self._h, _ptr(d_poses), _vp(stream)))
+
+    def drop_schedule(self):
+        _check(self._lib.pgmo_deform_drop_schedule(self._h))
 
     def set_search_mode(self, mode):
         _check(self._lib.pgmo_deform_set_search_mode(self._h, int(mode)))

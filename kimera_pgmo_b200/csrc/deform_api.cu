@@ -1,5 +1,6 @@
 // C ABI of the deformation path (see include/pgmo_b200.h).
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -444,11 +445,13 @@ int pgmo_deform_build_schedule(pgmo_deform_t* h, uint64_t n_stretches,
   ctrl.stamps = h->has_stamps ? h->h_stamps.data() : nullptr;
   ctrl.valid = h->has_valid ? h->h_valid.data() : nullptr;
   h->sched_ready = false;
+  const auto t_build0 = std::chrono::steady_clock::now();
   if (stamped) {
     buildStampedSchedule(ctrl, n_stretches, stretch_stamp, stretch_len, k, tol_t, 1.0, &h->sched);
   } else {
     buildUnstampedSchedule(ctrl, total_positions, k, 1.0, &h->sched);
   }
+  const auto t_build1 = std::chrono::steady_clock::now();
   ++h->sched_builds;
   if (h->sched.noop) return PGMO_NOOP;
   if (h->sched.degenerate) {
@@ -460,6 +463,12 @@ int pgmo_deform_build_schedule(pgmo_deform_t* h, uint64_t n_stretches,
     return PGMO_ERR_INVALID;
   }
   PGMO_TRY(uploadSchedule(h, h->stream));
+  if (std::getenv("PGMO_DEBUG")) {
+    const auto t_build2 = std::chrono::steady_clock::now();
+    fprintf(stderr, "pgmo debug: schedule replay %.3f ms, upload + per-run tables %.3f ms, %zu runs\n",
+            std::chrono::duration<double, std::milli>(t_build1 - t_build0).count(),
+            std::chrono::duration<double, std::milli>(t_build2 - t_build1).count(), h->sched.runs.size());
+  }
   h->sched_ready = true;
   h->sched_control_version = h->control_version;
   h->sched_k = k;
@@ -670,6 +679,12 @@ int pgmo_deform_run_device(pgmo_deform_t* h, uint64_t first_position, uint64_t n
   return runDeviceRange(h, first_position, n_local, d_x, d_y, d_z, d_subset_idx, precision,
                         d_out_x, d_out_y, d_out_z, d_out_xyz_f64, d_assoc, assoc_stride,
                         d_assoc_cnt, d_processed, n_resolved, stream, 0, n_local);
+}
+
+int pgmo_deform_drop_schedule(pgmo_deform_t* h) {
+  PGMO_CHECK_ARG(h != nullptr);
+  h->sched_ready = false;
+  return PGMO_OK;
 }
 
 int pgmo_deform_set_search_mode(pgmo_deform_t* h, int mode) {

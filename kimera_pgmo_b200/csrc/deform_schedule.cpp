@@ -9,7 +9,7 @@
 #include <climits>
 #include <cmath>
 #include <limits>
-#include <unordered_map>
+#include <vector>
 
 namespace pgmo {
 
@@ -35,11 +35,21 @@ struct VoxelKeyHash {
 
 // Leaf bookkeeping of the search octree: which voxels are occupied and by which control points.
 // No search structure is kept here — only what getLeafCount / deleteVoxelAtPoint observe.
+// Flat open-addressing table (every control point is added at most once, so a table of
+// >= 2 n_c slots never fills up even though deletions leave tombstones) with the points of a
+// leaf chained through `next_`: no allocation per add / remove, this runs once per changed
+// control table on the critical path of the first deformMesh after a solve.
 class LeafBook {
  public:
-  explicit LeafBook(double resolution) : res_(resolution) {}
+  LeafBook(double resolution, uint64_t n_points) : res_(resolution) {
+    uint64_t cap = 64;
+    while (cap < 2 * n_points + 16) cap <<= 1;
+    mask_ = cap - 1;
+    slots_.assign(cap, Slot());
+    next_.assign(n_points, -1);
+  }
 
-  size_t leafCount() const { return leaves_.size(); }
+  size_t leafCount() const { return n_leaves_; }
   uint32_t maxLeafPoints() const { return max_leaf_points_; }
 
   void frame(ScheduleRun* run) const {
@@ -56,9 +66,29 @@ class LeafBook {
   VoxelKey add(uint32_t j, const float p[3]) {
     growToFit(p);
     const VoxelKey stable = stableKey(p);
-    auto& pts = leaves_[stable];
-    pts.push_back(j);
-    max_leaf_points_ = std::max<uint32_t>(max_leaf_points_, static_cast<uint32_t>(pts.size()));
+    uint64_t at = VoxelKeyHash()(stable) & mask_;
+    int64_t first_tomb = -1;
+    while (true) {
+      Slot& s = slots_[at];
+      if (s.state == kLive && s.key == stable) break;
+      if (s.state == kTomb && first_tomb < 0) first_tomb = static_cast<int64_t>(at);
+      if (s.state == kEmpty) {
+        if (first_tomb >= 0) at = static_cast<uint64_t>(first_tomb);
+        Slot& fresh = slots_[at];
+        fresh.state = kLive;
+        fresh.key = stable;
+        fresh.head = -1;
+        fresh.count = 0;
+        ++n_leaves_;
+        break;
+      }
+      at = (at + 1) & mask_;
+    }
+    Slot& leaf = slots_[at];
+    next_[j] = leaf.head;
+    leaf.head = static_cast<int32_t>(j);
+    ++leaf.count;
+    max_leaf_points_ = std::max(max_leaf_points_, leaf.count);
     return stable;
   }
 
@@ -69,10 +99,19 @@ class LeafBook {
     for (int a = 0; a < 3; ++a) {
       if (p[a] < min_[a] || p[a] >= max_[a]) return;  // isPointWithinBoundingBox
     }
-    const auto it = leaves_.find(stableKey(p));
-    if (it == leaves_.end()) return;
-    killed->swap(it->second);
-    leaves_.erase(it);
+    const VoxelKey stable = stableKey(p);
+    uint64_t at = VoxelKeyHash()(stable) & mask_;
+    while (true) {
+      Slot& s = slots_[at];
+      if (s.state == kEmpty) return;
+      if (s.state == kLive && s.key == stable) {
+        for (int32_t j = s.head; j >= 0; j = next_[j]) killed->push_back(static_cast<uint32_t>(j));
+        s.state = kTomb;
+        --n_leaves_;
+        return;
+      }
+      at = (at + 1) & mask_;
+    }
   }
 
  private:
@@ -138,7 +177,17 @@ class LeafBook {
   double max_[3] = {0, 0, 0};
   uint32_t depth_ = 1;
   int32_t shift_[3] = {0, 0, 0};
-  std::unordered_map<VoxelKey, std::vector<uint32_t>, VoxelKeyHash> leaves_;
+  enum : uint8_t { kEmpty = 0, kLive = 1, kTomb = 2 };
+  struct Slot {
+    VoxelKey key{0, 0, 0};
+    int32_t head = -1;
+    uint32_t count = 0;
+    uint8_t state = kEmpty;
+  };
+  std::vector<Slot> slots_;
+  std::vector<int32_t> next_;
+  uint64_t mask_ = 0;
+  size_t n_leaves_ = 0;
   uint32_t max_leaf_points_ = 0;
 };
 
@@ -147,7 +196,7 @@ struct Builder {
   Schedule* out;
   LeafBook book;
   Builder(const ControlTableHost& c, double resolution, Schedule* o)
-      : ctrl(c), out(o), book(resolution) {
+      : ctrl(c), out(o), book(resolution, c.n) {
     out->runs.clear();
     out->del_run.assign(c.n, 0);
     out->stable_key.assign(3 * c.n, 0);
