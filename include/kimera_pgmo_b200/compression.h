@@ -251,6 +251,17 @@ class OctreeCompression : public MeshCompression {
     handle_.reset(h, [](pgmo_oct_t* p) { pgmo_oct_destroy(p); });
   }
 
+ protected:
+  // BlockCompression: same MeshCompression base flow, cell-hash structure tests
+  struct BlockTag {};
+  OctreeCompression(double resolution, int device, BlockTag) : MeshCompression(resolution) {
+    pgmo_oct_t* h = nullptr;
+    detail::throwOnError(pgmo_oct_create_block(resolution, device, &h));
+    handle_.reset(h, [](pgmo_oct_t* p) { pgmo_oct_destroy(p); });
+  }
+
+ public:
+
   // mesh_compression.cpp:216-417.  The dense per-vertex record from the GPU is replayed onto the
   // caller's persistent `remapping` with the reference's exact container operations:
   // reobservations overwrite (:288), new / converged vertices insert-if-absent (:366-372),
@@ -376,5 +387,14 @@ class OctreeCompression : public MeshCompression {
   std::vector<size_t> active_vertices_index_;
 };
 using OctreeCompressionPtr = std::shared_ptr<OctreeCompression>;
+
+// compression/block_compression.h:14-58: identical interface and base flow; a vertex is a
+// re-observation iff its cell floor(p / resolution) already holds an active vertex.
+class BlockCompression : public OctreeCompression {
+ public:
+  explicit BlockCompression(double resolution, int device = 0)
+      : OctreeCompression(resolution, device, BlockTag()) {}
+};
+using BlockCompressionPtr = std::shared_ptr<BlockCompression>;
 
 }  // namespace kimera_pgmo_b200

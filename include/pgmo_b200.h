@@ -219,6 +219,12 @@ int pgmo_vcc_integrate_device(pgmo_vcc_t* h, uint32_t n_blocks, const int32_t* b
 typedef struct pgmo_oct pgmo_oct_t;
 
 int pgmo_oct_create(double resolution, int device, pgmo_oct_t** out);
+/* Same MeshCompression base flow with BlockCompression's structure tests
+ * (include/kimera_pgmo/compression/block_compression.h:14-58, src/compression/
+ * block_compression.cpp:19-81): a vertex is a re-observation iff its cell
+ * floor(p / resolution) already holds an active vertex (the first one inserted wins).  Every
+ * other pgmo_oct_* entry point works on the handle unchanged. */
+int pgmo_oct_create_block(double resolution, int device, pgmo_oct_t** out);
 void pgmo_oct_destroy(pgmo_oct_t* h);
 
 /* MeshCompression::compressAndIntegrate (mesh_compression.cpp:216-417).  Inputs as for

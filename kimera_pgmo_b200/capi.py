@@ -78,6 +78,7 @@ SIGNATURES = {
     "pgmo_oct_snapshot": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pgmo_oct_last_outputs": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "pgmo_oct_last_stats": (C.c_int, [_vp, _vp]),
+    "pgmo_oct_create_block": (C.c_int, [C.c_double, C.c_int, C.POINTER(_vp)]),
 }
 
 _lib = None
@@ -331,12 +332,14 @@ class VccHandle:
 
 
 class OctHandle:
-    """pgmo_oct_t: OctreeCompression."""
+    """pgmo_oct_t: OctreeCompression, or BlockCompression with block=True (same base flow, cell-hash
+    structure tests)."""
 
-    def __init__(self, resolution: float, device: int = 0):
+    def __init__(self, resolution: float, device: int = 0, block: bool = False):
         self._lib = load()
         h = _vp()
-        _check(self._lib.pgmo_oct_create(float(resolution), device, C.byref(h)))
+        create = self._lib.pgmo_oct_create_block if block else self._lib.pgmo_oct_create
+        _check(create(float(resolution), device, C.byref(h)))
         self._h = h
 
     def close(self):

@@ -349,7 +349,9 @@ struct TreeStore {
 
 struct pgmo_oct {
   int device = 0;
+  int mode = 0;  // 0 = OctreeCompression, 1 = BlockCompression (cell hash)
   double resolution = 0.0;
+  float voxel_size_inv = 1.f;
   cudaStream_t stream = nullptr;
 
   // MeshCompression state (mesh_compression.h:133-147)
@@ -442,7 +444,8 @@ int treeErrorToRc(uint32_t error) {
     return PGMO_ERR_UNSUPPORTED;
   }
   if (error & 2u) {
-    setLastError("octree: vertex farther than 2^18 voxels from the first vertex");
+    setLastError("octree: vertex farther than 2^18 voxels from the first vertex (block mode: cell "
+                 "index beyond +-2^20)");
     return PGMO_ERR_UNSUPPORTED;
   }
   if (error & 8u) {
@@ -482,6 +485,24 @@ int buildPersistent(pgmo_oct_t* h, uint64_t first, cudaStream_t st) {
 
 int buildPersistentOnce(pgmo_oct_t* h, uint64_t first, cudaStream_t st, uint32_t* error_out) {
   const uint64_t n = h->n_act;
+  if (h->mode == 1) {
+    // cell hash: reInitializeStructure = emplace everybody in index order, updateStructure =
+    // emplace the new points; `emplace` keeps the first point of a cell = the smallest index
+    if (first == 0 || !h->ptree_built || h->ptree.factor * n > h->ptree.cap) {
+      PGMO_TRY(h->ptree.reset(2 * n, true, st));
+      h->ptree_built = true;
+      first = 0;
+    }
+    PGMO_CUDA(launchCellInsert(h->ptree.frames.ptr, h->ptree.table(), h->act_xyz.ptr,
+                               static_cast<uint32_t>(first), static_cast<uint32_t>(n),
+                               h->voxel_size_inv, st));
+    PGMO_TRY(checkTreeError(h, &h->ptree, st, error_out));
+    if (*error_out == 4u) {
+      PGMO_CUDA(cudaMemsetAsync(reinterpret_cast<char*>(h->ptree.frames.ptr) + offsetof(OctFrames, error), 0,
+                                sizeof(uint32_t), st));
+    }
+    return PGMO_OK;
+  }
   PGMO_TRY(h->act_next.reserve(h->act_xyz.cap));
   PGMO_TRY(h->act_sigma.reserve(h->act_xyz.cap));
   const bool full = first == 0 || !h->ptree_built || h->ptree.factor * n > h->ptree.cap;
@@ -571,6 +592,13 @@ int pgmo_oct_create(double resolution, int device, pgmo_oct_t** out) {
   return PGMO_OK;
 }
 
+int pgmo_oct_create_block(double resolution, int device, pgmo_oct_t** out) {
+  PGMO_TRY(pgmo_oct_create(resolution, device, out));
+  (*out)->mode = 1;
+  (*out)->voxel_size_inv = 1.0f / static_cast<float>(resolution);
+  return PGMO_OK;
+}
+
 void pgmo_oct_destroy(pgmo_oct_t* h) {
   if (!h) return;
   cudaSetDevice(h->device);
@@ -622,8 +650,13 @@ int pgmo_oct_integrate(pgmo_oct_t* h, uint32_t n_blocks, const int32_t* block_id
 
   // ---- persistent-structure test for every vertex (:268)
   if (!h->ptree_built) PGMO_TRY(buildPersistent(h, 0, st));
-  PGMO_CUDA(launchOctQueryPersistent(h->ptree.frames.ptr, h->ptree.table(), h->act_xyz.ptr,
-                                     h->act_next.ptr, h->d_xyz.ptr, n, res, h->reobs.ptr, st));
+  if (h->mode == 1) {
+    PGMO_CUDA(launchCellQueryPersistent(h->ptree.table(), h->d_xyz.ptr, n, h->voxel_size_inv,
+                                        h->reobs.ptr, st));
+  } else {
+    PGMO_CUDA(launchOctQueryPersistent(h->ptree.frames.ptr, h->ptree.table(), h->act_xyz.ptr,
+                                       h->act_next.ptr, h->d_xyz.ptr, n, res, h->reobs.ptr, st));
+  }
   octCandFlagsKernel<<<blocksFor(n), 256, 0, st>>>(h->reobs.ptr, n, h->flag.ptr);
   uint64_t n_cand = 0;
   PGMO_TRY(compact(h, h->flag.ptr, n, &h->cand_list, 0, st, &n_cand));
@@ -650,7 +683,24 @@ int pgmo_oct_integrate(pgmo_oct_t* h, uint32_t n_blocks, const int32_t* block_id
     cpts.xyz = h->cand_xyz.ptr;
     cpts.next = h->cand_next.ptr;
     cpts.sigma = h->cand_sigma.ptr;
-    while (true) {
+    while (h->mode == 1) {
+      // BlockCompression: the first candidate of a cell is the temp vertex, no iteration needed
+      h->last_rounds = 1;
+      PGMO_TRY(h->ttree.reset(n_cand, true, st));
+      PGMO_CUDA(launchCellInsert(h->ttree.frames.ptr, h->ttree.table(), h->cand_xyz.ptr, 0, nc,
+                                 h->voxel_size_inv, st));
+      PGMO_CUDA(launchCellDecideTemp(h->ttree.table(), h->cand_xyz.ptr, nc, h->voxel_size_inv, member,
+                                     h->decision.ptr, st));
+      uint32_t error = 0;
+      PGMO_TRY(checkTreeError(h, &h->ttree, st, &error));
+      if (error == 4u && h->ttree.factor < 256) {
+        h->ttree.factor *= 2;
+        continue;
+      }
+      PGMO_TRY(treeErrorToRc(error));
+      break;
+    }
+    while (h->mode == 0) {
       ++h->last_rounds;
       PGMO_TRY(h->ttree.reset(n_cand, true, st));
       PGMO_CUDA(launchOctGrow(h->ttree.frames.ptr, h->cand_xyz.ptr, member, 0, nc, res, st));

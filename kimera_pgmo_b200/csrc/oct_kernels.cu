@@ -348,7 +348,92 @@ octDecideTempKernel(const OctFrames* F, const OctTable t, const float4* __restri
   if (m != member_in[c]) atomicOr(changed, 1u);
 }
 
+// ---- BlockCompression cell hash
+constexpr long long kCellOffset = 1ll << 20;
+constexpr long long kCellLimit = 1ll << 21;
+
+__device__ __forceinline__ bool cellKey(float x, float y, float z, float inv,
+                                        unsigned long long* key) {
+  const long long cx = static_cast<long long>(floorf(__fmul_rn(x, inv))) + kCellOffset;
+  const long long cy = static_cast<long long>(floorf(__fmul_rn(y, inv))) + kCellOffset;
+  const long long cz = static_cast<long long>(floorf(__fmul_rn(z, inv))) + kCellOffset;
+  if (cx < 0 || cy < 0 || cz < 0 || cx >= kCellLimit || cy >= kCellLimit || cz >= kCellLimit) {
+    return false;
+  }
+  *key = (static_cast<unsigned long long>(cx) << 42) | (static_cast<unsigned long long>(cy) << 21) |
+         static_cast<unsigned long long>(cz);
+  return true;
+}
+
+__global__ void __launch_bounds__(256)
+cellInsertKernel(OctFrames* F, const OctTable t, const float4* __restrict__ xyz, uint32_t first,
+                 uint32_t n, float inv) {
+  const uint32_t i = first + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = xyz[i];
+  unsigned long long key;
+  if (!cellKey(p.x, p.y, p.z, inv, &key)) {
+    atomicOr(&F->error, 2u);
+    return;
+  }
+  if (tableInsert(t, key, i) == kOctNone) atomicOr(&F->error, 4u);
+}
+
+__global__ void __launch_bounds__(256)
+cellQueryPersistentKernel(const OctTable t, const float* __restrict__ xyz, uint32_t n, float inv,
+                          int32_t* __restrict__ result) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned long long key;
+  int32_t r = -1;
+  if (cellKey(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], inv, &key)) {
+    const uint32_t slot = tableFind(t, key);
+    if (slot != kOctNone) r = static_cast<int32_t>(t.minseq[slot]);
+  }
+  result[i] = r;
+}
+
+__global__ void __launch_bounds__(256)
+cellDecideTempKernel(const OctTable t, const float4* __restrict__ cand_xyz, uint32_t n_cand,
+                     float inv, uint8_t* __restrict__ member_out, int32_t* __restrict__ decision) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_cand) return;
+  const float4 p = cand_xyz[c];
+  unsigned long long key;
+  int32_t d = -1;
+  if (cellKey(p.x, p.y, p.z, inv, &key)) {
+    const uint32_t slot = tableFind(t, key);
+    if (slot != kOctNone && t.minseq[slot] != c) d = static_cast<int32_t>(t.minseq[slot]);
+  }
+  decision[c] = d;
+  member_out[c] = d < 0 ? 1 : 0;
+}
+
 }  // namespace
+
+cudaError_t launchCellInsert(OctFrames* frames, OctTable table, const float4* xyz, uint32_t first,
+                             uint32_t n, float voxel_size_inv, cudaStream_t stream) {
+  if (first >= n) return cudaSuccess;
+  cellInsertKernel<<<(n - first + 255) / 256, 256, 0, stream>>>(frames, table, xyz, first, n,
+                                                                voxel_size_inv);
+  return cudaGetLastError();
+}
+
+cudaError_t launchCellQueryPersistent(OctTable table, const float* xyz, uint32_t n,
+                                      float voxel_size_inv, int32_t* result, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  cellQueryPersistentKernel<<<(n + 255) / 256, 256, 0, stream>>>(table, xyz, n, voxel_size_inv, result);
+  return cudaGetLastError();
+}
+
+cudaError_t launchCellDecideTemp(OctTable table, const float4* cand_xyz, uint32_t n_cand,
+                                 float voxel_size_inv, uint8_t* member_out, int32_t* decision,
+                                 cudaStream_t stream) {
+  if (n_cand == 0) return cudaSuccess;
+  cellDecideTempKernel<<<(n_cand + 255) / 256, 256, 0, stream>>>(table, cand_xyz, n_cand,
+                                                                 voxel_size_inv, member_out, decision);
+  return cudaGetLastError();
+}
 
 cudaError_t launchOctGrow(OctFrames* frames, const float4* xyz, const uint8_t* member,
                           uint32_t first, uint32_t n, double resolution, cudaStream_t stream) {

@@ -101,4 +101,21 @@ cudaError_t launchOctDecideTemp(const OctFrames* frames, OctTable table, const f
                                 const uint8_t* member_in, uint8_t* member_out, int32_t* decision,
                                 uint32_t* changed, cudaStream_t stream);
 
+// ---- BlockCompression (kimera_pgmo/src/compression/block_compression.cpp:19-81): the structure
+// is a cell hash, cell = floor(p * (1 / voxel_size)) per axis in float (spatial_hash::Grid::toIndex
+// as restated by the oracle), value = the first point of the cell (`emplace` never overwrites).
+// Re-uses OctTable: keys = packed cell, minseq = smallest point index, frames->error for errors.
+
+// emplace(toIndex(p_i), i) for points [first, n)
+cudaError_t launchCellInsert(OctFrames* frames, OctTable table, const float4* xyz, uint32_t first,
+                             uint32_t n, float voxel_size_inv, cudaStream_t stream);
+// checkIfVertexUnique for every input vertex: result[i] = matched active position or -1
+cudaError_t launchCellQueryPersistent(OctTable table, const float* xyz, uint32_t n,
+                                      float voxel_size_inv, int32_t* result, cudaStream_t stream);
+// checkIfVertexTempUnique in sequence order: the first candidate of a cell is temp-unique, every
+// later one converges to it.  decision[c] = -1 or the ordinal of the first candidate of c's cell.
+cudaError_t launchCellDecideTemp(OctTable table, const float4* cand_xyz, uint32_t n_cand,
+                                 float voxel_size_inv, uint8_t* member_out, int32_t* decision,
+                                 cudaStream_t stream);
+
 }  // namespace pgmo

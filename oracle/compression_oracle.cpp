@@ -231,6 +231,58 @@ static bool inOctree(const OctreeSearchRestated& octree, const PointXYZ& v, int*
   return true;
 }
 
+// ---------------------------------------------------------------------------------------
+// block_compression.cpp:19-81
+LongIndex BlockCompression::toIndex(const PointXYZ& p) const {
+  LongIndex i;
+  i.x = static_cast<int64_t>(std::floor(p.x * voxel_size_inv_));
+  i.y = static_cast<int64_t>(std::floor(p.y * voxel_size_inv_));
+  i.z = static_cast<int64_t>(std::floor(p.z * voxel_size_inv_));
+  return i;
+}
+
+void BlockCompression::reInitializeStructure(const std::vector<PointXYZ>& active_vertices) {
+  cell_hash_.clear();
+  size_t idx = 0;
+  for (const auto& p : active_vertices) {
+    cell_hash_.emplace(toIndex(p), idx);  // first point of a cell keeps it
+    idx++;
+  }
+}
+
+bool BlockCompression::checkIfVertexUnique(const PointXYZ& v, int* matched_ind) const {
+  const auto it = cell_hash_.find(toIndex(v));
+  if (it == cell_hash_.end()) return true;
+  *matched_ind = static_cast<int>(it->second);
+  return false;
+}
+
+void BlockCompression::updateStructure(const std::vector<PointXYZ>& vertices) {
+  const size_t vertex_index = vertices.size() - 1;
+  cell_hash_.emplace(toIndex(vertices[vertex_index]), vertex_index);
+}
+
+bool BlockCompression::checkIfVertexTempUnique(const PointXYZ& v, int* matched_ind) const {
+  const auto it = temp_cell_hash_.find(toIndex(v));
+  if (it == temp_cell_hash_.end()) return true;
+  *matched_ind = static_cast<int>(it->second);
+  return false;
+}
+
+void BlockCompression::initializeTempStructure(const std::vector<PointXYZ>& vertices) {
+  temp_cell_hash_.clear();
+  size_t idx = 0;
+  for (const auto& p : vertices) {
+    temp_cell_hash_.emplace(toIndex(p), idx);
+    idx++;
+  }
+}
+
+void BlockCompression::updateTempStructure(const std::vector<PointXYZ>& vertices) {
+  const size_t vertex_index = vertices.size() - 1;
+  temp_cell_hash_.emplace(toIndex(vertices[vertex_index]), vertex_index);
+}
+
 OctreeCompression::OctreeCompression(double resolution) : MeshCompression(resolution) {
   octree_.reset(new OctreeSearchRestated(resolution));
   octree_->setInputCloud(&active_vertices_xyz_);

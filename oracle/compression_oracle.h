@@ -162,6 +162,29 @@ class OctreeCompression : public MeshCompression {
   std::unique_ptr<OctreeSearchRestated> temp_octree_;
 };
 
+// compression/block_compression.{h,cpp}: uniqueness by cell hash (SURVEY.md 8f "next" #1).
+// spatial_hash::Grid<LongIndex>::toIndex (MIT-SPARK/Spatial-Hash, unpinned, absent here) is
+// restated as floor(p * (1 / voxel_size)) per axis in float, the voxblox getGridIndexFromPoint
+// family it derives from without the epsilon; PARITY UNPINNED beyond what
+// test_block_compression.cpp checks (integer-aligned vertices).
+class BlockCompression : public MeshCompression {
+ public:
+  explicit BlockCompression(double resolution)
+      : MeshCompression(resolution), voxel_size_inv_(1.0f / static_cast<float>(resolution)) {}
+  void reInitializeStructure(const std::vector<PointXYZ>& active_vertices) override;
+  bool checkIfVertexUnique(const PointXYZ& v, int* matched_ind) const override;
+  void updateStructure(const std::vector<PointXYZ>& vertices) override;
+  bool checkIfVertexTempUnique(const PointXYZ& v, int* matched_ind) const override;
+  void initializeTempStructure(const std::vector<PointXYZ>& vertices) override;
+  void updateTempStructure(const std::vector<PointXYZ>& vertices) override;
+  LongIndex toIndex(const PointXYZ& p) const;
+
+ protected:
+  float voxel_size_inv_;
+  LongIndexHashMap<size_t> cell_hash_;
+  LongIndexHashMap<size_t> temp_cell_hash_;
+};
+
 class VoxelClearingCompression : public MeshCompression {
  public:
   explicit VoxelClearingCompression(double resolution) : MeshCompression(resolution) {}

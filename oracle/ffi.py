@@ -150,12 +150,12 @@ class GraphPath:
 
 
 class Compression:
-    """MeshCompression family: kind 'voxel_clearing' | 'octree'."""
+    """MeshCompression family: kind 'voxel_clearing' | 'octree' | 'block'."""
 
     def __init__(self, kind, resolution):
         self._lib = load()
         self.kind = kind
-        self._h = _vp(self._lib.oracle_comp_create(0 if kind == "voxel_clearing" else 1,
+        self._h = _vp(self._lib.oracle_comp_create({"voxel_clearing": 0, "octree": 1, "block": 2}[kind],
                                                    float(resolution)))
         self.elapsed_s = 0.0
 

@@ -292,6 +292,73 @@ void katOctreePrune() {
   KAT_EQ(s.triangles.at(3)[2], 10u);
 }
 
+
+// kimera_pgmo/test/test_block_compression.cpp:40-160 (returnedValues + storedValues),
+// :161-260 (pruneStoredMesh), :262-340 (…Compressed)
+template <typename C>
+void katSimpleMeshFlow(double res) {
+  C c(res);
+  Scratch s;
+  c.compressAndIntegrate(simpleMeshInterface(1.0), s.vertices, s.triangles, s.indices,
+                         s.remappings, 100.0);
+  KAT_EQ(s.vertices.size(), 5u);
+  KAT_EQ(s.triangles.size(), 4u);
+  KAT_TRUE(s.indices == (V{0, 1, 2, 3, 4}));
+  KAT_EQ(s.vertices[1].x, 1.f);
+  KAT_EQ(s.vertices[2].y, 1.f);
+  KAT_EQ(s.vertices[4].z, 1.f);
+  KAT_EQ(s.triangles.at(0)[0], 0u);
+  KAT_EQ(s.triangles.at(3)[2], 2u);
+  KAT_EQ(c.getVertices().size(), 5u);
+  KAT_EQ(c.getActiveVertices().size(), 5u);
+  KAT_EQ(c.getStoredPolygons().size(), 4u);
+  s = Scratch();
+  c.compressAndIntegrate(simpleMeshInterface(2.0), s.vertices, s.triangles, s.indices,
+                         s.remappings, 101.0);
+  KAT_EQ(s.vertices.size(), 4u);
+  KAT_EQ(s.triangles.size(), 4u);
+  KAT_TRUE(s.indices == (V{0, 5, 6, 7, 8}));
+  KAT_EQ(s.vertices[0].x, 2.f);
+  KAT_EQ(s.vertices[2].y, 2.f);
+  KAT_EQ(s.vertices[3].z, 2.f);
+  KAT_EQ(s.triangles.at(0)[0], 0u);
+  KAT_EQ(s.triangles.at(3)[2], 6u);
+  KAT_EQ(c.getVertices().size(), 9u);
+  KAT_EQ(c.getStoredPolygons().size(), 8u);
+  c.pruneStoredMesh(100.5);
+  KAT_EQ(c.getActiveVertices().size(), 5u);
+  KAT_EQ(c.getStoredPolygons().size(), 8u);
+  KAT_EQ(c.getVertices().size(), 9u);
+  KAT_EQ(c.getActiveVertices()[1].x, 2.f);
+  KAT_EQ(c.getActiveVerticesTimestamps().at(0), 101.0);
+  s = Scratch();
+  c.compressAndIntegrate(simpleMeshInterface(1.0), s.vertices, s.triangles, s.indices,
+                         s.remappings, 102.0);
+  KAT_EQ(s.vertices.size(), 4u);
+  KAT_EQ(s.triangles.size(), 4u);
+  KAT_TRUE(s.indices == (V{0, 9, 10, 11, 12}));
+  KAT_EQ(s.triangles.at(1)[1], 11u);
+  KAT_EQ(s.triangles.at(3)[2], 10u);
+}
+
+void katBlockCompression() {
+  katSimpleMeshFlow<BlockCompression>(0.1);
+  // test_block_compression.cpp:262-300: a 10 m cell swallows the whole mesh, nothing survives
+  BlockCompression c(10.0);
+  Scratch s;
+  c.compressAndIntegrate(simpleMeshInterface(1.0), s.vertices, s.triangles, s.indices,
+                         s.remappings, 100.0);
+  KAT_EQ(s.vertices.size(), 0u);
+  KAT_EQ(s.triangles.size(), 0u);
+  KAT_EQ(s.indices.size(), 0u);
+  KAT_EQ(c.getVertices().size(), 0u);
+  s = Scratch();
+  c.compressAndIntegrate(simpleMeshInterface(2.0), s.vertices, s.triangles, s.indices,
+                         s.remappings, 101.0);
+  KAT_EQ(s.vertices.size(), 0u);
+  KAT_EQ(c.getStoredPolygons().size(), 0u);
+}
+
 void katOctreeFullCollapse() {
   OctreeCompression c(10.0);
   Scratch s;
@@ -521,6 +588,7 @@ int runCompressionKats() {
   katOctreeReturnedAndStored();
   katOctreePrune();
   katOctreeFullCollapse();
+  katBlockCompression();
   katFrontendMeshes(0.5);
   katFrontendMeshes(0.1);
   katFrontendCollapse();

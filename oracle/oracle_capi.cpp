@@ -197,6 +197,8 @@ void* oracle_comp_create(int kind, double resolution) {
   if (kind == 0) {
     h->vcc = new VoxelClearingCompression(resolution);
     h->comp.reset(h->vcc);
+  } else if (kind == 2) {
+    h->comp.reset(new BlockCompression(resolution));
   } else {
     h->comp.reset(new OctreeCompression(resolution));
   }

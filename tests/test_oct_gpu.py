@@ -22,9 +22,9 @@ def _compare_state(gpu, ora):
     np.testing.assert_array_equal(gs["active_stamps"], os_["active_stamps"])
 
 
-def _run_stream(capi, oracle, stream, res, horizon=None, check_every=1):
-    gpu = capi.OctHandle(res, 0)
-    ora = oracle.Compression("octree", res)
+def _run_stream(capi, oracle, stream, res, horizon=None, check_every=1, kind="octree"):
+    gpu = capi.OctHandle(res, 0, block=(kind == "block"))
+    ora = oracle.Compression(kind, res)
     for m, (blocks, offsets, xyz, rgba, t) in enumerate(stream):
         if horizon is not None:
             gpu.prune(t - horizon)
@@ -85,6 +85,34 @@ def test_stream_with_horizon_pruning(capi, oracle):
     stream = list(synth.compression_stream(12, 3_000, n_blocks=3, seed=9, slide=4.0))
     _run_stream(capi, oracle, stream, 0.05, horizon=2.5)
     _run_stream(capi, oracle, stream, 0.3, horizon=1.5)
+
+
+@pytest.mark.parametrize("res", [0.05, 0.2, 1.0])
+def test_block_compression_parity(capi, oracle, res):
+    """BlockCompression (SURVEY 8f next row #1): same base flow, cell-hash structure tests."""
+    stream = list(synth.compression_stream(6, 6_000, n_blocks=4, seed=3))
+    _run_stream(capi, oracle, stream, res, kind="block")
+    stream = list(synth.compression_stream(10, 3_000, n_blocks=2, seed=9, slide=4.0))
+    _run_stream(capi, oracle, stream, res, horizon=2.5, kind="block")
+
+
+def test_block_compression_reference_scenarios(capi, oracle):
+    # kimera_pgmo/test/test_block_compression.cpp: createSimpleMesh(1.0) then (2.0), res 0.1 and 10
+    def simple(scale):
+        v = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0], [0, 0, 1]], dtype=np.float32) * scale
+        faces = [[0, 1, 2], [1, 3, 2], [0, 1, 4], [0, 4, 2]]
+        return _mesh([[v[i] for i in f] for f in faces])
+    for res in (0.1, 10.0):
+        stream = [(*simple(1.0), 100.0), (*simple(2.0), 101.0), (*simple(1.0), 102.0)]
+        _run_stream(capi, oracle, stream, res, kind="block")
+        _run_stream(capi, oracle, stream, res, horizon=0.9, kind="block")
+    h = capi.OctHandle(0.1, 0, block=True)
+    h.integrate(*simple(1.0), 100.0)
+    assert h.sizes()[0] == 5 and h.sizes()[1] == 4          # :52-54
+    assert h.last_outputs()["new_indices"].tolist() == [0, 1, 2, 3, 4]
+    h.integrate(*simple(2.0), 101.0)
+    assert h.last_outputs()["new_indices"].tolist() == [0, 5, 6, 7, 8]  # :79
+    h.close()
 
 
 def test_dense_chains_need_many_rounds(capi, oracle):
