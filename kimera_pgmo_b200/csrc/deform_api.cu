@@ -661,8 +661,9 @@ static int runDeviceRange(pgmo_deform_t* h, uint64_t first_position, uint64_t n_
     PGMO_CUDA(cudaStreamSynchronize(st));
     *n_resolved = h->h_counters.ptr[0];
     if (std::getenv("PGMO_DEBUG")) {
-      fprintf(stderr, "pgmo debug counters: resolved %llu groups %llu scanned %llu boxvol_l %llu\n",
-              h->h_counters.ptr[0], h->h_counters.ptr[1], h->h_counters.ptr[2], h->h_counters.ptr[3]);
+      fprintf(stderr, "pgmo debug counters: resolved %llu groups %llu scanned %llu box_area_mm2 %llu box_z_mm %llu\n",
+              h->h_counters.ptr[0], h->h_counters.ptr[4], h->h_counters.ptr[5], h->h_counters.ptr[6],
+              h->h_counters.ptr[7]);
     }
   }
   return PGMO_OK;

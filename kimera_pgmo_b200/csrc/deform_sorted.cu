@@ -7,9 +7,10 @@
 // bookkeeping.  This kernel removes both:
 //
 //   * One CTA = one work item (<= 2048 consecutive positions of ONE run, i.e. one alive set of
-//     a few hundred control points, staged in shared memory).  The vertices are counting-sorted
-//     in shared memory by 2x2x2-cell tile of a grid over their own bounding box, so that every
-//     group of 32 consecutive sorted vertices (= one warp pass) is a compact blob B.
+//     a few hundred control points, staged in shared memory).  The vertices are split, by two
+//     counting sorts in shared memory, into equal-count slabs along the longest axis of their
+//     box and then into groups of 32 along the second longest, so that every warp pass is a
+//     compact column B.
 //   * Per group, the warp buckets ALL alive points by a lower bound of their squared distance
 //     to B's bounding box (32 buckets of width r0^2/8) and walks the buckets outwards.  Lanes
 //     keep their (K+1) smallest keys in registers; the walk stops as soon as every lane's
@@ -47,7 +48,9 @@ constexpr int kSThreads = 256;
 constexpr int kSWarps = kSThreads / 32;
 constexpr int kSChunk = kDeformChunk;  // positions per work item
 constexpr int kSBuckets = 32;
-constexpr int kSMaxCells = 1024;       // sort bins (8 per tile)
+constexpr int kSMaxCells = 1024;       // sort bins of a pass
+constexpr int kSVBins = 128;           // bins along the second axis inside a slab (8 slabs)
+static_assert((kSChunk / 256) * kSVBins <= kSMaxCells, "slab x bin keys");
 constexpr int kStagedMaxPts = 256;     // alive-set size up to which the pose rows are staged
 
 template <int MAXPTS>
@@ -70,7 +73,10 @@ struct SortedSmem {
   float vx[kSChunk], vy[kSChunk], vz[kSChunk];
   uint16_t perm[kSChunk];                   // sorted position -> vertex of the item
   union alignas(16) {
-    uint32_t hist[kSMaxCells + 1];          // vertex sort only
+    struct {                                // vertex sort only
+      uint32_t hist[kSMaxCells + 1];
+      uint16_t perm1[kSChunk];              // order along the first split axis
+    } sort;
     struct {
       uint16_t tmp[kSWarps][MAXPTS];        // per point: bucket << slot bits | rank in the bucket
       uint16_t list[kSWarps][MAXPTS + 8];   // bucket-ordered: bucket << slot bits | point slot
@@ -102,12 +108,6 @@ __device__ __forceinline__ float warpMaxF(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
   return v;
-}
-
-__device__ __forceinline__ int clampCell(float p, float origin, float inv_cell, int n) {
-  int c = static_cast<int>((p - origin) * inv_cell);
-  c = c < 0 ? 0 : c;
-  return c >= n ? n - 1 : c;
 }
 
 // interpPoint's blend with the pose rows read from shared memory (same arithmetic, operation
@@ -283,7 +283,7 @@ deformKnnBlendSortedKernel(const DeformArgs a, const GridArgs ga,
     S.red[4][warp] = mx1;
     S.red[5][warp] = mx2;
   }
-  for (int i = t; i <= kSMaxCells; i += kSThreads) S.u.hist[i] = 0;
+  for (int i = t; i <= kSMaxCells; i += kSThreads) S.u.sort.hist[i] = 0;
   __syncthreads();
   if (t == 0) {
     float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
@@ -293,77 +293,44 @@ deformKnnBlendSortedKernel(const DeformArgs a, const GridArgs ga,
         hi[ax] = fmaxf(hi[ax], S.red[3 + ax][w]);
       }
     }
-    // sort grid over the vertices' box: ~4 vertices per cell, 2x2x2 cells per tile, so that 32
-    // consecutive sorted vertices fill about one tile.  NaN / inf coordinates degrade the
-    // ordering only (cells are clamped), never the result.
+    // Grouping = a two-level equal-count split over the two longest axes of the item's box:
+    // slabs of 256 vertices along u, then groups of 32 along v inside each slab, so that every
+    // warp pass is a compact column (the shortest axis — height, for a building-scale mesh — is
+    // left unsplit: the alive control points span it anyway).  NaN / inf coordinates degrade
+    // the ordering only (bins are clamped), never the result.
     float ext[3];
     for (int ax = 0; ax < 3; ++ax) {
       ext[ax] = hi[ax] - lo[ax];
       if (!(ext[ax] >= 0.f) || ext[ax] > 1e30f) ext[ax] = 0.f;
     }
-    const float target = fmaxf(static_cast<float>(count) * 0.25f, 1.f);
-    const float longest = fmaxf(fmaxf(ext[0], ext[1]), ext[2]);
-    float cell = 1.f;
-    if (longest > 0.f) {
-      // cell edge s with prod(max(ext / s, 1)) ~ target: thin extents count as one cell
-      float s = longest / target;  // 1-d answer: the smallest candidate
-      for (int it = 0; it < 3; ++it) {
-        float vol = 1.f;
-        int dims = 0;
-        for (int ax = 0; ax < 3; ++ax) {
-          if (ext[ax] > s) {
-            vol *= ext[ax];
-            ++dims;
-          }
-        }
-        if (dims == 0) break;
-        const float per = vol / target;
-        s = dims == 3 ? cbrtf(per) : (dims == 2 ? sqrtf(per) : per);
-      }
-      cell = fmaxf(s, longest * (1.f / 512.f));
-    }
-    int nx, ny, nz;
-    while (true) {
-      nx = static_cast<int>(ext[0] / cell) + 1;
-      ny = static_cast<int>(ext[1] / cell) + 1;
-      nz = static_cast<int>(ext[2] / cell) + 1;
-      const long long bins = 8ll * ((nx + 1) >> 1) * ((ny + 1) >> 1) * ((nz + 1) >> 1);
-      if (bins <= kSMaxCells) break;
-      cell *= 1.26f;
-    }
-    S.grid[0] = lo[0];
-    S.grid[1] = lo[1];
-    S.grid[2] = lo[2];
-    S.grid[3] = 1.f / cell;
-    S.grid[4] = __int_as_float(nx);
-    S.grid[5] = __int_as_float(ny);
-    S.grid[6] = __int_as_float(nz);
+    int u = 0;
+    if (ext[1] > ext[u]) u = 1;
+    if (ext[2] > ext[u]) u = 2;
+    int v = (u + 1) % 3, w3 = (u + 2) % 3;
+    if (ext[w3] > ext[v]) v = w3;
+    S.grid[0] = lo[u];
+    S.grid[1] = ext[u] > 0.f ? static_cast<float>(kSMaxCells) / ext[u] : 0.f;
+    S.grid[2] = lo[v];
+    S.grid[3] = ext[v] > 0.f ? static_cast<float>(kSVBins) / ext[v] : 0.f;
+    S.grid[4] = __int_as_float(u);
+    S.grid[5] = __int_as_float(v);
   }
   __syncthreads();
-  const float gox = S.grid[0], goy = S.grid[1], goz = S.grid[2], ginv = S.grid[3];
-  const int nx = __float_as_int(S.grid[4]), ny = __float_as_int(S.grid[5]),
-            nz = __float_as_int(S.grid[6]);
-  const int txs = (nx + 1) >> 1, tys = (ny + 1) >> 1, tzs = (nz + 1) >> 1;
-  const int n_bins = 8 * txs * tys * tzs;
+  const float u_lo = S.grid[0], u_inv = S.grid[1], v_lo = S.grid[2], v_inv = S.grid[3];
+  const int axis_u = __float_as_int(S.grid[4]), axis_v = __float_as_int(S.grid[5]);
+  const float* cu = axis_u == 0 ? S.vx : (axis_u == 1 ? S.vy : S.vz);
+  const float* cv = axis_v == 0 ? S.vx : (axis_v == 1 ? S.vy : S.vz);
+  uint16_t* perm1 = S.u.sort.perm1;
 
-  // ---- counting sort of the vertices by bin (tile-major, 8 cells per tile)
-  auto binOf = [&](int i) {
-    const int ix = clampCell(S.vx[i], gox, ginv, nx);
-    const int iy = clampCell(S.vy[i], goy, ginv, ny);
-    const int iz = clampCell(S.vz[i], goz, ginv, nz);
-    return ((((iz >> 1) * tys + (iy >> 1)) * txs + (ix >> 1)) << 3) | ((iz & 1) << 2) |
-           ((iy & 1) << 1) | (ix & 1);
-  };
-  for (int i = t; i < count; i += kSThreads) atomicAdd(&S.u.hist[binOf(i) + 1], 1u);
-  __syncthreads();
-  {
+  // block-wide exclusive scan of hist[1..n_bins] (in place: hist[i] = #entries in bins < i)
+  auto scanHist = [&](int n_bins) {
     constexpr int per = (kSMaxCells + kSThreads - 1) / kSThreads;
     uint32_t local[per];
     uint32_t sum = 0;
 #pragma unroll
     for (int e = 0; e < per; ++e) {
       const int i = 1 + t * per + e;
-      local[e] = i <= n_bins ? S.u.hist[i] : 0;
+      local[e] = i <= n_bins ? S.u.sort.hist[i] : 0;
       sum += local[e];
     }
     uint32_t incl = sum;
@@ -380,12 +347,40 @@ deformKnnBlendSortedKernel(const DeformArgs a, const GridArgs ga,
     for (int e = 0; e < per; ++e) {
       const int i = 1 + t * per + e;
       run_sum += local[e];
-      if (i <= n_bins) S.u.hist[i] = run_sum;  // hist[i] = #vertices in bins < i
+      if (i <= n_bins) S.u.sort.hist[i] = run_sum;
     }
+    __syncthreads();
+  };
+  auto clampBin = [](float c, float lo, float inv, int n) {
+    int b = static_cast<int>((c - lo) * inv);
+    b = b < 0 ? 0 : b;
+    return b >= n ? n - 1 : b;
+  };
+
+  // ---- pass 1: counting sort along u (1024 bins) -> perm1
+  for (int i = t; i < count; i += kSThreads) {
+    atomicAdd(&S.u.sort.hist[clampBin(cu[i], u_lo, u_inv, kSMaxCells) + 1], 1u);
   }
   __syncthreads();
+  scanHist(kSMaxCells);
   for (int i = t; i < count; i += kSThreads) {
-    const uint32_t at = atomicAdd(&S.u.hist[binOf(i)], 1u);
+    const uint32_t at = atomicAdd(&S.u.sort.hist[clampBin(cu[i], u_lo, u_inv, kSMaxCells)], 1u);
+    perm1[at] = static_cast<uint16_t>(i);
+  }
+  __syncthreads();
+  // ---- pass 2: inside each slab of 256 (by rank along u) counting sort along v (128 bins)
+  for (int i = t; i <= kSMaxCells; i += kSThreads) S.u.sort.hist[i] = 0;
+  __syncthreads();
+  for (int rk = t; rk < count; rk += kSThreads) {
+    const int key = (rk >> 8) * kSVBins + clampBin(cv[perm1[rk]], v_lo, v_inv, kSVBins);
+    atomicAdd(&S.u.sort.hist[key + 1], 1u);
+  }
+  __syncthreads();
+  scanHist(kSMaxCells);
+  for (int rk = t; rk < count; rk += kSThreads) {
+    const int i = perm1[rk];
+    const int key = (rk >> 8) * kSVBins + clampBin(cv[i], v_lo, v_inv, kSVBins);
+    const uint32_t at = atomicAdd(&S.u.sort.hist[key], 1u);
     S.perm[at] = static_cast<uint16_t>(i);
   }
   __syncthreads();  // hist is dead from here on: tmp / list alias it
@@ -401,7 +396,7 @@ deformKnnBlendSortedKernel(const DeformArgs a, const GridArgs ga,
   // ordinal bits: enough for every list position of this run
   const int ord_bits = n_alive <= 128 ? 7 : (n_alive <= 256 ? 8 : 9);
   const uint32_t ord_mask = (1u << ord_bits) - 1u;
-  const float bw = fmaxf(g.r0 * g.r0 * 0.125f, 1e-20f);  // bucket width in d^2
+  const float bw = fmaxf(g.r0 * g.r0 * 0.125f * ga.r_scale, 1e-20f);  // bucket width in d^2
   const float inv_bw = 1.f / bw;
   const float bw_lb = bw * 0.9999f;
   const bool full_k = n_need == KCAP;
@@ -494,6 +489,9 @@ deformKnnBlendSortedKernel(const DeformArgs a, const GridArgs ga,
         const bool ok = __uint_as_float(kth | ord_mask) < lb;
         if (__all_sync(full, ok)) break;
       }
+#ifdef PGMO_DEBUG_COUNTERS
+      if (lane == 0) atomicAdd(a.counters + 5, 4ull);
+#endif
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const float4 p = S.pts[e[u] & (kSMaxPts - 1)];  // same address in all lanes: broadcast
@@ -501,6 +499,13 @@ deformKnnBlendSortedKernel(const DeformArgs a, const GridArgs ga,
         chainInsert<KCAP>(best, (__float_as_uint(d2) & ~ord_mask) | static_cast<uint32_t>(c + u));
       }
     }
+#ifdef PGMO_DEBUG_COUNTERS
+    if (lane == 0) {
+      atomicAdd(a.counters + 4, 1ull);
+      atomicAdd(a.counters + 6, static_cast<unsigned long long>((hix - lox) * (hiy - loy) * 1000.f));
+      atomicAdd(a.counters + 7, static_cast<unsigned long long>((hiz - loz) * 1000.f));
+    }
+#endif
     if (!active) continue;
 
     // winners: exact d^2 and control index back from the list
