@@ -83,6 +83,9 @@ struct SortedSmem {
     } w;
   } u;
   uint32_t bcnt[kSWarps][kSBuckets];
+  // per warp: the alive points that can matter for the slab being processed (the rest sits in
+  // the catch-all tail of the list)
+  typename std::conditional<(MAXPTS <= 256), uint8_t, uint16_t>::type near[kSWarps][MAXPTS];
   float red[6][kSWarps];
   uint32_t warp_tot[kSWarps];
   float grid[8];                            // origin xyz, inv cell, nx, ny, nz (as float bits)
@@ -390,7 +393,6 @@ deformKnnBlendSortedKernel(const DeformArgs a, const GridArgs ga,
   uint16_t* tmp = S.u.w.tmp[warp];
   uint16_t* list = S.u.w.list[warp];
   uint32_t* bcnt = S.bcnt[warp];
-  const int n_groups = (count + 31) >> 5;
   const int n_need = n_alive < K + 1 ? n_alive : K + 1;
   const int n = n_alive < K ? n_alive : K;
   // ordinal bits: enough for every list position of this run
@@ -401,7 +403,66 @@ deformKnnBlendSortedKernel(const DeformArgs a, const GridArgs ga,
   const float bw_lb = bw * 0.9999f;
   const bool full_k = n_need == KCAP;
 
-  for (int group = warp; group < n_groups; group += kSWarps) {
+  // A warp takes whole slabs (256 sorted vertices = 8 groups).  Per slab the alive points are
+  // split once: points whose lower-bound distance to the SLAB's box already lands in the last
+  // bucket go straight to the tail of the list (they are in the last bucket for every group of
+  // the slab: a group's box lies inside the slab's and every step of the bound is monotone in
+  // float), the others ("near") are the only ones the per-group bucketing looks at.
+  using NearT = typename std::conditional<(MAXPTS <= 256), uint8_t, uint16_t>::type;
+  NearT* near = S.near[warp];
+  const int n_slabs = (count + 255) >> 8;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  for (int slab = warp; slab < n_slabs; slab += kSWarps) {
+    const int s_begin = slab << 8;
+    const int s_end = count < s_begin + 256 ? count : s_begin + 256;
+    float sl0 = FLT_MAX, sl1 = FLT_MAX, sl2 = FLT_MAX, sh0 = -FLT_MAX, sh1 = -FLT_MAX, sh2 = -FLT_MAX;
+    for (int rk = s_begin + lane; rk < s_end; rk += 32) {
+      const int vv = S.perm[rk];
+      sl0 = fminf(sl0, S.vx[vv]);
+      sh0 = fmaxf(sh0, S.vx[vv]);
+      sl1 = fminf(sl1, S.vy[vv]);
+      sh1 = fmaxf(sh1, S.vy[vv]);
+      sl2 = fminf(sl2, S.vz[vv]);
+      sh2 = fmaxf(sh2, S.vz[vv]);
+    }
+    sl0 = warpMinF(sl0);
+    sl1 = warpMinF(sl1);
+    sl2 = warpMinF(sl2);
+    sh0 = warpMaxF(sh0);
+    sh1 = warpMaxF(sh1);
+    sh2 = warpMaxF(sh2);
+    int n_near = 0, n_far = 0;
+    __syncwarp();  // the previous slab's walk is done with the list
+    for (int i0 = 0; i0 < n_alive; i0 += 32) {
+      const int i = i0 + lane;
+      const bool valid = i < n_alive;
+      bool is_near = false;
+      if (valid) {
+        const float4 c = S.pts[i];
+        const float ax = fmaxf(fmaxf(sl0 - c.x, c.x - sh0), 0.f);
+        const float ay = fmaxf(fmaxf(sl1 - c.y, c.y - sh1), 0.f);
+        const float az = fmaxf(fmaxf(sl2 - c.z, c.z - sh2), 0.f);
+        const float m = (ax * ax + ay * ay + az * az) * 0.9999f;
+        is_near = !(m * inv_bw >= static_cast<float>(kSBuckets - 1));  // NaN: near
+      }
+      const unsigned m_near = __ballot_sync(full, is_near);
+      const unsigned m_far = __ballot_sync(full, valid && !is_near);
+      if (is_near) {
+        near[n_near + __popc(m_near & lt_mask)] = static_cast<NearT>(i);
+      } else if (valid) {
+        list[n_alive - 1 - (n_far + __popc(m_far & lt_mask))] =
+            static_cast<uint16_t>(((kSBuckets - 1) << kSlotBits) | i);
+      }
+      n_near += __popc(m_near);
+      n_far += __popc(m_far);
+    }
+    // pad to a multiple of 4 with the point at infinity (last bucket): the walk needs no guards
+    if (lane < ((4 - (n_alive & 3)) & 3)) {
+      list[n_alive + lane] = static_cast<uint16_t>(((kSBuckets - 1) << kSlotBits) | n_alive);
+    }
+    __syncwarp();
+
+  for (int group = s_begin >> 5; group * 32 < s_end; ++group) {
     const int slot = group * 32 + lane;
     const bool active = slot < count;
     const int v = S.perm[active ? slot : group * 32];  // idle lanes shadow the group's first vertex
@@ -413,12 +474,12 @@ deformKnnBlendSortedKernel(const DeformArgs a, const GridArgs ga,
     // pass 1: bucket = floor(lower bound of d^2(point, box) / bw); rank inside the bucket
     bcnt[lane] = 0;
     __syncwarp();
-    for (int i0 = 0; i0 < n_alive; i0 += 32) {
+    for (int i0 = 0; i0 < n_near; i0 += 32) {
       const int i = i0 + lane;
-      const bool valid = i < n_alive;
+      const bool valid = i < n_near;
       int b = kSBuckets + lane;  // idle lanes: a key nobody shares
       if (valid) {
-        const float4 c = S.pts[i];
+        const float4 c = S.pts[near[i]];
         const float ax = fmaxf(fmaxf(lox - c.x, c.x - hix), 0.f);
         const float ay = fmaxf(fmaxf(loy - c.y, c.y - hiy), 0.f);
         const float az = fmaxf(fmaxf(loz - c.z, c.z - hiz), 0.f);
@@ -438,7 +499,7 @@ deformKnnBlendSortedKernel(const DeformArgs a, const GridArgs ga,
       }
       base = __shfl_sync(full, base, leader);
       if (valid) {
-        const uint32_t rank = base + __popc(peers & ((1u << lane) - 1u));
+        const uint32_t rank = base + __popc(peers & lt_mask);
         tmp[i] = static_cast<uint16_t>((b << kSlotBits) | rank);
       }
       __syncwarp();
@@ -456,14 +517,10 @@ deformKnnBlendSortedKernel(const DeformArgs a, const GridArgs ga,
       bcnt[lane] = incl - c;
     }
     __syncwarp();
-    for (int i = lane; i < n_alive; i += 32) {
+    for (int i = lane; i < n_near; i += 32) {
       const uint32_t e = tmp[i];
       const uint32_t pos = bcnt[e >> kSlotBits] + (e & (kSMaxPts - 1));
-      list[pos] = static_cast<uint16_t>((e & ~static_cast<uint32_t>(kSMaxPts - 1)) | i);
-    }
-    // pad to a multiple of 4 with the point at infinity (last bucket): the walk needs no guards
-    if (lane < ((4 - (n_alive & 3)) & 3)) {
-      list[n_alive + lane] = static_cast<uint16_t>(((kSBuckets - 1) << kSlotBits) | n_alive);
+      list[pos] = static_cast<uint16_t>((e & ~static_cast<uint32_t>(kSMaxPts - 1)) | near[i]);
     }
     __syncwarp();
 
@@ -585,6 +642,7 @@ deformKnnBlendSortedKernel(const DeformArgs a, const GridArgs ga,
       writeResultReg<KCAP>(a, p, ii, PREC, qx, qy, qz, nbr_d2, nbr_idx, n);
     }
     a.status[p] = kStatusDone;
+  }
   }
 }
 
