@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libpgmo_b200.so")
+# PGMO_B200_LIB: developer override to compare builds (e.g. one with -DPGMO_DEBUG_COUNTERS)
+LIB_PATH = os.environ.get("PGMO_B200_LIB") or os.path.join(_HERE, "lib", "libpgmo_b200.so")
 
 PGMO_OK = 0
 PGMO_NOOP = 1

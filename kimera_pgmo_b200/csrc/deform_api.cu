@@ -61,7 +61,7 @@ struct pgmo_deform {
   static constexpr int kPipe = 8;
   cudaEvent_t ev_in[kPipe] = {}, ev_done[kPipe] = {};
   cudaEvent_t ev_stamps = nullptr;
-  float r_scale = 1.0f, r_grow_mul = 1.5f, r_grow_add = 1.0f;
+  float r_scale = 1.0f, r_grow_mul = 1.5f, r_grow_add = 1.0f, far_mul = 3.0f;
   uint32_t n_items = 0;
   uint64_t items_first = ~0ull, items_n = 0, items_sched_builds = ~0ull;
 
@@ -256,6 +256,7 @@ int pgmo_deform_create(int device, pgmo_deform_t** out) {
   if (const char* e = std::getenv("PGMO_R_SCALE")) h->r_scale = static_cast<float>(atof(e));
   if (const char* e = std::getenv("PGMO_R_GROW_MUL")) h->r_grow_mul = static_cast<float>(atof(e));
   if (const char* e = std::getenv("PGMO_R_GROW_ADD")) h->r_grow_add = static_cast<float>(atof(e));
+  if (const char* e = std::getenv("PGMO_FAR_MUL")) h->far_mul = static_cast<float>(atof(e));
   cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&h->ev_stamps, cudaEventDisableTiming);
@@ -623,6 +624,7 @@ static int runDeviceRange(pgmo_deform_t* h, uint64_t first_position, uint64_t n_
     ga.r_scale = h->r_scale;
     ga.r_grow_mul = h->r_grow_mul;
     ga.r_grow_add = h->r_grow_add;
+    ga.far_mul = h->far_mul;
     if (h->profiling) PGMO_CUDA(cudaEventRecord(h->ev[0], st));
     // the requested range must start and end on work-item boundaries
     uint32_t i0 = 0, i1 = h->n_items;

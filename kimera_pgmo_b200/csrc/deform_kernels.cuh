@@ -64,7 +64,10 @@ struct RunGridDev {
   float r0;               // first search radius: ~1.25 x expected (K+1)-th neighbour distance
 };
 // up to kDeformChunk consecutive local positions of one run (one CTA of the grid kernels)
-constexpr uint32_t kDeformChunk = 2048;
+#ifndef PGMO_CHUNK
+#define PGMO_CHUNK 2048
+#endif
+constexpr uint32_t kDeformChunk = PGMO_CHUNK;
 // runs with at most this many alive control points go through the bucket-ordered kernel
 // (deform_sorted.cu); larger alive sets stay on the grid-walk kernel (deform_grid.cu)
 constexpr int kSortedMaxPoints = 512;
@@ -79,6 +82,9 @@ struct GridArgs {
   const uint32_t* cells;    // n_runs x (kGridMaxCells + 1) cell starts
   // search-box schedule, in units of the run's r0 / cell: first radius, then growth per round
   float r_scale, r_grow_mul, r_grow_add;
+  // bucket-ordered kernel: points farther than sqrt(far_mul) first radii from a slab of vertices
+  // are looked at only by the groups whose search radius gets that far
+  float far_mul;
 };
 
 struct CandEntry {

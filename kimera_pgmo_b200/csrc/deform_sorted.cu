@@ -47,17 +47,21 @@ using namespace dev;
 constexpr int kSThreads = 256;
 constexpr int kSWarps = kSThreads / 32;
 constexpr int kSChunk = kDeformChunk;  // positions per work item
-constexpr int kSBuckets = 32;
 constexpr int kSMaxCells = 1024;       // sort bins of a pass
-constexpr int kSVBins = 128;           // bins along the second axis inside a slab (8 slabs)
-static_assert((kSChunk / 256) * kSVBins <= kSMaxCells, "slab x bin keys");
-constexpr int kStagedMaxPts = 256;     // alive-set size up to which the pose rows are staged
-
-template <int MAXPTS>
-struct SlotBits {
-  static constexpr int value = MAXPTS == 512 ? 9 : 8;
-};
-static_assert(kSortedMaxPoints == 512, "slot bits");
+#ifndef PGMO_SLAB_SHIFT
+#define PGMO_SLAB_SHIFT 8
+#endif
+constexpr int kSlabShift = PGMO_SLAB_SHIFT;  // vertices per slab (first split axis) = 1 << kSlabShift
+constexpr int kSlab = 1 << kSlabShift;
+constexpr int kSVBins = kSMaxCells / (kSChunk / kSlab);  // bins along the second axis inside a slab
+static_assert((kSChunk / kSlab) * kSVBins <= kSMaxCells, "slab x bin keys");
+#ifndef PGMO_STAGED_MAX
+#define PGMO_STAGED_MAX 256
+#endif
+#ifndef PGMO_K3_CTAS
+#define PGMO_K3_CTAS 3
+#endif
+constexpr int kStagedMaxPts = PGMO_STAGED_MAX;  // alive-set size up to which the pose rows are staged
 
 // pose rows of the alive points, SoA: component c of slot s at row[c][s]
 template <typename T, int MAXPTS>
@@ -68,8 +72,8 @@ struct NoPoseRows {};
 
 template <int MAXPTS, typename POSE>
 struct SortedSmem {
-  float4 pts[MAXPTS];                       // alive control points: x, y, z, index (int bits);
-                                            // pts[n_alive] = a point at infinity when n_alive % 4 != 0
+  float4 pts[MAXPTS + 4];                   // alive control points: x, y, z, index (int bits);
+                                            // pts[n_alive] = a point at infinity (list padding)
   float vx[kSChunk], vy[kSChunk], vz[kSChunk];
   uint16_t perm[kSChunk];                   // sorted position -> vertex of the item
   union alignas(16) {
@@ -78,39 +82,59 @@ struct SortedSmem {
       uint16_t perm1[kSChunk];              // order along the first split axis
     } sort;
     struct {
-      uint16_t tmp[kSWarps][MAXPTS];        // per point: bucket << slot bits | rank in the bucket
-      uint16_t list[kSWarps][MAXPTS + 8];   // bucket-ordered: bucket << slot bits | point slot
+      uint16_t list[kSWarps][MAXPTS + 8];   // per warp: candidate slots in the order they are walked
     } w;
   } u;
-  uint32_t bcnt[kSWarps][kSBuckets];
-  // per warp: the alive points that can matter for the slab being processed (the rest sits in
-  // the catch-all tail of the list)
+  // per warp and slab: the alive slots, split into those that can matter for the slab ("near",
+  // from the front) and the rest ("far", from the back)
   typename std::conditional<(MAXPTS <= 256), uint8_t, uint16_t>::type near[kSWarps][MAXPTS];
   float red[6][kSWarps];
   uint32_t warp_tot[kSWarps];
-  float grid[8];                            // origin xyz, inv cell, nx, ny, nz (as float bits)
+  float grid[8];                            // split axes: origin and 1 / bin width, axis ids
   alignas(16) POSE pose;
 };
 
+// Inserts two keys into the ascending list at once.  The i-th smallest of the union of two
+// ascending sequences b and (lo, hi) is min(b[i], max(b[i-1], lo), max(b[i-2], hi)): per slot two
+// VIMNMX and one three-input VIMNMX3 (sm_100a), no dependence between slots — 10 instructions
+// per candidate instead of 13, and a dependency depth of 3 instead of 13.
 template <int KCAP>
-__device__ __forceinline__ void chainInsert(uint32_t (&best)[KCAP], uint32_t x) {
+__device__ __forceinline__ void pairInsert(uint32_t (&best)[KCAP], uint32_t x, uint32_t y) {
+  const uint32_t lo = min(x, y), hi = max(x, y);
 #pragma unroll
-  for (int i = 0; i < KCAP; ++i) {
-    const uint32_t lo = min(best[i], x);
-    x = max(best[i], x);
-    best[i] = lo;
+  for (int i = KCAP - 1; i >= 2; --i) {
+    best[i] = __vimin3_u32(best[i], max(best[i - 1], lo), max(best[i - 2], hi));
   }
+  if (KCAP > 1) best[1] = __vimin3_u32(best[1], max(best[0], lo), hi);
+  best[0] = min(best[0], lo);
 }
 
+// asynchronous global -> shared copies (LDGSTS): the staging of the alive points and their pose
+// rows overlaps the vertex loads and the vertex sort; waited for right before the first group
+template <int BYTES>
+__device__ __forceinline__ void cpAsync(void* smem_dst, const void* gsrc) {
+  const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  if constexpr (BYTES == 16) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc));
+  } else {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(gsrc), "n"(BYTES));
+  }
+}
+__device__ __forceinline__ void cpAsyncWaitAll() {
+  asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
+// warp-wide float min / max in one instruction (CREDUX.MIN/MAX.F32, sm_100a); NaN inputs are
+// ignored like fminf / fmaxf do
 __device__ __forceinline__ float warpMinF(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
-  return v;
+  float r;
+  asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+  return r;
 }
 __device__ __forceinline__ float warpMaxF(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
-  return v;
+  float r;
+  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+  return r;
 }
 
 // interpPoint's blend with the pose rows read from shared memory (same arithmetic, operation
@@ -208,12 +232,11 @@ struct SmemOf {
 };
 
 template <int KCAP, int PREC, int MAXPTS, bool STAGE>
-__global__ void __launch_bounds__(kSThreads, STAGE ? 3 : 4)
+__global__ void __launch_bounds__(kSThreads, STAGE ? PGMO_K3_CTAS : 4)
 deformKnnBlendSortedKernel(const DeformArgs a, const GridArgs ga,
                            const WorkItem* __restrict__ items) {
   using Smem = typename SmemOf<PREC, MAXPTS, STAGE>::type;
   constexpr int kSMaxPts = MAXPTS;
-  constexpr int kSlotBits = SlotBits<MAXPTS>::value;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& S = *reinterpret_cast<Smem*>(smem_raw);
 
@@ -237,22 +260,28 @@ deformKnnBlendSortedKernel(const DeformArgs a, const GridArgs ga,
     return;
   }
 
+  // Items of at most one group (the head vertex of a stamp stretch is a run of its own) skip
+  // the vertex sort and stage only the pose rows of their winners.
+  const bool tiny = count <= 32;
+
   // ---- stage the run's alive points; load the item's vertices and their bounding box
   {
     const float4* src = ga.points + g.point_offset;
-    for (int i = t; i < n_alive; i += kSThreads) S.pts[i] = __ldg(src + i);
+    for (int i = t; i < n_alive; i += kSThreads) cpAsync<16>(&S.pts[i], src + i);
     // list padding (see the walk): d^2 to this point is +inf for every finite query
-    if (t == 0 && (n_alive & 3)) S.pts[n_alive] = make_float4(3e30f, 3e30f, 3e30f, __int_as_float(-1));
+    if (t == 0) S.pts[n_alive] = make_float4(3e30f, 3e30f, 3e30f, __int_as_float(-1));
     if constexpr (STAGE) {
       // pose rows of the alive points: component-major so that lanes reading one component of
       // different slots never collide on a bank
-      for (int e = t; e < n_alive * 15; e += kSThreads) {
-        const int s_ = e / 15, c = e - s_ * 15;
-        const int j = __float_as_int(__ldg(src + s_).w);
-        if constexpr (PREC == 0) {
-          S.pose.row[c][s_] = c < 12 ? a.poses[12ull * j + c] : a.ctrl_pos[3ull * j + (c - 12)];
-        } else {
-          S.pose.row[c][s_] = a.ctrl_pose_f32[16ull * j + c];  // R(9) t(3) g(3)
+      if (!tiny) {
+        for (int e = t; e < n_alive * 15; e += kSThreads) {
+          const int s_ = e / 15, c = e - s_ * 15;
+          const int j = __float_as_int(__ldg(src + s_).w);
+          if constexpr (PREC == 0) {
+            cpAsync<8>(&S.pose.row[c][s_], c < 12 ? a.poses + 12ull * j + c : a.ctrl_pos + 3ull * j + (c - 12));
+          } else {
+            cpAsync<4>(&S.pose.row[c][s_], a.ctrl_pose_f32 + 16ull * j + c);  // R(9) t(3) g(3)
+          }
         }
       }
     }
@@ -272,6 +301,11 @@ deformKnnBlendSortedKernel(const DeformArgs a, const GridArgs ga,
     mn2 = fminf(mn2, z);
     mx2 = fmaxf(mx2, z);
   }
+  if (tiny) {
+    if (t < 32) S.perm[t] = static_cast<uint16_t>(t);
+    cpAsyncWaitAll();
+    __syncthreads();
+  } else {
   mn0 = warpMinF(mn0);
   mn1 = warpMinF(mn1);
   mn2 = warpMinF(mn2);
@@ -375,46 +409,46 @@ deformKnnBlendSortedKernel(const DeformArgs a, const GridArgs ga,
   for (int i = t; i <= kSMaxCells; i += kSThreads) S.u.sort.hist[i] = 0;
   __syncthreads();
   for (int rk = t; rk < count; rk += kSThreads) {
-    const int key = (rk >> 8) * kSVBins + clampBin(cv[perm1[rk]], v_lo, v_inv, kSVBins);
+    const int key = (rk >> kSlabShift) * kSVBins + clampBin(cv[perm1[rk]], v_lo, v_inv, kSVBins);
     atomicAdd(&S.u.sort.hist[key + 1], 1u);
   }
   __syncthreads();
   scanHist(kSMaxCells);
   for (int rk = t; rk < count; rk += kSThreads) {
     const int i = perm1[rk];
-    const int key = (rk >> 8) * kSVBins + clampBin(cv[i], v_lo, v_inv, kSVBins);
+    const int key = (rk >> kSlabShift) * kSVBins + clampBin(cv[i], v_lo, v_inv, kSVBins);
     const uint32_t at = atomicAdd(&S.u.sort.hist[key], 1u);
     S.perm[at] = static_cast<uint16_t>(i);
   }
-  __syncthreads();  // hist is dead from here on: tmp / list alias it
+  cpAsyncWaitAll();
+  __syncthreads();  // hist is dead from here on: the candidate lists alias it
+  }
 
-  // ---- per group of 32 sorted vertices: bucket the alive points around the group's box, walk
+  // ---- per group of 32 sorted vertices: select the alive points around the group's box, walk
   const unsigned full = 0xFFFFFFFFu;
-  uint16_t* tmp = S.u.w.tmp[warp];
   uint16_t* list = S.u.w.list[warp];
-  uint32_t* bcnt = S.bcnt[warp];
   const int n_need = n_alive < K + 1 ? n_alive : K + 1;
   const int n = n_alive < K ? n_alive : K;
-  // ordinal bits: enough for every list position of this run
-  const int ord_bits = n_alive <= 128 ? 7 : (n_alive <= 256 ? 8 : 9);
+  // ordinal bits: enough for every list position of this run (two padding entries included)
+  const int ord_bits = n_alive + 2 <= 128 ? 7 : (n_alive + 2 <= 256 ? 8 : (n_alive + 2 <= 512 ? 9 : 10));
   const uint32_t ord_mask = (1u << ord_bits) - 1u;
-  const float bw = fmaxf(g.r0 * g.r0 * 0.125f * ga.r_scale, 1e-20f);  // bucket width in d^2
-  const float inv_bw = 1.f / bw;
-  const float bw_lb = bw * 0.9999f;
+  // first selection radius^2 (box distance) and the radius^2 beyond which a point is "far"
+  const float t0 = fmaxf(g.r0 * g.r0 * 1.3f * ga.r_scale, 1e-20f);
+  const float t_far = fmaxf(ga.far_mul, 1.f) * t0;
   const bool full_k = n_need == KCAP;
 
   // A warp takes whole slabs (256 sorted vertices = 8 groups).  Per slab the alive points are
-  // split once: points whose lower-bound distance to the SLAB's box already lands in the last
-  // bucket go straight to the tail of the list (they are in the last bucket for every group of
-  // the slab: a group's box lies inside the slab's and every step of the bound is monotone in
-  // float), the others ("near") are the only ones the per-group bucketing looks at.
+  // split once: points whose lower-bound distance to the SLAB's box is beyond t_far are "far"
+  // for every group of the slab (a group's box lies inside the slab's and every step of the
+  // bound is monotone in float); the others ("near") are the only ones a group looks at unless
+  // its search radius reaches t_far.
   using NearT = typename std::conditional<(MAXPTS <= 256), uint8_t, uint16_t>::type;
   NearT* near = S.near[warp];
-  const int n_slabs = (count + 255) >> 8;
+  const int n_slabs = (count + kSlab - 1) >> kSlabShift;
   const unsigned lt_mask = (1u << lane) - 1u;
   for (int slab = warp; slab < n_slabs; slab += kSWarps) {
-    const int s_begin = slab << 8;
-    const int s_end = count < s_begin + 256 ? count : s_begin + 256;
+    const int s_begin = slab << kSlabShift;
+    const int s_end = count < s_begin + kSlab ? count : s_begin + kSlab;
     float sl0 = FLT_MAX, sl1 = FLT_MAX, sl2 = FLT_MAX, sh0 = -FLT_MAX, sh1 = -FLT_MAX, sh2 = -FLT_MAX;
     for (int rk = s_begin + lane; rk < s_end; rk += 32) {
       const int vv = S.perm[rk];
@@ -432,7 +466,7 @@ deformKnnBlendSortedKernel(const DeformArgs a, const GridArgs ga,
     sh1 = warpMaxF(sh1);
     sh2 = warpMaxF(sh2);
     int n_near = 0, n_far = 0;
-    __syncwarp();  // the previous slab's walk is done with the list
+    __syncwarp();  // the previous slab's groups are done with near[]
     for (int i0 = 0; i0 < n_alive; i0 += 32) {
       const int i = i0 + lane;
       const bool valid = i < n_alive;
@@ -443,22 +477,17 @@ deformKnnBlendSortedKernel(const DeformArgs a, const GridArgs ga,
         const float ay = fmaxf(fmaxf(sl1 - c.y, c.y - sh1), 0.f);
         const float az = fmaxf(fmaxf(sl2 - c.z, c.z - sh2), 0.f);
         const float m = (ax * ax + ay * ay + az * az) * 0.9999f;
-        is_near = !(m * inv_bw >= static_cast<float>(kSBuckets - 1));  // NaN: near
+        is_near = !(m >= t_far);  // NaN: near
       }
       const unsigned m_near = __ballot_sync(full, is_near);
       const unsigned m_far = __ballot_sync(full, valid && !is_near);
       if (is_near) {
         near[n_near + __popc(m_near & lt_mask)] = static_cast<NearT>(i);
       } else if (valid) {
-        list[n_alive - 1 - (n_far + __popc(m_far & lt_mask))] =
-            static_cast<uint16_t>(((kSBuckets - 1) << kSlotBits) | i);
+        near[n_alive - 1 - (n_far + __popc(m_far & lt_mask))] = static_cast<NearT>(i);
       }
       n_near += __popc(m_near);
       n_far += __popc(m_far);
-    }
-    // pad to a multiple of 4 with the point at infinity (last bucket): the walk needs no guards
-    if (lane < ((4 - (n_alive & 3)) & 3)) {
-      list[n_alive + lane] = static_cast<uint16_t>(((kSBuckets - 1) << kSlotBits) | n_alive);
     }
     __syncwarp();
 
@@ -471,69 +500,83 @@ deformKnnBlendSortedKernel(const DeformArgs a, const GridArgs ga,
     const float loy = warpMinF(qy), hiy = warpMaxF(qy);
     const float loz = warpMinF(qz), hiz = warpMaxF(qz);
 
-    // pass 1: bucket = floor(lower bound of d^2(point, box) / bw); rank inside the bucket
-    bcnt[lane] = 0;
-    __syncwarp();
-    for (int i0 = 0; i0 < n_near; i0 += 32) {
-      const int i = i0 + lane;
-      const bool valid = i < n_near;
-      int b = kSBuckets + lane;  // idle lanes: a key nobody shares
-      if (valid) {
-        const float4 c = S.pts[near[i]];
-        const float ax = fmaxf(fmaxf(lox - c.x, c.x - hix), 0.f);
-        const float ay = fmaxf(fmaxf(loy - c.y, c.y - hiy), 0.f);
-        const float az = fmaxf(fmaxf(loz - c.z, c.z - hiz), 0.f);
-        // 0.9999: the bound must hold against the separately rounded exact d^2 of every lane
-        const float m = (ax * ax + ay * ay + az * az) * 0.9999f;
-        b = static_cast<int>(fminf(m * inv_bw, static_cast<float>(kSBuckets - 1)));
-        b = b < 0 ? 0 : b;  // NaN coordinates
-      }
-      // rank inside the bucket: lanes of this round that share b are ranked by lane; the lowest
-      // of them advances the bucket's counter for everybody (no shared-memory atomics)
-      const unsigned peers = __match_any_sync(full, b);
-      const int leader = __ffs(peers) - 1;
-      uint32_t base = 0;
-      if (valid && lane == leader) {
-        base = bcnt[b];
-        bcnt[b] = base + __popc(peers);
-      }
-      base = __shfl_sync(full, base, leader);
-      if (valid) {
-        const uint32_t rank = base + __popc(peers & lt_mask);
-        tmp[i] = static_cast<uint16_t>((b << kSlotBits) | rank);
-      }
-      __syncwarp();
-    }
-    __syncwarp();
-    {
-      const uint32_t c = bcnt[lane];
-      uint32_t incl = c;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t up = __shfl_up_sync(full, incl, o);
-        if (lane >= o) incl += up;
-      }
-      __syncwarp();
-      bcnt[lane] = incl - c;
-    }
-    __syncwarp();
-    for (int i = lane; i < n_near; i += 32) {
-      const uint32_t e = tmp[i];
-      const uint32_t pos = bcnt[e >> kSlotBits] + (e & (kSMaxPts - 1));
-      list[pos] = static_cast<uint16_t>((e & ~static_cast<uint32_t>(kSMaxPts - 1)) | near[i]);
-    }
-    __syncwarp();
-
-    // pass 2: walk the list, 4 entries per step
+    // lower bound (with head room for the separately rounded exact d^2 of every lane) of the
+    // squared distance between near point i and the group's box
+    auto boxBound = [&](int i) {
+      const float4 c = S.pts[near[i]];
+      const float ax = fmaxf(fmaxf(lox - c.x, c.x - hix), 0.f);
+      const float ay = fmaxf(fmaxf(loy - c.y, c.y - hiy), 0.f);
+      const float az = fmaxf(fmaxf(loz - c.z, c.z - hiz), 0.f);
+      return (ax * ax + ay * ay + az * az) * 0.9999f;
+    };
     uint32_t best[KCAP];
 #pragma unroll
     for (int i = 0; i < KCAP; ++i) best[i] = 0xFFFFFFFFu;
-    for (int c = 0; c < n_alive; c += 4) {
-      const uint2 ee = *reinterpret_cast<const uint2*>(list + c);
-      uint32_t e[4] = {ee.x & 0xFFFFu, ee.x >> 16, ee.y & 0xFFFFu, ee.y >> 16};
-      if (c >= 8) {
-        // every unscanned point has d^2 >= lb for every lane; stop when nobody can use that
-        const float lb = static_cast<float>(e[0] >> kSlotBits) * bw_lb;
+    // Two selection phases, each followed by a walk of the selected slots (exact d^2 of every
+    // lane's vertex to the candidate — one broadcast LDS.128 each —, keys inserted two at a
+    // time).  Phase 0: the near points within t0 of the box, in slot order.  Phase 1: the other
+    // near points that are not farther from the box than the largest (K+1)-th distance found in
+    // phase 0 — nothing beyond that can enter (or tie with) anybody's list.
+    int n_list = 0;
+    float k_max = 0.f;
+    __syncwarp();  // the previous group's winners have been read back from the list
+#pragma unroll 1
+    for (int phase = 0; phase < 2; ++phase) {
+      const int c0 = n_list;
+      for (int i0 = 0; i0 < n_near; i0 += 32) {
+        const int i = i0 + lane;
+        bool sel = false;
+        if (i < n_near) {
+          const float m = boxBound(i);
+          sel = phase == 0 ? !(m >= t0) : (m >= t0 && m <= k_max);
+        }
+        const unsigned msel = __ballot_sync(full, sel);
+        if (sel) list[n_list + __popc(msel & lt_mask)] = near[i];
+        n_list += __popc(msel);
+      }
+      // too few to fill the lists (phase 0), or the search radius reaches the slab's far points
+      // (phase 1): take everything that is left (near[] holds all alive slots)
+      const bool everything = phase == 0 ? n_list < n_need : k_max >= t_far;
+      if (everything) {
+        const int from = phase == 0 ? 0 : n_near;
+        const int to = n_alive;
+        n_list = phase == 0 ? 0 : n_list;
+        for (int i = from + lane; i < to; i += 32) list[n_list + (i - from)] = near[i];
+        n_list += to - from;
+      }
+      if (n_list & 1) {
+        if (lane == 0) list[n_list] = static_cast<uint16_t>(n_alive);
+        ++n_list;
+      }
+      __syncwarp();
+      int c = c0;
+      for (; c + 4 <= n_list; c += 4) {
+        const uint32_t e01 = *reinterpret_cast<const uint32_t*>(list + c);
+        const uint32_t e23 = *reinterpret_cast<const uint32_t*>(list + c + 2);
+        const uint32_t e[4] = {e01 & 0xFFFFu, e01 >> 16, e23 & 0xFFFFu, e23 >> 16};
+        uint32_t key[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float4 p = S.pts[e[u]];  // same address in all lanes: broadcast
+          const float d2 = dist2Exact(p.x, p.y, p.z, qx, qy, qz);
+          key[u] = (__float_as_uint(d2) & ~ord_mask) | static_cast<uint32_t>(c + u);
+        }
+        pairInsert<KCAP>(best, key[0], key[1]);
+        pairInsert<KCAP>(best, key[2], key[3]);
+      }
+      if (c < n_list) {
+        const uint32_t e01 = *reinterpret_cast<const uint32_t*>(list + c);
+        const float4 p0 = S.pts[e01 & 0xFFFFu], p1 = S.pts[e01 >> 16];
+        const float d0 = dist2Exact(p0.x, p0.y, p0.z, qx, qy, qz);
+        const float d1 = dist2Exact(p1.x, p1.y, p1.z, qx, qy, qz);
+        pairInsert<KCAP>(best, (__float_as_uint(d0) & ~ord_mask) | static_cast<uint32_t>(c),
+                         (__float_as_uint(d1) & ~ord_mask) | static_cast<uint32_t>(c + 1));
+      }
+#ifdef PGMO_DEBUG_COUNTERS
+      if (lane == 0) atomicAdd(a.counters + 5, static_cast<unsigned long long>(n_list - c0));
+#endif
+      if (everything) break;
+      if (phase == 0) {
         uint32_t kth;  // best[n_need - 1]: the maximum of the first n_need (ascending) entries
         if (full_k) {
           kth = best[KCAP - 1];
@@ -542,18 +585,11 @@ deformKnnBlendSortedKernel(const DeformArgs a, const GridArgs ga,
 #pragma unroll
           for (int i = 0; i < KCAP; ++i) kth = i < n_need ? max(kth, best[i]) : kth;
         }
-        // (key | ord_mask) >= the entry's exact d^2 bits; unfilled slots are NaN: never "<"
-        const bool ok = __uint_as_float(kth | ord_mask) < lb;
-        if (__all_sync(full, ok)) break;
-      }
-#ifdef PGMO_DEBUG_COUNTERS
-      if (lane == 0) atomicAdd(a.counters + 5, 4ull);
-#endif
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float4 p = S.pts[e[u] & (kSMaxPts - 1)];  // same address in all lanes: broadcast
-        const float d2 = dist2Exact(p.x, p.y, p.z, qx, qy, qz);
-        chainInsert<KCAP>(best, (__float_as_uint(d2) & ~ord_mask) | static_cast<uint32_t>(c + u));
+        // (key | ord_mask) >= the entry's exact d^2 bits
+        const float kth_f = __uint_as_float(kth | ord_mask);
+        k_max = warpMaxF(kth_f);
+        if (__any_sync(full, !(kth_f == kth_f))) k_max = __int_as_float(0x7F800000);  // NaN / inf d^2
+        if (k_max < t0) break;  // the usual case: phase 0 already covered every lane's radius
       }
     }
 #ifdef PGMO_DEBUG_COUNTERS
@@ -570,25 +606,25 @@ deformKnnBlendSortedKernel(const DeformArgs a, const GridArgs ga,
     const uint64_t ii = a.subset ? a.subset[p] : p;
     float nbr_d2[KCAP];
     int nbr_idx[KCAP];
-    bool near = false;       // two winners agree above the ordinal bits
+    bool near_tie = false;   // two winners agree above the ordinal bits
     bool near_last = false;  // ... and one of them is the last tracked slot
 #pragma unroll
     for (int i = 0; i < KCAP; ++i) {
       nbr_d2[i] = FLT_MAX;
       nbr_idx[i] = -1;
       if (i < n_need) {
-        const int slot_i = list[best[i] & ord_mask] & (kSMaxPts - 1);
+        const int slot_i = list[best[i] & ord_mask];
         const float4 c = S.pts[slot_i];
         nbr_d2[i] = dist2Exact(c.x, c.y, c.z, qx, qy, qz);
         nbr_idx[i] = STAGE ? slot_i : __float_as_int(c.w);  // staged: the slot, resolved at the end
       }
       if (i > 0 && i < n_need && (best[i] >> ord_bits) == (best[i - 1] >> ord_bits)) {
-        near = true;
+        near_tie = true;
         near_last = near_last || (i == n_need - 1);
       }
     }
     bool tie = false;
-    if (near) {
+    if (near_tie) {
       // Keys that agree above the ordinal bits were ordered by list position, not by d^2.
       // Every point sharing that prefix is tracked unless the group reaches the last slot
       // (untracked points have keys >= the last slot's), so below the last slot the exact
@@ -637,6 +673,25 @@ deformKnnBlendSortedKernel(const DeformArgs a, const GridArgs ga,
       continue;
     }
     if constexpr (STAGE) {
+      if (tiny) {
+        // the pose rows were not staged: fetch those of this vertex's own neighbours (lanes
+        // that share a neighbour write identical values)
+#pragma unroll
+        for (int j = 0; j < KCAP; ++j) {
+          if (j < n - 1) {
+            const int s_ = nbr_idx[j];
+            const int cj = __float_as_int(S.pts[s_].w);
+#pragma unroll 1
+            for (int c = 0; c < 15; ++c) {
+              if constexpr (PREC == 0) {
+                S.pose.row[c][s_] = c < 12 ? a.poses[12ull * cj + c] : a.ctrl_pos[3ull * cj + (c - 12)];
+              } else {
+                S.pose.row[c][s_] = a.ctrl_pose_f32[16ull * cj + c];
+              }
+            }
+          }
+        }
+      }
       writeResultStaged<KCAP, PREC>(a, S, p, ii, qx, qy, qz, nbr_d2, nbr_idx, n);
     } else {
       writeResultReg<KCAP>(a, p, ii, PREC, qx, qy, qz, nbr_d2, nbr_idx, n);
