@@ -165,6 +165,19 @@ int pgmo_deform_run_device(pgmo_deform_t* h, uint64_t first_position, uint64_t n
 int pgmo_deform_schedule_info(pgmo_deform_t* h, uint64_t* n_runs, uint64_t capacity,
                               uint64_t* runs5);
 
+/* DeformationGraph::deformMesh (deformation_graph.cpp:523-559) on a mesh that already lives in
+ * HBM as the compressors keep it: n_v vertices as 16-byte records {float x, y, z; uint32 rgba}
+ * (pgmo_vcc_device_view / pgmo_oct_device_view) plus their u64 stamps (NULL: unstamped
+ * overload).  Replaces the blob -> cloud -> blob conversions and the host copies of a-1.  Writes
+ * d_out_xyzw[i] = {deformed xyz, input rgba} for every processed vertex and a copy of the input
+ * record otherwise (in place allowed); d_processed (optional, n_v bytes) as in
+ * pgmo_deform_points.  Stream-ordered on `stream` (NULL: the handle's) apart from the stamp
+ * fingerprint read-back; the caller synchronises before reading.  16-byte aligned pointers. */
+int pgmo_deform_mesh_device(pgmo_deform_t* h, uint64_t n_v, const void* d_vertices_xyzw,
+                            const uint64_t* d_stamps_ns, uint32_t k, double tol_t, int precision,
+                            void* d_out_xyzw, uint8_t* d_processed, uint64_t* n_resolved,
+                            void* stream);
+
 /* DeformationGraph::predeformPoints (deformation_graph.h:779-806): for i >= start_idx with
  * graph_indices[i] >= 0 and a valid pose: out[i] = float(R * (double(v_i) - g) + t); every other
  * i >= start_idx is appended to to_deform (ascending).  Host buffers.
@@ -205,6 +218,13 @@ int pgmo_vcc_snapshot(pgmo_vcc_t* h, float* vertices_xyz, uint32_t* vertices_rgb
                       uint64_t* stamps_ns, uint32_t* polygons, uint64_t* active,
                       uint64_t* invalid);
 
+/* getVertices / getTimestamps without the copy (mesh_compression.h:37-60 copy into caller
+ * shared_ptrs): device pointers to all_vertices_ as 16-byte records {float x, y, z; uint32 rgba}
+ * and to all_vertex_stamps_ (u64 ns), valid until the next integrate / prune on this handle.
+ * Feeds pgmo_deform_mesh_device so that the compressed mesh never leaves HBM. */
+int pgmo_vcc_device_view(pgmo_vcc_t* h, const void** d_vertices_xyzw, const uint64_t** d_stamps_ns,
+                         uint64_t* n_vertices);
+
 /* Device-resident integrate for throughput measurement: inputs already in HBM, remap written to
  * HBM, stream-ordered, no host synchronisation.  Single-block or multi-block as above;
  * block_offsets / block_idx_xyz stay host arrays (they are tiny). */
@@ -236,6 +256,9 @@ int pgmo_oct_integrate(pgmo_oct_t* h, uint32_t n_blocks, const int32_t* block_id
                        const uint64_t* block_offsets, const float* xyz, const uint32_t* rgba,
                        double stamp_s, int64_t* remap_index, uint8_t* remap_kind);
 int pgmo_oct_prune(pgmo_oct_t* h, double earliest_s);
+/* as pgmo_vcc_device_view, for MeshCompression's all_vertices_ / all_vertex_stamps_ */
+int pgmo_oct_device_view(pgmo_oct_t* h, const void** d_vertices_xyzw, const uint64_t** d_stamps_ns,
+                         uint64_t* n_vertices);
 /* sizes8 = [num_vertices, num_polygons, num_active, 0, num_new_vertices, num_new_triangles,
  *           num_new_indices, num_active] */
 int pgmo_oct_sizes(pgmo_oct_t* h, uint64_t* sizes8);

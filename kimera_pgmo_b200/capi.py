@@ -60,6 +60,10 @@ SIGNATURES = {
     "pgmo_deform_run_device": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _vp, _vp, _vp, _vp, C.c_int,
                                          _vp, _vp, _vp, _vp, _vp, C.c_uint32, _vp, _vp, _vp, _vp]),
     "pgmo_deform_schedule_info": (C.c_int, [_vp, _u64p, C.c_uint64, _vp]),
+    "pgmo_deform_mesh_device": (C.c_int, [_vp, C.c_uint64, _vp, _vp, C.c_uint32, C.c_double,
+                                          C.c_int, _vp, _vp, _vp, _vp]),
+    "pgmo_vcc_device_view": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), _u64p]),
+    "pgmo_oct_device_view": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), _u64p]),
     "pgmo_deform_predeform": (C.c_int, [_vp, C.c_uint64, _vp, _vp, _vp, _vp, C.c_uint64, _vp, _vp,
                                         _vp, _vp, _u64p]),
     "pgmo_vcc_create": (C.c_int, [C.c_double, C.c_int, C.POINTER(_vp)]),
@@ -251,6 +255,17 @@ class DeformHandle:
             C.cast(C.byref(resolved), _vp) if want_resolved else None, _vp(stream)))
         return int(resolved.value)
 
+    def deform_mesh_device(self, n_v, d_vertices_xyzw, d_stamps, d_out_xyzw, k=4, tol_t=10.0,
+                           precision=FP64, d_processed=None, want_resolved=False, stream=0):
+        """deformMesh on a device-resident {x, y, z, rgba} cloud (raw device pointers / tensors'
+        data_ptr()); returns (rc, n_resolved)."""
+        resolved = C.c_uint64(0)
+        rc = _check(self._lib.pgmo_deform_mesh_device(
+            self._h, n_v, _ptr(d_vertices_xyzw), _ptr(d_stamps), k, tol_t, precision,
+            _ptr(d_out_xyzw), _ptr(d_processed),
+            C.cast(C.byref(resolved), _vp) if want_resolved else None, _vp(stream)))
+        return rc, int(resolved.value)
+
     def predeform(self, x, y, z, graph_indices, start_idx, out):
         x = np.ascontiguousarray(x, dtype=np.float32)
         y = np.ascontiguousarray(y, dtype=np.float32)
@@ -315,6 +330,12 @@ class VccHandle:
         bi = np.ascontiguousarray(block_idx, dtype=np.int32).reshape(-1, 3)
         _check(self._lib.pgmo_vcc_clear_blocks(self._h, bi.shape[0], _ptr(bi)))
 
+    def device_view(self):
+        """(device pointer to the {x, y, z, rgba} records, device pointer to the u64 stamps, n)"""
+        v, st, n = _vp(), _vp(), C.c_uint64(0)
+        _check(self._lib.pgmo_vcc_device_view(self._h, C.byref(v), C.byref(st), C.byref(n)))
+        return v.value, st.value, int(n.value)
+
     def sizes(self):
         s = np.zeros(4, dtype=np.uint64)
         _check(self._lib.pgmo_vcc_sizes(self._h, _ptr(s)))
@@ -362,6 +383,12 @@ class OctHandle:
 
     def prune(self, earliest_s):
         _check(self._lib.pgmo_oct_prune(self._h, float(earliest_s)))
+
+    def device_view(self):
+        """(device pointer to the {x, y, z, rgba} records, device pointer to the u64 stamps, n)"""
+        v, st, n = _vp(), _vp(), C.c_uint64(0)
+        _check(self._lib.pgmo_oct_device_view(self._h, C.byref(v), C.byref(st), C.byref(n)))
+        return v.value, st.value, int(n.value)
 
     def sizes(self):
         s = np.zeros(8, dtype=np.uint64)

@@ -907,6 +907,44 @@ int pgmo_deform_points(pgmo_deform_t* h, uint64_t n_v, const float* x, const flo
   return PGMO_OK;
 }
 
+int pgmo_deform_mesh_device(pgmo_deform_t* h, uint64_t n_v, const void* d_vertices_xyzw,
+                            const uint64_t* d_stamps_ns, uint32_t k, double tol_t, int precision,
+                            void* d_out_xyzw, uint8_t* d_processed, uint64_t* n_resolved,
+                            void* stream) {
+  PGMO_CHECK_ARG(h != nullptr);
+  PGMO_TRY(ensureDevice(h->device));
+  if (n_v == 0) return PGMO_NOOP;
+  PGMO_CHECK_ARG(d_vertices_xyzw != nullptr && d_out_xyzw != nullptr);
+  PGMO_CHECK_ARG((reinterpret_cast<uintptr_t>(d_vertices_xyzw) & 15u) == 0 &&
+                 (reinterpret_cast<uintptr_t>(d_out_xyzw) & 15u) == 0);
+  cudaStream_t st = pick(h, stream);
+  const float4* in = static_cast<const float4*>(d_vertices_xyzw);
+  float4* out = static_cast<float4*>(d_out_xyzw);
+  PGMO_TRY(h->d_x.reserve(n_v));
+  PGMO_TRY(h->d_y.reserve(n_v));
+  PGMO_TRY(h->d_z.reserve(n_v));
+  PGMO_TRY(h->d_ox.reserve(n_v));
+  PGMO_TRY(h->d_oy.reserve(n_v));
+  PGMO_TRY(h->d_oz.reserve(n_v));
+  PGMO_TRY(h->d_status.reserve(n_v));
+  PGMO_CUDA(launchAosToSoa(n_v, in, h->d_x.ptr, h->d_y.ptr, h->d_z.ptr, st));
+  int rc;
+  if (d_stamps_ns) {
+    std::vector<uint64_t> s_stamp, s_len;
+    PGMO_TRY(stampStretches(h, d_stamps_ns, nullptr, n_v, &s_stamp, &s_len, st));
+    rc = pgmo_deform_build_schedule(h, s_stamp.size(), s_stamp.data(), s_len.data(), n_v, k, tol_t);
+  } else {
+    rc = pgmo_deform_build_schedule(h, 0, nullptr, nullptr, n_v, k, tol_t);
+  }
+  if (rc != PGMO_OK) return rc;  // NOOP (reference early return): nothing written
+  uint8_t* status = d_processed ? d_processed : h->d_status.ptr;
+  PGMO_TRY(pgmo_deform_run_device(h, 0, n_v, h->d_x.ptr, h->d_y.ptr, h->d_z.ptr, nullptr, precision,
+                                  h->d_ox.ptr, h->d_oy.ptr, h->d_oz.ptr, nullptr, nullptr, 0, nullptr,
+                                  status, n_resolved, st));
+  PGMO_CUDA(launchSoaToAos(n_v, in, h->d_ox.ptr, h->d_oy.ptr, h->d_oz.ptr, status, out, st));
+  return PGMO_OK;
+}
+
 int pgmo_deform_predeform(pgmo_deform_t* h, uint64_t n_v, const float* x, const float* y,
                           const float* z, const int32_t* graph_indices, uint64_t start_idx,
                           float* out_x, float* out_y, float* out_z, uint64_t* to_deform,

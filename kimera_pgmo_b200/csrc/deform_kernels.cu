@@ -203,6 +203,35 @@ __global__ void applyScheduleKernel(uint64_t n_c, const int32_t* __restrict__ de
   ctrl_key[j] = make_int4(stable_key3[3 * j], stable_key3[3 * j + 1], stable_key3[3 * j + 2], 0);
 }
 
+// ------------------------------------------------------------------------------------------
+// Device-resident meshes: the compressors keep their vertices as float4 {x, y, z, rgba bits}
+// (the reference's PointXYZRGBA cloud, deformation_graph.cpp:541,557 converts blob <-> cloud on
+// the host); K3 streams SoA.  Both directions are plain coalesced copies (28 B / vertex each).
+__global__ void aosToSoaKernel(uint64_t n, const float4* __restrict__ in, float* __restrict__ x,
+                               float* __restrict__ y, float* __restrict__ z) {
+  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 v = in[i];
+  x[i] = v.x;
+  y[i] = v.y;
+  z[i] = v.z;
+}
+
+// out[i] = {deformed xyz, in[i].w} for processed vertices, in[i] otherwise (in == out allowed)
+__global__ void soaToAosKernel(uint64_t n, const float4* in, const float* __restrict__ x,
+                               const float* __restrict__ y, const float* __restrict__ z,
+                               const uint8_t* __restrict__ status, float4* out) {
+  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 v = in[i];
+  if (status[i] == kStatusDone) {
+    v.x = x[i];
+    v.y = y[i];
+    v.z = z[i];
+  }
+  out[i] = v;
+}
+
 }  // namespace
 
 cudaError_t launchStampStretches(const uint64_t* stamps, const uint64_t* subset, uint64_t n,
@@ -275,6 +304,22 @@ cudaError_t launchApplySchedule(uint64_t n_c, const int32_t* del_run, const int3
   const unsigned threads = 256;
   applyScheduleKernel<<<static_cast<unsigned>((n_c + threads - 1) / threads), threads, 0, stream>>>(
       n_c, del_run, stable_key3, ctrl_f4, ctrl_key);
+  return cudaGetLastError();
+}
+
+cudaError_t launchAosToSoa(uint64_t n, const float4* in, float* x, float* y, float* z,
+                           cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  aosToSoaKernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(n, in, x, y, z);
+  return cudaGetLastError();
+}
+
+cudaError_t launchSoaToAos(uint64_t n, const float4* in, const float* x, const float* y,
+                           const float* z, const uint8_t* status, float4* out,
+                           cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  soaToAosKernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(n, in, x, y, z,
+                                                                            status, out);
   return cudaGetLastError();
 }
 

@@ -135,6 +135,13 @@ cudaError_t launchDeformResolve(const DeformArgs& args, const ResolveArgs& rargs
 uint32_t resolverResidentWarps(int device);
 
 // K5: rigid predeform by graph index.
+// float4 {x, y, z, w} cloud <-> the SoA streams of K3 (device-resident meshes)
+cudaError_t launchAosToSoa(uint64_t n, const float4* in, float* x, float* y, float* z,
+                           cudaStream_t stream);
+cudaError_t launchSoaToAos(uint64_t n, const float4* in, const float* x, const float* y,
+                           const float* z, const uint8_t* status, float4* out,
+                           cudaStream_t stream);
+
 cudaError_t launchPredeform(uint64_t n_v, uint64_t start_idx, const float* x, const float* y,
                             const float* z, const int32_t* graph_indices, uint64_t n_c,
                             const float4* ctrl_f4_valid, const uint8_t* valid,

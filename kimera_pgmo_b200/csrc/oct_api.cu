@@ -857,6 +857,17 @@ int pgmo_oct_prune(pgmo_oct_t* h, double earliest_s) {
   return buildPersistent(h, 0, st);  // reInitializeStructure: re-anchored at the first survivor
 }
 
+int pgmo_oct_device_view(pgmo_oct_t* h, const void** d_vertices_xyzw, const uint64_t** d_stamps_ns,
+                         uint64_t* n_vertices) {
+  PGMO_CHECK_ARG(h != nullptr && n_vertices != nullptr);
+  PGMO_TRY(ensureDevice(h->device));
+  PGMO_CUDA(cudaStreamSynchronize(h->stream));  // everything queued so far is visible to any stream
+  if (d_vertices_xyzw) *d_vertices_xyzw = h->all_vertices.ptr;
+  if (d_stamps_ns) *d_stamps_ns = reinterpret_cast<const uint64_t*>(h->all_stamps.ptr);
+  *n_vertices = h->n_all;
+  return PGMO_OK;
+}
+
 int pgmo_oct_sizes(pgmo_oct_t* h, uint64_t* sizes8) {
   PGMO_CHECK_ARG(h != nullptr && sizes8 != nullptr);
   sizes8[0] = h->n_all;

@@ -452,6 +452,18 @@ int pgmo_vcc_clear_blocks(pgmo_vcc_t* h, uint32_t n_blocks, const int32_t* block
   return pruneBlocks(h, to_clear, h->stream);
 }
 
+int pgmo_vcc_device_view(pgmo_vcc_t* h, const void** d_vertices_xyzw, const uint64_t** d_stamps_ns,
+                         uint64_t* n_vertices) {
+  PGMO_CHECK_ARG(h != nullptr && n_vertices != nullptr);
+  PGMO_TRY(ensureDevice(h->device));
+  if (h->pending) PGMO_TRY(syncCounters(h, h->stream));
+  PGMO_CUDA(cudaStreamSynchronize(h->stream));  // everything queued so far is visible to any stream
+  if (d_vertices_xyzw) *d_vertices_xyzw = h->vertices.ptr;
+  if (d_stamps_ns) *d_stamps_ns = h->stamps.ptr;
+  *n_vertices = h->max_index;
+  return PGMO_OK;
+}
+
 int pgmo_vcc_sizes(pgmo_vcc_t* h, uint64_t* sizes4) {
   PGMO_CHECK_ARG(h != nullptr && sizes4 != nullptr);
   PGMO_TRY(ensureDevice(h->device));
