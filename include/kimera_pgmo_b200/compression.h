@@ -122,6 +122,17 @@ class MeshCompression {
   virtual size_t getNumVertices() const = 0;
   virtual const std::vector<size_t>& getActiveVerticesIndex() const = 0;
 
+  // Extension (no reference counterpart): getVertices / getTimestamps without the copy —
+  // all_vertices_ as 16-byte {x, y, z, rgba} records and all_vertex_stamps_ in HBM, valid until
+  // the next compressAndIntegrate / pruneStoredMesh.  DeformationGraphMeshPath::
+  // deformMeshResident consumes it so that the compressed mesh never crosses PCIe.
+  struct DeviceView {
+    const void* vertices_xyzw = nullptr;
+    const uint64_t* stamps_ns = nullptr;
+    size_t num_vertices = 0;
+  };
+  virtual DeviceView deviceView() const = 0;
+
  protected:
   double resolution_;
 };
@@ -218,6 +229,13 @@ class VoxelClearingCompression : public MeshCompression {
     detail::fillPolygons(flat, polygons.get());
   }
 
+  DeviceView deviceView() const override {
+    DeviceView v;
+    uint64_t n = 0;
+    detail::throwOnError(pgmo_vcc_device_view(handle_.get(), &v.vertices_xyzw, &v.stamps_ns, &n));
+    v.num_vertices = n;
+    return v;
+  }
   size_t getNumVertices() const override {
     uint64_t sizes[4];
     detail::throwOnError(pgmo_vcc_sizes(handle_.get(), sizes));
@@ -363,6 +381,13 @@ class OctreeCompression : public MeshCompression {
     timestamps->assign(sizes[2], 0.0);
     detail::throwOnError(pgmo_oct_snapshot(handle_.get(), nullptr, nullptr, nullptr, nullptr,
                                            nullptr, nullptr, timestamps->data()));
+  }
+  DeviceView deviceView() const override {
+    DeviceView v;
+    uint64_t n = 0;
+    detail::throwOnError(pgmo_oct_device_view(handle_.get(), &v.vertices_xyzw, &v.stamps_ns, &n));
+    v.num_vertices = n;
+    return v;
   }
   size_t getNumVertices() const override {
     uint64_t sizes[8];

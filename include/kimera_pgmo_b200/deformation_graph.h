@@ -58,6 +58,27 @@ class DeformationGraphMeshPath {
     return new_mesh;
   }
 
+  // Extension (no reference counterpart): deformMesh's full recompute (start index 0) on a
+  // cloud that is already in HBM — 16-byte {x, y, z, rgba} records + u64 stamps, e.g. a
+  // compressor's MeshCompression::deviceView() — written to d_out_xyzw (device, same layout,
+  // may alias the input).  Same arithmetic and results as deformMesh; nothing is cached
+  // (last_calculated_vertices_ is a host-side cache).  Returns false where the reference
+  // returns early (unknown prefix / fewer control points than k).
+  bool deformMeshResident(const void* d_vertices_xyzw, const uint64_t* d_stamps_ns,
+                          size_t num_vertices, char prefix, const gtsam::Values& optimized_values,
+                          void* d_out_xyzw, size_t k = 4, double tol_t = 10.0,
+                          void* cuda_stream = nullptr) {
+    if (vertex_positions_.find(prefix) == vertex_positions_.end()) return false;
+    deformation::Backend& b = backend(prefix);
+    b.setControls(prefix, vertex_positions_.at(prefix), &vertex_stamps_.at(prefix),
+                  optimized_values);
+    const int rc = pgmo_deform_mesh_device(b.get(), num_vertices, d_vertices_xyzw, d_stamps_ns,
+                                           static_cast<uint32_t>(k), tol_t, PGMO_PRECISION_FP64,
+                                           d_out_xyzw, nullptr, nullptr, cuda_stream);
+    detail::throwOnError(rc);
+    return rc == PGMO_OK;
+  }
+
   // deformation_graph.cpp:561-581
   void deformPoints(pcl::PointCloud<pcl::PointXYZRGBA>& vertices,
                     const pcl::PointCloud<pcl::PointXYZRGBA>& old_vertices,

@@ -58,8 +58,21 @@ for m, (blocks, offsets, xyz, rgba, t) in enumerate(synth.compression_stream(n_k
         dh.update_poses(poses)
         dh.deform_points(x, y, z, st, k=4, tol_t=10.0)
         t_again = 1e3 * (time.perf_counter() - t2)
+        # the same re-deformation on the compressor's device-resident cloud (stored order; no
+        # vertex upload, deformed cloud stays in HBM)
+        import torch
+        d_v, d_st, n_res = oc.device_view()
+        d_out = torch.empty((n_res, 4), dtype=torch.float32, device="cuda:0")
+        dh.deform_mesh_device(n_res, d_v, d_st, d_out, k=4, tol_t=10.0)
+        torch.cuda.synchronize()
+        t3 = time.perf_counter()
+        dh.update_poses(poses)
+        dh.deform_mesh_device(n_res, d_v, d_st, d_out, k=4, tol_t=10.0)
+        torch.cuda.synchronize()
+        t_res = 1e3 * (time.perf_counter() - t3)
         closures.append({"keyframe": m + 1, "mesh_vertices": int(x.shape[0]), "controls": int(cp.shape[0]),
                          "deform_ms_new_controls": t_first, "deform_ms_same_controls": t_again,
+                         "deform_ms_resident_cloud": t_res,
                          "rc": int(r["rc"])})
 lat = np.array(lat_ms[5:])
 print(json.dumps({
