@@ -140,6 +140,16 @@ int pgmo_deform_stamp_stretches_device(pgmo_deform_t* h, uint64_t n_local,
                                        uint64_t* stretch_stamp, uint64_t* stretch_len,
                                        uint64_t* n_stretches, void* stream);
 
+/* K1 without the host round trip, for callers that keep a schedule across solves: _begin queues
+ * the stretch scan of the slab's stamps and the read-back of its 64-bit fingerprint on `stream`;
+ * _finish waits for that read-back only — work queued behind it (pgmo_deform_run_device on the
+ * cached schedule) keeps running — and sets *changed = 0 iff the slab still has the stretch list
+ * last returned by pgmo_deform_stamp_stretches_device.  On *changed = 1 the caller discards the
+ * speculative result: stamp_stretches_device -> (exchange) -> build_schedule -> run_device. */
+int pgmo_deform_stamp_check_begin(pgmo_deform_t* h, uint64_t n_local, const uint64_t* d_stamps_ns,
+                                  void* stream);
+int pgmo_deform_stamp_check_finish(pgmo_deform_t* h, int* changed);
+
 /* Replays the reference's add/remove window state machine (mesh_deformation.h:159-212) over the
  * stamp stretches and uploads the resulting schedule.  stretch_stamp == NULL selects the
  * unstamped overload for `total_positions` vertices.  Returns PGMO_NOOP for the reference's

@@ -60,6 +60,8 @@ SIGNATURES = {
     "pgmo_deform_run_device": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _vp, _vp, _vp, _vp, C.c_int,
                                          _vp, _vp, _vp, _vp, _vp, C.c_uint32, _vp, _vp, _vp, _vp]),
     "pgmo_deform_schedule_info": (C.c_int, [_vp, _u64p, C.c_uint64, _vp]),
+    "pgmo_deform_stamp_check_begin": (C.c_int, [_vp, C.c_uint64, _vp, _vp]),
+    "pgmo_deform_stamp_check_finish": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "pgmo_deform_mesh_device": (C.c_int, [_vp, C.c_uint64, _vp, _vp, C.c_uint32, C.c_double,
                                           C.c_int, _vp, _vp, _vp, _vp]),
     "pgmo_vcc_device_view": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), _u64p]),
@@ -227,6 +229,14 @@ class DeformHandle:
             if n.value <= cap:
                 return stamps[: n.value].copy(), lens[: n.value].copy()
             cap = int(n.value)
+
+    def stamp_check_begin(self, d_stamps, n_local, stream=0):
+        _check(self._lib.pgmo_deform_stamp_check_begin(self._h, n_local, _ptr(d_stamps), _vp(stream)))
+
+    def stamp_check_finish(self):
+        changed = C.c_int(1)
+        _check(self._lib.pgmo_deform_stamp_check_finish(self._h, C.byref(changed)))
+        return bool(changed.value)
 
     def build_schedule(self, stretch_stamp, stretch_len, total_positions, k, tol_t):
         if stretch_stamp is None:

@@ -81,6 +81,12 @@ struct pgmo_deform {
   DevBuf<CandEntry> d_scratch;
   PinnedBuf<unsigned long long> h_counters;
   PinnedBuf<ulonglong2> h_bounds;
+  // stamp check in flight (pgmo_deform_stamp_check_begin / _finish)
+  DevBuf<unsigned long long> d_fp;
+  PinnedBuf<unsigned long long> h_fp;
+  cudaEvent_t ev_fp = nullptr;
+  uint64_t fp_n_pos = 0;
+  bool fp_pending = false;
 
   // staging for the host-buffer entry points
   DevBuf<float> d_x, d_y, d_z, d_ox, d_oy, d_oz;
@@ -236,6 +242,37 @@ int stampStretches(pgmo_deform_t* h, const uint64_t* d_stamps, const uint64_t* d
   return PGMO_OK;
 }
 
+// K1 without the host round trip: the scan and the read-back of (count, fingerprint) are queued
+// on `st`; stampCheckFinish waits for the read-back only, so kernels queued behind it (a
+// deformation on the cached schedule) keep the GPU busy meanwhile.
+int stampCheckBegin(pgmo_deform_t* h, const uint64_t* d_stamps, uint64_t n_pos, cudaStream_t st) {
+  PGMO_TRY(h->d_fp.reserve(2));
+  PGMO_TRY(h->h_fp.reserve(2));
+  PGMO_TRY(h->d_bounds.reserve(std::max<uint64_t>(h->d_bounds.cap, 1u << 16)));
+  PGMO_CUDA(cudaMemsetAsync(h->d_fp.ptr, 0, 2 * sizeof(unsigned long long), st));
+  PGMO_CUDA(launchStampStretches(d_stamps, nullptr, n_pos, h->d_bounds.ptr, h->d_bounds.cap,
+                                 h->d_fp.ptr, st));
+  PGMO_CUDA(cudaMemcpyAsync(h->h_fp.ptr, h->d_fp.ptr, 2 * sizeof(unsigned long long),
+                            cudaMemcpyDeviceToHost, st));
+  PGMO_CUDA(cudaEventRecord(h->ev_fp, st));
+  h->fp_n_pos = n_pos;
+  h->fp_pending = true;
+  return PGMO_OK;
+}
+
+// *changed = 0 iff the scanned stamps have the stretch list this handle downloaded last
+int stampCheckFinish(pgmo_deform_t* h, int* changed) {
+  if (!h->fp_pending) {
+    setLastError("stamp check: no scan in flight");
+    return PGMO_ERR_INVALID;
+  }
+  PGMO_CUDA(cudaEventSynchronize(h->ev_fp));
+  h->fp_pending = false;
+  *changed = (h->h_fp.ptr[0] == h->sc_count && h->h_fp.ptr[1] == h->sc_sum &&
+              h->fp_n_pos == h->sc_n_pos) ? 0 : 1;
+  return PGMO_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -260,6 +297,7 @@ int pgmo_deform_create(int device, pgmo_deform_t** out) {
   cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&h->ev_stamps, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&h->ev_fp, cudaEventDisableTiming);
   for (int i = 0; i < pgmo_deform::kPipe; ++i) {
     cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming);
@@ -291,6 +329,7 @@ void pgmo_deform_destroy(pgmo_deform_t* h) {
     if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
   }
   if (h->ev_stamps) cudaEventDestroy(h->ev_stamps);
+  if (h->ev_fp) cudaEventDestroy(h->ev_fp);
   if (h->s_in) cudaStreamDestroy(h->s_in);
   if (h->s_out) cudaStreamDestroy(h->s_out);
   delete h;
@@ -417,6 +456,19 @@ int pgmo_deform_stamp_stretches_device(pgmo_deform_t* h, uint64_t n_local,
     if (stretch_len) stretch_len[i] = s_len[i];
   }
   return PGMO_OK;
+}
+
+int pgmo_deform_stamp_check_begin(pgmo_deform_t* h, uint64_t n_local, const uint64_t* d_stamps_ns,
+                                  void* stream) {
+  PGMO_CHECK_ARG(h != nullptr && n_local > 0 && d_stamps_ns != nullptr);
+  PGMO_TRY(ensureDevice(h->device));
+  return stampCheckBegin(h, d_stamps_ns, n_local, pick(h, stream));
+}
+
+int pgmo_deform_stamp_check_finish(pgmo_deform_t* h, int* changed) {
+  PGMO_CHECK_ARG(h != nullptr && changed != nullptr);
+  PGMO_TRY(ensureDevice(h->device));
+  return stampCheckFinish(h, changed);
 }
 
 int pgmo_deform_build_schedule(pgmo_deform_t* h, uint64_t n_stretches,
@@ -928,6 +980,31 @@ int pgmo_deform_mesh_device(pgmo_deform_t* h, uint64_t n_v, const void* d_vertic
   PGMO_TRY(h->d_oz.reserve(n_v));
   PGMO_TRY(h->d_status.reserve(n_v));
   PGMO_CUDA(launchAosToSoa(n_v, in, h->d_x.ptr, h->d_y.ptr, h->d_z.ptr, st));
+  uint8_t* status = d_processed ? d_processed : h->d_status.ptr;
+  // The usual call re-deforms a mesh whose stamps did not change since the last call (a new
+  // solve): deform on the cached schedule right away and check the stamps' fingerprint while
+  // the kernels run; only a mismatch pays for the download + schedule replay (and a second run).
+  if (d_stamps_ns && h->sched_ready && h->sched_stamped && h->sched_k == k && h->sched_tol == tol_t &&
+      h->sched_control_version == h->control_version && h->sched_total == n_v &&
+      h->sc_n_pos == n_v && h->sc_stamp == h->sched_stretch_stamp &&
+      h->sc_len == h->sched_stretch_len) {
+    PGMO_TRY(stampCheckBegin(h, d_stamps_ns, n_v, st));
+    PGMO_TRY(pgmo_deform_run_device(h, 0, n_v, h->d_x.ptr, h->d_y.ptr, h->d_z.ptr, nullptr,
+                                    precision, h->d_ox.ptr, h->d_oy.ptr, h->d_oz.ptr, nullptr,
+                                    nullptr, 0, nullptr, status, nullptr, st));
+    int changed = 1;
+    PGMO_TRY(stampCheckFinish(h, &changed));
+    if (!changed) {
+      PGMO_CUDA(launchSoaToAos(n_v, in, h->d_ox.ptr, h->d_oy.ptr, h->d_oz.ptr, status, out, st));
+      if (n_resolved) {
+        PGMO_CUDA(cudaMemcpyAsync(h->h_counters.ptr, h->d_counters.ptr, sizeof(unsigned long long),
+                                  cudaMemcpyDeviceToHost, st));
+        PGMO_CUDA(cudaStreamSynchronize(st));
+        *n_resolved = h->h_counters.ptr[0];
+      }
+      return PGMO_OK;
+    }
+  }
   int rc;
   if (d_stamps_ns) {
     std::vector<uint64_t> s_stamp, s_len;
@@ -937,7 +1014,6 @@ int pgmo_deform_mesh_device(pgmo_deform_t* h, uint64_t n_v, const void* d_vertic
     rc = pgmo_deform_build_schedule(h, 0, nullptr, nullptr, n_v, k, tol_t);
   }
   if (rc != PGMO_OK) return rc;  // NOOP (reference early return): nothing written
-  uint8_t* status = d_processed ? d_processed : h->d_status.ptr;
   PGMO_TRY(pgmo_deform_run_device(h, 0, n_v, h->d_x.ptr, h->d_y.ptr, h->d_z.ptr, nullptr, precision,
                                   h->d_ox.ptr, h->d_oy.ptr, h->d_oz.ptr, nullptr, nullptr, 0, nullptr,
                                   status, n_resolved, st));

@@ -106,3 +106,57 @@ def test_resident_in_place_and_view_tracks_the_compressor(capi):
     assert np.array_equal(vcc.snapshot()["vertices"], snap["vertices"])
     h.close()
     vcc.close()
+
+
+def test_speculative_rerun_detects_changed_stamps(capi):
+    """A second call on the same mesh deforms on the cached schedule while the stamp scan is in
+    flight; a mesh whose stamps changed (same size) must fall back to the full path."""
+    import torch
+
+    vcc = capi.VccHandle(0.05, 0)
+    _fill(vcc, 10, 6000, 1)
+    snap = vcc.snapshot()
+    n = snap["vertices"].shape[0]
+    cp, cs, poses = _controls(snap, 300, np.random.default_rng(11))
+    h = capi.DeformHandle(0)
+    h.set_controls(cp, cs, None, poses)
+    cloud = torch.from_numpy(np.concatenate([snap["vertices"], snap["rgba"].view(np.float32)[:, None]], 1)).cuda()
+    x, y, z = (np.ascontiguousarray(snap["vertices"][:, a]) for a in range(3))
+
+    def resident(stamps_np):
+        d_st = torch.from_numpy(stamps_np.view(np.int64)).cuda()
+        out = torch.empty_like(cloud)
+        rc, _ = h.deform_mesh_device(n, cloud, d_st, out, k=4, tol_t=2.0)
+        torch.cuda.synchronize()
+        assert rc == 0
+        return out.cpu().numpy()
+
+    first = resident(snap["stamps"])
+    builds0 = h.last_timings()[2]
+    again = resident(snap["stamps"])  # speculative: cached schedule, fingerprint matches
+    assert h.last_timings()[2] == builds0
+    assert np.array_equal(first.view(np.uint32), again.view(np.uint32))
+
+    # move one stretch boundary: same vertex count, different stretch list
+    st2 = snap["stamps"].copy()
+    b = np.flatnonzero(st2[1:] != st2[:-1])
+    assert b.shape[0] > 2
+    cut = int(b[b.shape[0] // 2])
+    st2[cut - 40:cut + 1] = st2[cut + 1]
+    changed = resident(st2)
+    assert h.last_timings()[2] == builds0 + 1
+    h2 = capi.DeformHandle(0)
+    h2.set_controls(cp, cs, None, poses)
+    ref = h2.deform_points(x, y, z, st2, k=4, tol_t=2.0)
+    for a, ax in enumerate("xyz"):
+        assert np.array_equal(changed[:, a], ref[ax]), ax
+    # and the explicit check API
+    d_st2 = torch.from_numpy(st2.view(np.int64)).cuda()
+    h.stamp_check_begin(d_st2, n)
+    assert h.stamp_check_finish() is False
+    d_st1 = torch.from_numpy(snap["stamps"].view(np.int64)).cuda()
+    h.stamp_check_begin(d_st1, n)
+    assert h.stamp_check_finish() is True
+    h.close()
+    h2.close()
+    vcc.close()
