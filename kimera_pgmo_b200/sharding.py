@@ -98,6 +98,40 @@ class StretchExchange:
         return self._last_global
 
 
+def plan_segments(counts, world: int):
+    """configs[3] / SURVEY 8e: a multi-robot mesh is one independent deformation problem per
+    robot prefix.  The robots' vertices are laid end to end (in the order given) and cut into
+    `world` contiguous slabs of equal size; a slab that straddles a robot boundary becomes two
+    segments.  Returns, per rank, a list of (robot, first, count) — `first` local to the robot.
+    Every vertex of every robot is owned by exactly one rank."""
+    counts = [int(c) for c in counts]
+    total = sum(counts)
+    starts = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    plan = []
+    for rank in range(world):
+        lo, n = slab_bounds(total, world, rank)
+        hi = lo + n
+        segs = []
+        for robot, c in enumerate(counts):
+            a, b = max(lo, int(starts[robot])), min(hi, int(starts[robot]) + c)
+            if b > a:
+                segs.append((robot, a - int(starts[robot]), b - a))
+        plan.append(segs)
+    return plan
+
+
+class MultiRobotExchange:
+    """One StretchExchange per robot: ranks that own no vertex of a robot contribute an empty
+    list (the collectives stay world-wide, a few KB each, and only run when a list changed)."""
+
+    def __init__(self, n_robots: int, world: int, device):
+        self._ex = [StretchExchange(world, device) for _ in range(n_robots)]
+
+    def __call__(self, robot: int, ss: np.ndarray, sl: np.ndarray):
+        return self._ex[robot](np.ascontiguousarray(ss, dtype=np.uint64),
+                               np.ascontiguousarray(sl, dtype=np.uint64))
+
+
 def broadcast_controls(tensors, src: int = 0):
     """Replicates the control table / poses (device or CPU tensors) from `src` to every rank."""
     import torch.distributed as dist

@@ -103,6 +103,62 @@ def deformation_slab(n_vertices_total: int, n_controls: int, first: int, count: 
     return ctrl
 
 
+def deformation_range(n_vertices_total: int, n_controls: int, first: int, count: int,
+                      ctrl_per_kf: int = 10, seed: int = 42, t0_ns: int = T0_NS,
+                      vertex_spread: float = 6.0, ctrl_spread: float = 5.0,
+                      chunk: int = 1 << 20, with_controls: bool = True):
+    """Vertices [first, first + count) of a mesh whose every vertex is a function of (seed, its
+    global index) only: generated in fixed chunks of `chunk` vertices, each from its own stream,
+    so that any partition of the index range into slabs materialises the identical mesh (shard
+    invariance tests, configs[3]).  Same workload family as deformation_case."""
+    ctrl = (deformation_case(0, n_controls, ctrl_per_kf, seed, t0_ns, 0.0, vertex_spread,
+                             ctrl_spread) if with_controls else {})
+    n_kf = max(n_controls // ctrl_per_kf, 1)
+    kf = _trajectory(n_kf).astype(np.float32)
+    kf_stamp = (np.uint64(t0_ns) + np.arange(n_kf, dtype=np.uint64) * np.uint64(1_000_000_000))
+    per_kf = -(-n_vertices_total // n_kf)
+    x = np.empty(count, dtype=np.float32)
+    y = np.empty(count, dtype=np.float32)
+    z = np.empty(count, dtype=np.float32)
+    last = first + count
+    c = first // chunk
+    while c * chunk < last:
+        lo, hi = c * chunk, min((c + 1) * chunk, n_vertices_total)
+        rng = np.random.default_rng([seed, 7919, c])
+        n = hi - lo
+        dx = rng.uniform(-vertex_spread, vertex_spread, n).astype(np.float32)
+        dy = rng.uniform(-vertex_spread, vertex_spread, n).astype(np.float32)
+        dz = rng.uniform(0.0, 3.0, n).astype(np.float32)
+        a, b = max(lo, first), min(hi, last)
+        if b > a:
+            v_kf = np.minimum(np.arange(a, b, dtype=np.int64) // per_kf, n_kf - 1)
+            x[a - first:b - first] = kf[v_kf, 0] + dx[a - lo:b - lo]
+            y[a - first:b - first] = kf[v_kf, 1] + dy[a - lo:b - lo]
+            z[a - first:b - first] = dz[a - lo:b - lo]
+        c += 1
+    v_kf = np.minimum(np.arange(first, last, dtype=np.int64) // per_kf, n_kf - 1)
+    ctrl.update(x=x, y=y, z=z, stamps=np.ascontiguousarray(kf_stamp[v_kf]))
+    return ctrl
+
+
+# kimera_pgmo/include/kimera_pgmo/utils/common_functions.h:19-61
+ROBOT_ID_TO_PREFIX = {i: chr(ord("a") + i) for i in range(8)}
+ROBOT_ID_TO_VERTEX_PREFIX = {i: chr(ord("s") + i) for i in range(8)}
+
+
+def symbol_key(prefix: str, index: int) -> int:
+    """gtsam::Symbol(chr, idx).key() = (chr << 56) | idx (test/data/graph.dgrf: 'a' ->
+    6989586621679009792)."""
+    return (ord(prefix) << 56) | int(index)
+
+
+def robot_range(robot_id: int, n_vertices: int, n_controls: int, first: int, count: int, **kw):
+    """configs[3]: robot `robot_id` of a multi-robot mesh — its own trajectory phase, stamps and
+    control table (seed and epoch offset by the robot id)."""
+    return deformation_range(n_vertices, n_controls, first, count, seed=42 + 1000 * robot_id,
+                             t0_ns=T0_NS + robot_id * 3_600_000_000_000, **kw)
+
+
 def lattice_case(n_side: int = 12, seed: int = 7, t0_ns: int = T0_NS, n_groups: int = 4,
                  points_per_voxel: int = 1):
     """Tie-heavy case: vertices and control points on a 0.5 m lattice, so exact float-distance

@@ -107,3 +107,75 @@ def test_two_ranks_build_identical_schedule(tmp_path):
     np.testing.assert_array_equal(r0["gs"], ws)
     np.testing.assert_array_equal(r0["gl"], wl)
     assert r0["runs"].shape[0] > 0
+
+
+def test_plan_segments_cover_every_robot_once():
+    from kimera_pgmo_b200 import sharding
+    for counts, world in (([25_000_000] * 4, 8), ([25_000_000] * 4, 3), ([10, 30, 5], 4), ([7], 8),
+                          ([0, 5, 0, 9], 2)):
+        plan = sharding.plan_segments(counts, world)
+        assert len(plan) == world
+        owned = [np.zeros(c, dtype=np.int32) for c in counts]
+        sizes = []
+        for segs in plan:
+            sizes.append(sum(c for _, _, c in segs))
+            for robot, first, count in segs:
+                assert count > 0
+                owned[robot][first:first + count] += 1
+        assert all((o == 1).all() for o in owned)
+        assert max(sizes) - min(sizes) <= 1  # equal slabs over the concatenated robots
+
+
+def test_range_generator_is_partition_invariant():
+    from kimera_pgmo_b200 import synth
+    n, n_c = 2_300_000, 2300
+    whole = synth.robot_range(1, n, n_c, 0, n)
+    for first, count in ((0, 17), (1_048_570, 20), (2_000_000, 300_000), (123_456, 1_500_000)):
+        part = synth.robot_range(1, n, n_c, first, count, with_controls=False)
+        for key in ("x", "y", "z", "stamps"):
+            np.testing.assert_array_equal(whole[key][first:first + count], part[key])
+    other = synth.robot_range(2, n, n_c, 0, 1000)
+    assert not np.array_equal(other["x"], whole["x"][:1000])
+    assert other["ctrl_stamps"][0] != whole["ctrl_stamps"][0]
+    # gtsam::Symbol keys of the reference's test data (test/data/graph.dgrf:1,4)
+    assert synth.symbol_key("a", 0) == 6989586621679009792
+    assert synth.symbol_key("v", 0) == 8502796096475496448
+    assert synth.ROBOT_ID_TO_VERTEX_PREFIX[3] == "v" and synth.ROBOT_ID_TO_PREFIX[7] == "h"
+
+
+WORKER_ROBOTS = r'''
+import os, sys
+import numpy as np
+import torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from kimera_pgmo_b200 import sharding, synth
+
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+R, n_v, n_c = 3, 40_000, 400
+plan = sharding.plan_segments([n_v] * R, world)
+ex = sharding.MultiRobotExchange(R, world, torch.device("cpu"))
+empty = np.zeros(0, np.uint64)
+for attempt in range(2):  # second pass: nothing changed, cached lists come back
+    local = {r: (empty, empty) for r in range(R)}
+    for r, first, count in plan[rank]:
+        local[r] = sharding.stretches_of(synth.robot_range(r, n_v, n_c, first, count, with_controls=False)["stamps"])
+    for r in range(R):
+        gs, gl = ex(r, *local[r])
+        ws, wl = sharding.stretches_of(synth.robot_range(r, n_v, n_c, 0, n_v, with_controls=False)["stamps"])
+        assert np.array_equal(gs, ws) and np.array_equal(gl, wl), (rank, r, attempt)
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+@pytest.mark.timeout(300)
+def test_two_ranks_three_robots_exchange(tmp_path):
+    worker = tmp_path / "worker_robots.py"
+    worker.write_text(WORKER_ROBOTS)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                        "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port",
+                        "29654", str(worker), ROOT], capture_output=True, text=True, env=env,
+                       timeout=280)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
