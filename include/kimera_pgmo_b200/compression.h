@@ -8,6 +8,10 @@
 // clearArchivedBlocks / getters; state lives in HBM behind pgmo_vcc_t / pgmo_oct_t handles.
 #pragma once
 
+#include <array>
+#include <limits>
+#include <map>
+
 #include <memory>
 #include <optional>
 #include <stdexcept>
@@ -54,6 +58,65 @@ class PclMeshInterface : public MeshInterface {
   BlockIndices indices_;
 };
 
+// kimera_pgmo_ros/include/kimera_pgmo_ros/voxblox_msg_interface.h + src/voxblox_msg_interface.cpp.
+// The message types mirror the fields of voxblox_msgs::Mesh / MeshBlock that the interface reads
+// (a ROS build passes the real message through a two-line adapter).  The
+// compressors recognise this interface and upload the packed u16 / u8 arrays as they are: the
+// per-vertex decode runs on the GPU (pgmo_*_integrate_voxblox).
+struct VoxbloxMeshBlock {
+  int64_t index[3] = {0, 0, 0};
+  std::vector<uint16_t> x, y, z;
+  std::vector<uint8_t> r, g, b;
+};
+struct VoxbloxMesh {
+  float block_edge_length = 0.f;
+  std::vector<VoxbloxMeshBlock> mesh_blocks;
+};
+
+class VoxbloxMsgInterface : public MeshInterface {
+ public:
+  explicit VoxbloxMsgInterface(const VoxbloxMesh& mesh) : active_mesh_block_(nullptr), mesh_(mesh) {
+    size_t count = 0;
+    for (const auto& block : mesh_.mesh_blocks) {
+      mesh_blocks_.emplace_back(block.index[0], block.index[1], block.index[2]);
+      block_lookup_[{block.index[0], block.index[1], block.index[2]}] = count;
+      ++count;
+    }
+  }
+  const BlockIndices& blockIndices() const override { return mesh_blocks_; }
+  void markBlockActive(const BlockIndex& block) const override {
+    const auto iter = block_lookup_.find({block.x(), block.y(), block.z()});
+    active_mesh_block_ = iter == block_lookup_.end() ? nullptr : &mesh_.mesh_blocks.at(iter->second);
+  }
+  size_t activeBlockSize() const override {
+    return active_mesh_block_ ? active_mesh_block_->x.size() : 0;
+  }
+  pcl::PointXYZRGBA getActiveVertex(size_t i) const override {  // :43-62
+    const VoxbloxMeshBlock& blk = *active_mesh_block_;
+    pcl::PointXYZRGBA point;
+    point.x = (static_cast<float>(blk.x.at(i)) * point_conv_factor_ + static_cast<float>(blk.index[0])) *
+              mesh_.block_edge_length;
+    point.y = (static_cast<float>(blk.y.at(i)) * point_conv_factor_ + static_cast<float>(blk.index[1])) *
+              mesh_.block_edge_length;
+    point.z = (static_cast<float>(blk.z.at(i)) * point_conv_factor_ + static_cast<float>(blk.index[2])) *
+              mesh_.block_edge_length;
+    point.r = blk.r[i];
+    point.g = blk.g[i];
+    point.b = blk.b[i];
+    point.a = std::numeric_limits<uint8_t>::max();
+    return point;
+  }
+  MeshInterface::Ptr clone() const override { return std::make_shared<VoxbloxMsgInterface>(*this); }
+  const VoxbloxMesh& message() const { return mesh_; }
+
+ protected:
+  mutable const VoxbloxMeshBlock* active_mesh_block_;
+  std::map<std::array<int64_t, 3>, size_t> block_lookup_;  // BlockIndexMap<size_t> upstream
+  BlockIndices mesh_blocks_;
+  const VoxbloxMesh& mesh_;
+  inline static constexpr float point_conv_factor_ = 2.0f / std::numeric_limits<uint16_t>::max();
+};
+
 namespace detail {
 // MeshInterface -> the flat arrays of the C ABI (blockIndices() order, cursor protocol kept)
 struct FlatMesh {
@@ -61,8 +124,33 @@ struct FlatMesh {
   std::vector<uint64_t> offsets;
   std::vector<float> xyz;
   std::vector<uint32_t> rgba;
+  // voxblox messages stay packed (decoded on the GPU)
+  bool packed = false;
+  std::vector<uint16_t> x16, y16, z16;
+  std::vector<uint8_t> r8, g8, b8;
+  float block_edge_length = 0.f;
   explicit FlatMesh(const MeshInterface& mesh) {
     offsets.push_back(0);
+    if (const auto* vb = dynamic_cast<const VoxbloxMsgInterface*>(&mesh)) {
+      packed = true;
+      block_edge_length = vb->message().block_edge_length;
+      for (const auto& blk : vb->message().mesh_blocks) {
+        for (int a = 0; a < 3; ++a) block_idx.push_back(static_cast<int32_t>(blk.index[a]));
+        const size_t n = blk.x.size();
+        if (blk.y.size() != n || blk.z.size() != n || blk.r.size() < n || blk.g.size() < n ||
+            blk.b.size() < n) {
+          throw std::out_of_range("voxblox mesh block: y/z/.at(i) or colour arrays shorter than x");
+        }
+        x16.insert(x16.end(), blk.x.begin(), blk.x.end());
+        y16.insert(y16.end(), blk.y.begin(), blk.y.end());
+        z16.insert(z16.end(), blk.z.begin(), blk.z.end());
+        r8.insert(r8.end(), blk.r.begin(), blk.r.begin() + n);
+        g8.insert(g8.end(), blk.g.begin(), blk.g.begin() + n);
+        b8.insert(b8.end(), blk.b.begin(), blk.b.begin() + n);
+        offsets.push_back(x16.size());
+      }
+      return;
+    }
     for (const auto& block : mesh.blockIndices()) {
       block_idx.push_back(block.x());
       block_idx.push_back(block.y());
@@ -80,6 +168,7 @@ struct FlatMesh {
     }
   }
   uint32_t numBlocks() const { return static_cast<uint32_t>(offsets.size() - 1); }
+  size_t numVertices() const { return static_cast<size_t>(offsets.back()); }
 };
 
 inline pcl::PointXYZRGBA makePoint(const float* xyz, uint32_t rgba) {
@@ -157,10 +246,17 @@ class VoxelClearingCompression : public MeshCompression {
     new_triangles.clear();
     new_indices.clear();
     const detail::FlatMesh flat(mesh);
-    std::vector<uint64_t> remap(flat.rgba.size());
-    detail::throwOnError(pgmo_vcc_integrate(handle_.get(), flat.numBlocks(), flat.block_idx.data(),
-                                            flat.offsets.data(), flat.xyz.data(), flat.rgba.data(),
-                                            stamp_in_sec, remap.data(), nullptr));
+    std::vector<uint64_t> remap(flat.numVertices());
+    if (flat.packed) {
+      detail::throwOnError(pgmo_vcc_integrate_voxblox(
+          handle_.get(), flat.numBlocks(), flat.block_idx.data(), flat.offsets.data(),
+          flat.x16.data(), flat.y16.data(), flat.z16.data(), flat.r8.data(), flat.g8.data(),
+          flat.b8.data(), flat.block_edge_length, stamp_in_sec, remap.data(), nullptr));
+    } else {
+      detail::throwOnError(pgmo_vcc_integrate(handle_.get(), flat.numBlocks(), flat.block_idx.data(),
+                                              flat.offsets.data(), flat.xyz.data(), flat.rgba.data(),
+                                              stamp_in_sec, remap.data(), nullptr));
+    }
     size_t b = 0;
     for (const auto& block : mesh.blockIndices()) {
       remapping.insert({block, IndexMapping()});  // :123
@@ -292,11 +388,18 @@ class OctreeCompression : public MeshCompression {
     new_triangles.clear();
     new_indices.clear();
     const detail::FlatMesh flat(mesh);
-    std::vector<int64_t> idx(flat.rgba.size());
-    std::vector<uint8_t> kind(flat.rgba.size());
-    detail::throwOnError(pgmo_oct_integrate(handle_.get(), flat.numBlocks(), flat.block_idx.data(),
-                                            flat.offsets.data(), flat.xyz.data(), flat.rgba.data(),
-                                            stamp_in_sec, idx.data(), kind.data()));
+    std::vector<int64_t> idx(flat.numVertices());
+    std::vector<uint8_t> kind(flat.numVertices());
+    if (flat.packed) {
+      detail::throwOnError(pgmo_oct_integrate_voxblox(
+          handle_.get(), flat.numBlocks(), flat.block_idx.data(), flat.offsets.data(),
+          flat.x16.data(), flat.y16.data(), flat.z16.data(), flat.r8.data(), flat.g8.data(),
+          flat.b8.data(), flat.block_edge_length, stamp_in_sec, idx.data(), kind.data()));
+    } else {
+      detail::throwOnError(pgmo_oct_integrate(handle_.get(), flat.numBlocks(), flat.block_idx.data(),
+                                              flat.offsets.data(), flat.xyz.data(), flat.rgba.data(),
+                                              stamp_in_sec, idx.data(), kind.data()));
+    }
     size_t b = 0;
     for (const auto& block : mesh.blockIndices()) {
       remapping.insert({block, IndexMapping()});  // :256

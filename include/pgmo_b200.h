@@ -282,6 +282,30 @@ int pgmo_oct_last_outputs(pgmo_oct_t* h, float* new_vertices_xyz, uint32_t* new_
  * vertices accepted into the mesh]. */
 int pgmo_oct_last_stats(pgmo_oct_t* h, uint64_t* stats4);
 
+/* ------------------------------------------------------------------------------------------
+ * MeshInterface inputs.  The integrate calls above take what MeshInterface::getActiveVertex
+ * yields, flattened.  A voxblox mesh message (VoxbloxMsgInterface,
+ * kimera_pgmo_ros/src/voxblox_msg_interface.cpp:11-62) stores u16 fixed-point coordinates per
+ * block; the *_voxblox calls take it as it is — per vertex x, y, z (u16) and r, g, b (u8),
+ * blocks concatenated in blockIndices() order — and evaluate getActiveVertex on the GPU:
+ *   p = (float(u16) * (2.0f / 65535) + float(block index)) * block_edge_length   (float, no FMA)
+ *   colour = (r, g, b, 255).
+ * ---------------------------------------------------------------------------------------- */
+int pgmo_voxblox_decode(int device, uint32_t n_blocks, const int32_t* block_idx_xyz,
+                        const uint64_t* block_offsets, const uint16_t* x, const uint16_t* y,
+                        const uint16_t* z, const uint8_t* r, const uint8_t* g, const uint8_t* b,
+                        float block_edge_length, float* xyz_out, uint32_t* rgba_out);
+int pgmo_vcc_integrate_voxblox(pgmo_vcc_t* h, uint32_t n_blocks, const int32_t* block_idx_xyz,
+                               const uint64_t* block_offsets, const uint16_t* x, const uint16_t* y,
+                               const uint16_t* z, const uint8_t* r, const uint8_t* g,
+                               const uint8_t* b, float block_edge_length, double stamp_s,
+                               uint64_t* remap_out, int64_t* keys_out);
+int pgmo_oct_integrate_voxblox(pgmo_oct_t* h, uint32_t n_blocks, const int32_t* block_idx_xyz,
+                               const uint64_t* block_offsets, const uint16_t* x, const uint16_t* y,
+                               const uint16_t* z, const uint8_t* r, const uint8_t* g,
+                               const uint8_t* b, float block_edge_length, double stamp_s,
+                               int64_t* remap_index, uint8_t* remap_kind);
+
 #ifdef __cplusplus
 }
 #endif

@@ -86,6 +86,11 @@ SIGNATURES = {
     "pgmo_oct_last_outputs": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "pgmo_oct_last_stats": (C.c_int, [_vp, _vp]),
     "pgmo_oct_create_block": (C.c_int, [C.c_double, C.c_int, C.POINTER(_vp)]),
+    "pgmo_voxblox_decode": (C.c_int, [C.c_int, C.c_uint32] + [_vp] * 8 + [C.c_float, _vp, _vp]),
+    "pgmo_vcc_integrate_voxblox": (C.c_int, [_vp, C.c_uint32] + [_vp] * 8 + [C.c_float, C.c_double,
+                                                                          _vp, _vp]),
+    "pgmo_oct_integrate_voxblox": (C.c_int, [_vp, C.c_uint32] + [_vp] * 8 + [C.c_float, C.c_double,
+                                                                          _vp, _vp]),
 }
 
 _lib = None
@@ -300,6 +305,25 @@ def _flatten_blocks(block_idx, offsets, xyz, rgba):
     return bi, off, pts, col
 
 
+def _voxblox_args(block_idx, offsets, x16, y16, z16, r, g, b):
+    bi = np.ascontiguousarray(block_idx, dtype=np.int32).reshape(-1, 3)
+    off = np.ascontiguousarray(offsets, dtype=np.uint64)
+    packed = [np.ascontiguousarray(a, dtype=np.uint16) for a in (x16, y16, z16)]
+    packed += [np.ascontiguousarray(a, dtype=np.uint8) for a in (r, g, b)]
+    return bi, off, packed
+
+
+def voxblox_decode(block_idx, offsets, x16, y16, z16, r, g, b, edge, device=0):
+    """VoxbloxMsgInterface::getActiveVertex for a whole message on the GPU -> (xyz f32, rgba)"""
+    bi, off, packed = _voxblox_args(block_idx, offsets, x16, y16, z16, r, g, b)
+    n = int(off[-1]) if off.shape[0] else 0
+    xyz = np.zeros((n, 3), dtype=np.float32)
+    rgba = np.zeros(n, dtype=np.uint32)
+    _check(load().pgmo_voxblox_decode(device, bi.shape[0], _ptr(bi), _ptr(off),
+                                      *[_ptr(a) for a in packed], float(edge), _ptr(xyz), _ptr(rgba)))
+    return xyz, rgba
+
+
 class VccHandle:
     """pgmo_vcc_t: VoxelClearingCompression."""
 
@@ -325,6 +349,17 @@ class VccHandle:
         _check(self._lib.pgmo_vcc_integrate(self._h, bi.shape[0], _ptr(bi), _ptr(off), _ptr(pts),
                                             _ptr(col), float(stamp_s), _ptr(remap), _ptr(keys)))
         return remap, keys
+
+    def integrate_voxblox(self, block_idx, offsets, x16, y16, z16, r, g, b, edge, stamp_s,
+                          want_keys=False):
+        bi, off, packed = _voxblox_args(block_idx, offsets, x16, y16, z16, r, g, b)
+        n = int(off[-1]) if off.shape[0] else 0
+        remap = np.zeros(n, dtype=np.uint64)
+        keys = np.zeros((n, 3), dtype=np.int64) if want_keys else None
+        _check(self._lib.pgmo_vcc_integrate_voxblox(
+            self._h, bi.shape[0], _ptr(bi), _ptr(off), *[_ptr(a) for a in packed], float(edge),
+            float(stamp_s), _ptr(remap), _ptr(keys)))
+        return (remap, keys) if want_keys else remap
 
     def integrate_device(self, block_idx, offsets, d_xyz, d_rgba, stamp_s, d_remap, stream=0):
         bi = np.ascontiguousarray(block_idx, dtype=np.int32).reshape(-1, 3)
@@ -389,6 +424,16 @@ class OctHandle:
         kind = np.zeros(n, dtype=np.uint8)
         _check(self._lib.pgmo_oct_integrate(self._h, bi.shape[0], _ptr(bi), _ptr(off), _ptr(pts),
                                             _ptr(col), float(stamp_s), _ptr(idx), _ptr(kind)))
+        return idx, kind
+
+    def integrate_voxblox(self, block_idx, offsets, x16, y16, z16, r, g, b, edge, stamp_s):
+        bi, off, packed = _voxblox_args(block_idx, offsets, x16, y16, z16, r, g, b)
+        n = int(off[-1]) if off.shape[0] else 0
+        idx = np.full(n, -1, dtype=np.int64)
+        kind = np.zeros(n, dtype=np.uint8)
+        _check(self._lib.pgmo_oct_integrate_voxblox(
+            self._h, bi.shape[0], _ptr(bi), _ptr(off), *[_ptr(a) for a in packed], float(edge),
+            float(stamp_s), _ptr(idx), _ptr(kind)))
         return idx, kind
 
     def prune(self, earliest_s):

@@ -12,6 +12,7 @@
 #include "common.cuh"
 #include "deform_schedule.h"  // stampFromSec
 #include "oct_kernels.cuh"
+#include "mesh_interface.cuh"
 #include "vcc_kernels.cuh"    // launchVccCompactLive / vccTileScratchEntries (ordered compaction)
 
 using namespace pgmo;
@@ -384,6 +385,7 @@ struct pgmo_oct {
   DevBuf<float> d_xyz;
   DevBuf<uint32_t> d_rgba;
   DevBuf<unsigned long long> d_offsets;
+  VoxbloxStage vb_stage;
   DevBuf<uint8_t> tri_end, flag, member_a, member_b, surf, check, keep, reobs_flag;
   DevBuf<int32_t> reobs, cand_of_vertex, decision, pot_of_cand, acc_rank;
   DevBuf<unsigned long long> cand_list, pot_list, acc_list, face_list;
@@ -609,9 +611,10 @@ void pgmo_oct_destroy(pgmo_oct_t* h) {
   delete h;
 }
 
-int pgmo_oct_integrate(pgmo_oct_t* h, uint32_t n_blocks, const int32_t* block_idx_xyz,
-                       const uint64_t* block_offsets, const float* xyz, const uint32_t* rgba,
-                       double stamp_s, int64_t* remap_index, uint8_t* remap_kind) {
+static int octIntegrate(pgmo_oct_t* h, uint32_t n_blocks, const int32_t* block_idx_xyz,
+                        const uint64_t* block_offsets, const float* xyz, const uint32_t* rgba,
+                        const VoxbloxInput* vb, double stamp_s, int64_t* remap_index,
+                        uint8_t* remap_kind) {
   PGMO_CHECK_ARG(h != nullptr);
   PGMO_CHECK_ARG(n_blocks == 0 || (block_idx_xyz && block_offsets));
   PGMO_TRY(ensureDevice(h->device));
@@ -620,7 +623,7 @@ int pgmo_oct_integrate(pgmo_oct_t* h, uint32_t n_blocks, const int32_t* block_id
   const uint64_t n64 = n_blocks ? block_offsets[n_blocks] : 0;
   if (n64 == 0) return PGMO_OK;
   PGMO_CHECK_ARG(n64 < 0x7FFFFFFFull);
-  PGMO_CHECK_ARG(xyz && remap_index && remap_kind);
+  PGMO_CHECK_ARG((xyz || vb) && remap_index && remap_kind);
   const uint32_t n = static_cast<uint32_t>(n64);
   const double res = h->resolution;
   const uint64_t n_orig = h->n_all;
@@ -629,8 +632,13 @@ int pgmo_oct_integrate(pgmo_oct_t* h, uint32_t n_blocks, const int32_t* block_id
   PGMO_TRY(h->d_xyz.reserve(3ull * n));
   PGMO_TRY(h->d_rgba.reserve(n));
   PGMO_TRY(h->d_offsets.reserve(n_blocks + 1));
-  PGMO_CUDA(cudaMemcpyAsync(h->d_xyz.ptr, xyz, 3ull * n * sizeof(float), cudaMemcpyHostToDevice, st));
-  if (rgba) PGMO_CUDA(cudaMemcpyAsync(h->d_rgba.ptr, rgba, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  if (vb) {
+    PGMO_TRY(stageVoxblox(&h->vb_stage, n_blocks, block_idx_xyz, block_offsets, *vb, h->d_xyz.ptr,
+                          h->d_rgba.ptr, st));
+  } else {
+    PGMO_CUDA(cudaMemcpyAsync(h->d_xyz.ptr, xyz, 3ull * n * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (rgba) PGMO_CUDA(cudaMemcpyAsync(h->d_rgba.ptr, rgba, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  }
   PGMO_CUDA(cudaMemcpyAsync(h->d_offsets.ptr, block_offsets, (n_blocks + 1) * sizeof(uint64_t),
                             cudaMemcpyHostToDevice, st));
   PGMO_TRY(h->tri_end.reserve(n));
@@ -766,7 +774,7 @@ int pgmo_oct_integrate(pgmo_oct_t* h, uint32_t n_blocks, const int32_t* block_id
   if (n_acc > 0) {
     octCommitVerticesKernel<<<blocksFor(n_acc), 256, 0, st>>>(
         static_cast<uint32_t>(n_acc), h->acc_list.ptr, h->pot_list.ptr, h->cand_list.ptr, h->d_xyz.ptr,
-        rgba ? h->d_rgba.ptr : nullptr, n_orig, h->n_act, stampFromSec(stamp_s), stamp_s,
+        (rgba || vb) ? h->d_rgba.ptr : nullptr, n_orig, h->n_act, stampFromSec(stamp_s), stamp_s,
         h->all_vertices.ptr, h->all_stamps.ptr, h->act_xyz.ptr, h->act_index.ptr, h->act_stamp.ptr,
         h->new_vertices.ptr);
   }
@@ -824,6 +832,23 @@ int pgmo_oct_integrate(pgmo_oct_t* h, uint32_t n_blocks, const int32_t* block_id
   h->n_new_indices = n_reobs + n_acc;
   if (n_acc > 0) PGMO_TRY(buildPersistent(h, first_new, st));
   return PGMO_OK;
+}
+
+int pgmo_oct_integrate(pgmo_oct_t* h, uint32_t n_blocks, const int32_t* block_idx_xyz,
+                       const uint64_t* block_offsets, const float* xyz, const uint32_t* rgba,
+                       double stamp_s, int64_t* remap_index, uint8_t* remap_kind) {
+  return octIntegrate(h, n_blocks, block_idx_xyz, block_offsets, xyz, rgba, nullptr, stamp_s,
+                      remap_index, remap_kind);
+}
+
+int pgmo_oct_integrate_voxblox(pgmo_oct_t* h, uint32_t n_blocks, const int32_t* block_idx_xyz,
+                               const uint64_t* block_offsets, const uint16_t* x, const uint16_t* y,
+                               const uint16_t* z, const uint8_t* r, const uint8_t* g,
+                               const uint8_t* b, float block_edge_length, double stamp_s,
+                               int64_t* remap_index, uint8_t* remap_kind) {
+  const VoxbloxInput in{x, y, z, r, g, b, block_edge_length};
+  return octIntegrate(h, n_blocks, block_idx_xyz, block_offsets, nullptr, nullptr, &in, stamp_s,
+                      remap_index, remap_kind);
 }
 
 int pgmo_oct_prune(pgmo_oct_t* h, double earliest_s) {

@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "deform_schedule.h"
 #include "vcc_kernels.cuh"
+#include "mesh_interface.cuh"
 
 using namespace pgmo;
 
@@ -89,6 +90,7 @@ struct pgmo_vcc {
   DevBuf<uint64_t> d_remap;
   DevBuf<int64_t> d_keys;
   DevBuf<uint64_t> d_active_list;
+  VoxbloxStage vb_stage;
 
   ~pgmo_vcc() {
     for (auto& kv : blocks) delete kv.second;
@@ -422,6 +424,35 @@ int pgmo_vcc_integrate(pgmo_vcc_t* h, uint32_t n_blocks, const int32_t* block_id
   PGMO_TRY(integrateCore(h, n_blocks, block_idx_xyz, block_offsets, h->d_xyz.ptr,
                          rgba ? h->d_rgba.ptr : nullptr, stamp_s, h->d_remap.ptr,
                          keys_out ? h->d_keys.ptr : nullptr, st));
+  if (n_total) {
+    PGMO_CUDA(cudaMemcpyAsync(remap_out, h->d_remap.ptr, n_total * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    if (keys_out) {
+      PGMO_CUDA(cudaMemcpyAsync(keys_out, h->d_keys.ptr, 3 * n_total * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    }
+  }
+  return syncCounters(h, st);
+}
+
+int pgmo_vcc_integrate_voxblox(pgmo_vcc_t* h, uint32_t n_blocks, const int32_t* block_idx_xyz,
+                               const uint64_t* block_offsets, const uint16_t* x, const uint16_t* y,
+                               const uint16_t* z, const uint8_t* r, const uint8_t* g,
+                               const uint8_t* b, float block_edge_length, double stamp_s,
+                               uint64_t* remap_out, int64_t* keys_out) {
+  PGMO_CHECK_ARG(h != nullptr);
+  PGMO_CHECK_ARG(n_blocks == 0 || (block_idx_xyz && block_offsets));
+  PGMO_TRY(ensureDevice(h->device));
+  cudaStream_t st = h->stream;
+  const uint64_t n_total = n_blocks ? block_offsets[n_blocks] : 0;
+  PGMO_CHECK_ARG(n_total == 0 || remap_out);
+  PGMO_TRY(h->d_xyz.reserve(3 * n_total + 3));
+  PGMO_TRY(h->d_rgba.reserve(n_total + 1));
+  PGMO_TRY(h->d_remap.reserve(n_total + 1));
+  if (keys_out) PGMO_TRY(h->d_keys.reserve(3 * n_total + 3));
+  const VoxbloxInput in{x, y, z, r, g, b, block_edge_length};
+  PGMO_TRY(stageVoxblox(&h->vb_stage, n_blocks, block_idx_xyz, block_offsets, in, h->d_xyz.ptr,
+                        h->d_rgba.ptr, st));
+  PGMO_TRY(integrateCore(h, n_blocks, block_idx_xyz, block_offsets, h->d_xyz.ptr, h->d_rgba.ptr,
+                         stamp_s, h->d_remap.ptr, keys_out ? h->d_keys.ptr : nullptr, st));
   if (n_total) {
     PGMO_CUDA(cudaMemcpyAsync(remap_out, h->d_remap.ptr, n_total * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     if (keys_out) {

@@ -56,6 +56,8 @@ def load():
     lib.oracle_comp_remap_lookup.argtypes = [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_uint64]
     lib.oracle_comp_remap_block_size.restype = C.c_int64
     lib.oracle_comp_remap_block_size.argtypes = [_vp, C.c_int32, C.c_int32, C.c_int32]
+    lib.oracle_voxblox_decode.restype = None
+    lib.oracle_voxblox_decode.argtypes = [C.c_uint32] + [_vp] * 8 + [C.c_float, _vp, _vp]
     lib.oracle_stamp_from_sec.restype = C.c_uint64
     lib.oracle_stamp_from_sec.argtypes = [C.c_double]
     _lib = lib
@@ -225,3 +227,18 @@ def run_kat():
         build()
     p = subprocess.run([KAT_PATH], capture_output=True, text=True)
     return p.returncode, p.stdout + p.stderr
+
+
+def voxblox_decode(block_idx, offsets, x16, y16, z16, r, g, b, block_edge_length):
+    """VoxbloxMsgInterface::getActiveVertex for every vertex of every block -> (xyz f32, rgba)"""
+    lib = load()
+    bi = np.ascontiguousarray(block_idx, dtype=np.int32).reshape(-1, 3)
+    off = np.ascontiguousarray(offsets, dtype=np.uint64)
+    n = int(off[-1]) if off.shape[0] else 0
+    arrs = [np.ascontiguousarray(a, dtype=np.uint16) for a in (x16, y16, z16)]
+    cols = [np.ascontiguousarray(a, dtype=np.uint8) for a in (r, g, b)]
+    xyz = np.zeros((n, 3), dtype=np.float32)
+    rgba = np.zeros(n, dtype=np.uint32)
+    lib.oracle_voxblox_decode(bi.shape[0], _ptr(bi), _ptr(off), *[_ptr(a) for a in arrs],
+                              *[_ptr(a) for a in cols], float(block_edge_length), _ptr(xyz), _ptr(rgba))
+    return xyz, rgba

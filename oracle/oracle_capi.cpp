@@ -2,6 +2,7 @@
 // Flat C entry points over the CPU restatement so that tests/ and bench.py's cpu_baseline /
 // --impl reference legs can drive it through ctypes.  Never linked into the product library.
 #include <chrono>
+#include <limits>
 #include <cstring>
 #include <memory>
 
@@ -97,6 +98,26 @@ FlatBlockMesh makeMesh(uint32_t n_blocks, const int32_t* block_idx, const uint64
 }  // namespace
 
 extern "C" {
+
+// VoxbloxMsgInterface::getActiveVertex (kimera_pgmo_ros/src/voxblox_msg_interface.cpp:43-62):
+// vertex i of block b = (float(u16) * (2.0f / 65535) + float(block index)) * block_edge_length,
+// every operation in float (no FMA: the reference is built without -march=native), colour
+// (r, g, b, 255).  rgba uses PCL's packing: a << 24 | r << 16 | g << 8 | b.
+void oracle_voxblox_decode(uint32_t n_blocks, const int32_t* block_idx_xyz,
+                           const uint64_t* block_offsets, const uint16_t* x, const uint16_t* y,
+                           const uint16_t* z, const uint8_t* r, const uint8_t* g, const uint8_t* b,
+                           float block_edge_length, float* xyz, uint32_t* rgba) {
+  const float conv = 2.0f / std::numeric_limits<uint16_t>::max();
+  for (uint32_t blk = 0; blk < n_blocks; ++blk) {
+    const int32_t* index = block_idx_xyz + 3 * blk;
+    for (uint64_t i = block_offsets[blk]; i < block_offsets[blk + 1]; ++i) {
+      xyz[3 * i + 0] = (static_cast<float>(x[i]) * conv + static_cast<float>(index[0])) * block_edge_length;
+      xyz[3 * i + 1] = (static_cast<float>(y[i]) * conv + static_cast<float>(index[1])) * block_edge_length;
+      xyz[3 * i + 2] = (static_cast<float>(z[i]) * conv + static_cast<float>(index[2])) * block_edge_length;
+      rgba[i] = 0xFF000000u | (static_cast<uint32_t>(r[i]) << 16) | (static_cast<uint32_t>(g[i]) << 8) | b[i];
+    }
+  }
+}
 
 // deformation::deformPoints (mesh_deformation.h:63-213).  out_* must be pre-filled by the
 // caller (the reference leaves skipped vertices untouched); in-place (out == in) is allowed.

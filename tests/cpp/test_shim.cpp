@@ -474,6 +474,75 @@ static void testOctreeCompression() {
   EXPECT_EQ(13u, compression.getNumVertices());
 }
 
+// ------------------------------------------------------ VoxbloxMsgInterface
+// The packed path (u16 / u8 arrays uploaded as they are, getActiveVertex evaluated on the GPU)
+// must give exactly what the generic MeshInterface path gives for the same message.
+static void testVoxbloxInterface() {
+  VoxbloxMesh msg;
+  msg.block_edge_length = 0.8f;
+  uint32_t seed = 12345u;
+  auto next = [&seed]() {
+    seed = seed * 1664525u + 1013904223u;
+    return seed >> 8;
+  };
+  const int64_t indices[3][3] = {{0, 0, 0}, {-1, 2, 0}, {3, -4, 1}};
+  for (const auto& index : indices) {
+    VoxbloxMeshBlock blk;
+    for (int a = 0; a < 3; ++a) blk.index[a] = index[a];
+    for (int t = 0; t < 40; ++t) {
+      const uint32_t ax = next() % 30000, ay = next() % 30000, az = next() % 30000;
+      for (int v = 0; v < 3; ++v) {
+        blk.x.push_back(static_cast<uint16_t>(ax + next() % 5000));
+        blk.y.push_back(static_cast<uint16_t>(ay + next() % 5000));
+        blk.z.push_back(static_cast<uint16_t>(az + next() % 5000));
+        blk.r.push_back(static_cast<uint8_t>(next()));
+        blk.g.push_back(static_cast<uint8_t>(next()));
+        blk.b.push_back(static_cast<uint8_t>(next()));
+      }
+    }
+    msg.mesh_blocks.push_back(blk);
+  }
+  msg.mesh_blocks[0].x[0] = 0;
+  msg.mesh_blocks[0].y[0] = 65535;
+  const VoxbloxMsgInterface packed(msg);
+  OrderedBlockMesh generic;  // the same message through per-vertex getActiveVertex on the host
+  for (const auto& block : packed.blockIndices()) {
+    generic.order.push_back(block);
+    generic.blocks.emplace_back();
+    packed.markBlockActive(block);
+    for (size_t i = 0; i < packed.activeBlockSize(); ++i) {
+      generic.blocks.back().push_back(packed.getActiveVertex(i));
+    }
+  }
+  EXPECT_EQ(3u, packed.blockIndices().size());
+  EXPECT_EQ(120u, generic.blocks[1].size());
+  EXPECT_EQ(255, static_cast<int>(generic.blocks[0][0].a));
+  EXPECT_NEAR(1.6f, generic.blocks[0][0].y, 1e-6);  // 65535 * (2 / 65535) * edge
+  for (int rep = 0; rep < 2; ++rep) {
+    VoxelClearingCompression a(0.05), b(0.05);
+    pcl::PointCloud<pcl::PointXYZRGBA> v;
+    std::vector<pcl::Vertices> tri;
+    std::vector<size_t> ind;
+    HashedIndexMapping ra, rb;
+    a.compressAndIntegrate(packed, v, tri, ind, ra, 10.0 + rep);
+    b.compressAndIntegrate(generic, v, tri, ind, rb, 10.0 + rep);
+    EXPECT_EQ(ra.size(), rb.size());
+    for (const auto& kv : rb) {
+      EXPECT_TRUE(ra.count(kv.first) == 1 && ra.at(kv.first) == kv.second);
+    }
+    CompressionOutput oa(a), ob(b);
+    EXPECT_EQ(oa.vertices->size(), ob.vertices->size());
+    bool same = oa.vertices->size() == ob.vertices->size();
+    for (size_t i = 0; same && i < oa.vertices->size(); ++i) {
+      const auto& p = oa.vertices->at(i);
+      const auto& q = ob.vertices->at(i);
+      same = p.x == q.x && p.y == q.y && p.z == q.z && p.rgba == q.rgba;
+    }
+    EXPECT_TRUE(same);
+    EXPECT_TRUE(oa.vertices->size() > 100);
+  }
+}
+
 int main(int argc, char** argv) {
   const bool with_octree = argc > 1 && std::strcmp(argv[1], "--octree") == 0;
   if (pgmo_device_count() <= 0) {
@@ -486,6 +555,7 @@ int main(int argc, char** argv) {
   testDeformMeshCube();
   testIncrementalWithPredeform();
   testVoxelClearing();
+  testVoxbloxInterface();
   if (with_octree) testOctreeCompression();
   std::printf("shim tests: %d checks, %d failures\n", g_checks, g_failures);
   return g_failures ? 1 : 0;
