@@ -188,6 +188,30 @@ int pgmo_deform_mesh_device(pgmo_deform_t* h, uint64_t n_v, const void* d_vertic
                             void* d_out_xyzw, uint8_t* d_processed, uint64_t* n_resolved,
                             void* stream);
 
+/* KimeraPgmoMesh wire format (kimera_pgmo_msgs/msg/KimeraPgmoMesh.msg) <-> device cloud, i.e.
+ * conversions::fillFromMsg / fillMsg (kimera_pgmo_ros/.../conversion/mesh_conversion.h:69-199) on
+ * the GPU.  Host arrays are the message's own vectors: vertices_xyz = geometry_msgs/Point[]
+ * (3 doubles per vertex), colors_rgba = std_msgs/ColorRGBA[] (4 floats, optional),
+ * stamps_sec_nsec = time[] ({uint32 sec, uint32 nsec}, optional).  Device side: the 16-byte
+ * {x, y, z, rgba} records + u64 ns stamps of pgmo_deform_mesh_device.
+ *   to_cloud: x = float(p.x); byte = uint8(255.0f * c); stamp = sec * 1e9 + nsec; no colours:
+ *             (0, 0, 0, 255).  Stream-ordered; the host arrays are read asynchronously (pin them
+ *             or synchronise the stream before reusing them).
+ *   to_msg:   p.x = double(x); c = (1.0f / 255) * byte; sec = ns / 1e9, nsec = ns % 1e9.
+ *             Synchronises the stream before returning.
+ * pgmo_deform_mesh_msg = to_cloud -> pgmo_deform_mesh_device -> to_msg: the backend's
+ * optimizeFullMesh path from the received message to the message it publishes, vertices only
+ * (faces, colours, stamps and vertex_indices of the output message are those of the input). */
+int pgmo_deform_msg_to_cloud(pgmo_deform_t* h, uint64_t n_v, const double* vertices_xyz,
+                             const float* colors_rgba, const uint32_t* stamps_sec_nsec,
+                             void* d_cloud_xyzw, uint64_t* d_stamps_ns, void* stream);
+int pgmo_deform_cloud_to_msg(pgmo_deform_t* h, uint64_t n_v, const void* d_cloud_xyzw,
+                             const uint64_t* d_stamps_ns, double* vertices_xyz, float* colors_rgba,
+                             uint32_t* stamps_sec_nsec, void* stream);
+int pgmo_deform_mesh_msg(pgmo_deform_t* h, uint64_t n_v, const double* vertices_xyz,
+                         const uint32_t* stamps_sec_nsec, uint32_t k, double tol_t, int precision,
+                         double* out_vertices_xyz, uint8_t* processed);
+
 /* DeformationGraph::predeformPoints (deformation_graph.h:779-806): for i >= start_idx with
  * graph_indices[i] >= 0 and a valid pose: out[i] = float(R * (double(v_i) - g) + t); every other
  * i >= start_idx is appended to to_deform (ascending).  Host buffers.

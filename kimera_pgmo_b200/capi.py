@@ -60,6 +60,10 @@ SIGNATURES = {
     "pgmo_deform_run_device": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _vp, _vp, _vp, _vp, C.c_int,
                                          _vp, _vp, _vp, _vp, _vp, C.c_uint32, _vp, _vp, _vp, _vp]),
     "pgmo_deform_schedule_info": (C.c_int, [_vp, _u64p, C.c_uint64, _vp]),
+    "pgmo_deform_msg_to_cloud": (C.c_int, [_vp, C.c_uint64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pgmo_deform_cloud_to_msg": (C.c_int, [_vp, C.c_uint64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pgmo_deform_mesh_msg": (C.c_int, [_vp, C.c_uint64, _vp, _vp, C.c_uint32, C.c_double, C.c_int,
+                                       _vp, _vp]),
     "pgmo_deform_stamp_check_begin": (C.c_int, [_vp, C.c_uint64, _vp, _vp]),
     "pgmo_deform_stamp_check_finish": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "pgmo_deform_mesh_device": (C.c_int, [_vp, C.c_uint64, _vp, _vp, C.c_uint32, C.c_double,
@@ -280,6 +284,31 @@ class DeformHandle:
             _ptr(d_out_xyzw), _ptr(d_processed),
             C.cast(C.byref(resolved), _vp) if want_resolved else None, _vp(stream)))
         return rc, int(resolved.value)
+
+    def msg_to_cloud(self, vertices_xyz, colors_rgba, stamps_sec_nsec, d_cloud, d_stamps, stream=0):
+        v = np.ascontiguousarray(vertices_xyz, dtype=np.float64).reshape(-1, 3)
+        c = None if colors_rgba is None else np.ascontiguousarray(colors_rgba, dtype=np.float32).reshape(-1, 4)
+        t = None if stamps_sec_nsec is None else np.ascontiguousarray(stamps_sec_nsec, dtype=np.uint32).reshape(-1, 2)
+        _check(self._lib.pgmo_deform_msg_to_cloud(self._h, v.shape[0], _ptr(v), _ptr(c), _ptr(t),
+                                                  _ptr(d_cloud), _ptr(d_stamps), _vp(stream)))
+        return v, c, t  # keep the host arrays alive until the stream has consumed them
+
+    def cloud_to_msg(self, n_v, d_cloud, d_stamps, want_colors=True, stream=0):
+        v = np.zeros((n_v, 3), dtype=np.float64)
+        c = np.zeros((n_v, 4), dtype=np.float32) if want_colors else None
+        t = np.zeros((n_v, 2), dtype=np.uint32) if d_stamps is not None else None
+        _check(self._lib.pgmo_deform_cloud_to_msg(self._h, n_v, _ptr(d_cloud), _ptr(d_stamps), _ptr(v),
+                                                  _ptr(c), _ptr(t), _vp(stream)))
+        return v, c, t
+
+    def deform_mesh_msg(self, vertices_xyz, stamps_sec_nsec, k=4, tol_t=10.0, precision=FP64):
+        v = np.ascontiguousarray(vertices_xyz, dtype=np.float64).reshape(-1, 3)
+        t = None if stamps_sec_nsec is None else np.ascontiguousarray(stamps_sec_nsec, dtype=np.uint32).reshape(-1, 2)
+        out = np.zeros_like(v)
+        processed = np.zeros(v.shape[0], dtype=np.uint8)
+        rc = _check(self._lib.pgmo_deform_mesh_msg(self._h, v.shape[0], _ptr(v), _ptr(t), k, float(tol_t),
+                                                   precision, _ptr(out), _ptr(processed)))
+        return dict(rc=rc, vertices=out, processed=processed)
 
     def predeform(self, x, y, z, graph_indices, start_idx, out):
         x = np.ascontiguousarray(x, dtype=np.float32)

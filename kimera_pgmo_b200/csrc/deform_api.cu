@@ -96,6 +96,12 @@ struct pgmo_deform {
   DevBuf<uint8_t> d_assoc_cnt;
   DevBuf<int32_t> d_graph_idx;
   DevBuf<uint8_t> d_needs;
+  // KimeraPgmoMesh message staging (pgmo_deform_mesh_msg & co.)
+  DevBuf<double> d_msg_pts;
+  DevBuf<float> d_msg_colors;
+  DevBuf<uint32_t> d_msg_stamps;
+  DevBuf<float4> d_msg_cloud, d_msg_cloud_out;
+  DevBuf<uint64_t> d_msg_ns;
 };
 
 namespace {
@@ -1019,6 +1025,92 @@ int pgmo_deform_mesh_device(pgmo_deform_t* h, uint64_t n_v, const void* d_vertic
                                   status, n_resolved, st));
   PGMO_CUDA(launchSoaToAos(n_v, in, h->d_ox.ptr, h->d_oy.ptr, h->d_oz.ptr, status, out, st));
   return PGMO_OK;
+}
+
+int pgmo_deform_msg_to_cloud(pgmo_deform_t* h, uint64_t n_v, const double* vertices_xyz,
+                             const float* colors_rgba, const uint32_t* stamps_sec_nsec,
+                             void* d_cloud_xyzw, uint64_t* d_stamps_ns, void* stream) {
+  PGMO_CHECK_ARG(h != nullptr);
+  PGMO_TRY(ensureDevice(h->device));
+  if (n_v == 0) return PGMO_OK;
+  PGMO_CHECK_ARG(vertices_xyz != nullptr && d_cloud_xyzw != nullptr);
+  PGMO_CHECK_ARG(stamps_sec_nsec == nullptr || d_stamps_ns != nullptr);
+  cudaStream_t st = pick(h, stream);
+  PGMO_TRY(h->d_msg_pts.reserve(3 * n_v));
+  PGMO_CUDA(cudaMemcpyAsync(h->d_msg_pts.ptr, vertices_xyz, 3 * n_v * sizeof(double),
+                            cudaMemcpyHostToDevice, st));
+  if (colors_rgba) {
+    PGMO_TRY(h->d_msg_colors.reserve(4 * n_v));
+    PGMO_CUDA(cudaMemcpyAsync(h->d_msg_colors.ptr, colors_rgba, 4 * n_v * sizeof(float),
+                              cudaMemcpyHostToDevice, st));
+  }
+  if (stamps_sec_nsec) {
+    PGMO_TRY(h->d_msg_stamps.reserve(2 * n_v));
+    PGMO_CUDA(cudaMemcpyAsync(h->d_msg_stamps.ptr, stamps_sec_nsec, 2 * n_v * sizeof(uint32_t),
+                              cudaMemcpyHostToDevice, st));
+  }
+  PGMO_CUDA(launchMsgToCloud(n_v, h->d_msg_pts.ptr, colors_rgba ? h->d_msg_colors.ptr : nullptr,
+                             stamps_sec_nsec ? h->d_msg_stamps.ptr : nullptr,
+                             static_cast<float4*>(d_cloud_xyzw), d_stamps_ns, st));
+  return PGMO_OK;
+}
+
+int pgmo_deform_cloud_to_msg(pgmo_deform_t* h, uint64_t n_v, const void* d_cloud_xyzw,
+                             const uint64_t* d_stamps_ns, double* vertices_xyz, float* colors_rgba,
+                             uint32_t* stamps_sec_nsec, void* stream) {
+  PGMO_CHECK_ARG(h != nullptr);
+  PGMO_TRY(ensureDevice(h->device));
+  if (n_v == 0) return PGMO_OK;
+  PGMO_CHECK_ARG(vertices_xyz != nullptr && d_cloud_xyzw != nullptr);
+  PGMO_CHECK_ARG(stamps_sec_nsec == nullptr || d_stamps_ns != nullptr);
+  cudaStream_t st = pick(h, stream);
+  PGMO_TRY(h->d_msg_pts.reserve(3 * n_v));
+  if (colors_rgba) PGMO_TRY(h->d_msg_colors.reserve(4 * n_v));
+  if (stamps_sec_nsec) PGMO_TRY(h->d_msg_stamps.reserve(2 * n_v));
+  PGMO_CUDA(launchCloudToMsg(n_v, static_cast<const float4*>(d_cloud_xyzw), d_stamps_ns,
+                             h->d_msg_pts.ptr, colors_rgba ? h->d_msg_colors.ptr : nullptr,
+                             stamps_sec_nsec ? h->d_msg_stamps.ptr : nullptr, st));
+  PGMO_CUDA(cudaMemcpyAsync(vertices_xyz, h->d_msg_pts.ptr, 3 * n_v * sizeof(double),
+                            cudaMemcpyDeviceToHost, st));
+  if (colors_rgba) {
+    PGMO_CUDA(cudaMemcpyAsync(colors_rgba, h->d_msg_colors.ptr, 4 * n_v * sizeof(float),
+                              cudaMemcpyDeviceToHost, st));
+  }
+  if (stamps_sec_nsec) {
+    PGMO_CUDA(cudaMemcpyAsync(stamps_sec_nsec, h->d_msg_stamps.ptr, 2 * n_v * sizeof(uint32_t),
+                              cudaMemcpyDeviceToHost, st));
+  }
+  PGMO_CUDA(cudaStreamSynchronize(st));
+  return PGMO_OK;
+}
+
+int pgmo_deform_mesh_msg(pgmo_deform_t* h, uint64_t n_v, const double* vertices_xyz,
+                         const uint32_t* stamps_sec_nsec, uint32_t k, double tol_t, int precision,
+                         double* out_vertices_xyz, uint8_t* processed) {
+  PGMO_CHECK_ARG(h != nullptr);
+  PGMO_TRY(ensureDevice(h->device));
+  if (n_v == 0) return PGMO_NOOP;
+  PGMO_CHECK_ARG(vertices_xyz != nullptr && out_vertices_xyz != nullptr);
+  cudaStream_t st = h->stream;
+  PGMO_TRY(h->d_msg_cloud.reserve(n_v));
+  PGMO_TRY(h->d_msg_cloud_out.reserve(n_v));
+  if (stamps_sec_nsec) PGMO_TRY(h->d_msg_ns.reserve(n_v));
+  PGMO_TRY(pgmo_deform_msg_to_cloud(h, n_v, vertices_xyz, nullptr, stamps_sec_nsec,
+                                    h->d_msg_cloud.ptr, stamps_sec_nsec ? h->d_msg_ns.ptr : nullptr,
+                                    st));
+  PGMO_TRY(h->d_status.reserve(n_v));
+  const int rc = pgmo_deform_mesh_device(h, n_v, h->d_msg_cloud.ptr,
+                                         stamps_sec_nsec ? h->d_msg_ns.ptr : nullptr, k, tol_t,
+                                         precision, h->d_msg_cloud_out.ptr, h->d_status.ptr, nullptr, st);
+  if (rc != PGMO_OK) {
+    cudaStreamSynchronize(st);  // the caller's buffers must not be read any more
+    return rc;
+  }
+  if (processed) {
+    PGMO_CUDA(cudaMemcpyAsync(processed, h->d_status.ptr, n_v, cudaMemcpyDeviceToHost, st));
+  }
+  return pgmo_deform_cloud_to_msg(h, n_v, h->d_msg_cloud_out.ptr, nullptr, out_vertices_xyz, nullptr,
+                                  nullptr, st);
 }
 
 int pgmo_deform_predeform(pgmo_deform_t* h, uint64_t n_v, const float* x, const float* y,

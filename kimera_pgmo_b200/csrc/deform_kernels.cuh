@@ -142,6 +142,13 @@ cudaError_t launchSoaToAos(uint64_t n, const float4* in, const float* x, const f
                            const float* z, const uint8_t* status, float4* out,
                            cudaStream_t stream);
 
+// KimeraPgmoMesh message arrays <-> {x, y, z, rgba} records + u64 stamps (mesh_msg.cu)
+cudaError_t launchMsgToCloud(uint64_t n, const double* pts, const float* colors,
+                             const uint32_t* stamps2, float4* cloud, uint64_t* stamps,
+                             cudaStream_t stream);
+cudaError_t launchCloudToMsg(uint64_t n, const float4* cloud, const uint64_t* stamps, double* pts,
+                             float* colors, uint32_t* stamps2, cudaStream_t stream);
+
 cudaError_t launchPredeform(uint64_t n_v, uint64_t start_idx, const float* x, const float* y,
                             const float* z, const int32_t* graph_indices, uint64_t n_c,
                             const float4* ctrl_f4_valid, const uint8_t* valid,

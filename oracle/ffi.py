@@ -56,6 +56,10 @@ def load():
     lib.oracle_comp_remap_lookup.argtypes = [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_uint64]
     lib.oracle_comp_remap_block_size.restype = C.c_int64
     lib.oracle_comp_remap_block_size.argtypes = [_vp, C.c_int32, C.c_int32, C.c_int32]
+    lib.oracle_msg_to_cloud.restype = None
+    lib.oracle_msg_to_cloud.argtypes = [C.c_uint64] + [_vp] * 6
+    lib.oracle_cloud_to_msg.restype = None
+    lib.oracle_cloud_to_msg.argtypes = [C.c_uint64] + [_vp] * 6
     lib.oracle_voxblox_decode.restype = None
     lib.oracle_voxblox_decode.argtypes = [C.c_uint32] + [_vp] * 8 + [C.c_float, _vp, _vp]
     lib.oracle_stamp_from_sec.restype = C.c_uint64
@@ -242,3 +246,31 @@ def voxblox_decode(block_idx, offsets, x16, y16, z16, r, g, b, block_edge_length
     lib.oracle_voxblox_decode(bi.shape[0], _ptr(bi), _ptr(off), *[_ptr(a) for a in arrs],
                               *[_ptr(a) for a in cols], float(block_edge_length), _ptr(xyz), _ptr(rgba))
     return xyz, rgba
+
+
+def msg_to_cloud(vertices_xyz, colors_rgba, stamps_sec_nsec):
+    """conversions::fillFromMsg per vertex -> (xyz f32, rgba u32, stamps_ns u64 | None)"""
+    lib = load()
+    v = np.ascontiguousarray(vertices_xyz, dtype=np.float64).reshape(-1, 3)
+    c = None if colors_rgba is None else np.ascontiguousarray(colors_rgba, dtype=np.float32).reshape(-1, 4)
+    t = None if stamps_sec_nsec is None else np.ascontiguousarray(stamps_sec_nsec, dtype=np.uint32).reshape(-1, 2)
+    n = v.shape[0]
+    xyz = np.zeros((n, 3), dtype=np.float32)
+    rgba = np.zeros(n, dtype=np.uint32)
+    ns = np.zeros(n, dtype=np.uint64) if t is not None else None
+    lib.oracle_msg_to_cloud(n, _ptr(v), _ptr(c), _ptr(t), _ptr(xyz), _ptr(rgba), _ptr(ns))
+    return xyz, rgba, ns
+
+
+def cloud_to_msg(xyz, rgba, stamps_ns):
+    """conversions::fillMsg per vertex -> (vertices f64, colors f32 x 4, stamps {sec, nsec} | None)"""
+    lib = load()
+    p = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+    col = np.ascontiguousarray(rgba, dtype=np.uint32)
+    ns = None if stamps_ns is None else np.ascontiguousarray(stamps_ns, dtype=np.uint64)
+    n = p.shape[0]
+    v = np.zeros((n, 3), dtype=np.float64)
+    c = np.zeros((n, 4), dtype=np.float32)
+    t = np.zeros((n, 2), dtype=np.uint32) if ns is not None else None
+    lib.oracle_cloud_to_msg(n, _ptr(p), _ptr(col), _ptr(ns), _ptr(v), _ptr(c), _ptr(t))
+    return v, c, t

@@ -119,6 +119,54 @@ void oracle_voxblox_decode(uint32_t n_blocks, const int32_t* block_idx_xyz,
   }
 }
 
+// conversions::fillFromMsg (kimera_pgmo_ros/include/kimera_pgmo_ros/conversion/mesh_conversion.h:
+// 153-199) per vertex: Pos(p.x, p.y, p.z) narrows the doubles to float; colour bytes are
+// static_cast<uint8_t>(255.0f * c); stamp = ros::Time::toNSec() = sec * 1e9 + nsec.  Without
+// colours the point keeps pcl::PointXYZRGBA's default (0, 0, 0, 255).  rgba in PCL's packing.
+void oracle_msg_to_cloud(uint64_t n, const double* vertices_xyz, const float* colors_rgba,
+                         const uint32_t* stamps_sec_nsec, float* xyz, uint32_t* rgba,
+                         uint64_t* stamps_ns) {
+  constexpr float color_conv_factor = 1.0f * std::numeric_limits<uint8_t>::max();
+  for (uint64_t i = 0; i < n; ++i) {
+    for (int a = 0; a < 3; ++a) xyz[3 * i + a] = static_cast<float>(vertices_xyz[3 * i + a]);
+    uint32_t packed = 0xFF000000u;
+    if (colors_rgba) {
+      const float* c = colors_rgba + 4 * i;
+      const uint8_t r = static_cast<uint8_t>(color_conv_factor * c[0]);
+      const uint8_t g = static_cast<uint8_t>(color_conv_factor * c[1]);
+      const uint8_t b = static_cast<uint8_t>(color_conv_factor * c[2]);
+      const uint8_t al = static_cast<uint8_t>(color_conv_factor * c[3]);
+      packed = (static_cast<uint32_t>(al) << 24) | (static_cast<uint32_t>(r) << 16) |
+               (static_cast<uint32_t>(g) << 8) | b;
+    }
+    rgba[i] = packed;
+    if (stamps_sec_nsec && stamps_ns) {
+      stamps_ns[i] = static_cast<uint64_t>(stamps_sec_nsec[2 * i]) * 1000000000ull + stamps_sec_nsec[2 * i + 1];
+    }
+  }
+}
+
+// conversions::fillMsg (:69-139): p.x = pos.x(); colour = (1.0f / 255) * byte;
+// ros::Time::fromNSec: sec = ns / 1e9, nsec = ns % 1e9.
+void oracle_cloud_to_msg(uint64_t n, const float* xyz, const uint32_t* rgba, const uint64_t* stamps_ns,
+                         double* vertices_xyz, float* colors_rgba, uint32_t* stamps_sec_nsec) {
+  constexpr float color_conv_factor = 1.0f / std::numeric_limits<uint8_t>::max();
+  for (uint64_t i = 0; i < n; ++i) {
+    for (int a = 0; a < 3; ++a) vertices_xyz[3 * i + a] = xyz[3 * i + a];
+    if (colors_rgba && rgba) {
+      const uint32_t p = rgba[i];
+      colors_rgba[4 * i + 0] = color_conv_factor * static_cast<uint8_t>(p >> 16);
+      colors_rgba[4 * i + 1] = color_conv_factor * static_cast<uint8_t>(p >> 8);
+      colors_rgba[4 * i + 2] = color_conv_factor * static_cast<uint8_t>(p);
+      colors_rgba[4 * i + 3] = color_conv_factor * static_cast<uint8_t>(p >> 24);
+    }
+    if (stamps_sec_nsec && stamps_ns) {
+      stamps_sec_nsec[2 * i] = static_cast<uint32_t>(stamps_ns[i] / 1000000000ull);
+      stamps_sec_nsec[2 * i + 1] = static_cast<uint32_t>(stamps_ns[i] % 1000000000ull);
+    }
+  }
+}
+
 // deformation::deformPoints (mesh_deformation.h:63-213).  out_* must be pre-filled by the
 // caller (the reference leaves skipped vertices untouched); in-place (out == in) is allowed.
 // Returns 0 = ran, 1 = reference early return.  elapsed_s (optional) = time inside the call.
