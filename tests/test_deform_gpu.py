@@ -283,3 +283,17 @@ def test_config_c_slice_parity(capi, oracle, precision):
         else:
             np.testing.assert_allclose(gpu[ax].astype(np.float64), ref[ax].astype(np.float64),
                                        rtol=0, atol=FP32_TOL)
+
+
+@pytest.mark.parametrize("n_ctrl", [7, 126, 127, 128, 254, 255, 256, 257, 510, 511, 512, 513, 700])
+def test_alive_set_sizes_at_kernel_boundaries(capi, oracle, n_ctrl):
+    """Unstamped: one run whose alive set is exactly n_ctrl points — the staged / unstaged
+    variants of the list kernel (<= 256 / <= 512 points), the grid-walk kernel beyond, and every
+    width of the list-position field inside the 32-bit keys (7 to 10 bits)."""
+    case = synth.deformation_case(6_000, n_ctrl, ctrl_per_kf=n_ctrl, seed=100 + n_ctrl, ctrl_spread=9.0,
+                                  vertex_spread=11.0)
+    gpu, ref = _run_both(capi, oracle, case, 4, 10.0, stamped=False)
+    _compare(gpu, ref)
+    # a stamped sweep whose window holds the same set for every vertex
+    gpu, ref = _run_both(capi, oracle, case, 4, 1.0e6)
+    _compare(gpu, ref)
