@@ -153,13 +153,25 @@ octGrowKernel(OctFrames* F, const float4* __restrict__ xyz, const uint8_t* __res
     }
     __syncthreads();
     const bool defined = s_events > 0;
-    for (uint32_t i = cursor + threadIdx.x; i < n; i += blockDim.x) {
-      if (member && !member[i]) continue;
-      const float4 p = xyz[i];
-      if (!defined || outsideBox(s_frame, p.x, p.y, p.z)) {
-        atomicMin(&s_min, i);
-        break;  // this thread's indices ascend: the first hit is its minimum
+    // four independent loads in flight per thread: the scan is one CTA wide and latency-bound
+    for (uint32_t i0 = cursor + threadIdx.x; i0 < n; i0 += 4 * blockDim.x) {
+      float4 p[4];
+      bool m[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t i = i0 + u * blockDim.x;
+        m[u] = i < n && (!member || member[i]);
+        p[u] = i < n ? xyz[i] : make_float4(0.f, 0.f, 0.f, 0.f);
       }
+      bool hit = false;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (!hit && m[u] && (!defined || outsideBox(s_frame, p[u].x, p[u].y, p[u].z))) {
+          atomicMin(&s_min, i0 + u * blockDim.x);
+          hit = true;  // this thread's indices ascend: the first hit is its minimum
+        }
+      }
+      if (hit) break;
     }
     __syncthreads();
     const uint32_t m = s_min;
@@ -194,7 +206,10 @@ __device__ __forceinline__ int queryFrame(const OctFrames* F, uint32_t seq) {
 __global__ void __launch_bounds__(256)
 octInsertKernel(OctFrames* F, const OctTable t, const OctPoints pts,
                 const uint8_t* __restrict__ member, uint32_t first, uint32_t n, double res) {
-  const uint32_t i = first + blockIdx.x * blockDim.x + threadIdx.x;
+  // 8 lanes per point: lane l inserts the nodes at heights l, l + 8, ... (independent keys), so
+  // a point costs ceil(depth / 8) dependent atomic round trips instead of `depth`
+  const uint32_t i = first + ((blockIdx.x * blockDim.x + threadIdx.x) >> 3);
+  const int lane8 = threadIdx.x & 7;
   if (i >= n) return;
   if (member && !member[i]) return;
   const int e = insertionFrame(F, i);
@@ -205,9 +220,9 @@ octInsertKernel(OctFrames* F, const OctTable t, const OctPoints pts,
   const long long sx = static_cast<long long>(static_cast<uint32_t>((static_cast<double>(p.x) - fi.min[0]) / res)) - fi.shift[0];
   const long long sy = static_cast<long long>(static_cast<uint32_t>((static_cast<double>(p.y) - fi.min[1]) / res)) - fi.shift[1];
   const long long sz = static_cast<long long>(static_cast<uint32_t>((static_cast<double>(p.z) - fi.min[2]) / res)) - fi.shift[2];
-  pts.sigma[i] = make_int4(static_cast<int>(sx), static_cast<int>(sy), static_cast<int>(sz), 0);
+  if (lane8 == 0) pts.sigma[i] = make_int4(static_cast<int>(sx), static_cast<int>(sy), static_cast<int>(sz), 0);
   const int depth = static_cast<int>(F->f[F->n - 1].depth);
-  for (int h = 0; h < depth; ++h) {
+  for (int h = lane8; h < depth; h += 8) {
     unsigned long long key;
     if (!packKey(h, (sx + F->base[h][0]) >> h, (sy + F->base[h][1]) >> h,
                  (sz + F->base[h][2]) >> h, &key)) {
@@ -245,12 +260,18 @@ __global__ void octRootChainKernel(OctFrames* F, const OctTable t) {
 // OctreePointCloudSearch::approxNearestSearchRecursive on the implicit tree as of `limit_seq`:
 // per level the existing child with the strictly smallest voxel-centre distance (first child
 // index wins ties), at the leaf the point with the strictly smallest d^2 in insertion order.
+//
+// Eight lanes (an aligned octet of a warp) serve one query: lane c probes child c of the current
+// node, so a level costs one hash-probe latency instead of eight, and a 3-step shuffle picks the
+// winner (smallest distance, then smallest child index == the reference's `d >= best` scan in
+// child order).  All eight lanes of an octet take the same path; `octet_mask` names them.
 __device__ int approxNearest(const OctFrames* F, const OctFrame& fr, const OctTable& t,
                              const float4* __restrict__ pts, const uint32_t* __restrict__ next,
                              float qx, float qy, float qz, uint32_t limit_seq, double res,
-                             float* out_d2) {
+                             float* out_d2, unsigned octet_mask) {
   long long kx = 0, ky = 0, kz = 0;
   const int depth = static_cast<int>(fr.depth);
+  const int c = threadIdx.x & 7;
   uint32_t leaf_slot = kOctNone;
   for (int td = 1; td <= depth; ++td) {
     const int h = depth - td;
@@ -258,34 +279,46 @@ __device__ int approxNearest(const OctFrames* F, const OctFrame& fr, const OctTa
     const long long ox = (fr.shift[0] - F->base[h][0]) >> h;
     const long long oy = (fr.shift[1] - F->base[h][1]) >> h;
     const long long oz = (fr.shift[2] - F->base[h][2]) >> h;
-    double best = DBL_MAX;
-    int best_c = -1;
+    const long long nx = (kx << 1) + ((c >> 2) & 1);
+    const long long ny = (ky << 1) + ((c >> 1) & 1);
+    const long long nz = (kz << 1) + (c & 1);
+    double d = DBL_MAX;
+    int best_c = 8;  // 8 = this child does not exist
     uint32_t best_slot = kOctNone;
-    for (int c = 0; c < 8; ++c) {
-      const long long nx = (kx << 1) + ((c >> 2) & 1);
-      const long long ny = (ky << 1) + ((c >> 1) & 1);
-      const long long nz = (kz << 1) + (c & 1);
-      unsigned long long key;
-      if (!packKey(h, nx - ox, ny - oy, nz - oz, &key)) continue;
+    unsigned long long key;
+    if (packKey(h, nx - ox, ny - oy, nz - oz, &key)) {
       const uint32_t slot = tableFind(t, key);
-      if (slot == kOctNone || t.minseq[slot] >= limit_seq) continue;
-      // genVoxelCenterFromOctreeKey: double arithmetic, float result
-      const float cx = __double2float_rn(__dadd_rn(__dmul_rn(__dadd_rn(static_cast<double>(nx), 0.5), side), fr.min[0]));
-      const float cy = __double2float_rn(__dadd_rn(__dmul_rn(__dadd_rn(static_cast<double>(ny), 0.5), side), fr.min[1]));
-      const float cz = __double2float_rn(__dadd_rn(__dmul_rn(__dadd_rn(static_cast<double>(nz), 0.5), side), fr.min[2]));
-      const double d = static_cast<double>(dist2Exact(cx, cy, cz, qx, qy, qz));
-      if (d >= best) continue;
-      best = d;
-      best_c = c;
-      best_slot = slot;
+      if (slot != kOctNone && t.minseq[slot] < limit_seq) {
+        // genVoxelCenterFromOctreeKey: double arithmetic, float result
+        const float cx = __double2float_rn(__dadd_rn(__dmul_rn(__dadd_rn(static_cast<double>(nx), 0.5), side), fr.min[0]));
+        const float cy = __double2float_rn(__dadd_rn(__dmul_rn(__dadd_rn(static_cast<double>(ny), 0.5), side), fr.min[1]));
+        const float cz = __double2float_rn(__dadd_rn(__dmul_rn(__dadd_rn(static_cast<double>(nz), 0.5), side), fr.min[2]));
+        d = static_cast<double>(dist2Exact(cx, cy, cz, qx, qy, qz));
+        best_c = c;
+        best_slot = slot;
+      }
     }
-    if (best_c < 0) return -1;  // PCL asserts; unreachable below an existing root
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      const double od = __shfl_xor_sync(octet_mask, d, o, 8);
+      const int oc = __shfl_xor_sync(octet_mask, best_c, o, 8);
+      const uint32_t os = __shfl_xor_sync(octet_mask, best_slot, o, 8);
+      // an existing child always beats a missing one (DBL_MAX from a real distance cannot
+      // happen: float d^2 <= FLT_MAX); equal distances: the smaller child index
+      if (oc < 8 && (best_c == 8 || od < d || (od == d && oc < best_c))) {
+        d = od;
+        best_c = oc;
+        best_slot = os;
+      }
+    }
+    if (best_c == 8) return -1;  // PCL asserts; unreachable below an existing root
     kx = (kx << 1) + ((best_c >> 2) & 1);
     ky = (ky << 1) + ((best_c >> 1) & 1);
     kz = (kz << 1) + (best_c & 1);
     leaf_slot = best_slot;
   }
   if (leaf_slot == kOctNone) return -1;
+  // the leaf's few points: every lane of the octet walks the list (same addresses: broadcast)
   float smallest = FLT_MAX;
   uint32_t result = kOctNone;
   for (uint32_t j = t.head[leaf_slot]; j != kOctNone; j = next[j]) {
@@ -303,10 +336,10 @@ __device__ int approxNearest(const OctFrames* F, const OctFrame& fr, const OctTa
   return static_cast<int>(result);
 }
 
-// OctreeCompression::inOctree (octree_compression.cpp:17-40)
+// OctreeCompression::inOctree (octree_compression.cpp:17-40); called by all 8 lanes of an octet
 __device__ int inOctree(const OctFrames* F, int frame, const OctTable& t,
                         const float4* __restrict__ pts, const uint32_t* __restrict__ next, float qx,
-                        float qy, float qz, uint32_t limit_seq, double res) {
+                        float qy, float qz, uint32_t limit_seq, double res, unsigned octet_mask) {
   if (frame < 0) return -1;  // getLeafCount() == 0
   const OctFrame& fr = F->f[frame];
   const double px = qx, py = qy, pz = qz;
@@ -316,21 +349,24 @@ __device__ int inOctree(const OctFrames* F, int frame, const OctTable& t,
   const double threshold = __dmul_rn(res, res);
   float sqr_distance = static_cast<float>(threshold + 1.0);
   float d2 = 0.f;
-  const int idx = approxNearest(F, fr, t, pts, next, qx, qy, qz, limit_seq, res, &d2);
+  const int idx = approxNearest(F, fr, t, pts, next, qx, qy, qz, limit_seq, res, &d2, octet_mask);
   if (idx >= 0) sqr_distance = d2;
   if (static_cast<double>(sqr_distance) >= threshold) return -1;
   return idx;
 }
 
+__device__ __forceinline__ unsigned octetMask() { return 0xFFu << (threadIdx.x & 24); }
+
 __global__ void __launch_bounds__(128)
 octQueryPersistentKernel(const OctFrames* F, const OctTable t, const float4* __restrict__ act_xyz,
                          const uint32_t* __restrict__ next, const float* __restrict__ xyz,
                          uint32_t n, double res, int32_t* __restrict__ result) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;  // 8 lanes per query
+  if (i >= n) return;  // whole octets leave together
   const int frame = static_cast<int>(F->n) - 1;
-  result[i] = inOctree(F, frame, t, act_xyz, next, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2],
-                       kOctNone, res);
+  const int r = inOctree(F, frame, t, act_xyz, next, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2],
+                         kOctNone, res, octetMask());
+  if ((threadIdx.x & 7) == 0) result[i] = r;
 }
 
 __global__ void __launch_bounds__(128)
@@ -338,10 +374,11 @@ octDecideTempKernel(const OctFrames* F, const OctTable t, const float4* __restri
                     const uint32_t* __restrict__ next, uint32_t n_cand, double res,
                     const uint8_t* __restrict__ member_in, uint8_t* __restrict__ member_out,
                     int32_t* __restrict__ decision, uint32_t* __restrict__ changed) {
-  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;  // 8 lanes per candidate
   if (c >= n_cand) return;
   const float4 q = cand_xyz[c];
-  const int d = inOctree(F, queryFrame(F, c), t, cand_xyz, next, q.x, q.y, q.z, c, res);
+  const int d = inOctree(F, queryFrame(F, c), t, cand_xyz, next, q.x, q.y, q.z, c, res, octetMask());
+  if ((threadIdx.x & 7) != 0) return;
   decision[c] = d;
   const uint8_t m = d < 0 ? 1 : 0;
   member_out[c] = m;
@@ -446,7 +483,7 @@ cudaError_t launchOctInsert(OctFrames* frames, OctTable table, OctPoints pts,
                             const uint8_t* member, uint32_t first, uint32_t n, double resolution,
                             cudaStream_t stream) {
   if (first >= n) return cudaSuccess;
-  octInsertKernel<<<(n - first + 255) / 256, 256, 0, stream>>>(frames, table, pts, member, first, n,
+  octInsertKernel<<<(n - first + 31) / 32, 256, 0, stream>>>(frames, table, pts, member, first, n,
                                                                resolution);
   return cudaGetLastError();
 }
@@ -460,7 +497,7 @@ cudaError_t launchOctQueryPersistent(const OctFrames* frames, OctTable table, co
                                      const uint32_t* next, const float* xyz, uint32_t n,
                                      double resolution, int32_t* result, cudaStream_t stream) {
   if (n == 0) return cudaSuccess;
-  octQueryPersistentKernel<<<(n + 127) / 128, 128, 0, stream>>>(frames, table, act_xyz, next, xyz, n,
+  octQueryPersistentKernel<<<(n + 15) / 16, 128, 0, stream>>>(frames, table, act_xyz, next, xyz, n,
                                                                resolution, result);
   return cudaGetLastError();
 }
@@ -470,7 +507,7 @@ cudaError_t launchOctDecideTemp(const OctFrames* frames, OctTable table, const f
                                 const uint8_t* member_in, uint8_t* member_out, int32_t* decision,
                                 uint32_t* changed, cudaStream_t stream) {
   if (n_cand == 0) return cudaSuccess;
-  octDecideTempKernel<<<(n_cand + 127) / 128, 128, 0, stream>>>(
+  octDecideTempKernel<<<(n_cand + 15) / 16, 128, 0, stream>>>(
       frames, table, cand_xyz, next, n_cand, resolution, member_in, member_out, decision, changed);
   return cudaGetLastError();
 }
