@@ -56,6 +56,15 @@ def load():
     lib.oracle_comp_remap_lookup.argtypes = [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_uint64]
     lib.oracle_comp_remap_block_size.restype = C.c_int64
     lib.oracle_comp_remap_block_size.argtypes = [_vp, C.c_int32, C.c_int32, C.c_int32]
+    lib.oracle_delta_create.restype = _vp
+    lib.oracle_delta_create.argtypes = [C.c_double]
+    lib.oracle_delta_destroy.argtypes = [_vp]
+    lib.oracle_delta_update.restype = C.c_int
+    lib.oracle_delta_update.argtypes = [_vp, C.c_uint32, _vp, _vp, _vp, _vp, C.c_uint64, _vp, _vp]
+    lib.oracle_delta_archive_by_time.argtypes = [_vp, C.c_uint64]
+    lib.oracle_delta_archive_blocks.argtypes = [_vp, C.c_uint32, _vp]
+    lib.oracle_delta_sizes.argtypes = [_vp, _vp]
+    lib.oracle_delta_fetch.argtypes = [_vp] * 10
     lib.oracle_msg_to_cloud.restype = None
     lib.oracle_msg_to_cloud.argtypes = [C.c_uint64] + [_vp] * 6
     lib.oracle_cloud_to_msg.restype = None
@@ -274,3 +283,56 @@ def cloud_to_msg(xyz, rgba, stamps_ns):
     t = np.zeros((n, 2), dtype=np.uint32) if ns is not None else None
     lib.oracle_cloud_to_msg(n, _ptr(p), _ptr(col), _ptr(ns), _ptr(v), _ptr(c), _ptr(t))
     return v, c, t
+
+
+class DeltaCompression:
+    """kimera_pgmo::DeltaCompression (insertion-ordered containers, see oracle/delta_oracle.h)."""
+
+    def __init__(self, resolution):
+        self._lib = load()
+        self._h = _vp(self._lib.oracle_delta_create(float(resolution)))
+        self.elapsed_s = 0.0
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._lib.oracle_delta_destroy(self._h)
+            self._h = None
+
+    def update(self, block_idx, offsets, xyz, rgba, stamp_ns):
+        """-> (remap per input vertex, delta dict)"""
+        bi = np.ascontiguousarray(block_idx, dtype=np.int32).reshape(-1, 3)
+        off = np.ascontiguousarray(offsets, dtype=np.uint64)
+        pts = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+        col = None if rgba is None else np.ascontiguousarray(rgba, dtype=np.uint32)
+        remap = np.zeros(pts.shape[0], dtype=np.uint64)
+        elapsed = C.c_double(0.0)
+        rc = self._lib.oracle_delta_update(self._h, bi.shape[0], _ptr(bi), _ptr(off), _ptr(pts), _ptr(col),
+                                           int(stamp_ns), _ptr(remap), C.cast(C.byref(elapsed), _vp))
+        assert rc == 0, "the reference would have thrown"
+        self.elapsed_s = elapsed.value
+        return remap, self.delta()
+
+    def archive_by_time(self, earliest_ns):
+        self._lib.oracle_delta_archive_by_time(self._h, int(earliest_ns))
+
+    def archive_blocks(self, block_idx):
+        bi = np.ascontiguousarray(block_idx, dtype=np.int32).reshape(-1, 3)
+        self._lib.oracle_delta_archive_blocks(self._h, bi.shape[0], _ptr(bi))
+
+    def sizes(self):
+        s = np.zeros(12, dtype=np.uint64)
+        self._lib.oracle_delta_sizes(self._h, _ptr(s))
+        return [int(v) for v in s]
+
+    def delta(self):
+        s = self.sizes()
+        d = dict(vertex_start=s[0], face_start=s[1], num_archived_vertices=s[3],
+                 vertices=np.zeros((s[2], 3), np.float32), rgba=np.zeros(s[2], np.uint32),
+                 stamps=np.zeros(s[2], np.uint64), faces=np.zeros((s[4], 3), np.uint32),
+                 faces_archive=np.zeros((s[5], 3), np.uint32), prev_to_curr=np.zeros((s[6], 2), np.uint64),
+                 deleted=np.zeros(s[7], np.uint64), observed=np.zeros(s[8], np.uint64),
+                 new=np.zeros(s[9], np.uint64), active_voxels=s[10], pending_archived_faces=s[11])
+        self._lib.oracle_delta_fetch(self._h, _ptr(d["vertices"]), _ptr(d["rgba"]), _ptr(d["stamps"]),
+                                     _ptr(d["faces"]), _ptr(d["faces_archive"]), _ptr(d["prev_to_curr"]),
+                                     _ptr(d["deleted"]), _ptr(d["observed"]), _ptr(d["new"]))
+        return d

@@ -5,12 +5,16 @@
 
 int runDeformKats();
 int runCompressionKats();
+int runDeltaKats();
 
 int main() {
   runDeformKats();
   const int after_deform = kat::failures();
   runCompressionKats();
-  std::printf("oracle KAT: %d checks, %d failures (%d deformation, %d compression)\n",
-              kat::checks(), kat::failures(), after_deform, kat::failures() - after_deform);
+  const int after_compression = kat::failures();
+  runDeltaKats();
+  std::printf("oracle KAT: %d checks, %d failures (%d deformation, %d compression, %d delta compression)\n",
+              kat::checks(), kat::failures(), after_deform, after_compression - after_deform,
+              kat::failures() - after_compression);
   return kat::failures() ? 1 : 0;
 }

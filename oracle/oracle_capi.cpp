@@ -7,6 +7,7 @@
 #include <memory>
 
 #include "compression_oracle.h"
+#include "delta_oracle.h"
 #include "deform_oracle.h"
 
 using namespace pgmo_oracle;
@@ -98,6 +99,133 @@ FlatBlockMesh makeMesh(uint32_t n_blocks, const int32_t* block_idx, const uint64
 }  // namespace
 
 extern "C" {
+
+// ---- DeltaCompression (delta_oracle.h) ---------------------------------------------------------
+struct DeltaHandle {
+  explicit DeltaHandle(double res) : comp(res) {}
+  DeltaCompression comp;
+  std::shared_ptr<MeshDelta> last;
+};
+
+void* oracle_delta_create(double resolution) { return new DeltaHandle(resolution); }
+void oracle_delta_destroy(void* h) { delete static_cast<DeltaHandle*>(h); }
+
+// DeltaCompression::update.  remap_out: per input vertex the delta index written to
+// remapping[block][i].  Returns 0, or -1 if the reference would have thrown (.at()).
+int oracle_delta_update(void* hv, uint32_t n_blocks, const int32_t* block_idx_xyz,
+                        const uint64_t* block_offsets, const float* xyz, const uint32_t* rgba,
+                        uint64_t stamp_ns, uint64_t* remap_out, double* elapsed_s) {
+  DeltaHandle* h = static_cast<DeltaHandle*>(hv);
+  FlatBlockMesh mesh;
+  mesh.offsets.push_back(0);
+  for (uint32_t b = 0; b < n_blocks; ++b) {
+    mesh.blocks.push_back({block_idx_xyz[3 * b], block_idx_xyz[3 * b + 1], block_idx_xyz[3 * b + 2]});
+    for (uint64_t i = block_offsets[b]; i < block_offsets[b + 1]; ++i) {
+      PointXYZRGBA p;
+      p.x = xyz[3 * i];
+      p.y = xyz[3 * i + 1];
+      p.z = xyz[3 * i + 2];
+      p.rgba = rgba ? rgba[i] : 0xFF000000u;
+      mesh.vertices.push_back(p);
+    }
+    mesh.offsets.push_back(mesh.vertices.size());
+  }
+  std::vector<uint64_t> remap;
+  const auto t0 = std::chrono::steady_clock::now();
+  try {
+    h->last = h->comp.update(mesh, stamp_ns, &remap);
+  } catch (const std::out_of_range&) {
+    return -1;
+  }
+  const auto t1 = std::chrono::steady_clock::now();
+  if (elapsed_s) *elapsed_s = std::chrono::duration<double>(t1 - t0).count();
+  if (remap_out) std::copy(remap.begin(), remap.end(), remap_out);
+  return 0;
+}
+
+void oracle_delta_archive_by_time(void* hv, uint64_t earliest_ns) {
+  static_cast<DeltaHandle*>(hv)->comp.archiveBlocksByTime(earliest_ns);
+}
+
+void oracle_delta_archive_blocks(void* hv, uint32_t n_blocks, const int32_t* block_idx_xyz) {
+  BlockIndices blocks;
+  for (uint32_t b = 0; b < n_blocks; ++b) {
+    blocks.push_back({block_idx_xyz[3 * b], block_idx_xyz[3 * b + 1], block_idx_xyz[3 * b + 2]});
+  }
+  static_cast<DeltaHandle*>(hv)->comp.clearArchivedBlocks(blocks);
+}
+
+// sizes12: vertex_start, face_start, n vertices, n archived vertices, n faces, n archived faces,
+// n prev_to_curr, n deleted, n observed, n new, active voxels, pending archived faces
+void oracle_delta_sizes(void* hv, uint64_t* s) {
+  DeltaHandle* h = static_cast<DeltaHandle*>(hv);
+  for (int i = 0; i < 12; ++i) s[i] = 0;
+  if (h->last) {
+    const MeshDelta& d = *h->last;
+    s[0] = d.vertex_start;
+    s[1] = d.face_start;
+    s[2] = d.vertex_updates.size();
+    s[3] = d.num_archived_vertices;
+    s[4] = d.face_updates.size();
+    s[5] = d.face_archive_updates.size();
+    s[6] = d.prev_to_curr.size();
+    s[7] = d.deleted_indices.size();
+    s[8] = d.observed_indices.size();
+    s[9] = d.new_indices.size();
+  }
+  s[10] = h->comp.numActiveVertices();
+  s[11] = h->comp.numPendingArchivedFaces();
+}
+
+void oracle_delta_fetch(void* hv, float* xyz, uint32_t* rgba, uint64_t* stamps, uint32_t* faces,
+                        uint32_t* faces_archive, uint64_t* prev_to_curr2, uint64_t* deleted,
+                        uint64_t* observed, uint64_t* new_indices) {
+  DeltaHandle* h = static_cast<DeltaHandle*>(hv);
+  if (!h->last) return;
+  const MeshDelta& d = *h->last;
+  for (size_t i = 0; i < d.vertex_updates.size(); ++i) {
+    if (xyz) {
+      xyz[3 * i] = d.vertex_updates[i].x;
+      xyz[3 * i + 1] = d.vertex_updates[i].y;
+      xyz[3 * i + 2] = d.vertex_updates[i].z;
+    }
+    if (rgba) rgba[i] = d.vertex_updates[i].rgba;
+    if (stamps) stamps[i] = d.stamp_updates[i];
+  }
+  for (size_t i = 0; faces && i < d.face_updates.size(); ++i) {
+    faces[3 * i] = d.face_updates[i].v1;
+    faces[3 * i + 1] = d.face_updates[i].v2;
+    faces[3 * i + 2] = d.face_updates[i].v3;
+  }
+  for (size_t i = 0; faces_archive && i < d.face_archive_updates.size(); ++i) {
+    faces_archive[3 * i] = d.face_archive_updates[i].v1;
+    faces_archive[3 * i + 1] = d.face_archive_updates[i].v2;
+    faces_archive[3 * i + 2] = d.face_archive_updates[i].v3;
+  }
+  size_t k = 0;
+  for (const auto& kv : d.prev_to_curr) {
+    if (prev_to_curr2) {
+      prev_to_curr2[2 * k] = kv.first;
+      prev_to_curr2[2 * k + 1] = kv.second;
+    }
+    ++k;
+  }
+  k = 0;
+  for (const auto v : d.deleted_indices) {
+    if (deleted) deleted[k] = v;
+    ++k;
+  }
+  k = 0;
+  for (const auto v : d.observed_indices) {
+    if (observed) observed[k] = v;
+    ++k;
+  }
+  k = 0;
+  for (const auto v : d.new_indices) {
+    if (new_indices) new_indices[k] = v;
+    ++k;
+  }
+}
 
 // VoxbloxMsgInterface::getActiveVertex (kimera_pgmo_ros/src/voxblox_msg_interface.cpp:43-62):
 // vertex i of block b = (float(u16) * (2.0f / 65535) + float(block index)) * block_edge_length,

@@ -32,3 +32,27 @@ def test_deform_points_python_binding(oracle):
     np.testing.assert_allclose(r["z"], 0.0, atol=1e-9)
     assert r["processed"].all()
     assert (r["assoc_cnt"] == 5).all()  # k + 1 neighbours are blended
+
+
+def test_delta_compression_python_binding(oracle):
+    """DeltaCompression restatement through ctypes: a small stream with archival; structural
+    invariants of MeshDelta (mesh_delta.cpp:203-260 validate / checkFaces)."""
+    import numpy as np
+    from kimera_pgmo_b200 import synth
+
+    d = oracle.DeltaCompression(0.05)
+    total_archived = 0
+    for m, (blocks, offsets, xyz, rgba, t) in enumerate(synth.compression_stream(8, 3000, n_blocks=5)):
+        if m >= 3:
+            d.archive_by_time(int((t - 2.0) * 1e9))
+        remap, delta = d.update(blocks, offsets, xyz, rgba, int(t * 1e9))
+        assert delta["vertex_start"] == total_archived
+        total_archived += delta["num_archived_vertices"]
+        n_total = delta["vertex_start"] + delta["vertices"].shape[0]
+        assert remap.shape[0] == xyz.shape[0] and (remap < n_total).all()
+        assert (remap >= delta["vertex_start"] + delta["num_archived_vertices"]).all()  # active vertices
+        assert (delta["faces"] < n_total).all()
+        assert (delta["faces_archive"] < total_archived).all()
+        assert delta["active_voxels"] == delta["vertices"].shape[0] - delta["num_archived_vertices"]
+        assert np.array_equal(np.intersect1d(delta["new"], delta["observed"]), delta["new"])
+    assert total_archived > 0
