@@ -307,6 +307,42 @@ int pgmo_oct_last_outputs(pgmo_oct_t* h, float* new_vertices_xyz, uint32_t* new_
 int pgmo_oct_last_stats(pgmo_oct_t* h, uint64_t* stats4);
 
 /* ------------------------------------------------------------------------------------------
+ * DeltaCompression (kimera_pgmo/include/kimera_pgmo/compression/delta_compression.h:60-149,
+ * src/compression/delta_compression.cpp): the compressor Hydra drives.  One handle per object.
+ * Iteration order of the reference's unordered containers (vertices_map_, block_info_map_,
+ * BlockInfo::vertices) is implementation-defined there; here — as in oracle/delta_oracle.h — it
+ * is insertion order, so the order of the vertices inside a delta is "first observed first".
+ * ---------------------------------------------------------------------------------------- */
+typedef struct pgmo_delta pgmo_delta_t;
+
+int pgmo_delta_create(double resolution, int device, pgmo_delta_t** out);
+void pgmo_delta_destroy(pgmo_delta_t* h);
+/* MeshDelta::Ptr update(MeshInterface&, uint64_t timestamp_ns, HashedIndexMapping* remapping)
+ * (:211-259).  Mesh flattened as for pgmo_vcc_integrate (every block a multiple of 3 vertices).
+ * remap_out (optional, one per input vertex): the delta index remapping[block][i] receives.
+ * The resulting MeshDelta is read with pgmo_delta_sizes / pgmo_delta_fetch. */
+int pgmo_delta_update(pgmo_delta_t* h, uint32_t n_blocks, const int32_t* block_idx_xyz,
+                      const uint64_t* block_offsets, const float* xyz, const uint32_t* rgba,
+                      uint64_t timestamp_ns, uint64_t* remap_out);
+/* archiveBlocksByTime (:306-310) / clearArchivedBlocks (:312-316) */
+int pgmo_delta_archive_by_time(pgmo_delta_t* h, uint64_t earliest_time_ns);
+int pgmo_delta_archive_blocks(pgmo_delta_t* h, uint32_t n_blocks, const int32_t* block_idx_xyz);
+/* sizes12 = [vertex_start, face_start, vertex_updates.size(), archived vertices in the delta,
+ * face_updates.size(), face_archive_updates.size(), capacity for prev_to_curr, for deleted, for
+ * observed, for new, active voxels, archived_faces_.size()] of the last update. */
+int pgmo_delta_sizes(pgmo_delta_t* h, uint64_t* sizes12);
+/* The last MeshDelta (mesh_delta.h:65-150): vertex_updates (xyz, rgba) / stamp_updates,
+ * face_updates, face_archive_updates (3 u32 each), prev_to_curr as (key, value) pairs in key
+ * order, deleted / observed / new indices ascending; the n_* receive the actual counts.  Any
+ * pointer may be NULL. */
+int pgmo_delta_fetch(pgmo_delta_t* h, float* vertices_xyz, uint32_t* vertices_rgba, uint64_t* stamps_ns,
+                     uint32_t* faces, uint32_t* faces_archive, uint64_t* prev_to_curr2,
+                     uint64_t* n_prev_to_curr, uint64_t* deleted, uint64_t* n_deleted,
+                     uint64_t* observed, uint64_t* n_observed, uint64_t* new_indices, uint64_t* n_new);
+/* stats4 = [redundancy fixed-point rounds of the last call, voxel records, blocks, table size] */
+int pgmo_delta_last_stats(pgmo_delta_t* h, uint64_t* stats4);
+
+/* ------------------------------------------------------------------------------------------
  * MeshInterface inputs.  The integrate calls above take what MeshInterface::getActiveVertex
  * yields, flattened.  A voxblox mesh message (VoxbloxMsgInterface,
  * kimera_pgmo_ros/src/voxblox_msg_interface.cpp:11-62) stores u16 fixed-point coordinates per

@@ -90,6 +90,15 @@ SIGNATURES = {
     "pgmo_oct_last_outputs": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "pgmo_oct_last_stats": (C.c_int, [_vp, _vp]),
     "pgmo_oct_create_block": (C.c_int, [C.c_double, C.c_int, C.POINTER(_vp)]),
+    "pgmo_delta_create": (C.c_int, [C.c_double, C.c_int, C.POINTER(_vp)]),
+    "pgmo_delta_destroy": (None, [_vp]),
+    "pgmo_delta_update": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, C.c_uint64, _vp]),
+    "pgmo_delta_archive_by_time": (C.c_int, [_vp, C.c_uint64]),
+    "pgmo_delta_archive_blocks": (C.c_int, [_vp, C.c_uint32, _vp]),
+    "pgmo_delta_sizes": (C.c_int, [_vp, _vp]),
+    "pgmo_delta_fetch": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _u64p, _vp, _u64p, _vp, _u64p,
+                                   _vp, _u64p]),
+    "pgmo_delta_last_stats": (C.c_int, [_vp, _vp]),
     "pgmo_voxblox_decode": (C.c_int, [C.c_int, C.c_uint32] + [_vp] * 8 + [C.c_float, _vp, _vp]),
     "pgmo_vcc_integrate_voxblox": (C.c_int, [_vp, C.c_uint32] + [_vp] * 8 + [C.c_float, C.c_double,
                                                                           _vp, _vp]),
@@ -508,3 +517,65 @@ class OctHandle:
                                                _ptr(out["new_rgba"]), _ptr(out["new_triangles"]),
                                                _ptr(out["new_indices"])))
         return out
+
+
+class DeltaHandle:
+    """kimera_pgmo::DeltaCompression through the C ABI; same result dicts as
+    oracle.ffi.DeltaCompression."""
+
+    def __init__(self, resolution: float, device: int = 0):
+        self._lib = load()
+        h = _vp()
+        _check(self._lib.pgmo_delta_create(float(resolution), device, C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.pgmo_delta_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def update(self, block_idx, offsets, xyz, rgba, stamp_ns, fetch=True):
+        bi, off, pts, col = _flatten_blocks(block_idx, offsets, xyz, rgba)
+        remap = np.zeros(pts.shape[0], dtype=np.uint64)
+        _check(self._lib.pgmo_delta_update(self._h, bi.shape[0], _ptr(bi), _ptr(off), _ptr(pts), _ptr(col),
+                                           int(stamp_ns), _ptr(remap)))
+        return remap, (self.delta() if fetch else None)
+
+    def archive_by_time(self, earliest_ns):
+        _check(self._lib.pgmo_delta_archive_by_time(self._h, int(earliest_ns)))
+
+    def archive_blocks(self, block_idx):
+        bi = np.ascontiguousarray(block_idx, dtype=np.int32).reshape(-1, 3)
+        _check(self._lib.pgmo_delta_archive_blocks(self._h, bi.shape[0], _ptr(bi)))
+
+    def sizes(self):
+        s = np.zeros(12, dtype=np.uint64)
+        _check(self._lib.pgmo_delta_sizes(self._h, _ptr(s)))
+        return [int(v) for v in s]
+
+    def last_stats(self):
+        s = np.zeros(4, dtype=np.uint64)
+        _check(self._lib.pgmo_delta_last_stats(self._h, _ptr(s)))
+        return [int(v) for v in s]
+
+    def delta(self):
+        s = self.sizes()
+        d = dict(vertex_start=s[0], face_start=s[1], num_archived_vertices=s[3],
+                 vertices=np.zeros((s[2], 3), np.float32), rgba=np.zeros(s[2], np.uint32),
+                 stamps=np.zeros(s[2], np.uint64), faces=np.zeros((s[4], 3), np.uint32),
+                 faces_archive=np.zeros((s[5], 3), np.uint32), prev_to_curr=np.zeros((s[6], 2), np.uint64),
+                 deleted=np.zeros(s[7], np.uint64), observed=np.zeros(s[8], np.uint64),
+                 new=np.zeros(s[9], np.uint64), active_voxels=s[10], pending_archived_faces=s[11])
+        n = [C.c_uint64(0) for _ in range(4)]
+        _check(self._lib.pgmo_delta_fetch(
+            self._h, _ptr(d["vertices"]), _ptr(d["rgba"]), _ptr(d["stamps"]), _ptr(d["faces"]),
+            _ptr(d["faces_archive"]), _ptr(d["prev_to_curr"]), C.byref(n[0]), _ptr(d["deleted"]),
+            C.byref(n[1]), _ptr(d["observed"]), C.byref(n[2]), _ptr(d["new"]), C.byref(n[3])))
+        d["prev_to_curr"] = d["prev_to_curr"][: n[0].value]
+        d["deleted"] = d["deleted"][: n[1].value]
+        d["observed"] = d["observed"][: n[2].value]
+        d["new"] = d["new"][: n[3].value]
+        return d

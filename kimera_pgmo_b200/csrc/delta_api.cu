@@ -1,0 +1,684 @@
+// C ABI of DeltaCompression (pgmo_delta_*): host orchestration around delta_kernels.cu.
+//
+// kimera_pgmo::DeltaCompression::update / archiveBlocksByTime / clearArchivedBlocks
+// (kimera_pgmo/src/compression/delta_compression.cpp:211-360).  The host keeps what the
+// reference keeps per block (block_info_map_ in insertion order: update time, sequence number,
+// where the block's index list and voxel list live in the device pools); everything per vertex,
+// voxel and face runs on the GPU.  One private stream per handle, no CPU fallback.
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+#include "delta_kernels.cuh"
+
+using namespace pgmo;
+
+namespace {
+
+struct BlockRec {
+  int32_t idx[3];
+  uint64_t update_time_ns = 0;
+  uint32_t seq = 0;
+  uint32_t f_off = 0, f_n = 0;  // face pool segment (BlockInfo::indices)
+  uint32_t x_off = 0, x_cap = 0;  // voxel pool segment (BlockInfo::vertices), capacity
+  uint32_t cnt_slot = 0;          // where its voxel count lives on the device
+};
+
+using BlockKey = std::array<int32_t, 3>;
+
+}  // namespace
+
+struct pgmo_delta {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  double resolution = 0.0, index_scale = 0.0;
+
+  // voxel table + records
+  DevBuf<unsigned long long> t_keys, t_first;
+  DevBuf<uint32_t> t_vslot;
+  uint32_t t_cap = 0;
+  DevBuf<unsigned long long> r_key, r_stamp;
+  DevBuf<float4> r_point;
+  DevBuf<uint32_t> r_mesh_index, r_seq;
+  DevBuf<int32_t> r_refs;
+  DevBuf<uint8_t> r_needs_archive, r_is_new, r_alive;
+  uint64_t n_records = 0;  // exact after every call
+
+  // block_info_map_
+  std::vector<BlockRec> blocks;  // insertion order, erased ones removed
+  std::map<BlockKey, size_t> block_index;  // -> position in `blocks`
+  DevBuf<uint32_t> f_pool, x_pool, blk_counts;
+  uint64_t f_used = 0, x_used = 0, f_live = 0, x_live = 0;
+  std::vector<uint32_t> free_cnt_slots;
+  uint32_t next_cnt_slot = 0;
+
+  // archived_faces_
+  DevBuf<uint32_t> pending, pending2;
+  uint64_t n_pending = 0;
+
+  // delta under construction / last finished delta
+  bool delta_open = false;
+  uint32_t vertex_start = 0, face_start = 0, prev_total = 0;
+  DevBuf<float4> o_point;
+  DevBuf<unsigned long long> o_stamp;
+  DevBuf<uint8_t> o_new, o_obs, o_del;
+  DevBuf<uint32_t> o_p2c, o_faces_upd, o_faces_arch;
+  uint64_t d_arch = 0, d_vertices = 0, d_faces_upd = 0, d_faces_arch = 0;  // host mirrors
+  bool have_delta = false;
+
+  uint32_t seq = 1, pass = 0;
+  uint64_t num_archived_vertices = 0, num_archived_faces = 0, last_total = 0;
+
+  // scratch
+  DevBuf<float> d_xyz;
+  DevBuf<uint32_t> d_rgba, tslot_of_vertex, active_remapping, tiles, work_faces;
+  DevBuf<uint8_t> flags, valid, acc_a, acc_b, f1, f2;
+  DevBuf<unsigned long long> d_remap, e_keys, counters;
+  DevBuf<uint32_t> e_minseq;
+  DevBuf<DeltaFaceBlock> d_fblocks;
+  PinnedBuf<unsigned long long> h_counters;
+  uint32_t last_rounds = 0;
+};
+
+namespace {
+
+DeltaTable tableOf(pgmo_delta* h) {
+  return DeltaTable{h->t_keys.ptr, h->t_vslot.ptr, h->t_first.ptr, h->t_cap - 1};
+}
+DeltaRecords recordsOf(pgmo_delta* h) {
+  return DeltaRecords{h->r_key.ptr, h->r_point.ptr, h->r_stamp.ptr, h->r_mesh_index.ptr, h->r_seq.ptr,
+                      h->r_refs.ptr, h->r_needs_archive.ptr, h->r_is_new.ptr, h->r_alive.ptr};
+}
+DeltaOut outOf(pgmo_delta* h) {
+  DeltaOut o;
+  o.point = h->o_point.ptr;
+  o.stamp = h->o_stamp.ptr;
+  o.is_new = h->o_new.ptr;
+  o.observed = h->o_obs.ptr;
+  o.p2c = h->o_p2c.ptr;
+  o.deleted = h->o_del.ptr;
+  o.prev_total = h->prev_total;
+  o.vertex_start = h->vertex_start;
+  o.faces_upd = h->o_faces_upd.ptr;
+  o.faces_arch = h->o_faces_arch.ptr;
+  return o;
+}
+
+int reserveRecords(pgmo_delta* h, uint64_t n, cudaStream_t st) {
+  const uint64_t keep = h->n_records;
+  PGMO_TRY(h->r_key.reserve(n, st, keep));
+  PGMO_TRY(h->r_stamp.reserve(n, st, keep));
+  PGMO_TRY(h->r_point.reserve(n, st, keep));
+  PGMO_TRY(h->r_mesh_index.reserve(n, st, keep));
+  PGMO_TRY(h->r_seq.reserve(n, st, keep));
+  PGMO_TRY(h->r_refs.reserve(n, st, keep));
+  PGMO_TRY(h->r_needs_archive.reserve(n, st, keep));
+  PGMO_TRY(h->r_is_new.reserve(n, st, keep));
+  PGMO_TRY(h->r_alive.reserve(n, st, keep));
+  return PGMO_OK;
+}
+
+// table with room for `entries` keys at load <= 0.5; rebuilt from the alive records when it grows
+// (tombstones and the keys of erased records disappear)
+int ensureTable(pgmo_delta* h, uint64_t entries, cudaStream_t st) {
+  uint64_t want = 1024;
+  while (want < 2 * entries + 2) want <<= 1;
+  if (want <= h->t_cap) return PGMO_OK;
+  PGMO_CHECK_ARG(want <= (1ull << 31));
+  want <<= 1;  // head room: rebuilds are rare
+  h->t_keys.release();
+  h->t_first.release();
+  h->t_vslot.release();
+  PGMO_TRY(h->t_keys.reserve(want));
+  PGMO_TRY(h->t_first.reserve(want));
+  PGMO_TRY(h->t_vslot.reserve(want));
+  h->t_cap = static_cast<uint32_t>(want);
+  PGMO_CUDA(launchDeltaInitTable(tableOf(h), st));
+  PGMO_CUDA(launchDeltaRehash(tableOf(h), recordsOf(h), h->counters.ptr,
+                              static_cast<uint32_t>(h->n_records), h->counters.ptr, st));
+  return PGMO_OK;
+}
+
+int readCounters(pgmo_delta* h, cudaStream_t st) {
+  PGMO_CUDA(cudaMemcpyAsync(h->h_counters.ptr, h->counters.ptr, kDcCount * sizeof(unsigned long long),
+                            cudaMemcpyDeviceToHost, st));
+  PGMO_CUDA(cudaStreamSynchronize(st));
+  const unsigned long long err = h->h_counters.ptr[kDcError];
+  if (err) {
+    PGMO_CUDA(cudaMemsetAsync(h->counters.ptr + kDcError, 0, sizeof(unsigned long long), st));
+    if (err & 1ull) {
+      setLastError("delta compression: voxel key beyond +-2^20 voxels");
+      return PGMO_ERR_UNSUPPORTED;
+    }
+    if (err & 4ull) {
+      setLastError("delta compression: map lookup of a missing key (the reference's .at() throws)");
+      return PGMO_ERR_OUT_OF_RANGE;
+    }
+    setLastError("delta compression: voxel table full");
+    return PGMO_ERR_CUDA;
+  }
+  h->n_records = h->h_counters.ptr[kDcNumRecords];
+  h->d_arch = h->h_counters.ptr[kDcArchVerts];
+  h->d_faces_upd = h->h_counters.ptr[kDcFacesUpd];
+  h->d_faces_arch = h->h_counters.ptr[kDcFacesArch];
+  h->n_pending = h->h_counters.ptr[kDcPending];
+  return PGMO_OK;
+}
+
+// delta_.reset(new MeshDelta(num_archived_vertices_, num_archived_faces_)) (:217-222, :321-323)
+int openDelta(pgmo_delta* h, cudaStream_t st) {
+  if (h->delta_open) return PGMO_OK;
+  h->vertex_start = static_cast<uint32_t>(h->num_archived_vertices);
+  h->face_start = static_cast<uint32_t>(h->num_archived_faces);
+  h->prev_total = static_cast<uint32_t>(h->last_total);
+  PGMO_TRY(h->o_p2c.reserve(h->prev_total + 1));
+  PGMO_TRY(h->o_del.reserve(h->prev_total + 1));
+  PGMO_CUDA(cudaMemsetAsync(h->o_p2c.ptr, 0xFF, (h->prev_total + 1ull) * sizeof(uint32_t), st));
+  PGMO_CUDA(cudaMemsetAsync(h->o_del.ptr, 0, h->prev_total + 1ull, st));
+  PGMO_CUDA(cudaMemsetAsync(h->counters.ptr + kDcArchVerts, 0, 3 * sizeof(unsigned long long), st));
+  h->d_arch = h->d_faces_upd = h->d_faces_arch = 0;
+  h->delta_open = true;
+  h->have_delta = false;
+  return PGMO_OK;
+}
+
+int reserveOutVertices(pgmo_delta* h, uint64_t n, cudaStream_t st) {
+  PGMO_TRY(h->o_point.reserve(n, st, h->d_arch));
+  PGMO_TRY(h->o_stamp.reserve(n, st, h->d_arch));
+  return PGMO_OK;
+}
+
+int reserveTiles(pgmo_delta* h, uint64_t n) {
+  PGMO_TRY(h->tiles.reserve(deltaTileEntries(n)));
+  PGMO_TRY(h->flags.reserve((n / kDeltaTile + 1) * kDeltaTile));
+  return PGMO_OK;
+}
+
+// RedunancyChecker over the ordered work list: the unique fixed point of "a valid face is
+// accepted unless both of its first two edges come from faces accepted before it" is what the
+// sequential check()/add() loop computes; Jacobi rounds from "everything valid is accepted"
+// extend the correct prefix by at least one face each.
+int redundancyFixedPoint(pgmo_delta* h, const uint32_t* faces, const uint8_t* valid, uint32_t n_faces,
+                         const uint8_t** accepted, cudaStream_t st) {
+  *accepted = valid;
+  if (n_faces == 0) return PGMO_OK;
+  uint64_t cap = 1024;
+  while (cap < 8ull * n_faces) cap <<= 1;
+  PGMO_TRY(h->e_keys.reserve(cap));
+  PGMO_TRY(h->e_minseq.reserve(cap));
+  PGMO_TRY(h->acc_a.reserve(n_faces));
+  PGMO_TRY(h->acc_b.reserve(n_faces));
+  DeltaEdgeTable e{h->e_keys.ptr, h->e_minseq.ptr, static_cast<uint32_t>(cap - 1)};
+  PGMO_CUDA(cudaMemcpyAsync(h->acc_a.ptr, valid, n_faces, cudaMemcpyDeviceToDevice, st));
+  uint8_t* in = h->acc_a.ptr;
+  uint8_t* out = h->acc_b.ptr;
+  for (uint32_t round = 0;; ++round) {
+    PGMO_CUDA(launchDeltaEdgeRound(e, faces, valid, in, out, n_faces, h->counters.ptr, st));
+    PGMO_CUDA(cudaMemcpyAsync(h->h_counters.ptr + kDcChanged, h->counters.ptr + kDcChanged,
+                              sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    PGMO_CUDA(cudaStreamSynchronize(st));
+    ++h->last_rounds;
+    std::swap(in, out);
+    if (h->h_counters.ptr[kDcChanged] == 0) break;
+    if (round > n_faces + 2) {
+      setLastError("delta compression: redundancy check did not converge");
+      return PGMO_ERR_CUDA;
+    }
+  }
+  *accepted = in;
+  return PGMO_OK;
+}
+
+uint32_t allocCountSlot(pgmo_delta* h) {
+  if (!h->free_cnt_slots.empty()) {
+    const uint32_t s = h->free_cnt_slots.back();
+    h->free_cnt_slots.pop_back();
+    return s;
+  }
+  return h->next_cnt_slot++;
+}
+
+// drops the garbage of replaced / erased blocks from the two pools
+int compactPools(pgmo_delta* h, cudaStream_t st) {
+  if (h->f_used <= 2 * h->f_live + (1u << 16) && h->x_used <= 2 * h->x_live + (1u << 16)) return PGMO_OK;
+  DevBuf<uint32_t> nf, nx;
+  PGMO_TRY(nf.reserve(h->f_live + 1));
+  PGMO_TRY(nx.reserve(h->x_live + 1));
+  uint64_t f = 0, x = 0;
+  for (auto& b : h->blocks) {
+    if (b.f_n) PGMO_CUDA(cudaMemcpyAsync(nf.ptr + f, h->f_pool.ptr + b.f_off, b.f_n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    if (b.x_cap) PGMO_CUDA(cudaMemcpyAsync(nx.ptr + x, h->x_pool.ptr + b.x_off, b.x_cap * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    b.f_off = static_cast<uint32_t>(f);
+    b.x_off = static_cast<uint32_t>(x);
+    f += b.f_n;
+    x += b.x_cap;
+  }
+  PGMO_CUDA(cudaStreamSynchronize(st));
+  std::swap(h->f_pool.ptr, nf.ptr);
+  std::swap(h->f_pool.cap, nf.cap);
+  std::swap(h->x_pool.ptr, nx.ptr);
+  std::swap(h->x_pool.cap, nx.cap);
+  h->f_used = f;
+  h->x_used = x;
+  return PGMO_OK;
+}
+
+int archiveChosen(pgmo_delta* h, const std::vector<size_t>& chosen) {
+  cudaStream_t st = h->stream;
+  PGMO_TRY(openDelta(h, st));
+  if (chosen.empty()) return PGMO_OK;
+  // ---- vertex loop (:329-349), block by block in block_info_map_ order
+  uint64_t x_total = 0, f_total = 0;
+  for (const size_t bi : chosen) {
+    x_total += h->blocks[bi].x_cap;
+    f_total += h->blocks[bi].f_n / 3;
+  }
+  PGMO_TRY(reserveOutVertices(h, h->d_arch + x_total + 1, st));
+  for (const size_t bi : chosen) {
+    const BlockRec& b = h->blocks[bi];
+    PGMO_TRY(reserveTiles(h, b.x_cap));
+    PGMO_CUDA(launchDeltaRelease(tableOf(h), recordsOf(h), outOf(h), h->x_pool.ptr + b.x_off,
+                                 h->blk_counts.ptr + b.cnt_slot, b.x_cap, true, h->flags.ptr,
+                                 h->tiles.ptr, h->counters.ptr, st));
+  }
+  // ---- archiveBlockFaces over the chosen blocks with one shared checker (:351-356, :362-414)
+  const uint32_t T = static_cast<uint32_t>(f_total);
+  if (T > 0) {
+    std::vector<DeltaFaceBlock> fb;
+    uint32_t first = 0;
+    for (const size_t bi : chosen) {
+      const BlockRec& b = h->blocks[bi];
+      if (b.f_n < 3) continue;
+      fb.push_back(DeltaFaceBlock{b.f_off, b.f_n, first, -1});
+      first += b.f_n / 3;
+    }
+    PGMO_TRY(h->d_fblocks.reserve(fb.size()));
+    PGMO_CUDA(cudaMemcpyAsync(h->d_fblocks.ptr, fb.data(), fb.size() * sizeof(DeltaFaceBlock),
+                              cudaMemcpyHostToDevice, st));
+    PGMO_CUDA(cudaStreamSynchronize(st));  // fb is a stack vector
+    PGMO_TRY(h->work_faces.reserve(3ull * T));
+    PGMO_TRY(h->f1.reserve(T));
+    PGMO_TRY(h->f2.reserve(T));
+    PGMO_CUDA(launchDeltaArchiveFaces(h->d_fblocks.ptr, static_cast<uint32_t>(fb.size()), T, h->f_pool.ptr,
+                                      outOf(h), static_cast<uint32_t>(h->num_archived_vertices),
+                                      h->counters.ptr, h->work_faces.ptr, h->f1.ptr, h->f2.ptr, st));
+    const uint8_t* acc = nullptr;
+    PGMO_TRY(redundancyFixedPoint(h, h->work_faces.ptr, h->f2.ptr, T, &acc, st));
+    PGMO_TRY(reserveTiles(h, T));
+    PGMO_TRY(h->o_faces_arch.reserve(3 * (h->d_faces_arch + T) + 3, st, 3 * h->d_faces_arch));
+    PGMO_CUDA(launchDeltaAppendFaces(h->work_faces.ptr, acc, T, h->o_faces_arch.ptr,
+                                     h->counters.ptr + kDcFacesArch, h->tiles.ptr, st));
+    PGMO_TRY(h->pending.reserve(3 * (h->n_pending + T) + 3, st, 3 * h->n_pending));
+    PGMO_CUDA(launchDeltaAppendFaces(h->work_faces.ptr, h->f1.ptr, T, h->pending.ptr,
+                                     h->counters.ptr + kDcPending, h->tiles.ptr, st));
+  }
+  // ---- block_info_map_.erase(idx)
+  std::vector<char> dead(h->blocks.size(), 0);
+  for (const size_t bi : chosen) dead[bi] = 1;
+  std::vector<BlockRec> kept;
+  h->block_index.clear();
+  for (size_t i = 0; i < h->blocks.size(); ++i) {
+    const BlockRec& b = h->blocks[i];
+    if (dead[i]) {
+      h->free_cnt_slots.push_back(b.cnt_slot);
+      h->f_live -= b.f_n;
+      h->x_live -= b.x_cap;
+      continue;
+    }
+    h->block_index[BlockKey{b.idx[0], b.idx[1], b.idx[2]}] = kept.size();
+    kept.push_back(b);
+  }
+  h->blocks.swap(kept);
+  return readCounters(h, st);
+}
+
+}  // namespace
+
+extern "C" {
+
+int pgmo_delta_create(double resolution, int device, pgmo_delta_t** out) {
+  PGMO_CHECK_ARG(out != nullptr && resolution > 0.0);
+  *out = nullptr;
+  PGMO_TRY(ensureDevice(device));
+  pgmo_delta* h = new (std::nothrow) pgmo_delta();
+  PGMO_CHECK_ARG(h != nullptr);
+  h->device = device;
+  h->resolution = resolution;
+  h->index_scale = 1.0 / resolution;  // :49
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete h;
+    setLastError("cudaStreamCreate failed");
+    return PGMO_ERR_CUDA;
+  }
+  if (h->counters.reserve(kDcCount) < 0 || h->h_counters.reserve(kDcCount) < 0) {
+    delete h;
+    return PGMO_ERR_CUDA;
+  }
+  cudaMemsetAsync(h->counters.ptr, 0, kDcCount * sizeof(unsigned long long), h->stream);
+  *out = h;
+  return PGMO_OK;
+}
+
+void pgmo_delta_destroy(pgmo_delta_t* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) {
+    cudaStreamSynchronize(h->stream);
+    cudaStreamDestroy(h->stream);
+  }
+  delete h;
+}
+
+int pgmo_delta_update(pgmo_delta_t* h, uint32_t n_blocks, const int32_t* block_idx_xyz,
+                      const uint64_t* block_offsets, const float* xyz, const uint32_t* rgba,
+                      uint64_t timestamp_ns, uint64_t* remap_out) {
+  PGMO_CHECK_ARG(h != nullptr);
+  PGMO_CHECK_ARG(n_blocks == 0 || (block_idx_xyz && block_offsets));
+  PGMO_TRY(ensureDevice(h->device));
+  cudaStream_t st = h->stream;
+  const uint64_t n_total = n_blocks ? block_offsets[n_blocks] : 0;
+  PGMO_CHECK_ARG(n_total == 0 || xyz != nullptr);
+  PGMO_CHECK_ARG(n_total < 0x7FFFFFFFull);
+  for (uint32_t b = 0; b < n_blocks; ++b) {
+    if ((block_offsets[b + 1] - block_offsets[b]) % 3 != 0) {
+      setLastError("delta compression: a block's vertex count is not a multiple of 3 (Face::at throws)");
+      return PGMO_ERR_OUT_OF_RANGE;
+    }
+    for (uint32_t c = 0; c < b; ++c) {
+      if (std::memcmp(block_idx_xyz + 3 * b, block_idx_xyz + 3 * c, 3 * sizeof(int32_t)) == 0) {
+        setLastError("delta compression: a block index appears twice in one message");
+        return PGMO_ERR_UNSUPPORTED;
+      }
+    }
+  }
+  h->last_rounds = 0;
+  PGMO_TRY(openDelta(h, st));  // 1) archive delta, if any, is the starting point (:215-222)
+
+  // ---- inputs and capacities
+  PGMO_TRY(h->d_xyz.reserve(3 * n_total + 3));
+  PGMO_TRY(h->d_rgba.reserve(n_total + 1));
+  if (n_total) {
+    PGMO_CUDA(cudaMemcpyAsync(h->d_xyz.ptr, xyz, 3 * n_total * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (rgba) PGMO_CUDA(cudaMemcpyAsync(h->d_rgba.ptr, rgba, n_total * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  }
+  PGMO_TRY(reserveRecords(h, h->n_records + n_total + 1, st));
+  PGMO_TRY(ensureTable(h, h->n_records + n_total, st));
+  PGMO_TRY(h->tslot_of_vertex.reserve(n_total + 1));
+  PGMO_TRY(h->active_remapping.reserve(n_total + 1));
+  PGMO_TRY(h->d_remap.reserve(n_total + 1));
+  PGMO_CUDA(cudaMemsetAsync(h->d_remap.ptr, 0xFF, (n_total + 1) * sizeof(unsigned long long), st));
+  PGMO_CUDA(cudaMemsetAsync(h->counters.ptr + kDcActiveSlots, 0, sizeof(unsigned long long), st));
+  const uint64_t out_cap = h->d_arch + 2 * h->n_records + n_total + 1;
+  PGMO_TRY(reserveOutVertices(h, out_cap, st));
+  PGMO_TRY(h->o_new.reserve(out_cap));
+  PGMO_TRY(h->o_obs.reserve(out_cap));
+  PGMO_CUDA(cudaMemsetAsync(h->o_new.ptr, 0, out_cap, st));
+  PGMO_CUDA(cudaMemsetAsync(h->o_obs.ptr, 0, out_cap, st));
+
+  // ---- 2) updateRemapping (:261-296), block by block
+  std::vector<int64_t> msg_offset_of_block(h->blocks.size(), -1);
+  for (uint32_t b = 0; b < n_blocks; ++b) {
+    const uint32_t n_b = static_cast<uint32_t>(block_offsets[b + 1] - block_offsets[b]);
+    const BlockKey key{block_idx_xyz[3 * b], block_idx_xyz[3 * b + 1], block_idx_xyz[3 * b + 2]};
+    auto it = h->block_index.find(key);
+    const bool is_block_new = it == h->block_index.end();
+    if (is_block_new) {
+      BlockRec rec;
+      rec.idx[0] = key[0], rec.idx[1] = key[1], rec.idx[2] = key[2];
+      it = h->block_index.emplace(key, h->blocks.size()).first;
+      h->blocks.push_back(rec);
+      msg_offset_of_block.push_back(-1);
+    }
+    BlockRec& rec = h->blocks[it->second];
+    const BlockRec prev = rec;
+    msg_offset_of_block[it->second] = static_cast<int64_t>(block_offsets[b]);
+    rec.update_time_ns = timestamp_ns;
+    rec.seq = h->seq;
+    // new segments at the end of the pools (the old ones become garbage)
+    PGMO_TRY(h->f_pool.reserve(h->f_used + n_b + 1, st, h->f_used));
+    PGMO_TRY(h->x_pool.reserve(h->x_used + n_b + 1, st, h->x_used));
+    rec.f_off = static_cast<uint32_t>(h->f_used);
+    rec.f_n = n_b;
+    rec.x_off = static_cast<uint32_t>(h->x_used);
+    rec.x_cap = n_b;
+    rec.cnt_slot = allocCountSlot(h);
+    h->f_used += n_b;
+    h->x_used += n_b;
+    h->f_live += n_b;
+    h->x_live += n_b;
+    PGMO_TRY(h->blk_counts.reserve(h->next_cnt_slot + 1, st, h->next_cnt_slot));
+    PGMO_TRY(reserveTiles(h, std::max<uint64_t>(n_b, prev.x_cap)));
+
+    DeltaBlockArgs a;
+    a.xyz = h->d_xyz.ptr;
+    a.rgba = rgba ? h->d_rgba.ptr : nullptr;
+    a.first_vertex = block_offsets[b];
+    a.n = n_b;
+    a.index_scale = h->index_scale;
+    a.stamp_ns = timestamp_ns;
+    a.pass = ++h->pass;
+    a.seq = h->seq;
+    a.tslot_of_vertex = h->tslot_of_vertex.ptr;
+    a.face_map = h->f_pool.ptr + rec.f_off;
+    a.voxels = h->x_pool.ptr + rec.x_off;
+    a.voxel_count = h->blk_counts.ptr + rec.cnt_slot;
+    a.active_remapping = h->active_remapping.ptr;
+    PGMO_CUDA(launchDeltaAddBlock(tableOf(h), recordsOf(h), a, h->tiles.ptr, h->counters.ptr, st));
+    if (!is_block_new) {  // removeBlockObservations(block_info.vertices) (:291-293)
+      PGMO_CUDA(launchDeltaRelease(tableOf(h), recordsOf(h), outOf(h), h->x_pool.ptr + prev.x_off,
+                                   h->blk_counts.ptr + prev.cnt_slot, prev.x_cap, false, h->flags.ptr,
+                                   h->tiles.ptr, h->counters.ptr, st));
+      h->free_cnt_slots.push_back(prev.cnt_slot);
+      h->f_live -= prev.f_n;
+      h->x_live -= prev.x_cap;
+    }
+  }
+
+  // ---- 3) addActiveVertices (:128-154)
+  const uint64_t rec_upper = h->n_records + n_total;
+  PGMO_TRY(reserveTiles(h, rec_upper));
+  PGMO_CUDA(launchDeltaActiveVertices(recordsOf(h), outOf(h), static_cast<uint32_t>(rec_upper), h->seq,
+                                      h->active_remapping.ptr, h->tiles.ptr, h->counters.ptr, st));
+
+  // ---- addActiveFaces (:156-209): every face of every block in block_info_map_ order
+  std::vector<DeltaFaceBlock> fb;
+  uint32_t T = 0;
+  for (size_t i = 0; i < h->blocks.size(); ++i) {
+    const BlockRec& b = h->blocks[i];
+    if (b.f_n < 3) continue;
+    fb.push_back(DeltaFaceBlock{b.f_off, b.f_n, T, msg_offset_of_block[i]});
+    T += b.f_n / 3;
+  }
+  PGMO_TRY(h->o_faces_upd.reserve(3 * (static_cast<uint64_t>(T) + h->n_pending) + 3));
+  if (T > 0) {
+    PGMO_TRY(h->d_fblocks.reserve(fb.size()));
+    PGMO_CUDA(cudaMemcpyAsync(h->d_fblocks.ptr, fb.data(), fb.size() * sizeof(DeltaFaceBlock),
+                              cudaMemcpyHostToDevice, st));
+    PGMO_TRY(h->work_faces.reserve(3ull * T));
+    PGMO_TRY(h->valid.reserve(T));
+    PGMO_CUDA(launchDeltaRemapFaces(h->d_fblocks.ptr, static_cast<uint32_t>(fb.size()), T, h->f_pool.ptr,
+                                    h->active_remapping.ptr, outOf(h), h->d_remap.ptr,
+                                    h->work_faces.ptr, h->valid.ptr, h->counters.ptr, st));
+    const uint8_t* acc = nullptr;
+    PGMO_TRY(redundancyFixedPoint(h, h->work_faces.ptr, h->valid.ptr, T, &acc, st));  // syncs: fb is done
+    PGMO_TRY(reserveTiles(h, T));
+    PGMO_CUDA(launchDeltaAppendFaces(h->work_faces.ptr, acc, T, h->o_faces_upd.ptr,
+                                     h->counters.ptr + kDcFacesUpd, h->tiles.ptr, st));
+  }
+
+  // ---- 4) updateAndAddArchivedFaces (:416-446)
+  if (h->n_pending > 0) {
+    const uint32_t P = static_cast<uint32_t>(h->n_pending);
+    PGMO_TRY(h->valid.reserve(P));
+    PGMO_TRY(h->f1.reserve(P));
+    PGMO_TRY(h->f2.reserve(P));
+    PGMO_TRY(h->pending2.reserve(3ull * P + 3));
+    PGMO_CUDA(launchDeltaPendingRemap(h->pending.ptr, P, outOf(h),
+                                      static_cast<uint32_t>(h->num_archived_vertices), h->valid.ptr, st));
+    const uint8_t* acc = nullptr;
+    PGMO_TRY(redundancyFixedPoint(h, h->pending.ptr, h->valid.ptr, P, &acc, st));
+    PGMO_CUDA(launchDeltaClassifyPending(h->pending.ptr, acc, P, h->counters.ptr, outOf(h), h->f1.ptr,
+                                         h->f2.ptr, st));
+    PGMO_TRY(reserveTiles(h, P));
+    PGMO_TRY(h->o_faces_arch.reserve(3 * (h->d_faces_arch + P) + 3, st, 3 * h->d_faces_arch));
+    PGMO_CUDA(launchDeltaAppendFaces(h->pending.ptr, h->f1.ptr, P, h->o_faces_arch.ptr,
+                                     h->counters.ptr + kDcFacesArch, h->tiles.ptr, st));
+    PGMO_CUDA(launchDeltaAppendFaces(h->pending.ptr, h->f2.ptr, P, h->o_faces_upd.ptr,
+                                     h->counters.ptr + kDcFacesUpd, h->tiles.ptr, st));
+    PGMO_CUDA(cudaMemsetAsync(h->counters.ptr + kDcPending, 0, sizeof(unsigned long long), st));
+    PGMO_CUDA(launchDeltaAppendFaces(h->pending.ptr, h->f2.ptr, P, h->pending2.ptr,
+                                     h->counters.ptr + kDcPending, h->tiles.ptr, st));
+    std::swap(h->pending.ptr, h->pending2.ptr);
+    std::swap(h->pending.cap, h->pending2.cap);
+  }
+
+  // ---- 5) book-keeping (:245-257)
+  if (remap_out && n_total) {
+    PGMO_CUDA(cudaMemcpyAsync(remap_out, h->d_remap.ptr, n_total * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  }
+  PGMO_TRY(readCounters(h, st));
+  h->d_vertices = h->d_arch + h->h_counters.ptr[kDcScratch];
+  h->num_archived_vertices = h->vertex_start + h->d_arch;
+  h->num_archived_faces = h->face_start + h->d_faces_arch;
+  h->last_total = h->vertex_start + h->d_vertices;
+  h->seq = (h->seq + 1) & 0xFFFFu;
+  if (h->seq == 0) h->seq = 1;
+  h->delta_open = false;
+  h->have_delta = true;
+  return compactPools(h, st);
+}
+
+int pgmo_delta_archive_by_time(pgmo_delta_t* h, uint64_t earliest_time_ns) {
+  PGMO_CHECK_ARG(h != nullptr);
+  PGMO_TRY(ensureDevice(h->device));
+  std::vector<size_t> chosen;
+  for (size_t i = 0; i < h->blocks.size(); ++i) {
+    if (h->blocks[i].update_time_ns <= earliest_time_ns) chosen.push_back(i);  // :306-310
+  }
+  return archiveChosen(h, chosen);
+}
+
+int pgmo_delta_archive_blocks(pgmo_delta_t* h, uint32_t n_blocks, const int32_t* block_idx_xyz) {
+  PGMO_CHECK_ARG(h != nullptr && (n_blocks == 0 || block_idx_xyz != nullptr));
+  PGMO_TRY(ensureDevice(h->device));
+  std::vector<size_t> chosen;
+  for (size_t i = 0; i < h->blocks.size(); ++i) {
+    for (uint32_t b = 0; b < n_blocks; ++b) {
+      if (std::memcmp(h->blocks[i].idx, block_idx_xyz + 3 * b, 3 * sizeof(int32_t)) == 0) {
+        chosen.push_back(i);
+        break;
+      }
+    }
+  }
+  return archiveChosen(h, chosen);
+}
+
+int pgmo_delta_sizes(pgmo_delta_t* h, uint64_t* s) {
+  PGMO_CHECK_ARG(h != nullptr && s != nullptr);
+  for (int i = 0; i < 12; ++i) s[i] = 0;
+  if (h->have_delta) {
+    s[0] = h->vertex_start;
+    s[1] = h->face_start;
+    s[2] = h->d_vertices;
+    s[3] = h->d_arch;
+    s[4] = h->d_faces_upd;
+    s[5] = h->d_faces_arch;
+    s[6] = h->prev_total;  // capacity for prev_to_curr / deleted (their index space)
+    s[7] = h->prev_total;
+    s[8] = h->d_vertices;  // capacity for observed / new
+    s[9] = h->d_vertices;
+  }
+  s[10] = h->have_delta ? h->d_vertices - h->d_arch : 0;
+  s[11] = h->n_pending;
+  return PGMO_OK;
+}
+
+int pgmo_delta_fetch(pgmo_delta_t* h, float* vertices_xyz, uint32_t* vertices_rgba, uint64_t* stamps_ns,
+                     uint32_t* faces, uint32_t* faces_archive, uint64_t* prev_to_curr2,
+                     uint64_t* n_prev_to_curr, uint64_t* deleted, uint64_t* n_deleted,
+                     uint64_t* observed, uint64_t* n_observed, uint64_t* new_indices, uint64_t* n_new) {
+  PGMO_CHECK_ARG(h != nullptr);
+  PGMO_TRY(ensureDevice(h->device));
+  if (!h->have_delta) {
+    setLastError("pgmo_delta_fetch: no finished delta (call pgmo_delta_update)");
+    return PGMO_ERR_INVALID;
+  }
+  cudaStream_t st = h->stream;
+  const uint64_t nv = h->d_vertices;
+  std::vector<float4> pts(nv);
+  std::vector<uint8_t> f_new(nv), f_obs(nv), f_del(h->prev_total);
+  std::vector<uint32_t> p2c(h->prev_total);
+  if (nv) {
+    PGMO_CUDA(cudaMemcpyAsync(pts.data(), h->o_point.ptr, nv * sizeof(float4), cudaMemcpyDeviceToHost, st));
+    if (stamps_ns) PGMO_CUDA(cudaMemcpyAsync(stamps_ns, h->o_stamp.ptr, nv * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    PGMO_CUDA(cudaMemcpyAsync(f_new.data(), h->o_new.ptr, nv, cudaMemcpyDeviceToHost, st));
+    PGMO_CUDA(cudaMemcpyAsync(f_obs.data(), h->o_obs.ptr, nv, cudaMemcpyDeviceToHost, st));
+  }
+  if (h->prev_total) {
+    PGMO_CUDA(cudaMemcpyAsync(f_del.data(), h->o_del.ptr, h->prev_total, cudaMemcpyDeviceToHost, st));
+    PGMO_CUDA(cudaMemcpyAsync(p2c.data(), h->o_p2c.ptr, h->prev_total * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  }
+  if (faces && h->d_faces_upd) {
+    PGMO_CUDA(cudaMemcpyAsync(faces, h->o_faces_upd.ptr, 3 * h->d_faces_upd * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  }
+  if (faces_archive && h->d_faces_arch) {
+    PGMO_CUDA(cudaMemcpyAsync(faces_archive, h->o_faces_arch.ptr, 3 * h->d_faces_arch * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  }
+  PGMO_CUDA(cudaStreamSynchronize(st));
+  for (uint64_t i = 0; i < nv; ++i) {
+    if (vertices_xyz) {
+      vertices_xyz[3 * i] = pts[i].x;
+      vertices_xyz[3 * i + 1] = pts[i].y;
+      vertices_xyz[3 * i + 2] = pts[i].z;
+    }
+    if (vertices_rgba) std::memcpy(vertices_rgba + i, &pts[i].w, sizeof(uint32_t));
+  }
+  // std::map / std::set contents in key order
+  uint64_t k = 0;
+  for (uint64_t i = 0; i < h->prev_total; ++i) {
+    if (p2c[i] == kDeltaNone) continue;
+    if (prev_to_curr2) {
+      prev_to_curr2[2 * k] = i;
+      prev_to_curr2[2 * k + 1] = p2c[i];
+    }
+    ++k;
+  }
+  if (n_prev_to_curr) *n_prev_to_curr = k;
+  k = 0;
+  for (uint64_t i = 0; i < h->prev_total; ++i) {
+    if (!f_del[i]) continue;
+    if (deleted) deleted[k] = i;
+    ++k;
+  }
+  if (n_deleted) *n_deleted = k;
+  uint64_t ko = 0, kn = 0;
+  for (uint64_t i = 0; i < nv; ++i) {
+    if (f_obs[i]) {
+      if (observed) observed[ko] = h->vertex_start + i;
+      ++ko;
+    }
+    if (f_new[i]) {
+      if (new_indices) new_indices[kn] = h->vertex_start + i;
+      ++kn;
+    }
+  }
+  if (n_observed) *n_observed = ko;
+  if (n_new) *n_new = kn;
+  return PGMO_OK;
+}
+
+int pgmo_delta_last_stats(pgmo_delta_t* h, uint64_t* stats4) {
+  PGMO_CHECK_ARG(h != nullptr && stats4 != nullptr);
+  stats4[0] = h->last_rounds;
+  stats4[1] = h->n_records;
+  stats4[2] = h->blocks.size();
+  stats4[3] = h->t_cap;
+  return PGMO_OK;
+}
+
+}  // extern "C"
