@@ -600,6 +600,39 @@ def bench_compression(dev_index, n_messages=200, verts=50_000, with_cpu=True, n_
             cpu_ms = 1e3 * total / (n_octree - w2)
             out["octree"]["cpu_baseline"] = {"value": verts / (cpu_ms * 1e-3), "unit": "vertices/s",
                                              "cores": 1, "kind": "port", "ms_per_message": cpu_ms}
+    # DeltaCompression on the first n_octree messages: archiveBlocksByTime
+    # (t - 10 s) + update with host buffers, remap out; the MeshDelta stays on the device
+    # (fetching it is a separate call)
+    if n_octree > 0:
+        w2 = min(5, n_octree - 1)
+        for n_blocks in (1, 64):
+            dmsgs = msgs[:n_octree] if n_blocks == 1 else list(synth.compression_stream(n_octree, verts, n_blocks=n_blocks))
+            dc = capi.DeltaHandle(0.05, dev_index)
+            t0 = None
+            for m, (blocks, offsets, xyz, rgba, t) in enumerate(dmsgs):
+                if m == w2:
+                    t0 = time.perf_counter()
+                dc.archive_by_time(int((t - 10.0) * 1e9))
+                dc.update(blocks, offsets, xyz, rgba, int(t * 1e9), fetch=False)
+            d_ms = 1e3 * (time.perf_counter() - t0) / (n_octree - w2)
+            key = "delta" if n_blocks == 1 else "delta_64_blocks"
+            out[key] = {"value": verts / (d_ms * 1e-3), "unit": "vertices/s", "ms_per_message": d_ms,
+                        "api": "pgmo_delta_archive_by_time + pgmo_delta_update (host buffers)",
+                        "active_vertices": int(dc.sizes()[10])}
+            dc.close()
+            if with_cpu:
+                from oracle import ffi
+                ora = ffi.DeltaCompression(0.05)
+                total = 0.0
+                for m, (blocks, offsets, xyz, rgba, t) in enumerate(dmsgs):
+                    t1 = time.perf_counter()
+                    ora.archive_by_time(int((t - 10.0) * 1e9))
+                    ora.update(blocks, offsets, xyz, rgba, int(t * 1e9))
+                    if m >= w2:
+                        total += time.perf_counter() - t1
+                cpu_ms = 1e3 * total / (n_octree - w2)
+                out[key]["cpu_baseline"] = {"value": verts / (cpu_ms * 1e-3), "unit": "vertices/s",
+                                            "cores": 1, "kind": "port", "ms_per_message": cpu_ms}
     return out
 
 

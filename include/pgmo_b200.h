@@ -339,7 +339,8 @@ int pgmo_delta_fetch(pgmo_delta_t* h, float* vertices_xyz, uint32_t* vertices_rg
                      uint32_t* faces, uint32_t* faces_archive, uint64_t* prev_to_curr2,
                      uint64_t* n_prev_to_curr, uint64_t* deleted, uint64_t* n_deleted,
                      uint64_t* observed, uint64_t* n_observed, uint64_t* new_indices, uint64_t* n_new);
-/* stats4 = [redundancy fixed-point rounds of the last call, voxel records, blocks, table size] */
+/* stats4 = [redundancy fixed-point rounds of the last call, voxel records, blocks, record
+ * compactions so far] */
 int pgmo_delta_last_stats(pgmo_delta_t* h, uint64_t* stats4);
 
 /* ------------------------------------------------------------------------------------------

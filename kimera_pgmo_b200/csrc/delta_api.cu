@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <array>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <new>
@@ -48,6 +49,15 @@ struct pgmo_delta {
   DevBuf<int32_t> r_refs;
   DevBuf<uint8_t> r_needs_archive, r_is_new, r_alive;
   uint64_t n_records = 0;  // exact after every call
+  DevBuf<uint32_t> new_id;
+  // second record buffer set: compaction target, then swapped in (no allocation in steady state)
+  DevBuf<unsigned long long> s_key, s_stamp;
+  DevBuf<float4> s_point;
+  DevBuf<uint32_t> s_mesh_index, s_seq;
+  DevBuf<int32_t> s_refs;
+  DevBuf<uint8_t> s_needs_archive, s_is_new, s_alive;
+  uint64_t record_compactions = 0;
+  uint64_t compact_slack = 1u << 19;  // PGMO_DELTA_COMPACT_SLACK: erased records tolerated
 
   // block_info_map_
   std::vector<BlockRec> blocks;  // insertion order, erased ones removed
@@ -245,7 +255,9 @@ uint32_t allocCountSlot(pgmo_delta* h) {
 
 // drops the garbage of replaced / erased blocks from the two pools
 int compactPools(pgmo_delta* h, cudaStream_t st) {
-  if (h->f_used <= 2 * h->f_live + (1u << 16) && h->x_used <= 2 * h->x_live + (1u << 16)) return PGMO_OK;
+  if (h->f_used <= 2 * h->f_live + h->compact_slack && h->x_used <= 2 * h->x_live + h->compact_slack) {
+    return PGMO_OK;
+  }
   DevBuf<uint32_t> nf, nx;
   PGMO_TRY(nf.reserve(h->f_live + 1));
   PGMO_TRY(nx.reserve(h->x_live + 1));
@@ -266,6 +278,59 @@ int compactPools(pgmo_delta* h, cudaStream_t st) {
   h->f_used = f;
   h->x_used = x;
   return PGMO_OK;
+}
+
+// Drops the erased voxel records (they only accumulate: every voxel that leaves the mesh and
+// comes back is a new insertion) once they outnumber the alive ones.
+int compactRecords(pgmo_delta* h, uint64_t alive, cudaStream_t st) {
+  if (h->n_records <= 2 * alive + h->compact_slack) return PGMO_OK;
+  const uint64_t n_old = h->n_records;
+  auto& key = h->s_key;
+  auto& stamp = h->s_stamp;
+  auto& point = h->s_point;
+  auto& mesh_index = h->s_mesh_index;
+  auto& seq = h->s_seq;
+  auto& refs = h->s_refs;
+  auto& needs_archive = h->s_needs_archive;
+  auto& is_new = h->s_is_new;
+  auto& alive_flag = h->s_alive;
+  const uint64_t cap = std::max<uint64_t>(alive + 1, h->r_key.cap);  // as roomy as the live set
+  PGMO_TRY(key.reserve(cap));
+  PGMO_TRY(stamp.reserve(cap));
+  PGMO_TRY(point.reserve(cap));
+  PGMO_TRY(mesh_index.reserve(cap));
+  PGMO_TRY(seq.reserve(cap));
+  PGMO_TRY(refs.reserve(cap));
+  PGMO_TRY(needs_archive.reserve(cap));
+  PGMO_TRY(is_new.reserve(cap));
+  PGMO_TRY(alive_flag.reserve(cap));
+  PGMO_TRY(h->new_id.reserve(n_old + 1));
+  PGMO_TRY(reserveTiles(h, n_old));
+  const DeltaRecords to{key.ptr, point.ptr, stamp.ptr, mesh_index.ptr, seq.ptr,
+                        refs.ptr, needs_archive.ptr, is_new.ptr, alive_flag.ptr};
+  PGMO_CUDA(launchDeltaCompactRecords(recordsOf(h), to, static_cast<uint32_t>(n_old), h->new_id.ptr,
+                                      h->x_pool.ptr, h->x_used, h->tiles.ptr, h->counters.ptr, st));
+  PGMO_CUDA(cudaStreamSynchronize(st));
+  auto swapBuf = [](auto& a, auto& b) {
+    std::swap(a.ptr, b.ptr);
+    std::swap(a.cap, b.cap);
+  };
+  swapBuf(h->r_key, key);
+  swapBuf(h->r_stamp, stamp);
+  swapBuf(h->r_point, point);
+  swapBuf(h->r_mesh_index, mesh_index);
+  swapBuf(h->r_seq, seq);
+  swapBuf(h->r_refs, refs);
+  swapBuf(h->r_needs_archive, needs_archive);
+  swapBuf(h->r_is_new, is_new);
+  swapBuf(h->r_alive, alive_flag);
+  h->n_records = alive;
+  ++h->record_compactions;
+  // fresh table over the compacted records (same capacity: tombstones are gone)
+  PGMO_CUDA(launchDeltaInitTable(tableOf(h), st));
+  PGMO_CUDA(launchDeltaRehash(tableOf(h), recordsOf(h), h->counters.ptr, static_cast<uint32_t>(alive),
+                              h->counters.ptr, st));
+  return readCounters(h, st);
 }
 
 int archiveChosen(pgmo_delta* h, const std::vector<size_t>& chosen) {
@@ -350,6 +415,7 @@ int pgmo_delta_create(double resolution, int device, pgmo_delta_t** out) {
   h->device = device;
   h->resolution = resolution;
   h->index_scale = 1.0 / resolution;  // :49
+  if (const char* e = std::getenv("PGMO_DELTA_COMPACT_SLACK")) h->compact_slack = std::strtoull(e, nullptr, 10);
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete h;
     setLastError("cudaStreamCreate failed");
@@ -468,11 +534,20 @@ int pgmo_delta_update(pgmo_delta_t* h, uint32_t n_blocks, const int32_t* block_i
     a.voxels = h->x_pool.ptr + rec.x_off;
     a.voxel_count = h->blk_counts.ptr + rec.cnt_slot;
     a.active_remapping = h->active_remapping.ptr;
-    PGMO_CUDA(launchDeltaAddBlock(tableOf(h), recordsOf(h), a, h->tiles.ptr, h->counters.ptr, st));
-    if (!is_block_new) {  // removeBlockObservations(block_info.vertices) (:291-293)
-      PGMO_CUDA(launchDeltaRelease(tableOf(h), recordsOf(h), outOf(h), h->x_pool.ptr + prev.x_off,
-                                   h->blk_counts.ptr + prev.cnt_slot, prev.x_cap, false, h->flags.ptr,
-                                   h->tiles.ptr, h->counters.ptr, st));
+    if (n_b <= static_cast<uint32_t>(kDeltaTile) && prev.x_cap <= static_cast<uint32_t>(kDeltaTile)) {
+      PGMO_CUDA(launchDeltaSmallBlock(tableOf(h), recordsOf(h), outOf(h), a,
+                                      is_block_new ? nullptr : h->x_pool.ptr + prev.x_off,
+                                      is_block_new ? nullptr : h->blk_counts.ptr + prev.cnt_slot,
+                                      h->counters.ptr, st));
+    } else {
+      PGMO_CUDA(launchDeltaAddBlock(tableOf(h), recordsOf(h), a, h->tiles.ptr, h->counters.ptr, st));
+      if (!is_block_new) {  // removeBlockObservations(block_info.vertices) (:291-293)
+        PGMO_CUDA(launchDeltaRelease(tableOf(h), recordsOf(h), outOf(h), h->x_pool.ptr + prev.x_off,
+                                     h->blk_counts.ptr + prev.cnt_slot, prev.x_cap, false, h->flags.ptr,
+                                     h->tiles.ptr, h->counters.ptr, st));
+      }
+    }
+    if (!is_block_new) {
       h->free_cnt_slots.push_back(prev.cnt_slot);
       h->f_live -= prev.f_n;
       h->x_live -= prev.x_cap;
@@ -550,7 +625,8 @@ int pgmo_delta_update(pgmo_delta_t* h, uint32_t n_blocks, const int32_t* block_i
   if (h->seq == 0) h->seq = 1;
   h->delta_open = false;
   h->have_delta = true;
-  return compactPools(h, st);
+  PGMO_TRY(compactPools(h, st));
+  return compactRecords(h, h->d_vertices - h->d_arch, st);
 }
 
 int pgmo_delta_archive_by_time(pgmo_delta_t* h, uint64_t earliest_time_ns) {
@@ -677,7 +753,7 @@ int pgmo_delta_last_stats(pgmo_delta_t* h, uint64_t* stats4) {
   stats4[0] = h->last_rounds;
   stats4[1] = h->n_records;
   stats4[2] = h->blocks.size();
-  stats4[3] = h->t_cap;
+  stats4[3] = h->record_compactions;
   return PGMO_OK;
 }
 

@@ -126,17 +126,26 @@ __device__ __forceinline__ uint32_t field(unsigned long long w, int k) {
 // tiles: 3 u32 per tile.  Turns per-tile counts into exclusive offsets, writes the old values of
 // the three target counters (the bases) to base_out[0..2] and adds the totals to them; a null
 // target keeps a private count (base 0).  totals_out (optional) receives the three totals.
+// One warp per field, 32 tiles per step.
 __global__ void scanTiles3Kernel(uint32_t* tiles, uint32_t n_tiles, unsigned long long* c0,
                                  unsigned long long* c1, unsigned long long* c2,
                                  uint32_t* base_out, unsigned long long* totals_out) {
-  const int k = threadIdx.x;
+  const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (k >= 3) return;
   uint32_t run = 0;
-  for (uint32_t t = 0; t < n_tiles; ++t) {
-    const uint32_t c = tiles[3 * t + k];
-    tiles[3 * t + k] = run;
-    run += c;
+  for (uint32_t t0 = 0; t0 < n_tiles; t0 += 32) {
+    const uint32_t t = t0 + lane;
+    const uint32_t c = t < n_tiles ? tiles[3 * t + k] : 0u;
+    uint32_t incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if (lane >= o) incl += up;
+    }
+    if (t < n_tiles) tiles[3 * t + k] = run + incl - c;
+    run += __shfl_sync(0xFFFFFFFFu, incl, 31);
   }
+  if (lane != 0) return;
   unsigned long long* target = k == 0 ? c0 : (k == 1 ? c1 : c2);
   uint32_t base = 0;
   if (target) {
@@ -533,6 +542,152 @@ archiveFacesKernel(const DeltaFaceBlock* __restrict__ blocks, uint32_t n_blocks,
   candidate[f] = cand ? 1 : 0;
 }
 
+// ---------------------------------------------------------------------------------- small blocks
+// A voxblox-like message is dozens of blocks of a few hundred vertices.  For a block (and its
+// previous voxel list) of at most 1024 entries one CTA does the whole of updateRemapping's body
+// — addPoint for every vertex, then removeBlockObservations — in a single launch; the phases
+// are the kernels above, separated by __syncthreads() instead of launch boundaries.
+__global__ void __launch_bounds__(kDeltaTile)
+smallBlockKernel(const DeltaTable t, const DeltaRecords r, const DeltaOut o, const DeltaBlockArgs b,
+                 const uint32_t* __restrict__ prev_voxels, const uint32_t* __restrict__ prev_count,
+                 unsigned long long* counters) {
+  const uint32_t i = threadIdx.x;
+  // ---- addPoint: hash insert + first occurrence
+  if (i < b.n) {
+    const uint64_t v = b.first_vertex + i;
+    unsigned long long key;
+    uint32_t slot = kDeltaNone;
+    if (!voxelKey(b.xyz, v, b.index_scale, &key)) {
+      atomicOr(counters + kDcError, 1ull);
+    } else if (!findOrInsert(t, key, &slot)) {
+      atomicOr(counters + kDcError, 2ull);
+      slot = kDeltaNone;
+    }
+    b.tslot_of_vertex[v] = slot;
+    if (slot != kDeltaNone) atomicMin(t.first + slot, (static_cast<unsigned long long>(~b.pass) << 32) | i);
+  }
+  __syncthreads();
+  const uint32_t base_rec = static_cast<uint32_t>(counters[kDcNumRecords]);
+  const uint32_t base_act = static_cast<uint32_t>(counters[kDcActiveSlots]);
+  const uint32_t base_arch = static_cast<uint32_t>(counters[kDcArchVerts]);
+  // ---- ordered ranks + apply
+  {
+    const AddFlags f = addFlags(t, r, b, i);
+    unsigned long long total;
+    const unsigned long long ex = blockScanPacked(pack3(f.first, f.fresh, f.pass_slot), &total);
+    if (f.first) {
+      const uint32_t pos = field(ex, 0);
+      uint32_t vs;
+      if (f.fresh) {
+        vs = base_rec + field(ex, 1);
+        t.vslot[f.tslot] = vs;
+        r.key[vs] = t.keys[f.tslot];
+        r.mesh_index[vs] = 0;
+        r.seq[vs] = 0;
+        r.refs[vs] = 0;
+        r.needs_archive[vs] = 0;
+        r.is_new[vs] = 1;
+        r.alive[vs] = 1;
+      } else {
+        vs = t.vslot[f.tslot];
+      }
+      if (f.pass_slot) {
+        const uint64_t v = b.first_vertex + i;
+        const uint32_t a = base_act + field(ex, 2);
+        r.stamp[vs] = b.stamp_ns;
+        r.point[vs] = make_float4(b.xyz[3 * v], b.xyz[3 * v + 1], b.xyz[3 * v + 2],
+                                  __uint_as_float(b.rgba ? b.rgba[v] : 0xFF000000u));
+        b.active_remapping[a] = r.mesh_index[vs];
+        r.mesh_index[vs] = a;
+        r.seq[vs] = b.seq;
+      }
+      r.refs[vs] += 1;
+      b.voxels[pos] = vs;
+    }
+    if (i == 0) {
+      *b.voxel_count = field(total, 0);
+      counters[kDcNumRecords] = base_rec + field(total, 1);
+      counters[kDcActiveSlots] = base_act + field(total, 2);
+    }
+  }
+  __syncthreads();
+  // ---- face map
+  if (i < b.n) {
+    const uint32_t tslot = b.tslot_of_vertex[b.first_vertex + i];
+    b.face_map[i] = tslot == kDeltaNone ? 0u : r.mesh_index[t.vslot[tslot]];
+  }
+  if (!prev_voxels) return;
+  __syncthreads();
+  // ---- removeBlockObservations over the previous voxel list
+  bool to_archive = false;
+  uint32_t vs = 0;
+  if (i < *prev_count) {
+    vs = prev_voxels[i];
+    if (!r.alive[vs]) {
+      atomicOr(counters + kDcError, 4ull);
+    } else {
+      const int refs = --r.refs[vs];
+      if (!r.needs_archive[vs] && refs <= 0) {
+        const uint32_t prev = r.mesh_index[vs];
+        if (prev < o.prev_total) o.deleted[prev] = 1;
+        eraseRecord(t, r, vs, counters);
+      } else if (r.needs_archive[vs] && refs <= 0) {
+        to_archive = true;
+      }
+    }
+  }
+  unsigned long long total;
+  const unsigned long long ex = blockScanPacked(pack3(to_archive, false, false), &total);
+  if (to_archive) {
+    const uint32_t local = base_arch + field(ex, 0);
+    o.point[local] = r.point[vs];
+    o.stamp[local] = r.stamp[vs];
+    const uint32_t prev = r.mesh_index[vs];
+    if (prev < o.prev_total) o.p2c[prev] = o.vertex_start + local;
+    eraseRecord(t, r, vs, counters);
+  }
+  if (i == 0) counters[kDcArchVerts] = base_arch + field(total, 0);
+}
+
+// ---------------------------------------------------------------------------------- compaction
+// Erased records leave holes; insertion order is all that matters, so the alive ones are moved
+// to the front in order (stable), the block voxel lists are renumbered and the table is rebuilt.
+__global__ void __launch_bounds__(kDeltaTile)
+compactMoveKernel(const DeltaRecords from, const DeltaRecords to, const uint32_t* __restrict__ tiles,
+                  const unsigned long long* counters, uint32_t* __restrict__ new_id) {
+  const uint32_t vs = blockIdx.x * kDeltaTile + threadIdx.x;
+  const bool in_range = vs < counters[kDcNumRecords];
+  const bool alive = in_range && from.alive[vs];
+  unsigned long long total;
+  const unsigned long long ex = blockScanPacked(pack3(alive, false, false), &total);
+  if (in_range) new_id[vs] = kDeltaNone;
+  if (!alive) return;
+  const uint32_t n = tiles[3 * blockIdx.x] + field(ex, 0);
+  new_id[vs] = n;
+  to.key[n] = from.key[vs];
+  to.point[n] = from.point[vs];
+  to.stamp[n] = from.stamp[vs];
+  to.mesh_index[n] = from.mesh_index[vs];
+  to.seq[n] = from.seq[vs];
+  to.refs[n] = from.refs[vs];
+  to.needs_archive[n] = from.needs_archive[vs];
+  to.is_new[n] = from.is_new[vs];
+  to.alive[n] = 1;
+}
+
+__global__ void renumberVoxelsKernel(uint32_t* pool, uint64_t n, const uint32_t* __restrict__ new_id,
+                                     uint32_t n_old) {
+  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t old = pool[i];
+  const uint32_t now = old < n_old ? new_id[old] : kDeltaNone;
+  pool[i] = now == kDeltaNone ? 0u : now;  // entries beyond a list's count / of replaced lists are garbage
+}
+
+__global__ void setCounterKernel(unsigned long long* dst, const unsigned long long* src) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) *dst = *src;
+}
+
 inline unsigned tilesFor(uint64_t n) { return static_cast<unsigned>((n + kDeltaTile - 1) / kDeltaTile); }
 
 }  // namespace
@@ -563,7 +718,7 @@ cudaError_t launchDeltaAddBlock(const DeltaTable& t, const DeltaRecords& r, cons
   }
   addInsertKernel<<<(b.n + 255) / 256, 256, 0, s>>>(t, b, counters);
   addCountKernel<<<n_tiles, kDeltaTile, 0, s>>>(t, r, b, tiles);
-  scanTiles3Kernel<<<1, 32, 0, s>>>(tiles, n_tiles, nullptr, counters + kDcNumRecords,
+  scanTiles3Kernel<<<1, 96, 0, s>>>(tiles, n_tiles, nullptr, counters + kDcNumRecords,
                                     counters + kDcActiveSlots, bases, totals);
   addApplyKernel<<<n_tiles, kDeltaTile, 0, s>>>(t, r, b, tiles, bases);
   cudaMemcpyAsync(b.voxel_count, totals, sizeof(uint32_t), cudaMemcpyDeviceToDevice, s);
@@ -580,7 +735,7 @@ cudaError_t launchDeltaRelease(const DeltaTable& t, const DeltaRecords& r, const
   uint32_t* bases = tiles + 3 * n_tiles;
   releaseFlagKernel<<<n_tiles, kDeltaTile, 0, s>>>(t, r, o, voxels, voxel_count, archive, flags, tiles,
                                                   counters);
-  scanTiles3Kernel<<<1, 32, 0, s>>>(tiles, n_tiles, counters + kDcArchVerts, nullptr, nullptr, bases,
+  scanTiles3Kernel<<<1, 96, 0, s>>>(tiles, n_tiles, counters + kDcArchVerts, nullptr, nullptr, bases,
                                     nullptr);
   releaseApplyKernel<<<n_tiles, kDeltaTile, 0, s>>>(t, r, o, voxels, flags, tiles, bases, counters);
   return cudaGetLastError();
@@ -597,7 +752,7 @@ cudaError_t launchDeltaActiveVertices(const DeltaRecords& r, const DeltaOut& o, 
   uint32_t* bases = tiles + 3 * n_tiles;
   activeCountKernel<<<n_tiles, kDeltaTile, 0, s>>>(r, counters, tiles);
   // the number of active vertices goes to counters[kDcScratch]
-  scanTiles3Kernel<<<1, 32, 0, s>>>(tiles, n_tiles, nullptr, nullptr, nullptr, bases,
+  scanTiles3Kernel<<<1, 96, 0, s>>>(tiles, n_tiles, nullptr, nullptr, nullptr, bases,
                                     counters + kDcScratch);
   activeApplyKernel<<<n_tiles, kDeltaTile, 0, s>>>(r, o, seq, active_remapping, tiles, counters);
   return cudaGetLastError();
@@ -634,7 +789,7 @@ cudaError_t launchDeltaAppendFaces(const uint32_t* faces, const uint8_t* flags, 
   const unsigned n_tiles = tilesFor(n_faces);
   uint32_t* bases = tiles + 3 * n_tiles;
   flagCountKernel<<<n_tiles, kDeltaTile, 0, s>>>(flags, n_faces, tiles);
-  scanTiles3Kernel<<<1, 32, 0, s>>>(tiles, n_tiles, count, nullptr, nullptr, bases, nullptr);
+  scanTiles3Kernel<<<1, 96, 0, s>>>(tiles, n_tiles, count, nullptr, nullptr, bases, nullptr);
   appendFacesKernel<<<n_tiles, kDeltaTile, 0, s>>>(faces, flags, n_faces, out, tiles, bases);
   return cudaGetLastError();
 }
@@ -663,6 +818,32 @@ cudaError_t launchDeltaArchiveFaces(const DeltaFaceBlock* blocks, uint32_t n_blo
   archiveFacesKernel<<<(n_faces + 255) / 256, 256, 0, s>>>(blocks, n_blocks, n_faces, pool, o,
                                                           num_archived_vertices, counters, work_faces,
                                                           to_pending, candidate);
+  return cudaGetLastError();
+}
+
+cudaError_t launchDeltaCompactRecords(const DeltaRecords& from, const DeltaRecords& to, uint32_t n_old,
+                                      uint32_t* new_id, uint32_t* voxel_pool, uint64_t pool_used,
+                                      uint32_t* tiles, unsigned long long* counters, cudaStream_t s) {
+  if (n_old == 0) return cudaSuccess;
+  const unsigned n_tiles = tilesFor(n_old);
+  uint32_t* bases = tiles + 3 * n_tiles;
+  activeCountKernel<<<n_tiles, kDeltaTile, 0, s>>>(from, counters, tiles);
+  scanTiles3Kernel<<<1, 96, 0, s>>>(tiles, n_tiles, nullptr, nullptr, nullptr, bases,
+                                    counters + kDcScratch + 4);
+  compactMoveKernel<<<n_tiles, kDeltaTile, 0, s>>>(from, to, tiles, counters, new_id);
+  if (pool_used) {
+    renumberVoxelsKernel<<<static_cast<unsigned>((pool_used + 255) / 256), 256, 0, s>>>(voxel_pool, pool_used,
+                                                                                       new_id, n_old);
+  }
+  setCounterKernel<<<1, 32, 0, s>>>(counters + kDcNumRecords, counters + kDcScratch + 4);
+  return cudaGetLastError();
+}
+
+cudaError_t launchDeltaSmallBlock(const DeltaTable& t, const DeltaRecords& r, const DeltaOut& o,
+                                  const DeltaBlockArgs& b, const uint32_t* prev_voxels,
+                                  const uint32_t* prev_count, unsigned long long* counters,
+                                  cudaStream_t s) {
+  smallBlockKernel<<<1, kDeltaTile, 0, s>>>(t, r, o, b, prev_voxels, prev_count, counters);
   return cudaGetLastError();
 }
 

@@ -94,6 +94,12 @@ cudaError_t launchDeltaRehash(const DeltaTable& t, const DeltaRecords& r, const 
 // updateRemapping for one block: addPoint for every vertex (:54-92)
 cudaError_t launchDeltaAddBlock(const DeltaTable& t, const DeltaRecords& r, const DeltaBlockArgs& b,
                                 uint32_t* tiles, unsigned long long* counters, cudaStream_t s);
+// both of the above for a block and a previous voxel list of at most kDeltaTile entries, in one
+// launch (prev_voxels == nullptr: a new block)
+cudaError_t launchDeltaSmallBlock(const DeltaTable& t, const DeltaRecords& r, const DeltaOut& o,
+                                  const DeltaBlockArgs& b, const uint32_t* prev_voxels,
+                                  const uint32_t* prev_count, unsigned long long* counters,
+                                  cudaStream_t s);
 // removeBlockObservations (:94-126, archive == false) / the vertex loop of archiveBlocks
 // (:336-349, archive == true) over one block's voxel list
 cudaError_t launchDeltaRelease(const DeltaTable& t, const DeltaRecords& r, const DeltaOut& o,
@@ -143,6 +149,12 @@ cudaError_t launchDeltaArchiveFaces(const DeltaFaceBlock* blocks, uint32_t n_blo
                                     uint32_t num_archived_vertices, const unsigned long long* counters,
                                     uint32_t* work_faces, uint8_t* to_pending, uint8_t* candidate,
                                     cudaStream_t s);
+// stable compaction of the alive records into `to`; new_id[old] = new index (kDeltaNone = erased);
+// the block voxel lists in voxel_pool[0, pool_used) are renumbered; counters[kDcNumRecords] =
+// the number of alive records afterwards
+cudaError_t launchDeltaCompactRecords(const DeltaRecords& from, const DeltaRecords& to, uint32_t n_old,
+                                      uint32_t* new_id, uint32_t* voxel_pool, uint64_t pool_used,
+                                      uint32_t* tiles, unsigned long long* counters, cudaStream_t s);
 uint64_t deltaTileEntries(uint64_t n);
 
 }  // namespace pgmo

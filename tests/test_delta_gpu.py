@@ -154,3 +154,22 @@ def test_empty_and_invalid_inputs(capi, oracle):
         gpu.update(*bad, 7)
     assert err.value.code == capi.PGMO_ERR_OUT_OF_RANGE
     gpu.close()
+
+
+def test_compaction_of_records_and_pools_keeps_parity(capi, oracle, monkeypatch):
+    """Erased voxel records and replaced block segments are garbage-collected (stable compaction,
+    table rebuild, voxel lists renumbered); with the slack set to 0 this happens after almost
+    every message and must not change a single output."""
+    monkeypatch.setenv("PGMO_DELTA_COMPACT_SLACK", "0")
+    gpu, ora = capi.DeltaHandle(0.05, 0), oracle.DeltaCompression(0.05)
+    for m, (blocks, offsets, xyz, rgba, t) in enumerate(synth.compression_stream(16, 6000, n_blocks=5, slide=4.0)):
+        if m >= 2:
+            cut = int((t - 2.0) * 1e9)
+            gpu.archive_by_time(cut)
+            ora.archive_by_time(cut)
+        gr, gd = gpu.update(blocks, offsets, xyz, rgba, int(t * 1e9))
+        orr, od = ora.update(blocks, offsets, xyz, rgba, int(t * 1e9))
+        np.testing.assert_array_equal(gr, orr, err_msg=f"message {m}: remap")
+        _same(gd, od, f"message {m}")
+    assert gpu.last_stats()[3] >= 3  # record compactions happened
+    gpu.close()
