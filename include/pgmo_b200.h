@@ -339,6 +339,11 @@ int pgmo_delta_fetch(pgmo_delta_t* h, float* vertices_xyz, uint32_t* vertices_rg
                      uint32_t* faces, uint32_t* faces_archive, uint64_t* prev_to_curr2,
                      uint64_t* n_prev_to_curr, uint64_t* deleted, uint64_t* n_deleted,
                      uint64_t* observed, uint64_t* n_observed, uint64_t* new_indices, uint64_t* n_new);
+/* block_info_map_ in iteration (insertion) order: index, update_time_ns, sequence_number of up to
+ * `capacity` blocks; *n_blocks = how many there are.  Lets a caller evaluate an arbitrary
+ * archiveBlocks(BlockFilter) (:318-360) and pass the chosen blocks to pgmo_delta_archive_blocks. */
+int pgmo_delta_blocks(pgmo_delta_t* h, uint64_t capacity, int32_t* block_idx_xyz,
+                      uint64_t* update_time_ns, uint32_t* sequence_number, uint64_t* n_blocks);
 /* stats4 = [redundancy fixed-point rounds of the last call, voxel records, blocks, record
  * compactions so far] */
 int pgmo_delta_last_stats(pgmo_delta_t* h, uint64_t* stats4);

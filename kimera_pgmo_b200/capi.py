@@ -99,6 +99,7 @@ SIGNATURES = {
     "pgmo_delta_fetch": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _u64p, _vp, _u64p, _vp, _u64p,
                                    _vp, _u64p]),
     "pgmo_delta_last_stats": (C.c_int, [_vp, _vp]),
+    "pgmo_delta_blocks": (C.c_int, [_vp, C.c_uint64, _vp, _vp, _vp, _u64p]),
     "pgmo_voxblox_decode": (C.c_int, [C.c_int, C.c_uint32] + [_vp] * 8 + [C.c_float, _vp, _vp]),
     "pgmo_vcc_integrate_voxblox": (C.c_int, [_vp, C.c_uint32] + [_vp] * 8 + [C.c_float, C.c_double,
                                                                           _vp, _vp]),
@@ -560,6 +561,16 @@ class DeltaHandle:
         s = np.zeros(4, dtype=np.uint64)
         _check(self._lib.pgmo_delta_last_stats(self._h, _ptr(s)))
         return [int(v) for v in s]
+
+    def blocks(self):
+        """block_info_map_ in iteration order: (index [n,3], update_time_ns [n], sequence [n])"""
+        n = C.c_uint64(0)
+        _check(self._lib.pgmo_delta_blocks(self._h, 0, None, None, None, C.byref(n)))
+        idx = np.zeros((n.value, 3), np.int32)
+        tm = np.zeros(n.value, np.uint64)
+        sq = np.zeros(n.value, np.uint32)
+        _check(self._lib.pgmo_delta_blocks(self._h, n.value, _ptr(idx), _ptr(tm), _ptr(sq), C.byref(n)))
+        return idx, tm, sq
 
     def delta(self):
         s = self.sizes()

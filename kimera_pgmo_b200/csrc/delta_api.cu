@@ -748,6 +748,18 @@ int pgmo_delta_fetch(pgmo_delta_t* h, float* vertices_xyz, uint32_t* vertices_rg
   return PGMO_OK;
 }
 
+int pgmo_delta_blocks(pgmo_delta_t* h, uint64_t capacity, int32_t* block_idx_xyz,
+                      uint64_t* update_time_ns, uint32_t* sequence_number, uint64_t* n_blocks) {
+  PGMO_CHECK_ARG(h != nullptr && n_blocks != nullptr);
+  *n_blocks = h->blocks.size();
+  for (uint64_t i = 0; i < h->blocks.size() && i < capacity; ++i) {
+    if (block_idx_xyz) std::memcpy(block_idx_xyz + 3 * i, h->blocks[i].idx, 3 * sizeof(int32_t));
+    if (update_time_ns) update_time_ns[i] = h->blocks[i].update_time_ns;
+    if (sequence_number) sequence_number[i] = h->blocks[i].seq;
+  }
+  return PGMO_OK;
+}
+
 int pgmo_delta_last_stats(pgmo_delta_t* h, uint64_t* stats4) {
   PGMO_CHECK_ARG(h != nullptr && stats4 != nullptr);
   stats4[0] = h->last_rounds;

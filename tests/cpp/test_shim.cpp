@@ -13,6 +13,7 @@
 
 #include "kimera_pgmo_b200/compression.h"
 #include "kimera_pgmo_b200/deformation_graph.h"
+#include "kimera_pgmo_b200/delta_compression.h"
 
 using namespace kimera_pgmo_b200;
 
@@ -543,6 +544,125 @@ static void testVoxbloxInterface() {
   }
 }
 
+// ------------------------------------------------------ TestDeltaCompression (CompressionCorrect)
+// test_delta_compression.cpp:334-435: the two richest configurations, checked the way
+// ExpectedDelta::checkOutput does (:189-270) — through absolute point ids in the colour channel.
+struct DeltaStep {
+  int prune_s;  // < 0: none
+  uint64_t stamp_s;
+  std::vector<BlockConfig> blocks;
+  size_t vertex_start, face_start, num_vertices;
+  std::vector<std::array<size_t, 3>> triangles;
+  std::vector<size_t> indices;
+};
+
+static void runDeltaConfig(const std::vector<DeltaStep>& steps) {
+  DeltaCompression compression(1.0e-3);
+  uint8_t point_index = 0;
+  std::map<size_t, size_t> prev_remapping;
+  for (const auto& step : steps) {
+    if (step.prune_s >= 0) compression.archiveBlocksByTime(static_cast<uint64_t>(step.prune_s) * 1000000000ull);
+    OrderedBlockMesh mesh;
+    for (const auto& c : step.blocks) {
+      mesh.order.push_back(BlockIndex(c.index[0], c.index[1], c.index[2]));
+      mesh.blocks.emplace_back();
+      for (const auto& f : c.faces) {
+        for (const auto& v : f) {
+          mesh.blocks.back().push_back(colored(v[0], v[1], v[2], point_index, point_index, point_index));
+          ++point_index;
+        }
+      }
+    }
+    HashedIndexMapping remapping;
+    const auto output = compression.update(mesh, step.stamp_s * 1000000000ull, &remapping);
+    EXPECT_TRUE(output != nullptr);
+    EXPECT_EQ(output->vertex_updates->size(), output->stamp_updates.size());
+    EXPECT_EQ(output->vertex_start, step.vertex_start);
+    EXPECT_EQ(output->face_start, step.face_start);
+    EXPECT_EQ(output->vertex_updates->size(), step.num_vertices);
+    std::map<size_t, size_t> result_remapping;
+    for (size_t i = 0; i < output->vertex_start; ++i) {
+      if (prev_remapping.count(i)) result_remapping[i] = prev_remapping.at(i);
+    }
+    for (size_t i = 0; i < output->vertex_updates->size(); ++i) {
+      result_remapping[i + output->vertex_start] = output->vertex_updates->at(i).r;
+    }
+    prev_remapping = result_remapping;
+    std::vector<Face> all(output->face_archive_updates);
+    all.insert(all.end(), output->face_updates.begin(), output->face_updates.end());
+    EXPECT_EQ(all.size(), step.triangles.size());
+    std::vector<std::set<size_t>> absolute;
+    for (const auto& f : all) {
+      const bool known = result_remapping.count(f.v1) && result_remapping.count(f.v2) && result_remapping.count(f.v3);
+      EXPECT_TRUE(known);
+      if (!known) continue;
+      absolute.push_back({result_remapping.at(f.v1), result_remapping.at(f.v2), result_remapping.at(f.v3)});
+      bool found = false;
+      for (const auto& e : step.triangles) found = found || std::set<size_t>(e.begin(), e.end()) == absolute.back();
+      EXPECT_TRUE(found);
+    }
+    for (const auto& e : step.triangles) {
+      bool found = false;
+      for (const auto& a : absolute) found = found || std::set<size_t>(e.begin(), e.end()) == a;
+      EXPECT_TRUE(found);
+    }
+    std::vector<size_t> flat;  // flattenRemapping (:105-126)
+    for (const auto& c : step.blocks) {
+      const auto iter = remapping.find(BlockIndex(c.index[0], c.index[1], c.index[2]));
+      if (iter == remapping.end()) continue;
+      std::vector<size_t> block_remapping(iter->second.size());
+      for (const auto& kv : iter->second) block_remapping.at(kv.first) = kv.second;
+      flat.insert(flat.end(), block_remapping.begin(), block_remapping.end());
+    }
+    std::vector<size_t> abs_indices;
+    for (const auto idx : flat) abs_indices.push_back(result_remapping.count(idx) ? result_remapping.at(idx) : 9999);
+    EXPECT_TRUE(abs_indices == step.indices);
+  }
+}
+
+static void testDeltaCompression() {
+  const BlockConfig b1_v1 = block1_test1, b2_v1 = block2_test1;
+  const BlockConfig b1_v2{{0, 0, 0},
+                          {{{{0.5, 0.5, 0.5}, {0.5, 0.75, 0.75}, {0.5, 0.75, 0.5}}},
+                           {{{0.0, 0.0, 0.0}, {0.0, 0.5, 0.5}, {0.0, 0.0, 0.5}}}}};
+  const BlockConfig b2_v2{{-1, 0, 0},
+                          {{{{-0.5, 0.5, 0.5}, {-0.5, 0.75, 0.75}, {-0.5, 0.75, 0.5}}},
+                           {{{0.0, 0.0, 0.0}, {0.0, 0.5, 0.5}, {0.0, 0.0, -0.5}}}}};
+  runDeltaConfig({  // MultiBlockPartialUpdates
+      {-1, 100, {b1_v1}, 0, 0, 6, {{0, 1, 2}, {6, 7, 8}}, {0, 1, 2, 0, 1, 2, 6, 7, 8}},
+      {-1, 102, {b2_v1}, 0, 0, 9, {{0, 1, 2}, {9, 10, 11}, {12, 13, 14}}, {9, 10, 11, 12, 13, 14}},
+      {101, 103, {block1_empty, b2_v1}, 0, 0, 9, {{0, 1, 2}, {15, 16, 17}, {18, 19, 20}, {18, 19, 20}},
+       {15, 16, 17, 18, 19, 20}},
+      {-1, 104, {b2_v1}, 3, 1, 6, {{21, 22, 23}, {24, 25, 26}, {24, 25, 26}}, {21, 22, 23, 24, 25, 26}},
+      {-1, 105, {b1_v1, b2_v1}, 3, 1, 9, {{27, 28, 29}, {33, 34, 35}, {36, 37, 38}, {33, 34, 35}},
+       {27, 28, 29, 27, 28, 29, 33, 34, 35, 36, 37, 38, 33, 34, 35}},
+      {-1, 106, {block1_empty, block2_empty}, 3, 1, 3, {{33, 34, 35}}, {}}});
+  runDeltaConfig({  // MultiBlockPartialArchive
+      {-1, 100, {b1_v2}, 0, 0, 6, {{0, 1, 2}, {3, 4, 5}}, {0, 1, 2, 3, 4, 5}},
+      {-1, 102, {b2_v2}, 0, 0, 10, {{0, 1, 2}, {9, 10, 5}, {6, 7, 8}, {9, 10, 11}}, {6, 7, 8, 9, 10, 11}},
+      {101, 103, {block1_empty, b2_v2}, 0, 0, 10, {{0, 1, 2}, {12, 13, 14}, {15, 16, 17}, {15, 16, 5}},
+       {12, 13, 14, 15, 16, 17}},
+      {-1, 104, {block2_empty}, 4, 1, 2, {{15, 16, 5}}, {}}});
+  // archiveBlocks with an arbitrary filter + MeshDelta::updateMesh
+  DeltaCompression c(1.0e-3);
+  OrderedBlockMesh mesh = createMesh({block1_test1, block2_test1});
+  auto d0 = c.update(mesh, 100ull * 1000000000ull);
+  c.archiveBlocks([](const BlockIndex& idx, const BlockInfo& info) {
+    return idx.x() == -1 && info.update_time_ns == 100ull * 1000000000ull && info.sequence_number == 1;
+  });
+  OrderedBlockMesh empty = createMesh({block1_empty});
+  auto d1 = c.update(empty, 101ull * 1000000000ull);
+  EXPECT_EQ(6u, d1->getNumArchivedVertices());  // block 2's 6 voxels (3 shared with the cleared block 1)
+  pcl::PointCloud<pcl::PointXYZRGBA> vertices;
+  std::vector<Timestamp> stamps;
+  std::vector<pcl::Vertices> faces;
+  d0->updateMesh(vertices, stamps, faces);
+  EXPECT_EQ(9u, vertices.size());
+  d1->updateMesh(vertices, stamps, faces);
+  EXPECT_EQ(d1->getTotalVertices(), vertices.size());
+  EXPECT_EQ(d1->getTotalFaces(), faces.size());
+}
+
 int main(int argc, char** argv) {
   const bool with_octree = argc > 1 && std::strcmp(argv[1], "--octree") == 0;
   if (pgmo_device_count() <= 0) {
@@ -556,6 +676,7 @@ int main(int argc, char** argv) {
   testIncrementalWithPredeform();
   testVoxelClearing();
   testVoxbloxInterface();
+  testDeltaCompression();
   if (with_octree) testOctreeCompression();
   std::printf("shim tests: %d checks, %d failures\n", g_checks, g_failures);
   return g_failures ? 1 : 0;
