@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <array>
 #include <cmath>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -62,7 +63,8 @@ struct pgmo_delta {
   // block_info_map_
   std::vector<BlockRec> blocks;  // insertion order, erased ones removed
   std::map<BlockKey, size_t> block_index;  // -> position in `blocks`
-  DevBuf<uint32_t> f_pool, x_pool, blk_counts;
+  DevBuf<uint32_t> f_pool, x_pool, blk_counts, f_spare, x_spare;
+  DevBuf<uint4> d_segs;
   uint64_t f_used = 0, x_used = 0, f_live = 0, x_live = 0;
   std::vector<uint32_t> free_cnt_slots;
   uint32_t next_cnt_slot = 0;
@@ -96,6 +98,16 @@ struct pgmo_delta {
 };
 
 namespace {
+
+// Allocation sizes: cudaMalloc / cudaFree take tens to hundreds of milliseconds on this platform,
+// so buffers are sized with generous head room (HBM is not the scarce resource here) and the
+// steady state never reallocates.
+inline uint64_t room(uint64_t n) { return std::max<uint64_t>(2 * n, 1ull << 22); }
+template <typename Buf>
+int roomy(Buf& buf, uint64_t n, cudaStream_t st = nullptr, uint64_t keep = 0) {
+  if (n <= buf.cap) return PGMO_OK;
+  return buf.reserve(std::max<uint64_t>(2 * n, 1ull << 20), st, keep);
+}
 
 DeltaTable tableOf(pgmo_delta* h) {
   return DeltaTable{h->t_keys.ptr, h->t_vslot.ptr, h->t_first.ptr, h->t_cap - 1};
@@ -186,8 +198,8 @@ int openDelta(pgmo_delta* h, cudaStream_t st) {
   h->vertex_start = static_cast<uint32_t>(h->num_archived_vertices);
   h->face_start = static_cast<uint32_t>(h->num_archived_faces);
   h->prev_total = static_cast<uint32_t>(h->last_total);
-  PGMO_TRY(h->o_p2c.reserve(h->prev_total + 1));
-  PGMO_TRY(h->o_del.reserve(h->prev_total + 1));
+  if (h->prev_total + 1ull > h->o_p2c.cap) PGMO_TRY(h->o_p2c.reserve(room(h->prev_total + 1ull)));
+  if (h->prev_total + 1ull > h->o_del.cap) PGMO_TRY(h->o_del.reserve(room(h->prev_total + 1ull)));
   PGMO_CUDA(cudaMemsetAsync(h->o_p2c.ptr, 0xFF, (h->prev_total + 1ull) * sizeof(uint32_t), st));
   PGMO_CUDA(cudaMemsetAsync(h->o_del.ptr, 0, h->prev_total + 1ull, st));
   PGMO_CUDA(cudaMemsetAsync(h->counters.ptr + kDcArchVerts, 0, 3 * sizeof(unsigned long long), st));
@@ -204,8 +216,8 @@ int reserveOutVertices(pgmo_delta* h, uint64_t n, cudaStream_t st) {
 }
 
 int reserveTiles(pgmo_delta* h, uint64_t n) {
-  PGMO_TRY(h->tiles.reserve(deltaTileEntries(n)));
-  PGMO_TRY(h->flags.reserve((n / kDeltaTile + 1) * kDeltaTile));
+  if (deltaTileEntries(n) > h->tiles.cap) PGMO_TRY(h->tiles.reserve(std::max<uint64_t>(2 * deltaTileEntries(n), 1u << 16)));
+  if ((n / kDeltaTile + 1) * kDeltaTile > h->flags.cap) PGMO_TRY(h->flags.reserve(room((n / kDeltaTile + 1) * kDeltaTile)));
   return PGMO_OK;
 }
 
@@ -219,10 +231,10 @@ int redundancyFixedPoint(pgmo_delta* h, const uint32_t* faces, const uint8_t* va
   if (n_faces == 0) return PGMO_OK;
   uint64_t cap = 1024;
   while (cap < 8ull * n_faces) cap <<= 1;
-  PGMO_TRY(h->e_keys.reserve(cap));
-  PGMO_TRY(h->e_minseq.reserve(cap));
-  PGMO_TRY(h->acc_a.reserve(n_faces));
-  PGMO_TRY(h->acc_b.reserve(n_faces));
+  PGMO_TRY(roomy(h->e_keys, cap));
+  PGMO_TRY(roomy(h->e_minseq, cap));
+  PGMO_TRY(roomy(h->acc_a, n_faces));
+  PGMO_TRY(roomy(h->acc_b, n_faces));
   DeltaEdgeTable e{h->e_keys.ptr, h->e_minseq.ptr, static_cast<uint32_t>(cap - 1)};
   PGMO_CUDA(cudaMemcpyAsync(h->acc_a.ptr, valid, n_faces, cudaMemcpyDeviceToDevice, st));
   uint8_t* in = h->acc_a.ptr;
@@ -244,6 +256,30 @@ int redundancyFixedPoint(pgmo_delta* h, const uint32_t* faces, const uint8_t* va
   return PGMO_OK;
 }
 
+struct PhaseTimer {  // PGMO_DEBUG=1: wall time per phase of slow updates (stream-synchronised)
+  bool on = std::getenv("PGMO_DEBUG") != nullptr;
+  cudaStream_t st;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  std::vector<std::pair<const char*, double>> marks;
+  explicit PhaseTimer(cudaStream_t s) : st(s) {}
+  void mark(const char* name) {
+    if (!on) return;
+    cudaStreamSynchronize(st);
+    const auto t1 = std::chrono::steady_clock::now();
+    marks.emplace_back(name, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+  ~PhaseTimer() {
+    double total = 0;
+    for (auto& m : marks) total += m.second;
+    if (on && total > 10.0) {
+      fprintf(stderr, "pgmo debug: slow delta update %.1f ms:", total);
+      for (auto& m : marks) fprintf(stderr, " %s %.1f", m.first, m.second);
+      fprintf(stderr, "\n");
+    }
+  }
+};
+
 uint32_t allocCountSlot(pgmo_delta* h) {
   if (!h->free_cnt_slots.empty()) {
     const uint32_t s = h->free_cnt_slots.back();
@@ -253,28 +289,33 @@ uint32_t allocCountSlot(pgmo_delta* h) {
   return h->next_cnt_slot++;
 }
 
-// drops the garbage of replaced / erased blocks from the two pools
+// drops the garbage of replaced / erased blocks from the two pools: the live segments are copied
+// in block order into a retained second pair of pools (no allocation in steady state)
 int compactPools(pgmo_delta* h, cudaStream_t st) {
   if (h->f_used <= 2 * h->f_live + h->compact_slack && h->x_used <= 2 * h->x_live + h->compact_slack) {
     return PGMO_OK;
   }
-  DevBuf<uint32_t> nf, nx;
-  PGMO_TRY(nf.reserve(h->f_live + 1));
-  PGMO_TRY(nx.reserve(h->x_live + 1));
+  PGMO_TRY(roomy(h->f_spare, std::max<uint64_t>(h->f_live + 1, h->f_pool.cap)));
+  PGMO_TRY(roomy(h->x_spare, std::max<uint64_t>(h->x_live + 1, h->x_pool.cap)));
+  std::vector<uint4> segs;
   uint64_t f = 0, x = 0;
   for (auto& b : h->blocks) {
-    if (b.f_n) PGMO_CUDA(cudaMemcpyAsync(nf.ptr + f, h->f_pool.ptr + b.f_off, b.f_n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
-    if (b.x_cap) PGMO_CUDA(cudaMemcpyAsync(nx.ptr + x, h->x_pool.ptr + b.x_off, b.x_cap * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    if (b.f_n) segs.push_back(make_uint4(b.f_off, static_cast<uint32_t>(f), b.f_n, 0));
+    if (b.x_cap) segs.push_back(make_uint4(b.x_off, static_cast<uint32_t>(x), b.x_cap, 1));
     b.f_off = static_cast<uint32_t>(f);
     b.x_off = static_cast<uint32_t>(x);
     f += b.f_n;
     x += b.x_cap;
   }
+  PGMO_TRY(roomy(h->d_segs, segs.size() + 1));
+  PGMO_CUDA(cudaMemcpyAsync(h->d_segs.ptr, segs.data(), segs.size() * sizeof(uint4), cudaMemcpyHostToDevice, st));
+  PGMO_CUDA(launchDeltaCopySegments(h->d_segs.ptr, static_cast<uint32_t>(segs.size()), h->f_pool.ptr,
+                                    h->f_spare.ptr, h->x_pool.ptr, h->x_spare.ptr, st));
   PGMO_CUDA(cudaStreamSynchronize(st));
-  std::swap(h->f_pool.ptr, nf.ptr);
-  std::swap(h->f_pool.cap, nf.cap);
-  std::swap(h->x_pool.ptr, nx.ptr);
-  std::swap(h->x_pool.cap, nx.cap);
+  std::swap(h->f_pool.ptr, h->f_spare.ptr);
+  std::swap(h->f_pool.cap, h->f_spare.cap);
+  std::swap(h->x_pool.ptr, h->x_spare.ptr);
+  std::swap(h->x_pool.cap, h->x_spare.cap);
   h->f_used = f;
   h->x_used = x;
   return PGMO_OK;
@@ -304,7 +345,7 @@ int compactRecords(pgmo_delta* h, uint64_t alive, cudaStream_t st) {
   PGMO_TRY(needs_archive.reserve(cap));
   PGMO_TRY(is_new.reserve(cap));
   PGMO_TRY(alive_flag.reserve(cap));
-  PGMO_TRY(h->new_id.reserve(n_old + 1));
+  PGMO_TRY(roomy(h->new_id, n_old + 1));
   PGMO_TRY(reserveTiles(h, n_old));
   const DeltaRecords to{key.ptr, point.ptr, stamp.ptr, mesh_index.ptr, seq.ptr,
                         refs.ptr, needs_archive.ptr, is_new.ptr, alive_flag.ptr};
@@ -362,23 +403,23 @@ int archiveChosen(pgmo_delta* h, const std::vector<size_t>& chosen) {
       fb.push_back(DeltaFaceBlock{b.f_off, b.f_n, first, -1});
       first += b.f_n / 3;
     }
-    PGMO_TRY(h->d_fblocks.reserve(fb.size()));
+    PGMO_TRY(roomy(h->d_fblocks, fb.size()));
     PGMO_CUDA(cudaMemcpyAsync(h->d_fblocks.ptr, fb.data(), fb.size() * sizeof(DeltaFaceBlock),
                               cudaMemcpyHostToDevice, st));
     PGMO_CUDA(cudaStreamSynchronize(st));  // fb is a stack vector
-    PGMO_TRY(h->work_faces.reserve(3ull * T));
-    PGMO_TRY(h->f1.reserve(T));
-    PGMO_TRY(h->f2.reserve(T));
+    PGMO_TRY(roomy(h->work_faces, 3ull * T));
+    PGMO_TRY(roomy(h->f1, T));
+    PGMO_TRY(roomy(h->f2, T));
     PGMO_CUDA(launchDeltaArchiveFaces(h->d_fblocks.ptr, static_cast<uint32_t>(fb.size()), T, h->f_pool.ptr,
                                       outOf(h), static_cast<uint32_t>(h->num_archived_vertices),
                                       h->counters.ptr, h->work_faces.ptr, h->f1.ptr, h->f2.ptr, st));
     const uint8_t* acc = nullptr;
     PGMO_TRY(redundancyFixedPoint(h, h->work_faces.ptr, h->f2.ptr, T, &acc, st));
     PGMO_TRY(reserveTiles(h, T));
-    PGMO_TRY(h->o_faces_arch.reserve(3 * (h->d_faces_arch + T) + 3, st, 3 * h->d_faces_arch));
+    PGMO_TRY(roomy(h->o_faces_arch, 3 * (h->d_faces_arch + T) + 3, st, 3 * h->d_faces_arch));
     PGMO_CUDA(launchDeltaAppendFaces(h->work_faces.ptr, acc, T, h->o_faces_arch.ptr,
                                      h->counters.ptr + kDcFacesArch, h->tiles.ptr, st));
-    PGMO_TRY(h->pending.reserve(3 * (h->n_pending + T) + 3, st, 3 * h->n_pending));
+    PGMO_TRY(roomy(h->pending, 3 * (h->n_pending + T) + 3, st, 3 * h->n_pending));
     PGMO_CUDA(launchDeltaAppendFaces(h->work_faces.ptr, h->f1.ptr, T, h->pending.ptr,
                                      h->counters.ptr + kDcPending, h->tiles.ptr, st));
   }
@@ -463,29 +504,31 @@ int pgmo_delta_update(pgmo_delta_t* h, uint32_t n_blocks, const int32_t* block_i
     }
   }
   h->last_rounds = 0;
+  PhaseTimer timer(st);
   PGMO_TRY(openDelta(h, st));  // 1) archive delta, if any, is the starting point (:215-222)
 
   // ---- inputs and capacities
-  PGMO_TRY(h->d_xyz.reserve(3 * n_total + 3));
-  PGMO_TRY(h->d_rgba.reserve(n_total + 1));
+  PGMO_TRY(roomy(h->d_xyz, 3 * n_total + 3));
+  PGMO_TRY(roomy(h->d_rgba, n_total + 1));
   if (n_total) {
     PGMO_CUDA(cudaMemcpyAsync(h->d_xyz.ptr, xyz, 3 * n_total * sizeof(float), cudaMemcpyHostToDevice, st));
     if (rgba) PGMO_CUDA(cudaMemcpyAsync(h->d_rgba.ptr, rgba, n_total * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
   }
-  PGMO_TRY(reserveRecords(h, h->n_records + n_total + 1, st));
+  if (h->n_records + n_total + 1 > h->r_key.cap) PGMO_TRY(reserveRecords(h, room(h->n_records + n_total + 1), st));
   PGMO_TRY(ensureTable(h, h->n_records + n_total, st));
-  PGMO_TRY(h->tslot_of_vertex.reserve(n_total + 1));
-  PGMO_TRY(h->active_remapping.reserve(n_total + 1));
-  PGMO_TRY(h->d_remap.reserve(n_total + 1));
+  PGMO_TRY(roomy(h->tslot_of_vertex, n_total + 1));
+  PGMO_TRY(roomy(h->active_remapping, n_total + 1));
+  PGMO_TRY(roomy(h->d_remap, n_total + 1));
   PGMO_CUDA(cudaMemsetAsync(h->d_remap.ptr, 0xFF, (n_total + 1) * sizeof(unsigned long long), st));
   PGMO_CUDA(cudaMemsetAsync(h->counters.ptr + kDcActiveSlots, 0, sizeof(unsigned long long), st));
   const uint64_t out_cap = h->d_arch + 2 * h->n_records + n_total + 1;
-  PGMO_TRY(reserveOutVertices(h, out_cap, st));
-  PGMO_TRY(h->o_new.reserve(out_cap));
-  PGMO_TRY(h->o_obs.reserve(out_cap));
+  if (out_cap > h->o_point.cap) PGMO_TRY(reserveOutVertices(h, room(out_cap), st));
+  if (out_cap > h->o_new.cap) PGMO_TRY(h->o_new.reserve(room(out_cap)));
+  if (out_cap > h->o_obs.cap) PGMO_TRY(h->o_obs.reserve(room(out_cap)));
   PGMO_CUDA(cudaMemsetAsync(h->o_new.ptr, 0, out_cap, st));
   PGMO_CUDA(cudaMemsetAsync(h->o_obs.ptr, 0, out_cap, st));
 
+  timer.mark("reserve");
   // ---- 2) updateRemapping (:261-296), block by block
   std::vector<int64_t> msg_offset_of_block(h->blocks.size(), -1);
   for (uint32_t b = 0; b < n_blocks; ++b) {
@@ -506,8 +549,14 @@ int pgmo_delta_update(pgmo_delta_t* h, uint32_t n_blocks, const int32_t* block_i
     rec.update_time_ns = timestamp_ns;
     rec.seq = h->seq;
     // new segments at the end of the pools (the old ones become garbage)
-    PGMO_TRY(h->f_pool.reserve(h->f_used + n_b + 1, st, h->f_used));
-    PGMO_TRY(h->x_pool.reserve(h->x_used + n_b + 1, st, h->x_used));
+    const auto tr0 = std::chrono::steady_clock::now();
+    if (h->f_used + n_b + 1 > h->f_pool.cap) PGMO_TRY(h->f_pool.reserve(room(h->f_used + n_b + 1), st, h->f_used));
+    if (h->x_used + n_b + 1 > h->x_pool.cap) PGMO_TRY(h->x_pool.reserve(room(h->x_used + n_b + 1), st, h->x_used));
+    if (timer.on) {
+      const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tr0).count();
+      if (ms > 5.0) fprintf(stderr, "pgmo debug: pool reserve %.1f ms (f_used %llu cap %zu, x_used %llu cap %zu)\n", ms,
+                            (unsigned long long)h->f_used, h->f_pool.cap, (unsigned long long)h->x_used, h->x_pool.cap);
+    }
     rec.f_off = static_cast<uint32_t>(h->f_used);
     rec.f_n = n_b;
     rec.x_off = static_cast<uint32_t>(h->x_used);
@@ -517,7 +566,7 @@ int pgmo_delta_update(pgmo_delta_t* h, uint32_t n_blocks, const int32_t* block_i
     h->x_used += n_b;
     h->f_live += n_b;
     h->x_live += n_b;
-    PGMO_TRY(h->blk_counts.reserve(h->next_cnt_slot + 1, st, h->next_cnt_slot));
+    PGMO_TRY(roomy(h->blk_counts, h->next_cnt_slot + 1, st, h->next_cnt_slot));
     PGMO_TRY(reserveTiles(h, std::max<uint64_t>(n_b, prev.x_cap)));
 
     DeltaBlockArgs a;
@@ -554,6 +603,7 @@ int pgmo_delta_update(pgmo_delta_t* h, uint32_t n_blocks, const int32_t* block_i
     }
   }
 
+  timer.mark("blocks");
   // ---- 3) addActiveVertices (:128-154)
   const uint64_t rec_upper = h->n_records + n_total;
   PGMO_TRY(reserveTiles(h, rec_upper));
@@ -569,13 +619,13 @@ int pgmo_delta_update(pgmo_delta_t* h, uint32_t n_blocks, const int32_t* block_i
     fb.push_back(DeltaFaceBlock{b.f_off, b.f_n, T, msg_offset_of_block[i]});
     T += b.f_n / 3;
   }
-  PGMO_TRY(h->o_faces_upd.reserve(3 * (static_cast<uint64_t>(T) + h->n_pending) + 3));
+  PGMO_TRY(roomy(h->o_faces_upd, 3 * (static_cast<uint64_t>(T) + h->n_pending) + 3));
   if (T > 0) {
-    PGMO_TRY(h->d_fblocks.reserve(fb.size()));
+    PGMO_TRY(roomy(h->d_fblocks, fb.size()));
     PGMO_CUDA(cudaMemcpyAsync(h->d_fblocks.ptr, fb.data(), fb.size() * sizeof(DeltaFaceBlock),
                               cudaMemcpyHostToDevice, st));
-    PGMO_TRY(h->work_faces.reserve(3ull * T));
-    PGMO_TRY(h->valid.reserve(T));
+    PGMO_TRY(roomy(h->work_faces, 3ull * T));
+    PGMO_TRY(roomy(h->valid, T));
     PGMO_CUDA(launchDeltaRemapFaces(h->d_fblocks.ptr, static_cast<uint32_t>(fb.size()), T, h->f_pool.ptr,
                                     h->active_remapping.ptr, outOf(h), h->d_remap.ptr,
                                     h->work_faces.ptr, h->valid.ptr, h->counters.ptr, st));
@@ -586,13 +636,14 @@ int pgmo_delta_update(pgmo_delta_t* h, uint32_t n_blocks, const int32_t* block_i
                                      h->counters.ptr + kDcFacesUpd, h->tiles.ptr, st));
   }
 
+  timer.mark("vertices+faces");
   // ---- 4) updateAndAddArchivedFaces (:416-446)
   if (h->n_pending > 0) {
     const uint32_t P = static_cast<uint32_t>(h->n_pending);
-    PGMO_TRY(h->valid.reserve(P));
-    PGMO_TRY(h->f1.reserve(P));
-    PGMO_TRY(h->f2.reserve(P));
-    PGMO_TRY(h->pending2.reserve(3ull * P + 3));
+    PGMO_TRY(roomy(h->valid, P));
+    PGMO_TRY(roomy(h->f1, P));
+    PGMO_TRY(roomy(h->f2, P));
+    PGMO_TRY(roomy(h->pending2, 3ull * P + 3));
     PGMO_CUDA(launchDeltaPendingRemap(h->pending.ptr, P, outOf(h),
                                       static_cast<uint32_t>(h->num_archived_vertices), h->valid.ptr, st));
     const uint8_t* acc = nullptr;
@@ -600,7 +651,7 @@ int pgmo_delta_update(pgmo_delta_t* h, uint32_t n_blocks, const int32_t* block_i
     PGMO_CUDA(launchDeltaClassifyPending(h->pending.ptr, acc, P, h->counters.ptr, outOf(h), h->f1.ptr,
                                          h->f2.ptr, st));
     PGMO_TRY(reserveTiles(h, P));
-    PGMO_TRY(h->o_faces_arch.reserve(3 * (h->d_faces_arch + P) + 3, st, 3 * h->d_faces_arch));
+    PGMO_TRY(roomy(h->o_faces_arch, 3 * (h->d_faces_arch + P) + 3, st, 3 * h->d_faces_arch));
     PGMO_CUDA(launchDeltaAppendFaces(h->pending.ptr, h->f1.ptr, P, h->o_faces_arch.ptr,
                                      h->counters.ptr + kDcFacesArch, h->tiles.ptr, st));
     PGMO_CUDA(launchDeltaAppendFaces(h->pending.ptr, h->f2.ptr, P, h->o_faces_upd.ptr,
@@ -617,6 +668,7 @@ int pgmo_delta_update(pgmo_delta_t* h, uint32_t n_blocks, const int32_t* block_i
     PGMO_CUDA(cudaMemcpyAsync(remap_out, h->d_remap.ptr, n_total * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
   }
   PGMO_TRY(readCounters(h, st));
+  timer.mark("pending+sync");
   h->d_vertices = h->d_arch + h->h_counters.ptr[kDcScratch];
   h->num_archived_vertices = h->vertex_start + h->d_arch;
   h->num_archived_faces = h->face_start + h->d_faces_arch;
@@ -626,7 +678,10 @@ int pgmo_delta_update(pgmo_delta_t* h, uint32_t n_blocks, const int32_t* block_i
   h->delta_open = false;
   h->have_delta = true;
   PGMO_TRY(compactPools(h, st));
-  return compactRecords(h, h->d_vertices - h->d_arch, st);
+  timer.mark("compact pools");
+  const int rc = compactRecords(h, h->d_vertices - h->d_arch, st);
+  timer.mark("compact records");
+  return rc;
 }
 
 int pgmo_delta_archive_by_time(pgmo_delta_t* h, uint64_t earliest_time_ns) {

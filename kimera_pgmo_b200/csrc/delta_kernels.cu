@@ -688,6 +688,16 @@ __global__ void setCounterKernel(unsigned long long* dst, const unsigned long lo
   if (threadIdx.x == 0 && blockIdx.x == 0) *dst = *src;
 }
 
+__global__ void copySegmentsKernel(const uint4* __restrict__ segs, const uint32_t* __restrict__ src_a,
+                                   uint32_t* __restrict__ dst_a, const uint32_t* __restrict__ src_b,
+                                   uint32_t* __restrict__ dst_b) {
+  // segs[i] = {src offset, dst offset, count, pool (0 = a, 1 = b)}: one CTA per segment
+  const uint4 sg = segs[blockIdx.x];
+  const uint32_t* src = (sg.w ? src_b : src_a) + sg.x;
+  uint32_t* dst = (sg.w ? dst_b : dst_a) + sg.y;
+  for (uint32_t i = threadIdx.x; i < sg.z; i += blockDim.x) dst[i] = src[i];
+}
+
 inline unsigned tilesFor(uint64_t n) { return static_cast<unsigned>((n + kDeltaTile - 1) / kDeltaTile); }
 
 }  // namespace
@@ -844,6 +854,14 @@ cudaError_t launchDeltaSmallBlock(const DeltaTable& t, const DeltaRecords& r, co
                                   const uint32_t* prev_count, unsigned long long* counters,
                                   cudaStream_t s) {
   smallBlockKernel<<<1, kDeltaTile, 0, s>>>(t, r, o, b, prev_voxels, prev_count, counters);
+  return cudaGetLastError();
+}
+
+cudaError_t launchDeltaCopySegments(const uint4* segs, uint32_t n_segs, const uint32_t* src_a,
+                                    uint32_t* dst_a, const uint32_t* src_b, uint32_t* dst_b,
+                                    cudaStream_t s) {
+  if (n_segs == 0) return cudaSuccess;
+  copySegmentsKernel<<<n_segs, 256, 0, s>>>(segs, src_a, dst_a, src_b, dst_b);
   return cudaGetLastError();
 }
 

@@ -155,6 +155,10 @@ cudaError_t launchDeltaArchiveFaces(const DeltaFaceBlock* blocks, uint32_t n_blo
 cudaError_t launchDeltaCompactRecords(const DeltaRecords& from, const DeltaRecords& to, uint32_t n_old,
                                       uint32_t* new_id, uint32_t* voxel_pool, uint64_t pool_used,
                                       uint32_t* tiles, unsigned long long* counters, cudaStream_t s);
+// pool garbage collection: segs[i] = {src offset, dst offset, count, pool (0 = a, 1 = b)}
+cudaError_t launchDeltaCopySegments(const uint4* segs, uint32_t n_segs, const uint32_t* src_a,
+                                    uint32_t* dst_a, const uint32_t* src_b, uint32_t* dst_b,
+                                    cudaStream_t s);
 uint64_t deltaTileEntries(uint64_t n);
 
 }  // namespace pgmo
