@@ -295,8 +295,9 @@ int compactPools(pgmo_delta* h, cudaStream_t st) {
   if (h->f_used <= 2 * h->f_live + h->compact_slack && h->x_used <= 2 * h->x_live + h->compact_slack) {
     return PGMO_OK;
   }
-  PGMO_TRY(roomy(h->f_spare, std::max<uint64_t>(h->f_live + 1, h->f_pool.cap)));
-  PGMO_TRY(roomy(h->x_spare, std::max<uint64_t>(h->x_live + 1, h->x_pool.cap)));
+  // (sized by what is alive, never by the capacity of the pool being replaced: the two swap roles)
+  if (h->f_live + 1 > h->f_spare.cap) PGMO_TRY(h->f_spare.reserve(room(h->f_live + 1)));
+  if (h->x_live + 1 > h->x_spare.cap) PGMO_TRY(h->x_spare.reserve(room(h->x_live + 1)));
   std::vector<uint4> segs;
   uint64_t f = 0, x = 0;
   for (auto& b : h->blocks) {
@@ -335,16 +336,18 @@ int compactRecords(pgmo_delta* h, uint64_t alive, cudaStream_t st) {
   auto& needs_archive = h->s_needs_archive;
   auto& is_new = h->s_is_new;
   auto& alive_flag = h->s_alive;
-  const uint64_t cap = std::max<uint64_t>(alive + 1, h->r_key.cap);  // as roomy as the live set
-  PGMO_TRY(key.reserve(cap));
-  PGMO_TRY(stamp.reserve(cap));
-  PGMO_TRY(point.reserve(cap));
-  PGMO_TRY(mesh_index.reserve(cap));
-  PGMO_TRY(seq.reserve(cap));
-  PGMO_TRY(refs.reserve(cap));
-  PGMO_TRY(needs_archive.reserve(cap));
-  PGMO_TRY(is_new.reserve(cap));
-  PGMO_TRY(alive_flag.reserve(cap));
+  if (alive + 1 > key.cap) {  // sized by what is alive, never by the set being replaced
+    const uint64_t cap = room(alive + 1);
+    PGMO_TRY(key.reserve(cap));
+    PGMO_TRY(stamp.reserve(cap));
+    PGMO_TRY(point.reserve(cap));
+    PGMO_TRY(mesh_index.reserve(cap));
+    PGMO_TRY(seq.reserve(cap));
+    PGMO_TRY(refs.reserve(cap));
+    PGMO_TRY(needs_archive.reserve(cap));
+    PGMO_TRY(is_new.reserve(cap));
+    PGMO_TRY(alive_flag.reserve(cap));
+  }
   PGMO_TRY(roomy(h->new_id, n_old + 1));
   PGMO_TRY(reserveTiles(h, n_old));
   const DeltaRecords to{key.ptr, point.ptr, stamp.ptr, mesh_index.ptr, seq.ptr,
