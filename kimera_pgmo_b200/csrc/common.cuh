@@ -43,6 +43,8 @@ int ensureDevice(int device);
   } while (0)
 
 // Grow-only device buffer (never shrinks: handles are long-lived and re-used per message).
+// cudaMalloc / cudaFree cost tens to hundreds of milliseconds on this platform: callers on a
+// message stream ask for generous head room when they have to grow.
 template <typename T>
 struct DevBuf {
   T* ptr = nullptr;

@@ -761,11 +761,13 @@ static int octIntegrate(pgmo_oct_t* h, uint32_t n_blocks, const int32_t* block_i
     }
   }
   // room for the accepted vertices
-  PGMO_TRY(h->all_vertices.reserve(n_orig + n_acc + 1, st, n_orig));
-  PGMO_TRY(h->all_stamps.reserve(n_orig + n_acc + 1, st, n_orig));
-  PGMO_TRY(h->act_xyz.reserve(h->n_act + n_acc + 1, st, h->n_act));
-  PGMO_TRY(h->act_index.reserve(h->n_act + n_acc + 1, st, h->n_act));
-  PGMO_TRY(h->act_stamp.reserve(h->n_act + n_acc + 1, st, h->n_act));
+  // grow rarely, by a lot: an allocation costs tens of milliseconds inside the message stream
+  auto roomy = [](uint64_t need, size_t cap) { return need <= cap ? need : std::max<uint64_t>(2 * need, 1ull << 21); };
+  PGMO_TRY(h->all_vertices.reserve(roomy(n_orig + n_acc + 1, h->all_vertices.cap), st, n_orig));
+  PGMO_TRY(h->all_stamps.reserve(roomy(n_orig + n_acc + 1, h->all_stamps.cap), st, n_orig));
+  PGMO_TRY(h->act_xyz.reserve(roomy(h->n_act + n_acc + 1, h->act_xyz.cap), st, h->n_act));
+  PGMO_TRY(h->act_index.reserve(roomy(h->n_act + n_acc + 1, h->act_index.cap), st, h->n_act));
+  PGMO_TRY(h->act_stamp.reserve(roomy(h->n_act + n_acc + 1, h->act_stamp.cap), st, h->n_act));
   PGMO_TRY(h->act_next.reserve(h->act_xyz.cap, st, h->n_act));
   PGMO_TRY(h->act_sigma.reserve(h->act_xyz.cap, st, h->n_act));
   PGMO_TRY(h->new_vertices.reserve(n_acc + 1));
@@ -799,7 +801,11 @@ static int octIntegrate(pgmo_oct_t* h, uint32_t n_blocks, const int32_t* block_i
 
   // ---- second pass over the candidate faces (:382-416)
   PGMO_TRY(ensurePolyTable(h, n / 3 + 1, st));
-  PGMO_TRY(h->polygons.reserve(3 * (h->n_poly + n / 3 + 1), st, 3 * h->n_poly));
+  {
+    const uint64_t need = 3 * (h->n_poly + n / 3 + 1);
+    PGMO_TRY(h->polygons.reserve(need <= h->polygons.cap ? need : std::max<uint64_t>(2 * need, 1ull << 22), st,
+                                 3 * h->n_poly));
+  }
   PGMO_TRY(h->new_triangles.reserve(3ull * (n / 3 + 1)));
   octFaceClassifyKernel<<<blocksFor(n), 256, 0, st>>>(n, h->surf.ptr, h->reindex.ptr, n_orig, polyTable(h),
                                                       h->keep.ptr, h->face_slot.ptr, h->flags32.ptr + 1);

@@ -205,12 +205,14 @@ int ensureIndexCapacity(pgmo_vcc_t* h, uint64_t extra, cudaStream_t st) {
   const uint64_t needed = h->max_index + extra;
   if (needed <= h->index_cap) return PGMO_OK;
   const uint64_t keep = h->index_cap;
-  PGMO_TRY(h->active.reserve(needed, st, keep));
-  PGMO_TRY(h->inactive.reserve(needed, st, keep));
-  PGMO_TRY(h->live.reserve(needed, st, keep));
-  PGMO_TRY(h->vertices.reserve(needed, st, keep));
-  PGMO_TRY(h->stamps.reserve(needed, st, keep));
-  PGMO_TRY(h->invalid.reserve(needed, st, keep));
+  // cudaMalloc / cudaFree cost tens to hundreds of ms on this platform: grow rarely, by a lot
+  const uint64_t roomy = std::max<uint64_t>(2 * needed, 1ull << 22);
+  PGMO_TRY(h->active.reserve(roomy, st, keep));
+  PGMO_TRY(h->inactive.reserve(roomy, st, keep));
+  PGMO_TRY(h->live.reserve(roomy, st, keep));
+  PGMO_TRY(h->vertices.reserve(roomy, st, keep));
+  PGMO_TRY(h->stamps.reserve(roomy, st, keep));
+  PGMO_TRY(h->invalid.reserve(roomy, st, keep));
   h->index_cap = std::min({h->active.cap, h->inactive.cap, h->live.cap, h->vertices.cap,
                            h->stamps.cap, h->invalid.cap});
   return PGMO_OK;
