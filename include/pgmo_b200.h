@@ -170,6 +170,12 @@ int pgmo_deform_run_device(pgmo_deform_t* h, uint64_t first_position, uint64_t n
                            uint32_t* d_assoc, uint32_t assoc_stride, uint8_t* d_assoc_cnt,
                            uint8_t* d_processed, uint64_t* n_resolved, void* stream);
 
+/* stats4 = [schedule builds so far, stretch the last build resumed from (0 = full replay: control
+ * points were not merely appended, or nothing could be kept), stretches, runs].  When control
+ * points are only appended between two calls (new keyframes) the window schedule is extended
+ * from the first stretch that can see them instead of being replayed from the start. */
+int pgmo_deform_schedule_stats(pgmo_deform_t* h, uint64_t* stats4);
+
 /* Schedule introspection (tests / diagnostics): number of runs, and per run
  * [first_position, lo, hi, k, skip] as u64 x 5. */
 int pgmo_deform_schedule_info(pgmo_deform_t* h, uint64_t* n_runs, uint64_t capacity,

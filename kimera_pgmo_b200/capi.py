@@ -60,6 +60,7 @@ SIGNATURES = {
     "pgmo_deform_run_device": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _vp, _vp, _vp, _vp, C.c_int,
                                          _vp, _vp, _vp, _vp, _vp, C.c_uint32, _vp, _vp, _vp, _vp]),
     "pgmo_deform_schedule_info": (C.c_int, [_vp, _u64p, C.c_uint64, _vp]),
+    "pgmo_deform_schedule_stats": (C.c_int, [_vp, _vp]),
     "pgmo_deform_msg_to_cloud": (C.c_int, [_vp, C.c_uint64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pgmo_deform_cloud_to_msg": (C.c_int, [_vp, C.c_uint64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pgmo_deform_mesh_msg": (C.c_int, [_vp, C.c_uint64, _vp, _vp, C.c_uint32, C.c_double, C.c_int,
@@ -265,6 +266,11 @@ class DeformHandle:
         sl = np.ascontiguousarray(stretch_len, dtype=np.uint64)
         return _check(self._lib.pgmo_deform_build_schedule(
             self._h, ss.shape[0], _ptr(ss), _ptr(sl), total_positions, k, float(tol_t)))
+
+    def schedule_stats(self):
+        s = np.zeros(4, dtype=np.uint64)
+        _check(self._lib.pgmo_deform_schedule_stats(self._h, _ptr(s)))
+        return [int(v) for v in s]
 
     def schedule_info(self):
         n = C.c_uint64(0)

@@ -43,6 +43,10 @@ struct pgmo_deform {
   double sched_tol = 0.0;
   bool sched_stamped = false;
   uint64_t sched_builds = 0;
+  // The control table only grew since `sched` was built (new keyframes: every old position /
+  // stamp / validity unchanged): the next build resumes the replay instead of starting over.
+  bool sched_extendable = false;
+  bool sched_intact = false;  // `sched` is the result of a successful stamped build
   DevBuf<uint64_t> d_run_start;
   DevBuf<uint4> d_run_info;
   DevBuf<RunFrameDev> d_run_frame;
@@ -192,6 +196,12 @@ int finishControls(pgmo_deform_t* h, bool positions_changed, cudaStream_t st) {
     h->sched_ready = false;
   }
   return PGMO_OK;
+}
+
+template <typename T>
+bool samePrefix(const std::vector<T>& have, const T* fresh, uint64_t n_new) {
+  if (!fresh) return have.empty();
+  return have.size() <= n_new && (have.empty() || std::memcmp(have.data(), fresh, have.size() * sizeof(T)) == 0);
 }
 
 template <typename T>
@@ -351,6 +361,13 @@ int pgmo_deform_set_controls(pgmo_deform_t* h, uint64_t n_c, const double* pos_x
   const bool changed = h->n_c != n_c || !sameArray(h->h_pos, pos_xyz, 3 * n_c) ||
                        !sameArray(h->h_stamps, stamps_ns, n_c) ||
                        !sameArray(h->h_valid, valid, n_c);
+  if (changed) {
+    // appended control points only?  (has_valid must not flip: "no validity array" = all valid)
+    const bool grew = h->n_c > 0 && n_c >= h->n_c && samePrefix(h->h_pos, pos_xyz, 3 * n_c) &&
+                      stamps_ns != nullptr && h->has_stamps && samePrefix(h->h_stamps, stamps_ns, n_c) &&
+                      (valid != nullptr) == h->has_valid && samePrefix(h->h_valid, valid, n_c);
+    h->sched_extendable = grew && (h->sched_extendable || h->sched_ready) && h->sched_intact;
+  }
   h->n_c = n_c;
   h->has_stamps = stamps_ns != nullptr;
   h->has_valid = valid != nullptr;
@@ -399,6 +416,13 @@ int pgmo_deform_set_controls_device(pgmo_deform_t* h, uint64_t n_c, const double
   }
   PGMO_CUDA(cudaStreamSynchronize(st));
   const bool changed = h->n_c != n_c || h->h_pos != pos || h->h_stamps != stamps || h->h_valid != valid;
+  if (changed) {
+    const bool grew = h->n_c > 0 && n_c >= h->n_c && samePrefix(h->h_pos, pos.data(), 3 * n_c) &&
+                      d_stamps_ns != nullptr && h->has_stamps && samePrefix(h->h_stamps, stamps.data(), n_c) &&
+                      (d_valid != nullptr) == h->has_valid &&
+                      samePrefix(h->h_valid, d_valid ? valid.data() : nullptr, n_c);
+    h->sched_extendable = grew && (h->sched_extendable || h->sched_ready) && h->sched_intact;
+  }
   h->n_c = n_c;
   h->has_stamps = d_stamps_ns != nullptr;
   h->has_valid = d_valid != nullptr;
@@ -505,13 +529,26 @@ int pgmo_deform_build_schedule(pgmo_deform_t* h, uint64_t n_stretches,
   ctrl.valid = h->has_valid ? h->h_valid.data() : nullptr;
   h->sched_ready = false;
   const auto t_build0 = std::chrono::steady_clock::now();
-  if (stamped) {
+  if (stamped && h->sched_extendable && h->sched_intact && h->sched_stamped && h->sched_k == k &&
+      h->sched_tol == tol_t) {
+    // appended control points (and possibly a grown mesh): resume the replay where the new
+    // inputs can first make a difference
+    uint64_t common = 0;
+    const uint64_t n_old = h->sched_stretch_stamp.size();
+    while (common < n_old && common < n_stretches && h->sched_stretch_stamp[common] == stretch_stamp[common] &&
+           h->sched_stretch_len[common] == stretch_len[common]) {
+      ++common;
+    }
+    extendStampedSchedule(ctrl, n_stretches, stretch_stamp, stretch_len, common, k, tol_t, 1.0, &h->sched);
+  } else if (stamped) {
     buildStampedSchedule(ctrl, n_stretches, stretch_stamp, stretch_len, k, tol_t, 1.0, &h->sched);
   } else {
     buildUnstampedSchedule(ctrl, total_positions, k, 1.0, &h->sched);
   }
   const auto t_build1 = std::chrono::steady_clock::now();
   ++h->sched_builds;
+  h->sched_extendable = false;
+  h->sched_intact = false;
   if (h->sched.noop) return PGMO_NOOP;
   if (h->sched.degenerate) {
     setLastError("a vertex would query an empty control-point tree (undefined in the reference)");
@@ -529,6 +566,7 @@ int pgmo_deform_build_schedule(pgmo_deform_t* h, uint64_t n_stretches,
             std::chrono::duration<double, std::milli>(t_build2 - t_build1).count(), h->sched.runs.size());
   }
   h->sched_ready = true;
+  h->sched_intact = stamped;
   h->sched_control_version = h->control_version;
   h->sched_k = k;
   h->sched_tol = tol_t;
@@ -745,6 +783,15 @@ int pgmo_deform_run_device(pgmo_deform_t* h, uint64_t first_position, uint64_t n
 int pgmo_deform_drop_schedule(pgmo_deform_t* h) {
   PGMO_CHECK_ARG(h != nullptr);
   h->sched_ready = false;
+  return PGMO_OK;
+}
+
+int pgmo_deform_schedule_stats(pgmo_deform_t* h, uint64_t* stats4) {
+  PGMO_CHECK_ARG(h != nullptr && stats4 != nullptr);
+  stats4[0] = h->sched_builds;
+  stats4[1] = h->sched.resumed_from_stretch;
+  stats4[2] = h->sched.checkpoints.empty() ? 0 : h->sched.checkpoints.size() - 1;
+  stats4[3] = h->sched.runs.size();
   return PGMO_OK;
 }
 

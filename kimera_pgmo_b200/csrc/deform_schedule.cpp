@@ -60,6 +60,44 @@ class LeafBook {
     run->shift[0] = shift_[0];
     run->shift[1] = shift_[1];
     run->shift[2] = shift_[2];
+    run->max_xyz[0] = max_[0];
+    run->max_xyz[1] = max_[1];
+    run->max_xyz[2] = max_[2];
+    run->box_defined = box_defined_ ? 1 : 0;
+  }
+
+  // extendStampedSchedule: the box as it was when `run` was emitted (it only changes inside
+  // add(), and every step that adds also emits a run), then the alive points re-inserted in
+  // index order by restore().  Stable keys do not depend on the growth history.
+  void restoreFrame(const ScheduleRun& run, uint32_t max_leaf_points_so_far) {
+    box_defined_ = run.box_defined != 0;
+    for (int a = 0; a < 3; ++a) {
+      min_[a] = run.min_xyz[a];
+      max_[a] = run.max_xyz[a];
+      shift_[a] = run.shift[a];
+    }
+    depth_ = run.depth;
+    max_leaf_points_ = max_leaf_points_so_far;
+  }
+  void restore(uint32_t j, const VoxelKey& stable) {
+    uint64_t at = VoxelKeyHash()(stable) & mask_;
+    while (true) {
+      Slot& s = slots_[at];
+      if (s.state == kLive && s.key == stable) break;
+      if (s.state == kEmpty) {
+        s.state = kLive;
+        s.key = stable;
+        s.head = -1;
+        s.count = 0;
+        ++n_leaves_;
+        break;
+      }
+      at = (at + 1) & mask_;
+    }
+    Slot& leaf = slots_[at];
+    next_[j] = leaf.head;
+    leaf.head = static_cast<int32_t>(j);
+    ++leaf.count;
   }
 
   // addPointFromCloud for control point j at float position p; returns its stable key
@@ -236,28 +274,39 @@ struct Builder {
 
 }  // namespace
 
-void buildStampedSchedule(const ControlTableHost& ctrl, uint64_t n_stretches,
-                          const uint64_t* stretch_stamp, const uint64_t* stretch_len,
-                          uint32_t k_in, double tol_t, double resolution, Schedule* out) {
-  Builder b(ctrl, resolution, out);
-  uint64_t total = 0;
-  for (uint64_t s = 0; s < n_stretches; ++s) total += stretch_len[s];
-  out->total_positions = total;
-  // mesh_deformation.h:143-152
-  if (total == 0 || ctrl.n < k_in) {
-    out->noop = true;
-    return;
-  }
+namespace {
 
+struct ReplayState {
+  size_t k = 0;             // mutated mid-sweep (:183) and stays changed
+  uint64_t hi = 0, lo = 0;  // ctrl_pt_idx / lower_ctrl_pt_idx
+  bool dirty = true;        // search state changed since the last emitted run
+  uint64_t position = 0;
+};
+
+// mesh_deformation.h:159-212 from stretch `s_begin` on
+void replayFrom(Builder& b, ReplayState st, uint64_t s_begin, uint64_t n_stretches,
+                const uint64_t* stretch_stamp, const uint64_t* stretch_len, double tol_t) {
+  const ControlTableHost& ctrl = b.ctrl;
+  Schedule* out = b.out;
   const uint64_t tol = stampFromSec(tol_t);
   const uint64_t n_c = ctrl.n;
-  size_t k = k_in;           // mutated mid-sweep (:183) and stays changed
-  uint64_t hi = 0, lo = 0;   // ctrl_pt_idx / lower_ctrl_pt_idx
-  bool dirty = true;         // search state changed since the last emitted run
-  uint64_t position = 0;
+  size_t k = st.k;
+  uint64_t hi = st.hi, lo = st.lo;
+  bool dirty = st.dirty;
+  uint64_t position = st.position;
   std::vector<uint32_t> killed;
+  out->checkpoints.resize(s_begin);
+  out->end_touch_stretch = ~0ull;
 
-  for (uint64_t s = 0; s < n_stretches; ++s) {
+  for (uint64_t s = s_begin; s < n_stretches; ++s) {
+    StretchCheckpoint cp;
+    cp.position = position;
+    cp.run_count = static_cast<uint32_t>(out->runs.size());
+    cp.lo = static_cast<uint32_t>(lo);
+    cp.hi = static_cast<uint32_t>(hi);
+    cp.k = static_cast<uint32_t>(k);
+    cp.dirty = dirty ? 1 : 0;
+    out->checkpoints.push_back(cp);
     const uint64_t stamp = stretch_stamp[s];
     const uint64_t len = stretch_len[s];
     for (uint64_t v = 0; v < len; ++v) {
@@ -271,6 +320,8 @@ void buildStampedSchedule(const ControlTableHost& ctrl, uint64_t n_stretches,
         if (!valid) continue;
         ++num_ctrl_pts;
       }
+      // the loop condition was just evaluated with hi == n_c: appended controls would change it
+      if (hi == n_c && out->end_touch_stretch == ~0ull) out->end_touch_stretch = s;
       bool skip = false;
       if (b.book.leafCount() < k + 1) {  // :180
         if (num_ctrl_pts > 1) {
@@ -308,7 +359,100 @@ void buildStampedSchedule(const ControlTableHost& ctrl, uint64_t n_stretches,
     }
     position += len;
   }
-  out->max_leaf_points = b.book.maxLeafPoints();
+  StretchCheckpoint last;  // behind the last stretch: where appended stretches resume
+  last.position = position;
+  last.run_count = static_cast<uint32_t>(out->runs.size());
+  last.lo = static_cast<uint32_t>(lo);
+  last.hi = static_cast<uint32_t>(hi);
+  last.k = static_cast<uint32_t>(k);
+  last.dirty = dirty ? 1 : 0;
+  out->checkpoints.push_back(last);
+  out->max_leaf_points = std::max(out->max_leaf_points, b.book.maxLeafPoints());
+  out->built_n_controls = n_c;
+}
+
+}  // namespace
+
+void buildStampedSchedule(const ControlTableHost& ctrl, uint64_t n_stretches,
+                          const uint64_t* stretch_stamp, const uint64_t* stretch_len,
+                          uint32_t k_in, double tol_t, double resolution, Schedule* out) {
+  Builder b(ctrl, resolution, out);
+  out->checkpoints.clear();
+  out->end_touch_stretch = ~0ull;
+  out->built_n_controls = ctrl.n;
+  out->resumed_from_stretch = 0;
+  uint64_t total = 0;
+  for (uint64_t s = 0; s < n_stretches; ++s) total += stretch_len[s];
+  out->total_positions = total;
+  // mesh_deformation.h:143-152
+  if (total == 0 || ctrl.n < k_in) {
+    out->noop = true;
+    return;
+  }
+  ReplayState st;
+  st.k = k_in;
+  replayFrom(b, st, 0, n_stretches, stretch_stamp, stretch_len, tol_t);
+}
+
+void extendStampedSchedule(const ControlTableHost& ctrl, uint64_t n_stretches,
+                           const uint64_t* stretch_stamp, const uint64_t* stretch_len,
+                           uint64_t common_stretches, uint32_t k_in, double tol_t, double resolution,
+                           Schedule* inout) {
+  const uint64_t n_old = inout->built_n_controls;
+  uint64_t total = 0;
+  for (uint64_t s = 0; s < n_stretches; ++s) total += stretch_len[s];
+  const bool has_state = !inout->noop && !inout->degenerate && !inout->runs.empty() &&
+                         !inout->checkpoints.empty() && n_old <= ctrl.n && inout->del_run.size() == n_old;
+  uint64_t s_resume = 0;
+  if (has_state) {
+    const uint64_t old_stretches = inout->checkpoints.size() - 1;
+    s_resume = std::min<uint64_t>({common_stretches, inout->end_touch_stretch, old_stretches, n_stretches});
+  }
+  if (!has_state || total == 0 || ctrl.n < k_in || inout->checkpoints[s_resume].run_count == 0) {
+    buildStampedSchedule(ctrl, n_stretches, stretch_stamp, stretch_len, k_in, tol_t, resolution, inout);
+    return;
+  }
+  const StretchCheckpoint cp = inout->checkpoints[s_resume];  // state at the start of that stretch
+  const uint32_t R = cp.run_count;
+  std::vector<ScheduleRun> runs(inout->runs.begin(), inout->runs.begin() + R);
+  std::vector<int32_t> del_run(inout->del_run);
+  std::vector<int32_t> stable_key(inout->stable_key);
+  const uint32_t max_leaf = inout->max_leaf_points;
+  const uint32_t max_k_prefix = [&] {
+    uint32_t m = 0;
+    for (const auto& r : runs) m = std::max(m, r.k);
+    return m;
+  }();
+  std::vector<StretchCheckpoint> cps(inout->checkpoints.begin(), inout->checkpoints.begin() + s_resume);
+
+  Builder b(ctrl, resolution, inout);  // resets the output for the new table
+  inout->runs = std::move(runs);
+  inout->max_k = max_k_prefix;
+  inout->max_leaf_points = max_leaf;
+  inout->checkpoints = std::move(cps);
+  inout->total_positions = total;
+  // per control point: dead before the resume point stays dead; everything else is alive again
+  for (uint64_t j = 0; j < n_old; ++j) {
+    if (!b.isValid(j)) continue;  // Builder set 0
+    inout->del_run[j] = del_run[j] <= static_cast<int32_t>(R) && del_run[j] != 0 ? del_run[j] : INT32_MAX;
+    inout->stable_key[3 * j + 0] = stable_key[3 * j + 0];
+    inout->stable_key[3 * j + 1] = stable_key[3 * j + 1];
+    inout->stable_key[3 * j + 2] = stable_key[3 * j + 2];
+  }
+  b.book.restoreFrame(inout->runs[R - 1], max_leaf);
+  for (uint64_t j = cp.lo; j < cp.hi; ++j) {  // added and not deleted yet
+    if (!b.isValid(j) || inout->del_run[j] != INT32_MAX) continue;
+    b.book.restore(static_cast<uint32_t>(j), VoxelKey{stable_key[3 * j + 0], stable_key[3 * j + 1],
+                                                      stable_key[3 * j + 2]});
+  }
+  ReplayState st;
+  st.k = cp.k;
+  st.hi = cp.hi;
+  st.lo = cp.lo;
+  st.dirty = cp.dirty != 0;
+  st.position = cp.position;
+  inout->resumed_from_stretch = s_resume;
+  replayFrom(b, st, s_resume, n_stretches, stretch_stamp, stretch_len, tol_t);
 }
 
 void buildUnstampedSchedule(const ControlTableHost& ctrl, uint64_t total_positions, uint32_t k,

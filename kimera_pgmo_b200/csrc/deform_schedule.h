@@ -26,6 +26,16 @@ struct ScheduleRun {
   double min_xyz[3] = {0, 0, 0};
   uint32_t depth = 0;
   int32_t shift[3] = {0, 0, 0};
+  double max_xyz[3] = {0, 0, 0};  // host only: lets extendStampedSchedule restore the box exactly
+  uint8_t box_defined = 0;        // host only: a control point had been added by then
+};
+
+// State of the replay at the start of a stretch (what extendStampedSchedule resumes from).
+struct StretchCheckpoint {
+  uint64_t position = 0;   // processing position of the stretch's first vertex
+  uint32_t run_count = 0;  // runs emitted so far
+  uint32_t lo = 0, hi = 0, k = 0;
+  uint8_t dirty = 0;
 };
 
 struct Schedule {
@@ -37,6 +47,13 @@ struct Schedule {
   uint32_t max_k = 0;
   bool noop = false;                  // reference early return
   bool degenerate = false;            // a processed vertex would query an empty tree (reference UB)
+  // for the incremental rebuild: one checkpoint per stretch plus one behind the last, and the first stretch whose replay
+  // looked at the end of the control table (UINT64_MAX: none did).  Everything before that
+  // stretch is independent of control points appended later.
+  std::vector<StretchCheckpoint> checkpoints;
+  uint64_t end_touch_stretch = ~0ull;
+  uint64_t built_n_controls = 0;
+  uint64_t resumed_from_stretch = 0;  // diagnostics: 0 = full replay
 };
 
 struct ControlTableHost {
@@ -50,6 +67,19 @@ struct ControlTableHost {
 void buildStampedSchedule(const ControlTableHost& ctrl, uint64_t n_stretches,
                           const uint64_t* stretch_stamp, const uint64_t* stretch_len,
                           uint32_t k, double tol_t, double resolution, Schedule* out);
+
+// The same schedule after control points were APPENDED to the table `inout` was built from
+// (positions / stamps / validity of the first inout->built_n_controls entries unchanged) and / or
+// the stretch list changed behind its first `common_stretches` entries: the replay resumes at
+// the first stretch that can see a difference — the earlier of `common_stretches` and the first
+// stretch that looked at the end of the old table — from that stretch's checkpoint, with the
+// octree's leaf bookkeeping rebuilt from the alive set recorded in the schedule itself.  Falls
+// back to a full replay when nothing can be kept.  Result == buildStampedSchedule on the new
+// inputs (tests/test_schedule_cpu.py).
+void extendStampedSchedule(const ControlTableHost& ctrl, uint64_t n_stretches,
+                           const uint64_t* stretch_stamp, const uint64_t* stretch_len,
+                           uint64_t common_stretches, uint32_t k, double tol_t, double resolution,
+                           Schedule* inout);
 
 // Unstamped overload (mesh_deformation.h:63-113): one run over all valid control points.
 void buildUnstampedSchedule(const ControlTableHost& ctrl, uint64_t total_positions, uint32_t k,

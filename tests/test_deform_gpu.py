@@ -297,3 +297,44 @@ def test_alive_set_sizes_at_kernel_boundaries(capi, oracle, n_ctrl):
     # a stamped sweep whose window holds the same set for every vertex
     gpu, ref = _run_both(capi, oracle, case, 4, 1.0e6)
     _compare(gpu, ref)
+
+
+def test_appended_controls_extend_the_schedule(capi, oracle):
+    """New keyframes since the last deformMesh: control points appended, mesh grown.  The window
+    schedule is resumed from the first stretch that can see them (not replayed from the start)
+    and the result is the one a fresh handle / the oracle gives."""
+    case = synth.deformation_case(60_000, 1200, seed=31, invalid_fraction=0.02)
+    n_c_old, n_v_old = 1100, 55_000
+    h = capi.DeformHandle(0)
+    h.set_controls(case["ctrl_xyz"][:n_c_old], case["ctrl_stamps"][:n_c_old], case["valid"][:n_c_old],
+                   case["poses"][:n_c_old])
+    first = h.deform_points(case["x"][:n_v_old], case["y"][:n_v_old], case["z"][:n_v_old],
+                            case["stamps"][:n_v_old], k=4, tol_t=10.0)
+    assert first["rc"] == 0
+    builds0 = h.schedule_stats()[0]
+    _set(h, case)
+    gpu = h.deform_points(case["x"], case["y"], case["z"], case["stamps"], k=4, tol_t=10.0, want_f64=True,
+                          want_assoc=True)
+    builds, resumed, n_stretches, _ = h.schedule_stats()
+    assert builds == builds0 + 1 and resumed > 0.5 * n_stretches, (builds, resumed, n_stretches)
+    ref = oracle.deform_points(case["x"], case["y"], case["z"], case["stamps"], case["ctrl_xyz"],
+                               case["ctrl_stamps"], case["valid"], case["poses"], k=4, tol_t=10.0)
+    _compare(gpu, ref)
+    # same table again, different k: nothing to extend from -> full replay, still right
+    gpu = h.deform_points(case["x"], case["y"], case["z"], case["stamps"], k=3, tol_t=10.0, want_f64=True,
+                          want_assoc=True)
+    assert h.schedule_stats()[1] == 0
+    ref = oracle.deform_points(case["x"], case["y"], case["z"], case["stamps"], case["ctrl_xyz"],
+                               case["ctrl_stamps"], case["valid"], case["poses"], k=3, tol_t=10.0)
+    _compare(gpu, ref)
+    # an old control point moved: not an append -> full replay
+    moved = case["ctrl_xyz"].copy()
+    moved[5, 0] += 0.25
+    h.set_controls(moved, case["ctrl_stamps"], case["valid"], case["poses"])
+    gpu = h.deform_points(case["x"], case["y"], case["z"], case["stamps"], k=3, tol_t=10.0, want_f64=True,
+                          want_assoc=True)
+    assert h.schedule_stats()[1] == 0
+    ref = oracle.deform_points(case["x"], case["y"], case["z"], case["stamps"], moved, case["ctrl_stamps"],
+                               case["valid"], case["poses"], k=3, tol_t=10.0)
+    _compare(gpu, ref)
+    h.close()

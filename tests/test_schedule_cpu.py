@@ -150,3 +150,47 @@ def test_reference_time_check_scenario(sched_lib, oracle):
     # arrive and the four stamp-0 survivors go
     assert runs[0, 2] == 6 and runs[1, 1] == 2
     assert list(del_run[:6]) == [1, 1, 3, 3, 3, 3] or del_run[0] == 1
+
+
+def _extend_check(lib, case, n_old, v_old, k=4, tol_t=10.0):
+    """old = first n_old controls + first v_old vertices; new = everything"""
+    lib.schedule_extend_check.restype = C.c_long
+    lib.schedule_extend_check.argtypes = [C.c_ulong, C.c_ulong, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_ulong, C.c_void_p, C.c_void_p, C.c_ulong, C.c_void_p,
+                                          C.c_void_p, C.c_uint, C.c_double, C.c_void_p]
+    pos = np.ascontiguousarray(case["ctrl_xyz"], dtype=np.float64)
+    cst = np.ascontiguousarray(case["ctrl_stamps"], dtype=np.uint64)
+    valid = np.ascontiguousarray(case["valid"], dtype=np.uint8)
+    so, lo = _stretches(case["stamps"][:v_old])
+    sn, ln = _stretches(case["stamps"])
+    resumed = C.c_ulong(0)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib.schedule_extend_check(n_old, pos.shape[0], p(pos), p(cst), p(valid), so.shape[0], p(so), p(lo),
+                                   sn.shape[0], p(sn), p(ln), k, tol_t, C.byref(resumed))
+    return rc, int(resumed.value), sn.shape[0]
+
+
+def test_incremental_schedule_equals_full_rebuild(sched_lib):
+    """Control points appended (new keyframes since the last deformMesh) and / or the mesh grown:
+    extendStampedSchedule must give exactly the from-scratch schedule, and resume late."""
+    resumed_late = 0
+    for seed, (n_v, n_c, kw) in enumerate([
+            (40_000, 800, {}), (40_000, 800, dict(invalid_fraction=0.05)), (30_000, 600, dict(ctrl_spread=1.0)),
+            (30_000, 300, dict(ctrl_per_kf=3)), (20_000, 400, dict(t0_ns=0))]):
+        case = synth.deformation_case(n_v, n_c, seed=20 + seed, **kw)
+        n_kf = n_c // kw.get("ctrl_per_kf", 10)
+        for frac_c, frac_v in ((0.9, 0.9), (0.99, 1.0), (1.0, 0.95), (0.5, 0.5), (0.97, 0.6), (0.3, 1.0), (0.999, 0.999)):
+            n_old = max(int(n_c * frac_c), 1)
+            v_old = max(int(n_v * frac_v), 1)
+            for k, tol in ((4, 10.0), (2, 3.0), (4, 1.0e6)):
+                rc, resumed, n_stretches = _extend_check(sched_lib, case, n_old, v_old, k, tol)
+                assert rc == 0, (seed, frac_c, frac_v, k, tol, rc)
+                if tol == 10.0 and frac_c >= 0.9 and frac_v >= 0.9:
+                    assert resumed > 0.5 * n_stretches, (seed, frac_c, frac_v, resumed, n_stretches, n_kf)
+                    resumed_late += 1
+    assert resumed_late >= 10
+    # nothing appended at all: still identical
+    case = synth.deformation_case(10_000, 200, seed=3)
+    assert _extend_check(sched_lib, case, 200, 10_000)[0] == 0
+    # fewer controls than k before the extension: the old schedule was a no-op
+    assert _extend_check(sched_lib, case, 3, 10_000)[0] == 0
