@@ -45,6 +45,7 @@ struct pgmo_deform {
   uint64_t sched_builds = 0;
   // The control table only grew since `sched` was built (new keyframes: every old position /
   // stamp / validity unchanged): the next build resumes the replay instead of starting over.
+  bool force_traversal = false;  // PGMO_RESOLVER_TRAVERSAL=1: always replay PCL's traversal (tests)
   bool sched_extendable = false;
   bool sched_intact = false;  // `sched` is the result of a successful stamped build
   DevBuf<uint64_t> d_run_start;
@@ -310,6 +311,7 @@ int pgmo_deform_create(int device, pgmo_deform_t** out) {
   if (const char* e = std::getenv("PGMO_R_GROW_MUL")) h->r_grow_mul = static_cast<float>(atof(e));
   if (const char* e = std::getenv("PGMO_R_GROW_ADD")) h->r_grow_add = static_cast<float>(atof(e));
   if (const char* e = std::getenv("PGMO_FAR_MUL")) h->far_mul = static_cast<float>(atof(e));
+  if (const char* e = std::getenv("PGMO_RESOLVER_TRAVERSAL")) h->force_traversal = atoi(e) != 0;
   cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&h->ev_stamps, cudaEventDisableTiming);
@@ -707,6 +709,7 @@ static int runDeviceRange(pgmo_deform_t* h, uint64_t first_position, uint64_t n_
   ResolveArgs ra;
   ra.n_warps = resolverResidentWarps(h->device);
   ra.cand_cap = h->sched.max_k + 2 + h->sched.max_leaf_points + 1;
+  ra.max_leaf_points = h->force_traversal ? 1000u : h->sched.max_leaf_points;
   PGMO_TRY(h->d_scratch.reserve(static_cast<size_t>(ra.n_warps) * ra.cand_cap * 2));
   ra.scratch = h->d_scratch.ptr;
 

@@ -96,6 +96,7 @@ struct ResolveArgs {
   CandEntry* scratch;        // one slab of cand_cap entries per resident warp
   uint32_t cand_cap;
   uint32_t n_warps;          // resident warps (grid is persistent)
+  uint32_t max_leaf_points;  // most control points ever sharing one voxel (Schedule)
 };
 
 // K1: boundaries of equal-stamp stretches.  Appends (position, stamp) of every position whose

@@ -1,6 +1,5 @@
-// K4 device code: exact replay of PCL's getKNearestNeighborRecursive for one vertex by one warp.
-// Shared by the stand-alone resolver kernel (deform_kernels.cu) and by the K3 kernel, whose CTAs
-// resolve their own few tied vertices after their last group (deform_sorted.cu).
+// K4 device code: PCL's nearestKSearch result, tie order included, for one vertex by one warp
+// (deform_kernels.cu: deformResolveKernel).
 #pragma once
 
 #include <cfloat>
@@ -33,7 +32,36 @@ constexpr int kResolveStage = 320;  // alive points of the vertex's run staged p
 struct ResolveStage {
   float4 pts[kResolveStage];    // x, y, z, control index (int bits), ascending control index
   uint32_t key[kResolveStage][3];  // leaf key in the run's octree frame
+  float d2[kResolveStage];      // exact d^2 to the vertex (order-of-visit path)
 };
+
+// Which of two alive points does PCL's depth-first search reach first?  Same leaf: the leaf
+// holds its points in insertion order (ascending control index = staged order).  Otherwise the
+// two root-to-leaf paths split at one node, whose children are visited by ascending float
+// distance of the voxel centre to the query, equal distances by descending child index
+// (getKNearestNeighborRecursive; the first child's whole subtree precedes the second's).
+__device__ __forceinline__ bool visitedBefore(const ResolveStage& st, int ia, int ib,
+                                              const RunFrameDev& frame, double resolution, float qx,
+                                              float qy, float qz) {
+  const uint32_t ax = st.key[ia][0], ay = st.key[ia][1], az = st.key[ia][2];
+  const uint32_t bx = st.key[ib][0], by = st.key[ib][1], bz = st.key[ib][2];
+  const uint32_t x = (ax ^ bx) | (ay ^ by) | (az ^ bz);
+  if (x == 0) return ia < ib;
+  const int m = 31 - __clz(x);  // the children that hold a and b are the nodes of height m
+  const double side = __dmul_rn(resolution, static_cast<double>(1u << m));
+  // genVoxelCenterFromOctreeKey: double arithmetic, float result
+  auto centreDist = [&](uint32_t kx, uint32_t ky, uint32_t kz) {
+    const float vx = __double2float_rn(__dadd_rn(__dmul_rn(__dadd_rn(static_cast<double>(kx >> m), 0.5), side), frame.min_xyz[0]));
+    const float vy = __double2float_rn(__dadd_rn(__dmul_rn(__dadd_rn(static_cast<double>(ky >> m), 0.5), side), frame.min_xyz[1]));
+    const float vz = __double2float_rn(__dadd_rn(__dmul_rn(__dadd_rn(static_cast<double>(kz >> m), 0.5), side), frame.min_xyz[2]));
+    return dist2Exact(vx, vy, vz, qx, qy, qz);
+  };
+  const float da = centreDist(ax, ay, az), db = centreDist(bx, by, bz);
+  if (da != db) return da < db;
+  const int ca = (((ax >> m) & 1) << 2) | (((ay >> m) & 1) << 1) | ((az >> m) & 1);
+  const int cb = (((bx >> m) & 1) << 2) | (((by >> m) & 1) << 1) | ((bz >> m) & 1);
+  return ca > cb;
+}
 
 __device__ __forceinline__ bool aliveInRun(const float4& c, int run) {
   return __float_as_int(c.w) > run;
@@ -81,12 +109,59 @@ __device__ __noinline__ void resolveOne(const DeformArgs& a, const ResolveArgs& 
   uint32_t n_cand = 0;
   double best = DBL_MAX;
 
+  // Order-of-visit path.  The candidate vector never holds more than K + (points of one leaf)
+  // entries; up to 16 of them std::sort is an insertion sort, i.e. stable, so equal distances
+  // stay in the order they were pushed = the order the search visits them, and a tied point is
+  // dropped at the K-th place exactly when it is visited later (it fails `d2 < smallest` once
+  // the list is full, or loses the stable sort's truncation).  The pruning bound never cuts a
+  // point closer than the current K-th distance, so the result is "the K smallest under
+  // (d^2, visit order)" — computed directly, without replaying the traversal.
+  const bool by_order = staged && K + ra.max_leaf_points <= 16 && K <= ra.cand_cap;
+  if (by_order) {
+    for (int i = lane; i < n_staged; i += 32) {
+      const float4 cp = stage.pts[i];
+      stage.d2[i] = dist2Exact(cp.x, cp.y, cp.z, qx, qy, qz);
+    }
+    __syncwarp();
+    uint32_t taken = 0;  // bit t: this lane's point lane + 32 t is already selected
+    const uint32_t want = static_cast<uint32_t>(n_staged) < K ? static_cast<uint32_t>(n_staged) : K;
+    for (uint32_t rnk = 0; rnk < want; ++rnk) {
+      int bi = -1;
+      float bd = 0.f;
+      for (int t = 0, i = lane; i < n_staged; ++t, i += 32) {
+        if (taken & (1u << t)) continue;
+        const float d = stage.d2[i];
+        if (bi < 0 || d < bd || (d == bd && visitedBefore(stage, i, bi, frame, a.resolution, qx, qy, qz))) {
+          bi = i;
+          bd = d;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const int oi = __shfl_xor_sync(full, bi, o);
+        const float od = __shfl_xor_sync(full, bd, o);
+        if (oi >= 0 && (bi < 0 || od < bd ||
+                        (od == bd && visitedBefore(stage, oi, bi, frame, a.resolution, qx, qy, qz)))) {
+          bi = oi;
+          bd = od;
+        }
+      }
+      if ((bi & 31) == lane) taken |= 1u << (bi >> 5);
+      if (lane == 0) {
+        cand[rnk].dist = bd;
+        cand[rnk].idx = __float_as_int(stage.pts[bi].w);
+      }
+    }
+    n_cand = want;
+  }
+
   int level = 0;
   if (lane == 0) {
     levels[0].key[0] = levels[0].key[1] = levels[0].key[2] = 0;
   }
   __syncwarp();
   bool entering = true;
+  if (by_order) level = -1;  // nothing left for the traversal
   while (level >= 0) {
     DfsLevel& L = levels[level];
     if (entering) {
