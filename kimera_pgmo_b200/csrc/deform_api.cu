@@ -56,6 +56,7 @@ struct pgmo_deform {
   int grid_mode = 1;  // 0 = brute force over the window, 1 = bucket-ordered lists (+ grid walk
                       // for alive sets > kSortedMaxPoints), 2 = grid walk only
   uint64_t widest_window = 0;
+  uint32_t sched_min_k = 0;  // smallest k over the processed runs (k shrinks when controls are scarce)
   DevBuf<RunGridDev> d_grids;
   DevBuf<float4> d_grid_points;
   DevBuf<uint32_t> d_grid_cells;
@@ -168,6 +169,11 @@ int uploadSchedule(pgmo_deform_t* h, cudaStream_t st) {
   }
   offsets[n_runs] = static_cast<uint32_t>(total_slots);
   h->widest_window = widest;
+  uint32_t min_k = ~0u;
+  for (size_t r = 0; r < n_runs; ++r) {
+    if (!s.runs[r].skip) min_k = std::min(min_k, s.runs[r].k);
+  }
+  h->sched_min_k = min_k == ~0u ? 0 : min_k;
   if (h->grid_mode != 0 && n_runs > 0 && widest > 48 && total_slots < (1ull << 28)) {
     PGMO_TRY(h->d_grids.reserve(n_runs));
     PGMO_TRY(h->d_grid_points.reserve(total_slots + 1));
@@ -736,7 +742,7 @@ static int runDeviceRange(pgmo_deform_t* h, uint64_t first_position, uint64_t n_
     }
     if (h->grid_mode == 1) {
       PGMO_CUDA(launchDeformKnnBlendSorted(a, ga, h->d_items.ptr + i0, i1 - i0, precision,
-                                           h->sched.max_k, h->widest_window, st));
+                                           h->sched.max_k, h->sched_min_k, h->widest_window, st));
       if (h->widest_window > static_cast<uint64_t>(kSortedMaxPoints)) {
         PGMO_CUDA(launchDeformKnnBlendGrid(a, ga, h->d_items.ptr + i0, i1 - i0, precision,
                                            h->sched.max_k, kSortedMaxPoints, st));

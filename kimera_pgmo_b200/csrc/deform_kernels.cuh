@@ -125,7 +125,8 @@ cudaError_t launchDeformKnnBlendGrid(const DeformArgs& args, const GridArgs& gar
 // alive points and leaves the others untouched.  Same result as the other two K3 kernels.
 cudaError_t launchDeformKnnBlendSorted(const DeformArgs& args, const GridArgs& gargs,
                                        const WorkItem* items, uint32_t n_items, int precision,
-                                       uint32_t max_k, uint64_t widest_window, cudaStream_t stream);
+                                       uint32_t max_k, uint32_t min_k, uint64_t widest_window,
+                                       cudaStream_t stream);
 
 // forces the lazy loading of the default K3 kernels (handle creation)
 void preloadDeformSortedKernels();

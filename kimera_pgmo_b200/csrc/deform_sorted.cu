@@ -231,7 +231,11 @@ struct SmemOf {
   using type = SortedSmem<MAXPTS, Pose>;
 };
 
-template <int KCAP, int PREC, int MAXPTS, bool STAGE>
+// FULL: every vertex blends exactly KCAP - 2 neighbours (k + 1 with KCAP = k + 3) — the caller
+// asked for one k (no mid-sweep change) and the item's alive set holds at least KCAP points.  The
+// neighbour counts are then compile-time constants and every per-slot guard disappears; items
+// that do not qualify (a handful of vertices at the start of a trajectory) go to the resolver.
+template <int KCAP, int PREC, int MAXPTS, bool STAGE, bool FULL>
 __global__ void __launch_bounds__(kSThreads, STAGE ? PGMO_K3_CTAS : 4)
 deformKnnBlendSortedKernel(const DeformArgs a, const GridArgs ga,
                            const WorkItem* __restrict__ items) {
@@ -255,7 +259,7 @@ deformKnnBlendSortedKernel(const DeformArgs a, const GridArgs ga,
   const int n_alive = static_cast<int>(g.n_alive);
   if (n_alive > kSMaxPts) return;  // another kernel's item
   const int K = static_cast<int>(info.z) + 2;
-  if (K + 1 > KCAP) {
+  if (K + 1 > KCAP || (FULL && (K + 1 != KCAP || n_alive < KCAP))) {
     for (int i = t; i < count; i += kSThreads) sendToResolver(a, p_base + i);
     return;
   }
@@ -427,15 +431,15 @@ deformKnnBlendSortedKernel(const DeformArgs a, const GridArgs ga,
   // ---- per group of 32 sorted vertices: select the alive points around the group's box, walk
   const unsigned full = 0xFFFFFFFFu;
   uint16_t* list = S.u.w.list[warp];
-  const int n_need = n_alive < K + 1 ? n_alive : K + 1;
-  const int n = n_alive < K ? n_alive : K;
+  const int n_need = FULL ? KCAP : (n_alive < K + 1 ? n_alive : K + 1);
+  const int n = FULL ? KCAP - 1 : (n_alive < K ? n_alive : K);
   // ordinal bits: enough for every list position of this run (two padding entries included)
   const int ord_bits = n_alive + 2 <= 128 ? 7 : (n_alive + 2 <= 256 ? 8 : (n_alive + 2 <= 512 ? 9 : 10));
   const uint32_t ord_mask = (1u << ord_bits) - 1u;
   // first selection radius^2 (box distance) and the radius^2 beyond which a point is "far"
   const float t0 = fmaxf(g.r0 * g.r0 * 1.3f * ga.r_scale, 1e-20f);
   const float t_far = fmaxf(ga.far_mul, 1.f) * t0;
-  const bool full_k = n_need == KCAP;
+  const bool full_k = FULL || n_need == KCAP;
 
   // A warp takes whole slabs (256 sorted vertices = 8 groups).  Per slab the alive points are
   // split once: points whose lower-bound distance to the SLAB's box is beyond t_far are "far"
@@ -701,7 +705,7 @@ deformKnnBlendSortedKernel(const DeformArgs a, const GridArgs ga,
   }
 }
 
-template <int KCAP, int PREC, int MAXPTS, bool STAGE>
+template <int KCAP, int PREC, int MAXPTS, bool STAGE, bool FULL>
 cudaError_t launchOne(const DeformArgs& args, const GridArgs& gargs, const WorkItem* items,
                       uint32_t n_items, cudaStream_t stream) {
   const size_t smem = sizeof(typename SmemOf<PREC, MAXPTS, STAGE>::type);
@@ -710,28 +714,28 @@ cudaError_t launchOne(const DeformArgs& args, const GridArgs& gargs, const WorkI
   cudaGetDevice(&device);
   if (configured_device != device) {
     const cudaError_t e =
-        cudaFuncSetAttribute(deformKnnBlendSortedKernel<KCAP, PREC, MAXPTS, STAGE>,
+        cudaFuncSetAttribute(deformKnnBlendSortedKernel<KCAP, PREC, MAXPTS, STAGE, FULL>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
     configured_device = device;
   }
-  deformKnnBlendSortedKernel<KCAP, PREC, MAXPTS, STAGE>
+  deformKnnBlendSortedKernel<KCAP, PREC, MAXPTS, STAGE, FULL>
       <<<n_items, kSThreads, smem, stream>>>(args, gargs, items);
   return cudaGetLastError();
 }
 
-template <int KCAP, int PREC>
+template <int KCAP, int PREC, bool FULL>
 cudaError_t launchVariant(const DeformArgs& args, const GridArgs& gargs, const WorkItem* items,
                           uint32_t n_items, bool staged, cudaStream_t stream) {
-  return staged ? launchOne<KCAP, PREC, kStagedMaxPts, true>(args, gargs, items, n_items, stream)
-                : launchOne<KCAP, PREC, kSortedMaxPoints, false>(args, gargs, items, n_items, stream);
+  return staged ? launchOne<KCAP, PREC, kStagedMaxPts, true, FULL>(args, gargs, items, n_items, stream)
+                : launchOne<KCAP, PREC, kSortedMaxPoints, false, FULL>(args, gargs, items, n_items, stream);
 }
 
 template <int KCAP, int PREC>
 void preloadVariants() {
   cudaFuncAttributes attr;
-  cudaFuncGetAttributes(&attr, deformKnnBlendSortedKernel<KCAP, PREC, kStagedMaxPts, true>);
-  cudaFuncGetAttributes(&attr, deformKnnBlendSortedKernel<KCAP, PREC, kSortedMaxPoints, false>);
+  cudaFuncGetAttributes(&attr, deformKnnBlendSortedKernel<KCAP, PREC, kStagedMaxPts, true, true>);
+  cudaFuncGetAttributes(&attr, deformKnnBlendSortedKernel<KCAP, PREC, kSortedMaxPoints, false, true>);
 }
 
 }  // namespace
@@ -745,16 +749,21 @@ void preloadDeformSortedKernels() {
 
 cudaError_t launchDeformKnnBlendSorted(const DeformArgs& args, const GridArgs& gargs,
                                        const WorkItem* items, uint32_t n_items, int precision,
-                                       uint32_t max_k, uint64_t widest_window, cudaStream_t stream) {
+                                       uint32_t max_k, uint32_t min_k, uint64_t widest_window,
+                                       cudaStream_t stream) {
   if (n_items == 0) return cudaSuccess;
   // every alive set fits the staged variant (pose rows in shared memory) iff the widest window does
   const bool staged = widest_window <= static_cast<uint64_t>(kStagedMaxPts);
-  if (max_k + 3 <= 7) {
-    return precision == 0 ? launchVariant<7, 0>(args, gargs, items, n_items, staged, stream)
-                          : launchVariant<7, 1>(args, gargs, items, n_items, staged, stream);
+  if (max_k == 4 && min_k == 4) {  // the reference's default k, never changed mid-sweep
+    return precision == 0 ? launchVariant<7, 0, true>(args, gargs, items, n_items, staged, stream)
+                          : launchVariant<7, 1, true>(args, gargs, items, n_items, staged, stream);
   }
-  return precision == 0 ? launchVariant<16, 0>(args, gargs, items, n_items, staged, stream)
-                        : launchVariant<16, 1>(args, gargs, items, n_items, staged, stream);
+  if (max_k + 3 <= 7) {
+    return precision == 0 ? launchVariant<7, 0, false>(args, gargs, items, n_items, staged, stream)
+                          : launchVariant<7, 1, false>(args, gargs, items, n_items, staged, stream);
+  }
+  return precision == 0 ? launchVariant<16, 0, false>(args, gargs, items, n_items, staged, stream)
+                        : launchVariant<16, 1, false>(args, gargs, items, n_items, staged, stream);
 }
 
 }  // namespace pgmo
