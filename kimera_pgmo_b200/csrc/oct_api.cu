@@ -312,35 +312,34 @@ uint64_t nextPow2(uint64_t v) {
 }
 
 struct TreeStore {
-  DevBuf<unsigned long long> keys;
-  DevBuf<uint32_t> minseq, head;
+  // keys (u64), minseq (u32) and head (u32) share one allocation so that emptying the table is
+  // one memset: slab[0, cap) keys, then cap minseq words, then cap head words
+  DevBuf<unsigned long long> slab;
   DevBuf<OctFrames> frames;
   uint64_t cap = 0;
   uint64_t factor = 8;  // table slots per point; doubled when a build reports "table full"
   OctTable table() const {
     OctTable t;
-    t.keys = keys.ptr;
-    t.minseq = minseq.ptr;
-    t.head = head.ptr;
+    t.keys = slab.ptr;
+    t.minseq = reinterpret_cast<uint32_t*>(slab.ptr + cap);
+    t.head = t.minseq + cap;
     t.mask = static_cast<uint32_t>(cap - 1);
     return t;
+  }
+  void releaseTable() {
+    slab.release();
+    cap = 0;
   }
   // empties the table (and optionally the frames) with room for `points` points
   int reset(uint64_t points, bool reset_frames, cudaStream_t st) {
     const uint64_t want = std::max<uint64_t>(nextPow2(factor * std::max<uint64_t>(points, 1)), 1024);
     if (want > cap) {
-      keys.release();
-      minseq.release();
-      head.release();
-      PGMO_TRY(keys.reserve(want));
-      PGMO_TRY(minseq.reserve(want));
-      PGMO_TRY(head.reserve(want));
+      slab.release();
+      PGMO_TRY(slab.reserve(2 * want));
       cap = want;
     }
     PGMO_TRY(frames.reserve(1));
-    PGMO_CUDA(cudaMemsetAsync(keys.ptr, 0xFF, cap * sizeof(unsigned long long), st));
-    PGMO_CUDA(cudaMemsetAsync(minseq.ptr, 0xFF, cap * sizeof(uint32_t), st));
-    PGMO_CUDA(cudaMemsetAsync(head.ptr, 0xFF, cap * sizeof(uint32_t), st));
+    PGMO_CUDA(cudaMemsetAsync(slab.ptr, 0xFF, 2 * cap * sizeof(unsigned long long), st));
     if (reset_frames) PGMO_CUDA(cudaMemsetAsync(frames.ptr, 0, sizeof(OctFrames), st));
     return PGMO_OK;
   }
@@ -473,10 +472,7 @@ int buildPersistent(pgmo_oct_t* h, uint64_t first, cudaStream_t st) {
       // table full: re-register everybody with twice the room.  The frames already hold every
       // growth event, so this neither re-anchors nor changes any key.
       h->ptree.factor *= 2;
-      h->ptree.cap = 0;
-      h->ptree.keys.release();
-      h->ptree.minseq.release();
-      h->ptree.head.release();
+      h->ptree.releaseTable();
       if (first == 0) h->ptree_built = false;
       else first = 1;  // forces the "re-register all" branch below without re-anchoring
       continue;
@@ -713,11 +709,11 @@ static int octIntegrate(pgmo_oct_t* h, uint32_t n_blocks, const int32_t* block_i
       PGMO_TRY(h->ttree.reset(n_cand, true, st));
       PGMO_CUDA(launchOctGrow(h->ttree.frames.ptr, h->cand_xyz.ptr, member, 0, nc, res, st));
       PGMO_CUDA(launchOctInsert(h->ttree.frames.ptr, h->ttree.table(), cpts, member, 0, nc, res, st));
-      PGMO_CUDA(cudaMemsetAsync(h->flags32.ptr, 0, sizeof(uint32_t), st));
+      // the "membership changed" flag is the spare word of the frames header: zeroed by the
+      // reset above, read back with the header by checkTreeError
       PGMO_CUDA(launchOctDecideTemp(h->ttree.frames.ptr, h->ttree.table(), h->cand_xyz.ptr,
                                     h->cand_next.ptr, nc, res, member, member_next, h->decision.ptr,
-                                    h->flags32.ptr, st));
-      PGMO_CUDA(cudaMemcpyAsync(h->h_flags.ptr, h->flags32.ptr, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+                                    &h->ttree.frames.ptr->pad, st));
       uint32_t error = 0;
       PGMO_TRY(checkTreeError(h, &h->ttree, st, &error));  // synchronises
       if (error == 4u && h->ttree.factor < 256) {  // table full: same round again, twice the room
@@ -726,7 +722,7 @@ static int octIntegrate(pgmo_oct_t* h, uint32_t n_blocks, const int32_t* block_i
         continue;
       }
       PGMO_TRY(treeErrorToRc(error));
-      if (h->h_flags.ptr[0] == 0) break;  // the hypothesis reproduced itself
+      if (h->h_frames.ptr->pad == 0) break;  // the hypothesis reproduced itself
       std::swap(member, member_next);
       if (h->last_rounds > n_cand + 2) {
         setLastError("octree temp pass did not converge");

@@ -37,13 +37,21 @@ __device__ __forceinline__ uint32_t hashKey(unsigned long long k) {
   return static_cast<uint32_t>(k);
 }
 
+// Test before test-and-set: the nodes near the root are shared by every point of a build, and
+// same-address atomics serialise in L2.  A key never changes once set and minseq only falls, so
+// a plain (volatile: L2) read that already shows this key / a small enough minseq makes the
+// atomic redundant; a stale read only costs the atomic it would have saved.
 __device__ __forceinline__ uint32_t tableInsert(const OctTable& t, unsigned long long key,
                                                 uint32_t seq) {
   uint32_t slot = hashKey(key) & t.mask;
   for (uint32_t probe = 0; probe <= t.mask; ++probe) {
-    const unsigned long long old = atomicCAS(t.keys + slot, kOctEmptyKey, key);
-    if (old == kOctEmptyKey || old == key) {
-      atomicMin(t.minseq + slot, seq);
+    unsigned long long k = *reinterpret_cast<volatile unsigned long long*>(t.keys + slot);
+    if (k == kOctEmptyKey) {
+      k = atomicCAS(t.keys + slot, kOctEmptyKey, key);
+      if (k == kOctEmptyKey) k = key;
+    }
+    if (k == key) {
+      if (*reinterpret_cast<volatile uint32_t*>(t.minseq + slot) > seq) atomicMin(t.minseq + slot, seq);
       return slot;
     }
     slot = (slot + 1) & t.mask;
@@ -73,12 +81,25 @@ __device__ __forceinline__ uint32_t ceilLog2(uint32_t v) {  // v >= 1
   return v <= 1 ? 0u : 32u - __clz(v - 1);
 }
 
+// Growth working state of one octGrowKernel launch: the newest frame, the event count and the
+// error word live in shared memory between events; every new frame is written through to the
+// global event list, which nothing re-reads inside the kernel (a global round trip per field
+// and event was what the kernel's time went to).
+struct GrowState {
+  OctFrame frame;
+  uint32_t n;
+  uint32_t error;
+};
+
 // One point's adoptBoundingBoxToPoint (+ getKeyBitSize for the very first point); appends one
 // event per doubling.  Single thread.
-__device__ void growForPoint(OctFrames* F, float x, float y, float z, uint32_t seq, double res) {
+// Every lane of the calling warp runs it on its own copy of the state (same inputs, same result);
+// `writer` names the one lane that stores the new frames to the global event list.
+__device__ void growForPoint(OctFrames* F, GrowState& g, float x, float y, float z, uint32_t seq,
+                             double res, bool writer) {
   const double eps = static_cast<double>(FLT_EPSILON);
   const double p[3] = {static_cast<double>(x), static_cast<double>(y), static_cast<double>(z)};
-  if (F->n == 0) {
+  if (g.n == 0) {
     OctFrame f;
     for (int a = 0; a < 3; ++a) {
       f.min[a] = p[a] - res / 2;
@@ -103,21 +124,25 @@ __device__ void growForPoint(OctFrames* F, float x, float y, float z, uint32_t s
     }
     f.depth = depth;
     f.seq = seq;
-    F->f[0] = f;
-    for (int h = 0; h < 32; ++h) {
-      F->base[h][0] = F->base[h][1] = F->base[h][2] = 0;
+    if (writer) {
+      F->f[0] = f;
+      for (int h = 0; h < 32; ++h) {
+        F->base[h][0] = F->base[h][1] = F->base[h][2] = 0;
+      }
+      for (int a = 0; a < 3; ++a) {
+        F->anchor_sigma[a] = static_cast<long long>(static_cast<uint32_t>((p[a] - f.min[a]) / res));
+      }
     }
-    for (int a = 0; a < 3; ++a) {
-      F->anchor_sigma[a] = static_cast<long long>(static_cast<uint32_t>((p[a] - f.min[a]) / res));
-    }
-    F->n = 1;
+    g.frame = f;
+    g.n = 1;
     return;
   }
-  OctFrame f = F->f[F->n - 1];
+  OctFrame f = g.frame;
+  uint32_t n = g.n;
   while (outsideBox(f, x, y, z)) {
-    if (F->n >= kOctMaxFrames || f.depth >= kOctMaxDepth) {
-      F->error |= 1u;
-      return;
+    if (n >= kOctMaxFrames || f.depth >= kOctMaxDepth) {
+      g.error |= 1u;
+      break;
     }
     const bool up[3] = {p[0] >= f.max[0], p[1] >= f.max[1], p[2] >= f.max[2]};
     double side = static_cast<double>(1u << f.depth) * res;
@@ -127,62 +152,130 @@ __device__ void growForPoint(OctFrames* F, float x, float y, float z, uint32_t s
         f.shift[a] += 1ll << f.depth;
       }
       // height f.depth comes into existence: its partition is fixed from now on
-      F->base[f.depth][a] = f.shift[a] & ((1ll << f.depth) - 1);
+      if (writer) F->base[f.depth][a] = f.shift[a] & ((1ll << f.depth) - 1);
     }
     ++f.depth;
     side = static_cast<double>(1u << f.depth) * res - eps;
     for (int a = 0; a < 3; ++a) f.max[a] = f.min[a] + side;
     f.seq = seq;
-    F->f[F->n] = f;
-    F->n += 1;
+    if (writer) F->f[n] = f;
+    ++n;
   }
+  g.frame = f;
+  g.n = n;
+}
+
+// The growth events of the members [first, n) in index order: an event is a member outside the
+// box as it stands when that member's turn comes (OctreePointCloud::addPointIdx tests every
+// point once, against the box of its time).  One CTA walks the members in windows:
+//   A  all threads flag the window's members that lie outside the box of the window's start, or
+//      within kGrowMargin of its faces, and compact them in index order into shared memory.
+//      Nothing else can become an event inside this window: the box never shrinks by more than
+//      FLT_EPSILON (the first doubling replaces max = min + side by min + side - eps) plus
+//      rounding, which the margin covers.  Most windows flag nothing and cost one barrier.
+//   B  warp 0 replays the flagged members in order with the exact test, every lane growing its
+//      own register copy of the box (no barrier, no memory round trip per event); lane 0 stores
+//      the new frames.
+constexpr int kGrowPerThread = 2;
+constexpr uint32_t kGrowWindow = 1024 * kGrowPerThread;
+constexpr double kGrowMargin = 1e-6;
+
+__device__ __forceinline__ bool nearOrOutsideBox(const OctFrame& f, float x, float y, float z) {
+  const double px = x, py = y, pz = z;
+  return px < f.min[0] + kGrowMargin || py < f.min[1] + kGrowMargin || pz < f.min[2] + kGrowMargin ||
+         px >= f.max[0] - kGrowMargin || py >= f.max[1] - kGrowMargin || pz >= f.max[2] - kGrowMargin;
 }
 
 __global__ void __launch_bounds__(1024)
 octGrowKernel(OctFrames* F, const float4* __restrict__ xyz, const uint8_t* __restrict__ member,
               uint32_t first, uint32_t n, double res) {
-  __shared__ uint32_t s_min;
-  __shared__ OctFrame s_frame;
-  __shared__ uint32_t s_events;
-  uint32_t cursor = first;
-  while (true) {
-    if (threadIdx.x == 0) {
-      s_min = kOctNone;
-      s_events = F->n;
-      if (F->n > 0) s_frame = F->f[F->n - 1];
+  __shared__ GrowState s_g;
+  __shared__ uint32_t s_wcount[2][32];
+  __shared__ float4 s_cand[kGrowWindow];
+  __shared__ uint32_t s_idx[kGrowWindow];
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    s_g.n = F->n;
+    s_g.error = F->error;
+    if (s_g.n > 0) s_g.frame = F->f[s_g.n - 1];
+  }
+  // a thread owns kGrowPerThread consecutive members of the window
+  float4 cur[kGrowPerThread], nxt[kGrowPerThread];
+  bool cur_m[kGrowPerThread], nxt_m[kGrowPerThread];
+  auto load = [&](float4* p, bool* m, uint32_t base) {
+#pragma unroll
+    for (int u = 0; u < kGrowPerThread; ++u) {
+      const uint32_t i = base + kGrowPerThread * threadIdx.x + u;
+      m[u] = i < n && (!member || member[i]);
+      p[u] = i < n ? xyz[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+  };
+  load(cur, cur_m, first);
+  __syncthreads();
+  int buf = 0;
+  for (uint32_t base = first; base < n; base += kGrowWindow, buf ^= 1) {
+    load(nxt, nxt_m, base + kGrowWindow);
+    const bool defined = s_g.n > 0;
+    bool flag[kGrowPerThread];
+    unsigned ballots[kGrowPerThread];
+    unsigned before = 0, mine_total = 0;
+#pragma unroll
+    for (int u = 0; u < kGrowPerThread; ++u) {
+      flag[u] = cur_m[u] && (!defined || nearOrOutsideBox(s_g.frame, cur[u].x, cur[u].y, cur[u].z));
+      ballots[u] = __ballot_sync(0xFFFFFFFFu, flag[u]);
+      before += __popc(ballots[u] & ((1u << lane) - 1u));
+      mine_total += __popc(ballots[u]);
+    }
+    if (lane == 0) s_wcount[buf][warp] = mine_total;
     __syncthreads();
-    const bool defined = s_events > 0;
-    // four independent loads in flight per thread: the scan is one CTA wide and latency-bound
-    for (uint32_t i0 = cursor + threadIdx.x; i0 < n; i0 += 4 * blockDim.x) {
-      float4 p[4];
-      bool m[4];
+    const uint32_t wc = s_wcount[buf][lane];
+    const uint32_t total = __reduce_add_sync(0xFFFFFFFFu, wc);
+    if (total != 0) {  // uniform over the CTA
+      uint32_t pos = __reduce_add_sync(0xFFFFFFFFu, lane < warp ? wc : 0u) + before;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const uint32_t i = i0 + u * blockDim.x;
-        m[u] = i < n && (!member || member[i]);
-        p[u] = i < n ? xyz[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      bool hit = false;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (!hit && m[u] && (!defined || outsideBox(s_frame, p[u].x, p[u].y, p[u].z))) {
-          atomicMin(&s_min, i0 + u * blockDim.x);
-          hit = true;  // this thread's indices ascend: the first hit is its minimum
+      for (int u = 0; u < kGrowPerThread; ++u) {
+        if (flag[u]) {
+          s_cand[pos] = cur[u];
+          s_idx[pos] = base + kGrowPerThread * threadIdx.x + u;
+          ++pos;
         }
       }
-      if (hit) break;
+      __syncthreads();
+      if (warp == 0) {
+        GrowState g = s_g;
+        const uint32_t n_before = g.n, error_before = g.error;
+        for (uint32_t b = 0; b < total && g.error == error_before; b += 32) {
+          const bool have = b + lane < total;
+          const float4 c = have ? s_cand[b + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+          const uint32_t ci = have ? s_idx[b + lane] : 0u;
+          unsigned done = 0;  // lanes of this batch whose turn has passed
+          while (g.error == error_before) {
+            const bool out = have && !((done >> lane) & 1u) &&
+                             (g.n == 0 || outsideBox(g.frame, c.x, c.y, c.z));
+            const unsigned mask = __ballot_sync(0xFFFFFFFFu, out);
+            if (mask == 0) break;
+            const int src = __ffs(mask) - 1;
+            growForPoint(F, g, __shfl_sync(0xFFFFFFFFu, c.x, src), __shfl_sync(0xFFFFFFFFu, c.y, src),
+                         __shfl_sync(0xFFFFFFFFu, c.z, src), __shfl_sync(0xFFFFFFFFu, ci, src), res,
+                         lane == 0);
+            done |= (2u << src) - 1u;  // members up to the event point are never tested again
+          }
+        }
+        if (lane == 0 && (g.n != n_before || g.error != error_before)) s_g = g;
+      }
+      __syncthreads();
+      if (s_g.error != 0 && (s_g.error & 1u)) break;  // box past the supported depth
     }
-    __syncthreads();
-    const uint32_t m = s_min;
-    if (m == kOctNone) break;
-    if (threadIdx.x == 0) {
-      const float4 p = xyz[m];
-      growForPoint(F, p.x, p.y, p.z, m, res);
+#pragma unroll
+    for (int u = 0; u < kGrowPerThread; ++u) {
+      cur[u] = nxt[u];
+      cur_m[u] = nxt_m[u];
     }
-    __syncthreads();
-    if (F->error) break;
-    cursor = m + 1;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    F->n = s_g.n;
+    F->error = s_g.error;
   }
 }
 
@@ -238,23 +331,21 @@ octInsertKernel(OctFrames* F, const OctTable t, const OctPoints pts,
   }
 }
 
+// one lane per height: the keys are independent
 __global__ void octRootChainKernel(OctFrames* F, const OctTable t) {
-  if (threadIdx.x != 0 || blockIdx.x != 0 || F->n == 0) return;
+  if (blockIdx.x != 0 || F->n == 0) return;
   const int depth = static_cast<int>(F->f[F->n - 1].depth);
   const uint32_t seq = F->f[0].seq;
-  for (int h = static_cast<int>(F->f[0].depth); h < depth; ++h) {
-    unsigned long long key;
-    if (!packKey(h, (F->anchor_sigma[0] + F->base[h][0]) >> h,
-                 (F->anchor_sigma[1] + F->base[h][1]) >> h,
-                 (F->anchor_sigma[2] + F->base[h][2]) >> h, &key)) {
-      F->error |= 2u;
-      return;
-    }
-    if (tableInsert(t, key, seq) == kOctNone) {
-      F->error |= 4u;
-      return;
-    }
+  const int h = static_cast<int>(F->f[0].depth) + static_cast<int>(threadIdx.x);
+  if (h >= depth) return;
+  unsigned long long key;
+  if (!packKey(h, (F->anchor_sigma[0] + F->base[h][0]) >> h,
+               (F->anchor_sigma[1] + F->base[h][1]) >> h,
+               (F->anchor_sigma[2] + F->base[h][2]) >> h, &key)) {
+    atomicOr(&F->error, 2u);
+    return;
   }
+  if (tableInsert(t, key, seq) == kOctNone) atomicOr(&F->error, 4u);
 }
 
 // OctreePointCloudSearch::approxNearestSearchRecursive on the implicit tree as of `limit_seq`:
