@@ -222,8 +222,17 @@ class MeshCompression {
   };
   virtual DeviceView deviceView() const = 0;
 
+  // Extension (no reference counterpart): what the last compressAndIntegrate did to `remapping`,
+  // as a dense record per input vertex in blockIndices() order - kind 0 = no write, 1 =
+  // overwrite, 2 = insert-if-absent; an empty kind vector = all overwrite.
+  // MeshFrontendInterface hands it to pgmo_m2g_update.
+  const std::vector<int64_t>& lastRemapIndex() const { return last_index_; }
+  const std::vector<uint8_t>& lastRemapKind() const { return last_kind_; }
+
  protected:
   double resolution_;
+  std::vector<int64_t> last_index_;
+  std::vector<uint8_t> last_kind_;
 };
 using MeshCompressionPtr = std::shared_ptr<MeshCompression>;
 
@@ -257,6 +266,8 @@ class VoxelClearingCompression : public MeshCompression {
                                               flat.offsets.data(), flat.xyz.data(), flat.rgba.data(),
                                               stamp_in_sec, remap.data(), nullptr));
     }
+    last_index_.assign(remap.begin(), remap.end());
+    last_kind_.clear();
     size_t b = 0;
     for (const auto& block : mesh.blockIndices()) {
       remapping.insert({block, IndexMapping()});  // :123
@@ -400,6 +411,8 @@ class OctreeCompression : public MeshCompression {
                                               flat.offsets.data(), flat.xyz.data(), flat.rgba.data(),
                                               stamp_in_sec, idx.data(), kind.data()));
     }
+    last_index_ = idx;
+    last_kind_ = kind;
     size_t b = 0;
     for (const auto& block : mesh.blockIndices()) {
       remapping.insert({block, IndexMapping()});  // :256

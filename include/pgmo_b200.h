@@ -355,6 +355,44 @@ int pgmo_delta_blocks(pgmo_delta_t* h, uint64_t capacity, int32_t* block_idx_xyz
 int pgmo_delta_last_stats(pgmo_delta_t* h, uint64_t* stats4);
 
 /* ------------------------------------------------------------------------------------------
+ * Mesh -> graph index bookkeeping of MeshFrontendInterface (members msg_to_mesh_idx_,
+ * msg_to_graph_idx_, mesh_to_graph_idx_: kimera_pgmo/include/kimera_pgmo/
+ * mesh_frontend_interface.h:118-120; updateMeshToGraphMappings:
+ * src/mesh_frontend_interface.cpp:197-211).  One handle per MeshFrontendInterface.  The three
+ * maps live in HBM: per block a dense msg-index -> stored-index array for each compressor
+ * (never cleared, like the reference's per-block maps) and a dense mesh-index -> graph-index
+ * array.  Where the reference's result depends on unordered_map iteration order (several msg
+ * vertices of one block on the same mesh vertex) the entries are taken in ascending msg index.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct pgmo_m2g pgmo_m2g_t;
+
+int pgmo_m2g_create(int device, pgmo_m2g_t** out);
+void pgmo_m2g_destroy(pgmo_m2g_t* h);
+/* One MeshFrontendInterface::update (:100-115) after both compressors have run on the message:
+ * applies their writes to the two persistent remappings, then updateMeshToGraphMappings over
+ * the message's blocks in the given order.  Mesh flattened as for pgmo_vcc_integrate.
+ *   mesh_index / mesh_kind    per input vertex, what the full-mesh compressor did to
+ *                             remapping[block][i]: kind 0 = no write, 1 = overwrite, 2 =
+ *                             insert-if-absent (pgmo_oct_integrate's remap_index / remap_kind);
+ *                             mesh_kind NULL = all overwrite (pgmo_vcc_integrate's remap_out)
+ *   graph_index / graph_kind  the same from the graph compressor */
+int pgmo_m2g_update(pgmo_m2g_t* h, uint32_t n_blocks, const int32_t* block_idx_xyz,
+                    const uint64_t* block_offsets, const int64_t* mesh_index,
+                    const uint8_t* mesh_kind, const int64_t* graph_index,
+                    const uint8_t* graph_kind);
+/* mesh_to_graph_idx_: its size, and its pairs in ascending mesh index */
+int pgmo_m2g_size(pgmo_m2g_t* h, uint64_t* n_pairs);
+int pgmo_m2g_fetch(pgmo_m2g_t* h, uint64_t* mesh_idx, uint64_t* graph_idx);
+/* msg_to_mesh_idx_[block] (which 0) / msg_to_graph_idx_[block] (which 1,
+ * getVoxbloxMsgToGraphMapping, mesh_frontend_interface.h:56) as a dense array over the msg
+ * vertex index, -1 = no entry.  *length = its length; min(length, cap) entries are copied.
+ * PGMO_ERR_INVALID for a block no update has named (the reference's .at() throws). */
+int pgmo_m2g_block_mapping(pgmo_m2g_t* h, const int32_t* block_idx_xyz, int which, int64_t* out,
+                           uint64_t cap, uint64_t* length);
+/* mesh_to_graph_idx_ in HBM: dense over mesh indices [0, span), -1 = no entry */
+int pgmo_m2g_device_view(pgmo_m2g_t* h, const int64_t** d_mesh_to_graph, uint64_t* span);
+
+/* ------------------------------------------------------------------------------------------
  * MeshInterface inputs.  The integrate calls above take what MeshInterface::getActiveVertex
  * yields, flattened.  A voxblox mesh message (VoxbloxMsgInterface,
  * kimera_pgmo_ros/src/voxblox_msg_interface.cpp:11-62) stores u16 fixed-point coordinates per

@@ -101,6 +101,13 @@ SIGNATURES = {
                                    _vp, _u64p]),
     "pgmo_delta_last_stats": (C.c_int, [_vp, _vp]),
     "pgmo_delta_blocks": (C.c_int, [_vp, C.c_uint64, _vp, _vp, _vp, _u64p]),
+    "pgmo_m2g_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
+    "pgmo_m2g_destroy": (None, [_vp]),
+    "pgmo_m2g_update": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pgmo_m2g_size": (C.c_int, [_vp, _u64p]),
+    "pgmo_m2g_fetch": (C.c_int, [_vp, _vp, _vp]),
+    "pgmo_m2g_block_mapping": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_uint64, _u64p]),
+    "pgmo_m2g_device_view": (C.c_int, [_vp, C.POINTER(_vp), _u64p]),
     "pgmo_voxblox_decode": (C.c_int, [C.c_int, C.c_uint32] + [_vp] * 8 + [C.c_float, _vp, _vp]),
     "pgmo_vcc_integrate_voxblox": (C.c_int, [_vp, C.c_uint32] + [_vp] * 8 + [C.c_float, C.c_double,
                                                                           _vp, _vp]),
@@ -596,3 +603,57 @@ class DeltaHandle:
         d["observed"] = d["observed"][: n[2].value]
         d["new"] = d["new"][: n[3].value]
         return d
+
+
+class MeshToGraphHandle:
+    """pgmo_m2g_t: msg_to_mesh_idx_ / msg_to_graph_idx_ / mesh_to_graph_idx_ of
+    MeshFrontendInterface, in HBM; same methods as oracle.ffi.MeshToGraph."""
+
+    def __init__(self, device: int = 0):
+        self._lib = load()
+        h = _vp()
+        _check(self._lib.pgmo_m2g_create(device, C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.pgmo_m2g_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def update(self, block_idx, offsets, mesh_index, mesh_kind, graph_index, graph_kind):
+        bi = np.ascontiguousarray(block_idx, dtype=np.int32).reshape(-1, 3)
+        off = np.ascontiguousarray(offsets, dtype=np.uint64)
+        mi = np.ascontiguousarray(mesh_index).astype(np.int64, copy=False)
+        gi = np.ascontiguousarray(graph_index).astype(np.int64, copy=False)
+        mk = None if mesh_kind is None else np.ascontiguousarray(mesh_kind, dtype=np.uint8)
+        gk = None if graph_kind is None else np.ascontiguousarray(graph_kind, dtype=np.uint8)
+        _check(self._lib.pgmo_m2g_update(self._h, bi.shape[0], _ptr(bi), _ptr(off), _ptr(mi), _ptr(mk),
+                                         _ptr(gi), _ptr(gk)))
+
+    def mesh_to_graph(self):
+        """-> (mesh indices ascending, graph indices)"""
+        n = C.c_uint64(0)
+        _check(self._lib.pgmo_m2g_size(self._h, C.byref(n)))
+        m, g = np.zeros(n.value, np.uint64), np.zeros(n.value, np.uint64)
+        if n.value:
+            _check(self._lib.pgmo_m2g_fetch(self._h, _ptr(m), _ptr(g)))
+        return m, g
+
+    def block_mapping(self, block, which):
+        bi = np.ascontiguousarray(block, dtype=np.int32)
+        n = C.c_uint64(0)
+        _check(self._lib.pgmo_m2g_block_mapping(self._h, _ptr(bi), int(which), None, 0, C.byref(n)))
+        out = np.full(n.value, -1, np.int64)
+        if n.value:
+            _check(self._lib.pgmo_m2g_block_mapping(self._h, _ptr(bi), int(which), _ptr(out), n.value,
+                                                    C.byref(n)))
+        return out
+
+    def device_view(self):
+        """-> (device pointer of the dense mesh -> graph array, its length)"""
+        p, n = _vp(), C.c_uint64(0)
+        _check(self._lib.pgmo_m2g_device_view(self._h, C.byref(p), C.byref(n)))
+        return p.value, n.value

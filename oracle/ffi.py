@@ -71,6 +71,16 @@ def load():
     lib.oracle_cloud_to_msg.argtypes = [C.c_uint64] + [_vp] * 6
     lib.oracle_voxblox_decode.restype = None
     lib.oracle_voxblox_decode.argtypes = [C.c_uint32] + [_vp] * 8 + [C.c_float, _vp, _vp]
+    lib.oracle_m2g_create.restype = _vp
+    lib.oracle_m2g_destroy.argtypes = [_vp]
+    lib.oracle_m2g_update.restype = None
+    lib.oracle_m2g_update.argtypes = [_vp, C.c_uint32] + [_vp] * 6
+    lib.oracle_m2g_size.restype = C.c_uint64
+    lib.oracle_m2g_size.argtypes = [_vp]
+    lib.oracle_m2g_fetch.restype = None
+    lib.oracle_m2g_fetch.argtypes = [_vp, _vp, _vp]
+    lib.oracle_m2g_block_mapping.restype = C.c_int64
+    lib.oracle_m2g_block_mapping.argtypes = [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_int, _vp, C.c_uint64]
     lib.oracle_stamp_from_sec.restype = C.c_uint64
     lib.oracle_stamp_from_sec.argtypes = [C.c_double]
     _lib = lib
@@ -336,3 +346,44 @@ class DeltaCompression:
                                      _ptr(d["faces"]), _ptr(d["faces_archive"]), _ptr(d["prev_to_curr"]),
                                      _ptr(d["deleted"]), _ptr(d["observed"]), _ptr(d["new"]))
         return d
+
+
+class MeshToGraph:
+    """mesh -> graph index bookkeeping of MeshFrontendInterface (oracle/frontend_oracle.h)."""
+
+    def __init__(self):
+        self._lib = load()
+        self._h = _vp(self._lib.oracle_m2g_create())
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._lib.oracle_m2g_destroy(self._h)
+            self._h = None
+
+    def update(self, block_idx, offsets, mesh_index, mesh_kind, graph_index, graph_kind):
+        bi = np.ascontiguousarray(block_idx, dtype=np.int32).reshape(-1, 3)
+        off = np.ascontiguousarray(offsets, dtype=np.uint64)
+        mi = np.ascontiguousarray(mesh_index, dtype=np.int64)
+        gi = np.ascontiguousarray(graph_index, dtype=np.int64)
+        mk = None if mesh_kind is None else np.ascontiguousarray(mesh_kind, dtype=np.uint8)
+        gk = None if graph_kind is None else np.ascontiguousarray(graph_kind, dtype=np.uint8)
+        self._lib.oracle_m2g_update(self._h, bi.shape[0], _ptr(bi), _ptr(off), _ptr(mi), _ptr(mk),
+                                    _ptr(gi), _ptr(gk))
+
+    def mesh_to_graph(self):
+        """-> (mesh indices ascending, graph indices)"""
+        n = int(self._lib.oracle_m2g_size(self._h))
+        m, g = np.zeros(n, np.uint64), np.zeros(n, np.uint64)
+        self._lib.oracle_m2g_fetch(self._h, _ptr(m), _ptr(g))
+        return m, g
+
+    def block_mapping(self, block, which):
+        """dense msg_to_mesh_idx_[block] (which 0) / msg_to_graph_idx_[block] (which 1), -1 = no entry"""
+        n = int(self._lib.oracle_m2g_block_mapping(self._h, int(block[0]), int(block[1]), int(block[2]),
+                                                   int(which), None, 0))
+        if n < 0:
+            return None
+        out = np.full(n, -1, np.int64)
+        self._lib.oracle_m2g_block_mapping(self._h, int(block[0]), int(block[1]), int(block[2]),
+                                           int(which), _ptr(out), n)
+        return out

@@ -9,6 +9,7 @@
 #include "compression_oracle.h"
 #include "delta_oracle.h"
 #include "deform_oracle.h"
+#include "frontend_oracle.h"
 
 using namespace pgmo_oracle;
 
@@ -532,5 +533,35 @@ int64_t oracle_comp_remap_block_size(void* hv, int32_t bx, int32_t by, int32_t b
 }
 
 uint64_t oracle_stamp_from_sec(double sec) { return stampFromSec(sec); }
+
+// ---- mesh -> graph index bookkeeping (frontend_oracle.h) ----------------------------------------
+void* oracle_m2g_create() { return new MeshToGraphOracle(); }
+void oracle_m2g_destroy(void* h) { delete static_cast<MeshToGraphOracle*>(h); }
+void oracle_m2g_update(void* h, uint32_t n_blocks, const int32_t* block_idx_xyz,
+                       const uint64_t* block_offsets, const int64_t* mesh_index,
+                       const uint8_t* mesh_kind, const int64_t* graph_index,
+                       const uint8_t* graph_kind) {
+  static_cast<MeshToGraphOracle*>(h)->update(n_blocks, block_idx_xyz, block_offsets, mesh_index,
+                                             mesh_kind, graph_index, graph_kind);
+}
+uint64_t oracle_m2g_size(void* h) { return static_cast<MeshToGraphOracle*>(h)->meshToGraph().size(); }
+// pairs in ascending mesh index
+void oracle_m2g_fetch(void* h, uint64_t* mesh_idx, uint64_t* graph_idx) {
+  size_t i = 0;
+  for (const auto& kv : static_cast<MeshToGraphOracle*>(h)->meshToGraph()) {
+    mesh_idx[i] = kv.first;
+    graph_idx[i] = kv.second;
+    ++i;
+  }
+}
+// dense msg_to_mesh_idx_[block] (which 0) / msg_to_graph_idx_[block] (which 1); returns its
+// length (-1: unknown block), copies min(length, cap) entries (-1 = no entry)
+int64_t oracle_m2g_block_mapping(void* h, int32_t bx, int32_t by, int32_t bz, int which,
+                                 int64_t* out, uint64_t cap) {
+  const auto* v = static_cast<MeshToGraphOracle*>(h)->blockMapping({bx, by, bz}, which);
+  if (!v) return -1;
+  for (size_t i = 0; i < v->size() && i < cap; ++i) out[i] = (*v)[i];
+  return static_cast<int64_t>(v->size());
+}
 
 }  // extern "C"

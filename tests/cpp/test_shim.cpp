@@ -14,6 +14,7 @@
 #include "kimera_pgmo_b200/compression.h"
 #include "kimera_pgmo_b200/deformation_graph.h"
 #include "kimera_pgmo_b200/delta_compression.h"
+#include "kimera_pgmo_b200/mesh_frontend_interface.h"
 
 using namespace kimera_pgmo_b200;
 
@@ -663,6 +664,71 @@ static void testDeltaCompression() {
   EXPECT_EQ(d1->getTotalFaces(), faces.size());
 }
 
+// ------------------------------------------------------------- MeshFrontendInterface (bookkeeping)
+// mesh_frontend_interface.cpp:100-115, :197-211.  The expected mesh_to_graph_idx_ is the
+// reference's own loop run on the host maps after every update, entries of a block taken in
+// ascending msg index (the order the device uses where the reference's is implementation-defined).
+static void testMeshFrontend() {
+  MeshFrontendInterface::Config config;
+  config.full_compression_method = MeshFrontendInterface::FullCompressionMethod::VOXEL_CLEARING;
+  config.graph_compression_method = MeshFrontendInterface::GraphCompressionMethod::OCTREE;
+  config.mesh_resolution = 0.05;
+  config.d_graph_resolution = 0.5;
+  config.time_horizon = 2.0;
+  MeshFrontendInterface frontend(config);
+  std::map<size_t, size_t> expected;
+  uint32_t seed = 777u;
+  auto next = [&seed]() {
+    seed = seed * 1664525u + 1013904223u;
+    return seed >> 8;
+  };
+  for (int msg = 0; msg < 6; ++msg) {
+    OrderedBlockMesh mesh;
+    const int n_blocks = 2 + msg % 3;
+    for (int b = 0; b < n_blocks; ++b) {
+      mesh.order.push_back(BlockIndex((b + msg) % 4, 0, 0));
+      mesh.blocks.emplace_back();
+      // fewer faces in later versions of a block: stale entries stay in its maps
+      const int faces = 60 - 7 * msg + 5 * b;
+      for (int f = 0; f < faces; ++f) {
+        const float ax = 0.8f * static_cast<float>((b + msg) % 4) + 0.02f * static_cast<float>(next() % 36);
+        const float ay = 0.02f * static_cast<float>(next() % 40), az = 0.1f * static_cast<float>(next() % 3);
+        const float corner[3][3] = {{ax, ay, az}, {ax + 0.04f, ay, az}, {ax, ay + 0.04f, az}};
+        for (const auto& c : corner) {
+          pcl::PointXYZRGBA p;
+          p.x = c[0];
+          p.y = c[1];
+          p.z = c[2];
+          p.r = 10;
+          p.g = 20;
+          p.b = 30;
+          p.a = 255;
+          mesh.blocks.back().push_back(p);
+        }
+      }
+    }
+    frontend.update(mesh, 10.0 + msg);
+    EXPECT_EQ(frontend.vertices()->size(), frontend.vertexStamps()->size());
+    EXPECT_TRUE(frontend.graphVertices()->size() > 0);
+    for (const auto& block : mesh.order) {
+      const IndexMapping& to_mesh = frontend.getMsgToMeshMapping().at(block);
+      const IndexMapping& to_graph = frontend.getVoxbloxMsgToGraphMapping().at(block);
+      const std::map<size_t, size_t> ordered(to_mesh.begin(), to_mesh.end());
+      for (const auto& remap : ordered) {
+        if (to_graph.count(remap.first)) expected.insert({remap.second, to_graph.at(remap.first)});
+      }
+    }
+    const IndexMapping got = frontend.getMeshToGraphMapping();
+    EXPECT_EQ(expected.size(), got.size());
+    bool same = expected.size() == got.size();
+    for (const auto& kv : expected) same = same && got.count(kv.first) == 1 && got.at(kv.first) == kv.second;
+    EXPECT_TRUE(same);
+  }
+  EXPECT_TRUE(expected.size() > 50);
+  const auto view = frontend.meshToGraphDevice();
+  EXPECT_TRUE(view.mesh_to_graph != nullptr && view.span >= frontend.vertices()->size());
+}
+
 int main(int argc, char** argv) {
   const bool with_octree = argc > 1 && std::strcmp(argv[1], "--octree") == 0;
   if (pgmo_device_count() <= 0) {
@@ -677,6 +743,7 @@ int main(int argc, char** argv) {
   testVoxelClearing();
   testVoxbloxInterface();
   testDeltaCompression();
+  testMeshFrontend();
   if (with_octree) testOctreeCompression();
   std::printf("shim tests: %d checks, %d failures\n", g_checks, g_failures);
   return g_failures ? 1 : 0;
