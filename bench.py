@@ -600,15 +600,16 @@ def bench_compression(dev_index, n_messages=200, verts=50_000, with_cpu=True, n_
     # n_octree messages, host buffers in / remap record out, prune(t - 10 s) before each
     if n_octree > 0:
         oc = capi.OctHandle(0.05, dev_index)
-        t0 = None
         w2 = min(5, n_octree - 1)
+        per_msg = []
         for m, (blocks, offsets, xyz, rgba, t) in enumerate(msgs[:n_octree]):
-            if m == w2:
-                t0 = time.perf_counter()
+            t1 = time.perf_counter()
             oc.prune(t - 10.0)
             oc.integrate(blocks, offsets, xyz, rgba, t)
-        oct_ms = 1e3 * (time.perf_counter() - t0) / (n_octree - w2)
+            per_msg.append(1e3 * (time.perf_counter() - t1))
+        oct_ms = float(np.mean(per_msg[w2:]))
         out["octree"] = {"value": verts / (oct_ms * 1e-3), "unit": "vertices/s", "ms_per_message": oct_ms,
+                         "ms_p50": float(np.median(per_msg[w2:])), "ms_max": float(np.max(per_msg[w2:])),
                          "api": "pgmo_oct_prune + pgmo_oct_integrate (host buffers)",
                          "stored_vertices": int(oc.sizes()[0])}
         oc.close()
@@ -633,15 +634,16 @@ def bench_compression(dev_index, n_messages=200, verts=50_000, with_cpu=True, n_
         for n_blocks in (1, 64):
             dmsgs = msgs[:n_octree] if n_blocks == 1 else list(synth.compression_stream(n_octree, verts, n_blocks=n_blocks))
             dc = capi.DeltaHandle(0.05, dev_index)
-            t0 = None
+            per_msg = []
             for m, (blocks, offsets, xyz, rgba, t) in enumerate(dmsgs):
-                if m == w2:
-                    t0 = time.perf_counter()
+                t1 = time.perf_counter()
                 dc.archive_by_time(int((t - 10.0) * 1e9))
                 dc.update(blocks, offsets, xyz, rgba, int(t * 1e9), fetch=False)
-            d_ms = 1e3 * (time.perf_counter() - t0) / (n_octree - w2)
+                per_msg.append(1e3 * (time.perf_counter() - t1))
+            d_ms = float(np.mean(per_msg[w2:]))
             key = "delta" if n_blocks == 1 else "delta_64_blocks"
             out[key] = {"value": verts / (d_ms * 1e-3), "unit": "vertices/s", "ms_per_message": d_ms,
+                        "ms_p50": float(np.median(per_msg[w2:])), "ms_max": float(np.max(per_msg[w2:])),
                         "api": "pgmo_delta_archive_by_time + pgmo_delta_update (host buffers)",
                         "active_vertices": int(dc.sizes()[10])}
             dc.close()
@@ -658,6 +660,49 @@ def bench_compression(dev_index, n_messages=200, verts=50_000, with_cpu=True, n_
                 cpu_ms = 1e3 * total / (n_octree - w2)
                 out[key]["cpu_baseline"] = {"value": verts / (cpu_ms * 1e-3), "unit": "vertices/s",
                                             "cores": 1, "kind": "port", "ms_per_message": cpu_ms}
+    # MeshFrontendInterface::update: full-mesh compressor (VoxelClearing,
+    # 0.05 m) + graph compressor (Octree, 0.5 m) + mesh -> graph index bookkeeping per message,
+    # 16 blocks per message, host buffers in, the three index maps left in HBM
+    if n_octree > 0:
+        w2 = min(5, n_octree - 1)
+        fmsgs = list(synth.compression_stream(n_octree, verts, n_blocks=16))
+        full, graph, m2g = capi.VccHandle(0.05, dev_index), capi.OctHandle(0.5, dev_index), capi.MeshToGraphHandle(dev_index)
+        per_msg = []
+        for m, (blocks, offsets, xyz, rgba, t) in enumerate(fmsgs):
+            t1 = time.perf_counter()
+            full.prune(t - 10.0)
+            graph.prune(t - 10.0)
+            remap, _ = full.integrate(blocks, offsets, xyz, rgba, t)
+            gi, gk = graph.integrate(blocks, offsets, xyz, rgba, t)
+            m2g.update(blocks, offsets, remap.view(np.int64), None, gi, gk)
+            per_msg.append(1e3 * (time.perf_counter() - t1))
+        f_ms = float(np.mean(per_msg[w2:]))
+        pairs_gpu = m2g.mesh_to_graph()
+        out["frontend"] = {"value": verts / (f_ms * 1e-3), "unit": "vertices/s", "ms_per_message": f_ms,
+                           "ms_p50": float(np.median(per_msg[w2:])), "ms_max": float(np.max(per_msg[w2:])),
+                           "api": "pgmo_vcc_prune/integrate + pgmo_oct_prune/integrate + pgmo_m2g_update (host buffers)",
+                           "mesh_to_graph_pairs": int(len(pairs_gpu[0]))}
+        for c in (full, graph, m2g):
+            c.close()
+        if with_cpu:
+            from oracle import ffi
+            o_full, o_graph, o_m2g = ffi.Compression("voxel_clearing", 0.05), ffi.Compression("octree", 0.5), ffi.MeshToGraph()
+            total = 0.0
+            for m, (blocks, offsets, xyz, rgba, t) in enumerate(fmsgs):
+                t1 = time.perf_counter()
+                o_full.prune(t - 10.0)
+                o_graph.prune(t - 10.0)
+                mi, mk, _ = o_full.integrate(blocks, offsets, xyz, rgba, t)
+                gi, gk, _ = o_graph.integrate(blocks, offsets, xyz, rgba, t)
+                o_m2g.update(blocks, offsets, mi, mk, gi, gk)
+                if m >= w2:
+                    total += time.perf_counter() - t1
+            cpu_ms = 1e3 * total / (n_octree - w2)
+            pairs_cpu = o_m2g.mesh_to_graph()
+            out["frontend"]["cpu_baseline"] = {"value": verts / (cpu_ms * 1e-3), "unit": "vertices/s",
+                                               "cores": 1, "kind": "port", "ms_per_message": cpu_ms}
+            out["frontend"]["pairs_identical_to_oracle"] = bool(
+                np.array_equal(pairs_gpu[0], pairs_cpu[0]) and np.array_equal(pairs_gpu[1], pairs_cpu[1]))
     return out
 
 

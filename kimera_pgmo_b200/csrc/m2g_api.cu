@@ -153,7 +153,9 @@ namespace {
 int growPools(pgmo_m2g_t* h, uint64_t extra) {
   const uint64_t need = h->pool_used + extra;
   if (need <= h->pool_m.cap) return PGMO_OK;
-  const uint64_t want = std::max<uint64_t>(2 * need, 1ull << 20);
+  // a stream of new blocks keeps appending segments, and a regrowth (cudaMalloc + copy +
+  // cudaFree, twice) costs milliseconds: start at 32 MB per pool and grow fourfold
+  const uint64_t want = std::max<uint64_t>(4 * need, 1ull << 22);
   PGMO_TRY(h->pool_m.reserve(want, h->stream, h->pool_used));
   PGMO_TRY(h->pool_g.reserve(want, h->stream, h->pool_used));
   return PGMO_OK;

@@ -318,6 +318,7 @@ struct TreeStore {
   DevBuf<OctFrames> frames;
   uint64_t cap = 0;
   uint64_t factor = 8;  // table slots per point; doubled when a build reports "table full"
+  uint64_t min_alloc_slots = 1024;  // floor of the allocation (not of the hashed range)
   OctTable table() const {
     OctTable t;
     t.keys = slab.ptr;
@@ -334,8 +335,15 @@ struct TreeStore {
   int reset(uint64_t points, bool reset_frames, cudaStream_t st) {
     const uint64_t want = std::max<uint64_t>(nextPow2(factor * std::max<uint64_t>(points, 1)), 1024);
     if (want > cap) {
-      slab.release();
-      PGMO_TRY(slab.reserve(2 * want));
+      // the table grows with the active set over the first messages of a stream, and every
+      // cudaFree + cudaMalloc pair costs milliseconds here: allocate for one or two more
+      // doublings (at least min_alloc_slots), so `cap` - the hashed and memset range - can grow
+      // in place
+      if (2 * want > slab.cap) {
+        slab.release();
+        const uint64_t room = want <= (1ull << 24) ? 4 * want : 2 * want;  // 16 B per slot
+        PGMO_TRY(slab.reserve(2 * std::max<uint64_t>(room, min_alloc_slots)));
+      }
       cap = want;
     }
     PGMO_TRY(frames.reserve(1));
@@ -574,6 +582,10 @@ int pgmo_oct_create(double resolution, int device, pgmo_oct_t** out) {
   PGMO_CHECK_ARG(h != nullptr);
   h->device = device;
   h->resolution = resolution;
+  // persistent structure: 64 MB of table up front (4 M slots) covers an active set of
+  // 250 k vertices, the steady state of a 50 k-vertex / 10 s-horizon stream, without a regrowth
+  h->ptree.min_alloc_slots = 1ull << 22;
+  h->ttree.min_alloc_slots = 1ull << 19;
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete h;
     setLastError("cudaStreamCreateWithFlags failed");
