@@ -1,3 +1,6 @@
+"""Per-call wall time of the MeshFrontendInterface path (VoxelClearing full mesh + Octree graph
+compressor + mesh -> graph bookkeeping) for 1 and 16 blocks per message; second pass reported
+(the first process on a fresh box is cold).  python scripts/frontend_breakdown.py"""
 import sys, time, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
