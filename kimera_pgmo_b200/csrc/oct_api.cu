@@ -429,10 +429,16 @@ int readCount(pgmo_oct_t* h, int which, cudaStream_t st, uint64_t* out) {
   return PGMO_OK;
 }
 
+// Grow rarely, by a lot: an allocation costs milliseconds (sometimes hundreds) inside the message
+// stream, and buffers sized by the whole mesh would otherwise regrow all along the stream.
+inline uint64_t roomy(uint64_t need, size_t cap) {
+  return need <= cap ? need : std::max<uint64_t>(2 * need, 1ull << 21);
+}
+
 int compact(pgmo_oct_t* h, const uint8_t* flags, uint64_t n, DevBuf<unsigned long long>* list,
             int counter, cudaStream_t st, uint64_t* count) {
-  PGMO_TRY(list->reserve(n + 1));
-  PGMO_TRY(h->tiles.reserve(vccTileScratchEntries(n) + 1));
+  PGMO_TRY(list->reserve(roomy(n + 1, list->cap)));
+  PGMO_TRY(h->tiles.reserve(roomy(vccTileScratchEntries(n) + 1, h->tiles.cap)));
   PGMO_CUDA(launchVccCompactLive(flags, n, reinterpret_cast<uint64_t*>(list->ptr), h->tiles.ptr,
                                  h->counts.ptr + counter, st));
   return readCount(h, counter, st, count);
@@ -551,7 +557,7 @@ int buildPersistentOnce(pgmo_oct_t* h, uint64_t first, cudaStream_t st, uint32_t
 int ensurePolyTable(pgmo_oct_t* h, uint64_t extra, cudaStream_t st) {
   const uint64_t want = std::max<uint64_t>(nextPow2(2 * (h->n_poly + extra) + 16), 1024);
   if (want <= h->pt_cap) return PGMO_OK;
-  const uint64_t cap = want * 2;  // grow with head room
+  const uint64_t cap = std::max<uint64_t>(want * 2, 1ull << 21);  // grow with head room
   h->pt_keys.release();
   h->pt_tri.release();
   h->pt_val.release();
@@ -769,8 +775,6 @@ static int octIntegrate(pgmo_oct_t* h, uint32_t n_blocks, const int32_t* block_i
     }
   }
   // room for the accepted vertices
-  // grow rarely, by a lot: an allocation costs tens of milliseconds inside the message stream
-  auto roomy = [](uint64_t need, size_t cap) { return need <= cap ? need : std::max<uint64_t>(2 * need, 1ull << 21); };
   PGMO_TRY(h->all_vertices.reserve(roomy(n_orig + n_acc + 1, h->all_vertices.cap), st, n_orig));
   PGMO_TRY(h->all_stamps.reserve(roomy(n_orig + n_acc + 1, h->all_stamps.cap), st, n_orig));
   PGMO_TRY(h->act_xyz.reserve(roomy(h->n_act + n_acc + 1, h->act_xyz.cap), st, h->n_act));
@@ -779,7 +783,7 @@ static int octIntegrate(pgmo_oct_t* h, uint32_t n_blocks, const int32_t* block_i
   PGMO_TRY(h->act_next.reserve(h->act_xyz.cap, st, h->n_act));
   PGMO_TRY(h->act_sigma.reserve(h->act_xyz.cap, st, h->n_act));
   PGMO_TRY(h->new_vertices.reserve(n_acc + 1));
-  PGMO_TRY(h->reobs_flag.reserve(n_orig + 1));
+  PGMO_TRY(h->reobs_flag.reserve(roomy(n_orig + 1, h->reobs_flag.cap)));
   PGMO_CUDA(cudaMemsetAsync(h->reobs_flag.ptr, 0, n_orig + 1, st));
   if (n_acc > 0) {
     octCommitVerticesKernel<<<blocksFor(n_acc), 256, 0, st>>>(
@@ -794,9 +798,9 @@ static int octIntegrate(pgmo_oct_t* h, uint32_t n_blocks, const int32_t* block_i
                                                  h->reindex.ptr, h->d_remap_index.ptr, h->d_remap_kind.ptr);
   // new_indices: re-observed indices ascending (sorted-unique insert, :293-299), then the new ones
   uint64_t n_reobs = 0;
-  PGMO_TRY(h->new_indices.reserve(n_orig + n_acc + 1));
+  PGMO_TRY(h->new_indices.reserve(roomy(n_orig + n_acc + 1, h->new_indices.cap)));
   if (n_orig > 0) {
-    PGMO_TRY(h->tiles.reserve(vccTileScratchEntries(n_orig) + 1));
+    PGMO_TRY(h->tiles.reserve(roomy(vccTileScratchEntries(n_orig) + 1, h->tiles.cap)));
     PGMO_CUDA(launchVccCompactLive(h->reobs_flag.ptr, n_orig, reinterpret_cast<uint64_t*>(h->new_indices.ptr),
                                    h->tiles.ptr, h->counts.ptr + 3, st));
   } else {
