@@ -83,6 +83,11 @@ struct pgmo_vcc {
   std::unordered_map<BlockKey, int, BlockKeyHash> block_face_map;  // value unused: order only
   std::unordered_map<BlockKey, BlockDevState*, BlockKeyHash> blocks;
   std::vector<uint32_t> archived_polygons;  // 3 per face
+  // states of pruned blocks, device buffers kept: a voxblox stream opens and archives a few
+  // blocks per message, and every cudaMalloc / cudaFree (the latter a device-wide sync) would
+  // land in the message stream
+  std::vector<BlockDevState*> free_states;
+  PinnedBuf<uint64_t> h_faces;  // prune: face maps of all blocks of a call, one read-back
 
   // staging for the host entry points
   DevBuf<float> d_xyz;
@@ -94,6 +99,7 @@ struct pgmo_vcc {
 
   ~pgmo_vcc() {
     for (auto& kv : blocks) delete kv.second;
+    for (BlockDevState* state : free_states) delete state;
   }
 };
 
@@ -260,7 +266,14 @@ int integrateCore(pgmo_vcc_t* h, uint32_t n_blocks, const int32_t* block_idx_xyz
     const BlockKey key{block_idx_xyz[3 * b], block_idx_xyz[3 * b + 1], block_idx_xyz[3 * b + 2]};
     h->block_update_times[key] = stamp_s;  // :122
     BlockDevState*& state = h->blocks[key];
-    if (!state) state = new BlockDevState();
+    if (!state) {
+      if (h->free_states.empty()) {
+        state = new BlockDevState();
+      } else {
+        state = h->free_states.back();
+        h->free_states.pop_back();
+      }
+    }
     const uint64_t first = block_offsets[b];
     const uint32_t n = static_cast<uint32_t>(block_offsets[b + 1] - first);
     const int cur = state->prev ^ 1;
@@ -316,26 +329,45 @@ int pruneBlocks(pgmo_vcc_t* h, const std::vector<BlockKey>& to_clear, cudaStream
   if (!h->table_cap) PGMO_TRY(ensureTable(h, 0, st));
   const VccTable t = tableOf(h);
   const VccIndexState s = indexStateOf(h);
+  // release the voxel sets and queue every face map into one pinned buffer: one read-back per call
+  uint64_t total_faces = 0;
+  for (const BlockKey& key : to_clear) {
+    const auto it = h->blocks.find(key);
+    if (it != h->blocks.end()) total_faces += it->second->face_count;
+  }
+  PGMO_TRY(h->h_faces.reserve(std::max<uint64_t>(2 * total_faces, 1ull << 16)));
+  uint64_t at = 0;
+  for (const BlockKey& key : to_clear) {
+    const auto it = h->blocks.find(key);
+    if (it == h->blocks.end()) continue;
+    BlockDevState* state = it->second;
+    if (state->has_prev) {
+      PGMO_CUDA(launchVccRelease(t, s, state->list[state->prev].ptr, state->prev_count, true,
+                                 h->counters.ptr, st));
+    }
+    if (state->face_count) {
+      PGMO_CUDA(cudaMemcpyAsync(h->h_faces.ptr + at, state->face_map.ptr,
+                                state->face_count * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+      at += state->face_count;
+    }
+  }
+  if (at) PGMO_CUDA(cudaStreamSynchronize(st));
+  at = 0;
   for (const BlockKey& key : to_clear) {
     auto it = h->blocks.find(key);
     if (it != h->blocks.end()) {
       BlockDevState* state = it->second;
-      if (state->has_prev) {
-        PGMO_CUDA(launchVccRelease(t, s, state->list[state->prev].ptr, state->prev_count, true,
-                                   h->counters.ptr, st));
-      }
       // polygons_.resize(archived); updatePolygons(polygons_, block_face_map_[idx]); archived = size
-      if (state->face_count) {
-        std::vector<uint64_t> faces(state->face_count);
-        PGMO_CUDA(cudaMemcpyAsync(faces.data(), state->face_map.ptr,
-                                  state->face_count * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-        PGMO_CUDA(cudaStreamSynchronize(st));
-        const uint64_t n_faces = state->face_count / 3;
-        for (uint64_t f = 0; f < 3 * n_faces; ++f) {
-          h->archived_polygons.push_back(static_cast<uint32_t>(faces[f]));
-        }
+      const uint64_t n_faces = state->face_count / 3;
+      for (uint64_t f = 0; f < 3 * n_faces; ++f) {
+        h->archived_polygons.push_back(static_cast<uint32_t>(h->h_faces.ptr[at + f]));
       }
-      delete state;
+      at += state->face_count;
+      state->prev = 0;
+      state->has_prev = false;
+      state->prev_count = 0;
+      state->face_count = 0;
+      h->free_states.push_back(state);  // the release kernel above is ordered before any reuse
       h->blocks.erase(it);
     }
     h->block_face_map[key];  // the reference's operator[] (:91) may rehash the map: mirror it
