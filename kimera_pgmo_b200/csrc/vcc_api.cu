@@ -36,12 +36,80 @@ struct BlockKeyHash {
   }
 };
 
+// Per-block device lists come from one pool per handle: a voxblox stream opens and archives a
+// few blocks per message, and a cudaMalloc / cudaFree pair per list (the latter a device-wide
+// sync, either of them tens of milliseconds now and then on this platform) would land in the
+// message stream.  Power-of-two size classes, free lists per class, 64 MB chunks that are never
+// returned.  A released list may be handed out again at once: all work of a handle is ordered
+// on one stream.
+struct BlockPool {
+  static constexpr int kMinClass = 10;  // 1024 entries
+  std::vector<DevBuf<uint64_t>*> chunks;
+  uint64_t chunk_used = 0;  // entries taken from chunks.back()
+  std::vector<uint64_t*> free_lists[48];
+  ~BlockPool() {
+    for (DevBuf<uint64_t>* c : chunks) delete c;
+  }
+  static int classOf(uint64_t n) {
+    int c = kMinClass;
+    while ((1ull << c) < n) ++c;
+    return c;
+  }
+  int alloc(uint64_t n, uint64_t** ptr, uint64_t* cap) {
+    const int c = classOf(n);
+    const uint64_t need = 1ull << c;
+    if (!free_lists[c].empty()) {
+      *ptr = free_lists[c].back();
+      free_lists[c].pop_back();
+    } else {
+      if (chunks.empty() || chunk_used + need > chunks.back()->cap) {
+        DevBuf<uint64_t>* chunk = new (std::nothrow) DevBuf<uint64_t>();
+        PGMO_CHECK_ARG(chunk != nullptr);
+        const int rc = chunk->reserve(std::max<uint64_t>(need, 1ull << 23));
+        if (rc < 0) {
+          delete chunk;
+          return rc;
+        }
+        chunks.push_back(chunk);
+        chunk_used = 0;
+      }
+      *ptr = chunks.back()->ptr + chunk_used;
+      chunk_used += need;
+    }
+    *cap = need;
+    return PGMO_OK;
+  }
+  void release(uint64_t* ptr, uint64_t cap) { free_lists[classOf(cap)].push_back(ptr); }
+};
+
+struct PoolBuf {  // the part of DevBuf's interface the block lists use
+  BlockPool* pool = nullptr;
+  uint64_t* ptr = nullptr;
+  uint64_t cap = 0;
+  PoolBuf() = default;
+  PoolBuf(const PoolBuf&) = delete;
+  PoolBuf& operator=(const PoolBuf&) = delete;
+  ~PoolBuf() {
+    if (ptr) pool->release(ptr, cap);
+  }
+  int reserve(uint64_t n) {  // contents are not kept: every list is rewritten whole
+    if (n <= cap) return PGMO_OK;
+    if (ptr) pool->release(ptr, cap);
+    ptr = nullptr;
+    cap = 0;
+    return pool->alloc(n, &ptr, &cap);
+  }
+};
+
 struct BlockDevState {
-  DevBuf<uint64_t> list[2];  // previous / current distinct voxel keys (ping-pong)
-  int prev = 0;              // which of list[] holds prev_meshes_[block]
+  explicit BlockDevState(BlockPool* pool) {
+    list[0].pool = list[1].pool = face_map.pool = pool;
+  }
+  PoolBuf list[2];  // previous / current distinct voxel keys (ping-pong)
+  int prev = 0;     // which of list[] holds prev_meshes_[block]
   bool has_prev = false;
   uint64_t prev_count = 0;
-  DevBuf<uint64_t> face_map;  // block_face_map_[block] (mesh index per input vertex)
+  PoolBuf face_map;  // block_face_map_[block] (mesh index per input vertex)
   uint64_t face_count = 0;
 };
 
@@ -83,10 +151,7 @@ struct pgmo_vcc {
   std::unordered_map<BlockKey, int, BlockKeyHash> block_face_map;  // value unused: order only
   std::unordered_map<BlockKey, BlockDevState*, BlockKeyHash> blocks;
   std::vector<uint32_t> archived_polygons;  // 3 per face
-  // states of pruned blocks, device buffers kept: a voxblox stream opens and archives a few
-  // blocks per message, and every cudaMalloc / cudaFree (the latter a device-wide sync) would
-  // land in the message stream
-  std::vector<BlockDevState*> free_states;
+  BlockPool block_pool;         // backs every BlockDevState's lists
   PinnedBuf<uint64_t> h_faces;  // prune: face maps of all blocks of a call, one read-back
 
   // staging for the host entry points
@@ -98,8 +163,7 @@ struct pgmo_vcc {
   VoxbloxStage vb_stage;
 
   ~pgmo_vcc() {
-    for (auto& kv : blocks) delete kv.second;
-    for (BlockDevState* state : free_states) delete state;
+    for (auto& kv : blocks) delete kv.second;  // hands the lists back to block_pool (still alive)
   }
 };
 
@@ -163,7 +227,9 @@ int ensureTable(pgmo_vcc_t* h, uint64_t extra, cudaStream_t st) {
   // stream of 50k-vertex messages is launch-latency-bound and a rebuild costs allocations.  The
   // spare buffer set is kept on the handle: a tombstone-only rebuild of the same size allocates
   // nothing.
-  uint64_t cap = std::max<uint64_t>(h->table_cap, 1024);
+  // The floor (4 M slots, 112 MB per buffer set) holds half a million live voxels at that load:
+  // the usual horizon-bounded stream never regrows, and the first table is built at creation.
+  uint64_t cap = std::max<uint64_t>(h->table_cap, 1ull << 22);
   while (cap < 8 * (h->n_live + extra) + 16) cap <<= 1;
   if (cap > (1ull << 31)) {
     setLastError("voxel table would exceed 2^31 slots");
@@ -203,6 +269,12 @@ int ensureTable(pgmo_vcc_t* h, uint64_t extra, cudaStream_t st) {
   h->table_cap = cap;
   h->n_tomb = 0;
   h->used_upper = h->n_live;
+  // the set that was just retired becomes the target of the next rebuild: bring it to the same
+  // size now, inside a call that is slow anyway, instead of inside a later message
+  PGMO_TRY(keys.reserve(cap));
+  PGMO_TRY(vals.reserve(cap));
+  PGMO_TRY(smin.reserve(cap));
+  PGMO_TRY(smax.reserve(cap));
   return PGMO_OK;
 }
 
@@ -266,14 +338,7 @@ int integrateCore(pgmo_vcc_t* h, uint32_t n_blocks, const int32_t* block_idx_xyz
     const BlockKey key{block_idx_xyz[3 * b], block_idx_xyz[3 * b + 1], block_idx_xyz[3 * b + 2]};
     h->block_update_times[key] = stamp_s;  // :122
     BlockDevState*& state = h->blocks[key];
-    if (!state) {
-      if (h->free_states.empty()) {
-        state = new BlockDevState();
-      } else {
-        state = h->free_states.back();
-        h->free_states.pop_back();
-      }
-    }
+    if (!state) state = new BlockDevState(&h->block_pool);
     const uint64_t first = block_offsets[b];
     const uint32_t n = static_cast<uint32_t>(block_offsets[b + 1] - first);
     const int cur = state->prev ^ 1;
@@ -363,11 +428,7 @@ int pruneBlocks(pgmo_vcc_t* h, const std::vector<BlockKey>& to_clear, cudaStream
         h->archived_polygons.push_back(static_cast<uint32_t>(h->h_faces.ptr[at + f]));
       }
       at += state->face_count;
-      state->prev = 0;
-      state->has_prev = false;
-      state->prev_count = 0;
-      state->face_count = 0;
-      h->free_states.push_back(state);  // the release kernel above is ordered before any reuse
+      delete state;  // lists back to the pool; the release kernel above is ordered before any reuse
       h->blocks.erase(it);
     }
     h->block_face_map[key];  // the reference's operator[] (:91) may rehash the map: mirror it
