@@ -782,6 +782,11 @@ static int octIntegrate(pgmo_oct_t* h, uint32_t n_blocks, const int32_t* block_i
   PGMO_TRY(h->act_stamp.reserve(roomy(h->n_act + n_acc + 1, h->act_stamp.cap), st, h->n_act));
   PGMO_TRY(h->act_next.reserve(h->act_xyz.cap, st, h->n_act));
   PGMO_TRY(h->act_sigma.reserve(h->act_xyz.cap, st, h->n_act));
+  // prune's compaction targets follow at once (they would otherwise be allocated inside the
+  // first prune that removes something, in the middle of the stream)
+  PGMO_TRY(h->act_xyz2.reserve(h->act_xyz.cap));
+  PGMO_TRY(h->act_index2.reserve(h->act_index.cap));
+  PGMO_TRY(h->act_stamp2.reserve(h->act_stamp.cap));
   PGMO_TRY(h->new_vertices.reserve(n_acc + 1));
   PGMO_TRY(h->reobs_flag.reserve(roomy(n_orig + 1, h->reobs_flag.cap)));
   PGMO_CUDA(cudaMemsetAsync(h->reobs_flag.ptr, 0, n_orig + 1, st));
