@@ -148,7 +148,9 @@ int reserveRecords(pgmo_delta* h, uint64_t n, cudaStream_t st) {
 // table with room for `entries` keys at load <= 0.5; rebuilt from the alive records when it grows
 // (tombstones and the keys of erased records disappear)
 int ensureTable(pgmo_delta* h, uint64_t entries, cudaStream_t st) {
-  uint64_t want = 1024;
+  // floor: 4 M slots (80 MB) after the doubling below, a million voxel records at load 1/4 - a
+  // horizon-bounded stream never regrows its table in the middle of the stream
+  uint64_t want = 1ull << 21;
   while (want < 2 * entries + 2) want <<= 1;
   if (want <= h->t_cap) return PGMO_OK;
   PGMO_CHECK_ARG(want <= (1ull << 31));
