@@ -45,9 +45,19 @@ class LeafBook {
     uint64_t cap = 64;
     while (cap < 2 * n_points + 16) cap <<= 1;
     mask_ = cap - 1;
+    // the storage of the previous build on this thread (a few MB): a fresh allocation would be
+    // paid in page faults on the critical path of every first deformMesh after a solve
+    slots_.swap(workspace().slots);
+    next_.swap(workspace().next);
     slots_.assign(cap, Slot());
     next_.assign(n_points, -1);
   }
+  ~LeafBook() {
+    slots_.swap(workspace().slots);
+    next_.swap(workspace().next);
+  }
+  LeafBook(const LeafBook&) = delete;
+  LeafBook& operator=(const LeafBook&) = delete;
 
   size_t leafCount() const { return n_leaves_; }
   uint32_t maxLeafPoints() const { return max_leaf_points_; }
@@ -155,9 +165,11 @@ class LeafBook {
  private:
   VoxelKey stableKey(const float p[3]) const {
     // genOctreeKeyforPoint: unsigned((p - min) / resolution), float promoted to double
-    const uint32_t kx = static_cast<uint32_t>((p[0] - min_[0]) / res_);
-    const uint32_t ky = static_cast<uint32_t>((p[1] - min_[1]) / res_);
-    const uint32_t kz = static_cast<uint32_t>((p[2] - min_[2]) / res_);
+    // (the search tree's resolution is 1 m, mesh_deformation.cpp:22-30: x / 1.0 is x, exactly)
+    const bool unit = res_ == 1.0;
+    const uint32_t kx = static_cast<uint32_t>(unit ? p[0] - min_[0] : (p[0] - min_[0]) / res_);
+    const uint32_t ky = static_cast<uint32_t>(unit ? p[1] - min_[1] : (p[1] - min_[1]) / res_);
+    const uint32_t kz = static_cast<uint32_t>(unit ? p[2] - min_[2] : (p[2] - min_[2]) / res_);
     return {static_cast<int32_t>(kx) - shift_[0], static_cast<int32_t>(ky) - shift_[1],
             static_cast<int32_t>(kz) - shift_[2]};
   }
@@ -222,6 +234,14 @@ class LeafBook {
     uint32_t count = 0;
     uint8_t state = kEmpty;
   };
+  struct Workspace {
+    std::vector<Slot> slots;
+    std::vector<int32_t> next;
+  };
+  static Workspace& workspace() {
+    static thread_local Workspace w;
+    return w;
+  }
   std::vector<Slot> slots_;
   std::vector<int32_t> next_;
   uint64_t mask_ = 0;
