@@ -254,7 +254,9 @@ int pgmo_m2g_update(pgmo_m2g_t* h, uint32_t n_blocks, const int32_t* block_idx_x
     PGMO_CHECK_ARG(size < (1ull << 40));
     Segment& seg = h->segments[key];
     if (size > seg.cap) {
-      // move the segment to the end of the pools, twice the room it needs now
+      // move the segment to the end of the pools, twice the room it needs now (the old segment
+      // is abandoned: with doubling, at most as much again as the block finally occupies; like
+      // the reference's maps, nothing here is ever given back)
       const uint64_t room = std::max<uint64_t>(2 * size, 64);
       PGMO_TRY(growPools(h, room));
       const uint64_t to = h->pool_used;
