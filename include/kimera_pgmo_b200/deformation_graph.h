@@ -116,9 +116,16 @@ class DeformationGraphMeshPath {
 
     const std::vector<size_t>* indices_ptr = start_idx == 0 ? nullptr : &to_deform;
     std::vector<std::set<size_t>> vertex_graph_map_deformed;
-    deformation::deformPoints(vertices, vertex_graph_map_deformed, old_vertices, prefix,
-                              vertex_positions_.at(prefix), vertex_stamps_.at(prefix),
-                              optimized_values, k, tol_t, indices_ptr, &b);
+    if (vertex_graph_map) {
+      deformation::deformPoints(vertices, vertex_graph_map_deformed, old_vertices, prefix,
+                                vertex_positions_.at(prefix), vertex_stamps_.at(prefix),
+                                optimized_values, k, tol_t, indices_ptr, &b);
+    } else {
+      // the reference fills a local map nobody reads (:848-855); deformMesh comes this way
+      deformation::deformPointsOnly(vertices, old_vertices, prefix, vertex_positions_.at(prefix),
+                                    vertex_stamps_.at(prefix), optimized_values, k, tol_t,
+                                    indices_ptr, &b);
+    }
 
     if (vertex_graph_map) {  // :857-866
       if (start_idx == 0) {
@@ -171,9 +178,12 @@ class DeformationGraphMeshPath {
   void fillPreviousPoints(Cloud& vertices, char prefix, size_t start_idx) const {
     const auto iter = last_calculated_vertices_.find(prefix);
     if (iter == last_calculated_vertices_.end()) return;
-    for (size_t i = 0; i < start_idx; i++) {
-      traits::set_vertex(vertices, i, traits::get_vertex(iter->second, i));
-    }
+    const auto& cache = iter->second;
+    detail::parallelFor(start_idx, [&](size_t begin, size_t end) {
+      for (size_t i = begin; i < end; i++) {
+        traits::set_vertex(vertices, i, traits::get_vertex(cache, i));
+      }
+    });
   }
 
   // :762-777
@@ -182,9 +192,12 @@ class DeformationGraphMeshPath {
     auto& cache = last_calculated_vertices_[prefix];
     const size_t total_vertices = traits::num_vertices(vertices);
     cache.resize(total_vertices);
-    for (size_t i = start_idx; i < total_vertices; i++) {
-      traits::set_vertex(cache, i, traits::get_vertex(vertices, i));
-    }
+    if (start_idx >= total_vertices) return;
+    detail::parallelFor(total_vertices - start_idx, [&](size_t begin, size_t end) {
+      for (size_t i = start_idx + begin; i < start_idx + end; i++) {
+        traits::set_vertex(cache, i, traits::get_vertex(vertices, i));
+      }
+    });
   }
 
   // :779-806 on the GPU (pgmo_deform_predeform)

@@ -9,14 +9,29 @@
 //   3. one C-ABI call (pgmo_deform_points),
 //   4. scatters the processed vertices back with traits::set_vertex (colour untouched) and
 //      rebuilds std::vector<std::set<size_t>> from the dense association output.
+// The staging buffers of 1. and 4. are page-locked and live in the Backend (PCIe-speed copies
+// that overlap with the kernels, no page faults per call); the gather / scatter loops run on a
+// few threads for large clouds.  Callers that do not read control_point_map (deformMesh, and
+// DeformationGraph::deformPoints without vertex_graph_map) go through deformPointsOnly: no
+// association output crosses PCIe and no std::set is built — for a 10 M-vertex mesh that is
+// the difference between ~50 M heap allocations and none.
 #pragma once
 
+#include <algorithm>
 #include <cstdint>
+#include <exception>
 #include <memory>
+#include <mutex>
 #include <set>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
+
+// upper bound on the threads of the shim's gather / scatter loops (1 = single-threaded)
+#ifndef KIMERA_PGMO_B200_SHIM_THREADS
+#define KIMERA_PGMO_B200_SHIM_THREADS 8
+#endif
 
 #include "kimera_pgmo_b200/deps.h"
 #include "pgmo_b200.h"
@@ -42,6 +57,73 @@ inline void throwOnError(int rc) {
   if (rc == PGMO_ERR_OUT_OF_RANGE) throw std::out_of_range(msg);  // what .at() would have thrown
   throw PgmoB200Error(rc, msg);
 }
+
+// fn(begin, end) over [0, n): on up to KIMERA_PGMO_B200_SHIM_THREADS threads when the range is
+// large, in place otherwise.  The first exception of any part (e.g. the std::out_of_range of a
+// cloud's .at()) is rethrown on the calling thread.
+template <typename Fn>
+void parallelFor(size_t n, Fn&& fn) {
+  constexpr size_t kMinPerThread = size_t(1) << 17;
+  const size_t hw = std::thread::hardware_concurrency();
+  const size_t n_threads = std::min<size_t>(
+      {hw ? hw : 1, static_cast<size_t>(KIMERA_PGMO_B200_SHIM_THREADS), n / kMinPerThread});
+  if (n_threads <= 1) {
+    fn(size_t(0), n);
+    return;
+  }
+  std::exception_ptr error;
+  std::mutex error_mutex;
+  auto part = [&](size_t t) {
+    try {
+      fn(n * t / n_threads, n * (t + 1) / n_threads);
+    } catch (...) {
+      std::lock_guard<std::mutex> lock(error_mutex);
+      if (!error) error = std::current_exception();
+    }
+  };
+  std::vector<std::thread> pool;
+  pool.reserve(n_threads - 1);
+  for (size_t t = 1; t < n_threads; ++t) pool.emplace_back(part, t);
+  part(0);
+  for (std::thread& th : pool) th.join();
+  if (error) std::rethrow_exception(error);
+}
+
+// Grow-only page-locked host block (pgmo_host_alloc), carved into the per-call arrays.
+class PinnedBlock {
+ public:
+  PinnedBlock() = default;
+  PinnedBlock(const PinnedBlock&) = delete;
+  PinnedBlock& operator=(const PinnedBlock&) = delete;
+  ~PinnedBlock() {
+    if (ptr_) pgmo_host_free(ptr_);
+  }
+  void reserve(size_t bytes) {
+    if (bytes <= bytes_) return;
+    if (ptr_) throwOnError(pgmo_host_free(ptr_));
+    ptr_ = nullptr;
+    bytes_ = 0;
+    const size_t want = bytes + bytes / 2;  // page-locking is slow: grow rarely
+    throwOnError(pgmo_host_alloc(want, &ptr_));
+    bytes_ = want;
+    used_ = 0;
+  }
+  void rewind() { used_ = 0; }
+  // the next `count` elements of T, 256-byte aligned (reserve() must have covered them)
+  template <typename T>
+  T* take(size_t count) {
+    used_ = (used_ + 255) & ~size_t(255);
+    T* out = reinterpret_cast<T*>(static_cast<char*>(ptr_) + used_);
+    used_ += count * sizeof(T);
+    if (used_ > bytes_) throw std::logic_error("pgmo_b200: staging block overrun");
+    return out;
+  }
+  static size_t padded(size_t bytes) { return (bytes + 255) & ~size_t(255); }
+
+ private:
+  void* ptr_ = nullptr;
+  size_t bytes_ = 0, used_ = 0;
+};
 }  // namespace detail
 
 namespace deformation {
@@ -56,6 +138,11 @@ class Backend {
     handle_.reset(h, [](pgmo_deform_t* p) { pgmo_deform_destroy(p); });
   }
   pgmo_deform_t* get() const { return handle_.get(); }
+  // page-locked staging shared by the copies of this Backend (calls are serial per Backend)
+  kimera_pgmo_b200::detail::PinnedBlock& staging() {
+    if (!staging_) staging_ = std::make_shared<kimera_pgmo_b200::detail::PinnedBlock>();
+    return *staging_;
+  }
 
   // Uploads control positions / stamps and the flattened `values`.
   void setControls(char prefix, const std::vector<gtsam::Point3>& control_points,
@@ -91,6 +178,7 @@ class Backend {
 
  private:
   std::shared_ptr<pgmo_deform_t> handle_;
+  std::shared_ptr<kimera_pgmo_b200::detail::PinnedBlock> staging_;
   std::vector<double> pos_, poses_;
   std::vector<uint8_t> valid_;
 };
@@ -103,45 +191,95 @@ inline Backend& defaultBackend() {
   return backend;
 }
 
+// control_point_map == nullptr: the caller does not read the associations (no association
+// output, no std::set construction).
 template <typename CloudOut, typename CloudIn>
 void run(Backend& backend, CloudOut& new_points,
-         std::vector<std::set<size_t>>& control_point_map, const CloudIn& points, bool stamped,
+         std::vector<std::set<size_t>>* control_point_map, const CloudIn& points, bool stamped,
          size_t k, double tol_t, const std::vector<size_t>* indices, int precision) {
+  using kimera_pgmo_b200::detail::parallelFor;
+  using kimera_pgmo_b200::detail::PinnedBlock;
   const size_t n_v = traits::num_vertices(points);
-  std::vector<float> x(n_v), y(n_v), z(n_v);
-  std::vector<uint64_t> stamps(stamped ? n_v : 0);
-  for (size_t i = 0; i < n_v; ++i) {
-    const traits::Pos p = traits::get_vertex(points, i);
-    x[i] = p.x();
-    y[i] = p.y();
-    z[i] = p.z();
-    if (stamped) stamps[i] = traits::get_timestamp(points, i);
-  }
+  const size_t n_pos = indices ? indices->size() : n_v;
+  PinnedBlock& stage = backend.staging();
+  stage.reserve(6 * PinnedBlock::padded(n_v * sizeof(float)) +
+                PinnedBlock::padded(stamped ? n_v * sizeof(uint64_t) : 0) +
+                PinnedBlock::padded(n_pos) + 256);
+  stage.rewind();
+  float* x = stage.take<float>(n_v);
+  float* y = stage.take<float>(n_v);
+  float* z = stage.take<float>(n_v);
+  float* ox = stage.take<float>(n_v);  // only read back where `processed` is set
+  float* oy = stage.take<float>(n_v);
+  float* oz = stage.take<float>(n_v);
+  uint64_t* stamps = stamped ? stage.take<uint64_t>(n_v) : nullptr;
+  uint8_t* processed = stage.take<uint8_t>(n_pos);
+  parallelFor(n_v, [&](size_t begin, size_t end) {
+    for (size_t i = begin; i < end; ++i) {
+      const traits::Pos p = traits::get_vertex(points, i);
+      x[i] = p.x();
+      y[i] = p.y();
+      z[i] = p.z();
+      if (stamped) stamps[i] = traits::get_timestamp(points, i);
+    }
+  });
   std::vector<uint64_t> subset;
   if (indices) subset.assign(indices->begin(), indices->end());
-  const size_t n_pos = indices ? indices->size() : n_v;
   const uint32_t stride = static_cast<uint32_t>(k + 2 > 8 ? k + 2 : 8);
-  std::vector<float> ox(x), oy(y), oz(z);
-  std::vector<uint32_t> assoc(n_pos * stride);
-  std::vector<uint8_t> cnt(n_pos), processed(n_pos);
-  int rc = pgmo_deform_points(backend.get(), n_v, x.data(), y.data(), z.data(),
-                              stamped ? stamps.data() : nullptr,
+  std::vector<uint32_t> assoc(control_point_map ? n_pos * stride : 0);
+  std::vector<uint8_t> cnt(control_point_map ? n_pos : 0);
+  int rc = pgmo_deform_points(backend.get(), n_v, x, y, z, stamps,
                               indices ? subset.data() : nullptr, subset.size(),
-                              static_cast<uint32_t>(k), tol_t, precision, ox.data(), oy.data(),
-                              oz.data(), nullptr, assoc.data(), stride, cnt.data(),
-                              processed.data());
+                              static_cast<uint32_t>(k), tol_t, precision, ox, oy, oz, nullptr,
+                              control_point_map ? assoc.data() : nullptr, stride,
+                              control_point_map ? cnt.data() : nullptr, processed);
   kimera_pgmo_b200::detail::throwOnError(rc);
   if (rc == PGMO_NOOP) return;  // the reference returned before control_point_map.clear()
-  control_point_map.clear();
+  if (!control_point_map) {
+    parallelFor(n_pos, [&](size_t begin, size_t end) {
+      for (size_t p = begin; p < end; ++p) {
+        if (!processed[p]) continue;  // skipped vertices stay as they are (:184-186)
+        const size_t ii = indices ? (*indices)[p] : p;
+        traits::set_vertex(new_points, ii, traits::Pos(ox[ii], oy[ii], oz[ii]));
+      }
+    });
+    return;
+  }
+  control_point_map->clear();
   for (size_t p = 0; p < n_pos; ++p) {
     if (!processed[p]) continue;  // skipped vertices own no entry (mesh_deformation.h:184-186)
     const size_t ii = indices ? (*indices)[p] : p;
-    control_point_map.emplace_back();
+    control_point_map->emplace_back();
     // neighbour counts above the stride only occur for degenerate k; the set is what callers use
     const uint32_t n = cnt[p] < stride ? cnt[p] : stride;
-    for (uint32_t j = 0; j < n; ++j) control_point_map.back().insert(assoc[p * stride + j]);
+    for (uint32_t j = 0; j < n; ++j) control_point_map->back().insert(assoc[p * stride + j]);
     traits::set_vertex(new_points, ii, traits::Pos(ox[ii], oy[ii], oz[ii]));
   }
+}
+
+// common body of the public overloads (early returns as in the reference)
+template <typename CloudOut, typename CloudIn>
+void deformPointsImpl(CloudOut& new_points, std::vector<std::set<size_t>>* control_point_map,
+                      const CloudIn& points, char prefix,
+                      const std::vector<gtsam::Point3>& control_points,
+                      const std::vector<Timestamp>& control_point_stamps,
+                      const gtsam::Values& values, size_t k, double tol_t,
+                      const std::vector<size_t>* indices, Backend* backend, int precision) {
+  constexpr bool kStamped = traits::has_get_stamp<CloudIn>::value;
+  const size_t num_points = indices ? indices->size() : traits::num_vertices(points);
+  if (!num_points) return;
+  if (kStamped) {
+    if (control_points.size() < k) return;  // "Not enough valid control points to deform points"
+    if (control_point_stamps.size() < control_points.size()) {
+      throw std::out_of_range("control_point_stamps shorter than control_points");
+    }
+  } else if (control_points.size() == 0) {
+    return;  // "No control points. No deformation"
+  }
+  Backend& b = backend ? *backend : defaultBackend();
+  b.setControls(prefix, control_points, kStamped ? &control_point_stamps : nullptr, values);
+  run(b, new_points, control_point_map, points, kStamped, k, kStamped ? tol_t : 0.0, indices,
+      precision);
 }
 
 }  // namespace detail
@@ -152,16 +290,12 @@ template <typename CloudOut, typename CloudIn,
 void deformPoints(CloudOut& new_points, std::vector<std::set<size_t>>& control_point_map,
                   const CloudIn& points, char prefix,
                   const std::vector<gtsam::Point3>& control_points,
-                  const std::vector<Timestamp>& /* control_point_stamps */,
-                  const gtsam::Values& values, size_t k = 4, double /* tol_t */ = 10.0,
+                  const std::vector<Timestamp>& control_point_stamps,
+                  const gtsam::Values& values, size_t k = 4, double tol_t = 10.0,
                   const std::vector<size_t>* indices = nullptr, Backend* backend = nullptr,
                   int precision = PGMO_PRECISION_FP64) {
-  const size_t num_points = indices ? indices->size() : traits::num_vertices(points);
-  if (!num_points) return;
-  if (control_points.size() == 0) return;  // "No control points. No deformation"
-  Backend& b = backend ? *backend : detail::defaultBackend();
-  b.setControls(prefix, control_points, nullptr, values);
-  detail::run(b, new_points, control_point_map, points, false, k, 0.0, indices, precision);
+  detail::deformPointsImpl(new_points, &control_point_map, points, prefix, control_points,
+                           control_point_stamps, values, k, tol_t, indices, backend, precision);
 }
 
 // mesh_deformation.h:129-213 — stamped clouds
@@ -174,15 +308,22 @@ void deformPoints(CloudOut& new_points, std::vector<std::set<size_t>>& control_p
                   const gtsam::Values& values, size_t k = 4, double tol_t = 10.0,
                   const std::vector<size_t>* indices = nullptr, Backend* backend = nullptr,
                   int precision = PGMO_PRECISION_FP64) {
-  const size_t num_points = indices ? indices->size() : traits::num_vertices(points);
-  if (!num_points) return;
-  if (control_points.size() < k) return;  // "Not enough valid control points to deform points"
-  if (control_point_stamps.size() < control_points.size()) {
-    throw std::out_of_range("control_point_stamps shorter than control_points");
-  }
-  Backend& b = backend ? *backend : detail::defaultBackend();
-  b.setControls(prefix, control_points, &control_point_stamps, values);
-  detail::run(b, new_points, control_point_map, points, true, k, tol_t, indices, precision);
+  detail::deformPointsImpl(new_points, &control_point_map, points, prefix, control_points,
+                           control_point_stamps, values, k, tol_t, indices, backend, precision);
+}
+
+// Extension (no reference counterpart): either overload above for callers that do not read
+// control_point_map — same vertices, same early returns; nothing is computed, copied or
+// allocated for the associations.
+template <typename CloudOut, typename CloudIn>
+void deformPointsOnly(CloudOut& new_points, const CloudIn& points, char prefix,
+                      const std::vector<gtsam::Point3>& control_points,
+                      const std::vector<Timestamp>& control_point_stamps,
+                      const gtsam::Values& values, size_t k = 4, double tol_t = 10.0,
+                      const std::vector<size_t>* indices = nullptr, Backend* backend = nullptr,
+                      int precision = PGMO_PRECISION_FP64) {
+  detail::deformPointsImpl(new_points, nullptr, points, prefix, control_points,
+                           control_point_stamps, values, k, tol_t, indices, backend, precision);
 }
 
 }  // namespace deformation

@@ -59,6 +59,13 @@ const char* pgmo_version(void);
 int pgmo_device_count(void);
 uint64_t pgmo_stamp_from_sec(double sec);
 
+/* Page-locked host memory for the caller's staging buffers (what the C++ shim gathers the
+ * reference's AoS clouds into): copies from / to it run at PCIe speed and overlap with the
+ * kernels; plain pageable memory is accepted everywhere too, only slower.  No reference
+ * counterpart (the reference has no device).  bytes == 0 yields *out = NULL. */
+int pgmo_host_alloc(uint64_t bytes, void** out);
+int pgmo_host_free(void* ptr);
+
 /* ------------------------------------------------------------------------------------------
  * Deformation: deformation::deformPoints behind one handle per (DeformationGraph, prefix).
  * ---------------------------------------------------------------------------------------- */

@@ -40,6 +40,8 @@ SIGNATURES = {
     "pgmo_version": (C.c_char_p, []),
     "pgmo_device_count": (C.c_int, []),
     "pgmo_stamp_from_sec": (C.c_uint64, [C.c_double]),
+    "pgmo_host_alloc": (C.c_int, [C.c_uint64, C.POINTER(_vp)]),
+    "pgmo_host_free": (C.c_int, [_vp]),
     "pgmo_deform_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
     "pgmo_deform_destroy": (None, [_vp]),
     "pgmo_deform_set_controls": (C.c_int, [_vp, C.c_uint64, _vp, _vp, _vp, _vp]),

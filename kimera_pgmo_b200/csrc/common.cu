@@ -70,4 +70,22 @@ int pgmo_device_count(void) {
 }
 uint64_t pgmo_stamp_from_sec(double sec) { return pgmo::stampFromSec(sec); }
 
+int pgmo_host_alloc(uint64_t bytes, void** out) {
+  PGMO_CHECK_ARG(out != nullptr);
+  *out = nullptr;
+  if (bytes == 0) return PGMO_OK;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) {
+    cudaGetLastError();
+    pgmo::setLastError("no CUDA device available; libpgmo_b200 has no CPU fallback");
+    return PGMO_ERR_NO_DEVICE;
+  }
+  PGMO_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocPortable));
+  return PGMO_OK;
+}
+int pgmo_host_free(void* ptr) {
+  if (ptr) PGMO_CUDA(cudaFreeHost(ptr));
+  return PGMO_OK;
+}
+
 }  // extern "C"
