@@ -117,6 +117,77 @@ static void testDeformPointsWithTimeCheck() {
   }
 }
 
+// No reference counterpart: a cloud large enough for the shim's threaded gather / scatter
+// (detail::parallelFor engages above 2^18 vertices).  deformPointsOnly must give the vertices
+// of deformPoints bit for bit, for the whole cloud and for an `indices` subset, and leave the
+// vertices outside the subset alone.
+static void testLargeCloudStaging() {
+  typedef pcl::PointXYZ Point;
+  const size_t n = 600000, n_ctrl = 300;
+  pcl::PointCloud<Point> points;
+  std::vector<Timestamp> stamps;
+  std::vector<gtsam::Point3> control_points;
+  std::vector<Timestamp> control_point_stamps;
+  gtsam::Values values;
+  const char prefix = 'a';
+  uint32_t lcg = 12345u;
+  auto unit = [&lcg]() {
+    lcg = lcg * 1664525u + 1013904223u;
+    return static_cast<float>(lcg >> 8) / 16777216.0f;
+  };
+  for (size_t j = 0; j < n_ctrl; j++) {
+    control_points.push_back(gtsam::Point3(0.5 * static_cast<double>(j), unit(), unit()));
+    control_point_stamps.push_back(stampFromSec(0.5 * static_cast<double>(j)));
+    values.insert(gtsam::Symbol(prefix, j),
+                  gtsam::Pose3(gtsam::Rot3::Rz(0.001 * static_cast<double>(j)),
+                               gtsam::Point3(0.5 * static_cast<double>(j) + 0.25, 0.5, -0.1)));
+  }
+  for (size_t i = 0; i < n; i++) {
+    const double s = 150.0 * static_cast<double>(i) / static_cast<double>(n);
+    points.push_back(Point(static_cast<float>(s) + unit(), 4.0f * unit() - 2.0f, 2.0f * unit()));
+    stamps.push_back(stampFromSec(std::floor(s)));
+  }
+  const ConstStampedCloud<Point> cloud{points, stamps};
+
+  pcl::PointCloud<Point> with_map = points, only = points;
+  std::vector<std::set<size_t>> control_point_map;
+  deformation::deformPoints(with_map, control_point_map, cloud, prefix, control_points,
+                            control_point_stamps, values, 4, 10.0);
+  deformation::deformPointsOnly(only, cloud, prefix, control_points, control_point_stamps, values,
+                                4, 10.0);
+  EXPECT_EQ(n, control_point_map.size());
+  size_t differing = 0, moved = 0, small_sets = 0;
+  for (size_t i = 0; i < n; i++) {
+    differing += std::memcmp(&with_map.points[i], &only.points[i], 3 * sizeof(float)) != 0;
+    moved += std::memcmp(&with_map.points[i], &points.points[i], 3 * sizeof(float)) != 0;
+  }
+  for (const auto& s : control_point_map) small_sets += s.size() < 2;
+  EXPECT_EQ(size_t(0), differing);
+  EXPECT_TRUE(moved > n / 2);
+  EXPECT_EQ(size_t(0), small_sets);
+
+  // incremental form: every third vertex of the second half
+  std::vector<size_t> indices;
+  for (size_t i = n / 2; i < n; i += 3) indices.push_back(i);
+  pcl::PointCloud<Point> sub_map = points, sub_only = points;
+  control_point_map.clear();
+  deformation::deformPoints(sub_map, control_point_map, cloud, prefix, control_points,
+                            control_point_stamps, values, 4, 10.0, &indices);
+  deformation::deformPointsOnly(sub_only, cloud, prefix, control_points, control_point_stamps,
+                                values, 4, 10.0, &indices);
+  EXPECT_EQ(indices.size(), control_point_map.size());
+  size_t sub_differing = 0, touched_outside = 0;
+  for (size_t i = 0; i < n; i++) {
+    sub_differing += std::memcmp(&sub_map.points[i], &sub_only.points[i], 3 * sizeof(float)) != 0;
+    const bool in_subset = i >= n / 2 && (i - n / 2) % 3 == 0;
+    if (!in_subset) {
+      touched_outside += std::memcmp(&sub_only.points[i], &points.points[i], 3 * sizeof(float)) != 0;
+    }
+  }
+  EXPECT_EQ(size_t(0), sub_differing);
+  EXPECT_EQ(size_t(0), touched_outside);
+}
+
 // ------------------------------------------------------------------ TestDeformationGraph
 static pcl::PointXYZRGBA colored(float x, float y, float z, uint8_t r, uint8_t g, uint8_t b) {
   pcl::PointXYZRGBA p;
@@ -737,6 +808,7 @@ int main(int argc, char** argv) {
   }
   testDeformPoints();
   testDeformPointsWithTimeCheck();
+  testLargeCloudStaging();
   testReconstructAndTranslate();
   testDeformMeshCube();
   testIncrementalWithPredeform();
