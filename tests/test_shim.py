@@ -37,6 +37,20 @@ def test_stdsort_restatement_matches_toolchain():
     assert p.returncode == 0, p.stdout + p.stderr
 
 
+def test_shim_host_side_helpers(capi):
+    """parallelFor / PinnedBlock arithmetic of the shim: pure host code, no device call."""
+    exe = os.path.join(ROOT, "build", "tests", "test_shim_host")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    lib_dir = os.path.join(ROOT, "kimera_pgmo_b200", "lib")
+    p = subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-pthread", "-I",
+                        os.path.join(ROOT, "include"), "-o", exe,
+                        os.path.join(ROOT, "tests", "cpp", "test_shim_host.cpp"), "-L", lib_dir,
+                        "-lpgmo_b200", f"-Wl,-rpath,{lib_dir}"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr[-3000:]
+    p = subprocess.run([exe], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+
+
 @pytest.mark.gpu
 def test_reference_unit_tests_through_shim(capi):
     _build()
