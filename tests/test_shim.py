@@ -51,6 +51,29 @@ def test_shim_host_side_helpers(capi):
     assert p.returncode == 0, p.stdout + p.stderr
 
 
+def test_shim_host_logic_against_oracle_backed_double():
+    """The deformation half of tests/cpp/test_shim.cpp (the reference's unit tests + the large
+    threaded-staging case) with tests/cpp/mock_deform_backend.cpp — a TEST DOUBLE of the C ABI on
+    top of the CPU oracle — linked instead of libpgmo_b200.so: checks the shim's host logic
+    (start index, cache, predeform scatter, staging, set rebuilding, early returns) without a
+    GPU.  The product library has no CPU path; the GPU suite runs the same file against it."""
+    exe = os.path.join(ROOT, "build", "tests", "test_shim_hostlogic")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    oracle_dir = os.path.join(ROOT, "oracle")
+    p = subprocess.run(["make", "-C", oracle_dir, "-j4"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    p = subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-pthread",
+                        "-DSHIM_TEST_DEFORMATION_ONLY", "-I", os.path.join(ROOT, "include"),
+                        "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_shim.cpp"),
+                        os.path.join(ROOT, "tests", "cpp", "mock_deform_backend.cpp"),
+                        "-L", oracle_dir, "-loracle", f"-Wl,-rpath,{oracle_dir}"],
+                       capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr[-3000:]
+    p = subprocess.run([exe], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert " 0 failures" in p.stdout
+
+
 @pytest.mark.gpu
 def test_reference_unit_tests_through_shim(capi):
     _build()
