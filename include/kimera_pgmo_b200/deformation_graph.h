@@ -53,7 +53,12 @@ class DeformationGraphMeshPath {
     deformPoints(new_vertices, new_vertices, stamps, prefix, optimized_values, k, tol_t,
                  &graph_indices);
     pcl::PolygonMesh new_mesh;
-    new_mesh.polygons = original_mesh.polygons;
+    // new_mesh.polygons = original_mesh.polygons (:555), one heap block per face: on a few
+    // threads for large meshes
+    new_mesh.polygons.resize(original_mesh.polygons.size());
+    detail::parallelFor(original_mesh.polygons.size(), [&](size_t begin, size_t end) {
+      for (size_t f = begin; f < end; f++) new_mesh.polygons[f] = original_mesh.polygons[f];
+    });
     pcl::toPCLPointCloud2(new_vertices, new_mesh.cloud);
     return new_mesh;
   }
