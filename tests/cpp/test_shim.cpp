@@ -192,6 +192,46 @@ static void testLargeCloudStaging() {
   }
   EXPECT_EQ(size_t(0), sub_differing);
   EXPECT_EQ(size_t(0), touched_outside);
+
+  // the same cloud as a mesh through DeformationGraph::deformMesh (full recompute): vertices of
+  // deformPointsOnly, colours and faces of the input (300k faces: the threaded polygon copy)
+  DeformationGraphMeshPath graph;
+  for (size_t j = 0; j < n_ctrl; j++) {
+    graph.addControlPoint(prefix, control_points[j], control_point_stamps[j]);
+  }
+  pcl::PointCloud<pcl::PointXYZRGBA> colored_points;
+  colored_points.points.resize(n);
+  for (size_t i = 0; i < n; i++) {
+    pcl::PointXYZRGBA& p = colored_points.points[i];
+    p.x = points.points[i].x;
+    p.y = points.points[i].y;
+    p.z = points.points[i].z;
+    p.rgba = static_cast<uint32_t>(i * 2654435761u);
+  }
+  pcl::PolygonMesh mesh;
+  pcl::toPCLPointCloud2(colored_points, mesh.cloud);
+  mesh.polygons.resize(n / 2);
+  for (size_t f = 0; f < mesh.polygons.size(); f++) {
+    const uint32_t a = static_cast<uint32_t>(2 * f);
+    mesh.polygons[f].vertices = {a, a + 1, static_cast<uint32_t>((a + 7) % n)};
+  }
+  const std::vector<int> graph_indices(n, 0);
+  const pcl::PolygonMesh deformed = graph.deformMesh(mesh, stamps, graph_indices, prefix, values, 4);
+  pcl::PointCloud<pcl::PointXYZRGBA> deformed_points;
+  pcl::fromPCLPointCloud2(deformed.cloud, deformed_points);
+  EXPECT_EQ(n, deformed_points.points.size());
+  EXPECT_EQ(mesh.polygons.size(), deformed.polygons.size());
+  size_t mesh_differing = 0, colour_differing = 0, face_differing = 0;
+  for (size_t i = 0; i < n && i < deformed_points.points.size(); i++) {
+    mesh_differing += std::memcmp(&deformed_points.points[i], &only.points[i], 3 * sizeof(float)) != 0;
+    colour_differing += deformed_points.points[i].rgba != colored_points.points[i].rgba;
+  }
+  for (size_t f = 0; f < mesh.polygons.size() && f < deformed.polygons.size(); f++) {
+    face_differing += !(mesh.polygons[f].vertices == deformed.polygons[f].vertices);
+  }
+  EXPECT_EQ(size_t(0), mesh_differing);
+  EXPECT_EQ(size_t(0), colour_differing);
+  EXPECT_EQ(size_t(0), face_differing);
 }
 
 // ------------------------------------------------------------------ TestDeformationGraph
