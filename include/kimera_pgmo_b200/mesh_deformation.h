@@ -19,7 +19,9 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <exception>
+#include <new>
 #include <memory>
 #include <mutex>
 #include <set>
@@ -89,25 +91,31 @@ void parallelFor(size_t n, Fn&& fn) {
   if (error) std::rethrow_exception(error);
 }
 
-// Grow-only page-locked host block (pgmo_host_alloc), carved into the per-call arrays.
+// Grow-only host block carved into the per-call arrays: page-locked (pgmo_host_alloc) when the
+// driver grants it, plain pageable memory otherwise (accepted by every entry point, only slower).
 class PinnedBlock {
  public:
   PinnedBlock() = default;
   PinnedBlock(const PinnedBlock&) = delete;
   PinnedBlock& operator=(const PinnedBlock&) = delete;
-  ~PinnedBlock() {
-    if (ptr_) pgmo_host_free(ptr_);
-  }
+  ~PinnedBlock() { release(); }
   void reserve(size_t bytes) {
     if (bytes <= bytes_) return;
-    if (ptr_) throwOnError(pgmo_host_free(ptr_));
-    ptr_ = nullptr;
-    bytes_ = 0;
+    release();
     const size_t want = bytes + bytes / 2;  // page-locking is slow: grow rarely
-    throwOnError(pgmo_host_alloc(want, &ptr_));
+    const int rc = pgmo_host_alloc(want, &ptr_);
+    if (rc == PGMO_ERR_CUDA) {  // e.g. the locked-memory limit: stage through pageable memory
+      ptr_ = std::malloc(want);
+      if (!ptr_) throw std::bad_alloc();
+      pinned_ = false;
+    } else {
+      throwOnError(rc);
+      pinned_ = true;
+    }
     bytes_ = want;
     used_ = 0;
   }
+  bool pinned() const { return pinned_; }
   void rewind() { used_ = 0; }
   // the next `count` elements of T, 256-byte aligned (reserve() must have covered them)
   template <typename T>
@@ -121,8 +129,15 @@ class PinnedBlock {
   static size_t padded(size_t bytes) { return (bytes + 255) & ~size_t(255); }
 
  private:
+  void release() {
+    if (ptr_ && pinned_) pgmo_host_free(ptr_);
+    if (ptr_ && !pinned_) std::free(ptr_);
+    ptr_ = nullptr;
+    bytes_ = used_ = 0;
+  }
   void* ptr_ = nullptr;
   size_t bytes_ = 0, used_ = 0;
+  bool pinned_ = true;
 };
 }  // namespace detail
 

@@ -80,7 +80,14 @@ int pgmo_host_alloc(uint64_t bytes, void** out) {
     pgmo::setLastError("no CUDA device available; libpgmo_b200 has no CPU fallback");
     return PGMO_ERR_NO_DEVICE;
   }
-  PGMO_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocPortable));
+  const cudaError_t err = cudaHostAlloc(out, bytes, cudaHostAllocPortable);
+  if (err != cudaSuccess) {
+    cudaGetLastError();  // not sticky: the caller may go on with pageable memory
+    *out = nullptr;
+    pgmo::setLastError("cudaHostAlloc(%llu bytes) -> %s", static_cast<unsigned long long>(bytes),
+                       cudaGetErrorString(err));
+    return PGMO_ERR_CUDA;
+  }
   return PGMO_OK;
 }
 int pgmo_host_free(void* ptr) {

@@ -44,6 +44,11 @@ int pgmo_device_count(void) { return 1; }
 uint64_t pgmo_stamp_from_sec(double sec) { return oracle_stamp_from_sec(sec); }
 
 int pgmo_host_alloc(uint64_t bytes, void** out) {
+  if (std::getenv("MOCK_PINNED_ALLOC_FAILS")) {  // the shim must go on with pageable staging
+    *out = nullptr;
+    g_error = "test double: page-locking refused";
+    return PGMO_ERR_CUDA;
+  }
   *out = bytes ? std::malloc(bytes) : nullptr;
   return bytes && !*out ? PGMO_ERR_CUDA : PGMO_OK;
 }

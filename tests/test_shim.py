@@ -72,6 +72,11 @@ def test_shim_host_logic_against_oracle_backed_double():
     p = subprocess.run([exe], capture_output=True, text=True)
     assert p.returncode == 0, p.stdout + p.stderr
     assert " 0 failures" in p.stdout
+    # page-locking refused (e.g. the locked-memory limit): the shim stages through pageable memory
+    p = subprocess.run([exe], capture_output=True, text=True,
+                       env=dict(os.environ, MOCK_PINNED_ALLOC_FAILS="1"))
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert " 0 failures" in p.stdout
 
 
 @pytest.mark.gpu
