@@ -123,6 +123,109 @@ static void testDeformPointsWithTimeCheck() {
   }
 }
 
+// The reference's silent early returns (mesh_deformation.h:78-86, :96-99, :143-152;
+// deformation_graph.h:819-823) and its .at() failures, through the shim.
+static pcl::PointXYZRGBA colored(float x, float y, float z, uint8_t r, uint8_t g, uint8_t b);
+static void testEarlyReturnsAndErrors() {
+  typedef pcl::PointXYZ Point;
+  const char prefix = 'a';
+  pcl::PointCloud<Point> points;
+  std::vector<Timestamp> stamps;
+  for (size_t i = 0; i < 20; i++) {
+    points.push_back(Point(static_cast<float>(i), 0.5f, 0.0f));
+    stamps.push_back(stampFromSec(1.0));
+  }
+  std::vector<gtsam::Point3> control_points;
+  std::vector<Timestamp> control_point_stamps;
+  gtsam::Values values;
+  for (size_t j = 0; j < 3; j++) {
+    control_points.push_back(gtsam::Point3(5.0 * static_cast<double>(j), 0.0, 0.0));
+    control_point_stamps.push_back(stampFromSec(1.0));
+    values.insert(gtsam::Symbol(prefix, j),
+                  gtsam::Pose3(gtsam::Rot3(), gtsam::Point3(5.0 * static_cast<double>(j), 2.0, 0.0)));
+  }
+  const std::vector<std::set<size_t>> sentinel(1, std::set<size_t>{42});
+  auto untouched = [&](const pcl::PointCloud<Point>& out, const std::vector<std::set<size_t>>& map) {
+    bool same = out.size() == points.size() && map == sentinel;
+    for (size_t i = 0; same && i < out.size(); i++) {
+      same = std::memcmp(&out.points[i], &points.points[i], 3 * sizeof(float)) == 0;
+    }
+    return same;
+  };
+  const ConstStampedCloud<Point> cloud{points, stamps};
+
+  {  // empty cloud (:78-80 / :143-145): the map is not even cleared
+    pcl::PointCloud<Point> none, out;
+    std::vector<std::set<size_t>> map = sentinel;
+    deformation::deformPoints(out, map, none, prefix, control_points, {}, values);
+    EXPECT_TRUE(map == sentinel);
+    EXPECT_EQ(size_t(0), out.size());
+  }
+  {  // unstamped, no control points (:83-86)
+    pcl::PointCloud<Point> out = points;
+    std::vector<std::set<size_t>> map = sentinel;
+    deformation::deformPoints(out, map, points, prefix, {}, {}, values);
+    EXPECT_TRUE(untouched(out, map));
+  }
+  {  // stamped, fewer control points than k (:148-152)
+    pcl::PointCloud<Point> out = points;
+    std::vector<std::set<size_t>> map = sentinel;
+    deformation::deformPoints(out, map, cloud, prefix, control_points, control_point_stamps, values,
+                              4, 10.0);
+    EXPECT_TRUE(untouched(out, map));
+    deformation::deformPointsOnly(out, cloud, prefix, control_points, control_point_stamps, values,
+                                  4, 10.0);
+    EXPECT_TRUE(untouched(out, map));
+  }
+  {  // empty `indices`: nothing to do
+    pcl::PointCloud<Point> out = points;
+    std::vector<std::set<size_t>> map = sentinel;
+    const std::vector<size_t> no_indices;
+    deformation::deformPoints(out, map, cloud, prefix, control_points, control_point_stamps, values,
+                              2, 10.0, &no_indices);
+    EXPECT_TRUE(untouched(out, map));
+  }
+  {  // control_point_stamps.at(j) past its end
+    pcl::PointCloud<Point> out = points;
+    std::vector<std::set<size_t>> map = sentinel;
+    const std::vector<Timestamp> short_stamps(2, stampFromSec(1.0));
+    bool thrown = false;
+    try {
+      deformation::deformPoints(out, map, cloud, prefix, control_points, short_stamps, values, 2,
+                                10.0);
+    } catch (const std::out_of_range&) {
+      thrown = true;
+    }
+    EXPECT_TRUE(thrown);
+  }
+  {  // indices->at() / cloud.at() past the cloud
+    pcl::PointCloud<Point> out = points;
+    std::vector<std::set<size_t>> map = sentinel;
+    const std::vector<size_t> bad_indices = {1, 2, 20};
+    bool thrown = false;
+    try {
+      deformation::deformPoints(out, map, cloud, prefix, control_points, control_point_stamps,
+                                values, 2, 10.0, &bad_indices);
+    } catch (const std::out_of_range&) {
+      thrown = true;
+    }
+    EXPECT_TRUE(thrown);
+  }
+  {  // a prefix the graph has never seen (deformation_graph.h:819-823): vertices as given
+    DeformationGraphMeshPath graph;
+    graph.addControlPoint('b', gtsam::Point3(0, 0, 0), 0);
+    pcl::PointCloud<pcl::PointXYZRGBA> verts, out;
+    for (size_t i = 0; i < 5; i++) verts.push_back(colored(static_cast<float>(i), 1, 2, 9, 8, 7));
+    out = verts;
+    const std::vector<Timestamp> five(5, 0);
+    graph.deformPoints(out, verts, five, 'c', values, 2, 10.0);
+    for (size_t i = 0; i < 5; i++) {
+      EXPECT_EQ(verts.points[i].x, out.points[i].x);
+      EXPECT_EQ(verts.points[i].rgba, out.points[i].rgba);
+    }
+  }
+}
+
 // No reference counterpart: a cloud large enough for the shim's threaded gather / scatter
 // (detail::parallelFor engages above 2^18 vertices).  deformPointsOnly must give the vertices
 // of deformPoints bit for bit, for the whole cloud and for an `indices` subset, and leave the
@@ -857,6 +960,7 @@ int main(int argc, char** argv) {
   }
   testDeformPoints();
   testDeformPointsWithTimeCheck();
+  testEarlyReturnsAndErrors();
   testLargeCloudStaging();
   testReconstructAndTranslate();
   testDeformMeshCube();
