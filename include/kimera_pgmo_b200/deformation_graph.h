@@ -213,26 +213,40 @@ class DeformationGraphMeshPath {
     const size_t n_v = traits::num_vertices(vertices);
     if (start_idx >= n_v) return;
     if (graph_indices.size() < n_v) throw std::out_of_range("graph_indices.at()");
-    std::vector<float> x(n_v), y(n_v), z(n_v), ox(n_v), oy(n_v), oz(n_v);
-    for (size_t i = start_idx; i < n_v; ++i) {
-      const traits::Pos p = traits::get_vertex(vertices, i);
-      x[i] = p.x();
-      y[i] = p.y();
-      z[i] = p.z();
-    }
-    std::vector<int32_t> gi(graph_indices.begin(), graph_indices.begin() + n_v);
-    std::vector<uint64_t> to_deform(n_v - start_idx);
+    // only [start_idx, n_v) is read or written (:786): that tail is what gets staged and shipped
+    static_assert(sizeof(int) == sizeof(int32_t), "graph_indices is passed as int32");
+    const size_t n = n_v - start_idx;
+    detail::PinnedBlock& stage = b.staging();
+    stage.reserve(6 * detail::PinnedBlock::padded(n * sizeof(float)) +
+                  detail::PinnedBlock::padded(n * sizeof(uint64_t)) + 256);
+    stage.rewind();
+    float* x = stage.take<float>(n);
+    float* y = stage.take<float>(n);
+    float* z = stage.take<float>(n);
+    float* ox = stage.take<float>(n);
+    float* oy = stage.take<float>(n);
+    float* oz = stage.take<float>(n);
+    uint64_t* to_deform = stage.take<uint64_t>(n);
+    detail::parallelFor(n, [&](size_t begin, size_t end) {
+      for (size_t i = begin; i < end; ++i) {
+        const traits::Pos p = traits::get_vertex(vertices, start_idx + i);
+        x[i] = p.x();
+        y[i] = p.y();
+        z[i] = p.z();
+      }
+    });
     uint64_t n_to = 0;
-    detail::throwOnError(pgmo_deform_predeform(b.get(), n_v, x.data(), y.data(), z.data(),
-                                               gi.data(), start_idx, ox.data(), oy.data(),
-                                               oz.data(), to_deform.data(), &n_to));
+    detail::throwOnError(pgmo_deform_predeform(
+        b.get(), n, x, y, z, reinterpret_cast<const int32_t*>(graph_indices.data()) + start_idx, 0,
+        ox, oy, oz, to_deform, &n_to));
+    indices_to_deform.reserve(indices_to_deform.size() + n_to);
     size_t next = 0;
-    for (size_t i = start_idx; i < n_v; ++i) {
+    for (size_t i = 0; i < n; ++i) {
       if (next < n_to && to_deform[next] == i) {
-        indices_to_deform.push_back(i);
+        indices_to_deform.push_back(start_idx + i);
         ++next;
       } else {
-        traits::set_vertex(new_vertices, i, traits::Pos(ox[i], oy[i], oz[i]));
+        traits::set_vertex(new_vertices, start_idx + i, traits::Pos(ox[i], oy[i], oz[i]));
       }
     }
   }

@@ -216,35 +216,38 @@ void run(Backend& backend, CloudOut& new_points,
   using kimera_pgmo_b200::detail::PinnedBlock;
   const size_t n_v = traits::num_vertices(points);
   const size_t n_pos = indices ? indices->size() : n_v;
+  // With `indices` the reference sweeps the listed vertices in the listed order and touches no
+  // other vertex (mesh_deformation.h:159-161): only those are gathered, in that order, and
+  // deformed as a cloud of their own — an incremental update of a few thousand vertices of a
+  // 10 M-vertex mesh moves a few thousand vertices across PCIe, not the mesh.
   PinnedBlock& stage = backend.staging();
-  stage.reserve(6 * PinnedBlock::padded(n_v * sizeof(float)) +
-                PinnedBlock::padded(stamped ? n_v * sizeof(uint64_t) : 0) +
+  stage.reserve(6 * PinnedBlock::padded(n_pos * sizeof(float)) +
+                PinnedBlock::padded(stamped ? n_pos * sizeof(uint64_t) : 0) +
                 PinnedBlock::padded(n_pos) + 256);
   stage.rewind();
-  float* x = stage.take<float>(n_v);
-  float* y = stage.take<float>(n_v);
-  float* z = stage.take<float>(n_v);
-  float* ox = stage.take<float>(n_v);  // only read back where `processed` is set
-  float* oy = stage.take<float>(n_v);
-  float* oz = stage.take<float>(n_v);
-  uint64_t* stamps = stamped ? stage.take<uint64_t>(n_v) : nullptr;
+  float* x = stage.take<float>(n_pos);
+  float* y = stage.take<float>(n_pos);
+  float* z = stage.take<float>(n_pos);
+  float* ox = stage.take<float>(n_pos);  // only read back where `processed` is set
+  float* oy = stage.take<float>(n_pos);
+  float* oz = stage.take<float>(n_pos);
+  uint64_t* stamps = stamped ? stage.take<uint64_t>(n_pos) : nullptr;
   uint8_t* processed = stage.take<uint8_t>(n_pos);
-  parallelFor(n_v, [&](size_t begin, size_t end) {
-    for (size_t i = begin; i < end; ++i) {
-      const traits::Pos p = traits::get_vertex(points, i);
-      x[i] = p.x();
-      y[i] = p.y();
-      z[i] = p.z();
-      if (stamped) stamps[i] = traits::get_timestamp(points, i);
+  parallelFor(n_pos, [&](size_t begin, size_t end) {
+    for (size_t p = begin; p < end; ++p) {
+      const size_t ii = indices ? (*indices)[p] : p;
+      if (ii >= n_v) throw std::out_of_range("pgmo_b200: vertex index past the cloud");  // .at()
+      const traits::Pos v = traits::get_vertex(points, ii);
+      x[p] = v.x();
+      y[p] = v.y();
+      z[p] = v.z();
+      if (stamped) stamps[p] = traits::get_timestamp(points, ii);
     }
   });
-  std::vector<uint64_t> subset;
-  if (indices) subset.assign(indices->begin(), indices->end());
   const uint32_t stride = static_cast<uint32_t>(k + 2 > 8 ? k + 2 : 8);
   std::vector<uint32_t> assoc(control_point_map ? n_pos * stride : 0);
   std::vector<uint8_t> cnt(control_point_map ? n_pos : 0);
-  int rc = pgmo_deform_points(backend.get(), n_v, x, y, z, stamps,
-                              indices ? subset.data() : nullptr, subset.size(),
+  int rc = pgmo_deform_points(backend.get(), n_pos, x, y, z, stamps, nullptr, 0,
                               static_cast<uint32_t>(k), tol_t, precision, ox, oy, oz, nullptr,
                               control_point_map ? assoc.data() : nullptr, stride,
                               control_point_map ? cnt.data() : nullptr, processed);
@@ -255,7 +258,7 @@ void run(Backend& backend, CloudOut& new_points,
       for (size_t p = begin; p < end; ++p) {
         if (!processed[p]) continue;  // skipped vertices stay as they are (:184-186)
         const size_t ii = indices ? (*indices)[p] : p;
-        traits::set_vertex(new_points, ii, traits::Pos(ox[ii], oy[ii], oz[ii]));
+        traits::set_vertex(new_points, ii, traits::Pos(ox[p], oy[p], oz[p]));
       }
     });
     return;
@@ -268,7 +271,7 @@ void run(Backend& backend, CloudOut& new_points,
     // neighbour counts above the stride only occur for degenerate k; the set is what callers use
     const uint32_t n = cnt[p] < stride ? cnt[p] : stride;
     for (uint32_t j = 0; j < n; ++j) control_point_map->back().insert(assoc[p * stride + j]);
-    traits::set_vertex(new_points, ii, traits::Pos(ox[ii], oy[ii], oz[ii]));
+    traits::set_vertex(new_points, ii, traits::Pos(ox[p], oy[p], oz[p]));
   }
 }
 
