@@ -11,13 +11,13 @@
 #include <cstring>
 #include <iostream>
 
-// SHIM_TEST_DEFORMATION_ONLY: the deformation tests alone, for the CPU suite's build against
-// tests/cpp/mock_deform_backend.cpp (host logic of the shim; see tests/test_shim.py)
-#ifndef SHIM_TEST_DEFORMATION_ONLY
+// SHIM_TEST_HOST_DOUBLE: the CPU suite's build against the oracle-backed test doubles
+// tests/cpp/mock_{deform,compression}_backend.cpp (host logic of the shim; see
+// tests/test_shim.py) — deformation, VoxelClearing, Octree and voxblox tests; DeltaCompression and
+// MeshFrontendInterface have no double and run on the GPU only.
 #include "kimera_pgmo_b200/compression.h"
-#endif
 #include "kimera_pgmo_b200/deformation_graph.h"
-#ifndef SHIM_TEST_DEFORMATION_ONLY
+#ifndef SHIM_TEST_HOST_DOUBLE
 #include "kimera_pgmo_b200/delta_compression.h"
 #include "kimera_pgmo_b200/mesh_frontend_interface.h"
 #endif
@@ -496,7 +496,6 @@ static void testIncrementalWithPredeform() {
   }
 }
 
-#ifndef SHIM_TEST_DEFORMATION_ONLY
 // ------------------------------------------------------ TestVoxelClearingCompression
 struct OrderedBlockMesh : MeshInterface {  // pgmo_fixtures.h:28-48
   BlockIndices order;
@@ -766,6 +765,7 @@ static void testVoxbloxInterface() {
   }
 }
 
+#ifndef SHIM_TEST_HOST_DOUBLE
 // ------------------------------------------------------ TestDeltaCompression (CompressionCorrect)
 // test_delta_compression.cpp:334-435: the two richest configurations, checked the way
 // ExpectedDelta::checkOutput does (:189-270) — through absolute point ids in the colour channel.
@@ -950,7 +950,7 @@ static void testMeshFrontend() {
   EXPECT_TRUE(view.mesh_to_graph != nullptr && view.span >= frontend.vertices()->size());
 }
 
-#endif  // SHIM_TEST_DEFORMATION_ONLY
+#endif  // SHIM_TEST_HOST_DOUBLE
 
 int main(int argc, char** argv) {
   const bool with_octree = argc > 1 && std::strcmp(argv[1], "--octree") == 0;
@@ -965,15 +965,13 @@ int main(int argc, char** argv) {
   testReconstructAndTranslate();
   testDeformMeshCube();
   testIncrementalWithPredeform();
-#ifndef SHIM_TEST_DEFORMATION_ONLY
   testVoxelClearing();
   testVoxbloxInterface();
+#ifndef SHIM_TEST_HOST_DOUBLE
   testDeltaCompression();
   testMeshFrontend();
-  if (with_octree) testOctreeCompression();
-#else
-  (void)with_octree;
 #endif
+  if (with_octree) testOctreeCompression();
   std::printf("shim tests: %d checks, %d failures\n", g_checks, g_failures);
   return g_failures ? 1 : 0;
 }

@@ -63,13 +63,14 @@ def test_shim_host_logic_against_oracle_backed_double():
     p = subprocess.run(["make", "-C", oracle_dir, "-j4"], capture_output=True, text=True)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
     p = subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-pthread",
-                        "-DSHIM_TEST_DEFORMATION_ONLY", "-I", os.path.join(ROOT, "include"),
+                        "-DSHIM_TEST_HOST_DOUBLE", "-I", os.path.join(ROOT, "include"),
                         "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_shim.cpp"),
                         os.path.join(ROOT, "tests", "cpp", "mock_deform_backend.cpp"),
+                        os.path.join(ROOT, "tests", "cpp", "mock_compression_backend.cpp"),
                         "-L", oracle_dir, "-loracle", f"-Wl,-rpath,{oracle_dir}"],
                        capture_output=True, text=True)
     assert p.returncode == 0, p.stderr[-3000:]
-    p = subprocess.run([exe], capture_output=True, text=True)
+    p = subprocess.run([exe, "--octree"], capture_output=True, text=True)
     assert p.returncode == 0, p.stdout + p.stderr
     assert " 0 failures" in p.stdout
     # page-locking refused (e.g. the locked-memory limit): the shim stages through pageable memory
