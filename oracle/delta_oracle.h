@@ -158,6 +158,12 @@ class DeltaCompression {
   size_t numActiveVertices() const { return vertices_map_.size(); }
   size_t numBlocks() const { return block_info_map_.size(); }
   size_t numPendingArchivedFaces() const { return archived_faces_.size(); }
+  // block_info_map_ in iteration (= insertion) order: f(index, info); what archiveBlocks'
+  // filter is shown (:323-331)
+  template <typename F>
+  void forEachBlock(F&& f) {
+    block_info_map_.forEach([&](const BlockIndex& idx, DeltaBlockInfo& info) { f(idx, info); });
+  }
 
  private:
   void addPoint(const PointXYZRGBA& point, uint64_t timestamp_ns, std::vector<size_t>& face_map,

@@ -156,6 +156,27 @@ void oracle_delta_archive_blocks(void* hv, uint32_t n_blocks, const int32_t* blo
   static_cast<DeltaHandle*>(hv)->comp.clearArchivedBlocks(blocks);
 }
 
+// block_info_map_ in iteration order: index, update_time_ns, sequence_number of up to `capacity`
+// blocks; returns how many there are
+uint64_t oracle_delta_blocks(void* hv, uint64_t capacity, int32_t* block_idx_xyz,
+                             uint64_t* update_time_ns, uint32_t* sequence_number) {
+  uint64_t n = 0;
+  static_cast<DeltaHandle*>(hv)->comp.forEachBlock(
+      [&](const BlockIndex& idx, const DeltaBlockInfo& info) {
+        if (n < capacity) {
+          if (block_idx_xyz) {
+            block_idx_xyz[3 * n] = idx.x;
+            block_idx_xyz[3 * n + 1] = idx.y;
+            block_idx_xyz[3 * n + 2] = idx.z;
+          }
+          if (update_time_ns) update_time_ns[n] = info.update_time_ns;
+          if (sequence_number) sequence_number[n] = info.sequence_number;
+        }
+        ++n;
+      });
+  return n;
+}
+
 // sizes12: vertex_start, face_start, n vertices, n archived vertices, n faces, n archived faces,
 // n prev_to_curr, n deleted, n observed, n new, active voxels, pending archived faces
 void oracle_delta_sizes(void* hv, uint64_t* s) {

@@ -13,14 +13,11 @@
 
 // SHIM_TEST_HOST_DOUBLE: the CPU suite's build against the oracle-backed test doubles
 // tests/cpp/mock_{deform,compression}_backend.cpp (host logic of the shim; see
-// tests/test_shim.py) — deformation, VoxelClearing, Octree and voxblox tests; DeltaCompression and
-// MeshFrontendInterface have no double and run on the GPU only.
+// tests/test_shim.py): every test of this file runs there too, without a GPU.
 #include "kimera_pgmo_b200/compression.h"
 #include "kimera_pgmo_b200/deformation_graph.h"
-#ifndef SHIM_TEST_HOST_DOUBLE
 #include "kimera_pgmo_b200/delta_compression.h"
 #include "kimera_pgmo_b200/mesh_frontend_interface.h"
-#endif
 
 using namespace kimera_pgmo_b200;
 
@@ -765,7 +762,6 @@ static void testVoxbloxInterface() {
   }
 }
 
-#ifndef SHIM_TEST_HOST_DOUBLE
 // ------------------------------------------------------ TestDeltaCompression (CompressionCorrect)
 // test_delta_compression.cpp:334-435: the two richest configurations, checked the way
 // ExpectedDelta::checkOutput does (:189-270) — through absolute point ids in the colour channel.
@@ -946,11 +942,12 @@ static void testMeshFrontend() {
     EXPECT_TRUE(same);
   }
   EXPECT_TRUE(expected.size() > 50);
+#ifndef SHIM_TEST_HOST_DOUBLE  // a device pointer: nothing the double can stand in for
   const auto view = frontend.meshToGraphDevice();
   EXPECT_TRUE(view.mesh_to_graph != nullptr && view.span >= frontend.vertices()->size());
+#endif
 }
 
-#endif  // SHIM_TEST_HOST_DOUBLE
 
 int main(int argc, char** argv) {
   const bool with_octree = argc > 1 && std::strcmp(argv[1], "--octree") == 0;
@@ -967,10 +964,8 @@ int main(int argc, char** argv) {
   testIncrementalWithPredeform();
   testVoxelClearing();
   testVoxbloxInterface();
-#ifndef SHIM_TEST_HOST_DOUBLE
   testDeltaCompression();
   testMeshFrontend();
-#endif
   if (with_octree) testOctreeCompression();
   std::printf("shim tests: %d checks, %d failures\n", g_checks, g_failures);
   return g_failures ? 1 : 0;

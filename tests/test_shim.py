@@ -52,11 +52,12 @@ def test_shim_host_side_helpers(capi):
 
 
 def test_shim_host_logic_against_oracle_backed_double():
-    """The deformation half of tests/cpp/test_shim.cpp (the reference's unit tests + the large
-    threaded-staging case) with tests/cpp/mock_deform_backend.cpp — a TEST DOUBLE of the C ABI on
-    top of the CPU oracle — linked instead of libpgmo_b200.so: checks the shim's host logic
-    (start index, cache, predeform scatter, staging, set rebuilding, early returns) without a
-    GPU.  The product library has no CPU path; the GPU suite runs the same file against it."""
+    """Every test of tests/cpp/test_shim.cpp (the reference's unit tests re-typed against the
+    shim + the large threaded-staging case) with tests/cpp/mock_{deform,compression}_backend.cpp
+    — TEST DOUBLES of the C ABI on top of the CPU oracle — linked instead of libpgmo_b200.so:
+    checks the shim's host logic (start index, cache, predeform scatter, staging, `remapping`
+    maintenance, MeshDelta reconstruction, block filters, getters) without a GPU.  The product
+    library has no CPU path; the GPU suite runs the same file against it."""
     exe = os.path.join(ROOT, "build", "tests", "test_shim_hostlogic")
     os.makedirs(os.path.dirname(exe), exist_ok=True)
     oracle_dir = os.path.join(ROOT, "oracle")
