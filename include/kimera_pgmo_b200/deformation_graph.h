@@ -108,10 +108,12 @@ class DeformationGraphMeshPath {
 
     deformation::Backend& b = backend(prefix);
     std::vector<size_t> to_deform;
+    bool controls_uploaded = false;
     if (start_idx != 0) {
       if (graph_indices) {
         b.setControls(prefix, vertex_positions_.at(prefix), &vertex_stamps_.at(prefix),
                       optimized_values);
+        controls_uploaded = true;
         predeformPoints(b, vertices, old_vertices, *graph_indices, to_deform, start_idx);
       } else {
         to_deform.resize(traits::num_vertices(vertices) - start_idx);
@@ -121,6 +123,10 @@ class DeformationGraphMeshPath {
 
     const std::vector<size_t>* indices_ptr = start_idx == 0 ? nullptr : &to_deform;
     std::vector<std::set<size_t>> vertex_graph_map_deformed;
+    // the table predeformPoints needed is the one deformation::deformPoints is about to upload
+    // (for a stamped cloud; an unstamped one uploads it without the stamps)
+    const deformation::Backend::KeepControls keep(
+        b, controls_uploaded && traits::has_get_stamp<CloudIn>::value);
     if (vertex_graph_map) {
       deformation::deformPoints(vertices, vertex_graph_map_deformed, old_vertices, prefix,
                                 vertex_positions_.at(prefix), vertex_stamps_.at(prefix),

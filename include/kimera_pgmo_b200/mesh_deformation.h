@@ -159,10 +159,29 @@ class Backend {
     return *staging_;
   }
 
+  // The next setControls is a repeat of the last one (DeformationGraph::deformPoints uploads the
+  // table for predeformPoints, then deformation::deformPoints would flatten and upload it again).
+  // Scoped: the flag is dropped when the guard goes, whether or not a setControls consumed it
+  // (deformPoints may return early or throw before it gets there).
+  class KeepControls {
+   public:
+    explicit KeepControls(Backend& b, bool keep) : b_(b) { b_.controls_kept_ = keep; }
+    ~KeepControls() { b_.controls_kept_ = false; }
+    KeepControls(const KeepControls&) = delete;
+    KeepControls& operator=(const KeepControls&) = delete;
+
+   private:
+    Backend& b_;
+  };
+
   // Uploads control positions / stamps and the flattened `values`.
   void setControls(char prefix, const std::vector<gtsam::Point3>& control_points,
                    const std::vector<Timestamp>* control_point_stamps,
                    const gtsam::Values& values) {
+    if (controls_kept_) {  // uploaded a moment ago by the same caller with the same arguments
+      controls_kept_ = false;
+      return;
+    }
     const size_t n_c = control_points.size();
     pos_.resize(3 * n_c);
     valid_.resize(n_c);
@@ -184,7 +203,7 @@ class Backend {
       poses_[12 * j + 11] = T.translation().z();
     }
     const uint64_t* stamps = nullptr;
-    if (control_point_stamps && control_point_stamps->size() == n_c) {
+    if (control_point_stamps && control_point_stamps->size() >= n_c) {  // .at(j), j < n_c
       stamps = control_point_stamps->data();
     }
     detail::throwOnError(pgmo_deform_set_controls(handle_.get(), n_c, pos_.data(), stamps,
@@ -194,6 +213,7 @@ class Backend {
  private:
   std::shared_ptr<pgmo_deform_t> handle_;
   std::shared_ptr<kimera_pgmo_b200::detail::PinnedBlock> staging_;
+  bool controls_kept_ = false;
   std::vector<double> pos_, poses_;
   std::vector<uint8_t> valid_;
 };

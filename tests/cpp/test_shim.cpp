@@ -491,6 +491,31 @@ static void testIncrementalWithPredeform() {
       EXPECT_TRUE(!vgm[i].empty());
     }
   }
+  // every new vertex tied to a graph node: nothing is left for deformation::deformPoints (its
+  // early return); the control table of the next solve must still reach the device
+  std::vector<int> all_tied;
+  for (size_t i = 0; i < 80; ++i) all_tied.push_back(int(i / 10));
+  graph.deformPoints(incr, verts, stamps, 'v', values, 2, 3.0, &all_tied);
+  gtsam::Values lifted;  // the same solve, every node 1 m higher
+  for (size_t j = 0; j < 8; ++j) {
+    lifted.insert(gtsam::Symbol('v', j),
+                  gtsam::Pose3(gtsam::Rot3::Rz(0.01 * j), gtsam::Point3(double(j), 0.1 * j, 1.0)));
+  }
+  graph.setRecalculateVertices(true);
+  pcl::PointCloud<pcl::PointXYZRGBA> after = verts;
+  graph.deformPoints(after, verts, stamps, 'v', lifted, 2, 3.0, &inds);
+  for (size_t i = 0; i < 80; ++i) {
+    EXPECT_NEAR(full.points[i].x, after.points[i].x, 1e-5);
+    EXPECT_NEAR(full.points[i].z + 1.0, after.points[i].z, 1e-5);
+  }
+  // and an incremental update right after it (table kept from predeformPoints to the knn call)
+  pcl::PointCloud<pcl::PointXYZRGBA> after_incr = verts;
+  graph.deformPoints(after_incr, verts, stamps, 'v', lifted, 2, 3.0, &inds);
+  for (size_t i = 0; i < 80; ++i) {
+    if (i >= 50 && inds[i] >= 0) continue;  // rigidly predeformed (checked above)
+    EXPECT_NEAR(after.points[i].x, after_incr.points[i].x, 1e-5);
+    EXPECT_NEAR(after.points[i].z, after_incr.points[i].z, 1e-5);
+  }
 }
 
 // ------------------------------------------------------ TestVoxelClearingCompression
