@@ -114,6 +114,20 @@ int pgmo_deform_set_search_mode(pgmo_deform_t* h, int mode);
 int pgmo_deform_set_profiling(pgmo_deform_t* h, int enabled);
 int pgmo_deform_last_timings(pgmo_deform_t* h, float* ms2, uint64_t* schedule_builds);
 
+/* Association cache.  interpPoint's neighbour set and weights (mesh_deformation.cpp:83-94) depend
+ * on the vertex, the control positions / stamps / validity and the window schedule, not on the
+ * poses.  The search leaves them in HBM (56 B per vertex at k = 4); a later call whose schedule is
+ * unchanged — the usual deformMesh after a new solve — runs the blend kernel alone, which checks a
+ * 64-bit fingerprint of every work item's vertex bits against the one the records were computed
+ * for and redoes the search for the items that fail it (on the device, stream-ordered).  Results
+ * are bit-identical either way.  enabled = 0: every call searches again (default: enabled). */
+int pgmo_deform_set_assoc_cache(pgmo_deform_t* h, int enabled);
+/* Diagnostics of the last pgmo_deform_run_device (waits for it): ms4 = [search kernel(s), tie
+ * resolver, blend kernel(s), all of them] (needs pgmo_deform_set_profiling), counts4 = [work items
+ * of the call, items whose records were rejected or missing, vertices that went through the tie
+ * resolver, 1 if the call started from cached records]. */
+int pgmo_deform_last_step_info(pgmo_deform_t* h, float* ms4, uint64_t* counts4);
+
 /* deformation::deformPoints, host buffers, whole job.
  *   x,y,z        n_v f32 each (SoA vertex stream)
  *   stamps_ns    n_v u64; NULL selects the unstamped overload (mesh_deformation.h:63-113)

@@ -52,6 +52,8 @@ SIGNATURES = {
     "pgmo_deform_set_search_mode": (C.c_int, [_vp, C.c_int]),
     "pgmo_deform_drop_schedule": (C.c_int, [_vp]),
     "pgmo_deform_last_timings": (C.c_int, [_vp, _vp, _u64p]),
+    "pgmo_deform_set_assoc_cache": (C.c_int, [_vp, C.c_int]),
+    "pgmo_deform_last_step_info": (C.c_int, [_vp, _vp, _vp]),
     "pgmo_deform_points": (C.c_int, [_vp, C.c_uint64, _vp, _vp, _vp, _vp, _vp, C.c_uint64,
                                      C.c_uint32, C.c_double, C.c_int, _vp, _vp, _vp, _vp, _vp,
                                      C.c_uint32, _vp, _vp]),
@@ -212,6 +214,18 @@ class DeformHandle:
 
     def set_profiling(self, enabled=True):
         _check(self._lib.pgmo_deform_set_profiling(self._h, 1 if enabled else 0))
+
+    def set_assoc_cache(self, enabled=True):
+        _check(self._lib.pgmo_deform_set_assoc_cache(self._h, 1 if enabled else 0))
+
+    def last_step_info(self):
+        """dict(search_ms, resolver_ms, blend_ms, total_ms, items, stale_items, resolved, warm)."""
+        ms = np.zeros(4, dtype=np.float32)
+        cnt = np.zeros(4, dtype=np.uint64)
+        _check(self._lib.pgmo_deform_last_step_info(self._h, _ptr(ms), _ptr(cnt)))
+        return dict(search_ms=float(ms[0]), resolver_ms=float(ms[1]), blend_ms=float(ms[2]),
+                    total_ms=float(ms[3]), items=int(cnt[0]), stale_items=int(cnt[1]),
+                    resolved=int(cnt[2]), warm=bool(cnt[3]))
 
     def last_timings(self):
         """(knn_blend_ms, resolver_ms, schedule_builds) of the last run_device."""

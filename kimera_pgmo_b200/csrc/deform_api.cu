@@ -28,6 +28,7 @@ struct pgmo_deform {
   DevBuf<uint8_t> d_valid;
   DevBuf<float4> d_ctrl_f4;
   DevBuf<float> d_pose_f32;
+  DevBuf<double> d_pose_rows;  // blend kernel rows: 16 doubles per control, chunk-swizzled
   DevBuf<int4> d_ctrl_key;
   DevBuf<int32_t> d_del_run, d_stable_key;
 
@@ -73,8 +74,23 @@ struct pgmo_deform {
 
   // optional kernel timing (bench / roofline): events on the launching stream
   bool profiling = false;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   bool ev_recorded = false;
+  bool last_run_warm = false;
+  uint32_t last_run_items = 0;
+
+  // association cache (deform_blend.cu): records + weights per local position of the slab the
+  // work items were cut for, fingerprints per work item.  Valid as long as the items are.
+  bool cache_enabled = true;   // false: every call redoes the search (records are scratch)
+  int n_sms = 148;
+  DevBuf<uint16_t> d_cache_rec;
+  DevBuf<unsigned char> d_cache_w;
+  DevBuf<unsigned long long> d_item_fp;
+  DevBuf<uint32_t> d_item_ok, d_stale_items, d_tie_slot;
+  uint64_t cache_items_first = ~0ull, cache_items_n = 0, cache_sched_builds = ~0ull;
+  int cache_precision = -1;
+  uint32_t cache_planes = 0, cache_w_planes = 0;
+  uint32_t cache_cold_lo = 0, cache_cold_hi = 0;  // work items searched since the last reset
 
   // work buffers
   DevBuf<ulonglong2> d_bounds;
@@ -196,8 +212,10 @@ int finishControls(pgmo_deform_t* h, bool positions_changed, cudaStream_t st) {
   PGMO_TRY(h->d_ctrl_f4.reserve(h->n_c + 1));
   PGMO_TRY(h->d_pose_f32.reserve(16 * h->n_c + 16));
   PGMO_TRY(h->d_ctrl_key.reserve(h->n_c + 1));
+  PGMO_TRY(h->d_pose_rows.reserve(16 * h->n_c + 16));
   PGMO_CUDA(launchBuildControlTables(h->n_c, h->d_pos.ptr, h->has_poses ? h->d_poses.ptr : nullptr,
-                                     h->d_ctrl_f4.ptr, h->d_pose_f32.ptr, positions_changed, st));
+                                     h->d_ctrl_f4.ptr, h->d_pose_f32.ptr, h->d_pose_rows.ptr,
+                                     positions_changed, st));
   if (positions_changed) {
     ++h->control_version;
     h->sched_ready = false;
@@ -334,6 +352,9 @@ int pgmo_deform_create(int device, pgmo_deform_t** out) {
     }
   }
   preloadDeformSortedKernels();
+  preloadDeformBlendKernels();
+  cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, device);
+  if (const char* e = std::getenv("PGMO_ASSOC_CACHE")) h->cache_enabled = atoi(e) != 0;
   *out = h;
   return PGMO_OK;
 }
@@ -652,6 +673,43 @@ static int ensureItems(pgmo_deform_t* h, uint64_t first_position, uint64_t n_loc
   return PGMO_OK;
 }
 
+// Association cache of the current work items: (re)allocates, and forgets every record when the
+// items, the precision or the record layout changed since they were written.
+static int prepareCache(pgmo_deform_t* h, int precision, cudaStream_t st, AssocCache* c) {
+  const uint64_t n_slots = h->items_n;
+  const uint32_t nb_max = std::max<uint32_t>(1u, std::min<uint32_t>(h->sched.max_k + 1, kCacheMaxNbr));
+  const uint32_t planes = nb_max > 7 ? 2 : 1;
+  const size_t w_size = precision == PGMO_PRECISION_FP64 ? sizeof(double) : sizeof(float);
+  const bool same = h->cache_items_first == h->items_first && h->cache_items_n == h->items_n &&
+                    h->cache_sched_builds == h->items_sched_builds && h->cache_precision == precision &&
+                    h->cache_planes == planes && h->cache_w_planes == nb_max;
+  PGMO_TRY(h->d_cache_rec.reserve(static_cast<size_t>(planes) * n_slots * 8 + 8));
+  PGMO_TRY(h->d_cache_w.reserve(static_cast<size_t>(nb_max) * n_slots * w_size + 16));
+  PGMO_TRY(h->d_item_fp.reserve(h->n_items + 1));
+  PGMO_TRY(h->d_item_ok.reserve(h->n_items + 1));
+  PGMO_TRY(h->d_stale_items.reserve(h->n_items + 1));
+  if (!same) {
+    PGMO_CUDA(cudaMemsetAsync(h->d_item_ok.ptr, 0, (h->n_items + 1) * sizeof(uint32_t), st));
+    h->cache_items_first = h->items_first;
+    h->cache_items_n = h->items_n;
+    h->cache_sched_builds = h->items_sched_builds;
+    h->cache_precision = precision;
+    h->cache_planes = planes;
+    h->cache_w_planes = nb_max;
+    h->cache_cold_lo = h->cache_cold_hi = 0;
+  }
+  c->rec = h->d_cache_rec.ptr;
+  c->weight = h->d_cache_w.ptr;
+  c->w_planes = nb_max;
+  c->n_slots = n_slots;
+  c->item_fp = h->d_item_fp.ptr;
+  c->item_ok = h->d_item_ok.ptr;
+  c->stale_items = h->d_stale_items.ptr;
+  c->pose_rows = precision == PGMO_PRECISION_FP64 ? static_cast<const void*>(h->d_pose_rows.ptr)
+                                                  : static_cast<const void*>(h->d_pose_f32.ptr);
+  return PGMO_OK;
+}
+
 static int runDeviceRange(pgmo_deform_t* h, uint64_t first_position, uint64_t n_local,
                            const float* d_x, const float* d_y, const float* d_z,
                            const uint64_t* d_subset_idx, int precision, float* d_out_x,
@@ -711,6 +769,8 @@ static int runDeviceRange(pgmo_deform_t* h, uint64_t first_position, uint64_t n_
   a.counters = h->d_counters.ptr;
   PGMO_TRY(h->d_tie_list.reserve(n_local));
   a.tie_list = h->d_tie_list.ptr;
+  PGMO_TRY(h->d_tie_slot.reserve(n_local));
+  a.tie_slot = h->d_tie_slot.ptr;
 
   ResolveArgs ra;
   ra.n_warps = resolverResidentWarps(h->device);
@@ -719,6 +779,8 @@ static int runDeviceRange(pgmo_deform_t* h, uint64_t first_position, uint64_t n_
   PGMO_TRY(h->d_scratch.reserve(static_cast<size_t>(ra.n_warps) * ra.cand_cap * 2));
   ra.scratch = h->d_scratch.ptr;
 
+  h->last_run_warm = false;
+  h->last_run_items = 0;
   if (h->profiling) PGMO_CUDA(cudaEventRecord(h->ev[0], st));
   if (h->use_grid) {
     PGMO_TRY(ensureItems(h, first_position, n_local, st));
@@ -730,7 +792,6 @@ static int runDeviceRange(pgmo_deform_t* h, uint64_t first_position, uint64_t n_
     ga.r_grow_mul = h->r_grow_mul;
     ga.r_grow_add = h->r_grow_add;
     ga.far_mul = h->far_mul;
-    if (h->profiling) PGMO_CUDA(cudaEventRecord(h->ev[0], st));
     // the requested range must start and end on work-item boundaries
     uint32_t i0 = 0, i1 = h->n_items;
     if (range_begin != 0 || range_end != n_local) {
@@ -740,24 +801,59 @@ static int runDeviceRange(pgmo_deform_t* h, uint64_t first_position, uint64_t n_
       i1 = static_cast<uint32_t>(std::lower_bound(it.begin(), it.end(), range_end,
                [](const WorkItem& w, uint64_t v) { return w.start < v; }) - it.begin());
     }
+    h->last_run_items = i1 - i0;
     if (h->grid_mode == 1) {
-      PGMO_CUDA(launchDeformKnnBlendSorted(a, ga, h->d_items.ptr + i0, i1 - i0, precision,
-                                           h->sched.max_k, h->sched_min_k, h->widest_window, st));
+      // K3a (search -> association records) -> K4 (ties) -> K3b (records + pose rows -> points).
+      // With records of an earlier call at hand K3b goes first and validates them; what it
+      // rejects is searched again.  Everything is stream-ordered: no host round trip.
+      AssocCache c;
+      PGMO_TRY(prepareCache(h, precision, st, &c));
+      const bool warm = h->cache_enabled && i0 >= h->cache_cold_lo && i1 <= h->cache_cold_hi && i1 > i0;
+      h->last_run_warm = warm;
+      const uint32_t max_k = h->sched.max_k, min_k = h->sched_min_k;
+      if (warm) {
+        PGMO_CUDA(launchDeformBlendCached(a, ga, c, h->d_items.ptr, i0, i1 - i0, precision, max_k, min_k,
+                                          h->widest_window, 1, h->n_sms, st));
+      }
+      if (h->profiling) PGMO_CUDA(cudaEventRecord(h->ev[1], st));
+      PGMO_CUDA(launchDeformSearchSorted(a, ga, c, h->d_items.ptr, i0, i1 - i0, precision, max_k, min_k,
+                                         h->widest_window, warm, h->n_sms, st));
       if (h->widest_window > static_cast<uint64_t>(kSortedMaxPoints)) {
         PGMO_CUDA(launchDeformKnnBlendGrid(a, ga, h->d_items.ptr + i0, i1 - i0, precision,
                                            h->sched.max_k, kSortedMaxPoints, st));
       }
+      if (h->profiling) PGMO_CUDA(cudaEventRecord(h->ev[2], st));
+      PGMO_CUDA(launchDeformResolve(a, ra, &c, precision, st));
+      if (h->profiling) PGMO_CUDA(cudaEventRecord(h->ev[3], st));
+      PGMO_CUDA(launchDeformBlendCached(a, ga, c, h->d_items.ptr, i0, i1 - i0, precision, max_k, min_k,
+                                        h->widest_window, warm ? 2 : 0, h->n_sms, st));
+      if (!warm) {  // the searched interval of work items (contiguous calls extend it)
+        if (h->cache_cold_hi > h->cache_cold_lo && i0 <= h->cache_cold_hi && i1 >= h->cache_cold_lo) {
+          h->cache_cold_lo = std::min(h->cache_cold_lo, i0);
+          h->cache_cold_hi = std::max(h->cache_cold_hi, i1);
+        } else {
+          h->cache_cold_lo = i0;
+          h->cache_cold_hi = i1;
+        }
+      }
     } else {
+      if (h->profiling) PGMO_CUDA(cudaEventRecord(h->ev[1], st));
       PGMO_CUDA(launchDeformKnnBlendGrid(a, ga, h->d_items.ptr + i0, i1 - i0, precision,
                                          h->sched.max_k, 0, st));
+      if (h->profiling) PGMO_CUDA(cudaEventRecord(h->ev[2], st));
+      PGMO_CUDA(launchDeformResolve(a, ra, nullptr, precision, st));
+      if (h->profiling) PGMO_CUDA(cudaEventRecord(h->ev[3], st));
     }
   } else {
+    if (h->profiling) PGMO_CUDA(cudaEventRecord(h->ev[1], st));
     PGMO_CUDA(launchDeformKnnBlend(a, precision, h->sched.max_k, st));
+    if (h->profiling) PGMO_CUDA(cudaEventRecord(h->ev[2], st));
+    PGMO_CUDA(launchDeformResolve(a, ra, nullptr, precision, st));
+    if (h->profiling) PGMO_CUDA(cudaEventRecord(h->ev[3], st));
   }
-  if (h->profiling) PGMO_CUDA(cudaEventRecord(h->ev[1], st));
-  PGMO_CUDA(launchDeformResolve(a, ra, precision, st));
+  PGMO_CUDA(launchDeformStepDone(h->d_counters.ptr, st));
   if (h->profiling) {
-    PGMO_CUDA(cudaEventRecord(h->ev[2], st));
+    PGMO_CUDA(cudaEventRecord(h->ev[4], st));
     h->ev_recorded = true;
   }
 
@@ -825,9 +921,51 @@ int pgmo_deform_last_timings(pgmo_deform_t* h, float* ms2, uint64_t* schedule_bu
   if (ms2) {
     ms2[0] = ms2[1] = 0.f;
     if (h->profiling && h->ev_recorded) {
-      PGMO_CUDA(cudaEventSynchronize(h->ev[2]));
-      PGMO_CUDA(cudaEventElapsedTime(&ms2[0], h->ev[0], h->ev[1]));
-      PGMO_CUDA(cudaEventElapsedTime(&ms2[1], h->ev[1], h->ev[2]));
+      float a = 0.f, b = 0.f, c = 0.f;
+      PGMO_CUDA(cudaEventSynchronize(h->ev[4]));
+      PGMO_CUDA(cudaEventElapsedTime(&a, h->ev[0], h->ev[2]));
+      PGMO_CUDA(cudaEventElapsedTime(&b, h->ev[2], h->ev[3]));
+      PGMO_CUDA(cudaEventElapsedTime(&c, h->ev[3], h->ev[4]));
+      ms2[0] = a + c;
+      ms2[1] = b;
+    }
+  }
+  return PGMO_OK;
+}
+
+int pgmo_deform_set_assoc_cache(pgmo_deform_t* h, int enabled) {
+  PGMO_CHECK_ARG(h != nullptr);
+  h->cache_enabled = enabled != 0;
+  return PGMO_OK;
+}
+
+int pgmo_deform_last_step_info(pgmo_deform_t* h, float* ms4, uint64_t* counts4) {
+  PGMO_CHECK_ARG(h != nullptr);
+  PGMO_TRY(ensureDevice(h->device));
+  if (ms4) {
+    ms4[0] = ms4[1] = ms4[2] = ms4[3] = 0.f;
+    if (h->profiling && h->ev_recorded) {
+      float validate = 0.f, blend = 0.f;
+      PGMO_CUDA(cudaEventSynchronize(h->ev[4]));
+      PGMO_CUDA(cudaEventElapsedTime(&validate, h->ev[0], h->ev[1]));
+      PGMO_CUDA(cudaEventElapsedTime(&ms4[0], h->ev[1], h->ev[2]));
+      PGMO_CUDA(cudaEventElapsedTime(&ms4[1], h->ev[2], h->ev[3]));
+      PGMO_CUDA(cudaEventElapsedTime(&blend, h->ev[3], h->ev[4]));
+      PGMO_CUDA(cudaEventElapsedTime(&ms4[3], h->ev[0], h->ev[4]));
+      ms4[2] = validate + blend;
+    }
+  }
+  if (counts4) {
+    counts4[0] = h->last_run_items;
+    counts4[1] = counts4[2] = 0;
+    counts4[3] = h->last_run_warm ? 1 : 0;
+    if (h->d_counters.ptr) {
+      PGMO_TRY(h->h_counters.reserve(8));
+      PGMO_CUDA(cudaMemcpyAsync(h->h_counters.ptr, h->d_counters.ptr, 4 * sizeof(unsigned long long),
+                                cudaMemcpyDeviceToHost, h->stream));
+      PGMO_CUDA(cudaStreamSynchronize(h->stream));
+      counts4[1] = h->h_counters.ptr[2];
+      counts4[2] = h->h_counters.ptr[0];
     }
   }
   return PGMO_OK;

@@ -16,11 +16,67 @@ __device__ __forceinline__ float dist2Exact(float ax, float ay, float az, float 
   return __fadd_rn(__fmul_rn(dx, dx), __fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dz, dz)));
 }
 
-// hands local position p to the PCL-order resolver (K4)
-__device__ __forceinline__ void sendToResolver(const DeformArgs& a, uint64_t p) {
+// hands local position p to the PCL-order resolver (K4); slot = where its association record
+// lives (kNoCacheSlot: the vertex has none, the resolver's own blend is final)
+__device__ __forceinline__ void sendToResolver(const DeformArgs& a, uint64_t p,
+                                               uint32_t slot = kNoCacheSlot) {
   a.status[p] = kStatusNeedsTie;
   const unsigned long long at = atomicAdd(a.counters, 1ull);
   a.tie_list[at] = static_cast<uint32_t>(p);
+  a.tie_slot[at] = slot;
+}
+
+// interpPoint's weights (mesh_deformation.cpp:85-94) for neighbour j of n, distances ascending:
+// d_max = double(sqrtf(d2[n-1])); 1 if sqrtf(d2[0]) == d_max or d_max == 0, else
+// 1 - double(sqrtf(d2[j])) / d_max.
+__device__ __forceinline__ double weightFp64(float d2_j, float d_max_f, bool const_w) {
+  return const_w ? 1.0
+                 : __dsub_rn(1.0, __ddiv_rn(static_cast<double>(__fsqrt_rn(d2_j)),
+                                            static_cast<double>(d_max_f)));
+}
+__device__ __forceinline__ bool constWeight(float d2_first, float d_max_f) {
+  return (__fsqrt_rn(d2_first) == d_max_f) || d_max_f == 0.0f;
+}
+// FP32 mode: same formula in float with a reciprocal (no FMA: the cached value must not depend
+// on the kernel it was computed in)
+__device__ __forceinline__ float weightFp32(float d2_j, float inv_dmax, bool const_w) {
+  return const_w ? 1.0f : __fsub_rn(1.0f, __fmul_rn(__fsqrt_rn(d2_j), inv_dmax));
+}
+
+// Fingerprint of a work item's vertices: the wrapping sum over its vertices of a 64-bit mix of
+// the coordinate bits, the offset inside the item and (with an indices list) the vertex index.
+// The association records of an item are valid for exactly the vertex bits they were computed
+// from; K3b recomputes the sum from the vertices it is given and compares.
+__device__ __forceinline__ unsigned long long vertexFingerprint(float x, float y, float z,
+                                                                uint32_t offset, uint64_t index) {
+  unsigned long long m = (static_cast<unsigned long long>(__float_as_uint(y)) << 32) | __float_as_uint(x);
+  m = (m + 0x9e3779b97f4a7c15ull * (offset + 1u)) * 0xbf58476d1ce4e5b9ull;
+  m ^= m >> 29;
+  m = (m ^ __float_as_uint(z) ^ (index * 0x2545f4914f6cdd1dull)) * 0x94d049bb133111ebull;
+  m ^= m >> 32;
+  return m;
+}
+__device__ __forceinline__ unsigned long long warpSumU64(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+  return v;
+}
+
+// can the vertices of a run {lo, hi, k, skip} have association records?  (neighbour count and
+// the 16-bit relative control index of the record layout)
+__device__ __forceinline__ bool runCacheable(const uint4& info) {
+  return static_cast<int>(info.z) + 1 <= kCacheMaxNbr && info.y - info.x <= 65536u;
+}
+
+// record slot `slot` of the association cache: neighbour j's control index relative to run.lo
+__device__ __forceinline__ void cacheStoreNbr(const AssocCache& c, uint64_t slot, int j, uint32_t rel) {
+  const uint64_t plane = j < 7 ? 0 : 1;
+  c.rec[(plane * c.n_slots + slot) * 8 + (j < 7 ? 1 + j : j - 7)] = static_cast<uint16_t>(rel);
+}
+__device__ __forceinline__ void cacheStoreWeight(const AssocCache& c, uint64_t slot, int j, int precision,
+                                                 double w64, float w32) {
+  if (precision == 0) static_cast<double*>(c.weight)[static_cast<uint64_t>(j) * c.n_slots + slot] = w64;
+  else static_cast<float*>(c.weight)[static_cast<uint64_t>(j) * c.n_slots + slot] = w32;
 }
 
 __device__ __forceinline__ uint32_t findRun(const uint64_t* __restrict__ run_start,

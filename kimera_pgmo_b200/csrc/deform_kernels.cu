@@ -122,7 +122,8 @@ deformKnnBlendKernel(const DeformArgs a, const int precision) {
 // ------------------------------------------------------------------------------------------
 // K4 kernel: one flagged vertex per warp (resolveOne: deform_resolve.cuh)
 __global__ void __launch_bounds__(kResolveWarpsPerBlock * 32)
-deformResolveKernel(const DeformArgs a, const ResolveArgs ra, const int precision) {
+deformResolveKernel(const DeformArgs a, const ResolveArgs ra, const AssocCache cache,
+                    const int use_cache, const int precision) {
   __shared__ DfsLevel s_levels[kResolveWarpsPerBlock][kResolverMaxDepth + 1];
   __shared__ ResolveStage s_stage[kResolveWarpsPerBlock];
   const int lane = threadIdx.x & 31;
@@ -134,12 +135,15 @@ deformResolveKernel(const DeformArgs a, const ResolveArgs ra, const int precisio
   const unsigned long long begin = a.counters[1], end = a.counters[0];
   for (unsigned long long i = begin + warp; i < end; i += ra.n_warps) {
     resolveOne(a, ra, s_levels[warp_in_block], s_stage[warp_in_block], cand, a.tie_list[i], precision,
-               lane);
+               lane, use_cache ? &cache : nullptr, a.tie_slot[i]);
   }
 }
 
-__global__ void deformResolveDoneKernel(unsigned long long* counters) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) counters[1] = counters[0];
+__global__ void deformStepDoneKernel(unsigned long long* counters) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    counters[1] = counters[0];
+    counters[3] = counters[2];
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -177,7 +181,8 @@ __global__ void predeformKernel(uint64_t n_v, uint64_t start_idx, const float* _
 __global__ void buildControlTablesKernel(uint64_t n_c, const double* __restrict__ ctrl_pos,
                                          const double* __restrict__ poses,
                                          float4* __restrict__ ctrl_f4,
-                                         float* __restrict__ pose_f32, int positions_changed) {
+                                         float* __restrict__ pose_f32,
+                                         double* __restrict__ pose_rows64, int positions_changed) {
   const uint64_t j = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (j >= n_c) return;
   const double gx = ctrl_pos[3 * j], gy = ctrl_pos[3 * j + 1], gz = ctrl_pos[3 * j + 2];
@@ -192,6 +197,19 @@ __global__ void buildControlTablesKernel(uint64_t n_c, const double* __restrict_
   o[13] = __double2float_rn(gy);
   o[14] = __double2float_rn(gz);
   o[15] = 0.f;
+  if (pose_rows64) {
+    // blend-kernel row: R(9) t(3) g(3) pad as eight 16-byte chunks, chunk c stored at c ^ (j & 7)
+    // so that lanes reading the same chunk of different rows spread over the shared-memory banks
+    double row[16];
+    for (int i = 0; i < 12; ++i) row[i] = poses ? poses[12 * j + i] : 0.0;
+    row[12] = gx;
+    row[13] = gy;
+    row[14] = gz;
+    row[15] = 0.0;
+    double2* dst = reinterpret_cast<double2*>(pose_rows64 + 16 * j);
+    const int sw = static_cast<int>(j & 7);
+    for (int c = 0; c < 8; ++c) dst[c ^ sw] = make_double2(row[2 * c], row[2 * c + 1]);
+  }
 }
 
 __global__ void applyScheduleKernel(uint64_t n_c, const int32_t* __restrict__ del_run,
@@ -265,12 +283,17 @@ uint32_t resolverResidentWarps(int device) {
   return static_cast<uint32_t>(sms) * 4 * kResolveWarpsPerBlock;
 }
 
-cudaError_t launchDeformResolve(const DeformArgs& args, const ResolveArgs& rargs, int precision,
-                                cudaStream_t stream) {
+cudaError_t launchDeformResolve(const DeformArgs& args, const ResolveArgs& rargs,
+                                const AssocCache* cache, int precision, cudaStream_t stream) {
   if (args.n_local == 0) return cudaSuccess;
   const unsigned blocks = rargs.n_warps / kResolveWarpsPerBlock;
-  deformResolveKernel<<<blocks, kResolveWarpsPerBlock * 32, 0, stream>>>(args, rargs, precision);
-  deformResolveDoneKernel<<<1, 32, 0, stream>>>(args.counters);
+  deformResolveKernel<<<blocks, kResolveWarpsPerBlock * 32, 0, stream>>>(
+      args, rargs, cache ? *cache : AssocCache{}, cache ? 1 : 0, precision);
+  return cudaGetLastError();
+}
+
+cudaError_t launchDeformStepDone(unsigned long long* counters, cudaStream_t stream) {
+  deformStepDoneKernel<<<1, 32, 0, stream>>>(counters);
   return cudaGetLastError();
 }
 
@@ -288,12 +311,12 @@ cudaError_t launchPredeform(uint64_t n_v, uint64_t start_idx, const float* x, co
 }
 
 cudaError_t launchBuildControlTables(uint64_t n_c, const double* ctrl_pos, const double* poses,
-                                     float4* ctrl_f4, float* ctrl_pose_f32, bool positions_changed,
-                                     cudaStream_t stream) {
+                                     float4* ctrl_f4, float* ctrl_pose_f32, double* pose_rows64,
+                                     bool positions_changed, cudaStream_t stream) {
   if (n_c == 0) return cudaSuccess;
   const unsigned threads = 256;
   buildControlTablesKernel<<<static_cast<unsigned>((n_c + threads - 1) / threads), threads, 0,
-                             stream>>>(n_c, ctrl_pos, poses, ctrl_f4, ctrl_pose_f32,
+                             stream>>>(n_c, ctrl_pos, poses, ctrl_f4, ctrl_pose_f32, pose_rows64,
                                        positions_changed ? 1 : 0);
   return cudaGetLastError();
 }

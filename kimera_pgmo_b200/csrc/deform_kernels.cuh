@@ -49,8 +49,36 @@ struct DeformArgs {
   uint32_t assoc_stride;
   uint8_t* assoc_cnt;         // or null
   uint8_t* status;            // per position (always present)
-  unsigned long long* counters;  // [0] = vertices sent to the resolver, [1] = already resolved
+  unsigned long long* counters;  // [0] = vertices sent to the resolver, [1] = already resolved,
+                                 // [2] = work items found stale by the validating blend pass,
+                                 // [3] = stale items already redone
   uint32_t* tie_list;            // local positions sent to the resolver (capacity n_local)
+  uint32_t* tie_slot;            // their slot in the association cache (kNoCacheSlot: none)
+};
+
+// ------------------------------------------------------------------------------------------
+// Association cache (deform_blend.cu).  interpPoint's neighbour set and weights
+// (kimera_pgmo/src/mesh_deformation.cpp:83-94) depend on the vertex, the control positions /
+// stamps / validity and the window schedule - not on the poses.  The search kernel (K3a) leaves
+// them in HBM, one record per local position in the order the search grouped the vertices, and
+// the blend kernel (K3b) turns records + pose rows into deformed points.  After a new solve
+// (poses only) K3b alone runs: it re-reads the vertices, checks a 64-bit fingerprint of the
+// item's vertex bits against the one the records were computed for and redoes the search only
+// for items that fail it.
+constexpr uint32_t kNoCacheSlot = 0xFFFFFFFFu;
+constexpr int kCacheMaxNbr = 14;  // blended neighbours a record can hold (k <= 13)
+struct AssocCache {
+  // plane 0: {vertex offset inside the item, nbr 0..6}, plane 1: {nbr 7..14}; nbr = control
+  // index - run.lo; slot = local position of the record (item start + rank in search order)
+  uint16_t* rec;       // planes x n_slots x 8
+  void* weight;        // w_planes x n_slots, double (FP64 mode) or float (FP32 mode)
+  uint32_t w_planes;   // neighbours a record holds weights for (>= max_k + 1)
+  uint64_t n_slots;    // = n_local of the slab the cache belongs to
+  unsigned long long* item_fp;  // per work item: fingerprint of the vertex bits
+  uint32_t* item_ok;   // per work item: 1 = records valid for item_fp
+  uint32_t* stale_items;  // work items the validating pass rejected (capacity: all items)
+  const void* pose_rows;  // n_c rows: 16 doubles (128 B, 16-byte chunk c stored at c ^ (j & 7))
+                          // or 16 floats (FP32 mode): R(9) t(3) g(3) pad
 };
 
 // per-run uniform grid over the run's alive control points (deform_grid.cu)
@@ -131,9 +159,29 @@ cudaError_t launchDeformKnnBlendSorted(const DeformArgs& args, const GridArgs& g
 // forces the lazy loading of the default K3 kernels (handle creation)
 void preloadDeformSortedKernels();
 
+// K3a on the cache: as launchDeformKnnBlendSorted, but instead of blending the kernel writes the
+// association records.  from_stale_list: a persistent grid walks cache.stale_items
+// [counters[3], counters[2]) instead of `items` (the items are then indexed through it).
+cudaError_t launchDeformSearchSorted(const DeformArgs& args, const GridArgs& gargs,
+                                     const AssocCache& cache, const WorkItem* items,
+                                     uint32_t first_item, uint32_t n_items, int precision,
+                                     uint32_t max_k, uint32_t min_k, uint64_t widest_window,
+                                     bool from_stale_list, int n_sms, cudaStream_t stream);
+// K3b: blend from the association records.  mode 0 = items [first_item, first_item + n_items),
+// records trusted; 1 = same items, records validated against the vertices (stale items are
+// appended to cache.stale_items and left untouched); 2 = persistent grid over the stale list.
+cudaError_t launchDeformBlendCached(const DeformArgs& args, const GridArgs& gargs,
+                                    const AssocCache& cache, const WorkItem* items,
+                                    uint32_t first_item, uint32_t n_items, int precision,
+                                    uint32_t max_k, uint32_t min_k, uint64_t widest_window,
+                                    int mode, int n_sms, cudaStream_t stream);
+void preloadDeformBlendKernels();
+// counters[1] = counters[0]; counters[3] = counters[2]
+cudaError_t launchDeformStepDone(unsigned long long* counters, cudaStream_t stream);
+
 // K4: PCL-order resolution of the vertices flagged kStatusNeedsTie.
-cudaError_t launchDeformResolve(const DeformArgs& args, const ResolveArgs& rargs, int precision,
-                                cudaStream_t stream);
+cudaError_t launchDeformResolve(const DeformArgs& args, const ResolveArgs& rargs,
+                                const AssocCache* cache, int precision, cudaStream_t stream);
 uint32_t resolverResidentWarps(int device);
 
 // K5: rigid predeform by graph index.
@@ -158,10 +206,11 @@ cudaError_t launchPredeform(uint64_t n_v, uint64_t start_idx, const float* x, co
                             float* oz, uint8_t* needs_deform, int* out_of_range,
                             cudaStream_t stream);
 
-// builds ctrl_f4 (only when positions changed) / ctrl_pose_f32 from the f64 tables
+// builds ctrl_f4 (only when positions changed) / ctrl_pose_f32 / the chunk-swizzled f64 pose
+// rows of the blend kernel from the f64 tables
 cudaError_t launchBuildControlTables(uint64_t n_c, const double* ctrl_pos, const double* poses,
-                                     float4* ctrl_f4, float* ctrl_pose_f32, bool positions_changed,
-                                     cudaStream_t stream);
+                                     float4* ctrl_f4, float* ctrl_pose_f32, double* pose_rows64,
+                                     bool positions_changed, cudaStream_t stream);
 // writes del_run into ctrl_f4[].w and the stable keys (after build_schedule)
 cudaError_t launchApplySchedule(uint64_t n_c, const int32_t* del_run, const int32_t* stable_key3,
                                 float4* ctrl_f4, int4* ctrl_key, cudaStream_t stream);

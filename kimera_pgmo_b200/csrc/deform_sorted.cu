@@ -1,4 +1,4 @@
-// K3, bucket-ordered candidate lists (sm_100a): the main knn + blend kernel.
+// K3a, bucket-ordered candidate lists (sm_100a): the main knn kernel.
 //
 // deformation::interpPoint (kimera_pgmo/src/mesh_deformation.cpp:73-106) needs, per vertex, the
 // K = k + 2 nearest alive control points in ascending float-d^2 order.  The profile of the
@@ -25,14 +25,16 @@
 //     they are re-ordered on their exact d^2 in registers; exact ties (and near ties that
 //     touch the last tracked slot) are handed to the PCL-order resolver (K4), which is exact.
 //
-//   * The pose table rows of the run's alive points (R, t, g: 15 doubles, or floats in FP32
-//     mode) are staged in shared memory as SoA when the alive set has <= 256 points, so that
-//     the blend's 75 gathered loads per vertex are conflict-free LDS instead of L2 round trips
-//     (profiles/r01e: the gathers were 1/3 of all stall samples and most of the LSU traffic).
+//   * The kernel does not blend.  Neighbour set and weights depend on the vertex, the control
+//     positions and the schedule, not on the poses: each vertex leaves an association record
+//     (AssocCache, deform_kernels.cuh: vertex offset, k + 1 control indices relative to run.lo,
+//     k + 1 weights) in HBM, in the order the search grouped the vertices, and the blend kernel
+//     (deform_blend.cu, K3b) turns records + pose rows into points — after every search, and
+//     alone when only the poses changed since.
 //
-// The result is bit-identical to the brute-force and grid-walk kernels (tests/test_deform_gpu.py
-// ::test_search_modes_agree).  Runs with more than kSMaxPts alive points stay on the grid-walk
-// kernel (deform_grid.cu).
+// Search + blend are bit-identical to the brute-force and grid-walk kernels
+// (tests/test_deform_gpu.py::test_search_modes_agree).  Runs with more than kSMaxPts alive
+// points stay on the grid-walk kernel (deform_grid.cu), which blends by itself.
 #include <cfloat>
 #include <type_traits>
 
@@ -55,22 +57,12 @@ constexpr int kSlabShift = PGMO_SLAB_SHIFT;  // vertices per slab (first split a
 constexpr int kSlab = 1 << kSlabShift;
 constexpr int kSVBins = kSMaxCells / (kSChunk / kSlab);  // bins along the second axis inside a slab
 static_assert((kSChunk / kSlab) * kSVBins <= kSMaxCells, "slab x bin keys");
-#ifndef PGMO_STAGED_MAX
-#define PGMO_STAGED_MAX 256
-#endif
 #ifndef PGMO_K3_CTAS
-#define PGMO_K3_CTAS 3
+#define PGMO_K3_CTAS 4
 #endif
-constexpr int kStagedMaxPts = PGMO_STAGED_MAX;  // alive-set size up to which the pose rows are staged
+constexpr int kSmallMaxPts = 256;  // alive sets up to here use the leaner variant
 
-// pose rows of the alive points, SoA: component c of slot s at row[c][s]
-template <typename T, int MAXPTS>
-struct PoseRows {
-  T row[15][MAXPTS];  // R0..R8, t0..t2, g0..g2
-};
-struct NoPoseRows {};
-
-template <int MAXPTS, typename POSE>
+template <int MAXPTS>
 struct SortedSmem {
   float4 pts[MAXPTS + 4];                   // alive control points: x, y, z, index (int bits);
                                             // pts[n_alive] = a point at infinity (list padding)
@@ -91,8 +83,16 @@ struct SortedSmem {
   float red[6][kSWarps];
   uint32_t warp_tot[kSWarps];
   float grid[8];                            // split axes: origin and 1 / bin width, axis ids
-  alignas(16) POSE pose;
+  unsigned long long fp_w[kSWarps];         // per warp: fingerprint of its vertices' bits
 };
+
+template <typename Smem>
+__device__ __forceinline__ unsigned long long itemFingerprint(const Smem& S) {
+  unsigned long long f = 0ull;
+#pragma unroll
+  for (int w = 0; w < kSWarps; ++w) f += S.fp_w[w];
+  return f;
+}
 
 // Inserts two keys into the ascending list at once.  The i-th smallest of the union of two
 // ascending sequences b and (lo, hi) is min(b[i], max(b[i-1], lo), max(b[i-2], hi)): per slot two
@@ -137,135 +137,51 @@ __device__ __forceinline__ float warpMaxF(float v) {
   return r;
 }
 
-// interpPoint's blend with the pose rows read from shared memory (same arithmetic, operation
-// for operation, as dev::writeResultReg).  nbr_slot: slots of the neighbours in S.pts / S.pose.
-template <int KCAP, int PREC, typename Smem>
-__device__ __forceinline__ void writeResultStaged(const DeformArgs& a, const Smem& S, uint64_t p,
-                                                  uint64_t ii, float qx, float qy, float qz,
-                                                  const float (&nbr_d2)[KCAP],
-                                                  const int (&nbr_slot)[KCAP], int n) {
-  float last_d2 = nbr_d2[0];
-#pragma unroll
-  for (int j = 1; j < KCAP; ++j) last_d2 = j < n ? fmaxf(last_d2, nbr_d2[j]) : last_d2;
-  if constexpr (PREC == 0) {
-    const float d_max_f = __fsqrt_rn(last_d2);
-    const double d_max = static_cast<double>(d_max_f);
-    const bool const_w = (__fsqrt_rn(nbr_d2[0]) == d_max_f) || d_max == 0.0;
-    double wsum = 0.0, acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
-    const double v0 = static_cast<double>(qx), v1 = static_cast<double>(qy),
-                 v2 = static_cast<double>(qz);
-#pragma unroll
-    for (int j = 0; j < KCAP; ++j) {
-      if (j < n - 1) {
-        const int s = nbr_slot[j];
-        const double w =
-            const_w ? 1.0
-                    : __dsub_rn(1.0, __ddiv_rn(static_cast<double>(__fsqrt_rn(nbr_d2[j])), d_max));
-        wsum = __dadd_rn(wsum, w);
-        const double p0 = __dsub_rn(v0, S.pose.row[12][s]);
-        const double p1 = __dsub_rn(v1, S.pose.row[13][s]);
-        const double p2 = __dsub_rn(v2, S.pose.row[14][s]);
-        const double r0 = __dadd_rn(__dadd_rn(__dmul_rn(S.pose.row[0][s], p0), __dmul_rn(S.pose.row[1][s], p1)), __dmul_rn(S.pose.row[2][s], p2));
-        const double r1 = __dadd_rn(__dadd_rn(__dmul_rn(S.pose.row[3][s], p0), __dmul_rn(S.pose.row[4][s], p1)), __dmul_rn(S.pose.row[5][s], p2));
-        const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(S.pose.row[6][s], p0), __dmul_rn(S.pose.row[7][s], p1)), __dmul_rn(S.pose.row[8][s], p2));
-        acc0 = __dadd_rn(acc0, __dmul_rn(w, __dadd_rn(r0, S.pose.row[9][s])));
-        acc1 = __dadd_rn(acc1, __dmul_rn(w, __dadd_rn(r1, S.pose.row[10][s])));
-        acc2 = __dadd_rn(acc2, __dmul_rn(w, __dadd_rn(r2, S.pose.row[11][s])));
-      }
-    }
-    const double o0 = __ddiv_rn(acc0, wsum), o1 = __ddiv_rn(acc1, wsum), o2 = __ddiv_rn(acc2, wsum);
-    a.ox[ii] = __double2float_rn(o0);
-    a.oy[ii] = __double2float_rn(o1);
-    a.oz[ii] = __double2float_rn(o2);
-    if (a.of64) {
-      a.of64[3 * p + 0] = o0;
-      a.of64[3 * p + 1] = o1;
-      a.of64[3 * p + 2] = o2;
-    }
-  } else {
-    const float d_max = __fsqrt_rn(last_d2);
-    const bool const_w = (__fsqrt_rn(nbr_d2[0]) == d_max) || d_max == 0.0f;
-    const float inv_dmax = const_w ? 0.0f : __frcp_rn(d_max);
-    float wsum = 0.f, acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
-#pragma unroll
-    for (int j = 0; j < KCAP; ++j) {
-      if (j < n - 1) {
-        const int s = nbr_slot[j];
-        const float w = const_w ? 1.0f : 1.0f - __fsqrt_rn(nbr_d2[j]) * inv_dmax;
-        wsum += w;
-        const float p0 = qx - S.pose.row[12][s], p1 = qy - S.pose.row[13][s],
-                    p2 = qz - S.pose.row[14][s];
-        acc0 += w * (S.pose.row[0][s] * p0 + S.pose.row[1][s] * p1 + S.pose.row[2][s] * p2 + S.pose.row[9][s]);
-        acc1 += w * (S.pose.row[3][s] * p0 + S.pose.row[4][s] * p1 + S.pose.row[5][s] * p2 + S.pose.row[10][s]);
-        acc2 += w * (S.pose.row[6][s] * p0 + S.pose.row[7][s] * p1 + S.pose.row[8][s] * p2 + S.pose.row[11][s]);
-      }
-    }
-    const float o0 = acc0 / wsum, o1 = acc1 / wsum, o2 = acc2 / wsum;
-    a.ox[ii] = o0;
-    a.oy[ii] = o1;
-    a.oz[ii] = o2;
-    if (a.of64) {
-      a.of64[3 * p + 0] = o0;
-      a.of64[3 * p + 1] = o1;
-      a.of64[3 * p + 2] = o2;
-    }
-  }
-  if (a.assoc) {
-#pragma unroll
-    for (int j = 0; j < KCAP; ++j) {
-      if (static_cast<uint32_t>(j) < a.assoc_stride) {
-        a.assoc[p * a.assoc_stride + j] =
-            (j < n - 1) ? static_cast<uint32_t>(__float_as_int(S.pts[nbr_slot[j]].w)) : 0xFFFFFFFFu;
-      }
-    }
-    for (uint32_t j = KCAP; j < a.assoc_stride; ++j) a.assoc[p * a.assoc_stride + j] = 0xFFFFFFFFu;
-  }
-  if (a.assoc_cnt) a.assoc_cnt[p] = static_cast<uint8_t>(n - 1 > 255 ? 255 : n - 1);
-}
-
-template <int PREC, int MAXPTS, bool STAGE>
-struct SmemOf {
-  using Pose = typename std::conditional<
-      STAGE, typename std::conditional<PREC == 0, PoseRows<double, MAXPTS>, PoseRows<float, MAXPTS>>::type,
-      NoPoseRows>::type;
-  using type = SortedSmem<MAXPTS, Pose>;
-};
-
 // FULL: every vertex blends exactly KCAP - 2 neighbours (k + 1 with KCAP = k + 3) — the caller
 // asked for one k (no mid-sweep change) and the item's alive set holds at least KCAP points.  The
 // neighbour counts are then compile-time constants and every per-slot guard disappears; items
 // that do not qualify (a handful of vertices at the start of a trajectory) go to the resolver.
-template <int KCAP, int PREC, int MAXPTS, bool STAGE, bool FULL>
-__global__ void __launch_bounds__(kSThreads, STAGE ? PGMO_K3_CTAS : 4)
-deformKnnBlendSortedKernel(const DeformArgs a, const GridArgs ga,
-                           const WorkItem* __restrict__ items) {
-  using Smem = typename SmemOf<PREC, MAXPTS, STAGE>::type;
+template <int KCAP, int PREC, int MAXPTS, bool FULL>
+__device__ __forceinline__ void searchItem(const DeformArgs& a, const GridArgs& ga,
+                                           const AssocCache& cache, const WorkItem& item,
+                                           uint32_t item_index, SortedSmem<MAXPTS>& S) {
   constexpr int kSMaxPts = MAXPTS;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  Smem& S = *reinterpret_cast<Smem*>(smem_raw);
-
-  const WorkItem item = items[blockIdx.x];
   const uint32_t r = item.run;
   const uint4 info = __ldg(a.run_info + r);
   const uint64_t p_base = item.start;
   const int t = threadIdx.x;
   const int lane = t & 31, warp = t >> 5;
   const int count = static_cast<int>(item.count);
-  if (info.w) {
-    for (int i = t; i < count; i += kSThreads) a.status[p_base + i] = kStatusSkipped;
-    return;
-  }
+  if (info.w) return;  // skipped run: K3b writes the status bytes
   const RunGridDev g = ga.grids[r];
   const int n_alive = static_cast<int>(g.n_alive);
-  if (n_alive > kSMaxPts) return;  // another kernel's item
+  if (n_alive > kSortedMaxPoints) return;  // the grid-walk kernel's item
   const int K = static_cast<int>(info.z) + 2;
-  if (K + 1 > KCAP || (FULL && (K + 1 != KCAP || n_alive < KCAP))) {
-    for (int i = t; i < count; i += kSThreads) sendToResolver(a, p_base + i);
+  const bool cacheable = runCacheable(info);
+  if (!cacheable || n_alive > kSMaxPts || K + 1 > KCAP || (FULL && (K + 1 != KCAP || n_alive < KCAP))) {
+    // not this variant's item (a handful of vertices at the start of a trajectory, or a k this
+    // build has no register path for): the resolver computes the neighbours, in item order
+    unsigned long long fp = 0ull;
+    for (int i = t; i < count; i += kSThreads) {
+      const uint64_t p = p_base + i;
+      const uint64_t ii = a.subset ? a.subset[p] : p;
+      fp += vertexFingerprint(a.x[ii], a.y[ii], a.z[ii], static_cast<uint32_t>(i),
+                              a.subset ? ii : 0ull);
+      if (cacheable) cache.rec[p * 8] = static_cast<uint16_t>(i);
+      sendToResolver(a, p, cacheable ? static_cast<uint32_t>(p) : kNoCacheSlot);
+    }
+    fp = warpSumU64(fp);
+    if (lane == 0) S.fp_w[warp] = fp;
+    __syncthreads();
+    if (t == 0) {
+      cache.item_fp[item_index] = itemFingerprint(S);
+      cache.item_ok[item_index] = cacheable ? 1u : 0u;
+    }
     return;
   }
 
   // Items of at most one group (the head vertex of a stamp stretch is a run of its own) skip
-  // the vertex sort and stage only the pose rows of their winners.
+  // the vertex sort.
   const bool tiny = count <= 32;
 
   // ---- stage the run's alive points; load the item's vertices and their bounding box
@@ -274,27 +190,14 @@ deformKnnBlendSortedKernel(const DeformArgs a, const GridArgs ga,
     for (int i = t; i < n_alive; i += kSThreads) cpAsync<16>(&S.pts[i], src + i);
     // list padding (see the walk): d^2 to this point is +inf for every finite query
     if (t == 0) S.pts[n_alive] = make_float4(3e30f, 3e30f, 3e30f, __int_as_float(-1));
-    if constexpr (STAGE) {
-      // pose rows of the alive points: component-major so that lanes reading one component of
-      // different slots never collide on a bank
-      if (!tiny) {
-        for (int e = t; e < n_alive * 15; e += kSThreads) {
-          const int s_ = e / 15, c = e - s_ * 15;
-          const int j = __float_as_int(__ldg(src + s_).w);
-          if constexpr (PREC == 0) {
-            cpAsync<8>(&S.pose.row[c][s_], c < 12 ? a.poses + 12ull * j + c : a.ctrl_pos + 3ull * j + (c - 12));
-          } else {
-            cpAsync<4>(&S.pose.row[c][s_], a.ctrl_pose_f32 + 16ull * j + c);  // R(9) t(3) g(3)
-          }
-        }
-      }
-    }
   }
+  unsigned long long fp = 0ull;
   float mn0 = FLT_MAX, mn1 = FLT_MAX, mn2 = FLT_MAX, mx0 = -FLT_MAX, mx1 = -FLT_MAX,
         mx2 = -FLT_MAX;
   for (int i = t; i < count; i += kSThreads) {
     const uint64_t ii = a.subset ? a.subset[p_base + i] : p_base + i;
     const float x = a.x[ii], y = a.y[ii], z = a.z[ii];
+    fp += vertexFingerprint(x, y, z, static_cast<uint32_t>(i), a.subset ? ii : 0ull);
     S.vx[i] = x;
     S.vy[i] = y;
     S.vz[i] = z;
@@ -305,6 +208,8 @@ deformKnnBlendSortedKernel(const DeformArgs a, const GridArgs ga,
     mn2 = fminf(mn2, z);
     mx2 = fmaxf(mx2, z);
   }
+  fp = warpSumU64(fp);
+  if (lane == 0) S.fp_w[warp] = fp;
   if (tiny) {
     if (t < 32) S.perm[t] = static_cast<uint16_t>(t);
     cpAsyncWaitAll();
@@ -607,7 +512,6 @@ deformKnnBlendSortedKernel(const DeformArgs a, const GridArgs ga,
 
     // winners: exact d^2 and control index back from the list
     const uint64_t p = p_base + v;
-    const uint64_t ii = a.subset ? a.subset[p] : p;
     float nbr_d2[KCAP];
     int nbr_idx[KCAP];
     bool near_tie = false;   // two winners agree above the ordinal bits
@@ -620,7 +524,7 @@ deformKnnBlendSortedKernel(const DeformArgs a, const GridArgs ga,
         const int slot_i = list[best[i] & ord_mask];
         const float4 c = S.pts[slot_i];
         nbr_d2[i] = dist2Exact(c.x, c.y, c.z, qx, qy, qz);
-        nbr_idx[i] = STAGE ? slot_i : __float_as_int(c.w);  // staged: the slot, resolved at the end
+        nbr_idx[i] = __float_as_int(c.w);
       }
       if (i > 0 && i < n_need && (best[i] >> ord_bits) == (best[i - 1] >> ord_bits)) {
         near_tie = true;
@@ -672,70 +576,128 @@ deformKnnBlendSortedKernel(const DeformArgs a, const GridArgs ga,
         if (i < n_need && nbr_d2[i] <= nbr_d2[i - 1]) tie = true;
       }
     }
+    // ---- association record: vertex offset + neighbours (relative to run.lo) + weights
+    const uint64_t rec_slot = p_base + static_cast<uint64_t>(slot);
+    uint32_t rel[KCAP];
+#pragma unroll
+    for (int j = 0; j < KCAP; ++j) rel[j] = (j < n - 1) ? static_cast<uint32_t>(nbr_idx[j]) - info.x : 0u;
+    {
+      uint4 rec0;
+      rec0.x = static_cast<uint32_t>(v) | (rel[0] << 16);
+      rec0.y = (KCAP > 1 ? rel[1] : 0u) | ((KCAP > 2 ? rel[2] : 0u) << 16);
+      rec0.z = (KCAP > 3 ? rel[3] : 0u) | ((KCAP > 4 ? rel[4] : 0u) << 16);
+      rec0.w = (KCAP > 5 ? rel[5] : 0u) | ((KCAP > 6 ? rel[6] : 0u) << 16);
+      reinterpret_cast<uint4*>(cache.rec)[rec_slot] = rec0;
+      if (KCAP >= 15 && cache.w_planes > 7) {  // more than 7 blended neighbours: plane 1 = nbr 7..14
+        const uint4 rec1 = make_uint4(rel[7] | (rel[8] << 16), rel[9] | (rel[10] << 16),
+                                      rel[11] | (rel[12] << 16), rel[13] | (rel[14] << 16));
+        reinterpret_cast<uint4*>(cache.rec)[cache.n_slots + rec_slot] = rec1;
+      }
+    }
     if (tie) {  // exact tie (or an unresolvable near tie): the resolver is exact for both
-      sendToResolver(a, p);
+      sendToResolver(a, p, static_cast<uint32_t>(rec_slot));
       continue;
     }
-    if constexpr (STAGE) {
-      if (tiny) {
-        // the pose rows were not staged: fetch those of this vertex's own neighbours (lanes
-        // that share a neighbour write identical values)
+    {
+      // nbr_d2[n - 1] without dynamic indexing: distances ascend
+      float last_d2 = nbr_d2[0];
+#pragma unroll
+      for (int j = 1; j < KCAP; ++j) last_d2 = j < n ? fmaxf(last_d2, nbr_d2[j]) : last_d2;
+      const float d_max_f = __fsqrt_rn(last_d2);
+      const bool const_w = constWeight(nbr_d2[0], d_max_f);
+      if constexpr (PREC == 0) {
+        double* wp = static_cast<double*>(cache.weight) + rec_slot;
 #pragma unroll
         for (int j = 0; j < KCAP; ++j) {
-          if (j < n - 1) {
-            const int s_ = nbr_idx[j];
-            const int cj = __float_as_int(S.pts[s_].w);
-#pragma unroll 1
-            for (int c = 0; c < 15; ++c) {
-              if constexpr (PREC == 0) {
-                S.pose.row[c][s_] = c < 12 ? a.poses[12ull * cj + c] : a.ctrl_pos[3ull * cj + (c - 12)];
-              } else {
-                S.pose.row[c][s_] = a.ctrl_pose_f32[16ull * cj + c];
-              }
-            }
-          }
+          if (j < n - 1) wp[static_cast<uint64_t>(j) * cache.n_slots] = weightFp64(nbr_d2[j], d_max_f, const_w);
+        }
+      } else {
+        const float inv_dmax = const_w ? 0.0f : __frcp_rn(d_max_f);
+        float* wp = static_cast<float*>(cache.weight) + rec_slot;
+#pragma unroll
+        for (int j = 0; j < KCAP; ++j) {
+          if (j < n - 1) wp[static_cast<uint64_t>(j) * cache.n_slots] = weightFp32(nbr_d2[j], inv_dmax, const_w);
         }
       }
-      writeResultStaged<KCAP, PREC>(a, S, p, ii, qx, qy, qz, nbr_d2, nbr_idx, n);
-    } else {
-      writeResultReg<KCAP>(a, p, ii, PREC, qx, qy, qz, nbr_d2, nbr_idx, n);
     }
-    a.status[p] = kStatusDone;
   }
+  }
+  __syncthreads();  // every record of the item is on its way: publish the item
+  if (t == 0) {
+    cache.item_fp[item_index] = itemFingerprint(S);
+    cache.item_ok[item_index] = 1u;
   }
 }
 
-template <int KCAP, int PREC, int MAXPTS, bool STAGE, bool FULL>
-cudaError_t launchOne(const DeformArgs& args, const GridArgs& gargs, const WorkItem* items,
-                      uint32_t n_items, cudaStream_t stream) {
-  const size_t smem = sizeof(typename SmemOf<PREC, MAXPTS, STAGE>::type);
+// one CTA per work item
+template <int KCAP, int PREC, int MAXPTS, bool FULL>
+__global__ void __launch_bounds__(kSThreads, PGMO_K3_CTAS)
+deformSearchSortedKernel(const DeformArgs a, const GridArgs ga, const AssocCache cache,
+                         const WorkItem* __restrict__ items, const uint32_t first_item) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SortedSmem<MAXPTS>& S = *reinterpret_cast<SortedSmem<MAXPTS>*>(smem_raw);
+  const uint32_t item_index = first_item + blockIdx.x;
+  searchItem<KCAP, PREC, MAXPTS, FULL>(a, ga, cache, items[item_index], item_index, S);
+}
+
+// persistent grid over the items the validating blend pass found stale
+template <int KCAP, int PREC, int MAXPTS, bool FULL>
+__global__ void __launch_bounds__(kSThreads, PGMO_K3_CTAS)
+deformSearchStaleKernel(const DeformArgs a, const GridArgs ga, const AssocCache cache,
+                        const WorkItem* __restrict__ items) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SortedSmem<MAXPTS>& S = *reinterpret_cast<SortedSmem<MAXPTS>*>(smem_raw);
+  const unsigned long long begin = a.counters[3], end = a.counters[2];
+  for (unsigned long long i = begin + blockIdx.x; i < end; i += gridDim.x) {
+    const uint32_t item_index = cache.stale_items[i];
+    searchItem<KCAP, PREC, MAXPTS, FULL>(a, ga, cache, items[item_index], item_index, S);
+    __syncthreads();  // shared memory is reused by the next item
+  }
+}
+
+template <int KCAP, int PREC, int MAXPTS, bool FULL>
+cudaError_t launchOne(const DeformArgs& args, const GridArgs& gargs, const AssocCache& cache,
+                      const WorkItem* items, uint32_t first_item, uint32_t n_items,
+                      bool from_stale_list, int n_sms, cudaStream_t stream) {
+  const size_t smem = sizeof(SortedSmem<MAXPTS>);
   static thread_local int configured_device = -1;
   int device = 0;
   cudaGetDevice(&device);
   if (configured_device != device) {
-    const cudaError_t e =
-        cudaFuncSetAttribute(deformKnnBlendSortedKernel<KCAP, PREC, MAXPTS, STAGE, FULL>,
+    cudaError_t e = cudaFuncSetAttribute(deformSearchSortedKernel<KCAP, PREC, MAXPTS, FULL>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(deformSearchStaleKernel<KCAP, PREC, MAXPTS, FULL>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
     configured_device = device;
   }
-  deformKnnBlendSortedKernel<KCAP, PREC, MAXPTS, STAGE, FULL>
-      <<<n_items, kSThreads, smem, stream>>>(args, gargs, items);
+  if (from_stale_list) {
+    deformSearchStaleKernel<KCAP, PREC, MAXPTS, FULL>
+        <<<static_cast<unsigned>(n_sms * PGMO_K3_CTAS), kSThreads, smem, stream>>>(args, gargs, cache, items);
+  } else {
+    deformSearchSortedKernel<KCAP, PREC, MAXPTS, FULL>
+        <<<n_items, kSThreads, smem, stream>>>(args, gargs, cache, items, first_item);
+  }
   return cudaGetLastError();
 }
 
 template <int KCAP, int PREC, bool FULL>
-cudaError_t launchVariant(const DeformArgs& args, const GridArgs& gargs, const WorkItem* items,
-                          uint32_t n_items, bool staged, cudaStream_t stream) {
-  return staged ? launchOne<KCAP, PREC, kStagedMaxPts, true, FULL>(args, gargs, items, n_items, stream)
-                : launchOne<KCAP, PREC, kSortedMaxPoints, false, FULL>(args, gargs, items, n_items, stream);
+cudaError_t launchVariant(const DeformArgs& args, const GridArgs& gargs, const AssocCache& cache,
+                          const WorkItem* items, uint32_t first_item, uint32_t n_items, bool small,
+                          bool from_stale_list, int n_sms, cudaStream_t stream) {
+  return small ? launchOne<KCAP, PREC, kSmallMaxPts, FULL>(args, gargs, cache, items, first_item, n_items,
+                                                          from_stale_list, n_sms, stream)
+               : launchOne<KCAP, PREC, kSortedMaxPoints, FULL>(args, gargs, cache, items, first_item,
+                                                               n_items, from_stale_list, n_sms, stream);
 }
 
 template <int KCAP, int PREC>
 void preloadVariants() {
   cudaFuncAttributes attr;
-  cudaFuncGetAttributes(&attr, deformKnnBlendSortedKernel<KCAP, PREC, kStagedMaxPts, true, true>);
-  cudaFuncGetAttributes(&attr, deformKnnBlendSortedKernel<KCAP, PREC, kSortedMaxPoints, false, true>);
+  cudaFuncGetAttributes(&attr, deformSearchSortedKernel<KCAP, PREC, kSmallMaxPts, true>);
+  cudaFuncGetAttributes(&attr, deformSearchStaleKernel<KCAP, PREC, kSmallMaxPts, true>);
+  cudaFuncGetAttributes(&attr, deformSearchSortedKernel<KCAP, PREC, kSortedMaxPoints, true>);
 }
 
 }  // namespace
@@ -747,23 +709,24 @@ void preloadDeformSortedKernels() {
   preloadVariants<7, 1>();
 }
 
-cudaError_t launchDeformKnnBlendSorted(const DeformArgs& args, const GridArgs& gargs,
-                                       const WorkItem* items, uint32_t n_items, int precision,
-                                       uint32_t max_k, uint32_t min_k, uint64_t widest_window,
-                                       cudaStream_t stream) {
-  if (n_items == 0) return cudaSuccess;
-  // every alive set fits the staged variant (pose rows in shared memory) iff the widest window does
-  const bool staged = widest_window <= static_cast<uint64_t>(kStagedMaxPts);
+cudaError_t launchDeformSearchSorted(const DeformArgs& args, const GridArgs& gargs,
+                                     const AssocCache& cache, const WorkItem* items,
+                                     uint32_t first_item, uint32_t n_items, int precision,
+                                     uint32_t max_k, uint32_t min_k, uint64_t widest_window,
+                                     bool from_stale_list, int n_sms, cudaStream_t stream) {
+  if (n_items == 0 && !from_stale_list) return cudaSuccess;
+  // every alive set fits the lean variant iff the widest window does
+  const bool small = widest_window <= static_cast<uint64_t>(kSmallMaxPts);
   if (max_k == 4 && min_k == 4) {  // the reference's default k, never changed mid-sweep
-    return precision == 0 ? launchVariant<7, 0, true>(args, gargs, items, n_items, staged, stream)
-                          : launchVariant<7, 1, true>(args, gargs, items, n_items, staged, stream);
+    return precision == 0 ? launchVariant<7, 0, true>(args, gargs, cache, items, first_item, n_items, small, from_stale_list, n_sms, stream)
+                          : launchVariant<7, 1, true>(args, gargs, cache, items, first_item, n_items, small, from_stale_list, n_sms, stream);
   }
   if (max_k + 3 <= 7) {
-    return precision == 0 ? launchVariant<7, 0, false>(args, gargs, items, n_items, staged, stream)
-                          : launchVariant<7, 1, false>(args, gargs, items, n_items, staged, stream);
+    return precision == 0 ? launchVariant<7, 0, false>(args, gargs, cache, items, first_item, n_items, small, from_stale_list, n_sms, stream)
+                          : launchVariant<7, 1, false>(args, gargs, cache, items, first_item, n_items, small, from_stale_list, n_sms, stream);
   }
-  return precision == 0 ? launchVariant<16, 0, false>(args, gargs, items, n_items, staged, stream)
-                        : launchVariant<16, 1, false>(args, gargs, items, n_items, staged, stream);
+  return precision == 0 ? launchVariant<16, 0, false>(args, gargs, cache, items, first_item, n_items, small, from_stale_list, n_sms, stream)
+                        : launchVariant<16, 1, false>(args, gargs, cache, items, first_item, n_items, small, from_stale_list, n_sms, stream);
 }
 
 }  // namespace pgmo
