@@ -128,6 +128,12 @@ int pgmo_deform_set_assoc_cache(pgmo_deform_t* h, int enabled);
  * resolver, 1 if the call started from cached records]. */
 int pgmo_deform_last_step_info(pgmo_deform_t* h, float* ms4, uint64_t* counts4);
 
+/* Diagnostics: the association records of the slab last deformed, 8 u16 per local position in
+ * search order: {vertex offset inside its work item, neighbour 0..6 as (control index - run.lo) |
+ * bank class << 13}.  *n_slots = how many there are; min(n_slots, capacity) are copied. */
+int pgmo_deform_cache_records(pgmo_deform_t* h, uint16_t* records8, uint64_t capacity,
+                              uint64_t* n_slots);
+
 /* deformation::deformPoints, host buffers, whole job.
  *   x,y,z        n_v f32 each (SoA vertex stream)
  *   stamps_ns    n_v u64; NULL selects the unstamped overload (mesh_deformation.h:63-113)

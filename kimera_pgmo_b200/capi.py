@@ -54,6 +54,7 @@ SIGNATURES = {
     "pgmo_deform_last_timings": (C.c_int, [_vp, _vp, _u64p]),
     "pgmo_deform_set_assoc_cache": (C.c_int, [_vp, C.c_int]),
     "pgmo_deform_last_step_info": (C.c_int, [_vp, _vp, _vp]),
+    "pgmo_deform_cache_records": (C.c_int, [_vp, _vp, C.c_uint64, _u64p]),
     "pgmo_deform_points": (C.c_int, [_vp, C.c_uint64, _vp, _vp, _vp, _vp, _vp, C.c_uint64,
                                      C.c_uint32, C.c_double, C.c_int, _vp, _vp, _vp, _vp, _vp,
                                      C.c_uint32, _vp, _vp]),
@@ -217,6 +218,14 @@ class DeformHandle:
 
     def set_assoc_cache(self, enabled=True):
         _check(self._lib.pgmo_deform_set_assoc_cache(self._h, 1 if enabled else 0))
+
+    def cache_records(self):
+        """(n_slots, 8) uint16: the association records in search order (diagnostics)."""
+        n = C.c_uint64(0)
+        _check(self._lib.pgmo_deform_cache_records(self._h, None, 0, C.byref(n)))
+        rec = np.zeros((int(n.value), 8), dtype=np.uint16)
+        _check(self._lib.pgmo_deform_cache_records(self._h, _ptr(rec), rec.shape[0], C.byref(n)))
+        return rec
 
     def last_step_info(self):
         """dict(search_ms, resolver_ms, blend_ms, total_ms, items, stale_items, resolved, warm)."""

@@ -1,6 +1,7 @@
 // C ABI of the deformation path (see include/pgmo_b200.h).
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -82,6 +83,10 @@ struct pgmo_deform {
   // association cache (deform_blend.cu): records + weights per local position of the slab the
   // work items were cut for, fingerprints per work item.  Valid as long as the items are.
   bool cache_enabled = true;   // false: every call redoes the search (records are scratch)
+  double class_cell = 0.0;     // hash-grid edge of the colouring below
+  std::vector<uint8_t> h_class;  // bank class of every control point's pose row (AssocCache)
+  uint64_t class_n = 0;        // control points coloured so far
+  DevBuf<uint8_t> d_class;
   int n_sms = 148;
   DevBuf<uint16_t> d_cache_rec;
   DevBuf<unsigned char> d_cache_w;
@@ -215,11 +220,145 @@ int finishControls(pgmo_deform_t* h, bool positions_changed, cudaStream_t st) {
   PGMO_TRY(h->d_pose_rows.reserve(16 * h->n_c + 16));
   PGMO_CUDA(launchBuildControlTables(h->n_c, h->d_pos.ptr, h->has_poses ? h->d_poses.ptr : nullptr,
                                      h->d_ctrl_f4.ptr, h->d_pose_f32.ptr, h->d_pose_rows.ptr,
-                                     positions_changed, st));
+                                     h->d_class.ptr, positions_changed, st));
   if (positions_changed) {
     ++h->control_version;
     h->sched_ready = false;
   }
+  return PGMO_OK;
+}
+
+// Typical spacing of the control points, estimated from the nearest-neighbour distance of a
+// sample (looked for among the points close in index = close in time).
+double estimateControlSpacing(const std::vector<double>& pos, uint64_t n) {
+  if (n < 2) return 1.0;
+  std::vector<double> nn;
+  const uint64_t n_samples = std::min<uint64_t>(n, 256);
+  for (uint64_t s = 0; s < n_samples; ++s) {
+    const uint64_t i = s * n / n_samples;
+    const uint64_t j0 = i > 256 ? i - 256 : 0, j1 = std::min<uint64_t>(n, i + 257);
+    double best = -1.0;
+    for (uint64_t j = j0; j < j1; ++j) {
+      if (j == i) continue;
+      const double dx = pos[3 * j] - pos[3 * i], dy = pos[3 * j + 1] - pos[3 * i + 1],
+                   dz = pos[3 * j + 2] - pos[3 * i + 2];
+      const double d2 = dx * dx + dy * dy + dz * dz;
+      if (d2 > 0.0 && (best < 0.0 || d2 < best)) best = d2;
+    }
+    if (best > 0.0 && std::isfinite(best)) nn.push_back(std::sqrt(best));
+  }
+  if (nn.empty()) return 1.0;
+  std::nth_element(nn.begin(), nn.begin() + nn.size() / 2, nn.end());
+  const double spacing = nn[nn.size() / 2] / 0.554;  // mean nn distance = 0.554 x spacing
+  return std::min(std::max(spacing, 1e-4), 1e6);
+}
+
+// Bank classes of the pose rows (AssocCache::pose_rows): a greedy 8-colouring of the control
+// points in index order — every point takes the colour that weighs least (sum of 1 / d^2) among
+// its nearest already coloured points.  The quarter warps of the blend kernel read the rows of
+// control points that lie close together (the j-th neighbours of eight nearby vertices), and
+// rows of different classes sit in different bank groups.  Points [0, n_keep) keep their class
+// (appended control points: the records of the old ones stay decodable).  Affects speed only.
+void colourControls(const std::vector<double>& pos, uint64_t n, uint64_t n_keep, double* cell_io,
+                    std::vector<uint8_t>* cls) {
+  cls->resize(n);
+  if (n_keep >= n) return;
+  if (n_keep == 0 || !(*cell_io > 0.0)) *cell_io = estimateControlSpacing(pos, n);
+  const double cell = *cell_io, inv = 1.0 / cell;
+  auto cellOf = [&](uint64_t i, int64_t c[3]) {
+    for (int a = 0; a < 3; ++a) {
+      double v = std::floor(pos[3 * i + a] * inv);
+      if (!(v > -1e9)) v = -1e9;  // NaN / huge coordinates: one far-away bucket
+      if (v > 1e9) v = 1e9;
+      c[a] = static_cast<int64_t>(v);
+    }
+  };
+  auto keyOf = [](const int64_t c[3]) {
+    return static_cast<uint64_t>(c[0] + (1ll << 30)) * 0x9E3779B97F4A7C15ull ^
+           static_cast<uint64_t>(c[1] + (1ll << 30)) * 0xC2B2AE3D27D4EB4Full ^
+           static_cast<uint64_t>(c[2] + (1ll << 30)) * 0x165667B19E3779F9ull;
+  };
+  // open-addressing table: cell key -> head of a per-cell list through `next` (points inserted
+  // in index order, so a list only ever holds earlier points)
+  uint64_t cap = 64;
+  while (cap < 2 * n) cap <<= 1;
+  std::vector<uint64_t> keys(cap, ~0ull);
+  std::vector<int32_t> head(cap, -1), next(n, -1);
+  auto slotOf = [&](uint64_t key) {
+    uint64_t s = (key * 0xD6E8FEB86659FD93ull) & (cap - 1);
+    while (keys[s] != ~0ull && keys[s] != key) s = (s + 1) & (cap - 1);
+    return s;
+  };
+  auto insert = [&](uint64_t i) {
+    int64_t c[3];
+    cellOf(i, c);
+    uint64_t key = keyOf(c);
+    if (key == ~0ull) key = 0;
+    const uint64_t s = slotOf(key);
+    keys[s] = key;
+    next[i] = head[s];
+    head[s] = static_cast<int32_t>(i);
+  };
+  for (uint64_t i = 0; i < n_keep; ++i) insert(i);
+  constexpr int kNear = 10;
+  for (uint64_t i = n_keep; i < n; ++i) {
+    int64_t c[3];
+    cellOf(i, c);
+    double best_d[kNear];
+    int best_c[kNear];
+    int n_best = 0;
+    for (int64_t dz = -1; dz <= 1; ++dz) {
+      for (int64_t dy = -1; dy <= 1; ++dy) {
+        for (int64_t dx = -1; dx <= 1; ++dx) {
+          const int64_t cc[3] = {c[0] + dx, c[1] + dy, c[2] + dz};
+          uint64_t key = keyOf(cc);
+          if (key == ~0ull) key = 0;
+          const uint64_t s = slotOf(key);
+          if (keys[s] != key) continue;
+          int walked = 0;
+          for (int32_t j = head[s]; j >= 0 && walked < 64; j = next[j], ++walked) {
+            const double ex = pos[3 * j] - pos[3 * i], ey = pos[3 * j + 1] - pos[3 * i + 1],
+                         ez = pos[3 * j + 2] - pos[3 * i + 2];
+            const double d2 = ex * ex + ey * ey + ez * ez;
+            if (!(d2 >= 0.0)) continue;
+            int at = n_best < kNear ? n_best : (d2 < best_d[kNear - 1] ? kNear - 1 : -1);
+            if (at < 0) continue;
+            if (n_best < kNear) ++n_best;
+            while (at > 0 && best_d[at - 1] > d2) {
+              best_d[at] = best_d[at - 1];
+              best_c[at] = best_c[at - 1];
+              --at;
+            }
+            best_d[at] = d2;
+            best_c[at] = (*cls)[j];
+          }
+        }
+      }
+    }
+    double weight[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const double floor2 = 1e-6 * cell * cell;
+    for (int b = 0; b < n_best; ++b) weight[best_c[b]] += 1.0 / (best_d[b] + floor2);
+    int pick = static_cast<int>(i & 7);  // no coloured point nearby: spread by index
+    if (n_best > 0) {
+      pick = 0;
+      for (int k = 1; k < 8; ++k) {
+        if (weight[k] < weight[pick]) pick = k;
+      }
+    }
+    (*cls)[i] = static_cast<uint8_t>(pick);
+    insert(i);
+  }
+}
+
+// Bank classes after h_pos changed (grew: the old points are a prefix and keep theirs).
+int refreshClasses(pgmo_deform_t* h, bool grew, cudaStream_t st) {
+  const uint64_t n = h->h_pos.size() / 3;
+  const uint64_t keep = grew ? std::min<uint64_t>(h->class_n, n) : 0;
+  colourControls(h->h_pos, n, keep, &h->class_cell, &h->h_class);
+  h->class_n = n;
+  PGMO_TRY(h->d_class.reserve(n + 1));
+  if (n) PGMO_CUDA(cudaMemcpyAsync(h->d_class.ptr, h->h_class.data(), n, cudaMemcpyHostToDevice, st));
+  PGMO_CUDA(cudaStreamSynchronize(st));
   return PGMO_OK;
 }
 
@@ -390,6 +529,8 @@ int pgmo_deform_set_controls(pgmo_deform_t* h, uint64_t n_c, const double* pos_x
   const bool changed = h->n_c != n_c || !sameArray(h->h_pos, pos_xyz, 3 * n_c) ||
                        !sameArray(h->h_stamps, stamps_ns, n_c) ||
                        !sameArray(h->h_valid, valid, n_c);
+  // old positions are a prefix of the new ones: their pose rows keep their bank classes
+  const bool pos_kept = h->n_c > 0 && n_c >= h->n_c && samePrefix(h->h_pos, pos_xyz, 3 * n_c);
   if (changed) {
     // appended control points only?  (has_valid must not flip: "no validity array" = all valid)
     const bool grew = h->n_c > 0 && n_c >= h->n_c && samePrefix(h->h_pos, pos_xyz, 3 * n_c) &&
@@ -407,6 +548,7 @@ int pgmo_deform_set_controls(pgmo_deform_t* h, uint64_t n_c, const double* pos_x
   PGMO_TRY(h->d_valid.reserve(n_c + 1));
   if (changed) {
     h->h_pos.assign(pos_xyz, pos_xyz + 3 * n_c);
+    PGMO_TRY(refreshClasses(h, pos_kept, st));
     if (stamps_ns) h->h_stamps.assign(stamps_ns, stamps_ns + n_c);
     else h->h_stamps.clear();
     if (valid) h->h_valid.assign(valid, valid + n_c);
@@ -445,6 +587,7 @@ int pgmo_deform_set_controls_device(pgmo_deform_t* h, uint64_t n_c, const double
   }
   PGMO_CUDA(cudaStreamSynchronize(st));
   const bool changed = h->n_c != n_c || h->h_pos != pos || h->h_stamps != stamps || h->h_valid != valid;
+  const bool pos_kept = h->n_c > 0 && n_c >= h->n_c && samePrefix(h->h_pos, pos.data(), 3 * n_c);
   if (changed) {
     const bool grew = h->n_c > 0 && n_c >= h->n_c && samePrefix(h->h_pos, pos.data(), 3 * n_c) &&
                       d_stamps_ns != nullptr && h->has_stamps && samePrefix(h->h_stamps, stamps.data(), n_c) &&
@@ -461,6 +604,7 @@ int pgmo_deform_set_controls_device(pgmo_deform_t* h, uint64_t n_c, const double
   PGMO_TRY(h->d_valid.reserve(n_c + 1));
   if (changed) {
     h->h_pos.swap(pos);
+    PGMO_TRY(refreshClasses(h, pos_kept, st));
     h->h_stamps.swap(stamps);
     h->h_valid.swap(valid);
     PGMO_CUDA(cudaMemcpyAsync(h->d_pos.ptr, d_pos_xyz, 3 * n_c * sizeof(double), cudaMemcpyDeviceToDevice, st));
@@ -707,6 +851,7 @@ static int prepareCache(pgmo_deform_t* h, int precision, cudaStream_t st, AssocC
   c->stale_items = h->d_stale_items.ptr;
   c->pose_rows = precision == PGMO_PRECISION_FP64 ? static_cast<const void*>(h->d_pose_rows.ptr)
                                                   : static_cast<const void*>(h->d_pose_f32.ptr);
+  c->ctrl_class = h->d_class.ptr;
   return PGMO_OK;
 }
 
@@ -936,6 +1081,20 @@ int pgmo_deform_last_timings(pgmo_deform_t* h, float* ms2, uint64_t* schedule_bu
 int pgmo_deform_set_assoc_cache(pgmo_deform_t* h, int enabled) {
   PGMO_CHECK_ARG(h != nullptr);
   h->cache_enabled = enabled != 0;
+  return PGMO_OK;
+}
+
+int pgmo_deform_cache_records(pgmo_deform_t* h, uint16_t* records8, uint64_t capacity,
+                              uint64_t* n_slots) {
+  PGMO_CHECK_ARG(h != nullptr && n_slots != nullptr);
+  PGMO_TRY(ensureDevice(h->device));
+  *n_slots = h->d_cache_rec.ptr ? h->cache_items_n : 0;
+  const uint64_t n = std::min<uint64_t>(*n_slots, capacity);
+  if (records8 && n) {
+    PGMO_CUDA(cudaMemcpyAsync(records8, h->d_cache_rec.ptr, n * 8 * sizeof(uint16_t),
+                              cudaMemcpyDeviceToHost, h->stream));
+    PGMO_CUDA(cudaStreamSynchronize(h->stream));
+  }
   return PGMO_OK;
 }
 

@@ -12,9 +12,11 @@
 //     run's window [lo, hi) — R(9) t(3) g(3) as 128-byte rows, one contiguous block of the
 //     table — arrive by ONE bulk asynchronous copy (cp.async.bulk, TMA engine; completion on an
 //     mbarrier) that overlaps the vertex loads.
-//   * The table stores 16-byte chunk c of row j at c ^ (j & 7): the 8 lanes of a quarter warp
-//     reading chunk c of 8 different rows hit 8 different bank groups unless two rows agree in
-//     j & 7, instead of all hitting the same one.
+//   * The table stores 16-byte chunk c of row j at c ^ class(j), class = the colour of the
+//     control point's cell in a lattice colouring (AssocCache::class_inv_cell): the 8 lanes of a
+//     quarter warp read chunk c of the rows of control points that lie close together, and
+//     close-by points have different classes, i.e. different bank groups, instead of all
+//     hitting the same one.
 //   * Vertices are loaded coalesced, fingerprinted (validating mode) and staged in shared
 //     memory; a lane takes the vertex of its record (records are in search order: neighbouring
 //     lanes share neighbours, equal addresses are broadcast), blends in the reference's
@@ -85,14 +87,15 @@ __device__ __forceinline__ void mbarWait(unsigned long long* bar, uint32_t parit
 __device__ __forceinline__ void accumulate64(const double2* __restrict__ row, int sw, double w,
                                              double v0, double v1, double v2, double& wsum,
                                              double& acc0, double& acc1, double& acc2) {
-  const double2 c6 = row[6 ^ sw], c7 = row[7 ^ sw];  // g0 g1 | g2 -
+  const double2 c6 = row[6 ^ sw];                                             // g0 g1
+  const double c7x = *reinterpret_cast<const double*>(row + (7 ^ sw));  // g2
   const double2 c0 = row[0 ^ sw], c1 = row[1 ^ sw];  // R0 R1 | R2 R3
   const double2 c2 = row[2 ^ sw], c3 = row[3 ^ sw];  // R4 R5 | R6 R7
   const double2 c4 = row[4 ^ sw], c5 = row[5 ^ sw];  // R8 t0 | t1 t2
   wsum = __dadd_rn(wsum, w);
   const double p0 = __dsub_rn(v0, c6.x);
   const double p1 = __dsub_rn(v1, c6.y);
-  const double p2 = __dsub_rn(v2, c7.x);
+  const double p2 = __dsub_rn(v2, c7x);
   const double r0 = __dadd_rn(__dadd_rn(__dmul_rn(c0.x, p0), __dmul_rn(c0.y, p1)), __dmul_rn(c1.x, p2));
   const double r1 = __dadd_rn(__dadd_rn(__dmul_rn(c1.y, p0), __dmul_rn(c2.x, p1)), __dmul_rn(c2.y, p2));
   const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(c3.x, p0), __dmul_rn(c3.y, p1)), __dmul_rn(c4.x, p2));
@@ -113,11 +116,12 @@ __device__ __forceinline__ void accumulate32(const float4* __restrict__ row, flo
 }
 
 // the blend proper: lane <-> record (search order).  NB > 0: compile-time neighbour count.
-template <int PREC, int NB>
+// IN_PLACE: pose rows read from the table in global memory instead of the staged copy.
+template <int PREC, int NB, bool IN_PLACE>
 __device__ __forceinline__ void blendVertices(const DeformArgs& a, const AssocCache& cache,
                                               BlendSmemHead& S, const unsigned char* rows,
                                               uint64_t p_base, int count, int nb_runtime,
-                                              uint32_t lo, bool tiny) {
+                                              uint32_t lo) {
   const int t = threadIdx.x;
   const int nb = NB > 0 ? NB : nb_runtime;
   const uint4* rec0 = reinterpret_cast<const uint4*>(cache.rec);
@@ -154,24 +158,24 @@ __device__ __forceinline__ void blendVertices(const DeformArgs& a, const AssocCa
       const double v0 = static_cast<double>(qx), v1 = static_cast<double>(qy),
                    v2 = static_cast<double>(qz);
       double wsum = 0.0, acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
-      const double2* table = tiny ? static_cast<const double2*>(cache.pose_rows) + 8ull * lo
-                                  : reinterpret_cast<const double2*>(rows);
+      const double2* table = IN_PLACE ? static_cast<const double2*>(cache.pose_rows) + 8ull * lo
+                                      : reinterpret_cast<const double2*>(rows);
       if (NB > 0) {
         double w[NB > 0 ? NB : 1];
 #pragma unroll
         for (int j = 0; j < NB; ++j) w[j] = __ldg(wp + static_cast<uint64_t>(j) * cache.n_slots);
 #pragma unroll
         for (int j = 0; j < NB; ++j) {
-          accumulate64(table + 8u * rel[j], static_cast<int>((lo + rel[j]) & 7u), w[j], v0, v1, v2,
-                       wsum, acc0, acc1, acc2);
+          accumulate64(table + 8u * (rel[j] & kCacheRelMask), static_cast<int>(rel[j] >> kCacheRelBits),
+                       w[j], v0, v1, v2, wsum, acc0, acc1, acc2);
         }
       } else {
 #pragma unroll
         for (int j = 0; j < kCacheMaxNbr; ++j) {
           if (j < nb) {
             const double w = __ldg(wp + static_cast<uint64_t>(j) * cache.n_slots);
-            accumulate64(table + 8u * rel[j], static_cast<int>((lo + rel[j]) & 7u), w, v0, v1, v2,
-                         wsum, acc0, acc1, acc2);
+            accumulate64(table + 8u * (rel[j] & kCacheRelMask), static_cast<int>(rel[j] >> kCacheRelBits),
+                         w, v0, v1, v2, wsum, acc0, acc1, acc2);
           }
         }
       }
@@ -187,13 +191,13 @@ __device__ __forceinline__ void blendVertices(const DeformArgs& a, const AssocCa
     } else {
       const float* wp = static_cast<const float*>(cache.weight) + slot;
       float wsum = 0.f, acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
-      const float4* table = tiny ? static_cast<const float4*>(cache.pose_rows) + 4ull * lo
-                                 : reinterpret_cast<const float4*>(rows);
+      const float4* table = IN_PLACE ? static_cast<const float4*>(cache.pose_rows) + 4ull * lo
+                                     : reinterpret_cast<const float4*>(rows);
 #pragma unroll
       for (int j = 0; j < (NB > 0 ? NB : kCacheMaxNbr); ++j) {
         if (NB > 0 || j < nb) {
           const float w = __ldg(wp + static_cast<uint64_t>(j) * cache.n_slots);
-          accumulate32(table + 4u * rel[j], w, qx, qy, qz, wsum, acc0, acc1, acc2);
+          accumulate32(table + 4u * (rel[j] & kCacheRelMask), w, qx, qy, qz, wsum, acc0, acc1, acc2);
         }
       }
       const float o0 = acc0 / wsum, o1 = acc1 / wsum, o2 = acc2 / wsum;
@@ -210,7 +214,7 @@ __device__ __forceinline__ void blendVertices(const DeformArgs& a, const AssocCa
 #pragma unroll
       for (int j = 0; j <= kCacheMaxNbr; ++j) {
         if (static_cast<uint32_t>(j) < a.assoc_stride) {
-          a.assoc[p * a.assoc_stride + j] = j < nb ? lo + rel[j] : 0xFFFFFFFFu;
+          a.assoc[p * a.assoc_stride + j] = j < nb ? lo + (rel[j] & kCacheRelMask) : 0xFFFFFFFFu;
         }
       }
       for (uint32_t j = kCacheMaxNbr + 1; j < a.assoc_stride; ++j) a.assoc[p * a.assoc_stride + j] = 0xFFFFFFFFu;
@@ -303,8 +307,9 @@ __device__ __forceinline__ void blendItem(const DeformArgs& a, const GridArgs& g
     bar_phase ^= 1u;
   }
 
-  if (nb == 5) blendVertices<PREC, 5>(a, cache, S, rows, p_base, count, nb, lo, tiny);
-  else blendVertices<PREC, 0>(a, cache, S, rows, p_base, count, nb, lo, tiny);
+  if (tiny) blendVertices<PREC, 0, true>(a, cache, S, rows, p_base, count, nb, lo);
+  else if (nb == 5) blendVertices<PREC, 5, false>(a, cache, S, rows, p_base, count, nb, lo);
+  else blendVertices<PREC, 0, false>(a, cache, S, rows, p_base, count, nb, lo);
   __syncthreads();
   // ---- results out (coalesced)
   for (int i = t; i < count; i += kBThreads) {

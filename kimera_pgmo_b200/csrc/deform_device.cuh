@@ -65,10 +65,10 @@ __device__ __forceinline__ unsigned long long warpSumU64(unsigned long long v) {
 // can the vertices of a run {lo, hi, k, skip} have association records?  (neighbour count and
 // the 16-bit relative control index of the record layout)
 __device__ __forceinline__ bool runCacheable(const uint4& info) {
-  return static_cast<int>(info.z) + 1 <= kCacheMaxNbr && info.y - info.x <= 65536u;
+  return static_cast<int>(info.z) + 1 <= kCacheMaxNbr && info.y - info.x <= (1u << kCacheRelBits);
 }
-
 // record slot `slot` of the association cache: neighbour j's control index relative to run.lo
+// (| bank class << kCacheRelBits)
 __device__ __forceinline__ void cacheStoreNbr(const AssocCache& c, uint64_t slot, int j, uint32_t rel) {
   const uint64_t plane = j < 7 ? 0 : 1;
   c.rec[(plane * c.n_slots + slot) * 8 + (j < 7 ? 1 + j : j - 7)] = static_cast<uint16_t>(rel);

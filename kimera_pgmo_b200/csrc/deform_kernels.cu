@@ -182,7 +182,9 @@ __global__ void buildControlTablesKernel(uint64_t n_c, const double* __restrict_
                                          const double* __restrict__ poses,
                                          float4* __restrict__ ctrl_f4,
                                          float* __restrict__ pose_f32,
-                                         double* __restrict__ pose_rows64, int positions_changed) {
+                                         double* __restrict__ pose_rows64,
+                                         const uint8_t* __restrict__ ctrl_class,
+                                         int positions_changed) {
   const uint64_t j = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (j >= n_c) return;
   const double gx = ctrl_pos[3 * j], gy = ctrl_pos[3 * j + 1], gz = ctrl_pos[3 * j + 2];
@@ -198,8 +200,9 @@ __global__ void buildControlTablesKernel(uint64_t n_c, const double* __restrict_
   o[14] = __double2float_rn(gz);
   o[15] = 0.f;
   if (pose_rows64) {
-    // blend-kernel row: R(9) t(3) g(3) pad as eight 16-byte chunks, chunk c stored at c ^ (j & 7)
-    // so that lanes reading the same chunk of different rows spread over the shared-memory banks
+    // blend-kernel row: R(9) t(3) g(3) pad as eight 16-byte chunks, chunk c stored at
+    // c ^ class so that lanes reading the same chunk of the rows of control points that lie
+    // close together spread over the shared-memory banks
     double row[16];
     for (int i = 0; i < 12; ++i) row[i] = poses ? poses[12 * j + i] : 0.0;
     row[12] = gx;
@@ -207,7 +210,7 @@ __global__ void buildControlTablesKernel(uint64_t n_c, const double* __restrict_
     row[14] = gz;
     row[15] = 0.0;
     double2* dst = reinterpret_cast<double2*>(pose_rows64 + 16 * j);
-    const int sw = static_cast<int>(j & 7);
+    const int sw = ctrl_class ? static_cast<int>(ctrl_class[j] & 7u) : 0;
     for (int c = 0; c < 8; ++c) dst[c ^ sw] = make_double2(row[2 * c], row[2 * c + 1]);
   }
 }
@@ -312,12 +315,13 @@ cudaError_t launchPredeform(uint64_t n_v, uint64_t start_idx, const float* x, co
 
 cudaError_t launchBuildControlTables(uint64_t n_c, const double* ctrl_pos, const double* poses,
                                      float4* ctrl_f4, float* ctrl_pose_f32, double* pose_rows64,
-                                     bool positions_changed, cudaStream_t stream) {
+                                     const uint8_t* ctrl_class, bool positions_changed,
+                                     cudaStream_t stream) {
   if (n_c == 0) return cudaSuccess;
   const unsigned threads = 256;
   buildControlTablesKernel<<<static_cast<unsigned>((n_c + threads - 1) / threads), threads, 0,
                              stream>>>(n_c, ctrl_pos, poses, ctrl_f4, ctrl_pose_f32, pose_rows64,
-                                       positions_changed ? 1 : 0);
+                                       ctrl_class, positions_changed ? 1 : 0);
   return cudaGetLastError();
 }
 

@@ -68,8 +68,9 @@ struct DeformArgs {
 constexpr uint32_t kNoCacheSlot = 0xFFFFFFFFu;
 constexpr int kCacheMaxNbr = 14;  // blended neighbours a record can hold (k <= 13)
 struct AssocCache {
-  // plane 0: {vertex offset inside the item, nbr 0..6}, plane 1: {nbr 7..14}; nbr = control
-  // index - run.lo; slot = local position of the record (item start + rank in search order)
+  // plane 0: {vertex offset inside the item, nbr 0..6}, plane 1: {nbr 7..14}; nbr = (control
+  // index - run.lo) | bank class << 13; slot = local position of the record (item start + rank in
+  // search order)
   uint16_t* rec;       // planes x n_slots x 8
   void* weight;        // w_planes x n_slots, double (FP64 mode) or float (FP32 mode)
   uint32_t w_planes;   // neighbours a record holds weights for (>= max_k + 1)
@@ -77,9 +78,16 @@ struct AssocCache {
   unsigned long long* item_fp;  // per work item: fingerprint of the vertex bits
   uint32_t* item_ok;   // per work item: 1 = records valid for item_fp
   uint32_t* stale_items;  // work items the validating pass rejected (capacity: all items)
-  const void* pose_rows;  // n_c rows: 16 doubles (128 B, 16-byte chunk c stored at c ^ (j & 7))
+  const void* pose_rows;  // n_c rows: 16 doubles (128 B, 16-byte chunk c stored at c ^ class)
                           // or 16 floats (FP32 mode): R(9) t(3) g(3) pad
+  // Bank class (0..7) of every control point's row: a colouring in which points that lie close
+  // together differ (deform_api.cu: colourControls).  The lanes of a quarter warp read rows of
+  // control points that lie close together; different classes put the same chunk of their rows
+  // into different bank groups.
+  const uint8_t* ctrl_class;
 };
+constexpr uint32_t kCacheRelBits = 13;
+constexpr uint32_t kCacheRelMask = (1u << kCacheRelBits) - 1u;
 
 // per-run uniform grid over the run's alive control points (deform_grid.cu)
 constexpr int kGridMaxCells = 1024;
@@ -210,7 +218,8 @@ cudaError_t launchPredeform(uint64_t n_v, uint64_t start_idx, const float* x, co
 // rows of the blend kernel from the f64 tables
 cudaError_t launchBuildControlTables(uint64_t n_c, const double* ctrl_pos, const double* poses,
                                      float4* ctrl_f4, float* ctrl_pose_f32, double* pose_rows64,
-                                     bool positions_changed, cudaStream_t stream);
+                                     const uint8_t* ctrl_class, bool positions_changed,
+                                     cudaStream_t stream);
 // writes del_run into ctrl_f4[].w and the stable keys (after build_schedule)
 cudaError_t launchApplySchedule(uint64_t n_c, const int32_t* del_run, const int32_t* stable_key3,
                                 float4* ctrl_f4, int4* ctrl_key, cudaStream_t stream);

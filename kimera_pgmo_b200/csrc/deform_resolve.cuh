@@ -68,15 +68,16 @@ __device__ __forceinline__ bool aliveInRun(const float4& c, int run) {
 }
 
 // the resolver's neighbour list as an association record (what K3a writes for untied vertices)
-__device__ __forceinline__ void cacheFromResolver(const AssocCache& c, uint32_t slot, uint32_t lo,
-                                                  const float* d2, const int* idx, int n,
-                                                  int precision) {
+__device__ __forceinline__ void cacheFromResolver(const DeformArgs&, const AssocCache& c,
+                                                  uint32_t slot, uint32_t lo, const float* d2,
+                                                  const int* idx, int n, int precision) {
   if (n - 1 > kCacheMaxNbr) return;  // the item is not cacheable (K3b skips it)
   const float d_max_f = __fsqrt_rn(d2[n - 1]);
   const bool const_w = constWeight(d2[0], d_max_f);
   const float inv_dmax = const_w ? 0.0f : __frcp_rn(d_max_f);
   for (int j = 0; j < n - 1; ++j) {
-    cacheStoreNbr(c, slot, j, static_cast<uint32_t>(idx[j]) - lo);
+    cacheStoreNbr(c, slot, j, (static_cast<uint32_t>(idx[j]) - lo) |
+                                  (static_cast<uint32_t>(__ldg(c.ctrl_class + idx[j])) << kCacheRelBits));
     cacheStoreWeight(c, slot, j, precision, weightFp64(d2[j], d_max_f, const_w),
                      weightFp32(d2[j], inv_dmax, const_w));
   }
@@ -361,7 +362,7 @@ __device__ __noinline__ void resolveOne(const DeformArgs& a, const ResolveArgs& 
         }
         writeResult(a, p, ii, precision, qx, qy, qz, d2, idx, static_cast<int>(n_cand));
         if (cache && slot != kNoCacheSlot) {
-          cacheFromResolver(*cache, slot, info.x, d2, idx, static_cast<int>(n_cand), precision);
+          cacheFromResolver(a, *cache, slot, info.x, d2, idx, static_cast<int>(n_cand), precision);
         }
       } else {
         // large-k path: split the struct array into the two views writeResult expects, in place
@@ -374,7 +375,7 @@ __device__ __noinline__ void resolveOne(const DeformArgs& a, const ResolveArgs& 
         }
         writeResult(a, p, ii, precision, qx, qy, qz, d2, idx, static_cast<int>(n_cand));
         if (cache && slot != kNoCacheSlot) {
-          cacheFromResolver(*cache, slot, info.x, d2, idx, static_cast<int>(n_cand), precision);
+          cacheFromResolver(a, *cache, slot, info.x, d2, idx, static_cast<int>(n_cand), precision);
         }
       }
       a.status[p] = kStatusDone;

@@ -403,11 +403,42 @@ __device__ __forceinline__ void searchItem(const DeformArgs& a, const GridArgs& 
   for (int group = s_begin >> 5; group * 32 < s_end; ++group) {
     const int slot = group * 32 + lane;
     const bool active = slot < count;
-    const int v = S.perm[active ? slot : group * 32];  // idle lanes shadow the group's first vertex
-    const float qx = S.vx[v], qy = S.vy[v], qz = S.vz[v];
+    int v = S.perm[active ? slot : group * 32];  // idle lanes shadow the group's first vertex
+    float qx = S.vx[v], qy = S.vy[v], qz = S.vz[v];
     const float lox = warpMinF(qx), hix = warpMaxF(qx);
     const float loy = warpMinF(qy), hiy = warpMaxF(qy);
     const float loz = warpMinF(qz), hiz = warpMaxF(qz);
+#ifndef PGMO_NO_LANE_REGROUP
+    // Lanes regrouped by octant of the group's box (the shortest axis is the lowest key bit, so
+    // that a quarter warp = two octants that differ along it).  Records are written in lane
+    // order: the quarter warps of the blend kernel then read the pose rows of vertices that lie
+    // close together — fewer distinct rows per shared-memory phase.  The search result does not
+    // depend on the lane a vertex sits in.
+    {
+      const float ex = hix - lox, ey = hiy - loy, ez = hiz - loz;
+      const uint32_t bx = qx > 0.5f * (lox + hix) ? 1u : 0u;
+      const uint32_t by = qy > 0.5f * (loy + hiy) ? 1u : 0u;
+      const uint32_t bz = qz > 0.5f * (loz + hiz) ? 1u : 0u;
+      uint32_t key;
+      if (ex <= ey && ex <= ez) key = (ey >= ez ? (by << 2) | (bz << 1) : (bz << 2) | (by << 1)) | bx;
+      else if (ey <= ez) key = (ex >= ez ? (bx << 2) | (bz << 1) : (bz << 2) | (bx << 1)) | by;
+      else key = (ex >= ey ? (bx << 2) | (by << 1) : (by << 2) | (bx << 1)) | bz;
+      if (!active) key = 8u;
+      uint32_t rank = __popc(__match_any_sync(full, key) & lt_mask);
+#pragma unroll
+      for (uint32_t c = 0; c < 8; ++c) {
+        const unsigned m = __ballot_sync(full, key == c);
+        rank += key > c ? __popc(m) : 0;
+      }
+      __syncwarp();
+      if (active) S.perm[group * 32 + rank] = static_cast<uint16_t>(v);
+      __syncwarp();
+      v = S.perm[active ? slot : group * 32];
+      qx = S.vx[v];
+      qy = S.vy[v];
+      qz = S.vz[v];
+    }
+#endif
 
     // lower bound (with head room for the separately rounded exact d^2 of every lane) of the
     // squared distance between near point i and the group's box
@@ -514,17 +545,20 @@ __device__ __forceinline__ void searchItem(const DeformArgs& a, const GridArgs& 
     const uint64_t p = p_base + v;
     float nbr_d2[KCAP];
     int nbr_idx[KCAP];
+    uint32_t nbr_cls[KCAP];  // bank class of the neighbour's pose row (deform_blend.cu)
     bool near_tie = false;   // two winners agree above the ordinal bits
     bool near_last = false;  // ... and one of them is the last tracked slot
 #pragma unroll
     for (int i = 0; i < KCAP; ++i) {
       nbr_d2[i] = FLT_MAX;
       nbr_idx[i] = -1;
+      nbr_cls[i] = 0u;
       if (i < n_need) {
         const int slot_i = list[best[i] & ord_mask];
         const float4 c = S.pts[slot_i];
         nbr_d2[i] = dist2Exact(c.x, c.y, c.z, qx, qy, qz);
         nbr_idx[i] = __float_as_int(c.w);
+        nbr_cls[i] = __ldg(cache.ctrl_class + nbr_idx[i]);
       }
       if (i > 0 && i < n_need && (best[i] >> ord_bits) == (best[i - 1] >> ord_bits)) {
         near_tie = true;
@@ -568,6 +602,9 @@ __device__ __forceinline__ void searchItem(const DeformArgs& a, const GridArgs& 
             const int ti = nbr_idx[i];
             nbr_idx[i] = nbr_idx[i - 1];
             nbr_idx[i - 1] = ti;
+            const uint32_t tc = nbr_cls[i];
+            nbr_cls[i] = nbr_cls[i - 1];
+            nbr_cls[i - 1] = tc;
           }
         }
       }
@@ -580,7 +617,9 @@ __device__ __forceinline__ void searchItem(const DeformArgs& a, const GridArgs& 
     const uint64_t rec_slot = p_base + static_cast<uint64_t>(slot);
     uint32_t rel[KCAP];
 #pragma unroll
-    for (int j = 0; j < KCAP; ++j) rel[j] = (j < n - 1) ? static_cast<uint32_t>(nbr_idx[j]) - info.x : 0u;
+    for (int j = 0; j < KCAP; ++j) {
+      rel[j] = (j < n - 1) ? (static_cast<uint32_t>(nbr_idx[j]) - info.x) | (nbr_cls[j] << kCacheRelBits) : 0u;
+    }
     {
       uint4 rec0;
       rec0.x = static_cast<uint32_t>(v) | (rel[0] << 16);
