@@ -51,6 +51,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-compression", action="store_true")
+    ap.add_argument("--no-config3", action="store_true")
+    ap.add_argument("--config3-vertices-per-robot", type=int, default=25_000_000)
     return ap.parse_args()
 
 
@@ -231,6 +233,8 @@ def run_b200(args):
             raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # staging buffers are allocated below: stay on the CPUs of the GPU's NUMA node from here on
+    numa_node = sharding.gpu_numa_affinity(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -269,6 +273,23 @@ def run_b200(args):
     h.set_controls_device(n_ctrl, d_cpos, d_cst, d_cvalid, d_poses, stream)
     h.set_profiling(True)
     exchange_stretches = sharding.StretchExchange(world, dev)
+    # N > 1: a solve result is written once into rank 0's pose source; after one 1-element
+    # all_reduce (ordering only) every rank's table-build kernel pulls the control-point rows its
+    # slab references straight from rank 0's memory over NVLink — no broadcast of the whole table
+    pose_src = sharding.PoseSource(h, n_ctrl, rank, world, dev) if world > 1 else None
+    sync_flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    ctrl_range = [0, n_ctrl]
+
+    def new_poses(poses):
+        """a new solve result (device tensor, or pinned host tensor on rank 0) reaches every GPU"""
+        if world > 1:
+            pose_src.write(poses, stream)
+            dist.all_reduce(sync_flag)
+            pose_src.pull(ctrl_range[0], ctrl_range[1], stream)
+        elif poses.is_cuda:
+            h.update_poses_device(poses, stream)
+        else:
+            h.update_poses(poses.numpy())
 
     knn_ms, res_ms = [], []
     infos = []
@@ -298,10 +319,8 @@ def run_b200(args):
 
     def step(record=False):
         t0 = time.perf_counter()
-        # 1. a new solve result: poses replicated to every GPU
-        if world > 1:
-            dist.broadcast(d_poses, src=0)
-        h.update_poses_device(d_poses, stream)
+        # 1. a new solve result reaches every GPU
+        new_poses(d_poses)
         t0 = _mark("poses", t0)
         changed = True
         if state["valid"]:
@@ -323,6 +342,9 @@ def run_b200(args):
             t0 = _mark("exchange", t0)
             rc = h.build_schedule(ss, sl, n_total, K_NEIGHBOURS, TOL_T)
             assert rc == 0
+            ctrl_range[:] = h.slab_control_range(first, n_local)
+            if world > 1:  # the tables outside the old range may be stale: one full pull
+                h.update_poses_from_source((pose_src.step - 1) % 2, 0, n_ctrl, stream)
             t0 = _mark("schedule", t0)
             run_slab()
             t0 = _mark("run", t0)
@@ -424,32 +446,36 @@ def run_b200(args):
     # ---- end to end: host buffers in, host buffers out ------------------------------------
     e2e = None
     if not args.no_e2e:
-        h2d = n_local * (12 + 8) + n_ctrl * 96
+        # Host buffers in, host buffers out through the C ABI at every N.  The mesh stamps did not
+        # change since the schedule was built (a new solve moves poses only), so per step the
+        # coordinates go up (12 B / vertex), the poses go up once (rank 0) and the deformed
+        # coordinates come back (12 B / vertex): pgmo_deform_run_host_slab pipelines H2D,
+        # kernels and D2H in slabs of work items.
         d2h = n_local * 12
         if world == 1:
+            h2d = n_local * 12 + n_ctrl * 96
             he = capi.DeformHandle(local_rank)
             he.set_controls(case["ctrl_xyz"], case["ctrl_stamps"], case["valid"], case["poses"])
+            # the first deformMesh on this mesh: stamps go up, the schedule is built
+            rc2 = capi._check(he._lib.pgmo_deform_points(
+                he._h, n_local, capi._ptr(h_in["x"]), capi._ptr(h_in["y"]), capi._ptr(h_in["z"]),
+                capi._ptr(h_stamps), None, 0, K_NEIGHBOURS, TOL_T, precision,
+                capi._ptr(h_out[0]), capi._ptr(h_out[1]), capi._ptr(h_out[2]), None, None, 0,
+                None, None))
+            assert rc2 == 0
 
             def e2e_step():
-                # the reference-facing C-ABI call: pinned host pointers, copies inside
                 he.update_poses(h_poses.numpy())
-                rc2 = capi._check(he._lib.pgmo_deform_points(
-                    he._h, n_local, capi._ptr(h_in["x"]), capi._ptr(h_in["y"]), capi._ptr(h_in["z"]),
-                    capi._ptr(h_stamps), None, 0, K_NEIGHBOURS, TOL_T, precision,
-                    capi._ptr(h_out[0]), capi._ptr(h_out[1]), capi._ptr(h_out[2]), None, None, 0,
-                    None, None))
-                assert rc2 == 0
+                he.run_host_slab(0, n_local, h_in["x"], h_in["y"], h_in["z"], h_out, precision=precision)
+            e2e_api = "pgmo_deform_update_poses + pgmo_deform_run_host_slab (host pointers)"
         else:
+            h2d = n_local * 12 + (n_ctrl * 96 if rank == 0 else 0)
+
             def e2e_step():
-                if rank == 0:
-                    d_poses.copy_(h_poses, non_blocking=True)
-                for k2 in ("x", "y", "z"):
-                    d[k2].copy_(h_in[k2], non_blocking=True)
-                d_stamps.copy_(h_stamps, non_blocking=True)
-                step()
-                for o, ho in zip(d_out, h_out):
-                    ho.copy_(o, non_blocking=True)
-                torch.cuda.synchronize()
+                new_poses(h_poses)  # rank 0: pinned host -> pose source; everybody: sync + pull
+                h.run_host_slab(first, n_local, h_in["x"], h_in["y"], h_in["z"], h_out, precision=precision)
+            e2e_api = ("pgmo_deform_pose_source_write (rank 0) + pgmo_deform_update_poses_from_source + "
+                       "pgmo_deform_run_host_slab (host pointers) per rank")
 
         for _ in range(3):
             e2e_step()
@@ -464,10 +490,13 @@ def run_b200(args):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
+        if world == 1:
+            assert torch.equal(h_out[0], d_out[0].cpu()) and torch.equal(h_out[2], d_out[2].cpu())
         e2e = {"value": n_total / (e2e_ms * 1e-3), "unit": "vertices/s", "ms_per_step": e2e_ms,
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "api": "pgmo_deform_update_poses + pgmo_deform_points (host pointers)" if world == 1
-               else "pinned H2D + pgmo_deform_*_device + pinned D2H per rank"}
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "api": e2e_api,
+               "bytes_note": "per rank (rank 0 also uploads the pose table); the stamps went up with "
+                             "the first deformMesh and are not sent again",
+               "numa_node_of_rank0": numa_node}
 
     # ---- device-resident mesh: the mesh sits in HBM as the compressors keep it
     # ({x, y, z, rgba} records + stamps, pgmo_*_device_view); per step only the new poses go up
@@ -505,6 +534,13 @@ def run_b200(args):
         hr.close()
         del cloud, d_cloud_out, h_cloud
 
+    config3 = None
+    if not args.no_config3:
+        h.close()
+        del d, d_out, d_stamps
+        torch.cuda.empty_cache()
+        config3 = bench_config3(args, world, rank, local_rank, dev, stream, flag_group,
+                                measured_peak_gbs()[0])
     if phases and rank == 0:
         print("phase ms per step:", {k: v / (args.steps + max(args.warmup, 3) + 1) for k, v in phase_ms.items()},
               file=sys.stderr)
@@ -553,7 +589,7 @@ def run_b200(args):
                 },
             },
             "clocks": clocks.summary(),
-            "e2e": e2e, "e2e_resident_mesh": resident,
+            "e2e": e2e, "e2e_resident_mesh": resident, "config3": config3,
             # buildControlTables, K1, K3b (validating), K3a / K4 / K3b over the stale list, done
             "gpu_launches": 7 * args.steps,
             "resolved_by_tie_kernel": int(n_resolved),
@@ -581,6 +617,209 @@ def run_b200(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def bench_config3(args, world, rank, local_rank, dev, stream, flag_group, peak):
+    """BASELINE configs[3]: a 100M-vertex mesh of 4 robots (robot ids 0..3: pose prefixes 'a'..,
+    vertex prefixes 's'.., kimera_pgmo/include/kimera_pgmo/utils/common_functions.h:19-61), one
+    independent deformation problem per robot (own control table, handle and window schedule),
+    the robots' vertices laid end to end and cut into one contiguous slab per rank (STRONG
+    scaling: the total is fixed).  Poses: rank 0's pose source per robot, pulled by the ranks that
+    own a segment of the robot.  Reports the pose-only re-deformation step, the first deformation,
+    shard-count-invariant checksums of the output bits and an oracle comparison at every segment
+    start (swept with a 22-stretch warm-up, see tests/test_full_size_gpu.py)."""
+    import torch
+    import torch.distributed as dist
+
+    from kimera_pgmo_b200 import capi, sharding, synth
+    R, n_v, n_c = 4, args.config3_vertices_per_robot, CTRL_PER_GPU
+    plan = sharding.plan_segments([n_v] * R, world)
+    mine = plan[rank]
+    precision = capi.FP64 if args.precision == "fp64" else capi.FP32
+
+    # control tables: generated on rank 0, replicated once by broadcast (positions / stamps /
+    # validity never change afterwards); every rank keeps a handle per robot it owns a segment
+    # of, rank 0 one per robot (it owns every pose source)
+    handles, sources, poses = {}, {}, {}
+    for r in range(R):
+        if rank == 0:
+            c = synth.robot_range(r, n_v, n_c, 0, 0)
+            t = [torch.from_numpy(c["ctrl_xyz"]), torch.from_numpy(c["ctrl_stamps"].view(np.int64)),
+                 torch.from_numpy(c["valid"]), torch.from_numpy(c["poses"])]
+        else:
+            t = [torch.zeros((n_c, 3), dtype=torch.float64), torch.zeros(n_c, dtype=torch.int64),
+                 torch.zeros(n_c, dtype=torch.uint8), torch.zeros((n_c, 12), dtype=torch.float64)]
+        t = [x.to(dev) for x in t]
+        sharding.broadcast_controls(t, src=0)
+        owns = any(seg[0] == r for seg in mine)
+        if owns or rank == 0:
+            hd = capi.DeformHandle(local_rank)
+            hd.set_controls_device(n_c, t[0], t[1], t[2], t[3], stream)
+            handles[r] = hd
+        poses[r] = t[3]
+        if world > 1:
+            # collective over all ranks (handle broadcast); ranks without a handle take part with
+            # a throw-away one so that the calls match
+            hd = handles.get(r)
+            tmp = None
+            if hd is None:
+                tmp = capi.DeformHandle(local_rank)
+                tmp.set_controls_device(n_c, t[0], t[1], t[2], t[3], stream)
+            sources[r] = sharding.PoseSource(hd or tmp, n_c, rank, world, dev)
+            if tmp is not None:
+                sources[r] = None
+                tmp.close()
+    segs = []
+    for r, first, count in mine:
+        case = synth.robot_range(r, n_v, n_c, first, count, with_controls=False)
+        d = {k: torch.from_numpy(case[k]).to(dev) for k in ("x", "y", "z")}
+        d["stamps"] = torch.from_numpy(case["stamps"].view(np.int64)).to(dev)
+        d["out"] = [torch.empty(count, dtype=torch.float32, device=dev) for _ in range(3)]
+        d["range"] = [0, n_c]
+        segs.append((r, first, count, d))
+    exchange = sharding.MultiRobotExchange(R, world, dev)
+    state = {"valid": False, "step": 0}
+    flag = torch.zeros(1, dtype=torch.int32)
+    sync_flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    empty = np.zeros(0, np.uint64)
+
+    def step():
+        # a new solve for every robot
+        if world > 1:
+            buf = state["step"] % 2
+            if rank == 0:
+                for r in range(R):
+                    handles[r].pose_source_write(buf, poses[r], stream)
+            dist.all_reduce(sync_flag)
+            for r, first, count, d in segs:
+                handles[r].update_poses_from_source(buf, d["range"][0], d["range"][1], stream)
+        else:
+            for r in range(R):
+                handles[r].update_poses_device(poses[r], stream)
+        state["step"] += 1
+        changed = True
+        if state["valid"]:
+            for r, first, count, d in segs:
+                handles[r].stamp_check_begin(d["stamps"], count, stream)
+                handles[r].run_device(first, count, d["x"], d["y"], d["z"], *d["out"],
+                                      precision=precision, stream=stream)
+            changed = False
+            for r, _, _, _ in segs:
+                changed = handles[r].stamp_check_finish() or changed
+            if world > 1:
+                flag[0] = int(changed)
+                dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=flag_group)
+                changed = bool(flag[0])
+        if changed:
+            local = {r: (empty, empty) for r in range(R)}
+            for r, first, count, d in segs:
+                local[r] = handles[r].stamp_stretches_device(d["stamps"], count, stream)
+            for r in range(R):
+                gs, gl = exchange(r, *local[r])
+                if any(seg[0] == r for seg in mine):
+                    assert handles[r].build_schedule(gs, gl, n_v, K_NEIGHBOURS, TOL_T) == 0
+            for r, first, count, d in segs:
+                d["range"][:] = handles[r].slab_control_range(first, count)
+                handles[r].run_device(first, count, d["x"], d["y"], d["z"], *d["out"],
+                                      precision=precision, stream=stream)
+            state["valid"] = True
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # two segments of one robot on one rank would share a handle's work items: not with
+    # contiguous slabs (a rank's segments belong to different robots)
+    barrier()
+    t0 = time.perf_counter()
+    step()
+    barrier()
+    first_ms = 1e3 * (time.perf_counter() - t0)
+    for _ in range(3):
+        step()
+    barrier()
+    n_steps = max(3, min(args.steps, 10))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n_steps):
+        step()
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1) / n_steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    # the step when every vertex is searched again (records ignored)
+    for hd in handles.values():
+        hd.set_assoc_cache(False)
+    step()
+    barrier()
+    e0.record()
+    for _ in range(3):
+        step()
+    e1.record()
+    barrier()
+    search_ms = torch.tensor([e0.elapsed_time(e1) / 3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(search_ms, op=dist.ReduceOp.MAX)
+    search_ms = float(search_ms.item())
+
+    # shard-count invariant checksums of the output bits, per robot
+    sums = torch.zeros((R, 2), dtype=torch.int64, device=dev)
+    for r, first, count, d in segs:
+        idx = torch.arange(first + 1, first + count + 1, dtype=torch.int64, device=dev)
+        for a, o in enumerate(d["out"]):
+            bits = o.view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+            sums[r, 0] += bits.sum() * (a + 1)
+            sums[r, 1] += (bits * idx).sum() * (a + 1)  # wraps mod 2^64: position-sensitive
+    if world > 1:
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+
+    # oracle at every segment start (the window state there depends on the earlier stamps: the
+    # oracle sweeps 22 stretches of warm-up first, tests/test_full_size_gpu.py explains why)
+    checked = mismatched = 0
+    if not args.no_cpu_baseline:
+        from oracle import ffi
+        per_kf = -(-n_v // (n_c // 10))
+        for r, first, count, d in segs:
+            s0 = -(-first // per_kf)                     # first stretch that starts in the segment
+            a, c0 = max(s0 - 22, 0) * per_kf, s0 * per_kf
+            b = min(c0 + 2 * per_kf, first + count)
+            if b <= c0:
+                continue
+            ref_case = synth.robot_range(r, n_v, n_c, a, b - a)
+            ref = ffi.deform_points(ref_case["x"], ref_case["y"], ref_case["z"], ref_case["stamps"],
+                                    ref_case["ctrl_xyz"], ref_case["ctrl_stamps"], ref_case["valid"],
+                                    ref_case["poses"], k=K_NEIGHBOURS, tol_t=TOL_T, want_trace=False)
+            for ax_i, ax in enumerate("xyz"):
+                got = d["out"][ax_i][c0 - first:b - first].cpu().numpy()
+                mismatched += int((got.view(np.uint32) != ref[ax][c0 - a:].view(np.uint32)).sum())
+            checked += b - c0
+    tot = torch.tensor([checked, mismatched], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    for hd in handles.values():
+        hd.close()
+    total = R * n_v
+    pulled = sum((d["range"][1] - d["range"][0]) * 96 for _, _, _, d in segs)
+    return {
+        "workload": f"configs[3]: {R} robots x {n_v} vertices, {n_c} control points each, k=4, one "
+                    f"contiguous vertex slab per rank over {world} GPU(s); strong scaling",
+        "n_gpus": world, "scaling": "strong", "ms_per_step": ms, "value": total / (ms * 1e-3),
+        "unit": "vertices/s", "what": "full re-deformation of all robots after a new solve (poses only)",
+        "step_frac_of_hbm_at_32B": BYTES_STEP_PER_VERTEX * total / world / (ms * 1e-3) / 1e9 / peak,
+        "searching_step": {"ms_per_step": search_ms, "value": total / (search_ms * 1e-3),
+                           "what": "the same step with the association records ignored"},
+        "first_step_ms": first_ms,
+        "segments_per_rank": [[list(sg) for sg in pl] for pl in plan],
+        "pose_rows_pulled_bytes_per_step_rank0": int(pulled),
+        "checksums_per_robot": {synth.ROBOT_ID_TO_VERTEX_PREFIX[r]: [int(sums[r, 0]), int(sums[r, 1])]
+                                for r in range(R)},
+        "oracle": {"vertices_checked_at_segment_starts": int(tot[0]),
+                   "output_floats_differing": int(tot[1])},
+    }
+
 
 
 def bench_compression(dev_index, n_messages=200, verts=50_000, with_cpu=True, n_octree=40):

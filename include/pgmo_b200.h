@@ -95,6 +95,35 @@ int pgmo_deform_set_controls_device(pgmo_deform_t* h, uint64_t n_c, const double
 int pgmo_deform_update_poses(pgmo_deform_t* h, const double* poses12);
 int pgmo_deform_update_poses_device(pgmo_deform_t* h, const double* d_poses12, void* stream);
 
+/* --- pose source: one upload per solve, every GPU pulls what it needs ----------------------------
+ * Multi-GPU deformation replicates the optimised poses.  Instead of a broadcast of the
+ * whole table followed by a table-build kernel, one handle OWNS a pose source — two buffers of
+ * n_c x 12 doubles in its device's memory, used alternately so that a new solve can be written
+ * while slower devices still read the previous one — and every handle (the owner included) builds
+ * its derived tables from it with a kernel that reads the source rows directly: a peer device's
+ * memory over NVLink, mapped by CUDA IPC (other process) or peer access (same process).  Only the
+ * rows [row_begin, row_end) the handle's slab references are pulled
+ * (pgmo_deform_slab_control_range).  The caller orders writer and readers (a stream-ordered
+ * collective or an event): readers of buffer b must run after the write of buffer b, and the
+ * write of buffer b after the readers of its previous content.
+ *   create   allocate on the handle's device; ipc_handle64 (optional, 64 bytes) receives the CUDA
+ *            IPC handle for other processes, *d_base (optional) the device pointer for handles of
+ *            the same process
+ *   attach   map the owner's source: pass the IPC handle OR (d_base, owner_device)
+ *   write    owner only: poses12 (host or device memory, n_c x 12 f64) -> buffer, stream-ordered
+ *   update_poses_from_source   as pgmo_deform_update_poses for rows [row_begin, row_end) */
+int pgmo_deform_pose_source_create(pgmo_deform_t* h, uint64_t n_c, void* ipc_handle64,
+                                   const double** d_base);
+int pgmo_deform_pose_source_attach(pgmo_deform_t* h, uint64_t n_c, const void* ipc_handle64,
+                                   const double* d_base, int owner_device);
+int pgmo_deform_pose_source_write(pgmo_deform_t* h, int buffer, const double* poses12, void* stream);
+int pgmo_deform_update_poses_from_source(pgmo_deform_t* h, int buffer, uint64_t row_begin,
+                                         uint64_t row_end, void* stream);
+/* Control-point rows the slab [first_position, first_position + n_local) can reference under the
+ * current schedule: the union of its runs' windows. */
+int pgmo_deform_slab_control_range(pgmo_deform_t* h, uint64_t first_position, uint64_t n_local,
+                                   uint64_t* row_begin, uint64_t* row_end);
+
 /* Forgets the cached window schedule (and the per-run tables built from it), so that the next
  * pgmo_deform_build_schedule / pgmo_deform_points rebuilds it even if nothing changed.  What a
  * caller gets implicitly whenever control positions / stamps / validity or the mesh stamps
@@ -207,6 +236,17 @@ int pgmo_deform_schedule_stats(pgmo_deform_t* h, uint64_t* stats4);
  * [first_position, lo, hi, k, skip] as u64 x 5. */
 int pgmo_deform_schedule_info(pgmo_deform_t* h, uint64_t* n_runs, uint64_t capacity,
                               uint64_t* runs5);
+
+/* Host buffers in, host buffers out for the slab [first_position, first_position + n_local) on the
+ * CURRENT window schedule (pgmo_deform_build_schedule, or the one the last pgmo_deform_points
+ * built): what a caller uses when the mesh stamps did not change since the schedule was built —
+ * the usual re-deformation after a new solve — and what every rank of a sharded job calls on its
+ * slab.  Only the coordinates cross PCIe (12 B per vertex each way instead of 20 + 12); uploads,
+ * kernels and downloads are pipelined in slabs of work items.  x / y / z / out_* are local to the
+ * slab.  Skipped vertices (mesh_deformation.h:184-186) come back with their input coordinates. */
+int pgmo_deform_run_host_slab(pgmo_deform_t* h, uint64_t first_position, uint64_t n_local,
+                              const float* x, const float* y, const float* z, int precision,
+                              float* out_x, float* out_y, float* out_z, uint8_t* processed);
 
 /* DeformationGraph::deformMesh (deformation_graph.cpp:523-559) on a mesh that already lives in
  * HBM as the compressors keep it: n_v vertices as 16-byte records {float x, y, z; uint32 rgba}

@@ -53,6 +53,13 @@ SIGNATURES = {
     "pgmo_deform_drop_schedule": (C.c_int, [_vp]),
     "pgmo_deform_last_timings": (C.c_int, [_vp, _vp, _u64p]),
     "pgmo_deform_set_assoc_cache": (C.c_int, [_vp, C.c_int]),
+    "pgmo_deform_pose_source_create": (C.c_int, [_vp, C.c_uint64, _vp, C.POINTER(_vp)]),
+    "pgmo_deform_pose_source_attach": (C.c_int, [_vp, C.c_uint64, _vp, _vp, C.c_int]),
+    "pgmo_deform_pose_source_write": (C.c_int, [_vp, C.c_int, _vp, _vp]),
+    "pgmo_deform_update_poses_from_source": (C.c_int, [_vp, C.c_int, C.c_uint64, C.c_uint64, _vp]),
+    "pgmo_deform_slab_control_range": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _u64p, _u64p]),
+    "pgmo_deform_run_host_slab": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _vp, _vp, _vp, C.c_int, _vp,
+                                            _vp, _vp, _vp]),
     "pgmo_deform_last_step_info": (C.c_int, [_vp, _vp, _vp]),
     "pgmo_deform_cache_records": (C.c_int, [_vp, _vp, C.c_uint64, _u64p]),
     "pgmo_deform_points": (C.c_int, [_vp, C.c_uint64, _vp, _vp, _vp, _vp, _vp, C.c_uint64,
@@ -215,6 +222,37 @@ class DeformHandle:
 
     def set_profiling(self, enabled=True):
         _check(self._lib.pgmo_deform_set_profiling(self._h, 1 if enabled else 0))
+
+    # --- pose source (multi-GPU pose replication by peer pull) -----------------------------------
+    def pose_source_create(self, n_c):
+        """-> (64-byte CUDA IPC handle, device base pointer)"""
+        handle = np.zeros(64, dtype=np.uint8)
+        base = _vp()
+        _check(self._lib.pgmo_deform_pose_source_create(self._h, n_c, _ptr(handle), C.byref(base)))
+        return handle, int(base.value)
+
+    def pose_source_attach(self, n_c, ipc_handle=None, d_base=None, owner_device=0):
+        _check(self._lib.pgmo_deform_pose_source_attach(
+            self._h, n_c, None if ipc_handle is None else _ptr(np.ascontiguousarray(ipc_handle, dtype=np.uint8)),
+            None if d_base is None else _vp(d_base), owner_device))
+
+    def pose_source_write(self, buffer, poses12, stream=0):
+        _check(self._lib.pgmo_deform_pose_source_write(self._h, buffer, _ptr(poses12), _vp(stream)))
+
+    def update_poses_from_source(self, buffer, row_begin, row_end, stream=0):
+        _check(self._lib.pgmo_deform_update_poses_from_source(self._h, buffer, row_begin, row_end, _vp(stream)))
+
+    def slab_control_range(self, first_position, n_local):
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        _check(self._lib.pgmo_deform_slab_control_range(self._h, first_position, n_local, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
+    def run_host_slab(self, first_position, n_local, x, y, z, out, precision=FP64, processed=None):
+        """pinned / pageable host arrays (numpy or CPU tensors) in and out, current schedule"""
+        ox, oy, oz = out
+        return _check(self._lib.pgmo_deform_run_host_slab(
+            self._h, first_position, n_local, _ptr(x), _ptr(y), _ptr(z), precision, _ptr(ox), _ptr(oy),
+            _ptr(oz), _ptr(processed)))
 
     def set_assoc_cache(self, enabled=True):
         _check(self._lib.pgmo_deform_set_assoc_cache(self._h, 1 if enabled else 0))

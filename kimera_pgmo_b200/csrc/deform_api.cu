@@ -80,6 +80,12 @@ struct pgmo_deform {
   bool last_run_warm = false;
   uint32_t last_run_items = 0;
 
+  // pose source (multi-GPU): the table the solve result is written to once; every device pulls
+  // the rows its slab references from it (2 buffers of n_c x 12 doubles, used alternately)
+  double* pose_src = nullptr;
+  uint64_t pose_src_n = 0;
+  bool pose_src_owned = false, pose_src_ipc = false;
+
   // association cache (deform_blend.cu): records + weights per local position of the slab the
   // work items were cut for, fingerprints per work item.  Valid as long as the items are.
   bool cache_enabled = true;   // false: every call redoes the search (records are scratch)
@@ -516,6 +522,8 @@ void pgmo_deform_destroy(pgmo_deform_t* h) {
   if (h->ev_fp) cudaEventDestroy(h->ev_fp);
   if (h->s_in) cudaStreamDestroy(h->s_in);
   if (h->s_out) cudaStreamDestroy(h->s_out);
+  if (h->pose_src && h->pose_src_owned) cudaFree(h->pose_src);
+  if (h->pose_src && h->pose_src_ipc) cudaIpcCloseMemHandle(h->pose_src);
   delete h;
 }
 
@@ -639,6 +647,120 @@ int pgmo_deform_update_poses_device(pgmo_deform_t* h, const double* d_poses12, v
   PGMO_TRY(h->d_poses.reserve(12 * h->n_c + 12));
   PGMO_CUDA(cudaMemcpyAsync(h->d_poses.ptr, d_poses12, 12 * h->n_c * sizeof(double), cudaMemcpyDeviceToDevice, st));
   PGMO_TRY(finishControls(h, false, st));
+  return PGMO_OK;
+}
+
+int pgmo_deform_pose_source_create(pgmo_deform_t* h, uint64_t n_c, void* ipc_handle64,
+                                   const double** d_base) {
+  PGMO_CHECK_ARG(h != nullptr && n_c > 0);
+  PGMO_TRY(ensureDevice(h->device));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+  if (h->pose_src) {
+    setLastError("pose source already set on this handle");
+    return PGMO_ERR_INVALID;
+  }
+  PGMO_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->pose_src), 2 * 12 * n_c * sizeof(double)));
+  h->pose_src_n = n_c;
+  h->pose_src_owned = true;
+  if (ipc_handle64) {
+    cudaIpcMemHandle_t m;
+    PGMO_CUDA(cudaIpcGetMemHandle(&m, h->pose_src));
+    std::memcpy(ipc_handle64, &m, sizeof(m));
+  }
+  if (d_base) *d_base = h->pose_src;
+  return PGMO_OK;
+}
+
+int pgmo_deform_pose_source_attach(pgmo_deform_t* h, uint64_t n_c, const void* ipc_handle64,
+                                   const double* d_base, int owner_device) {
+  PGMO_CHECK_ARG(h != nullptr && n_c > 0);
+  PGMO_CHECK_ARG((ipc_handle64 != nullptr) != (d_base != nullptr));
+  PGMO_TRY(ensureDevice(h->device));
+  if (h->pose_src) {
+    setLastError("pose source already set on this handle");
+    return PGMO_ERR_INVALID;
+  }
+  if (ipc_handle64) {
+    cudaIpcMemHandle_t m;
+    std::memcpy(&m, ipc_handle64, sizeof(m));
+    void* p = nullptr;
+    PGMO_CUDA(cudaIpcOpenMemHandle(&p, m, cudaIpcMemLazyEnablePeerAccess));
+    h->pose_src = static_cast<double*>(p);
+    h->pose_src_ipc = true;
+  } else {
+    if (owner_device != h->device) {
+      int can = 0;
+      PGMO_CUDA(cudaDeviceCanAccessPeer(&can, h->device, owner_device));
+      if (!can) {
+        setLastError("device %d cannot map the memory of device %d", h->device, owner_device);
+        return PGMO_ERR_UNSUPPORTED;
+      }
+      const cudaError_t e = cudaDeviceEnablePeerAccess(owner_device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+        setLastError("cudaDeviceEnablePeerAccess(%d) -> %s", owner_device, cudaGetErrorString(e));
+        return PGMO_ERR_CUDA;
+      }
+      cudaGetLastError();  // clear "already enabled"
+    }
+    h->pose_src = const_cast<double*>(d_base);
+  }
+  h->pose_src_n = n_c;
+  return PGMO_OK;
+}
+
+int pgmo_deform_pose_source_write(pgmo_deform_t* h, int buffer, const double* poses12, void* stream) {
+  PGMO_CHECK_ARG(h != nullptr && poses12 != nullptr && (buffer == 0 || buffer == 1));
+  PGMO_TRY(ensureDevice(h->device));
+  if (!h->pose_src || !h->pose_src_owned) {
+    setLastError("pose_source_write: this handle does not own a pose source");
+    return PGMO_ERR_INVALID;
+  }
+  PGMO_CUDA(cudaMemcpyAsync(h->pose_src + static_cast<uint64_t>(buffer) * 12 * h->pose_src_n, poses12,
+                            12 * h->pose_src_n * sizeof(double), cudaMemcpyDefault, pick(h, stream)));
+  return PGMO_OK;
+}
+
+int pgmo_deform_update_poses_from_source(pgmo_deform_t* h, int buffer, uint64_t row_begin,
+                                         uint64_t row_end, void* stream) {
+  PGMO_CHECK_ARG(h != nullptr && (buffer == 0 || buffer == 1));
+  PGMO_TRY(ensureDevice(h->device));
+  if (!h->pose_src || h->pose_src_n != h->n_c) {
+    setLastError("update_poses_from_source: no pose source for %llu control points",
+                 static_cast<unsigned long long>(h->n_c));
+    return PGMO_ERR_INVALID;
+  }
+  PGMO_CHECK_ARG(row_begin <= row_end && row_end <= h->n_c);
+  cudaStream_t st = pick(h, stream);
+  h->has_poses = true;
+  PGMO_TRY(h->d_poses.reserve(12 * h->n_c + 12));
+  PGMO_TRY(h->d_pose_f32.reserve(16 * h->n_c + 16));
+  PGMO_TRY(h->d_pose_rows.reserve(16 * h->n_c + 16));
+  PGMO_CUDA(launchPullBuildPoseTables(row_begin, row_end,
+                                      h->pose_src + static_cast<uint64_t>(buffer) * 12 * h->pose_src_n,
+                                      h->d_poses.ptr, h->d_pos.ptr, h->d_pose_f32.ptr,
+                                      h->d_pose_rows.ptr, h->d_class.ptr, st));
+  return PGMO_OK;
+}
+
+int pgmo_deform_slab_control_range(pgmo_deform_t* h, uint64_t first_position, uint64_t n_local,
+                                   uint64_t* row_begin, uint64_t* row_end) {
+  PGMO_CHECK_ARG(h != nullptr && row_begin != nullptr && row_end != nullptr);
+  if (!h->sched_ready) {
+    setLastError("slab_control_range: no schedule");
+    return PGMO_ERR_INVALID;
+  }
+  const auto& runs = h->sched.runs;
+  uint64_t lo = ~0ull, hi = 0;
+  const uint64_t slab_end = first_position + n_local;
+  for (size_t r = 0; r < runs.size(); ++r) {
+    const uint64_t run_end = r + 1 < runs.size() ? runs[r + 1].first_position : h->sched.total_positions;
+    if (run_end <= first_position || runs[r].first_position >= slab_end || runs[r].skip) continue;
+    lo = std::min<uint64_t>(lo, runs[r].lo);
+    hi = std::max<uint64_t>(hi, runs[r].hi);
+  }
+  if (lo > hi) lo = hi = 0;
+  *row_begin = lo;
+  *row_end = hi;
   return PGMO_OK;
 }
 
@@ -1017,6 +1139,72 @@ static int runDeviceRange(pgmo_deform_t* h, uint64_t first_position, uint64_t n_
   return PGMO_OK;
 }
 
+// Vertex streams up in kPipe chunks on the copy stream, one event per chunk.
+static int queueVertexUpload(pgmo_deform_t* h, uint64_t n_v, const float* x, const float* y,
+                             const float* z, cudaStream_t up, uint64_t* chunk_end) {
+  const int n_chunks = pgmo_deform::kPipe;
+  for (int c = 0; c < n_chunks; ++c) {
+    const uint64_t b = n_v * static_cast<uint64_t>(c) / n_chunks;
+    const uint64_t e = n_v * static_cast<uint64_t>(c + 1) / n_chunks;
+    chunk_end[c] = e;
+    if (e > b) {
+      PGMO_CUDA(cudaMemcpyAsync(h->d_x.ptr + b, x + b, (e - b) * sizeof(float), cudaMemcpyHostToDevice, up));
+      PGMO_CUDA(cudaMemcpyAsync(h->d_y.ptr + b, y + b, (e - b) * sizeof(float), cudaMemcpyHostToDevice, up));
+      PGMO_CUDA(cudaMemcpyAsync(h->d_z.ptr + b, z + b, (e - b) * sizeof(float), cudaMemcpyHostToDevice, up));
+    }
+    PGMO_CUDA(cudaEventRecord(h->ev_in[c], up));
+  }
+  return PGMO_OK;
+}
+
+// Pipelined host path: vertex chunks arrive on the copy stream (queueVertexUpload), slabs of work
+// items are deformed on the compute stream as soon as their last chunk is in and downloaded on a
+// second copy stream, so that H2D, kernels and D2H overlap (PCIe is full duplex).
+static int runPipelined(pgmo_deform_t* h, uint64_t first_position, uint64_t n_pos, int precision,
+                        float* out_x, float* out_y, float* out_z, uint8_t* processed,
+                        const uint64_t* chunk_end) {
+  cudaStream_t st = h->stream;
+  const int n_chunks = pgmo_deform::kPipe;
+  PGMO_TRY(h->d_status.reserve(n_pos));
+  PGMO_TRY(ensureItems(h, first_position, n_pos, st));
+  const int n_slabs = pgmo_deform::kPipe;
+  uint64_t begin = 0;
+  int waited = -1;  // chunks [0, waited] are known to the compute stream
+  for (int sl = 0; sl < n_slabs && begin < n_pos; ++sl) {
+    uint64_t end = n_pos;
+    if (sl + 1 < n_slabs) {
+      // first item starting at or after the ideal cut
+      const uint64_t want = n_pos * static_cast<uint64_t>(sl + 1) / n_slabs;
+      const auto it = std::lower_bound(h->h_items.begin(), h->h_items.end(), want,
+                                       [](const WorkItem& w, uint64_t v) { return w.start < v; });
+      end = it == h->h_items.end() ? n_pos : it->start;
+    }
+    if (end <= begin) continue;
+    const uint64_t cnt = end - begin;
+    int need = 0;
+    while (need + 1 < n_chunks && chunk_end[need] < end) ++need;
+    if (need > waited) {
+      PGMO_CUDA(cudaStreamWaitEvent(st, h->ev_in[need], 0));  // in-order stream: covers <= need
+      waited = need;
+    }
+    PGMO_TRY(runDeviceRange(h, first_position, n_pos, h->d_x.ptr, h->d_y.ptr, h->d_z.ptr, nullptr,
+                            precision, h->d_ox.ptr, h->d_oy.ptr, h->d_oz.ptr, nullptr, nullptr, 0,
+                            nullptr, h->d_status.ptr, nullptr, st, begin, end));
+    PGMO_CUDA(cudaEventRecord(h->ev_done[sl], st));
+    PGMO_CUDA(cudaStreamWaitEvent(h->s_out, h->ev_done[sl], 0));
+    PGMO_CUDA(cudaMemcpyAsync(out_x + begin, h->d_ox.ptr + begin, cnt * sizeof(float), cudaMemcpyDeviceToHost, h->s_out));
+    PGMO_CUDA(cudaMemcpyAsync(out_y + begin, h->d_oy.ptr + begin, cnt * sizeof(float), cudaMemcpyDeviceToHost, h->s_out));
+    PGMO_CUDA(cudaMemcpyAsync(out_z + begin, h->d_oz.ptr + begin, cnt * sizeof(float), cudaMemcpyDeviceToHost, h->s_out));
+    if (processed) {
+      PGMO_CUDA(cudaMemcpyAsync(processed + begin, h->d_status.ptr + begin, cnt, cudaMemcpyDeviceToHost, h->s_out));
+    }
+    begin = end;
+  }
+  PGMO_CUDA(cudaStreamSynchronize(h->s_out));
+  PGMO_CUDA(cudaStreamSynchronize(st));
+  return PGMO_OK;
+}
+
 extern "C" {
 
 int pgmo_deform_run_device(pgmo_deform_t* h, uint64_t first_position, uint64_t n_local,
@@ -1181,16 +1369,12 @@ int pgmo_deform_points(pgmo_deform_t* h, uint64_t n_v, const float* x, const flo
     }
   }
   uint64_t chunk_end[pgmo_deform::kPipe];
-  for (int c = 0; c < n_chunks; ++c) {
-    const uint64_t b = n_v * static_cast<uint64_t>(c) / n_chunks;
-    const uint64_t e = n_v * static_cast<uint64_t>(c + 1) / n_chunks;
-    chunk_end[c] = e;
-    if (e > b) {
-      PGMO_CUDA(cudaMemcpyAsync(h->d_x.ptr + b, x + b, (e - b) * sizeof(float), cudaMemcpyHostToDevice, up));
-      PGMO_CUDA(cudaMemcpyAsync(h->d_y.ptr + b, y + b, (e - b) * sizeof(float), cudaMemcpyHostToDevice, up));
-      PGMO_CUDA(cudaMemcpyAsync(h->d_z.ptr + b, z + b, (e - b) * sizeof(float), cudaMemcpyHostToDevice, up));
-    }
-    if (copy_stream) PGMO_CUDA(cudaEventRecord(h->ev_in[c], up));
+  if (copy_stream) {
+    PGMO_TRY(queueVertexUpload(h, n_v, x, y, z, up, chunk_end));
+  } else {
+    PGMO_CUDA(cudaMemcpyAsync(h->d_x.ptr, x, n_v * sizeof(float), cudaMemcpyHostToDevice, up));
+    PGMO_CUDA(cudaMemcpyAsync(h->d_y.ptr, y, n_v * sizeof(float), cudaMemcpyHostToDevice, up));
+    PGMO_CUDA(cudaMemcpyAsync(h->d_z.ptr, z, n_v * sizeof(float), cudaMemcpyHostToDevice, up));
   }
 
   int rc;
@@ -1216,44 +1400,7 @@ int pgmo_deform_points(pgmo_deform_t* h, uint64_t n_v, const float* x, const flo
   // boundaries are work-item boundaries.
   if (!subset_idx && !any_skip && h->use_grid && !out_xyz_f64 && !assoc && !assoc_cnt &&
       n_pos >= (1u << 18) && copy_stream) {
-    PGMO_TRY(h->d_status.reserve(n_pos));
-    PGMO_TRY(ensureItems(h, 0, n_pos, st));
-    const int n_slabs = pgmo_deform::kPipe;
-    uint64_t begin = 0;
-    int waited = -1;  // chunks [0, waited] are known to the compute stream
-    for (int sl = 0; sl < n_slabs && begin < n_pos; ++sl) {
-      uint64_t end = n_pos;
-      if (sl + 1 < n_slabs) {
-        // first item starting at or after the ideal cut
-        const uint64_t want = n_pos * static_cast<uint64_t>(sl + 1) / n_slabs;
-        const auto it = std::lower_bound(h->h_items.begin(), h->h_items.end(), want,
-                                         [](const WorkItem& w, uint64_t v) { return w.start < v; });
-        end = it == h->h_items.end() ? n_pos : it->start;
-      }
-      if (end <= begin) continue;
-      const uint64_t cnt = end - begin;
-      int need = 0;
-      while (need + 1 < n_chunks && chunk_end[need] < end) ++need;
-      if (need > waited) {
-        PGMO_CUDA(cudaStreamWaitEvent(st, h->ev_in[need], 0));  // in-order stream: covers <= need
-        waited = need;
-      }
-      PGMO_TRY(runDeviceRange(h, 0, n_pos, h->d_x.ptr, h->d_y.ptr, h->d_z.ptr, nullptr, precision,
-                              h->d_ox.ptr, h->d_oy.ptr, h->d_oz.ptr, nullptr, nullptr, 0, nullptr,
-                              h->d_status.ptr, nullptr, st, begin, end));
-      PGMO_CUDA(cudaEventRecord(h->ev_done[sl], st));
-      PGMO_CUDA(cudaStreamWaitEvent(h->s_out, h->ev_done[sl], 0));
-      PGMO_CUDA(cudaMemcpyAsync(out_x + begin, h->d_ox.ptr + begin, cnt * sizeof(float), cudaMemcpyDeviceToHost, h->s_out));
-      PGMO_CUDA(cudaMemcpyAsync(out_y + begin, h->d_oy.ptr + begin, cnt * sizeof(float), cudaMemcpyDeviceToHost, h->s_out));
-      PGMO_CUDA(cudaMemcpyAsync(out_z + begin, h->d_oz.ptr + begin, cnt * sizeof(float), cudaMemcpyDeviceToHost, h->s_out));
-      if (processed) {
-        PGMO_CUDA(cudaMemcpyAsync(processed + begin, h->d_status.ptr + begin, cnt, cudaMemcpyDeviceToHost, h->s_out));
-      }
-      begin = end;
-    }
-    PGMO_CUDA(cudaStreamSynchronize(h->s_out));
-    PGMO_CUDA(cudaStreamSynchronize(st));
-    return PGMO_OK;
+    return runPipelined(h, 0, n_pos, precision, out_x, out_y, out_z, processed, chunk_end);
   }
   // everything else: wait for the whole upload, then one pass on the compute stream
   if (copy_stream) PGMO_CUDA(cudaStreamWaitEvent(st, h->ev_in[n_chunks - 1], 0));
@@ -1316,6 +1463,57 @@ int pgmo_deform_points(pgmo_deform_t* h, uint64_t n_v, const float* x, const flo
   }
   PGMO_CUDA(cudaStreamSynchronize(st));
   return PGMO_OK;
+}
+
+int pgmo_deform_run_host_slab(pgmo_deform_t* h, uint64_t first_position, uint64_t n_local,
+                              const float* x, const float* y, const float* z, int precision,
+                              float* out_x, float* out_y, float* out_z, uint8_t* processed) {
+  PGMO_CHECK_ARG(h != nullptr);
+  PGMO_CHECK_ARG(precision == PGMO_PRECISION_FP64 || precision == PGMO_PRECISION_FP32);
+  PGMO_TRY(ensureDevice(h->device));
+  if (!h->sched_ready) {
+    setLastError("pgmo_deform_run_host_slab: no schedule (call pgmo_deform_build_schedule)");
+    return PGMO_ERR_INVALID;
+  }
+  PGMO_CHECK_ARG(first_position + n_local <= h->sched.total_positions);
+  if (n_local == 0) return PGMO_OK;
+  PGMO_CHECK_ARG(x && y && z && out_x && out_y && out_z);
+  if (!h->s_in || !h->s_out) {
+    setLastError("pgmo_deform_run_host_slab: copy streams unavailable");
+    return PGMO_ERR_CUDA;
+  }
+  PGMO_TRY(h->d_x.reserve(n_local));
+  PGMO_TRY(h->d_y.reserve(n_local));
+  PGMO_TRY(h->d_z.reserve(n_local));
+  PGMO_TRY(h->d_ox.reserve(n_local));
+  PGMO_TRY(h->d_oy.reserve(n_local));
+  PGMO_TRY(h->d_oz.reserve(n_local));
+  uint64_t chunk_end[pgmo_deform::kPipe];
+  PGMO_TRY(queueVertexUpload(h, n_local, x, y, z, h->s_in, chunk_end));
+  bool any_skip = false;
+  for (const ScheduleRun& run : h->sched.runs) any_skip = any_skip || run.skip;
+  if (any_skip || !h->use_grid) {
+    // skipped vertices come back with their input coordinates (the reference's new_points starts
+    // as a copy of the input cloud and `continue`s past them): seed the outputs, then one pass
+    cudaStream_t st = h->stream;
+    PGMO_CUDA(cudaStreamWaitEvent(st, h->ev_in[pgmo_deform::kPipe - 1], 0));
+    PGMO_CUDA(cudaMemcpyAsync(h->d_ox.ptr, h->d_x.ptr, n_local * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    PGMO_CUDA(cudaMemcpyAsync(h->d_oy.ptr, h->d_y.ptr, n_local * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    PGMO_CUDA(cudaMemcpyAsync(h->d_oz.ptr, h->d_z.ptr, n_local * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    PGMO_TRY(h->d_status.reserve(n_local));
+    PGMO_TRY(pgmo_deform_run_device(h, first_position, n_local, h->d_x.ptr, h->d_y.ptr, h->d_z.ptr,
+                                    nullptr, precision, h->d_ox.ptr, h->d_oy.ptr, h->d_oz.ptr, nullptr,
+                                    nullptr, 0, nullptr, h->d_status.ptr, nullptr, st));
+    PGMO_CUDA(cudaMemcpyAsync(out_x, h->d_ox.ptr, n_local * sizeof(float), cudaMemcpyDeviceToHost, st));
+    PGMO_CUDA(cudaMemcpyAsync(out_y, h->d_oy.ptr, n_local * sizeof(float), cudaMemcpyDeviceToHost, st));
+    PGMO_CUDA(cudaMemcpyAsync(out_z, h->d_oz.ptr, n_local * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (processed) {
+      PGMO_CUDA(cudaMemcpyAsync(processed, h->d_status.ptr, n_local, cudaMemcpyDeviceToHost, st));
+    }
+    PGMO_CUDA(cudaStreamSynchronize(st));
+    return PGMO_OK;
+  }
+  return runPipelined(h, first_position, n_local, precision, out_x, out_y, out_z, processed, chunk_end);
 }
 
 int pgmo_deform_mesh_device(pgmo_deform_t* h, uint64_t n_v, const void* d_vertices_xyzw,

@@ -215,6 +215,46 @@ __global__ void buildControlTablesKernel(uint64_t n_c, const double* __restrict_
   }
 }
 
+// Pose rows [row_begin, row_end) pulled from `src` — the table one device received the solve
+// result in, possibly a PEER device's memory mapped over NVLink — and turned into this device's
+// tables in the same kernel: the local f64 copy (tie resolver, grid-walk kernel), the f32 rows
+// and the chunk-swizzled f64 rows of the blend kernel.  A block takes 128 rows: the 12 x 128
+// doubles are read flat (consecutive threads, consecutive 16-byte words: full NVLink / HBM
+// sectors) into shared memory, then one thread builds one row.
+constexpr int kPullRows = 128;
+__global__ void __launch_bounds__(kPullRows)
+pullBuildPoseTablesKernel(uint64_t row_begin, uint64_t row_end, const double* __restrict__ src,
+                          double* __restrict__ poses_local, const double* __restrict__ ctrl_pos,
+                          float* __restrict__ pose_f32, double* __restrict__ pose_rows64,
+                          const uint8_t* __restrict__ ctrl_class) {
+  __shared__ double2 stage[kPullRows * 6];
+  const uint64_t r0 = row_begin + static_cast<uint64_t>(blockIdx.x) * kPullRows;
+  const uint64_t n_rows = row_end - r0 < static_cast<uint64_t>(kPullRows) ? row_end - r0 : kPullRows;
+  const double2* s2 = reinterpret_cast<const double2*>(src + 12 * r0);     // 96-byte rows: 16-byte aligned
+  double2* l2 = poses_local ? reinterpret_cast<double2*>(poses_local + 12 * r0) : nullptr;
+  for (uint32_t e = threadIdx.x; e < n_rows * 6; e += kPullRows) {
+    const double2 v = s2[e];
+    stage[e] = v;
+    if (l2 && l2 != s2) l2[e] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x >= n_rows) return;
+  const uint64_t j = r0 + threadIdx.x;
+  double row[16];
+  const double* mine = reinterpret_cast<const double*>(stage) + 12 * threadIdx.x;
+  for (int i = 0; i < 12; ++i) row[i] = mine[i];
+  row[12] = ctrl_pos[3 * j];
+  row[13] = ctrl_pos[3 * j + 1];
+  row[14] = ctrl_pos[3 * j + 2];
+  row[15] = 0.0;
+  float* o = pose_f32 + 16 * j;
+  for (int i = 0; i < 15; ++i) o[i] = __double2float_rn(row[i]);
+  o[15] = 0.f;
+  double2* dst = reinterpret_cast<double2*>(pose_rows64 + 16 * j);
+  const int sw = ctrl_class ? static_cast<int>(ctrl_class[j] & 7u) : 0;
+  for (int c = 0; c < 8; ++c) dst[c ^ sw] = make_double2(row[2 * c], row[2 * c + 1]);
+}
+
 __global__ void applyScheduleKernel(uint64_t n_c, const int32_t* __restrict__ del_run,
                                     const int32_t* __restrict__ stable_key3,
                                     float4* __restrict__ ctrl_f4, int4* __restrict__ ctrl_key) {
@@ -322,6 +362,17 @@ cudaError_t launchBuildControlTables(uint64_t n_c, const double* ctrl_pos, const
   buildControlTablesKernel<<<static_cast<unsigned>((n_c + threads - 1) / threads), threads, 0,
                              stream>>>(n_c, ctrl_pos, poses, ctrl_f4, ctrl_pose_f32, pose_rows64,
                                        ctrl_class, positions_changed ? 1 : 0);
+  return cudaGetLastError();
+}
+
+cudaError_t launchPullBuildPoseTables(uint64_t row_begin, uint64_t row_end, const double* src,
+                                      double* poses_local, const double* ctrl_pos,
+                                      float* ctrl_pose_f32, double* pose_rows64,
+                                      const uint8_t* ctrl_class, cudaStream_t stream) {
+  if (row_end <= row_begin) return cudaSuccess;
+  const uint64_t blocks = (row_end - row_begin + kPullRows - 1) / kPullRows;
+  pullBuildPoseTablesKernel<<<static_cast<unsigned>(blocks), kPullRows, 0, stream>>>(
+      row_begin, row_end, src, poses_local, ctrl_pos, ctrl_pose_f32, pose_rows64, ctrl_class);
   return cudaGetLastError();
 }
 

@@ -220,6 +220,12 @@ cudaError_t launchBuildControlTables(uint64_t n_c, const double* ctrl_pos, const
                                      float4* ctrl_f4, float* ctrl_pose_f32, double* pose_rows64,
                                      const uint8_t* ctrl_class, bool positions_changed,
                                      cudaStream_t stream);
+// Rows [row_begin, row_end) of the pose table `src` (local or a peer device's memory) -> this
+// device's f64 copy (poses_local, may be null or == src), f32 rows and swizzled f64 rows.
+cudaError_t launchPullBuildPoseTables(uint64_t row_begin, uint64_t row_end, const double* src,
+                                      double* poses_local, const double* ctrl_pos,
+                                      float* ctrl_pose_f32, double* pose_rows64,
+                                      const uint8_t* ctrl_class, cudaStream_t stream);
 // writes del_run into ctrl_f4[].w and the stable keys (after build_schedule)
 cudaError_t launchApplySchedule(uint64_t n_c, const int32_t* del_run, const int32_t* stable_key3,
                                 float4* ctrl_f4, int4* ctrl_key, cudaStream_t stream);

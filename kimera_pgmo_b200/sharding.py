@@ -132,6 +132,78 @@ class MultiRobotExchange:
                                np.ascontiguousarray(sl, dtype=np.uint64))
 
 
+class PoseSource:
+    """Replication of a solve result by peer pull (pgmo_deform_pose_source_*): the owner rank
+    writes the new poses once into its device's source table (two buffers, used alternately);
+    after one stream-ordered synchronisation (any collective the caller already runs, e.g. a
+    1-element all_reduce) every rank's table-build kernel reads the rows its slab references
+    straight from the owner's memory over NVLink (CUDA IPC mapping).  `handle` is this rank's
+    DeformHandle for the control table in question."""
+
+    def __init__(self, handle, n_c: int, rank: int, world: int, device, owner: int = 0):
+        import torch
+        self.h, self.n_c, self.rank, self.world, self.owner = handle, n_c, rank, world, owner
+        self.step = 0
+        ipc = torch.zeros(64, dtype=torch.uint8, device=device)
+        if rank == owner:
+            handle_bytes, _ = handle.pose_source_create(n_c)
+            ipc.copy_(torch.from_numpy(handle_bytes))
+        if world > 1:
+            import torch.distributed as dist
+            dist.broadcast(ipc, src=owner)
+            if rank != owner:
+                handle.pose_source_attach(n_c, ipc_handle=ipc.cpu().numpy())
+
+    def write(self, poses, stream=0):
+        """owner: poses (device tensor, or pinned host tensor / array) -> the buffer of this step"""
+        if self.rank == self.owner:
+            self.h.pose_source_write(self.step % 2, poses, stream)
+
+    def pull(self, row_begin: int, row_end: int, stream=0):
+        """every rank, after the synchronisation that follows write()"""
+        self.h.update_poses_from_source(self.step % 2, row_begin, row_end, stream)
+        self.step += 1
+
+
+def gpu_numa_affinity(device_index: int):
+    """Pins the calling process to the CPUs of the NUMA node the GPU hangs off (so that the
+    staging buffers it allocates next are local to the GPU's PCIe root).  Returns the node id, or
+    None when the topology cannot be read."""
+    import os
+    try:
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            phys = device_index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                ids = [v for v in vis.split(",") if v.strip() != ""]
+                if device_index < len(ids) and ids[device_index].strip().isdigit():
+                    phys = int(ids[device_index])
+            bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(phys)).busId
+            bus = bus.decode() if isinstance(bus, bytes) else bus
+            dom, rest = bus.split(":", 1)
+            bdf = f"{int(dom, 16):04x}:{rest.lower()}"
+        except Exception:
+            import torch
+            p = torch.cuda.get_device_properties(device_index)
+            bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.extend(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def broadcast_controls(tensors, src: int = 0):
     """Replicates the control table / poses (device or CPU tensors) from `src` to every rank."""
     import torch.distributed as dist
