@@ -52,6 +52,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-compression", action="store_true")
     ap.add_argument("--no-config3", action="store_true")
+    ap.add_argument("--only-config3", action="store_true")
     ap.add_argument("--config3-vertices-per-robot", type=int, default=25_000_000)
     return ap.parse_args()
 
@@ -233,12 +234,26 @@ def run_b200(args):
             raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # One explicit stream for everything: torch's copies, the NCCL waits torch inserts and the
+    # library's kernels (a NULL stream would select the handle's own stream, which is not
+    # ordered with torch's default stream).
+    torch.cuda.set_stream(torch.cuda.Stream(dev))
     # staging buffers are allocated below: stay on the CPUs of the GPU's NUMA node from here on
     numa_node = sharding.gpu_numa_affinity(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
+    if args.only_config3:
+        flag_group = dist.new_group(backend="gloo") if world > 1 else None
+        c3 = bench_config3(args, world, rank, local_rank, dev, torch.cuda.current_stream().cuda_stream,
+                           flag_group, measured_peak_gbs()[0])
+        if rank == 0:
+            print(json.dumps({"config3": c3}))
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     n_local = args.vertices_per_gpu
     n_total = n_local * world
     n_ctrl = CTRL_PER_GPU * world
@@ -765,6 +780,11 @@ def bench_config3(args, world, rank, local_rank, dev, stream, flag_group, peak):
         dist.all_reduce(search_ms, op=dist.ReduceOp.MAX)
     search_ms = float(search_ms.item())
 
+    if os.environ.get("PGMO_BENCH_DEBUG"):
+        for r, first, count, d in segs:
+            print(f"[config3 debug] rank {rank} robot {r} first {first} count {count} range {d['range']} "
+                  f"info {handles[r].last_step_info()} out0 {d['out'][0][:4].tolist()} "
+                  f"in0 {d['x'][:4].tolist()}", file=sys.stderr, flush=True)
     # shard-count invariant checksums of the output bits, per robot
     sums = torch.zeros((R, 2), dtype=torch.int64, device=dev)
     for r, first, count, d in segs:
