@@ -261,6 +261,33 @@ int pgmo_deform_mesh_device(pgmo_deform_t* h, uint64_t n_v, const void* d_vertic
                             void* d_out_xyzw, uint8_t* d_processed, uint64_t* n_resolved,
                             void* stream);
 
+/* --- every visible GPU behind one call ----------------------------------------------------------
+ * A group is DeformationGraph's mesh path over several devices of one box from one host thread's
+ * point of view (inside a call the library runs one host thread per device): contiguous vertex
+ * slabs, control positions / stamps / validity replicated from the host, the poses written once
+ * into device 0's pose source and pulled over NVLink by the other devices' table-build kernels
+ * (devices that cannot map device 0 get them from the host), stamp-stretch lists merged so that
+ * every device replays the same window schedule.  Results are bit-identical to one device.
+ *   create   devices = NULL, n_devices = 0: every visible device
+ *   points   as pgmo_deform_points without indices / association outputs
+ *   repeat   the same mesh stamps as the last `points` call (a new solve: set_controls or
+ *            update_poses in between): only coordinates cross PCIe */
+typedef struct pgmo_deform_group pgmo_deform_group_t;
+int pgmo_deform_group_create(int n_devices, const int* devices, pgmo_deform_group_t** out);
+void pgmo_deform_group_destroy(pgmo_deform_group_t* g);
+int pgmo_deform_group_size(pgmo_deform_group_t* g);
+int pgmo_deform_group_set_controls(pgmo_deform_group_t* g, uint64_t n_c, const double* pos_xyz,
+                                   const uint64_t* stamps_ns, const uint8_t* valid,
+                                   const double* poses12);
+int pgmo_deform_group_update_poses(pgmo_deform_group_t* g, const double* poses12);
+int pgmo_deform_group_points(pgmo_deform_group_t* g, uint64_t n_v, const float* x, const float* y,
+                             const float* z, const uint64_t* stamps_ns, uint32_t k, double tol_t,
+                             int precision, float* out_x, float* out_y, float* out_z,
+                             uint8_t* processed);
+int pgmo_deform_group_repeat(pgmo_deform_group_t* g, uint64_t n_v, const float* x, const float* y,
+                             const float* z, int precision, float* out_x, float* out_y,
+                             float* out_z, uint8_t* processed);
+
 /* KimeraPgmoMesh wire format (kimera_pgmo_msgs/msg/KimeraPgmoMesh.msg) <-> device cloud, i.e.
  * conversions::fillFromMsg / fillMsg (kimera_pgmo_ros/.../conversion/mesh_conversion.h:69-199) on
  * the GPU.  Host arrays are the message's own vectors: vertices_xyz = geometry_msgs/Point[]

@@ -62,6 +62,14 @@ SIGNATURES = {
                                             _vp, _vp, _vp]),
     "pgmo_deform_last_step_info": (C.c_int, [_vp, _vp, _vp]),
     "pgmo_deform_cache_records": (C.c_int, [_vp, _vp, C.c_uint64, _u64p]),
+    "pgmo_deform_group_create": (C.c_int, [C.c_int, _vp, C.POINTER(_vp)]),
+    "pgmo_deform_group_destroy": (None, [_vp]),
+    "pgmo_deform_group_size": (C.c_int, [_vp]),
+    "pgmo_deform_group_set_controls": (C.c_int, [_vp, C.c_uint64, _vp, _vp, _vp, _vp]),
+    "pgmo_deform_group_update_poses": (C.c_int, [_vp, _vp]),
+    "pgmo_deform_group_points": (C.c_int, [_vp, C.c_uint64, _vp, _vp, _vp, _vp, C.c_uint32, C.c_double,
+                                           C.c_int, _vp, _vp, _vp, _vp]),
+    "pgmo_deform_group_repeat": (C.c_int, [_vp, C.c_uint64, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp]),
     "pgmo_deform_points": (C.c_int, [_vp, C.c_uint64, _vp, _vp, _vp, _vp, _vp, C.c_uint64,
                                      C.c_uint32, C.c_double, C.c_int, _vp, _vp, _vp, _vp, _vp,
                                      C.c_uint32, _vp, _vp]),
@@ -409,6 +417,60 @@ class DeformHandle:
                                                start_idx, _ptr(ox), _ptr(oy), _ptr(oz),
                                                _ptr(to_deform), C.byref(n_to)))
         return to_deform[: n_to.value].copy()
+
+
+class DeformGroup:
+    """pgmo_deform_group_t: the deformation path over several GPUs of one box from one call."""
+
+    def __init__(self, devices=None):
+        self._lib = load()
+        g = _vp()
+        if devices is None:
+            _check(self._lib.pgmo_deform_group_create(0, None, C.byref(g)))
+        else:
+            d = np.ascontiguousarray(devices, dtype=np.int32)
+            _check(self._lib.pgmo_deform_group_create(d.shape[0], _ptr(d), C.byref(g)))
+        self._g = g
+
+    def close(self):
+        if getattr(self, "_g", None):
+            self._lib.pgmo_deform_group_destroy(self._g)
+            self._g = None
+
+    def __del__(self):
+        self.close()
+
+    def size(self):
+        return int(self._lib.pgmo_deform_group_size(self._g))
+
+    def set_controls(self, pos_xyz, stamps_ns, valid, poses12):
+        pos = np.ascontiguousarray(pos_xyz, dtype=np.float64).reshape(-1, 3)
+        st = None if stamps_ns is None else np.ascontiguousarray(stamps_ns, dtype=np.uint64)
+        va = None if valid is None else np.ascontiguousarray(valid, dtype=np.uint8)
+        po = np.ascontiguousarray(poses12, dtype=np.float64).reshape(-1, 12)
+        _check(self._lib.pgmo_deform_group_set_controls(self._g, pos.shape[0], _ptr(pos), _ptr(st), _ptr(va),
+                                                        _ptr(po)))
+
+    def update_poses(self, poses12):
+        po = np.ascontiguousarray(poses12, dtype=np.float64).reshape(-1, 12)
+        _check(self._lib.pgmo_deform_group_update_poses(self._g, _ptr(po)))
+
+    def deform_points(self, x, y, z, stamps_ns, k=4, tol_t=10.0, precision=FP64, out=None):
+        n_v = x.shape[0]
+        ox, oy, oz = out if out is not None else (np.array(x, copy=True), np.array(y, copy=True), np.array(z, copy=True))
+        processed = np.zeros(n_v, dtype=np.uint8)
+        rc = _check(self._lib.pgmo_deform_group_points(
+            self._g, n_v, _ptr(x), _ptr(y), _ptr(z), _ptr(stamps_ns), k, float(tol_t), precision, _ptr(ox),
+            _ptr(oy), _ptr(oz), _ptr(processed)))
+        return dict(rc=rc, x=ox, y=oy, z=oz, processed=processed)
+
+    def repeat(self, x, y, z, precision=FP64, out=None):
+        n_v = x.shape[0]
+        ox, oy, oz = out if out is not None else (np.array(x, copy=True), np.array(y, copy=True), np.array(z, copy=True))
+        processed = np.zeros(n_v, dtype=np.uint8)
+        rc = _check(self._lib.pgmo_deform_group_repeat(self._g, n_v, _ptr(x), _ptr(y), _ptr(z), precision,
+                                                       _ptr(ox), _ptr(oy), _ptr(oz), _ptr(processed)))
+        return dict(rc=rc, x=ox, y=oy, z=oz, processed=processed)
 
 
 def _flatten_blocks(block_idx, offsets, xyz, rgba):

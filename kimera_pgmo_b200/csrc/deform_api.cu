@@ -1718,3 +1718,251 @@ int pgmo_deform_predeform(pgmo_deform_t* h, uint64_t n_v, const float* x, const 
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------
+// Multi-GPU group: DeformationGraph::deformMesh over every visible device from ONE call.
+// One process, one host thread per device inside a call: contiguous vertex slabs,
+// control positions / stamps / validity replicated from the host, poses written once into
+// device 0's pose source and pulled over NVLink by every other device's table-build kernel, the
+// slabs' stamp-stretch lists merged on the host so that every device replays the same window
+// schedule.  No vertex data moves between devices.
+#include <thread>
+
+struct pgmo_deform_group {
+  std::vector<int> devices;
+  std::vector<pgmo_deform_t*> h;
+  bool peer_pull = false;      // every device maps device 0's pose source
+  uint64_t source_n = 0;
+  int buffer = 0;              // pose-source buffer holding the current solve
+  std::vector<double> poses;   // host copy for devices that cannot map device 0 (no peer access)
+  uint64_t n_v = 0;            // mesh of the cached schedule (pgmo_deform_group_repeat)
+  bool ready = false;
+};
+
+namespace {
+
+template <typename Fn>
+int forEachDevice(pgmo_deform_group* g, Fn&& fn) {
+  const size_t n = g->h.size();
+  std::vector<int> rc(n, PGMO_OK);
+  std::vector<std::string> err(n);
+  auto body = [&](size_t r) {
+    rc[r] = fn(r);
+    if (rc[r] < 0) err[r] = pgmo_last_error();  // thread-local: carry it to the caller's thread
+  };
+  std::vector<std::thread> pool;
+  for (size_t r = 1; r < n; ++r) pool.emplace_back(body, r);
+  body(0);
+  for (std::thread& t : pool) t.join();
+  int worst = PGMO_OK;
+  for (size_t r = 0; r < n; ++r) {
+    if (rc[r] < 0 && worst >= 0) {
+      worst = rc[r];
+      setLastError("device %d: %s", g->devices[r], err[r].c_str());
+    } else if (rc[r] > 0 && worst == PGMO_OK) {
+      worst = rc[r];
+    }
+  }
+  return worst;
+}
+
+void resetPoseSource(pgmo_deform_t* h) {
+  if (!h->pose_src) return;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  if (h->pose_src_owned) cudaFree(h->pose_src);
+  if (h->pose_src_ipc) cudaIpcCloseMemHandle(h->pose_src);
+  h->pose_src = nullptr;
+  h->pose_src_n = 0;
+  h->pose_src_owned = h->pose_src_ipc = false;
+}
+
+// the current solve reaches device r's tables: rows [lo, hi) from the pose source, or the whole
+// table from the host when the device cannot map device 0
+int groupPullPoses(pgmo_deform_group* g, size_t r, uint64_t lo, uint64_t hi) {
+  if (g->peer_pull) return pgmo_deform_update_poses_from_source(g->h[r], g->buffer, lo, hi, nullptr);
+  return pgmo_deform_update_poses(g->h[r], g->poses.data());
+}
+
+int groupWritePoses(pgmo_deform_group* g, const double* poses12, uint64_t n_c) {
+  g->buffer ^= 1;
+  if (g->peer_pull) {
+    pgmo_deform_t* h0 = g->h[0];
+    PGMO_TRY(pgmo_deform_pose_source_write(h0, g->buffer, poses12, nullptr));
+    PGMO_TRY(ensureDevice(h0->device));
+    PGMO_CUDA(cudaStreamSynchronize(h0->stream));  // readers start after this returns
+  } else {
+    g->poses.assign(poses12, poses12 + 12 * n_c);
+  }
+  return PGMO_OK;
+}
+
+// slabs [first, first + count) of n_v vertices
+void groupSlab(const pgmo_deform_group* g, uint64_t n_v, size_t r, uint64_t* first, uint64_t* count) {
+  const uint64_t n = g->h.size();
+  *first = n_v * r / n;
+  *count = n_v * (r + 1) / n - *first;
+}
+
+// pulls + pipelined host pass of every slab on the schedules the handles hold
+int groupRunSlabs(pgmo_deform_group* g, uint64_t n_v, const float* x, const float* y, const float* z,
+                  int precision, float* out_x, float* out_y, float* out_z, uint8_t* processed) {
+  return forEachDevice(g, [&](size_t r) -> int {
+    uint64_t first, count;
+    groupSlab(g, n_v, r, &first, &count);
+    if (count == 0) return PGMO_OK;
+    uint64_t lo = 0, hi = 0;
+    PGMO_TRY(pgmo_deform_slab_control_range(g->h[r], first, count, &lo, &hi));
+    PGMO_TRY(groupPullPoses(g, r, lo, hi));
+    return pgmo_deform_run_host_slab(g->h[r], first, count, x + first, y + first, z + first, precision,
+                                     out_x + first, out_y + first, out_z + first,
+                                     processed ? processed + first : nullptr);
+  });
+}
+
+}  // namespace
+
+extern "C" {
+
+int pgmo_deform_group_create(int n_devices, const int* devices, pgmo_deform_group_t** out) {
+  PGMO_CHECK_ARG(out != nullptr && n_devices >= 0);
+  *out = nullptr;
+  std::vector<int> dev;
+  if (n_devices == 0) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+      cudaGetLastError();
+      setLastError("no CUDA device (there is no CPU fallback)");
+      return PGMO_ERR_NO_DEVICE;
+    }
+    for (int i = 0; i < n; ++i) dev.push_back(i);
+  } else {
+    PGMO_CHECK_ARG(devices != nullptr);
+    dev.assign(devices, devices + n_devices);
+  }
+  pgmo_deform_group* g = new (std::nothrow) pgmo_deform_group();
+  PGMO_CHECK_ARG(g != nullptr);
+  g->devices = dev;
+  for (int d : dev) {
+    pgmo_deform_t* h = nullptr;
+    const int rc = pgmo_deform_create(d, &h);
+    if (rc != PGMO_OK) {
+      for (pgmo_deform_t* p : g->h) pgmo_deform_destroy(p);
+      delete g;
+      return rc;
+    }
+    g->h.push_back(h);
+  }
+  *out = g;
+  return PGMO_OK;
+}
+
+void pgmo_deform_group_destroy(pgmo_deform_group_t* g) {
+  if (!g) return;
+  for (size_t r = g->h.size(); r-- > 0;) pgmo_deform_destroy(g->h[r]);  // owner (0) last
+  delete g;
+}
+
+int pgmo_deform_group_size(pgmo_deform_group_t* g) { return g ? static_cast<int>(g->h.size()) : 0; }
+
+int pgmo_deform_group_set_controls(pgmo_deform_group_t* g, uint64_t n_c, const double* pos_xyz,
+                                   const uint64_t* stamps_ns, const uint8_t* valid,
+                                   const double* poses12) {
+  PGMO_CHECK_ARG(g != nullptr && poses12 != nullptr);
+  // position / stamp / validity: replicated from the host (33 B per control point per device)
+  PGMO_TRY(forEachDevice(g, [&](size_t r) -> int {
+    return pgmo_deform_set_controls(g->h[r], n_c, pos_xyz, stamps_ns, valid, poses12);
+  }));
+  g->ready = false;
+  if (n_c == 0) return PGMO_OK;
+  if (g->source_n != n_c) {  // (re)create the pose source for this table size
+    for (size_t r = g->h.size(); r-- > 0;) resetPoseSource(g->h[r]);
+    g->peer_pull = false;
+    g->source_n = n_c;
+    const double* base = nullptr;
+    if (pgmo_deform_pose_source_create(g->h[0], n_c, nullptr, &base) == PGMO_OK) {
+      bool all = true;
+      for (size_t r = 1; r < g->h.size() && all; ++r) {
+        all = pgmo_deform_pose_source_attach(g->h[r], n_c, nullptr, base, g->devices[0]) == PGMO_OK;
+      }
+      if (all) {
+        g->peer_pull = true;
+      } else {
+        for (size_t r = g->h.size(); r-- > 0;) resetPoseSource(g->h[r]);
+      }
+    }
+  }
+  return groupWritePoses(g, poses12, n_c);
+}
+
+int pgmo_deform_group_update_poses(pgmo_deform_group_t* g, const double* poses12) {
+  PGMO_CHECK_ARG(g != nullptr && poses12 != nullptr);
+  if (g->source_n == 0) {
+    setLastError("pgmo_deform_group_update_poses: no control table");
+    return PGMO_ERR_INVALID;
+  }
+  return groupWritePoses(g, poses12, g->source_n);
+}
+
+int pgmo_deform_group_points(pgmo_deform_group_t* g, uint64_t n_v, const float* x, const float* y,
+                             const float* z, const uint64_t* stamps_ns, uint32_t k, double tol_t,
+                             int precision, float* out_x, float* out_y, float* out_z,
+                             uint8_t* processed) {
+  PGMO_CHECK_ARG(g != nullptr);
+  if (n_v == 0) return PGMO_NOOP;
+  PGMO_CHECK_ARG(x && y && z && out_x && out_y && out_z);
+  g->ready = false;
+  const size_t n = g->h.size();
+  // 1. stamp stretches of every slab (K1 on its device), merged in slab order
+  std::vector<std::vector<uint64_t>> s_stamp(n), s_len(n);
+  if (stamps_ns) {
+    PGMO_TRY(forEachDevice(g, [&](size_t r) -> int {
+      uint64_t first, count;
+      groupSlab(g, n_v, r, &first, &count);
+      if (count == 0) return PGMO_OK;
+      pgmo_deform_t* h = g->h[r];
+      PGMO_TRY(ensureDevice(h->device));
+      PGMO_TRY(h->d_vstamps.reserve(count));
+      PGMO_CUDA(cudaMemcpyAsync(h->d_vstamps.ptr, stamps_ns + first, count * sizeof(uint64_t),
+                                cudaMemcpyHostToDevice, h->stream));
+      return stampStretches(h, h->d_vstamps.ptr, nullptr, count, &s_stamp[r], &s_len[r], h->stream);
+    }));
+  }
+  std::vector<uint64_t> stamp, len;
+  for (size_t r = 0; r < n; ++r) {
+    for (size_t i = 0; i < s_stamp[r].size(); ++i) {
+      if (!stamp.empty() && stamp.back() == s_stamp[r][i]) {
+        len.back() += s_len[r][i];  // a stretch that continues across the slab boundary
+      } else {
+        stamp.push_back(s_stamp[r][i]);
+        len.push_back(s_len[r][i]);
+      }
+    }
+  }
+  // 2. the same window schedule on every device
+  const int rc = forEachDevice(g, [&](size_t r) -> int {
+    return stamps_ns ? pgmo_deform_build_schedule(g->h[r], stamp.size(), stamp.data(), len.data(), n_v, k, tol_t)
+                     : pgmo_deform_build_schedule(g->h[r], 0, nullptr, nullptr, n_v, k, tol_t);
+  });
+  if (rc != PGMO_OK) return rc;  // reference early return (outputs untouched) or error
+  // 3. poses pulled, slabs deformed
+  PGMO_TRY(groupRunSlabs(g, n_v, x, y, z, precision, out_x, out_y, out_z, processed));
+  g->n_v = n_v;
+  g->ready = true;
+  return PGMO_OK;
+}
+
+int pgmo_deform_group_repeat(pgmo_deform_group_t* g, uint64_t n_v, const float* x, const float* y,
+                             const float* z, int precision, float* out_x, float* out_y,
+                             float* out_z, uint8_t* processed) {
+  PGMO_CHECK_ARG(g != nullptr);
+  if (!g->ready || g->n_v != n_v) {
+    setLastError("pgmo_deform_group_repeat: no schedule for a mesh of %llu vertices (call "
+                 "pgmo_deform_group_points first)", static_cast<unsigned long long>(n_v));
+    return PGMO_ERR_INVALID;
+  }
+  PGMO_CHECK_ARG(x && y && z && out_x && out_y && out_z);
+  return groupRunSlabs(g, n_v, x, y, z, precision, out_x, out_y, out_z, processed);
+}
+
+}  // extern "C"
