@@ -14,6 +14,7 @@
 #pragma once
 
 #include <algorithm>
+#include <cstring>
 #include <map>
 #include <numeric>
 
@@ -23,7 +24,11 @@ namespace kimera_pgmo_b200 {
 
 class DeformationGraphMeshPath {
  public:
-  explicit DeformationGraphMeshPath(int device = 0) : device_(device) {}
+  // n_devices: 1 = `device` only (default); 0 = every visible device; n = devices 0 .. n - 1.
+  // With several devices a full deformMesh is sharded by vertex range over all of them
+  // (deformation::Backend); results are bit-identical.
+  explicit DeformationGraphMeshPath(int device = 0, int n_devices = 1)
+      : device_(device), n_devices_(n_devices) {}
 
   // DeformationGraph::addNewMeshNode (deformation_graph.cpp:362-378) appends in index order
   void addControlPoint(char prefix, const gtsam::Point3& position, Timestamp stamp) {
@@ -48,18 +53,34 @@ class DeformationGraphMeshPath {
                               const std::vector<int>& graph_indices, const char& prefix,
                               const gtsam::Values& optimized_values, size_t k = 4,
                               double tol_t = 10.0) {
-    pcl::PointCloud<pcl::PointXYZRGBA> new_vertices;
-    pcl::fromPCLPointCloud2(original_mesh.cloud, new_vertices);
-    deformPoints(new_vertices, new_vertices, stamps, prefix, optimized_values, k, tol_t,
-                 &graph_indices);
     pcl::PolygonMesh new_mesh;
+    detail::BlobCloud in;
+    if (detail::blobView(original_mesh.cloud, &in)) {
+      // The blob already has the layout toPCLPointCloud2 writes for a PointXYZRGBA cloud, so
+      // blob -> cloud -> blob (:540, :557) would change nothing but x / y / z: copy the blob
+      // once (threads) and deform the copy in place through the traits layer.
+      detail::blobCloneShape(original_mesh.cloud, new_mesh.cloud);
+      detail::BlobCloud out;
+      detail::blobView(new_mesh.cloud, &out);
+      detail::parallelFor(in.n, [&](size_t begin, size_t end) {
+        std::memcpy(out.base + begin * out.step, in.base + begin * in.step, (end - begin) * in.step);
+      });
+      in.stamps = &stamps;
+      out.stamps = &stamps;
+      deformPoints(out, in, prefix, optimized_values, k, tol_t, &graph_indices);
+    } else {
+      pcl::PointCloud<pcl::PointXYZRGBA> new_vertices;
+      pcl::fromPCLPointCloud2(original_mesh.cloud, new_vertices);
+      deformPoints(new_vertices, new_vertices, stamps, prefix, optimized_values, k, tol_t,
+                   &graph_indices);
+      pcl::toPCLPointCloud2(new_vertices, new_mesh.cloud);
+    }
     // new_mesh.polygons = original_mesh.polygons (:555), one heap block per face: on a few
     // threads for large meshes
     new_mesh.polygons.resize(original_mesh.polygons.size());
     detail::parallelFor(original_mesh.polygons.size(), [&](size_t begin, size_t end) {
       for (size_t f = begin; f < end; f++) new_mesh.polygons[f] = original_mesh.polygons[f];
     });
-    pcl::toPCLPointCloud2(new_vertices, new_mesh.cloud);
     return new_mesh;
   }
 
@@ -180,7 +201,9 @@ class DeformationGraphMeshPath {
  private:
   deformation::Backend& backend(char prefix) {
     auto it = backends_.find(prefix);
-    if (it == backends_.end()) it = backends_.emplace(prefix, deformation::Backend(device_)).first;
+    if (it == backends_.end()) {
+      it = backends_.emplace(prefix, deformation::Backend(device_, n_devices_)).first;
+    }
     return it->second;
   }
 
@@ -258,6 +281,7 @@ class DeformationGraphMeshPath {
   }
 
   int device_;
+  int n_devices_;
   std::map<char, std::vector<gtsam::Point3>> vertex_positions_;
   std::map<char, std::vector<Timestamp>> vertex_stamps_;
   bool recalculate_vertices_ = false;

@@ -18,8 +18,10 @@
 #pragma once
 
 #include <algorithm>
+#include <cstddef>
 #include <cstdint>
 #include <cstdlib>
+#include <cstring>
 #include <exception>
 #include <new>
 #include <memory>
@@ -139,6 +141,98 @@ class PinnedBlock {
   size_t bytes_ = 0, used_ = 0;
   bool pinned_ = true;
 };
+// The x / y / z of the points inside the byte blob of a pcl::PCLPointCloud2, as a cloud the traits
+// layer understands (ADL customization points below): deformMesh works on the blobs directly
+// instead of converting blob -> PointCloud -> blob (deformation_graph.cpp:540, :557: two copies
+// of 32 B per vertex plus a temporary cloud).
+struct BlobCloud {
+  unsigned char* base = nullptr;  // first point
+  size_t step = 0;                // bytes per point
+  size_t off[3] = {0, 4, 8};      // byte offsets of the float x / y / z inside a point
+  size_t n = 0;
+  const std::vector<Timestamp>* stamps = nullptr;
+};
+inline size_t pgmoNumVertices(const BlobCloud& c) { return c.n; }
+inline traits::Pos pgmoGetVertex(const BlobCloud& c, size_t i, traits::VertexTraits* t) {
+  if (i >= c.n) throw std::out_of_range("pgmo_b200: vertex index past the cloud");  // cloud.at()
+  float v[3];
+  const unsigned char* p = c.base + i * c.step;
+  for (int a = 0; a < 3; ++a) std::memcpy(&v[a], p + c.off[a], sizeof(float));
+  if (t && c.stamps && i < c.stamps->size()) t->stamp = (*c.stamps)[i];
+  return traits::Pos(v[0], v[1], v[2]);
+}
+inline void pgmoSetVertex(BlobCloud& c, size_t i, const traits::Pos& pos, const traits::VertexTraits&) {
+  if (i >= c.n) throw std::out_of_range("pgmo_b200: vertex index past the cloud");
+  unsigned char* p = c.base + i * c.step;
+  const float v[3] = {pos.x(), pos.y(), pos.z()};
+  for (int a = 0; a < 3; ++a) std::memcpy(p + c.off[a], &v[a], sizeof(float));  // colour untouched
+}
+inline Timestamp pgmoGetVertexStamp(const BlobCloud& c, size_t i) { return c.stamps->at(i); }
+
+// Where the points of `blob` are, if the blob has exactly the layout toPCLPointCloud2 gives a
+// PointXYZRGBA cloud (then blob -> cloud -> blob is the identity on everything but x / y / z and
+// the blob can be deformed in place); false: take the generic route.
+#ifdef KIMERA_PGMO_B200_REAL_DEPS
+inline bool blobView(const pcl::PCLPointCloud2& blob, BlobCloud* view) {
+  static const pcl::PCLPointCloud2 canonical = [] {
+    pcl::PCLPointCloud2 c;
+    pcl::toPCLPointCloud2(pcl::PointCloud<pcl::PointXYZRGBA>(), c);
+    return c;
+  }();
+  const size_t n = static_cast<size_t>(blob.width) * blob.height;
+  if (blob.is_bigendian || blob.point_step != canonical.point_step ||
+      blob.fields.size() != canonical.fields.size() || blob.data.size() != n * blob.point_step ||
+      (blob.height > 1 && blob.row_step != blob.width * blob.point_step)) {
+    return false;
+  }
+  int found = 0;
+  for (size_t f = 0; f < blob.fields.size(); ++f) {
+    const auto& a = blob.fields[f];
+    const auto& b = canonical.fields[f];
+    if (a.name != b.name || a.offset != b.offset || a.datatype != b.datatype || a.count != b.count) return false;
+    for (int ax = 0; ax < 3; ++ax) {
+      if (a.name == (ax == 0 ? "x" : ax == 1 ? "y" : "z")) {
+        if (a.datatype != pcl::PCLPointField::FLOAT32) return false;
+        view->off[ax] = a.offset;
+        ++found;
+      }
+    }
+  }
+  if (found != 3) return false;
+  view->base = const_cast<unsigned char*>(blob.data.data());
+  view->step = blob.point_step;
+  view->n = n;
+  return true;
+}
+// `out` = `in` without the point bytes (header, fields, sizes; data sized, contents unspecified)
+inline void blobCloneShape(const pcl::PCLPointCloud2& in, pcl::PCLPointCloud2& out) {
+  out.header = in.header;
+  out.height = in.height;
+  out.width = in.width;
+  out.fields = in.fields;
+  out.is_bigendian = in.is_bigendian;
+  out.point_step = in.point_step;
+  out.row_step = in.row_step;
+  out.is_dense = in.is_dense;
+  out.data.resize(in.data.size());
+}
+#else
+inline bool blobView(const pcl::PCLPointCloud2& blob, BlobCloud* view) {
+  // the stand-in keeps the blob typed: x, y, z lead every record
+  view->base = reinterpret_cast<unsigned char*>(const_cast<pcl::PointXYZRGBA*>(blob.data.data()));
+  view->step = sizeof(pcl::PointXYZRGBA);
+  view->off[0] = offsetof(pcl::PointXYZRGBA, x);
+  view->off[1] = offsetof(pcl::PointXYZRGBA, y);
+  view->off[2] = offsetof(pcl::PointXYZRGBA, z);
+  view->n = blob.data.size();
+  return true;
+}
+inline void blobCloneShape(const pcl::PCLPointCloud2& in, pcl::PCLPointCloud2& out) {
+  out.width = in.width;
+  out.height = in.height;
+  out.data.resize(in.data.size());
+}
+#endif
 }  // namespace detail
 
 namespace deformation {
@@ -147,12 +241,55 @@ namespace deformation {
 // graph (one per prefix); not thread-safe, like the reference's DeformationGraph.
 class Backend {
  public:
-  explicit Backend(int device = 0) {
+  // n_devices: 1 = `device` only; 0 = every visible device; n > 1 = devices 0 .. n - 1.  With more
+  // than one device, full-cloud calls of at least groupMinVertices() vertices that do not ask for
+  // the association map are sharded by vertex range over all of them (pgmo_deform_group_*);
+  // everything else (indices, small clouds, association output) runs on `device`.
+  explicit Backend(int device = 0, int n_devices = 1) {
     pgmo_deform_t* h = nullptr;
     detail::throwOnError(pgmo_deform_create(device, &h));
     handle_.reset(h, [](pgmo_deform_t* p) { pgmo_deform_destroy(p); });
+    const int visible = pgmo_device_count();
+    group_list_.clear();
+    for (int i = 0; i < (n_devices == 0 ? visible : std::min(n_devices, visible)); ++i) group_list_.push_back(i);
+    // test / tuning knob: an explicit device list, e.g. "0,0" = two slabs on one device
+    if (const char* e = std::getenv("KIMERA_PGMO_B200_GROUP_DEVICES")) {
+      if (n_devices != 1) {
+        group_list_.clear();
+        for (const char* p = e; *p;) {
+          char* end = nullptr;
+          const long d = std::strtol(p, &end, 10);
+          if (end == p) break;
+          group_list_.push_back(static_cast<int>(d));
+          p = *end ? end + 1 : end;
+        }
+      }
+    }
+    group_devices_ = static_cast<int>(group_list_.size());
+  }
+  // clouds below this size stay on one device (tuning knob; process-wide)
+  static size_t& groupMinVertices() {
+    static size_t n = size_t(1) << 20;
+    return n;
   }
   pgmo_deform_t* get() const { return handle_.get(); }
+  int groupDevices() const { return group_devices_; }
+  // the device group with the control table of the last setControls (created on first use)
+  pgmo_deform_group_t* group() {
+    if (!group_) {
+      pgmo_deform_group_t* g = nullptr;
+      detail::throwOnError(pgmo_deform_group_create(group_devices_, group_list_.data(), &g));
+      group_.reset(g, [](pgmo_deform_group_t* p) { pgmo_deform_group_destroy(p); });
+      group_stale_ = true;
+    }
+    if (group_stale_) {
+      detail::throwOnError(pgmo_deform_group_set_controls(
+          group_.get(), valid_.size(), pos_.data(), has_stamps_ ? stamps_.data() : nullptr,
+          valid_.data(), poses_.data()));
+      group_stale_ = false;
+    }
+    return group_.get();
+  }
   // page-locked staging shared by the copies of this Backend (calls are serial per Backend)
   kimera_pgmo_b200::detail::PinnedBlock& staging() {
     if (!staging_) staging_ = std::make_shared<kimera_pgmo_b200::detail::PinnedBlock>();
@@ -208,10 +345,20 @@ class Backend {
     }
     detail::throwOnError(pgmo_deform_set_controls(handle_.get(), n_c, pos_.data(), stamps,
                                                   valid_.data(), poses_.data()));
+    if (group_devices_ > 1) {  // the group gets the table when (if) a call is sharded
+      has_stamps_ = stamps != nullptr;
+      if (stamps) stamps_.assign(stamps, stamps + n_c);
+      group_stale_ = true;
+    }
   }
 
  private:
   std::shared_ptr<pgmo_deform_t> handle_;
+  std::shared_ptr<pgmo_deform_group_t> group_;
+  int group_devices_ = 1;
+  std::vector<int> group_list_;
+  bool group_stale_ = true, has_stamps_ = false;
+  std::vector<uint64_t> stamps_;
   std::shared_ptr<kimera_pgmo_b200::detail::PinnedBlock> staging_;
   bool controls_kept_ = false;
   std::vector<double> pos_, poses_;
@@ -267,10 +414,18 @@ void run(Backend& backend, CloudOut& new_points,
   const uint32_t stride = static_cast<uint32_t>(k + 2 > 8 ? k + 2 : 8);
   std::vector<uint32_t> assoc(control_point_map ? n_pos * stride : 0);
   std::vector<uint8_t> cnt(control_point_map ? n_pos : 0);
-  int rc = pgmo_deform_points(backend.get(), n_pos, x, y, z, stamps, nullptr, 0,
-                              static_cast<uint32_t>(k), tol_t, precision, ox, oy, oz, nullptr,
-                              control_point_map ? assoc.data() : nullptr, stride,
-                              control_point_map ? cnt.data() : nullptr, processed);
+  int rc;
+  if (!control_point_map && !indices && backend.groupDevices() > 1 &&
+      n_pos >= Backend::groupMinVertices()) {
+    // vertex slabs over every device of the box; same results, bit for bit
+    rc = pgmo_deform_group_points(backend.group(), n_pos, x, y, z, stamps, static_cast<uint32_t>(k),
+                                  tol_t, precision, ox, oy, oz, processed);
+  } else {
+    rc = pgmo_deform_points(backend.get(), n_pos, x, y, z, stamps, nullptr, 0,
+                            static_cast<uint32_t>(k), tol_t, precision, ox, oy, oz, nullptr,
+                            control_point_map ? assoc.data() : nullptr, stride,
+                            control_point_map ? cnt.data() : nullptr, processed);
+  }
   kimera_pgmo_b200::detail::throwOnError(rc);
   if (rc == PGMO_NOOP) return;  // the reference returned before control_point_map.clear()
   if (!control_point_map) {

@@ -45,7 +45,9 @@ int main(int argc, char** argv) {
     return static_cast<float>(lcg >> 8) / 16777216.0f;
   };
 
-  DeformationGraphMeshPath graph;
+  // PGMO_SHIM_DEVICES: 1 (default) = device 0 only, 0 = every visible device, n = devices 0..n-1
+  const int n_devices = std::getenv("PGMO_SHIM_DEVICES") ? std::atoi(std::getenv("PGMO_SHIM_DEVICES")) : 1;
+  DeformationGraphMeshPath graph(0, n_devices);
   std::vector<gtsam::Point3> ctrl;
   for (size_t j = 0; j < n_c; ++j) {
     double kx, ky;
@@ -147,11 +149,12 @@ int main(int argc, char** argv) {
       "{\"what\": \"DeformationGraphMeshPath::deformMesh through the C++ shim, host wall clock\", "
       "\"vertices\": %zu, \"controls\": %zu, \"k\": 4, \"faces\": %zu, \"first_call_ms\": %.2f, "
       "\"mean_ms\": %.2f, \"best_ms\": %.2f, \"polygon_copy_ms\": %.2f, \"vertices_per_s\": %.4g, "
-      "\"shim_threads\": %d, \"incremental_deformPoints_ms\": %.2f, "
+      "\"shim_threads\": %d, \"devices\": %d, \"incremental_deformPoints_ms\": %.2f, "
       "\"incremental_vertices\": %zu, "
       "\"last_vertex_moved_m\": %.4f}\n",
       n_v, n_c, mesh.polygons.size(), first_ms, mean_ms, best_ms, polygon_copy_ms,
       n_v / (mean_ms * 1e-3),
-      KIMERA_PGMO_B200_SHIM_THREADS, incremental_ms, incremental_vertices, moved);
+      KIMERA_PGMO_B200_SHIM_THREADS, n_devices == 1 ? 1 : (n_devices == 0 ? pgmo_device_count() : n_devices),
+      incremental_ms, incremental_vertices, moved);
   return 0;
 }

@@ -40,7 +40,7 @@ static thread_local const char* g_error = "";
 extern "C" {
 
 const char* pgmo_last_error(void) { return g_error; }
-int pgmo_device_count(void) { return 1; }
+int pgmo_device_count(void) { return 2; }  // lets the shim's device-group path be driven
 uint64_t pgmo_stamp_from_sec(double sec) { return oracle_stamp_from_sec(sec); }
 
 int pgmo_host_alloc(uint64_t bytes, void** out) {
@@ -125,6 +125,34 @@ int pgmo_deform_predeform(pgmo_deform_t* h, uint64_t n_v, const float* x, const 
   }
   *n_to_deform = n_to;
   return PGMO_OK;
+}
+
+// pgmo_deform_group_*: the double deforms the whole cloud in one go (what the real group's slabs
+// add up to), so that the shim's routing and argument handling are exercised without a device
+struct pgmo_deform_group {
+  pgmo_deform table;
+  int n_devices = 0;
+  uint64_t calls = 0;
+};
+int pgmo_deform_group_create(int n_devices, const int*, pgmo_deform_group_t** out) {
+  *out = new pgmo_deform_group();
+  (*out)->n_devices = n_devices == 0 ? pgmo_device_count() : n_devices;
+  return PGMO_OK;
+}
+void pgmo_deform_group_destroy(pgmo_deform_group_t* g) { delete g; }
+int pgmo_deform_group_size(pgmo_deform_group_t* g) { return g->n_devices; }
+int pgmo_deform_group_set_controls(pgmo_deform_group_t* g, uint64_t n_c, const double* pos_xyz,
+                                   const uint64_t* stamps_ns, const uint8_t* valid,
+                                   const double* poses12) {
+  return pgmo_deform_set_controls(&g->table, n_c, pos_xyz, stamps_ns, valid, poses12);
+}
+int pgmo_deform_group_points(pgmo_deform_group_t* g, uint64_t n_v, const float* x, const float* y,
+                             const float* z, const uint64_t* stamps_ns, uint32_t k, double tol_t,
+                             int precision, float* out_x, float* out_y, float* out_z,
+                             uint8_t* processed) {
+  ++g->calls;
+  return pgmo_deform_points(&g->table, n_v, x, y, z, stamps_ns, nullptr, 0, k, tol_t, precision, out_x,
+                            out_y, out_z, nullptr, nullptr, 0, nullptr, processed);
 }
 
 // not reachable from the tests that link this file

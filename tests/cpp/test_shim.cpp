@@ -334,6 +334,69 @@ static void testLargeCloudStaging() {
   EXPECT_EQ(size_t(0), face_differing);
 }
 
+// No reference counterpart: DeformationGraphMeshPath over several devices (vertex slabs,
+// pgmo_deform_group_*) gives the single-device mesh bit for bit, for a first deformMesh and for
+// a second one after a new solve.  One visible device: two slabs on it.
+static void testDeviceGroup() {
+  const size_t n = 400000, n_ctrl = 400;
+  const char prefix = 'a';
+  deformation::Backend::groupMinVertices() = 100000;
+  if (pgmo_device_count() < 2) setenv("KIMERA_PGMO_B200_GROUP_DEVICES", "0,0", 1);
+  DeformationGraphMeshPath single(0, 1), multi(0, 0);
+  gtsam::Values values, values2;
+  uint32_t lcg = 777u;
+  auto unit = [&lcg]() {
+    lcg = lcg * 1664525u + 1013904223u;
+    return static_cast<float>(lcg >> 8) / 16777216.0f;
+  };
+  for (size_t j = 0; j < n_ctrl; j++) {
+    const gtsam::Point3 g(0.5 * static_cast<double>(j), unit(), unit());
+    const Timestamp t = stampFromSec(0.5 * static_cast<double>(j));
+    single.addControlPoint(prefix, g, t);
+    multi.addControlPoint(prefix, g, t);
+    values.insert(gtsam::Symbol(prefix, j), gtsam::Pose3(gtsam::Rot3::Rz(0.001 * static_cast<double>(j)),
+                                                        gtsam::Point3(g.x() + 0.25, 0.5, -0.1)));
+    values2.insert(gtsam::Symbol(prefix, j), gtsam::Pose3(gtsam::Rot3::Rz(-0.002 * static_cast<double>(j)),
+                                                         gtsam::Point3(g.x() - 0.1, 0.3, 0.2)));
+  }
+  pcl::PointCloud<pcl::PointXYZRGBA> cloud;
+  std::vector<Timestamp> stamps;
+  cloud.points.resize(n);
+  for (size_t i = 0; i < n; i++) {
+    const double s = 200.0 * static_cast<double>(i) / static_cast<double>(n);
+    pcl::PointXYZRGBA& p = cloud.points[i];
+    p.x = static_cast<float>(s) + unit();
+    p.y = 4.0f * unit() - 2.0f;
+    p.z = 2.0f * unit();
+    p.rgba = static_cast<uint32_t>(i * 2654435761u);
+    stamps.push_back(stampFromSec(std::floor(s)));
+  }
+  cloud.width = static_cast<uint32_t>(n);
+  pcl::PolygonMesh mesh;
+  pcl::toPCLPointCloud2(cloud, mesh.cloud);
+  const std::vector<int> graph_indices(n, -1);
+  for (const gtsam::Values* v : {&values, &values2}) {
+    single.setRecalculateVertices();
+    multi.setRecalculateVertices();
+    const pcl::PolygonMesh a = single.deformMesh(mesh, stamps, graph_indices, prefix, *v, 4);
+    const pcl::PolygonMesh b = multi.deformMesh(mesh, stamps, graph_indices, prefix, *v, 4);
+    pcl::PointCloud<pcl::PointXYZRGBA> pa, pb;
+    pcl::fromPCLPointCloud2(a.cloud, pa);
+    pcl::fromPCLPointCloud2(b.cloud, pb);
+    EXPECT_EQ(n, pa.points.size());
+    EXPECT_EQ(n, pb.points.size());
+    size_t differing = 0, moved = 0;
+    for (size_t i = 0; i < n && i < pa.points.size() && i < pb.points.size(); i++) {
+      differing += std::memcmp(&pa.points[i], &pb.points[i], sizeof(pcl::PointXYZRGBA)) != 0;
+      moved += std::memcmp(&pa.points[i], &cloud.points[i], 3 * sizeof(float)) != 0;
+    }
+    EXPECT_EQ(size_t(0), differing);
+    EXPECT_TRUE(moved > n / 2);
+  }
+  unsetenv("KIMERA_PGMO_B200_GROUP_DEVICES");
+  deformation::Backend::groupMinVertices() = size_t(1) << 20;
+}
+
 // ------------------------------------------------------------------ TestDeformationGraph
 static pcl::PointXYZRGBA colored(float x, float y, float z, uint8_t r, uint8_t g, uint8_t b) {
   pcl::PointXYZRGBA p;
@@ -984,6 +1047,7 @@ int main(int argc, char** argv) {
   testDeformPointsWithTimeCheck();
   testEarlyReturnsAndErrors();
   testLargeCloudStaging();
+  testDeviceGroup();
   testReconstructAndTranslate();
   testDeformMeshCube();
   testIncrementalWithPredeform();
