@@ -55,19 +55,23 @@ class DeformationGraphMeshPath {
                               double tol_t = 10.0) {
     pcl::PolygonMesh new_mesh;
     detail::BlobCloud in;
+    detail::Trace trace("deformMesh");
     if (detail::blobView(original_mesh.cloud, &in)) {
       // The blob already has the layout toPCLPointCloud2 writes for a PointXYZRGBA cloud, so
       // blob -> cloud -> blob (:540, :557) would change nothing but x / y / z: copy the blob
       // once (threads) and deform the copy in place through the traits layer.
       detail::blobCloneShape(original_mesh.cloud, new_mesh.cloud);
+      trace.mark("blob allocate");
       detail::BlobCloud out;
       detail::blobView(new_mesh.cloud, &out);
       detail::parallelFor(in.n, [&](size_t begin, size_t end) {
         std::memcpy(out.base + begin * out.step, in.base + begin * in.step, (end - begin) * in.step);
       });
+      trace.mark("blob copy");
       in.stamps = &stamps;
       out.stamps = &stamps;
       deformPoints(out, in, prefix, optimized_values, k, tol_t, &graph_indices);
+      trace.mark("deformPoints");
     } else {
       pcl::PointCloud<pcl::PointXYZRGBA> new_vertices;
       pcl::fromPCLPointCloud2(original_mesh.cloud, new_vertices);
@@ -77,10 +81,11 @@ class DeformationGraphMeshPath {
     }
     // new_mesh.polygons = original_mesh.polygons (:555), one heap block per face: on a few
     // threads for large meshes
-    new_mesh.polygons.resize(original_mesh.polygons.size());
+    detail::resizePrefaulted(new_mesh.polygons, original_mesh.polygons.size());
     detail::parallelFor(original_mesh.polygons.size(), [&](size_t begin, size_t end) {
       for (size_t f = begin; f < end; f++) new_mesh.polygons[f] = original_mesh.polygons[f];
-    });
+    }, size_t(1) << 15);
+    trace.mark("polygons");
     return new_mesh;
   }
 
@@ -170,7 +175,9 @@ class DeformationGraphMeshPath {
       }
     }
 
+    detail::Trace trace("deformPoints");
     cacheNewPoints(vertices, prefix, start_idx);
+    trace.mark("cacheNewPoints");
     recalculate_vertices_ = false;
   }
 

@@ -18,6 +18,10 @@
 #pragma once
 
 #include <algorithm>
+#ifdef KIMERA_PGMO_B200_TRACE
+#include <chrono>
+#include <cstdio>
+#endif
 #include <cstddef>
 #include <cstdint>
 #include <cstdlib>
@@ -30,11 +34,12 @@
 #include <stdexcept>
 #include <string>
 #include <thread>
+#include <type_traits>
 #include <vector>
 
 // upper bound on the threads of the shim's gather / scatter loops (1 = single-threaded)
 #ifndef KIMERA_PGMO_B200_SHIM_THREADS
-#define KIMERA_PGMO_B200_SHIM_THREADS 8
+#define KIMERA_PGMO_B200_SHIM_THREADS 16
 #endif
 
 #include "kimera_pgmo_b200/deps.h"
@@ -55,6 +60,25 @@ class PgmoB200Error : public std::runtime_error {
 };
 
 namespace detail {
+// -DKIMERA_PGMO_B200_TRACE: phase timings of the shim's host side on stderr (development aid)
+#ifdef KIMERA_PGMO_B200_TRACE
+struct Trace {
+  explicit Trace(const char* what) : what_(what), t0_(std::chrono::steady_clock::now()), last_(t0_) {}
+  void mark(const char* phase) {
+    const auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[shim trace] %s / %s: %.2f ms\n", what_, phase,
+                 std::chrono::duration<double, std::milli>(now - last_).count());
+    last_ = now;
+  }
+  const char* what_;
+  std::chrono::steady_clock::time_point t0_, last_;
+};
+#else
+struct Trace {
+  explicit Trace(const char*) {}
+  void mark(const char*) {}
+};
+#endif
 inline void throwOnError(int rc) {
   if (rc >= 0) return;
   const std::string msg = std::string("pgmo_b200: ") + pgmo_last_error();
@@ -66,8 +90,7 @@ inline void throwOnError(int rc) {
 // large, in place otherwise.  The first exception of any part (e.g. the std::out_of_range of a
 // cloud's .at()) is rethrown on the calling thread.
 template <typename Fn>
-void parallelFor(size_t n, Fn&& fn) {
-  constexpr size_t kMinPerThread = size_t(1) << 17;
+void parallelFor(size_t n, Fn&& fn, size_t kMinPerThread = size_t(1) << 17) {
   const size_t hw = std::thread::hardware_concurrency();
   const size_t n_threads = std::min<size_t>(
       {hw ? hw : 1, static_cast<size_t>(KIMERA_PGMO_B200_SHIM_THREADS), n / kMinPerThread});
@@ -91,6 +114,26 @@ void parallelFor(size_t n, Fn&& fn) {
   part(0);
   for (std::thread& th : pool) th.join();
   if (error) std::rethrow_exception(error);
+}
+
+// Touches every page of freshly allocated (reserved, not yet sized) vector storage on the shim's
+// threads, so that the single-threaded value-initialisation of the resize() that follows runs
+// over mapped memory: first-touch page faults are most of the cost of creating a 320 MB output
+// blob (deformMesh returns a new mesh by value, deformation_graph.cpp:532).
+template <typename T>
+void resizePrefaulted(std::vector<T>& v, size_t n) {
+  if (n <= v.capacity() || n * sizeof(T) < (size_t(1) << 24)) {
+    v.resize(n);
+    return;
+  }
+  v.reserve(n);
+  // raw bytes of the capacity beyond size(): no element lives there yet
+  volatile unsigned char* raw = reinterpret_cast<volatile unsigned char*>(v.data());
+  const size_t begin_byte = v.size() * sizeof(T), bytes = n * sizeof(T);
+  parallelFor((bytes - begin_byte + 4095) / 4096, [&](size_t b, size_t e) {
+    for (size_t page = b; page < e; ++page) raw[begin_byte + page * 4096] = 0;
+  }, 2048);
+  v.resize(n);
 }
 
 // Grow-only host block carved into the per-call arrays: page-locked (pgmo_host_alloc) when the
@@ -214,7 +257,7 @@ inline void blobCloneShape(const pcl::PCLPointCloud2& in, pcl::PCLPointCloud2& o
   out.point_step = in.point_step;
   out.row_step = in.row_step;
   out.is_dense = in.is_dense;
-  out.data.resize(in.data.size());
+  resizePrefaulted(out.data, in.data.size());
 }
 #else
 inline bool blobView(const pcl::PCLPointCloud2& blob, BlobCloud* view) {
@@ -230,6 +273,14 @@ inline bool blobView(const pcl::PCLPointCloud2& blob, BlobCloud* view) {
 inline void blobCloneShape(const pcl::PCLPointCloud2& in, pcl::PCLPointCloud2& out) {
   out.width = in.width;
   out.height = in.height;
+  out.data.reserve(in.data.size());
+  {  // as resizePrefaulted (the stand-in's point type has a constructor)
+    volatile unsigned char* raw = reinterpret_cast<volatile unsigned char*>(out.data.data());
+    const size_t bytes = in.data.size() * sizeof(pcl::PointXYZRGBA);
+    parallelFor((bytes + 4095) / 4096, [&](size_t b, size_t e) {
+      for (size_t page = b; page < e; ++page) raw[page * 4096] = 0;
+    }, 2048);
+  }
   out.data.resize(in.data.size());
 }
 #endif
@@ -323,22 +374,25 @@ class Backend {
     pos_.resize(3 * n_c);
     valid_.resize(n_c);
     poses_.assign(12 * n_c, 0.0);
-    for (size_t j = 0; j < n_c; ++j) {
-      pos_[3 * j + 0] = control_points[j].x();
-      pos_[3 * j + 1] = control_points[j].y();
-      pos_[3 * j + 2] = control_points[j].z();
-      const gtsam::Key key = gtsam::Symbol(prefix, j);
-      valid_[j] = values.exists(key) ? 1 : 0;
-      if (!valid_[j]) continue;
-      const gtsam::Pose3& T = values.at<gtsam::Pose3>(key);
-      const auto R = T.rotation().matrix();
-      for (int r = 0; r < 3; ++r) {
-        for (int c = 0; c < 3; ++c) poses_[12 * j + 3 * r + c] = R(r, c);
+    // read-only look-ups of `values` (two ordered-map searches per control point): on threads
+    kimera_pgmo_b200::detail::parallelFor(n_c, [&](size_t begin, size_t end) {
+      for (size_t j = begin; j < end; ++j) {
+        pos_[3 * j + 0] = control_points[j].x();
+        pos_[3 * j + 1] = control_points[j].y();
+        pos_[3 * j + 2] = control_points[j].z();
+        const gtsam::Key key = gtsam::Symbol(prefix, j);
+        valid_[j] = values.exists(key) ? 1 : 0;
+        if (!valid_[j]) continue;
+        const gtsam::Pose3& T = values.at<gtsam::Pose3>(key);
+        const auto R = T.rotation().matrix();
+        for (int r = 0; r < 3; ++r) {
+          for (int c = 0; c < 3; ++c) poses_[12 * j + 3 * r + c] = R(r, c);
+        }
+        poses_[12 * j + 9] = T.translation().x();
+        poses_[12 * j + 10] = T.translation().y();
+        poses_[12 * j + 11] = T.translation().z();
       }
-      poses_[12 * j + 9] = T.translation().x();
-      poses_[12 * j + 10] = T.translation().y();
-      poses_[12 * j + 11] = T.translation().z();
-    }
+    }, 4096);
     const uint64_t* stamps = nullptr;
     if (control_point_stamps && control_point_stamps->size() >= n_c) {  // .at(j), j < n_c
       stamps = control_point_stamps->data();
@@ -387,11 +441,13 @@ void run(Backend& backend, CloudOut& new_points,
   // other vertex (mesh_deformation.h:159-161): only those are gathered, in that order, and
   // deformed as a cloud of their own — an incremental update of a few thousand vertices of a
   // 10 M-vertex mesh moves a few thousand vertices across PCIe, not the mesh.
+  kimera_pgmo_b200::detail::Trace trace("run");
   PinnedBlock& stage = backend.staging();
   stage.reserve(6 * PinnedBlock::padded(n_pos * sizeof(float)) +
                 PinnedBlock::padded(stamped ? n_pos * sizeof(uint64_t) : 0) +
                 PinnedBlock::padded(n_pos) + 256);
   stage.rewind();
+  trace.mark("staging reserve");
   float* x = stage.take<float>(n_pos);
   float* y = stage.take<float>(n_pos);
   float* z = stage.take<float>(n_pos);
@@ -411,6 +467,7 @@ void run(Backend& backend, CloudOut& new_points,
       if (stamped) stamps[p] = traits::get_timestamp(points, ii);
     }
   });
+  trace.mark("gather");
   const uint32_t stride = static_cast<uint32_t>(k + 2 > 8 ? k + 2 : 8);
   std::vector<uint32_t> assoc(control_point_map ? n_pos * stride : 0);
   std::vector<uint8_t> cnt(control_point_map ? n_pos : 0);
@@ -427,6 +484,7 @@ void run(Backend& backend, CloudOut& new_points,
                             control_point_map ? cnt.data() : nullptr, processed);
   }
   kimera_pgmo_b200::detail::throwOnError(rc);
+  trace.mark("C ABI call");
   if (rc == PGMO_NOOP) return;  // the reference returned before control_point_map.clear()
   if (!control_point_map) {
     parallelFor(n_pos, [&](size_t begin, size_t end) {
@@ -436,6 +494,7 @@ void run(Backend& backend, CloudOut& new_points,
         traits::set_vertex(new_points, ii, traits::Pos(ox[p], oy[p], oz[p]));
       }
     });
+    trace.mark("scatter");
     return;
   }
   control_point_map->clear();
@@ -470,7 +529,9 @@ void deformPointsImpl(CloudOut& new_points, std::vector<std::set<size_t>>* contr
     return;  // "No control points. No deformation"
   }
   Backend& b = backend ? *backend : defaultBackend();
+  kimera_pgmo_b200::detail::Trace trace("deformPointsImpl");
   b.setControls(prefix, control_points, kStamped ? &control_point_stamps : nullptr, values);
+  trace.mark("setControls");
   run(b, new_points, control_point_map, points, kStamped, k, kStamped ? tol_t : 0.0, indices,
       precision);
 }
