@@ -124,14 +124,18 @@ struct FlatMesh {
   std::vector<uint64_t> offsets;
   std::vector<float> xyz;
   std::vector<uint32_t> rgba;
+  std::vector<uint32_t> labels;  // getActiveSemantics (0xFFFFFFFF = nullopt) when hasSemantics()
   // voxblox messages stay packed (decoded on the GPU)
   bool packed = false;
   std::vector<uint16_t> x16, y16, z16;
   std::vector<uint8_t> r8, g8, b8;
   float block_edge_length = 0.f;
-  explicit FlatMesh(const MeshInterface& mesh) {
+  // allow_packed = false: every interface goes through getActiveVertex (compressors without a
+  // packed entry point); with_semantics: also collect getActiveSemantics
+  explicit FlatMesh(const MeshInterface& mesh, bool allow_packed = true, bool with_semantics = false) {
     offsets.push_back(0);
-    if (const auto* vb = dynamic_cast<const VoxbloxMsgInterface*>(&mesh)) {
+    const auto* vb = allow_packed ? dynamic_cast<const VoxbloxMsgInterface*>(&mesh) : nullptr;
+    if (vb) {
       packed = true;
       block_edge_length = vb->message().block_edge_length;
       for (const auto& blk : vb->message().mesh_blocks) {
@@ -163,6 +167,10 @@ struct FlatMesh {
         xyz.push_back(p.y);
         xyz.push_back(p.z);
         rgba.push_back(p.rgba);
+        if (with_semantics && mesh.hasSemantics()) {
+          const std::optional<uint32_t> label = mesh.getActiveSemantics(i);
+          labels.push_back(label ? *label : 0xFFFFFFFFu);
+        }
       }
       offsets.push_back(rgba.size());
     }

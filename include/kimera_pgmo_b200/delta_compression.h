@@ -39,7 +39,8 @@ class MeshDelta {  // mesh_delta.h:65-150: what DeltaCompression::update produce
   size_t getTotalFaces() const { return face_start + face_archive_updates.size() + face_updates.size(); }
   size_t getLocalIndex(size_t index) const { return index - vertex_start; }
   size_t getGlobalIndex(size_t index) const { return index + vertex_start; }
-  bool hasSemantics() const { return false; }
+  // mesh_delta.cpp:112-114
+  bool hasSemantics() const { return semantic_updates.size() == vertex_updates->size(); }
 
   // updateVertices / updateFaces (mesh_delta.h:171-215) for the PCL containers
   void updateMesh(pcl::PointCloud<pcl::PointXYZRGBA>& vertices, std::vector<Timestamp>& stamps,
@@ -100,12 +101,13 @@ class DeltaCompression {
   // delta_compression.cpp:211-259
   MeshDelta::Ptr update(MeshInterface& mesh, uint64_t timestamp_ns,
                         HashedIndexMapping* remapping = nullptr) {
-    const detail::FlatMesh flat(mesh);
-    if (flat.packed) throw std::logic_error("DeltaCompression: pass voxblox messages through getActiveVertex");
+    // any MeshInterface (voxblox messages included) through getActiveVertex /
+    // getActiveSemantics, like the reference (:278-288)
+    const detail::FlatMesh flat(mesh, /* allow_packed */ false, /* with_semantics */ true);
     std::vector<uint64_t> remap(flat.numVertices());
-    detail::throwOnError(pgmo_delta_update(handle_.get(), flat.numBlocks(), flat.block_idx.data(),
-                                           flat.offsets.data(), flat.xyz.data(), flat.rgba.data(),
-                                           timestamp_ns, remap.data()));
+    detail::throwOnError(pgmo_delta_update_labeled(
+        handle_.get(), flat.numBlocks(), flat.block_idx.data(), flat.offsets.data(), flat.xyz.data(),
+        flat.rgba.data(), flat.labels.empty() ? nullptr : flat.labels.data(), timestamp_ns, remap.data()));
     if (remapping) {  // :171-174, :186-192: insert-if-absent into the caller's maps
       size_t b = 0;
       for (const auto& block : mesh.blockIndices()) {
@@ -168,6 +170,15 @@ class DeltaCompression {
     for (uint64_t i = 0; i < s[2]; ++i) {
       delta->vertex_updates->push_back(detail::makePoint(xyz.data() + 3 * i, rgba[i]));
       delta->stamp_updates.push_back(stamps[i]);
+    }
+    int any_label = 0;
+    detail::throwOnError(pgmo_delta_fetch_labels(handle_.get(), nullptr, &any_label));
+    if (any_label && s[2]) {  // addVertex pushes a label only where there is one (mesh_delta.cpp:152-154)
+      std::vector<uint32_t> labels(s[2]);
+      detail::throwOnError(pgmo_delta_fetch_labels(handle_.get(), labels.data(), nullptr));
+      for (uint32_t label : labels) {
+        if (label != 0xFFFFFFFFu) delta->semantic_updates.push_back(label);
+      }
     }
     delta->num_archived_vertices_ = s[3];
     for (uint64_t f = 0; f < s[4]; ++f) delta->face_updates.emplace_back(faces[3 * f], faces[3 * f + 1], faces[3 * f + 2]);

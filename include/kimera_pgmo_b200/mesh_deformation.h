@@ -485,7 +485,14 @@ void run(Backend& backend, CloudOut& new_points,
   }
   kimera_pgmo_b200::detail::throwOnError(rc);
   trace.mark("C ABI call");
-  if (rc == PGMO_NOOP) return;  // the reference returned before control_point_map.clear()
+  if (rc == PGMO_NOOP) {
+    // The early returns that precede control_point_map.clear() (no points :78-80 / :143-146, no /
+    // too few control points :83-86 / :149-152) were taken by deformPointsImpl; what is left is
+    // "octree has fewer than k leaves" of the unstamped overload (:96-99), which comes AFTER the
+    // clear() of :88.
+    if (control_point_map) control_point_map->clear();
+    return;
+  }
   if (!control_point_map) {
     parallelFor(n_pos, [&](size_t begin, size_t end) {
       for (size_t p = begin; p < end; ++p) {

@@ -389,6 +389,11 @@ void pgmo_oct_destroy(pgmo_oct_t* h);
 int pgmo_oct_integrate(pgmo_oct_t* h, uint32_t n_blocks, const int32_t* block_idx_xyz,
                        const uint64_t* block_offsets, const float* xyz, const uint32_t* rgba,
                        double stamp_s, int64_t* remap_index, uint8_t* remap_kind);
+/* Failure semantics of the compressors: argument errors are reported before anything changes.  A
+ * capacity / range error detected on the device (octree deeper than supported, voxel key outside
+ * the packed range, table full) is reported after the stored mesh has started to change; the
+ * handle then refuses every further call (PGMO_ERR_INVALID) instead of continuing on a
+ * half-updated mesh — create a new compressor. */
 int pgmo_oct_prune(pgmo_oct_t* h, double earliest_s);
 /* as pgmo_vcc_device_view, for MeshCompression's all_vertices_ / all_vertex_stamps_ */
 int pgmo_oct_device_view(pgmo_oct_t* h, const void** d_vertices_xyzw, const uint64_t** d_stamps_ns,
@@ -424,6 +429,17 @@ void pgmo_delta_destroy(pgmo_delta_t* h);
 int pgmo_delta_update(pgmo_delta_t* h, uint32_t n_blocks, const int32_t* block_idx_xyz,
                       const uint64_t* block_offsets, const float* xyz, const uint32_t* rgba,
                       uint64_t timestamp_ns, uint64_t* remap_out);
+/* The same with semantic labels: labels[i] = *mesh.getActiveSemantics(i) of input vertex i
+ * (0xFFFFFFFF = std::nullopt).  A voxel keeps the label of the vertex that set its point
+ * (delta_compression.cpp:72-77) and hands it to the delta (addVertex, :120, :128, :347).
+ * labels == NULL: every vertex of this message is unlabelled. */
+int pgmo_delta_update_labeled(pgmo_delta_t* h, uint32_t n_blocks, const int32_t* block_idx_xyz,
+                              const uint64_t* block_offsets, const float* xyz, const uint32_t* rgba,
+                              const uint32_t* labels, uint64_t timestamp_ns, uint64_t* remap_out);
+/* MeshDelta::semantic_updates of the last delta, one entry per vertex_updates entry (0xFFFFFFFF
+ * where the reference pushed nothing); *any_label = 1 iff some update of this handle carried
+ * labels.  Either pointer may be NULL. */
+int pgmo_delta_fetch_labels(pgmo_delta_t* h, uint32_t* labels, int* any_label);
 /* archiveBlocksByTime (:306-310) / clearArchivedBlocks (:312-316) */
 int pgmo_delta_archive_by_time(pgmo_delta_t* h, uint64_t earliest_time_ns);
 int pgmo_delta_archive_blocks(pgmo_delta_t* h, uint32_t n_blocks, const int32_t* block_idx_xyz);
@@ -470,6 +486,8 @@ void pgmo_m2g_destroy(pgmo_m2g_t* h);
  *                             insert-if-absent (pgmo_oct_integrate's remap_index / remap_kind);
  *                             mesh_kind NULL = all overwrite (pgmo_vcc_integrate's remap_out)
  *   graph_index / graph_kind  the same from the graph compressor */
+/* Block indices must be unique within a message (PGMO_ERR_UNSUPPORTED otherwise; the same holds
+ * for pgmo_vcc_integrate, pgmo_oct_integrate and pgmo_delta_update). */
 int pgmo_m2g_update(pgmo_m2g_t* h, uint32_t n_blocks, const int32_t* block_idx_xyz,
                     const uint64_t* block_offsets, const int64_t* mesh_index,
                     const uint8_t* mesh_kind, const int64_t* graph_index,

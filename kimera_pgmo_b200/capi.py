@@ -114,6 +114,8 @@ SIGNATURES = {
     "pgmo_delta_create": (C.c_int, [C.c_double, C.c_int, C.POINTER(_vp)]),
     "pgmo_delta_destroy": (None, [_vp]),
     "pgmo_delta_update": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, C.c_uint64, _vp]),
+    "pgmo_delta_update_labeled": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp, C.c_uint64, _vp]),
+    "pgmo_delta_fetch_labels": (C.c_int, [_vp, _vp, C.POINTER(C.c_int)]),
     "pgmo_delta_archive_by_time": (C.c_int, [_vp, C.c_uint64]),
     "pgmo_delta_archive_blocks": (C.c_int, [_vp, C.c_uint32, _vp]),
     "pgmo_delta_sizes": (C.c_int, [_vp, _vp]),
@@ -676,12 +678,26 @@ class DeltaHandle:
     def __del__(self):
         self.close()
 
-    def update(self, block_idx, offsets, xyz, rgba, stamp_ns, fetch=True):
+    def update(self, block_idx, offsets, xyz, rgba, stamp_ns, fetch=True, labels=None):
         bi, off, pts, col = _flatten_blocks(block_idx, offsets, xyz, rgba)
         remap = np.zeros(pts.shape[0], dtype=np.uint64)
-        _check(self._lib.pgmo_delta_update(self._h, bi.shape[0], _ptr(bi), _ptr(off), _ptr(pts), _ptr(col),
-                                           int(stamp_ns), _ptr(remap)))
+        if labels is None:
+            _check(self._lib.pgmo_delta_update(self._h, bi.shape[0], _ptr(bi), _ptr(off), _ptr(pts), _ptr(col),
+                                               int(stamp_ns), _ptr(remap)))
+        else:
+            lab = np.ascontiguousarray(labels, dtype=np.uint32)
+            assert lab.shape[0] == pts.shape[0]
+            _check(self._lib.pgmo_delta_update_labeled(self._h, bi.shape[0], _ptr(bi), _ptr(off), _ptr(pts),
+                                                       _ptr(col), _ptr(lab), int(stamp_ns), _ptr(remap)))
         return remap, (self.delta() if fetch else None)
+
+    def labels(self):
+        """semantic_updates of the last delta (0xFFFFFFFF = none), and whether labels were ever given"""
+        n = self.sizes()[2]
+        out = np.zeros(n, dtype=np.uint32)
+        flag = C.c_int(0)
+        _check(self._lib.pgmo_delta_fetch_labels(self._h, _ptr(out), C.byref(flag)))
+        return out, bool(flag.value)
 
     def archive_by_time(self, earliest_ns):
         _check(self._lib.pgmo_delta_archive_by_time(self._h, int(earliest_ns)))

@@ -46,7 +46,7 @@ struct pgmo_delta {
   uint32_t t_cap = 0;
   DevBuf<unsigned long long> r_key, r_stamp;
   DevBuf<float4> r_point;
-  DevBuf<uint32_t> r_mesh_index, r_seq;
+  DevBuf<uint32_t> r_mesh_index, r_seq, r_label;
   DevBuf<int32_t> r_refs;
   DevBuf<uint8_t> r_needs_archive, r_is_new, r_alive;
   uint64_t n_records = 0;  // exact after every call
@@ -54,7 +54,7 @@ struct pgmo_delta {
   // second record buffer set: compaction target, then swapped in (no allocation in steady state)
   DevBuf<unsigned long long> s_key, s_stamp;
   DevBuf<float4> s_point;
-  DevBuf<uint32_t> s_mesh_index, s_seq;
+  DevBuf<uint32_t> s_mesh_index, s_seq, s_label;
   DevBuf<int32_t> s_refs;
   DevBuf<uint8_t> s_needs_archive, s_is_new, s_alive;
   uint64_t record_compactions = 0;
@@ -78,6 +78,8 @@ struct pgmo_delta {
   uint32_t vertex_start = 0, face_start = 0, prev_total = 0;
   DevBuf<float4> o_point;
   DevBuf<unsigned long long> o_stamp;
+  DevBuf<uint32_t> o_label, d_label;
+  bool labeled = false;  // some update carried semantic labels
   DevBuf<uint8_t> o_new, o_obs, o_del;
   DevBuf<uint32_t> o_p2c, o_faces_upd, o_faces_arch;
   uint64_t d_arch = 0, d_vertices = 0, d_faces_upd = 0, d_faces_arch = 0;  // host mirrors
@@ -114,12 +116,14 @@ DeltaTable tableOf(pgmo_delta* h) {
 }
 DeltaRecords recordsOf(pgmo_delta* h) {
   return DeltaRecords{h->r_key.ptr, h->r_point.ptr, h->r_stamp.ptr, h->r_mesh_index.ptr, h->r_seq.ptr,
-                      h->r_refs.ptr, h->r_needs_archive.ptr, h->r_is_new.ptr, h->r_alive.ptr};
+                      h->r_refs.ptr, h->r_needs_archive.ptr, h->r_is_new.ptr, h->r_alive.ptr,
+                      h->r_label.ptr};
 }
 DeltaOut outOf(pgmo_delta* h) {
   DeltaOut o;
   o.point = h->o_point.ptr;
   o.stamp = h->o_stamp.ptr;
+  o.label = h->o_label.ptr;
   o.is_new = h->o_new.ptr;
   o.observed = h->o_obs.ptr;
   o.p2c = h->o_p2c.ptr;
@@ -136,6 +140,7 @@ int reserveRecords(pgmo_delta* h, uint64_t n, cudaStream_t st) {
   PGMO_TRY(h->r_key.reserve(n, st, keep));
   PGMO_TRY(h->r_stamp.reserve(n, st, keep));
   PGMO_TRY(h->r_point.reserve(n, st, keep));
+  PGMO_TRY(h->r_label.reserve(n, st, keep));
   PGMO_TRY(h->r_mesh_index.reserve(n, st, keep));
   PGMO_TRY(h->r_seq.reserve(n, st, keep));
   PGMO_TRY(h->r_refs.reserve(n, st, keep));
@@ -214,6 +219,7 @@ int openDelta(pgmo_delta* h, cudaStream_t st) {
 int reserveOutVertices(pgmo_delta* h, uint64_t n, cudaStream_t st) {
   PGMO_TRY(h->o_point.reserve(n, st, h->d_arch));
   PGMO_TRY(h->o_stamp.reserve(n, st, h->d_arch));
+  PGMO_TRY(h->o_label.reserve(n, st, h->d_arch));
   return PGMO_OK;
 }
 
@@ -338,6 +344,7 @@ int compactRecords(pgmo_delta* h, uint64_t alive, cudaStream_t st) {
   auto& needs_archive = h->s_needs_archive;
   auto& is_new = h->s_is_new;
   auto& alive_flag = h->s_alive;
+  auto& label = h->s_label;
   if (alive + 1 > key.cap) {  // sized by what is alive, never by the set being replaced
     const uint64_t cap = room(alive + 1);
     PGMO_TRY(key.reserve(cap));
@@ -349,11 +356,12 @@ int compactRecords(pgmo_delta* h, uint64_t alive, cudaStream_t st) {
     PGMO_TRY(needs_archive.reserve(cap));
     PGMO_TRY(is_new.reserve(cap));
     PGMO_TRY(alive_flag.reserve(cap));
+    PGMO_TRY(label.reserve(cap));
   }
   PGMO_TRY(roomy(h->new_id, n_old + 1));
   PGMO_TRY(reserveTiles(h, n_old));
   const DeltaRecords to{key.ptr, point.ptr, stamp.ptr, mesh_index.ptr, seq.ptr,
-                        refs.ptr, needs_archive.ptr, is_new.ptr, alive_flag.ptr};
+                        refs.ptr, needs_archive.ptr, is_new.ptr, alive_flag.ptr, label.ptr};
   PGMO_CUDA(launchDeltaCompactRecords(recordsOf(h), to, static_cast<uint32_t>(n_old), h->new_id.ptr,
                                       h->x_pool.ptr, h->x_used, h->tiles.ptr, h->counters.ptr, st));
   PGMO_CUDA(cudaStreamSynchronize(st));
@@ -370,6 +378,7 @@ int compactRecords(pgmo_delta* h, uint64_t alive, cudaStream_t st) {
   swapBuf(h->r_needs_archive, needs_archive);
   swapBuf(h->r_is_new, is_new);
   swapBuf(h->r_alive, alive_flag);
+  swapBuf(h->r_label, label);
   h->n_records = alive;
   ++h->record_compactions;
   // fresh table over the compacted records (same capacity: tombstones are gone)
@@ -489,6 +498,13 @@ void pgmo_delta_destroy(pgmo_delta_t* h) {
 int pgmo_delta_update(pgmo_delta_t* h, uint32_t n_blocks, const int32_t* block_idx_xyz,
                       const uint64_t* block_offsets, const float* xyz, const uint32_t* rgba,
                       uint64_t timestamp_ns, uint64_t* remap_out) {
+  return pgmo_delta_update_labeled(h, n_blocks, block_idx_xyz, block_offsets, xyz, rgba, nullptr,
+                                   timestamp_ns, remap_out);
+}
+
+int pgmo_delta_update_labeled(pgmo_delta_t* h, uint32_t n_blocks, const int32_t* block_idx_xyz,
+                              const uint64_t* block_offsets, const float* xyz, const uint32_t* rgba,
+                              const uint32_t* labels, uint64_t timestamp_ns, uint64_t* remap_out) {
   PGMO_CHECK_ARG(h != nullptr);
   PGMO_CHECK_ARG(n_blocks == 0 || (block_idx_xyz && block_offsets));
   PGMO_TRY(ensureDevice(h->device));
@@ -518,6 +534,11 @@ int pgmo_delta_update(pgmo_delta_t* h, uint32_t n_blocks, const int32_t* block_i
   if (n_total) {
     PGMO_CUDA(cudaMemcpyAsync(h->d_xyz.ptr, xyz, 3 * n_total * sizeof(float), cudaMemcpyHostToDevice, st));
     if (rgba) PGMO_CUDA(cudaMemcpyAsync(h->d_rgba.ptr, rgba, n_total * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  }
+  if (labels) {
+    PGMO_TRY(roomy(h->d_label, n_total + 1));
+    if (n_total) PGMO_CUDA(cudaMemcpyAsync(h->d_label.ptr, labels, n_total * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    h->labeled = true;
   }
   if (h->n_records + n_total + 1 > h->r_key.cap) PGMO_TRY(reserveRecords(h, room(h->n_records + n_total + 1), st));
   PGMO_TRY(ensureTable(h, h->n_records + n_total, st));
@@ -577,6 +598,7 @@ int pgmo_delta_update(pgmo_delta_t* h, uint32_t n_blocks, const int32_t* block_i
     DeltaBlockArgs a;
     a.xyz = h->d_xyz.ptr;
     a.rgba = rgba ? h->d_rgba.ptr : nullptr;
+    a.label = labels ? h->d_label.ptr : nullptr;
     a.first_vertex = block_offsets[b];
     a.n = n_b;
     a.index_scale = h->index_scale;
@@ -731,6 +753,22 @@ int pgmo_delta_sizes(pgmo_delta_t* h, uint64_t* s) {
   }
   s[10] = h->have_delta ? h->d_vertices - h->d_arch : 0;
   s[11] = h->n_pending;
+  return PGMO_OK;
+}
+
+int pgmo_delta_fetch_labels(pgmo_delta_t* h, uint32_t* labels, int* any_label) {
+  PGMO_CHECK_ARG(h != nullptr);
+  PGMO_TRY(ensureDevice(h->device));
+  if (!h->have_delta) {
+    setLastError("pgmo_delta_fetch_labels: no finished delta (call pgmo_delta_update)");
+    return PGMO_ERR_INVALID;
+  }
+  if (any_label) *any_label = h->labeled ? 1 : 0;
+  if (labels && h->d_vertices) {
+    PGMO_CUDA(cudaMemcpyAsync(labels, h->o_label.ptr, h->d_vertices * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                              h->stream));
+    PGMO_CUDA(cudaStreamSynchronize(h->stream));
+  }
   return PGMO_OK;
 }
 

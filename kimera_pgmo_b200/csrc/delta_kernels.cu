@@ -253,6 +253,7 @@ addApplyKernel(const DeltaTable t, const DeltaRecords r, const DeltaBlockArgs b,
     r.stamp[vs] = b.stamp_ns;
     r.point[vs] = make_float4(b.xyz[3 * v], b.xyz[3 * v + 1], b.xyz[3 * v + 2],
                               __uint_as_float(b.rgba ? b.rgba[v] : 0xFF000000u));
+    r.label[vs] = b.label ? b.label[v] : kDeltaNoLabel;  // info.label = semantic_label (:76)
     b.active_remapping[a] = r.mesh_index[vs];  // cache previous index
     r.mesh_index[vs] = a;
     r.seq[vs] = b.seq;
@@ -313,6 +314,7 @@ releaseApplyKernel(const DeltaTable t, const DeltaRecords r, const DeltaOut o,
   const uint32_t local = bases[0] + tiles[3 * blockIdx.x] + field(ex, 0);  // delta->addVertex(archive)
   o.point[local] = r.point[vs];
   o.stamp[local] = r.stamp[vs];
+    o.label[local] = r.label[vs];
   const uint32_t prev = r.mesh_index[vs];
   if (prev < o.prev_total) o.p2c[prev] = o.vertex_start + local;
   eraseRecord(t, r, vs, counters);
@@ -340,6 +342,7 @@ activeApplyKernel(const DeltaRecords r, const DeltaOut o, uint32_t seq, uint32_t
   const uint32_t new_idx = o.vertex_start + local;
   o.point[local] = r.point[vs];
   o.stamp[local] = r.stamp[vs];
+    o.label[local] = r.label[vs];
   const uint32_t mi = r.mesh_index[vs];
   if (r.seq[vs] != seq) {
     if (mi < o.prev_total) o.p2c[mi] = new_idx;  // not seen this pass (:131-133)
@@ -597,6 +600,7 @@ smallBlockKernel(const DeltaTable t, const DeltaRecords r, const DeltaOut o, con
         r.stamp[vs] = b.stamp_ns;
         r.point[vs] = make_float4(b.xyz[3 * v], b.xyz[3 * v + 1], b.xyz[3 * v + 2],
                                   __uint_as_float(b.rgba ? b.rgba[v] : 0xFF000000u));
+        r.label[vs] = b.label ? b.label[v] : kDeltaNoLabel;
         b.active_remapping[a] = r.mesh_index[vs];
         r.mesh_index[vs] = a;
         r.seq[vs] = b.seq;
@@ -642,6 +646,7 @@ smallBlockKernel(const DeltaTable t, const DeltaRecords r, const DeltaOut o, con
     const uint32_t local = base_arch + field(ex, 0);
     o.point[local] = r.point[vs];
     o.stamp[local] = r.stamp[vs];
+    o.label[local] = r.label[vs];
     const uint32_t prev = r.mesh_index[vs];
     if (prev < o.prev_total) o.p2c[prev] = o.vertex_start + local;
     eraseRecord(t, r, vs, counters);
@@ -667,6 +672,7 @@ compactMoveKernel(const DeltaRecords from, const DeltaRecords to, const uint32_t
   to.key[n] = from.key[vs];
   to.point[n] = from.point[vs];
   to.stamp[n] = from.stamp[vs];
+  to.label[n] = from.label[vs];
   to.mesh_index[n] = from.mesh_index[vs];
   to.seq[n] = from.seq[vs];
   to.refs[n] = from.refs[vs];

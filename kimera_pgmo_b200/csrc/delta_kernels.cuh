@@ -57,11 +57,14 @@ struct DeltaRecords {
   uint8_t* needs_archive;
   uint8_t* is_new;
   uint8_t* alive;
+  uint32_t* label;  // VoxelInfo::label (delta_compression.h:23-24); kDeltaNoLabel = nullopt
 };
+constexpr uint32_t kDeltaNoLabel = 0xFFFFFFFFu;
 
 struct DeltaOut {      // the delta under construction
   float4* point;       // [archived..., active...]
   unsigned long long* stamp;
+  uint32_t* label;     // semantic_updates (kDeltaNoLabel where the reference pushed nothing)
   uint8_t* is_new;     // per delta vertex (local index)
   uint8_t* observed;
   uint32_t* p2c;       // dense over the previous delta's global indices, kDeltaNone = absent
@@ -75,6 +78,7 @@ struct DeltaOut {      // the delta under construction
 struct DeltaBlockArgs {
   const float* xyz;      // message vertices, interleaved
   const uint32_t* rgba;  // may be null
+  const uint32_t* label; // MeshInterface::getActiveSemantics per vertex, may be null
   uint64_t first_vertex;
   uint32_t n;
   double index_scale;    // 1.0 / resolution

@@ -20,6 +20,7 @@
 // oracle/frontend_oracle.h.  The ordered insert is "flag -> smallest (block ordinal, msg index)
 // claims the mesh index (atomicMin) -> the claimant writes".
 #include <algorithm>
+#include <array>
 #include <new>
 #include <unordered_map>
 #include <vector>
@@ -234,6 +235,18 @@ int pgmo_m2g_update(pgmo_m2g_t* h, uint32_t n_blocks, const int32_t* block_idx_x
   // validate, find the mesh index range
   uint64_t span = 0;
   for (uint32_t b = 0; b < n_blocks; ++b) PGMO_CHECK_ARG(block_offsets[b] <= block_offsets[b + 1]);
+  {
+    // a block index twice in one message: the second occurrence could move the block's segment
+    // while the row of the first still points at the old one (unique blocks are assumed, as by
+    // the compressors that feed this call)
+    std::vector<std::array<int32_t, 3>> seen(n_blocks);
+    for (uint32_t b = 0; b < n_blocks; ++b) seen[b] = {block_idx_xyz[3 * b], block_idx_xyz[3 * b + 1], block_idx_xyz[3 * b + 2]};
+    std::sort(seen.begin(), seen.end());
+    if (std::adjacent_find(seen.begin(), seen.end()) != seen.end()) {
+      setLastError("mesh -> graph bookkeeping: a block index appears twice in one message");
+      return PGMO_ERR_UNSUPPORTED;
+    }
+  }
   for (uint64_t v = 0; v < n; ++v) {
     const uint8_t km = mesh_kind ? mesh_kind[v] : 1, kg = graph_kind ? graph_kind[v] : 1;
     PGMO_CHECK_ARG(km <= 2 && kg <= 2);

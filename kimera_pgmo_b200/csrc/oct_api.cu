@@ -356,6 +356,11 @@ struct TreeStore {
 }  // namespace
 
 struct pgmo_oct {
+  // A failure reported after the stored mesh started to change (table full, depth / range limits,
+  // CUDA errors inside the commit phase) leaves stamps refreshed and faces half inserted: the
+  // handle refuses further work instead of continuing on that state.
+  bool committing = false;  // the current call has started to change persistent state
+  bool poisoned = false;
   int device = 0;
   int mode = 0;  // 0 = OctreeCompression, 1 = BlockCompression (cell hash)
   double resolution = 0.0;
@@ -641,6 +646,17 @@ static int octIntegrate(pgmo_oct_t* h, uint32_t n_blocks, const int32_t* block_i
   const uint32_t n = static_cast<uint32_t>(n64);
   const double res = h->resolution;
   const uint64_t n_orig = h->n_all;
+  // A block index twice in one message: the reference resolves both occurrences to one block
+  // through its block map; the per-block bookkeeping here assumes unique blocks (as
+  // pgmo_vcc_integrate and pgmo_delta_update do).
+  for (uint32_t b = 0; b < n_blocks; ++b) {
+    for (uint32_t c = 0; c < b; ++c) {
+      if (std::memcmp(block_idx_xyz + 3 * b, block_idx_xyz + 3 * c, 3 * sizeof(int32_t)) == 0) {
+        setLastError("octree compression: a block index appears twice in one message");
+        return PGMO_ERR_UNSUPPORTED;
+      }
+    }
+  }
 
   // ---- inputs
   PGMO_TRY(h->d_xyz.reserve(3ull * n));
@@ -790,6 +806,7 @@ static int octIntegrate(pgmo_oct_t* h, uint32_t n_blocks, const int32_t* block_i
   PGMO_TRY(h->new_vertices.reserve(n_acc + 1));
   PGMO_TRY(h->reobs_flag.reserve(roomy(n_orig + 1, h->reobs_flag.cap)));
   PGMO_CUDA(cudaMemsetAsync(h->reobs_flag.ptr, 0, n_orig + 1, st));
+  h->committing = true;  // from here on the stored mesh changes
   if (n_acc > 0) {
     octCommitVerticesKernel<<<blocksFor(n_acc), 256, 0, st>>>(
         static_cast<uint32_t>(n_acc), h->acc_list.ptr, h->pot_list.ptr, h->cand_list.ptr, h->d_xyz.ptr,
@@ -857,11 +874,30 @@ static int octIntegrate(pgmo_oct_t* h, uint32_t n_blocks, const int32_t* block_i
   return PGMO_OK;
 }
 
+// refuses a poisoned handle; poisons it when a call fails after it started to commit
+static int guardedIntegrate(pgmo_oct_t* h, uint32_t n_blocks, const int32_t* block_idx_xyz,
+                            const uint64_t* block_offsets, const float* xyz, const uint32_t* rgba,
+                            const VoxbloxInput* vb, double stamp_s, int64_t* remap_index,
+                            uint8_t* remap_kind) {
+  PGMO_CHECK_ARG(h != nullptr);
+  if (h->poisoned) {
+    setLastError("octree compression: an earlier integrate failed while the stored mesh was being "
+                 "updated; this handle is unusable, create a new compressor");
+    return PGMO_ERR_INVALID;
+  }
+  h->committing = false;
+  const int rc = octIntegrate(h, n_blocks, block_idx_xyz, block_offsets, xyz, rgba, vb, stamp_s,
+                              remap_index, remap_kind);
+  if (rc < 0 && h->committing) h->poisoned = true;
+  h->committing = false;
+  return rc;
+}
+
 int pgmo_oct_integrate(pgmo_oct_t* h, uint32_t n_blocks, const int32_t* block_idx_xyz,
                        const uint64_t* block_offsets, const float* xyz, const uint32_t* rgba,
                        double stamp_s, int64_t* remap_index, uint8_t* remap_kind) {
-  return octIntegrate(h, n_blocks, block_idx_xyz, block_offsets, xyz, rgba, nullptr, stamp_s,
-                      remap_index, remap_kind);
+  return guardedIntegrate(h, n_blocks, block_idx_xyz, block_offsets, xyz, rgba, nullptr, stamp_s,
+                          remap_index, remap_kind);
 }
 
 int pgmo_oct_integrate_voxblox(pgmo_oct_t* h, uint32_t n_blocks, const int32_t* block_idx_xyz,
@@ -870,12 +906,16 @@ int pgmo_oct_integrate_voxblox(pgmo_oct_t* h, uint32_t n_blocks, const int32_t* 
                                const uint8_t* b, float block_edge_length, double stamp_s,
                                int64_t* remap_index, uint8_t* remap_kind) {
   const VoxbloxInput in{x, y, z, r, g, b, block_edge_length};
-  return octIntegrate(h, n_blocks, block_idx_xyz, block_offsets, nullptr, nullptr, &in, stamp_s,
-                      remap_index, remap_kind);
+  return guardedIntegrate(h, n_blocks, block_idx_xyz, block_offsets, nullptr, nullptr, &in, stamp_s,
+                          remap_index, remap_kind);
 }
 
 int pgmo_oct_prune(pgmo_oct_t* h, double earliest_s) {
   PGMO_CHECK_ARG(h != nullptr);
+  if (h->poisoned) {
+    setLastError("octree compression: this handle is unusable after a failed integrate");
+    return PGMO_ERR_INVALID;
+  }
   PGMO_TRY(ensureDevice(h->device));
   cudaStream_t st = h->stream;
   if (h->n_act == 0) return PGMO_OK;  // :420-422

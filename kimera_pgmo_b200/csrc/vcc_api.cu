@@ -116,6 +116,7 @@ struct BlockDevState {
 }  // namespace
 
 struct pgmo_vcc {
+  bool poisoned = false;  // a device-side error was reported after state had changed
   int device = 0;
   double resolution = 0.0;
   cudaStream_t stream = nullptr;
@@ -209,7 +210,11 @@ int syncCounters(pgmo_vcc_t* h, cudaStream_t st) {
   h->used_upper = h->n_live + h->n_tomb;
   const unsigned long long err = h->h_counters.ptr[kVccError];
   if (err) {
-    setLastError("voxel clearing: %s%s%s",
+    // the kernels that hit the error had already changed reference counts / the voxel table:
+    // the handle stays in the error state instead of going on with a half-updated mesh
+    h->poisoned = true;
+    setLastError("voxel clearing: %s%s%s(the handle is unusable from here on: its stored mesh was "
+                 "partially updated; create a new compressor)",
                  (err & 1) ? "voxel key outside the packed +-2^20 range; " : "",
                  (err & 2) ? "voxel table full; " : "",
                  (err & 4) ? "previous voxel missing from the table; " : "");
@@ -300,6 +305,11 @@ int ensureIndexCapacity(pgmo_vcc_t* h, uint64_t extra, cudaStream_t st) {
 int integrateCore(pgmo_vcc_t* h, uint32_t n_blocks, const int32_t* block_idx_xyz,
                   const uint64_t* block_offsets, const float* d_xyz, const uint32_t* d_rgba,
                   double stamp_s, uint64_t* d_remap_out, int64_t* d_keys_out, cudaStream_t st) {
+  if (h->poisoned) {
+    setLastError("voxel clearing: an earlier call reported a device-side error after the stored mesh "
+                 "had changed; this handle is unusable, create a new compressor");
+    return PGMO_ERR_INVALID;
+  }
   const uint64_t n_total = n_blocks ? block_offsets[n_blocks] : 0;
   for (uint32_t b = 0; b < n_blocks; ++b) {
     PGMO_CHECK_ARG(block_offsets[b] <= block_offsets[b + 1]);
@@ -559,6 +569,10 @@ int pgmo_vcc_integrate_voxblox(pgmo_vcc_t* h, uint32_t n_blocks, const int32_t* 
 
 int pgmo_vcc_prune(pgmo_vcc_t* h, double earliest_s) {
   PGMO_CHECK_ARG(h != nullptr);
+  if (h->poisoned) {
+    setLastError("voxel clearing: this handle is unusable after a device-side error");
+    return PGMO_ERR_INVALID;
+  }
   PGMO_TRY(ensureDevice(h->device));
   std::vector<BlockKey> to_clear;
   for (const auto& kv : h->block_update_times) {  // iteration order of the reference's map

@@ -72,6 +72,10 @@ struct MeshInterface {
   virtual void markBlockActive(const BlockIndex& block) const = 0;
   virtual size_t activeBlockSize() const = 0;
   virtual PointXYZRGBA getActiveVertex(size_t i) const = 0;
+  // mesh_interface.h:28-33 (kNoLabel stands for std::nullopt)
+  static constexpr uint32_t kNoLabel = 0xFFFFFFFFu;
+  virtual bool hasSemantics() const { return false; }
+  virtual uint32_t getActiveSemantics(size_t /* i */) const { return kNoLabel; }
 };
 
 // Flat block mesh: block b owns vertices [offsets[b], offsets[b+1]).  Covers both the
@@ -82,6 +86,7 @@ struct FlatBlockMesh : MeshInterface {
   BlockIndices blocks;
   std::vector<size_t> offsets;  // blocks.size() + 1
   std::vector<PointXYZRGBA> vertices;
+  std::vector<uint32_t> labels;  // empty: no semantics
   mutable size_t active = 0;
   const BlockIndices& blockIndices() const override { return blocks; }
   void markBlockActive(const BlockIndex& block) const override {
@@ -91,6 +96,8 @@ struct FlatBlockMesh : MeshInterface {
   }
   size_t activeBlockSize() const override { return offsets[active + 1] - offsets[active]; }
   PointXYZRGBA getActiveVertex(size_t i) const override { return vertices[offsets[active] + i]; }
+  bool hasSemantics() const override { return !labels.empty(); }
+  uint32_t getActiveSemantics(size_t i) const override { return labels.at(offsets[active] + i); }
 };
 
 // common_functions.cpp:166-185

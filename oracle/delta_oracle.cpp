@@ -26,10 +26,13 @@ bool canBeArchived(const DeltaFace& face, size_t archive_threshold) {  // :448-4
 }  // namespace
 
 // mesh_delta.cpp:144-169
-size_t MeshDelta::addVertex(uint64_t timestamp_ns, const PointXYZRGBA& point, bool archive) {
+size_t MeshDelta::addVertex(uint64_t timestamp_ns, const PointXYZRGBA& point, uint32_t label,
+                            bool archive) {
   const size_t index = vertex_start + vertex_updates.size();
   vertex_updates.push_back(point);
   stamp_updates.push_back(timestamp_ns);
+  if (label != MeshInterface::kNoLabel) semantic_updates.push_back(label);  // :152-154
+  label_of_vertex.push_back(label);
   if (archive) num_archived_vertices++;
   return index;
 }
@@ -67,7 +70,7 @@ DeltaCompression::DeltaCompression(double resolution)  // :47-52
       num_archived_faces_(0) {}
 
 // :54-92
-void DeltaCompression::addPoint(const PointXYZRGBA& point, uint64_t timestamp_ns,
+void DeltaCompression::addPoint(const PointXYZRGBA& point, uint64_t timestamp_ns, uint32_t semantic_label,
                                 std::vector<size_t>& face_map, std::vector<LongIndex>& curr_voxels,
                                 std::set<std::array<int64_t, 3>>& curr_set) {
   // float * double product, std::round half away from zero, narrowed to int64 (:61-63)
@@ -79,6 +82,7 @@ void DeltaCompression::addPoint(const PointXYZRGBA& point, uint64_t timestamp_ns
   if (info->sequence_number != sequence_number_) {
     info->timestamp_ns = timestamp_ns;
     info->point = point;
+    info->label = semantic_label;  // :76
     const size_t prev_index = info->mesh_index;
     info->mesh_index = active_remapping_.size();
     active_remapping_.push_back(prev_index);  // cache previous index
@@ -106,7 +110,7 @@ void DeltaCompression::removeBlockObservations(const std::vector<LongIndex>& to_
       continue;
     }
     if (!info.shouldArchive()) continue;
-    const size_t mesh_index = delta_->addVertex(info.timestamp_ns, info.point, true);
+    const size_t mesh_index = delta_->addVertex(info.timestamp_ns, info.point, info.label, true);
     delta_->prev_to_curr[info.mesh_index] = mesh_index;
     vertices_map_.erase(prev);
   }
@@ -115,7 +119,7 @@ void DeltaCompression::removeBlockObservations(const std::vector<LongIndex>& to_
 // :128-154
 void DeltaCompression::addActiveVertices() {
   vertices_map_.forEach([&](const LongIndex&, VertexInfo& info) {
-    const size_t new_idx = delta_->addVertex(info.timestamp_ns, info.point);
+    const size_t new_idx = delta_->addVertex(info.timestamp_ns, info.point, info.label);
     if (info.sequence_number != sequence_number_) {
       delta_->prev_to_curr[info.mesh_index] = new_idx;
     } else {
@@ -209,7 +213,9 @@ void DeltaCompression::updateRemapping(const MeshInterface& mesh, uint64_t stamp
     std::set<std::array<int64_t, 3>> curr_set;
     mesh.markBlockActive(block_index);
     for (size_t i = 0; i < mesh.activeBlockSize(); ++i) {
-      addPoint(mesh.getActiveVertex(i), stamp_ns, block_info->indices, curr_voxels, curr_set);
+      addPoint(mesh.getActiveVertex(i), stamp_ns,
+               mesh.hasSemantics() ? mesh.getActiveSemantics(i) : MeshInterface::kNoLabel,  // :285
+               block_info->indices, curr_voxels, curr_set);
     }
     if (!is_block_new) removeBlockObservations(block_info->vertices);
     block_info->vertices = curr_voxels;
@@ -244,7 +250,7 @@ void DeltaCompression::archiveImpl(const std::vector<BlockIndex>& to_erase) {
       info->needs_archive = true;
       --info->active_refs;
       if (!info->shouldArchive()) continue;
-      const size_t new_index = archive_delta_->addVertex(info->timestamp_ns, info->point, true);
+      const size_t new_index = archive_delta_->addVertex(info->timestamp_ns, info->point, info->label, true);
       archive_delta_->prev_to_curr[info->mesh_index] = new_index;
       vertices_map_.erase(voxel);
     }

@@ -98,7 +98,10 @@ struct DeltaFace {
 struct MeshDelta {
   MeshDelta(size_t vertex_start_, size_t face_start_)
       : vertex_start(vertex_start_), face_start(face_start_) {}
-  size_t addVertex(uint64_t timestamp_ns, const PointXYZRGBA& point, bool archive = false);
+  // label == MeshInterface::kNoLabel: std::nullopt (nothing is pushed to semantic_updates)
+  size_t addVertex(uint64_t timestamp_ns, const PointXYZRGBA& point,
+                   uint32_t label = MeshInterface::kNoLabel, bool archive = false);
+  bool hasSemantics() const { return semantic_updates.size() == vertex_updates.size(); }  // mesh_delta.cpp:112
   void addFace(const DeltaFace& face, bool archive = false);
   size_t getTotalArchivedVertices() const { return vertex_start + num_archived_vertices; }
   size_t getTotalArchivedFaces() const { return face_start + face_archive_updates.size(); }
@@ -107,6 +110,8 @@ struct MeshDelta {
   size_t face_start = 0;
   std::vector<PointXYZRGBA> vertex_updates;
   std::vector<uint64_t> stamp_updates;
+  std::vector<uint32_t> semantic_updates;       // mesh_delta.h:126
+  std::vector<uint32_t> label_of_vertex;        // oracle only: the label handed to addVertex, per vertex
   std::vector<DeltaFace> face_updates;
   std::vector<DeltaFace> face_archive_updates;
   std::map<size_t, size_t> prev_to_curr;
@@ -127,6 +132,7 @@ struct RedunancyChecker {  // redundancy_checker.cpp:12-43
 struct VertexInfo {  // delta_compression.h:17-46
   uint64_t timestamp_ns = 0;
   PointXYZRGBA point;
+  uint32_t label = MeshInterface::kNoLabel;  // std::optional<uint32_t> label (:23-24)
   size_t mesh_index = 0;
   bool is_new = true;
   uint16_t sequence_number = 0;
@@ -166,8 +172,9 @@ class DeltaCompression {
   }
 
  private:
-  void addPoint(const PointXYZRGBA& point, uint64_t timestamp_ns, std::vector<size_t>& face_map,
-                std::vector<LongIndex>& curr_voxels, std::set<std::array<int64_t, 3>>& curr_set);
+  void addPoint(const PointXYZRGBA& point, uint64_t timestamp_ns, uint32_t semantic_label,
+                std::vector<size_t>& face_map, std::vector<LongIndex>& curr_voxels,
+                std::set<std::array<int64_t, 3>>& curr_set);
   void removeBlockObservations(const std::vector<LongIndex>& to_remove);
   void addActiveVertices();
   void addActiveFaces(const MeshInterface& mesh, std::vector<uint64_t>* remap_out);

@@ -61,6 +61,10 @@ def load():
     lib.oracle_delta_destroy.argtypes = [_vp]
     lib.oracle_delta_update.restype = C.c_int
     lib.oracle_delta_update.argtypes = [_vp, C.c_uint32, _vp, _vp, _vp, _vp, C.c_uint64, _vp, _vp]
+    lib.oracle_delta_update_labeled.restype = C.c_int
+    lib.oracle_delta_update_labeled.argtypes = [_vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp, C.c_uint64, _vp, _vp]
+    lib.oracle_delta_fetch_labels.restype = C.c_uint64
+    lib.oracle_delta_fetch_labels.argtypes = [_vp, _vp]
     lib.oracle_delta_archive_by_time.argtypes = [_vp, C.c_uint64]
     lib.oracle_delta_archive_blocks.argtypes = [_vp, C.c_uint32, _vp]
     lib.oracle_delta_sizes.argtypes = [_vp, _vp]
@@ -308,7 +312,14 @@ class DeltaCompression:
             self._lib.oracle_delta_destroy(self._h)
             self._h = None
 
-    def update(self, block_idx, offsets, xyz, rgba, stamp_ns):
+    def labels(self):
+        """(label per delta vertex, 0xFFFFFFFF = none; len(semantic_updates))"""
+        n = self.sizes()[2]
+        out = np.zeros(n, dtype=np.uint32)
+        k = self._lib.oracle_delta_fetch_labels(self._h, _ptr(out))
+        return out, int(k)
+
+    def update(self, block_idx, offsets, xyz, rgba, stamp_ns, labels=None):
         """-> (remap per input vertex, delta dict)"""
         bi = np.ascontiguousarray(block_idx, dtype=np.int32).reshape(-1, 3)
         off = np.ascontiguousarray(offsets, dtype=np.uint64)
@@ -316,8 +327,10 @@ class DeltaCompression:
         col = None if rgba is None else np.ascontiguousarray(rgba, dtype=np.uint32)
         remap = np.zeros(pts.shape[0], dtype=np.uint64)
         elapsed = C.c_double(0.0)
-        rc = self._lib.oracle_delta_update(self._h, bi.shape[0], _ptr(bi), _ptr(off), _ptr(pts), _ptr(col),
-                                           int(stamp_ns), _ptr(remap), C.cast(C.byref(elapsed), _vp))
+        lab = None if labels is None else np.ascontiguousarray(labels, dtype=np.uint32)
+        rc = self._lib.oracle_delta_update_labeled(self._h, bi.shape[0], _ptr(bi), _ptr(off), _ptr(pts),
+                                                   _ptr(col), _ptr(lab), int(stamp_ns), _ptr(remap),
+                                                   C.cast(C.byref(elapsed), _vp))
         assert rc == 0, "the reference would have thrown"
         self.elapsed_s = elapsed.value
         return remap, self.delta()

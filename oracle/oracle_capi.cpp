@@ -113,9 +113,21 @@ void oracle_delta_destroy(void* h) { delete static_cast<DeltaHandle*>(h); }
 
 // DeltaCompression::update.  remap_out: per input vertex the delta index written to
 // remapping[block][i].  Returns 0, or -1 if the reference would have thrown (.at()).
+int oracle_delta_update_labeled(void* hv, uint32_t n_blocks, const int32_t* block_idx_xyz,
+                                const uint64_t* block_offsets, const float* xyz, const uint32_t* rgba,
+                                const uint32_t* labels, uint64_t stamp_ns, uint64_t* remap_out,
+                                double* elapsed_s);
 int oracle_delta_update(void* hv, uint32_t n_blocks, const int32_t* block_idx_xyz,
                         const uint64_t* block_offsets, const float* xyz, const uint32_t* rgba,
                         uint64_t stamp_ns, uint64_t* remap_out, double* elapsed_s) {
+  return oracle_delta_update_labeled(hv, n_blocks, block_idx_xyz, block_offsets, xyz, rgba, nullptr,
+                                     stamp_ns, remap_out, elapsed_s);
+}
+// labels (optional): MeshInterface::getActiveSemantics per input vertex, 0xFFFFFFFF = nullopt
+int oracle_delta_update_labeled(void* hv, uint32_t n_blocks, const int32_t* block_idx_xyz,
+                                const uint64_t* block_offsets, const float* xyz, const uint32_t* rgba,
+                                const uint32_t* labels, uint64_t stamp_ns, uint64_t* remap_out,
+                                double* elapsed_s) {
   DeltaHandle* h = static_cast<DeltaHandle*>(hv);
   FlatBlockMesh mesh;
   mesh.offsets.push_back(0);
@@ -128,6 +140,7 @@ int oracle_delta_update(void* hv, uint32_t n_blocks, const int32_t* block_idx_xy
       p.z = xyz[3 * i + 2];
       p.rgba = rgba ? rgba[i] : 0xFF000000u;
       mesh.vertices.push_back(p);
+      if (labels) mesh.labels.push_back(labels[i]);
     }
     mesh.offsets.push_back(mesh.vertices.size());
   }
@@ -197,6 +210,16 @@ void oracle_delta_sizes(void* hv, uint64_t* s) {
   }
   s[10] = h->comp.numActiveVertices();
   s[11] = h->comp.numPendingArchivedFaces();
+}
+
+// per delta vertex the label handed to addVertex (0xFFFFFFFF = none); returns
+// semantic_updates.size() (== the vertex count iff MeshDelta::hasSemantics())
+uint64_t oracle_delta_fetch_labels(void* hv, uint32_t* labels) {
+  DeltaHandle* h = static_cast<DeltaHandle*>(hv);
+  if (!h->last) return 0;
+  const MeshDelta& d = *h->last;
+  for (size_t i = 0; labels && i < d.label_of_vertex.size(); ++i) labels[i] = d.label_of_vertex[i];
+  return d.semantic_updates.size();
 }
 
 void oracle_delta_fetch(void* hv, float* xyz, uint32_t* rgba, uint64_t* stamps, uint32_t* faces,

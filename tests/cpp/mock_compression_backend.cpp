@@ -38,6 +38,11 @@ void oracle_delta_destroy(void* h);
 int oracle_delta_update(void* h, uint32_t n_blocks, const int32_t* block_idx_xyz,
                         const uint64_t* block_offsets, const float* xyz, const uint32_t* rgba,
                         uint64_t stamp_ns, uint64_t* remap_out, double* elapsed_s);
+int oracle_delta_update_labeled(void* h, uint32_t n_blocks, const int32_t* block_idx_xyz,
+                                const uint64_t* block_offsets, const float* xyz, const uint32_t* rgba,
+                                const uint32_t* labels, uint64_t stamp_ns, uint64_t* remap_out,
+                                double* elapsed_s);
+uint64_t oracle_delta_fetch_labels(void* h, uint32_t* labels);
 void oracle_delta_archive_by_time(void* h, uint64_t earliest_ns);
 void oracle_delta_archive_blocks(void* h, uint32_t n_blocks, const int32_t* block_idx_xyz);
 uint64_t oracle_delta_blocks(void* h, uint64_t capacity, int32_t* block_idx_xyz,
@@ -64,6 +69,7 @@ struct pgmo_oct {
 };
 struct pgmo_delta {
   void* oracle;
+  bool labeled = false;
 };
 struct pgmo_m2g {
   void* oracle;
@@ -235,6 +241,19 @@ int pgmo_delta_update(pgmo_delta_t* h, uint32_t n_blocks, const int32_t* block_i
   const int rc = oracle_delta_update(h->oracle, n_blocks, block_idx_xyz, block_offsets, xyz, rgba,
                                      timestamp_ns, remap_out, nullptr);
   return rc == 0 ? PGMO_OK : PGMO_ERR_OUT_OF_RANGE;
+}
+int pgmo_delta_update_labeled(pgmo_delta_t* h, uint32_t n_blocks, const int32_t* block_idx_xyz,
+                              const uint64_t* block_offsets, const float* xyz, const uint32_t* rgba,
+                              const uint32_t* labels, uint64_t timestamp_ns, uint64_t* remap_out) {
+  if (labels) h->labeled = true;
+  const int rc = oracle_delta_update_labeled(h->oracle, n_blocks, block_idx_xyz, block_offsets, xyz, rgba,
+                                             labels, timestamp_ns, remap_out, nullptr);
+  return rc == 0 ? PGMO_OK : PGMO_ERR_OUT_OF_RANGE;
+}
+int pgmo_delta_fetch_labels(pgmo_delta_t* h, uint32_t* labels, int* any_label) {
+  if (any_label) *any_label = h->labeled ? 1 : 0;
+  if (labels) oracle_delta_fetch_labels(h->oracle, labels);
+  return PGMO_OK;
 }
 int pgmo_delta_archive_by_time(pgmo_delta_t* h, uint64_t earliest_time_ns) {
   oracle_delta_archive_by_time(h->oracle, earliest_time_ns);

@@ -151,6 +151,21 @@ static void testEarlyReturnsAndErrors() {
   };
   const ConstStampedCloud<Point> cloud{points, stamps};
 
+  {  // unstamped overload, fewer occupied voxels than k (:96-99): returns AFTER clear() (:88)
+    gtsam::Values two;  // only two of the three control points have a pose
+    for (size_t j = 0; j < 2; j++) {
+      two.insert(gtsam::Symbol(prefix, j), gtsam::Pose3(gtsam::Rot3(), gtsam::Point3(0.0, 2.0, 0.0)));
+    }
+    pcl::PointCloud<Point> out = points;
+    std::vector<std::set<size_t>> map = sentinel;
+    deformation::deformPoints(out, map, points, prefix, control_points, control_point_stamps, two, 3);
+    EXPECT_TRUE(map.empty());
+    bool same = out.size() == points.size();
+    for (size_t i = 0; same && i < out.size(); i++) {
+      same = std::memcmp(&out.points[i], &points.points[i], 3 * sizeof(float)) == 0;
+    }
+    EXPECT_TRUE(same);
+  }
   {  // empty cloud (:78-80 / :143-145): the map is not even cleared
     pcl::PointCloud<Point> none, out;
     std::vector<std::set<size_t>> map = sentinel;
@@ -594,6 +609,12 @@ struct OrderedBlockMesh : MeshInterface {  // pgmo_fixtures.h:28-48
   }
   size_t activeBlockSize() const override { return blocks[active].size(); }
   pcl::PointXYZRGBA getActiveVertex(size_t i) const override { return blocks[active][i]; }
+  // optional semantics (mesh_interface.h:28-33): labels[b][i], empty = none
+  std::vector<std::vector<uint32_t>> labels;
+  bool hasSemantics() const override { return !labels.empty(); }
+  std::optional<uint32_t> getActiveSemantics(size_t i) const override {
+    return labels.empty() ? std::nullopt : std::optional<uint32_t>(labels[active][i]);
+  }
   Ptr clone() const override { return std::make_shared<OrderedBlockMesh>(*this); }
 };
 
@@ -967,6 +988,82 @@ static void testDeltaCompression() {
   d1->updateMesh(vertices, stamps, faces);
   EXPECT_EQ(d1->getTotalVertices(), vertices.size());
   EXPECT_EQ(d1->getTotalFaces(), faces.size());
+
+  // Semantic labels (delta_compression.cpp:76, :120, :128, :285, :347): a voxel keeps the label
+  // of the vertex that set its point and hands it to the delta; MeshDelta::hasSemantics() iff
+  // every vertex of the delta carries one.
+  {
+    DeltaCompression labelled(1.0e-3);
+    OrderedBlockMesh m = createMesh({block1_test1, block2_test1});
+    for (const auto& blk : m.blocks) {
+      m.labels.emplace_back();
+      for (size_t i = 0; i < blk.size(); ++i) m.labels.back().push_back(static_cast<uint32_t>(100 * m.labels.size() + i));
+    }
+    auto d = labelled.update(m, 100ull * 1000000000ull);
+    EXPECT_TRUE(d->hasSemantics());
+    EXPECT_EQ(d->vertex_updates->size(), d->semantic_updates.size());
+    // the delta's vertices in first-observation order: block 1's three distinct corners of its
+    // first face (labels 100..102; its second face repeats them with labels 103..105, which lose),
+    // then its third face (106..108), then block 2's first face (200..202); block 2's second face
+    // re-observes block 1's third-face voxels, which keep 106..108
+    const std::vector<uint32_t> expected{100, 101, 102, 106, 107, 108, 200, 201, 202};
+    EXPECT_EQ(expected.size(), d->semantic_updates.size());
+    for (size_t i = 0; i < expected.size() && i < d->semantic_updates.size(); ++i) {
+      EXPECT_EQ(expected[i], d->semantic_updates[i]);
+    }
+    // an unlabelled message afterwards: re-observed voxels lose their label, like info.label = nullopt
+    OrderedBlockMesh plain = createMesh({block1_test1});
+    auto d2 = labelled.update(plain, 101ull * 1000000000ull);
+    EXPECT_TRUE(!d2->hasSemantics());
+    EXPECT_EQ(size_t(3), d2->semantic_updates.size());  // block 2's own three voxels keep theirs
+  }
+
+  // DeltaCompression::update takes any MeshInterface (:278-288), a voxblox message included:
+  // same delta as the same vertices handed over through a generic interface
+  {
+    VoxbloxMesh msg;
+    msg.block_edge_length = 0.8f;
+    uint32_t seed = 99u;
+    auto next = [&seed]() {
+      seed = seed * 1664525u + 1013904223u;
+      return seed >> 8;
+    };
+    for (int b = 0; b < 3; ++b) {
+      VoxbloxMeshBlock blk;
+      blk.index[0] = b;
+      blk.index[1] = -b;
+      for (int v = 0; v < 60; ++v) {
+        blk.x.push_back(static_cast<uint16_t>(next() % 65536));
+        blk.y.push_back(static_cast<uint16_t>(next() % 65536));
+        blk.z.push_back(static_cast<uint16_t>(next() % 65536));
+        blk.r.push_back(static_cast<uint8_t>(next()));
+        blk.g.push_back(static_cast<uint8_t>(next()));
+        blk.b.push_back(static_cast<uint8_t>(next()));
+      }
+      msg.mesh_blocks.push_back(blk);
+    }
+    const VoxbloxMsgInterface voxblox(msg);
+    OrderedBlockMesh generic;
+    for (const auto& block : voxblox.blockIndices()) {
+      generic.order.push_back(block);
+      generic.blocks.emplace_back();
+      voxblox.markBlockActive(block);
+      for (size_t i = 0; i < voxblox.activeBlockSize(); ++i) generic.blocks.back().push_back(voxblox.getActiveVertex(i));
+    }
+    DeltaCompression a(0.05), b(0.05);
+    HashedIndexMapping remap_a, remap_b;
+    auto da = a.update(const_cast<VoxbloxMsgInterface&>(voxblox), 5ull * 1000000000ull, &remap_a);
+    auto db = b.update(generic, 5ull * 1000000000ull, &remap_b);
+    EXPECT_EQ(db->vertex_updates->size(), da->vertex_updates->size());
+    EXPECT_EQ(db->face_updates.size(), da->face_updates.size());
+    EXPECT_TRUE(da->vertex_updates->size() > 100);
+    bool same = da->vertex_updates->size() == db->vertex_updates->size();
+    for (size_t i = 0; same && i < da->vertex_updates->size(); ++i) {
+      same = std::memcmp(&da->vertex_updates->at(i), &db->vertex_updates->at(i), sizeof(pcl::PointXYZRGBA)) == 0;
+    }
+    EXPECT_TRUE(same);
+    EXPECT_TRUE(remap_a == remap_b);
+  }
 }
 
 // ------------------------------------------------------------- MeshFrontendInterface (bookkeeping)

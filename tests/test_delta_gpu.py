@@ -173,3 +173,36 @@ def test_compaction_of_records_and_pools_keeps_parity(capi, oracle, monkeypatch)
         _same(gd, od, f"message {m}")
     assert gpu.last_stats()[3] >= 3  # record compactions happened
     gpu.close()
+
+
+@pytest.mark.parametrize("n_blocks,horizon", [(1, None), (6, 3.0), (40, 2.0)])
+def test_semantic_labels_follow_the_points(capi, oracle, n_blocks, horizon, monkeypatch):
+    """MeshInterface::getActiveSemantics -> VertexInfo::label -> MeshDelta::semantic_updates
+    (delta_compression.cpp:76, :120, :128, :285, :347): a voxel keeps the label of the vertex that
+    set its point in its last observed pass; archived and carried-over vertices keep theirs;
+    unlabelled messages in between reset the labels of what they re-observe.  Also with the record
+    compaction forced after every message."""
+    for compact in (False, True):
+        if compact:
+            monkeypatch.setenv("PGMO_DELTA_COMPACT_SLACK", "0")
+        gpu, ora = capi.DeltaHandle(0.05, 0), oracle.DeltaCompression(0.05)
+        rng = np.random.default_rng(4)
+        for m, (blocks, offsets, xyz, rgba, t) in enumerate(synth.compression_stream(12, 6000, n_blocks=n_blocks)):
+            if horizon is not None and m >= 3:
+                cut = int((t - horizon) * 1e9)
+                gpu.archive_by_time(cut)
+                ora.archive_by_time(cut)
+            labels = None
+            if m % 4 != 2:  # every fourth message carries no semantics
+                labels = rng.integers(0, 40, xyz.shape[0]).astype(np.uint32)
+                labels[rng.random(xyz.shape[0]) < 0.05] = 0xFFFFFFFF  # std::nullopt for some vertices
+            gr, gd = gpu.update(blocks, offsets, xyz, rgba, int(t * 1e9), labels=labels)
+            orr, od = ora.update(blocks, offsets, xyz, rgba, int(t * 1e9), labels=labels)
+            np.testing.assert_array_equal(gr, orr, err_msg=f"message {m}: remap")
+            _same(gd, od, f"message {m}")
+            gl, any_label = gpu.labels()
+            ol, n_sem = ora.labels()
+            assert any_label
+            np.testing.assert_array_equal(gl, ol, err_msg=f"message {m}: labels")
+            assert int((gl != 0xFFFFFFFF).sum()) == n_sem
+        gpu.close()

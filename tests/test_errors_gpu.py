@@ -100,3 +100,62 @@ def test_duplicate_block_index_in_one_vcc_message_is_unsupported(capi):
     with pytest.raises(capi.PgmoError) as e:
         vcc.integrate(blocks, offsets, xyz, np.zeros(6, np.uint32), 1.0)
     assert e.value.code == capi.PGMO_ERR_UNSUPPORTED
+
+
+def test_duplicate_block_in_one_message_is_rejected(capi):
+    """The per-block bookkeeping of every compressor and of the mesh -> graph maps assumes that a
+    block index appears once per message (the reference resolves duplicates through a block map);
+    a duplicate is refused before anything changes."""
+    blocks = np.array([[0, 0, 0], [1, 0, 0], [0, 0, 0]], dtype=np.int32)
+    offsets = np.array([0, 3, 6, 9], dtype=np.uint64)
+    xyz = np.random.default_rng(0).uniform(0, 1, (9, 3)).astype(np.float32)
+    rgba = np.zeros(9, dtype=np.uint32)
+    for make in (lambda: capi.OctHandle(0.05, 0), lambda: capi.VccHandle(0.05), lambda: capi.DeltaHandle(0.05, 0)):
+        h = make()
+        with pytest.raises(capi.PgmoError) as e:
+            if isinstance(h, capi.DeltaHandle):
+                h.update(blocks, offsets, xyz, rgba, 1_000_000_000)
+            else:
+                h.integrate(blocks, offsets, xyz, rgba, 1.0)
+        assert e.value.code == capi.PGMO_ERR_UNSUPPORTED
+        # nothing changed: the same handle takes a well-formed message
+        if isinstance(h, capi.DeltaHandle):
+            h.update(blocks[:2], offsets[:3], xyz[:6], rgba[:6], 1_000_000_000)
+        else:
+            h.integrate(blocks[:2], offsets[:3], xyz[:6], rgba[:6], 1.0)
+        h.close()
+    m2g = capi.MeshToGraphHandle(0)
+    idx = np.arange(9, dtype=np.int64)
+    with pytest.raises(capi.PgmoError) as e:
+        m2g.update(blocks, offsets, idx, None, idx, None)
+    assert e.value.code == capi.PGMO_ERR_UNSUPPORTED
+    m2g.update(blocks[:2], offsets[:3], idx[:6], None, idx[:6], None)
+    m2g.close()
+
+
+def test_device_side_error_poisons_the_compressor(capi):
+    """A range error found by the kernels is reported after reference counts / the voxel table
+    have changed: the handle refuses further work instead of continuing on that state."""
+    vcc = capi.VccHandle(1.0e-3)
+    far = np.array([[2000.0, 0, 0], [0, 0, 0], [1, 1, 1]], dtype=np.float32)  # key 2e6 > 2^20
+    one_block = (np.zeros((1, 3), np.int32), np.array([0, 3], np.uint64))
+    with pytest.raises(capi.PgmoError) as e:
+        vcc.integrate(*one_block, far, None, 1.0)
+    assert e.value.code == capi.PGMO_ERR_UNSUPPORTED
+    near = np.array([[0.1, 0, 0], [0, 0.1, 0], [0, 0, 0.1]], dtype=np.float32)
+    with pytest.raises(capi.PgmoError) as e:
+        vcc.integrate(*one_block, near, None, 2.0)
+    assert e.value.code == capi.PGMO_ERR_INVALID and "unusable" in str(e.value)
+    with pytest.raises(capi.PgmoError):
+        vcc.prune(0.0)
+    vcc.close()
+    # the octree compressor: a vertex farther than 2^18 voxels from the first one
+    oc = capi.OctHandle(1.0e-3, 0)
+    oc.integrate(*one_block, near, None, 1.0)
+    with pytest.raises(capi.PgmoError) as e:
+        oc.integrate(*one_block, near + np.float32(500.0), None, 2.0)
+    assert e.value.code in (capi.PGMO_ERR_UNSUPPORTED, capi.PGMO_ERR_CUDA)
+    with pytest.raises(capi.PgmoError) as e:
+        oc.integrate(*one_block, near, None, 3.0)
+    assert e.value.code == capi.PGMO_ERR_INVALID and "unusable" in str(e.value)
+    oc.close()
