@@ -25,6 +25,10 @@
  *   - Host entry points take host pointers, copy them in, and do not retain them.
  *     *_device entry points take device pointers valid on the handle's device and enqueue on
  *     the given CUDA stream (cudaStream_t passed as void*; NULL = the handle's own stream).
+ *     Calls on one handle take effect in call order whatever stream each one was given: a
+ *     call that uses another stream than the previous call on the handle first makes its
+ *     stream wait (cudaStreamWaitEvent) for what that call queued.  The pose-source buffers
+ *     are the exception (their readers are other handles: see below).
  *   - Handles are independent: no global state, one CUDA stream each, never the default
  *     stream; two handles may be driven from two host threads concurrently (the reference
  *     runs two compressors on two std::threads, mesh_frontend_interface.cpp:100-110).  A single

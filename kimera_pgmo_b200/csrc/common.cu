@@ -96,3 +96,13 @@ int pgmo_host_free(void* ptr) {
 }
 
 }  // extern "C"
+
+// CUDA loads a kernel lazily at its first launch (tens to hundreds of ms for a module): pull
+// every kernel of this file in when a handle is created instead of inside a message stream.
+namespace pgmo {
+void preloadCommonKernels() {
+  cudaFuncAttributes attr;
+  cudaFuncGetAttributes(&attr, probeKernel);
+  cudaGetLastError();
+}
+}  // namespace pgmo

@@ -99,6 +99,19 @@ struct PinnedBuf {
   }
 };
 
+// per-file kernel preloading (cudaFuncGetAttributes on every kernel: forces the lazy module load
+// at handle creation, not inside a message stream)
+void preloadCommonKernels();
+void preloadDeltaKernels();
+void preloadVccKernels();
+void preloadOctTreeKernels();
+void preloadOctApiKernels();
+void preloadM2gKernels();
+void preloadMeshInterfaceKernels();
+void preloadMeshMsgKernels();
+void preloadDeformMiscKernels();
+void preloadDeformGridKernels();
+
 inline unsigned divUp(uint64_t a, uint64_t b) { return static_cast<unsigned>((a + b - 1) / b); }
 
 }  // namespace pgmo

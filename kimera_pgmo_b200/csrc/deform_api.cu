@@ -16,6 +16,11 @@ using namespace pgmo;
 struct pgmo_deform {
   int device = 0;
   cudaStream_t stream = nullptr;
+  // Calls on one handle take effect in call order whatever stream each one was given: every
+  // entry point records order_ev on the stream it used when it returns, and a call that uses
+  // another stream makes it wait for that event first (CallOrder).
+  cudaEvent_t order_ev = nullptr;
+  cudaStream_t last_stream = nullptr;
 
   // control table
   uint64_t n_c = 0;
@@ -142,6 +147,21 @@ namespace {
 cudaStream_t pick(pgmo_deform_t* h, void* stream) {
   return stream ? static_cast<cudaStream_t>(stream) : h->stream;
 }
+
+struct CallOrder {
+  pgmo_deform_t* h;
+  cudaStream_t st;
+  CallOrder(pgmo_deform_t* handle, cudaStream_t stream) : h(handle), st(stream) {
+    if (h->order_ev && h->last_stream && h->last_stream != st) cudaStreamWaitEvent(st, h->order_ev, 0);
+  }
+  ~CallOrder() {
+    if (!h->order_ev) return;
+    if (cudaEventRecord(h->order_ev, st) == cudaSuccess) h->last_stream = st;
+    else cudaGetLastError();
+  }
+  CallOrder(const CallOrder&) = delete;
+  CallOrder& operator=(const CallOrder&) = delete;
+};
 
 int uploadSchedule(pgmo_deform_t* h, cudaStream_t st) {
   const Schedule& s = h->sched;
@@ -483,6 +503,10 @@ int pgmo_deform_create(int device, pgmo_deform_t** out) {
   if (const char* e = std::getenv("PGMO_RESOLVER_TRAVERSAL")) h->force_traversal = atoi(e) != 0;
   cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking);
+  if (cudaEventCreateWithFlags(&h->order_ev, cudaEventDisableTiming) != cudaSuccess) {
+    h->order_ev = nullptr;  // without it calls are ordered per stream only
+    cudaGetLastError();
+  }
   cudaEventCreateWithFlags(&h->ev_stamps, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&h->ev_fp, cudaEventDisableTiming);
   for (int i = 0; i < pgmo_deform::kPipe; ++i) {
@@ -498,6 +522,9 @@ int pgmo_deform_create(int device, pgmo_deform_t** out) {
   }
   preloadDeformSortedKernels();
   preloadDeformBlendKernels();
+  preloadDeformMiscKernels();
+  preloadDeformGridKernels();
+  preloadMeshMsgKernels();
   cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, device);
   if (const char* e = std::getenv("PGMO_ASSOC_CACHE")) h->cache_enabled = atoi(e) != 0;
   *out = h;
@@ -507,6 +534,7 @@ int pgmo_deform_create(int device, pgmo_deform_t** out) {
 void pgmo_deform_destroy(pgmo_deform_t* h) {
   if (!h) return;
   cudaSetDevice(h->device);
+  if (h->order_ev && h->last_stream) cudaEventSynchronize(h->order_ev);
   if (h->stream) {
     cudaStreamSynchronize(h->stream);
     cudaStreamDestroy(h->stream);
@@ -520,6 +548,10 @@ void pgmo_deform_destroy(pgmo_deform_t* h) {
   }
   if (h->ev_stamps) cudaEventDestroy(h->ev_stamps);
   if (h->ev_fp) cudaEventDestroy(h->ev_fp);
+  if (h->order_ev) {
+    cudaEventSynchronize(h->order_ev);  // work a call left on a caller's stream
+    cudaEventDestroy(h->order_ev);
+  }
   if (h->s_in) cudaStreamDestroy(h->s_in);
   if (h->s_out) cudaStreamDestroy(h->s_out);
   if (h->pose_src && h->pose_src_owned) cudaFree(h->pose_src);
@@ -551,6 +583,7 @@ int pgmo_deform_set_controls(pgmo_deform_t* h, uint64_t n_c, const double* pos_x
   h->has_valid = valid != nullptr;
   h->has_poses = poses12 != nullptr;
   cudaStream_t st = h->stream;
+  CallOrder call_order(h, st);
   PGMO_TRY(h->d_pos.reserve(3 * n_c + 3));
   PGMO_TRY(h->d_poses.reserve(12 * n_c + 12));
   PGMO_TRY(h->d_valid.reserve(n_c + 1));
@@ -582,6 +615,7 @@ int pgmo_deform_set_controls_device(pgmo_deform_t* h, uint64_t n_c, const double
   PGMO_CHECK_ARG(n_c < 0x7FFFFFFFull);
   PGMO_TRY(ensureDevice(h->device));
   cudaStream_t st = pick(h, stream);
+  CallOrder call_order(h, st);
   // the window schedule is host logic: it needs position / stamp / validity (33 B per control)
   std::vector<double> pos(3 * n_c);
   std::vector<uint64_t> stamps(d_stamps_ns ? n_c : 0);
@@ -631,6 +665,7 @@ int pgmo_deform_update_poses(pgmo_deform_t* h, const double* poses12) {
   PGMO_CHECK_ARG(h != nullptr && poses12 != nullptr);
   PGMO_TRY(ensureDevice(h->device));
   cudaStream_t st = h->stream;
+  CallOrder call_order(h, st);
   h->has_poses = true;
   PGMO_TRY(h->d_poses.reserve(12 * h->n_c + 12));
   PGMO_CUDA(cudaMemcpyAsync(h->d_poses.ptr, poses12, 12 * h->n_c * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -643,6 +678,7 @@ int pgmo_deform_update_poses_device(pgmo_deform_t* h, const double* d_poses12, v
   PGMO_CHECK_ARG(h != nullptr && d_poses12 != nullptr);
   PGMO_TRY(ensureDevice(h->device));
   cudaStream_t st = pick(h, stream);
+  CallOrder call_order(h, st);
   h->has_poses = true;
   PGMO_TRY(h->d_poses.reserve(12 * h->n_c + 12));
   PGMO_CUDA(cudaMemcpyAsync(h->d_poses.ptr, d_poses12, 12 * h->n_c * sizeof(double), cudaMemcpyDeviceToDevice, st));
@@ -731,6 +767,7 @@ int pgmo_deform_update_poses_from_source(pgmo_deform_t* h, int buffer, uint64_t 
   }
   PGMO_CHECK_ARG(row_begin <= row_end && row_end <= h->n_c);
   cudaStream_t st = pick(h, stream);
+  CallOrder call_order(h, st);
   h->has_poses = true;
   PGMO_TRY(h->d_poses.reserve(12 * h->n_c + 12));
   PGMO_TRY(h->d_pose_f32.reserve(16 * h->n_c + 16));
@@ -772,6 +809,7 @@ int pgmo_deform_stamp_stretches_device(pgmo_deform_t* h, uint64_t n_local,
   PGMO_CHECK_ARG(n_local == 0 || d_stamps_ns != nullptr);
   PGMO_TRY(ensureDevice(h->device));
   cudaStream_t st = pick(h, stream);
+  CallOrder call_order(h, st);
   *n_stretches = 0;
   std::vector<uint64_t> s_stamp, s_len;
   PGMO_TRY(stampStretches(h, d_stamps_ns, nullptr, n_local, &s_stamp, &s_len, st));
@@ -787,7 +825,9 @@ int pgmo_deform_stamp_check_begin(pgmo_deform_t* h, uint64_t n_local, const uint
                                   void* stream) {
   PGMO_CHECK_ARG(h != nullptr && n_local > 0 && d_stamps_ns != nullptr);
   PGMO_TRY(ensureDevice(h->device));
-  return stampCheckBegin(h, d_stamps_ns, n_local, pick(h, stream));
+  cudaStream_t st = pick(h, stream);
+  CallOrder call_order(h, st);
+  return stampCheckBegin(h, d_stamps_ns, n_local, st);
 }
 
 int pgmo_deform_stamp_check_finish(pgmo_deform_t* h, int* changed) {
@@ -997,6 +1037,7 @@ static int runDeviceRange(pgmo_deform_t* h, uint64_t first_position, uint64_t n_
   PGMO_CHECK_ARG(d_x && d_y && d_z && d_out_x && d_out_y && d_out_z);
   PGMO_CHECK_ARG(d_assoc == nullptr || assoc_stride > 0);
   cudaStream_t st = pick(h, stream);
+  CallOrder call_order(h, st);
 
   uint8_t* status = d_processed;
   if (!status) {
@@ -1164,6 +1205,7 @@ static int runPipelined(pgmo_deform_t* h, uint64_t first_position, uint64_t n_po
                         float* out_x, float* out_y, float* out_z, uint8_t* processed,
                         const uint64_t* chunk_end) {
   cudaStream_t st = h->stream;
+  CallOrder call_order(h, st);
   const int n_chunks = pgmo_deform::kPipe;
   PGMO_TRY(h->d_status.reserve(n_pos));
   PGMO_TRY(ensureItems(h, first_position, n_pos, st));
@@ -1339,6 +1381,7 @@ int pgmo_deform_points(pgmo_deform_t* h, uint64_t n_v, const float* x, const flo
     }
   }
   cudaStream_t st = h->stream;
+  CallOrder call_order(h, st);
   PGMO_TRY(h->d_x.reserve(n_v));
   PGMO_TRY(h->d_y.reserve(n_v));
   PGMO_TRY(h->d_z.reserve(n_v));
@@ -1482,6 +1525,7 @@ int pgmo_deform_run_host_slab(pgmo_deform_t* h, uint64_t first_position, uint64_
     setLastError("pgmo_deform_run_host_slab: copy streams unavailable");
     return PGMO_ERR_CUDA;
   }
+  CallOrder call_order(h, h->stream);
   PGMO_TRY(h->d_x.reserve(n_local));
   PGMO_TRY(h->d_y.reserve(n_local));
   PGMO_TRY(h->d_z.reserve(n_local));
@@ -1527,6 +1571,7 @@ int pgmo_deform_mesh_device(pgmo_deform_t* h, uint64_t n_v, const void* d_vertic
   PGMO_CHECK_ARG((reinterpret_cast<uintptr_t>(d_vertices_xyzw) & 15u) == 0 &&
                  (reinterpret_cast<uintptr_t>(d_out_xyzw) & 15u) == 0);
   cudaStream_t st = pick(h, stream);
+  CallOrder call_order(h, st);
   const float4* in = static_cast<const float4*>(d_vertices_xyzw);
   float4* out = static_cast<float4*>(d_out_xyzw);
   PGMO_TRY(h->d_x.reserve(n_v));
@@ -1587,6 +1632,7 @@ int pgmo_deform_msg_to_cloud(pgmo_deform_t* h, uint64_t n_v, const double* verti
   PGMO_CHECK_ARG(vertices_xyz != nullptr && d_cloud_xyzw != nullptr);
   PGMO_CHECK_ARG(stamps_sec_nsec == nullptr || d_stamps_ns != nullptr);
   cudaStream_t st = pick(h, stream);
+  CallOrder call_order(h, st);
   PGMO_TRY(h->d_msg_pts.reserve(3 * n_v));
   PGMO_CUDA(cudaMemcpyAsync(h->d_msg_pts.ptr, vertices_xyz, 3 * n_v * sizeof(double),
                             cudaMemcpyHostToDevice, st));
@@ -1615,6 +1661,7 @@ int pgmo_deform_cloud_to_msg(pgmo_deform_t* h, uint64_t n_v, const void* d_cloud
   PGMO_CHECK_ARG(vertices_xyz != nullptr && d_cloud_xyzw != nullptr);
   PGMO_CHECK_ARG(stamps_sec_nsec == nullptr || d_stamps_ns != nullptr);
   cudaStream_t st = pick(h, stream);
+  CallOrder call_order(h, st);
   PGMO_TRY(h->d_msg_pts.reserve(3 * n_v));
   if (colors_rgba) PGMO_TRY(h->d_msg_colors.reserve(4 * n_v));
   if (stamps_sec_nsec) PGMO_TRY(h->d_msg_stamps.reserve(2 * n_v));
@@ -1643,6 +1690,7 @@ int pgmo_deform_mesh_msg(pgmo_deform_t* h, uint64_t n_v, const double* vertices_
   if (n_v == 0) return PGMO_NOOP;
   PGMO_CHECK_ARG(vertices_xyz != nullptr && out_vertices_xyz != nullptr);
   cudaStream_t st = h->stream;
+  CallOrder call_order(h, st);
   PGMO_TRY(h->d_msg_cloud.reserve(n_v));
   PGMO_TRY(h->d_msg_cloud_out.reserve(n_v));
   if (stamps_sec_nsec) PGMO_TRY(h->d_msg_ns.reserve(n_v));
@@ -1678,6 +1726,7 @@ int pgmo_deform_predeform(pgmo_deform_t* h, uint64_t n_v, const float* x, const 
     return PGMO_ERR_INVALID;
   }
   cudaStream_t st = h->stream;
+  CallOrder call_order(h, st);
   const uint64_t n = n_v - start_idx;
   PGMO_TRY(h->d_x.reserve(n_v));
   PGMO_TRY(h->d_y.reserve(n_v));

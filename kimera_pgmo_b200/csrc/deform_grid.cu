@@ -500,3 +500,13 @@ cudaError_t launchDeformKnnBlendGrid(const DeformArgs& args, const GridArgs& gar
 }
 
 }  // namespace pgmo
+
+// CUDA loads a kernel lazily at its first launch (tens to hundreds of ms for a module): pull
+// every kernel of this file in when a handle is created instead of inside a message stream.
+namespace pgmo {
+void preloadDeformGridKernels() {
+  cudaFuncAttributes attr;
+  cudaFuncGetAttributes(&attr, buildRunGridsKernel);
+  cudaGetLastError();
+}
+}  // namespace pgmo

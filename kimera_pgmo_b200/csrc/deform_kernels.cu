@@ -402,3 +402,21 @@ cudaError_t launchSoaToAos(uint64_t n, const float4* in, const float* x, const f
 }
 
 }  // namespace pgmo
+
+// CUDA loads a kernel lazily at its first launch (tens to hundreds of ms for a module): pull
+// every kernel of this file in when a handle is created instead of inside a message stream.
+namespace pgmo {
+void preloadDeformMiscKernels() {
+  cudaFuncAttributes attr;
+  cudaFuncGetAttributes(&attr, stampStretchKernel);
+  cudaFuncGetAttributes(&attr, deformResolveKernel);
+  cudaFuncGetAttributes(&attr, deformStepDoneKernel);
+  cudaFuncGetAttributes(&attr, predeformKernel);
+  cudaFuncGetAttributes(&attr, buildControlTablesKernel);
+  cudaFuncGetAttributes(&attr, pullBuildPoseTablesKernel);
+  cudaFuncGetAttributes(&attr, applyScheduleKernel);
+  cudaFuncGetAttributes(&attr, aosToSoaKernel);
+  cudaFuncGetAttributes(&attr, soaToAosKernel);
+  cudaGetLastError();
+}
+}  // namespace pgmo

@@ -481,6 +481,8 @@ int pgmo_delta_create(double resolution, int device, pgmo_delta_t** out) {
     return PGMO_ERR_CUDA;
   }
   cudaMemsetAsync(h->counters.ptr, 0, kDcCount * sizeof(unsigned long long), h->stream);
+  preloadDeltaKernels();
+  preloadCommonKernels();
   *out = h;
   return PGMO_OK;
 }

@@ -872,3 +872,36 @@ cudaError_t launchDeltaCopySegments(const uint4* segs, uint32_t n_segs, const ui
 }
 
 }  // namespace pgmo
+
+// CUDA loads a kernel lazily at its first launch (tens to hundreds of ms for a module): pull
+// every kernel of this file in when a handle is created instead of inside a message stream.
+namespace pgmo {
+void preloadDeltaKernels() {
+  cudaFuncAttributes attr;
+  cudaFuncGetAttributes(&attr, scanTiles3Kernel);
+  cudaFuncGetAttributes(&attr, initTableKernel);
+  cudaFuncGetAttributes(&attr, rehashKernel);
+  cudaFuncGetAttributes(&attr, addInsertKernel);
+  cudaFuncGetAttributes(&attr, addCountKernel);
+  cudaFuncGetAttributes(&attr, addApplyKernel);
+  cudaFuncGetAttributes(&attr, addFaceMapKernel);
+  cudaFuncGetAttributes(&attr, releaseFlagKernel);
+  cudaFuncGetAttributes(&attr, releaseApplyKernel);
+  cudaFuncGetAttributes(&attr, activeCountKernel);
+  cudaFuncGetAttributes(&attr, activeApplyKernel);
+  cudaFuncGetAttributes(&attr, remapFacesKernel);
+  cudaFuncGetAttributes(&attr, edgeInsertKernel);
+  cudaFuncGetAttributes(&attr, edgeDecideKernel);
+  cudaFuncGetAttributes(&attr, flagCountKernel);
+  cudaFuncGetAttributes(&attr, appendFacesKernel);
+  cudaFuncGetAttributes(&attr, pendingRemapKernel);
+  cudaFuncGetAttributes(&attr, classifyPendingKernel);
+  cudaFuncGetAttributes(&attr, archiveFacesKernel);
+  cudaFuncGetAttributes(&attr, smallBlockKernel);
+  cudaFuncGetAttributes(&attr, compactMoveKernel);
+  cudaFuncGetAttributes(&attr, renumberVoxelsKernel);
+  cudaFuncGetAttributes(&attr, setCounterKernel);
+  cudaFuncGetAttributes(&attr, copySegmentsKernel);
+  cudaGetLastError();
+}
+}  // namespace pgmo

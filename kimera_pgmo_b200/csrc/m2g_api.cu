@@ -205,6 +205,8 @@ int pgmo_m2g_create(int device, pgmo_m2g_t** out) {
     pgmo_m2g_destroy(h);
     return rc;
   }
+  preloadM2gKernels();
+  preloadCommonKernels();
   *out = h;
   return PGMO_OK;
 }
@@ -391,3 +393,15 @@ int pgmo_m2g_device_view(pgmo_m2g_t* h, const int64_t** d_mesh_to_graph, uint64_
 }
 
 }  // extern "C"
+
+// CUDA loads a kernel lazily at its first launch (tens to hundreds of ms for a module): pull
+// every kernel of this file in when a handle is created instead of inside a message stream.
+namespace pgmo {
+void preloadM2gKernels() {
+  cudaFuncAttributes attr;
+  cudaFuncGetAttributes(&attr, m2gApplyKernel);
+  cudaFuncGetAttributes(&attr, m2gFlagKernel);
+  cudaFuncGetAttributes(&attr, m2gGatherKernel);
+  cudaGetLastError();
+}
+}  // namespace pgmo

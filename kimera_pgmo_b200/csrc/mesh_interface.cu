@@ -86,3 +86,13 @@ extern "C" int pgmo_voxblox_decode(int device, uint32_t n_blocks, const int32_t*
   PGMO_CUDA(cudaMemcpy(rgba_out, d_rgba.ptr, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
   return PGMO_OK;
 }
+
+// CUDA loads a kernel lazily at its first launch (tens to hundreds of ms for a module): pull
+// every kernel of this file in when a handle is created instead of inside a message stream.
+namespace pgmo {
+void preloadMeshInterfaceKernels() {
+  cudaFuncAttributes attr;
+  cudaFuncGetAttributes(&attr, voxbloxDecodeKernel);
+  cudaGetLastError();
+}
+}  // namespace pgmo

@@ -89,3 +89,14 @@ cudaError_t launchCloudToMsg(uint64_t n, const float4* cloud, const uint64_t* st
 }
 
 }  // namespace pgmo
+
+// CUDA loads a kernel lazily at its first launch (tens to hundreds of ms for a module): pull
+// every kernel of this file in when a handle is created instead of inside a message stream.
+namespace pgmo {
+void preloadMeshMsgKernels() {
+  cudaFuncAttributes attr;
+  cudaFuncGetAttributes(&attr, msgToCloudKernel);
+  cudaFuncGetAttributes(&attr, cloudToMsgKernel);
+  cudaGetLastError();
+}
+}  // namespace pgmo

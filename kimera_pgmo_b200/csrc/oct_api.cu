@@ -609,6 +609,10 @@ int pgmo_oct_create(double resolution, int device, pgmo_oct_t** out) {
   cudaMemsetAsync(h->counts.ptr, 0, 16 * sizeof(unsigned long long), h->stream);
   cudaMemsetAsync(h->flags32.ptr, 0, 4 * sizeof(uint32_t), h->stream);
   cudaStreamSynchronize(h->stream);
+  preloadOctTreeKernels();
+  preloadOctApiKernels();
+  preloadMeshInterfaceKernels();
+  preloadCommonKernels();
   *out = h;
   return PGMO_OK;
 }
@@ -1057,3 +1061,27 @@ int pgmo_oct_last_outputs(pgmo_oct_t* h, float* new_vertices_xyz, uint32_t* new_
 }
 
 }  // extern "C"
+
+// CUDA loads a kernel lazily at its first launch (tens to hundreds of ms for a module): pull
+// every kernel of this file in when a handle is created instead of inside a message stream.
+namespace pgmo {
+void preloadOctApiKernels() {
+  cudaFuncAttributes attr;
+  cudaFuncGetAttributes(&attr, octTriEndKernel);
+  cudaFuncGetAttributes(&attr, octCandFlagsKernel);
+  cudaFuncGetAttributes(&attr, octGatherCandKernel);
+  cudaFuncGetAttributes(&attr, octScatterRankKernel);
+  cudaFuncGetAttributes(&attr, octTempReindexKernel);
+  cudaFuncGetAttributes(&attr, octFaceCheckKernel);
+  cudaFuncGetAttributes(&attr, octCommitVerticesKernel);
+  cudaFuncGetAttributes(&attr, octReindexKernel);
+  cudaFuncGetAttributes(&attr, octAppendNewIndicesKernel);
+  cudaFuncGetAttributes(&attr, octFaceClassifyKernel);
+  cudaFuncGetAttributes(&attr, octFaceFinalizeKernel);
+  cudaFuncGetAttributes(&attr, octCommitFacesKernel);
+  cudaFuncGetAttributes(&attr, octPolyRehashKernel);
+  cudaFuncGetAttributes(&attr, octPruneFlagsKernel);
+  cudaFuncGetAttributes(&attr, octPruneGatherKernel);
+  cudaGetLastError();
+}
+}  // namespace pgmo

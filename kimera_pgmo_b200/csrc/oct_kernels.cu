@@ -604,3 +604,20 @@ cudaError_t launchOctDecideTemp(const OctFrames* frames, OctTable table, const f
 }
 
 }  // namespace pgmo
+
+// CUDA loads a kernel lazily at its first launch (tens to hundreds of ms for a module): pull
+// every kernel of this file in when a handle is created instead of inside a message stream.
+namespace pgmo {
+void preloadOctTreeKernels() {
+  cudaFuncAttributes attr;
+  cudaFuncGetAttributes(&attr, octGrowKernel);
+  cudaFuncGetAttributes(&attr, octInsertKernel);
+  cudaFuncGetAttributes(&attr, octRootChainKernel);
+  cudaFuncGetAttributes(&attr, octQueryPersistentKernel);
+  cudaFuncGetAttributes(&attr, octDecideTempKernel);
+  cudaFuncGetAttributes(&attr, cellInsertKernel);
+  cudaFuncGetAttributes(&attr, cellQueryPersistentKernel);
+  cudaFuncGetAttributes(&attr, cellDecideTempKernel);
+  cudaGetLastError();
+}
+}  // namespace pgmo

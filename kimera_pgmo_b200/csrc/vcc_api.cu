@@ -117,6 +117,11 @@ struct BlockDevState {
 
 struct pgmo_vcc {
   bool poisoned = false;  // a device-side error was reported after state had changed
+  // pgmo_vcc_integrate_device may queue on a caller's stream: the event marks the end of that
+  // work and every later call makes the stream it uses wait for it (calls on one handle take
+  // effect in call order whatever streams they were given)
+  cudaEvent_t foreign_done = nullptr;
+  cudaStream_t foreign_stream = nullptr;  // non-null: work may still be running there
   int device = 0;
   double resolution = 0.0;
   cudaStream_t stream = nullptr;
@@ -191,7 +196,17 @@ VccIndexState indexStateOf(pgmo_vcc_t* h) {
   return s;
 }
 
+// `st` is about to be used: order it after what an earlier call left on another stream
+int orderAfterForeign(pgmo_vcc_t* h, cudaStream_t st) {
+  if (h->foreign_stream && h->foreign_stream != st) {
+    PGMO_CUDA(cudaStreamWaitEvent(st, h->foreign_done, 0));
+    h->foreign_stream = nullptr;
+  }
+  return PGMO_OK;
+}
+
 int syncCounters(pgmo_vcc_t* h, cudaStream_t st) {
+  PGMO_TRY(orderAfterForeign(h, st));
   const size_t n = kVccNumGlobal + h->pending_blocks.size();
   PGMO_TRY(h->h_counters.reserve(n));
   PGMO_CUDA(cudaMemcpyAsync(h->h_counters.ptr, h->counters.ptr, n * sizeof(unsigned long long),
@@ -463,9 +478,11 @@ int pgmo_vcc_create(double resolution, int device, pgmo_vcc_t** out) {
   PGMO_CHECK_ARG(h != nullptr);
   h->device = device;
   h->resolution = resolution;
-  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->foreign_done, cudaEventDisableTiming) != cudaSuccess) {
+    if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
-    setLastError("cudaStreamCreateWithFlags failed");
+    setLastError("cudaStreamCreateWithFlags / cudaEventCreateWithFlags failed");
     return PGMO_ERR_CUDA;
   }
   int rc = h->counters.reserve(kVccNumGlobal + 64);
@@ -479,6 +496,9 @@ int pgmo_vcc_create(double resolution, int device, pgmo_vcc_t** out) {
     pgmo_vcc_destroy(h);
     return rc;
   }
+  preloadVccKernels();
+  preloadMeshInterfaceKernels();
+  preloadCommonKernels();
   *out = h;
   return PGMO_OK;
 }
@@ -486,10 +506,12 @@ int pgmo_vcc_create(double resolution, int device, pgmo_vcc_t** out) {
 void pgmo_vcc_destroy(pgmo_vcc_t* h) {
   if (!h) return;
   cudaSetDevice(h->device);
+  if (h->foreign_stream) cudaEventSynchronize(h->foreign_done);
   if (h->stream) {
     cudaStreamSynchronize(h->stream);
     cudaStreamDestroy(h->stream);
   }
+  if (h->foreign_done) cudaEventDestroy(h->foreign_done);
   delete h;
 }
 
@@ -503,8 +525,13 @@ int pgmo_vcc_integrate_device(pgmo_vcc_t* h, uint32_t n_blocks, const int32_t* b
   cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->stream;
   const uint64_t n_total = n_blocks ? block_offsets[n_blocks] : 0;
   PGMO_CHECK_ARG(n_total == 0 || (d_xyz && d_remap_out));
-  return integrateCore(h, n_blocks, block_idx_xyz, block_offsets, d_xyz, d_rgba, stamp_s,
-                       d_remap_out, nullptr, st);
+  PGMO_TRY(orderAfterForeign(h, st));
+  const int rc = integrateCore(h, n_blocks, block_idx_xyz, block_offsets, d_xyz, d_rgba, stamp_s,
+                               d_remap_out, nullptr, st);
+  // no host synchronisation here: remember where the work runs
+  PGMO_CUDA(cudaEventRecord(h->foreign_done, st));
+  h->foreign_stream = st;
+  return rc;
 }
 
 int pgmo_vcc_integrate(pgmo_vcc_t* h, uint32_t n_blocks, const int32_t* block_idx_xyz,
@@ -514,6 +541,7 @@ int pgmo_vcc_integrate(pgmo_vcc_t* h, uint32_t n_blocks, const int32_t* block_id
   PGMO_CHECK_ARG(n_blocks == 0 || (block_idx_xyz && block_offsets));
   PGMO_TRY(ensureDevice(h->device));
   cudaStream_t st = h->stream;
+  PGMO_TRY(orderAfterForeign(h, st));
   const uint64_t n_total = n_blocks ? block_offsets[n_blocks] : 0;
   PGMO_CHECK_ARG(n_total == 0 || (xyz && remap_out));
   PGMO_TRY(h->d_xyz.reserve(3 * n_total + 3));
@@ -547,6 +575,7 @@ int pgmo_vcc_integrate_voxblox(pgmo_vcc_t* h, uint32_t n_blocks, const int32_t* 
   PGMO_CHECK_ARG(n_blocks == 0 || (block_idx_xyz && block_offsets));
   PGMO_TRY(ensureDevice(h->device));
   cudaStream_t st = h->stream;
+  PGMO_TRY(orderAfterForeign(h, st));
   const uint64_t n_total = n_blocks ? block_offsets[n_blocks] : 0;
   PGMO_CHECK_ARG(n_total == 0 || remap_out);
   PGMO_TRY(h->d_xyz.reserve(3 * n_total + 3));
@@ -578,6 +607,7 @@ int pgmo_vcc_prune(pgmo_vcc_t* h, double earliest_s) {
   for (const auto& kv : h->block_update_times) {  // iteration order of the reference's map
     if (kv.second <= earliest_s) to_clear.push_back(kv.first);
   }
+  PGMO_TRY(orderAfterForeign(h, h->stream));
   return pruneBlocks(h, to_clear, h->stream);
 }
 
@@ -589,6 +619,7 @@ int pgmo_vcc_clear_blocks(pgmo_vcc_t* h, uint32_t n_blocks, const int32_t* block
   for (uint32_t b = 0; b < n_blocks; ++b) {
     to_clear[b] = {block_idx_xyz[3 * b], block_idx_xyz[3 * b + 1], block_idx_xyz[3 * b + 2]};
   }
+  PGMO_TRY(orderAfterForeign(h, h->stream));
   return pruneBlocks(h, to_clear, h->stream);
 }
 
@@ -596,6 +627,7 @@ int pgmo_vcc_device_view(pgmo_vcc_t* h, const void** d_vertices_xyzw, const uint
                          uint64_t* n_vertices) {
   PGMO_CHECK_ARG(h != nullptr && n_vertices != nullptr);
   PGMO_TRY(ensureDevice(h->device));
+  PGMO_TRY(orderAfterForeign(h, h->stream));
   if (h->pending) PGMO_TRY(syncCounters(h, h->stream));
   PGMO_CUDA(cudaStreamSynchronize(h->stream));  // everything queued so far is visible to any stream
   if (d_vertices_xyzw) *d_vertices_xyzw = h->vertices.ptr;
@@ -623,6 +655,7 @@ int pgmo_vcc_snapshot(pgmo_vcc_t* h, float* vertices_xyz, uint32_t* vertices_rgb
   PGMO_CHECK_ARG(h != nullptr);
   PGMO_TRY(ensureDevice(h->device));
   cudaStream_t st = h->stream;
+  PGMO_TRY(orderAfterForeign(h, st));
   if (h->pending) PGMO_TRY(syncCounters(h, st));
   const uint64_t n = h->max_index;
   if ((vertices_xyz || vertices_rgba) && n) {

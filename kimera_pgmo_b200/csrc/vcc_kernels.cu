@@ -420,3 +420,24 @@ cudaError_t launchVccCompactLive(const uint8_t* live, uint64_t n, uint64_t* out,
 }
 
 }  // namespace pgmo
+
+// CUDA loads a kernel lazily at its first launch (tens to hundreds of ms for a module): pull
+// every kernel of this file in when a handle is created instead of inside a message stream.
+namespace pgmo {
+void preloadVccKernels() {
+  cudaFuncAttributes attr;
+  cudaFuncGetAttributes(&attr, vccInsertKernel);
+  cudaFuncGetAttributes(&attr, vccCountCreatorsKernel);
+  cudaFuncGetAttributes(&attr, vccScanTilesKernel);
+  cudaFuncGetAttributes(&attr, vccAssignKernel);
+  cudaFuncGetAttributes(&attr, vccCommitNewKernel);
+  cudaFuncGetAttributes(&attr, vccWriteKernel);
+  cudaFuncGetAttributes(&attr, vccReleaseKernel);
+  cudaFuncGetAttributes(&attr, vccInitTableKernel);
+  cudaFuncGetAttributes(&attr, vccRehashKernel);
+  cudaFuncGetAttributes(&attr, countLiveKernel);
+  cudaFuncGetAttributes(&attr, writeLiveKernel);
+  cudaFuncGetAttributes(&attr, copyTotalKernel);
+  cudaGetLastError();
+}
+}  // namespace pgmo

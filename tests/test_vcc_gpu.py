@@ -223,3 +223,35 @@ def test_two_handles_two_threads(capi, oracle):
         for m, (blocks, offsets, xyz, rgba, t) in enumerate(msgs):
             idx, _, _ = ora.integrate(blocks, offsets, xyz, rgba, t)
             np.testing.assert_array_equal(results[name][m].astype(np.int64), idx)
+
+
+def test_device_resident_integrate_on_a_caller_stream(capi):
+    """pgmo_vcc_integrate_device queues on the caller's stream, pgmo_vcc_prune on the handle's
+    own: calls on one handle take effect in call order (the bench's device-resident loop).  The
+    stored state must equal the host-buffer path's on the same messages."""
+    import torch
+    dev = torch.device("cuda", 0)
+    msgs = list(synth.compression_stream(60, 50_000, n_blocks=1))
+    host = capi.VccHandle(0.05)
+    for blocks, offsets, xyz, rgba, t in msgs:
+        host.prune(t - 3.0)
+        host.integrate(blocks, offsets, xyz, rgba, t)
+    want = host.snapshot()
+    host.close()
+    side = torch.cuda.Stream(device=dev)
+    d_msgs = [(torch.from_numpy(x).to(dev), torch.from_numpy(c.view(np.int32)).to(dev))
+              for _, _, x, c, _ in msgs]
+    d_remap = torch.empty(50_000, dtype=torch.int64, device=dev)
+    torch.cuda.synchronize()
+    for rep in range(3):
+        gpu = capi.VccHandle(0.05)
+        with torch.cuda.stream(side):
+            for m, (blocks, offsets, _, _, t) in enumerate(msgs):
+                gpu.prune(t - 3.0)
+                gpu.integrate_device(blocks, offsets, d_msgs[m][0], d_msgs[m][1], t, d_remap,
+                                     side.cuda_stream if m % 5 else 0)
+        got = gpu.snapshot()
+        gpu.close()
+        for key in ("vertices", "stamps", "active", "polygons"):
+            np.testing.assert_array_equal(got[key], want[key], err_msg=f"{key}, repetition {rep}")
+        np.testing.assert_array_equal(np.sort(got["invalid"]), np.sort(want["invalid"]))
