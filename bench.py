@@ -195,7 +195,10 @@ def run_reference(args):
         "unit": "vertices/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, n_total, n_ctrl),
+        "config": dict(workload_config(args, n_total, n_ctrl),
+                       reference_sample=f"each step times the first {sample} vertices of the workload; "
+                                        "`value` is that per-vertex rate (extrapolated to the full "
+                                        "mesh, not a full-mesh run), `ms_per_step` is per sample"),
         "cpu_baseline": {"value": value, "unit": "vertices/s", "cores": 1, "kind": "port",
                          "sample": f"first {sample} vertices of the workload, full control table, "
                                    "oracle/liboracle.so (g++ -O2, single thread like the reference)"},
@@ -566,7 +569,10 @@ def run_b200(args):
 
         blend_bytes = BYTES_BLEND_PER_VERTEX if args.precision == "fp64" else BYTES_BLEND_PER_VERTEX_FP32
         blend_ms = mean("blend_ms", warm_infos)
-        achieved = blend_bytes * n_local / (blend_ms * 1e-3) / 1e9
+        # algorithmic bytes = 32 B per vertex, whatever the kernel moves on top of
+        # them (its association records and weights show up in `traffic` and in `own_bytes`)
+        achieved = BYTES_STEP_PER_VERTEX * n_local / (blend_ms * 1e-3) / 1e9
+        own = blend_bytes * n_local / (blend_ms * 1e-3) / 1e9
         f_search, f_blend = mean("search_ms", first_infos), mean("blend_ms", first_infos)
         f_achieved = BYTES_STEP_PER_VERTEX * n_local / ((f_search + f_blend) * 1e-3) / 1e9
         line = {
@@ -579,15 +585,18 @@ def run_b200(args):
                 "bound": "hbm", "kernel": "deformBlendCachedKernel", "achieved": achieved,
                 "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": load_ncu_traffic("blend_traffic.json"), "kernel_ms": blend_ms,
-                "bytes_per_vertex": blend_bytes,
-                "bytes_note": "the blend-only kernel's own bytes: xyz in, association record, "
-                              "k + 1 weights, xyz out, status",
+                "bytes_per_vertex": BYTES_STEP_PER_VERTEX,
+                "bytes_note": "SURVEY 8(d): 12 B xyz read + 8 B stamp read + 12 B xyz written per vertex",
+                "own_bytes": {
+                    "bytes_per_vertex": blend_bytes, "achieved": own, "frac": own / peak,
+                    "note": "what the blend-only kernel itself moves per vertex: xyz in, 16-byte "
+                            "association record, k + 1 weights, xyz out, status (= `traffic`)"},
+                "limiter": "shared-memory data pipe (pose-row gather: 35 LDS.128 per vertex, "
+                           "l1tex__data_pipe_lsu_wavefronts 87 % of peak; DESIGN.md 2.4)",
                 "search_ms": mean("search_ms", warm_infos),
                 "resolver_ms": mean("resolver_ms", warm_infos),
                 "stale_items": mean("stale_items", warm_infos),
                 "warm": all(r["warm"] for r in warm_infos),
-                "frac_at_32B": BYTES_STEP_PER_VERTEX * n_local / (blend_ms * 1e-3) / 1e9 / peak,
-                "step_bytes_per_vertex": BYTES_STEP_PER_VERTEX,
                 "step_frac": BYTES_STEP_PER_VERTEX * n_local / (ms_per_step * 1e-3) / 1e9 / peak,
             },
             "first_deform": {

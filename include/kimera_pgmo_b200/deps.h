@@ -30,6 +30,7 @@
 #include "kimera_pgmo/hashing.h"
 #include "kimera_pgmo/mesh_traits.h"
 #include "kimera_pgmo/pcl_mesh_traits.h"
+#include "kimera_pgmo/utils/common_functions.h"
 
 namespace kimera_pgmo_b200 {
 namespace traits = ::kimera_pgmo::traits;
@@ -40,6 +41,12 @@ using ::kimera_pgmo::HashedIndexMapping;
 using ::kimera_pgmo::IndexMapping;
 using ::kimera_pgmo::StampedCloud;
 using Timestamp = ::kimera_pgmo::traits::Timestamp;
+using ::kimera_pgmo::GetRobotPrefix;
+using ::kimera_pgmo::GetVertexPrefix;
+using ::kimera_pgmo::robot_id_to_prefix;
+using ::kimera_pgmo::robot_id_to_vertex_prefix;
+using ::kimera_pgmo::robot_prefix_to_id;
+using ::kimera_pgmo::vertex_prefix_to_id;
 }  // namespace kimera_pgmo_b200
 
 #else  // stand-ins
@@ -56,6 +63,33 @@ using IndexMapping = std::unordered_map<size_t, size_t>;
 using spatial_hash::BlockIndex;
 using spatial_hash::BlockIndices;
 using HashedIndexMapping = spatial_hash::IndexHashMap<IndexMapping>;
+
+// Robot id <-> gtsam::Symbol prefix (kimera_pgmo/utils/common_functions.h:19-81): robots 0..7 own
+// the pose prefixes 'a'..'h' and the mesh-vertex prefixes 's'..'z'; anything else has no prefix.
+constexpr size_t kMaxRobots = 8;
+inline char GetRobotPrefix(size_t robot_id) {
+  return robot_id < kMaxRobots ? static_cast<char>('a' + robot_id) : '\0';
+}
+inline char GetVertexPrefix(size_t robot_id) {
+  return robot_id < kMaxRobots ? static_cast<char>('s' + robot_id) : '\0';
+}
+namespace detail {
+inline std::map<size_t, char> idToPrefixMap(char first) {
+  std::map<size_t, char> m;
+  for (size_t id = 0; id < kMaxRobots; ++id) m[id] = static_cast<char>(first + id);
+  return m;
+}
+inline std::map<char, size_t> prefixToIdMap(char first) {
+  std::map<char, size_t> m;
+  for (size_t id = 0; id < kMaxRobots; ++id) m[static_cast<char>(first + id)] = id;
+  return m;
+}
+}  // namespace detail
+// the reference's four lookup tables, same names (callers use .count() / .at())
+inline const std::map<size_t, char> robot_id_to_prefix = detail::idToPrefixMap('a');
+inline const std::map<char, size_t> robot_prefix_to_id = detail::prefixToIdMap('a');
+inline const std::map<size_t, char> robot_id_to_vertex_prefix = detail::idToPrefixMap('s');
+inline const std::map<char, size_t> vertex_prefix_to_id = detail::prefixToIdMap('s');
 
 namespace traits {
 using Color = std::array<std::uint8_t, 4>;
@@ -193,3 +227,16 @@ Timestamp get_timestamp(const T& vertices, size_t i) {
 }  // namespace kimera_pgmo_b200
 
 #endif  // KIMERA_PGMO_B200_REAL_DEPS
+
+
+namespace kimera_pgmo_b200 {
+// robot id of a pose / vertex prefix, -1 when the character is neither
+inline int GetRobotIdFromPrefix(char prefix) {
+  const auto it = robot_prefix_to_id.find(prefix);
+  return it == robot_prefix_to_id.end() ? -1 : static_cast<int>(it->second);
+}
+inline int GetRobotIdFromVertexPrefix(char prefix) {
+  const auto it = vertex_prefix_to_id.find(prefix);
+  return it == vertex_prefix_to_id.end() ? -1 : static_cast<int>(it->second);
+}
+}  // namespace kimera_pgmo_b200

@@ -73,6 +73,23 @@ class Rot3 {
  public:
   Rot3() = default;
   explicit Rot3(const Eigen::Matrix3d& R) : R_(R) {}
+  // gtsam::Rot3(w, x, y, z) = Eigen::Quaterniond(w, x, y, z).toRotationMatrix(), operation for
+  // operation (what DeformationGraph::load builds from a NODE line)
+  Rot3(double w, double x, double y, double z) {
+    const double tx = 2.0 * x, ty = 2.0 * y, tz = 2.0 * z;
+    const double twx = tx * w, twy = ty * w, twz = tz * w;
+    const double txx = tx * x, txy = ty * x, txz = tz * x;
+    const double tyy = ty * y, tyz = tz * y, tzz = tz * z;
+    R_(0, 0) = 1.0 - (tyy + tzz);
+    R_(0, 1) = txy - twz;
+    R_(0, 2) = txz + twy;
+    R_(1, 0) = txy + twz;
+    R_(1, 1) = 1.0 - (txx + tzz);
+    R_(1, 2) = tyz - twx;
+    R_(2, 0) = txz - twy;
+    R_(2, 1) = tyz + twx;
+    R_(2, 2) = 1.0 - (txx + tyy);
+  }
   static Rot3 Rz(double t) {
     Eigen::Matrix3d R;
     R(0, 0) = std::cos(t);
