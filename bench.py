@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-compression", action="store_true")
+    ap.add_argument("--no-tie-sweep", action="store_true")
     ap.add_argument("--no-config3", action="store_true")
     ap.add_argument("--only-config3", action="store_true")
     ap.add_argument("--config3-vertices-per-robot", type=int, default=25_000_000)
@@ -637,6 +638,8 @@ def run_b200(args):
                           "(the reference path is single-threaded)"}
         if world == 1 and not args.no_compression:
             line["compression"] = bench_compression(local_rank, with_cpu=not args.no_cpu_baseline)
+        if world == 1 and not args.no_tie_sweep:
+            line["tie_sweep"] = bench_tie_sweep(local_rank, n_local, n_ctrl)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -851,6 +854,62 @@ def bench_config3(args, world, rank, local_rank, dev, stream, flag_group, peak):
 
 
 
+def bench_tie_sweep(dev_index, n_v, n_c, fractions=(1e-4, 1e-3, 1e-2)):
+    """configs[2] with exact float-distance ties planted at a chosen rate (synth.
+    deformation_case_with_ties): what the PCL tie-order resolver (K4) costs when vertices sit on
+    a lattice.  Inputs resident in HBM, device times from the handle's own CUDA events (search /
+    resolver / blend): the first deformation (every vertex searched, tied ones resolved) and the
+    pose-only step that follows (blend from the association records, the resolver's included)."""
+    import torch
+
+    from kimera_pgmo_b200 import capi, synth
+    dev = torch.device("cuda", dev_index)
+    stream = torch.cuda.current_stream().cuda_stream
+    rows = []
+    for f in fractions:
+        case, tied = synth.deformation_case_with_ties(n_v, n_c, f)
+        d = {k: torch.from_numpy(case[k]).to(dev) for k in ("x", "y", "z")}
+        d_stamps = torch.from_numpy(case["stamps"].view(np.int64)).to(dev)
+        d_out = [torch.empty(n_v, dtype=torch.float32, device=dev) for _ in range(3)]
+        d_poses = torch.from_numpy(case["poses"]).to(dev)
+        h = capi.DeformHandle(dev_index)
+        h.set_profiling(True)
+        h.set_controls(case["ctrl_xyz"], case["ctrl_stamps"], case["valid"], case["poses"])
+        ss, sl = h.stamp_stretches_device(d_stamps, n_v, stream)
+        assert h.build_schedule(ss, sl, n_v, K_NEIGHBOURS, TOL_T) == 0
+
+        def run():
+            h.update_poses_device(d_poses, stream)
+            n = h.run_device(0, n_v, d["x"], d["y"], d["z"], d_out[0], d_out[1], d_out[2],
+                             want_resolved=True, stream=stream)
+            return n, h.last_step_info()
+
+        h.set_assoc_cache(False)  # every call searches again
+        first = [run() for _ in range(3)][-1]
+        h.set_assoc_cache(True)
+        run()
+        warm = []
+        for i in range(5):
+            d_poses[:, 9:] += 0.01
+            warm.append(run()[1])
+        h.close()
+        n_res, fi = first
+        rows.append({
+            "tie_fraction_planted": f, "tied_vertices": int(tied.size),
+            "resolved_by_tie_kernel": int(n_res),
+            "first_deform": {"search_ms": fi["search_ms"], "resolver_ms": fi["resolver_ms"],
+                             "blend_ms": fi["blend_ms"], "total_ms": fi["total_ms"]},
+            "pose_only_step": {"total_ms": float(np.median([w["total_ms"] for w in warm])),
+                               "resolver_ms": float(np.median([w["resolver_ms"] for w in warm])),
+                               "warm": all(w["warm"] for w in warm)},
+        })
+        del case, d, d_stamps, d_out, d_poses
+        torch.cuda.empty_cache()
+    return {"workload": f"{n_v} vertices, {n_c} control points snapped to a 2^-5 m lattice, k=4; "
+                        "a fraction of the vertices moved to the exact midpoint of two control points",
+            "timing": "inputs in HBM, CUDA events inside the handle (kernels only)", "rows": rows}
+
+
 def bench_compression(dev_index, n_messages=200, verts=50_000, with_cpu=True, n_octree=40):
     """configs[1]: VoxelClearingCompression of streamed 50k-vertex mesh blocks at 0.05 m on one GPU.
     Three numbers: device-resident throughput (inputs in HBM, pgmo_vcc_integrate_device, CUDA
@@ -932,7 +991,8 @@ def bench_compression(dev_index, n_messages=200, verts=50_000, with_cpu=True, n_
             per_msg.append(1e3 * (time.perf_counter() - t1))
         oct_ms = float(np.mean(per_msg[w2:]))
         out["octree"] = {"value": verts / (oct_ms * 1e-3), "unit": "vertices/s", "ms_per_message": oct_ms,
-                         "ms_p50": float(np.median(per_msg[w2:])), "ms_max": float(np.max(per_msg[w2:])),
+                         "ms_p50": float(np.median(per_msg[w2:])), "ms_max": float(np.max(per_msg[w2:])), "ms_max_at_message": int(np.argmax(per_msg[w2:])) + w2,
+                        "slowest_messages": [[int(i) + w2, round(float(per_msg[w2:][i]), 3)] for i in np.argsort(per_msg[w2:])[::-1][:3]],
                          "api": "pgmo_oct_prune + pgmo_oct_integrate (host buffers)",
                          "stored_vertices": int(oc.sizes()[0])}
         oc.close()
@@ -966,7 +1026,8 @@ def bench_compression(dev_index, n_messages=200, verts=50_000, with_cpu=True, n_
             d_ms = float(np.mean(per_msg[w2:]))
             key = "delta" if n_blocks == 1 else "delta_64_blocks"
             out[key] = {"value": verts / (d_ms * 1e-3), "unit": "vertices/s", "ms_per_message": d_ms,
-                        "ms_p50": float(np.median(per_msg[w2:])), "ms_max": float(np.max(per_msg[w2:])),
+                        "ms_p50": float(np.median(per_msg[w2:])), "ms_max": float(np.max(per_msg[w2:])), "ms_max_at_message": int(np.argmax(per_msg[w2:])) + w2,
+                        "slowest_messages": [[int(i) + w2, round(float(per_msg[w2:][i]), 3)] for i in np.argsort(per_msg[w2:])[::-1][:3]],
                         "api": "pgmo_delta_archive_by_time + pgmo_delta_update (host buffers)",
                         "active_vertices": int(dc.sizes()[10])}
             dc.close()
@@ -1002,7 +1063,8 @@ def bench_compression(dev_index, n_messages=200, verts=50_000, with_cpu=True, n_
         f_ms = float(np.mean(per_msg[w2:]))
         pairs_gpu = m2g.mesh_to_graph()
         out["frontend"] = {"value": verts / (f_ms * 1e-3), "unit": "vertices/s", "ms_per_message": f_ms,
-                           "ms_p50": float(np.median(per_msg[w2:])), "ms_max": float(np.max(per_msg[w2:])),
+                           "ms_p50": float(np.median(per_msg[w2:])), "ms_max": float(np.max(per_msg[w2:])), "ms_max_at_message": int(np.argmax(per_msg[w2:])) + w2,
+                        "slowest_messages": [[int(i) + w2, round(float(per_msg[w2:][i]), 3)] for i in np.argsort(per_msg[w2:])[::-1][:3]],
                            "api": "pgmo_vcc_prune/integrate + pgmo_oct_prune/integrate + pgmo_m2g_update (host buffers)",
                            "mesh_to_graph_pairs": int(len(pairs_gpu[0]))}
         for c in (full, graph, m2g):

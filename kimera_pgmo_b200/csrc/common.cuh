@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <string>
 
 #include "pgmo_b200.h"
@@ -45,6 +46,13 @@ int ensureDevice(int device);
 // Grow-only device buffer (never shrinks: handles are long-lived and re-used per message).
 // cudaMalloc / cudaFree cost tens to hundreds of milliseconds on this platform: callers on a
 // message stream ask for generous head room when they have to grow.
+// PGMO_TRACE_ALLOC=1: every device / pinned allocation made after start-up is reported on stderr
+// (cudaMalloc and cudaFree cost 0.1 - 100 ms here: a steady-state message must not allocate)
+inline bool traceAlloc() {
+  static const bool on = std::getenv("PGMO_TRACE_ALLOC") != nullptr;
+  return on;
+}
+
 template <typename T>
 struct DevBuf {
   T* ptr = nullptr;
@@ -64,6 +72,7 @@ struct DevBuf {
     size_t new_cap = cap ? cap : 256;
     while (new_cap < n) new_cap += new_cap / 2 + 256;
     T* fresh = nullptr;
+    if (traceAlloc()) fprintf(stderr, "pgmo alloc: device %zu -> %zu bytes\n", cap * sizeof(T), new_cap * sizeof(T));
     PGMO_CUDA(cudaMalloc(&fresh, new_cap * sizeof(T)));
     if (ptr && keep_n) {
       PGMO_CUDA(cudaMemcpyAsync(fresh, ptr, keep_n * sizeof(T), cudaMemcpyDeviceToDevice, stream));
@@ -93,6 +102,7 @@ struct PinnedBuf {
     ptr = nullptr;
     cap = 0;
     size_t new_cap = n + n / 4 + 64;
+    if (traceAlloc()) fprintf(stderr, "pgmo alloc: pinned %zu bytes\n", new_cap * sizeof(T));
     PGMO_CUDA(cudaMallocHost(&ptr, new_cap * sizeof(T)));
     cap = new_cap;
     return PGMO_OK;

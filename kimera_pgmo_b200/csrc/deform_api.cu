@@ -80,6 +80,7 @@ struct pgmo_deform {
 
   // optional kernel timing (bench / roofline): events on the launching stream
   bool profiling = false;
+  uint32_t blend_copies_override = 0;  // PGMO_BLEND_COPIES: cap on the pose-row copies (0 = what fits)
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   bool ev_recorded = false;
   bool last_run_warm = false;
@@ -243,7 +244,7 @@ int finishControls(pgmo_deform_t* h, bool positions_changed, cudaStream_t st) {
   PGMO_TRY(h->d_ctrl_f4.reserve(h->n_c + 1));
   PGMO_TRY(h->d_pose_f32.reserve(16 * h->n_c + 16));
   PGMO_TRY(h->d_ctrl_key.reserve(h->n_c + 1));
-  PGMO_TRY(h->d_pose_rows.reserve(16 * h->n_c + 16));
+  PGMO_TRY(h->d_pose_rows.reserve(16 * h->n_c * kBlendCopies + 16));
   PGMO_CUDA(launchBuildControlTables(h->n_c, h->d_pos.ptr, h->has_poses ? h->d_poses.ptr : nullptr,
                                      h->d_ctrl_f4.ptr, h->d_pose_f32.ptr, h->d_pose_rows.ptr,
                                      h->d_class.ptr, positions_changed, st));
@@ -527,6 +528,7 @@ int pgmo_deform_create(int device, pgmo_deform_t** out) {
   preloadMeshMsgKernels();
   cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, device);
   if (const char* e = std::getenv("PGMO_ASSOC_CACHE")) h->cache_enabled = atoi(e) != 0;
+  if (const char* e = std::getenv("PGMO_BLEND_COPIES")) h->blend_copies_override = static_cast<uint32_t>(atoi(e));
   *out = h;
   return PGMO_OK;
 }
@@ -771,8 +773,8 @@ int pgmo_deform_update_poses_from_source(pgmo_deform_t* h, int buffer, uint64_t 
   h->has_poses = true;
   PGMO_TRY(h->d_poses.reserve(12 * h->n_c + 12));
   PGMO_TRY(h->d_pose_f32.reserve(16 * h->n_c + 16));
-  PGMO_TRY(h->d_pose_rows.reserve(16 * h->n_c + 16));
-  PGMO_CUDA(launchPullBuildPoseTables(row_begin, row_end,
+  PGMO_TRY(h->d_pose_rows.reserve(16 * h->n_c * kBlendCopies + 16));
+  PGMO_CUDA(launchPullBuildPoseTables(row_begin, row_end, h->n_c,
                                       h->pose_src + static_cast<uint64_t>(buffer) * 12 * h->pose_src_n,
                                       h->d_poses.ptr, h->d_pos.ptr, h->d_pose_f32.ptr,
                                       h->d_pose_rows.ptr, h->d_class.ptr, st));
@@ -1013,6 +1015,9 @@ static int prepareCache(pgmo_deform_t* h, int precision, cudaStream_t st, AssocC
   c->stale_items = h->d_stale_items.ptr;
   c->pose_rows = precision == PGMO_PRECISION_FP64 ? static_cast<const void*>(h->d_pose_rows.ptr)
                                                   : static_cast<const void*>(h->d_pose_f32.ptr);
+  c->plane_rows = h->n_c;
+  c->n_copies = h->blend_copies_override ? std::min<uint32_t>(h->blend_copies_override, blendCopiesFor(precision, h->widest_window))
+                                         : blendCopiesFor(precision, h->widest_window);
   c->ctrl_class = h->d_class.ptr;
   return PGMO_OK;
 }
@@ -1132,6 +1137,11 @@ static int runDeviceRange(pgmo_deform_t* h, uint64_t first_position, uint64_t n_
       }
       if (h->profiling) PGMO_CUDA(cudaEventRecord(h->ev[2], st));
       PGMO_CUDA(launchDeformResolve(a, ra, &c, precision, st));
+      // records that will be read again get their row copies placed (once per record: the
+      // search kernel and the resolver leave copy 0); counted with the resolver's time
+      if (h->cache_enabled && c.n_copies > 1) {
+        PGMO_CUDA(launchPlaceRecords(a, ga, c, h->d_items.ptr, i0, i1 - i0, warm, h->n_sms, st));
+      }
       if (h->profiling) PGMO_CUDA(cudaEventRecord(h->ev[3], st));
       PGMO_CUDA(launchDeformBlendCached(a, ga, c, h->d_items.ptr, i0, i1 - i0, precision, max_k, min_k,
                                         h->widest_window, warm ? 2 : 0, h->n_sms, st));
@@ -1310,6 +1320,11 @@ int pgmo_deform_last_timings(pgmo_deform_t* h, float* ms2, uint64_t* schedule_bu
 
 int pgmo_deform_set_assoc_cache(pgmo_deform_t* h, int enabled) {
   PGMO_CHECK_ARG(h != nullptr);
+  if (!h->cache_enabled && enabled) {
+    // records written while the cache was off never went through the placement pass: the next
+    // call searches again instead of blending from them
+    h->cache_cold_lo = h->cache_cold_hi = 0;
+  }
   h->cache_enabled = enabled != 0;
   return PGMO_OK;
 }

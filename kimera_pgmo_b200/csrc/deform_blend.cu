@@ -12,11 +12,15 @@
 //     run's window [lo, hi) — R(9) t(3) g(3) as 128-byte rows, one contiguous block of the
 //     table — arrive by ONE bulk asynchronous copy (cp.async.bulk, TMA engine; completion on an
 //     mbarrier) that overlaps the vertex loads.
-//   * The table stores 16-byte chunk c of row j at c ^ class(j), class = the colour of the
-//     control point's cell in a lattice colouring (AssocCache::class_inv_cell): the 8 lanes of a
-//     quarter warp read chunk c of the rows of control points that lie close together, and
-//     close-by points have different classes, i.e. different bank groups, instead of all
-//     hitting the same one.
+//   * The kernel is bound by the shared-memory data pipe: per vertex and neighbour a lane gathers
+//     a 120-byte row (7 LDS.128 + 1 LDS.64), an LDS.128 is served per quarter warp, and the 8
+//     lanes of a quarter warp want ~4.5 different rows (scripts/cache_stats.py): one wavefront
+//     only if those rows sit in different 16-byte bank groups.  The table therefore stores 16-byte
+//     chunk c of row j at c ^ class(j) (class = the colour of the control point in a colouring of
+//     the table, deform_api.cu: colourControls) — and stores every row kBlendCopies times under
+//     different classes.  A placement pass (placeRecordsKernel, below) over fresh records picks,
+//     per quarter warp and neighbour slot, copies whose bank groups differ: measured on the 10 M
+//     benchmark 1.69 -> ~1.1 wavefronts per quarter warp and LDS.128.
 //   * Vertices are loaded coalesced, fingerprinted (validating mode) and staged in shared
 //     memory; a lane takes the vertex of its record (records are in search order: neighbouring
 //     lanes share neighbours, equal addresses are broadcast), blends in the reference's
@@ -25,6 +29,7 @@
 //   * Validating mode: an item whose fingerprint differs from the one its records were computed
 //     for (or that has no records yet) is appended to the stale list and left untouched; the
 //     search kernel, the resolver and this kernel then run over that list.
+#include <algorithm>
 #include <cfloat>
 
 #include "deform_device.cuh"
@@ -35,12 +40,23 @@ namespace {
 
 using namespace dev;
 
-constexpr int kBThreads = 256;
-constexpr int kBWarps = kBThreads / 32;
-constexpr int kBChunk = kDeformChunk;
+// CTA shape: 256 threads x 4 CTAs per SM (PGMO_K3B_THREADS / PGMO_K3B_CTAS).  An item goes
+// through phases (vertices in, barrier, rows landed, blend, barrier, results out) and only other
+// CTAs of the SM fill the shared-memory pipe while one of them loads or stores: 512 x 2 — which
+// would leave room for kBlendCopies staged copies of the window's rows — measured 0.52 ms against
+// 0.42 ms per 10 M vertices with one copy, 0.46 ms with three.
+#ifndef PGMO_K3B_THREADS
+#define PGMO_K3B_THREADS 256
+#endif
 #ifndef PGMO_K3B_CTAS
 #define PGMO_K3B_CTAS 4
 #endif
+constexpr int kBThreads = PGMO_K3B_THREADS;
+constexpr int kBWarps = kBThreads / 32;
+constexpr int kBChunk = kDeformChunk;
+// shared memory one CTA may use so that PGMO_K3B_CTAS of them fit an SM (228 KB, 1 KB per CTA
+// reserved by the driver)
+constexpr size_t kBSmemBudget = (228u * 1024u - PGMO_K3B_CTAS * 1024u) / PGMO_K3B_CTAS;
 
 struct alignas(128) BlendSmemHead {
   float vx[kBChunk], vy[kBChunk], vz[kBChunk];  // vertices in, results out (same slots)
@@ -58,11 +74,14 @@ __device__ __forceinline__ void mbarInit(unsigned long long* bar, uint32_t count
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
-// one bulk copy global -> shared, completion (byte count) signalled on `bar`
-__device__ __forceinline__ void bulkLoad(void* dst, const void* src, uint32_t bytes,
-                                         unsigned long long* bar) {
+// bulk copies global -> shared: the barrier is told the total byte count once, every copy
+// signals its share on it
+__device__ __forceinline__ void expectTx(unsigned long long* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes)
                : "memory");
+}
+__device__ __forceinline__ void bulkLoad(void* dst, const void* src, uint32_t bytes,
+                                         unsigned long long* bar) {
   asm volatile(
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
           smemAddr(dst)),
@@ -121,7 +140,7 @@ template <int PREC, int NB, bool IN_PLACE>
 __device__ __forceinline__ void blendVertices(const DeformArgs& a, const AssocCache& cache,
                                               BlendSmemHead& S, const unsigned char* rows,
                                               uint64_t p_base, int count, int nb_runtime,
-                                              uint32_t lo) {
+                                              uint32_t lo, uint32_t staged_rows) {
   const int t = threadIdx.x;
   const int nb = NB > 0 ? NB : nb_runtime;
   const uint4* rec0 = reinterpret_cast<const uint4*>(cache.rec);
@@ -158,24 +177,31 @@ __device__ __forceinline__ void blendVertices(const DeformArgs& a, const AssocCa
       const double v0 = static_cast<double>(qx), v1 = static_cast<double>(qy),
                    v2 = static_cast<double>(qz);
       double wsum = 0.0, acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
+      // row of neighbour field f: copy plane (f >> 11 & 3) of the staged window / of the table
       const double2* table = IN_PLACE ? static_cast<const double2*>(cache.pose_rows) + 8ull * lo
                                       : reinterpret_cast<const double2*>(rows);
+      const uint64_t plane = IN_PLACE ? cache.plane_rows : static_cast<uint64_t>(staged_rows);
+      auto rowOf = [&](uint32_t f) {
+        const uint32_t copy = (f >> kCacheCopyShift) & kCacheCopyMask;
+        if (IN_PLACE) return table + 8ull * ((f & kCacheRelMask) + copy * plane);
+        return table + 8u * ((f & kCacheRelMask) + copy * static_cast<uint32_t>(plane));
+      };
       if (NB > 0) {
         double w[NB > 0 ? NB : 1];
 #pragma unroll
         for (int j = 0; j < NB; ++j) w[j] = __ldg(wp + static_cast<uint64_t>(j) * cache.n_slots);
 #pragma unroll
         for (int j = 0; j < NB; ++j) {
-          accumulate64(table + 8u * (rel[j] & kCacheRelMask), static_cast<int>(rel[j] >> kCacheRelBits),
-                       w[j], v0, v1, v2, wsum, acc0, acc1, acc2);
+          accumulate64(rowOf(rel[j]), static_cast<int>(rel[j] >> kCacheClassShift), w[j], v0, v1, v2,
+                       wsum, acc0, acc1, acc2);
         }
       } else {
 #pragma unroll
         for (int j = 0; j < kCacheMaxNbr; ++j) {
           if (j < nb) {
             const double w = __ldg(wp + static_cast<uint64_t>(j) * cache.n_slots);
-            accumulate64(table + 8u * (rel[j] & kCacheRelMask), static_cast<int>(rel[j] >> kCacheRelBits),
-                         w, v0, v1, v2, wsum, acc0, acc1, acc2);
+            accumulate64(rowOf(rel[j]), static_cast<int>(rel[j] >> kCacheClassShift), w, v0, v1, v2,
+                         wsum, acc0, acc1, acc2);
           }
         }
       }
@@ -263,8 +289,15 @@ __device__ __forceinline__ void blendItem(const DeformArgs& a, const GridArgs& g
   const bool tiny = count <= 32 || n_rows > max_rows;
 
   if (!tiny && t == 0) {
-    bulkLoad(rows, static_cast<const unsigned char*>(cache.pose_rows) + static_cast<uint64_t>(lo) * kRowBytes,
-             n_rows * kRowBytes, &S.bar);
+    // the window's rows, every copy plane the launch has room for (FP32 rows have one)
+    const uint32_t n_copies = PREC == 0 ? cache.n_copies : 1u;
+    expectTx(&S.bar, n_copies * n_rows * kRowBytes);
+    for (uint32_t m = 0; m < n_copies; ++m) {
+      bulkLoad(rows + static_cast<size_t>(m) * n_rows * kRowBytes,
+               static_cast<const unsigned char*>(cache.pose_rows) +
+                   (static_cast<uint64_t>(m) * cache.plane_rows + lo) * kRowBytes,
+               n_rows * kRowBytes, &S.bar);
+    }
   }
   // ---- vertices in (coalesced), fingerprint
   unsigned long long fp = 0ull;
@@ -307,9 +340,9 @@ __device__ __forceinline__ void blendItem(const DeformArgs& a, const GridArgs& g
     bar_phase ^= 1u;
   }
 
-  if (tiny) blendVertices<PREC, 0, true>(a, cache, S, rows, p_base, count, nb, lo);
-  else if (nb == 5) blendVertices<PREC, 5, false>(a, cache, S, rows, p_base, count, nb, lo);
-  else blendVertices<PREC, 0, false>(a, cache, S, rows, p_base, count, nb, lo);
+  if (tiny) blendVertices<PREC, 0, true>(a, cache, S, rows, p_base, count, nb, lo, n_rows);
+  else if (nb == 5) blendVertices<PREC, 5, false>(a, cache, S, rows, p_base, count, nb, lo, n_rows);
+  else blendVertices<PREC, 0, false>(a, cache, S, rows, p_base, count, nb, lo, n_rows);
   __syncthreads();
   // ---- results out (coalesced)
   for (int i = t; i < count; i += kBThreads) {
@@ -344,12 +377,116 @@ deformBlendCachedKernel(const DeformArgs a, const GridArgs ga, const AssocCache 
   }
 }
 
+
+// ---- placement pass --------------------------------------------------------------------------
+// Which copy of its pose row a neighbour field reads.  For one neighbour slot of the 32 records
+// of a warp, per quarter warp (the unit an LDS.128 is served in): distinct rows are represented
+// by their first lane; round m lets every representative still without a bank group ask for the
+// group of its copy m, and the first asker of a free group gets it.  Representatives left over
+// after the last round keep copy 0 (that quarter warp pays a second wavefront).  All four
+// quarter warps run in the same instructions: match.any on (group, quarter) keys, one redux.or
+// over one-hot group bytes.
+__device__ __forceinline__ uint32_t placeSlot(uint32_t field, bool active, uint32_t lo,
+                                              const AssocCache& cache, int lane) {
+  const unsigned full = 0xFFFFFFFFu;
+  const uint32_t q = static_cast<uint32_t>(lane) >> 3;
+  const uint32_t rel = field & kCacheRelMask;
+  const uint64_t row = static_cast<uint64_t>(lo) + rel;
+  const uint32_t class0 = active ? (__ldg(cache.ctrl_class + row) & 7u) : 0u;
+  // idle lanes get keys nobody shares (bit 31 / bit 30 + lane)
+  const unsigned same_row = __match_any_sync(full, active ? (rel | (q << 16)) : (0x80000000u | lane));
+  const int rep_lane = __ffs(same_row) - 1;
+  const bool rep = active && lane == rep_lane;
+  uint32_t cls[kBlendCopies];
+#pragma unroll
+  for (int m = 0; m < kBlendCopies; ++m) cls[m] = blendClass(class0, row, m);
+  uint32_t taken = 0u;  // bank groups taken in this lane's quarter warp (one-hot byte)
+  int copy = -1;
+#pragma unroll
+  for (int m = 0; m < kBlendCopies; ++m) {
+    if (static_cast<uint32_t>(m) < cache.n_copies) {
+      const bool asks = rep && copy < 0 && !((taken >> cls[m]) & 1u);
+      const unsigned askers = __match_any_sync(full, asks ? (cls[m] | (q << 3)) : (0x40000000u | lane));
+      const bool wins = asks && lane == __ffs(askers) - 1;
+      if (wins) copy = m;
+      const uint32_t all = __reduce_or_sync(full, wins ? (1u << cls[m]) << (8u * q) : 0u);
+      taken |= (all >> (8u * q)) & 0xFFu;
+    }
+  }
+  if (copy < 0) copy = 0;
+  copy = __shfl_sync(full, copy, rep_lane);  // every lane of a row reads the same address
+  const uint32_t c = copy == 0 ? cls[0] : (copy == 1 ? cls[1] : cls[2]);
+  return rel | (static_cast<uint32_t>(copy) << kCacheCopyShift) | (c << kCacheClassShift);
+}
+
+__device__ __forceinline__ void placeItem(const DeformArgs& a, const GridArgs& ga,
+                                          const AssocCache& cache, const WorkItem& item) {
+  const uint32_t r = item.run;
+  const uint4 info = __ldg(a.run_info + r);
+  if (info.w) return;
+  const int n_alive = static_cast<int>(ga.grids[r].n_alive);
+  if (n_alive > kSortedMaxPoints || !runCacheable(info)) return;  // no records (see blendItem)
+  const int K = static_cast<int>(info.z) + 2;
+  const int nb = (n_alive < K ? n_alive : K) - 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  const int count = static_cast<int>(item.count);
+  uint4* rec0 = reinterpret_cast<uint4*>(cache.rec);
+  for (int g = warp; g * 32 < count; g += n_warps) {
+    const int q = g * 32 + lane;
+    const bool active = q < count;
+    const uint64_t slot = item.start + static_cast<uint64_t>(active ? q : 0);
+    uint4 r0 = rec0[slot];
+    uint32_t f[7] = {r0.x >> 16, r0.y & 0xFFFFu, r0.y >> 16, r0.z & 0xFFFFu, r0.z >> 16,
+                     r0.w & 0xFFFFu, r0.w >> 16};
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+      if (j < nb) f[j] = placeSlot(f[j], active, info.x, cache, lane);
+    }
+    if (active) {
+      r0.x = (r0.x & 0xFFFFu) | (f[0] << 16);
+      r0.y = f[1] | (f[2] << 16);
+      r0.z = f[3] | (f[4] << 16);
+      r0.w = f[5] | (f[6] << 16);
+      rec0[slot] = r0;
+    }
+    if (nb > 7) {  // plane 1: neighbours 7..14
+      uint4 r1 = rec0[cache.n_slots + slot];
+      uint32_t h[8] = {r1.x & 0xFFFFu, r1.x >> 16, r1.y & 0xFFFFu, r1.y >> 16,
+                       r1.z & 0xFFFFu, r1.z >> 16, r1.w & 0xFFFFu, r1.w >> 16};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (7 + j < nb) h[j] = placeSlot(h[j], active, info.x, cache, lane);
+      }
+      if (active) {
+        rec0[cache.n_slots + slot] = make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16),
+                                                h[4] | (h[5] << 16), h[6] | (h[7] << 16));
+      }
+    }
+  }
+}
+
+constexpr int kPlaceThreads = 256;
+template <bool FROM_LIST>
+__global__ void __launch_bounds__(kPlaceThreads)
+placeRecordsKernel(const DeformArgs a, const GridArgs ga, const AssocCache cache,
+                   const WorkItem* __restrict__ items, const uint32_t first_item) {
+  if (!FROM_LIST) {
+    placeItem(a, ga, cache, items[first_item + blockIdx.x]);
+  } else {
+    const unsigned long long begin = a.counters[3], end = a.counters[2];
+    for (unsigned long long i = begin + blockIdx.x; i < end; i += gridDim.x) {
+      placeItem(a, ga, cache, items[cache.stale_items[i]]);
+    }
+  }
+}
+
 uint32_t blendRows(uint64_t widest_window) {
   return static_cast<uint32_t>(widest_window < static_cast<uint64_t>(kSortedMaxPoints)
                                    ? widest_window : static_cast<uint64_t>(kSortedMaxPoints));
 }
-size_t blendSmemBytes(int precision, uint64_t widest_window) {
-  return sizeof(BlendSmemHead) + static_cast<size_t>(blendRows(widest_window)) * (precision == 0 ? 128 : 64);
+size_t blendSmemBytes(int precision, uint64_t widest_window, uint32_t n_copies) {
+  return sizeof(BlendSmemHead) +
+         static_cast<size_t>(blendRows(widest_window)) * (precision == 0 ? 128u * n_copies : 64u);
 }
 
 template <int PREC, int MODE>
@@ -362,11 +499,11 @@ cudaError_t launchBlend(const DeformArgs& args, const GridArgs& gargs, const Ass
   if (configured_device != device) {
     const cudaError_t e = cudaFuncSetAttribute(
         deformBlendCachedKernel<PREC, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-        static_cast<int>(blendSmemBytes(PREC, kSortedMaxPoints)));
+        static_cast<int>(std::max(kBSmemBudget, blendSmemBytes(PREC, kSortedMaxPoints, 1))));
     if (e != cudaSuccess) return e;
     configured_device = device;
   }
-  const size_t smem = blendSmemBytes(PREC, widest_window);
+  const size_t smem = blendSmemBytes(PREC, widest_window, PREC == 0 ? cache.n_copies : 1u);
   const unsigned grid = MODE == 2 ? static_cast<unsigned>(n_sms * PGMO_K3B_CTAS) : n_items;
   deformBlendCachedKernel<PREC, MODE><<<grid, kBThreads, smem, stream>>>(args, gargs, cache, items,
                                                                         first_item, blendRows(widest_window));
@@ -397,6 +534,32 @@ void preloadBlend() {
 void preloadDeformBlendKernels() {
   preloadBlend<0>();
   preloadBlend<1>();
+  cudaFuncAttributes attr;
+  cudaFuncGetAttributes(&attr, placeRecordsKernel<false>);
+  cudaFuncGetAttributes(&attr, placeRecordsKernel<true>);
+}
+
+uint32_t blendCopiesFor(int precision, uint64_t widest_window) {
+  if (precision != 0) return 1u;
+  const size_t per_copy = static_cast<size_t>(blendRows(widest_window)) * 128u;
+  if (per_copy == 0) return 1u;
+  const size_t room = kBSmemBudget > sizeof(BlendSmemHead) ? kBSmemBudget - sizeof(BlendSmemHead) : 0;
+  const size_t fit = room / per_copy;
+  return static_cast<uint32_t>(fit < 1 ? 1 : (fit > static_cast<size_t>(kBlendCopies) ? kBlendCopies : fit));
+}
+
+cudaError_t launchPlaceRecords(const DeformArgs& args, const GridArgs& gargs, const AssocCache& cache,
+                               const WorkItem* items, uint32_t first_item, uint32_t n_items,
+                               bool from_stale_list, int n_sms, cudaStream_t stream) {
+  if (cache.n_copies <= 1) return cudaSuccess;
+  if (from_stale_list) {
+    placeRecordsKernel<true><<<static_cast<unsigned>(n_sms * 4), kPlaceThreads, 0, stream>>>(
+        args, gargs, cache, items, first_item);
+  } else {
+    if (n_items == 0) return cudaSuccess;
+    placeRecordsKernel<false><<<n_items, kPlaceThreads, 0, stream>>>(args, gargs, cache, items, first_item);
+  }
+  return cudaGetLastError();
 }
 
 cudaError_t launchDeformBlendCached(const DeformArgs& args, const GridArgs& gargs,

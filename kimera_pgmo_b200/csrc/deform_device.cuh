@@ -62,13 +62,24 @@ __device__ __forceinline__ unsigned long long warpSumU64(unsigned long long v) {
   return v;
 }
 
+// Bank class of copy `copy` of pose row `row` (class0 = the colouring's class of the row): the three
+// copies of a row sit under three different XOR masks, so that a quarter warp that needs several
+// rows of one class can read some of them from another bank group.
+__host__ __device__ __forceinline__ uint32_t blendClass(uint32_t class0, uint64_t row, int copy) {
+  if (copy == 0) return class0 & 7u;
+  const uint32_t a = 1u + static_cast<uint32_t>(row % 7u);                  // 1..7
+  if (copy == 1) return (class0 ^ a) & 7u;
+  const uint32_t b = 1u + (a + static_cast<uint32_t>((row / 7u) % 6u)) % 7u;  // 1..7, != a
+  return (class0 ^ b) & 7u;
+}
+
 // can the vertices of a run {lo, hi, k, skip} have association records?  (neighbour count and
 // the 16-bit relative control index of the record layout)
 __device__ __forceinline__ bool runCacheable(const uint4& info) {
   return static_cast<int>(info.z) + 1 <= kCacheMaxNbr && info.y - info.x <= (1u << kCacheRelBits);
 }
 // record slot `slot` of the association cache: neighbour j's control index relative to run.lo
-// (| bank class << kCacheRelBits)
+// (| bank class << kCacheClassShift; copy 0 until the placement pass has seen the record)
 __device__ __forceinline__ void cacheStoreNbr(const AssocCache& c, uint64_t slot, int j, uint32_t rel) {
   const uint64_t plane = j < 7 ? 0 : 1;
   c.rec[(plane * c.n_slots + slot) * 8 + (j < 7 ? 1 + j : j - 7)] = static_cast<uint16_t>(rel);

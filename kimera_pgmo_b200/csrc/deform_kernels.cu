@@ -209,9 +209,12 @@ __global__ void buildControlTablesKernel(uint64_t n_c, const double* __restrict_
     row[13] = gy;
     row[14] = gz;
     row[15] = 0.0;
-    double2* dst = reinterpret_cast<double2*>(pose_rows64 + 16 * j);
-    const int sw = ctrl_class ? static_cast<int>(ctrl_class[j] & 7u) : 0;
-    for (int c = 0; c < 8; ++c) dst[c ^ sw] = make_double2(row[2 * c], row[2 * c + 1]);
+    const uint32_t class0 = ctrl_class ? (ctrl_class[j] & 7u) : 0u;
+    for (int m = 0; m < kBlendCopies; ++m) {  // one plane of n_c rows per copy
+      double2* dst = reinterpret_cast<double2*>(pose_rows64 + 16 * (static_cast<uint64_t>(m) * n_c + j));
+      const int sw = static_cast<int>(dev::blendClass(class0, j, m));
+      for (int c = 0; c < 8; ++c) dst[c ^ sw] = make_double2(row[2 * c], row[2 * c + 1]);
+    }
   }
 }
 
@@ -223,7 +226,8 @@ __global__ void buildControlTablesKernel(uint64_t n_c, const double* __restrict_
 // sectors) into shared memory, then one thread builds one row.
 constexpr int kPullRows = 128;
 __global__ void __launch_bounds__(kPullRows)
-pullBuildPoseTablesKernel(uint64_t row_begin, uint64_t row_end, const double* __restrict__ src,
+pullBuildPoseTablesKernel(uint64_t row_begin, uint64_t row_end, uint64_t n_c,
+                          const double* __restrict__ src,
                           double* __restrict__ poses_local, const double* __restrict__ ctrl_pos,
                           float* __restrict__ pose_f32, double* __restrict__ pose_rows64,
                           const uint8_t* __restrict__ ctrl_class) {
@@ -250,9 +254,12 @@ pullBuildPoseTablesKernel(uint64_t row_begin, uint64_t row_end, const double* __
   float* o = pose_f32 + 16 * j;
   for (int i = 0; i < 15; ++i) o[i] = __double2float_rn(row[i]);
   o[15] = 0.f;
-  double2* dst = reinterpret_cast<double2*>(pose_rows64 + 16 * j);
-  const int sw = ctrl_class ? static_cast<int>(ctrl_class[j] & 7u) : 0;
-  for (int c = 0; c < 8; ++c) dst[c ^ sw] = make_double2(row[2 * c], row[2 * c + 1]);
+  const uint32_t class0 = ctrl_class ? (ctrl_class[j] & 7u) : 0u;
+  for (int m = 0; m < kBlendCopies; ++m) {
+    double2* dst = reinterpret_cast<double2*>(pose_rows64 + 16 * (static_cast<uint64_t>(m) * n_c + j));
+    const int sw = static_cast<int>(dev::blendClass(class0, j, m));
+    for (int c = 0; c < 8; ++c) dst[c ^ sw] = make_double2(row[2 * c], row[2 * c + 1]);
+  }
 }
 
 __global__ void applyScheduleKernel(uint64_t n_c, const int32_t* __restrict__ del_run,
@@ -365,14 +372,14 @@ cudaError_t launchBuildControlTables(uint64_t n_c, const double* ctrl_pos, const
   return cudaGetLastError();
 }
 
-cudaError_t launchPullBuildPoseTables(uint64_t row_begin, uint64_t row_end, const double* src,
-                                      double* poses_local, const double* ctrl_pos,
+cudaError_t launchPullBuildPoseTables(uint64_t row_begin, uint64_t row_end, uint64_t n_c,
+                                      const double* src, double* poses_local, const double* ctrl_pos,
                                       float* ctrl_pose_f32, double* pose_rows64,
                                       const uint8_t* ctrl_class, cudaStream_t stream) {
   if (row_end <= row_begin) return cudaSuccess;
   const uint64_t blocks = (row_end - row_begin + kPullRows - 1) / kPullRows;
   pullBuildPoseTablesKernel<<<static_cast<unsigned>(blocks), kPullRows, 0, stream>>>(
-      row_begin, row_end, src, poses_local, ctrl_pos, ctrl_pose_f32, pose_rows64, ctrl_class);
+      row_begin, row_end, n_c, src, poses_local, ctrl_pos, ctrl_pose_f32, pose_rows64, ctrl_class);
   return cudaGetLastError();
 }
 

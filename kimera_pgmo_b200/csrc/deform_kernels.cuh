@@ -69,8 +69,8 @@ constexpr uint32_t kNoCacheSlot = 0xFFFFFFFFu;
 constexpr int kCacheMaxNbr = 14;  // blended neighbours a record can hold (k <= 13)
 struct AssocCache {
   // plane 0: {vertex offset inside the item, nbr 0..6}, plane 1: {nbr 7..14}; nbr = (control
-  // index - run.lo) | bank class << 13; slot = local position of the record (item start + rank in
-  // search order)
+  // index - run.lo) | row copy << 11 | bank class << 13; slot = local position of the record
+  // (item start + rank in search order)
   uint16_t* rec;       // planes x n_slots x 8
   void* weight;        // w_planes x n_slots, double (FP64 mode) or float (FP32 mode)
   uint32_t w_planes;   // neighbours a record holds weights for (>= max_k + 1)
@@ -78,16 +78,28 @@ struct AssocCache {
   unsigned long long* item_fp;  // per work item: fingerprint of the vertex bits
   uint32_t* item_ok;   // per work item: 1 = records valid for item_fp
   uint32_t* stale_items;  // work items the validating pass rejected (capacity: all items)
-  const void* pose_rows;  // n_c rows: 16 doubles (128 B, 16-byte chunk c stored at c ^ class)
-                          // or 16 floats (FP32 mode): R(9) t(3) g(3) pad
+  const void* pose_rows;  // FP64 mode: kBlendCopies planes of plane_rows rows of 16 doubles (128 B,
+                          // 16-byte chunk c of copy m stored at c ^ blendClass(class, row, m));
+                          // FP32 mode: n_c rows of 16 floats.  Row = R(9) t(3) g(3) pad
+  uint64_t plane_rows;    // rows per copy plane (= control points the table was built for)
+  uint32_t n_copies;      // copies the blend kernel stages (what fits its shared memory)
   // Bank class (0..7) of every control point's row: a colouring in which points that lie close
   // together differ (deform_api.cu: colourControls).  The lanes of a quarter warp read rows of
   // control points that lie close together; different classes put the same chunk of their rows
   // into different bank groups.
   const uint8_t* ctrl_class;
 };
-constexpr uint32_t kCacheRelBits = 13;
+// A record's neighbour field: [10:0] control index - run.lo, [12:11] which copy of the pose row
+// the blend kernel reads, [15:13] the bank class of that copy (the XOR its chunks are stored under).
+// Every row is stored kBlendCopies times under different classes; a placement pass over fresh
+// records (placeRecordsKernel) picks, per quarter warp and neighbour slot, copies whose bank groups
+// differ, which is what an LDS.128 of 8 lanes needs to be one wavefront.
+constexpr uint32_t kCacheRelBits = 11;
 constexpr uint32_t kCacheRelMask = (1u << kCacheRelBits) - 1u;
+constexpr uint32_t kCacheCopyShift = 11;
+constexpr uint32_t kCacheCopyMask = 3u;
+constexpr uint32_t kCacheClassShift = 13;
+constexpr int kBlendCopies = 3;
 
 // per-run uniform grid over the run's alive control points (deform_grid.cu)
 constexpr int kGridMaxCells = 1024;
@@ -184,6 +196,13 @@ cudaError_t launchDeformBlendCached(const DeformArgs& args, const GridArgs& garg
                                     uint32_t max_k, uint32_t min_k, uint64_t widest_window,
                                     int mode, int n_sms, cudaStream_t stream);
 void preloadDeformBlendKernels();
+// copies of the pose rows the blend kernel can stage for windows of up to widest_window rows
+uint32_t blendCopiesFor(int precision, uint64_t widest_window);
+// Placement pass over records the search kernel / the resolver just wrote (cache.n_copies > 1):
+// chooses the row copy of every neighbour field.  from_stale_list as in launchDeformSearchSorted.
+cudaError_t launchPlaceRecords(const DeformArgs& args, const GridArgs& gargs, const AssocCache& cache,
+                               const WorkItem* items, uint32_t first_item, uint32_t n_items,
+                               bool from_stale_list, int n_sms, cudaStream_t stream);
 // counters[1] = counters[0]; counters[3] = counters[2]
 cudaError_t launchDeformStepDone(unsigned long long* counters, cudaStream_t stream);
 
@@ -219,11 +238,11 @@ cudaError_t launchPredeform(uint64_t n_v, uint64_t start_idx, const float* x, co
 cudaError_t launchBuildControlTables(uint64_t n_c, const double* ctrl_pos, const double* poses,
                                      float4* ctrl_f4, float* ctrl_pose_f32, double* pose_rows64,
                                      const uint8_t* ctrl_class, bool positions_changed,
-                                     cudaStream_t stream);
+                                     cudaStream_t stream);  // pose_rows64: kBlendCopies x n_c rows
 // Rows [row_begin, row_end) of the pose table `src` (local or a peer device's memory) -> this
 // device's f64 copy (poses_local, may be null or == src), f32 rows and swizzled f64 rows.
-cudaError_t launchPullBuildPoseTables(uint64_t row_begin, uint64_t row_end, const double* src,
-                                      double* poses_local, const double* ctrl_pos,
+cudaError_t launchPullBuildPoseTables(uint64_t row_begin, uint64_t row_end, uint64_t n_c,
+                                      const double* src, double* poses_local, const double* ctrl_pos,
                                       float* ctrl_pose_f32, double* pose_rows64,
                                       const uint8_t* ctrl_class, cudaStream_t stream);
 // writes del_run into ctrl_f4[].w and the stable keys (after build_schedule)

@@ -77,7 +77,7 @@ __device__ __forceinline__ void cacheFromResolver(const DeformArgs&, const Assoc
   const float inv_dmax = const_w ? 0.0f : __frcp_rn(d_max_f);
   for (int j = 0; j < n - 1; ++j) {
     cacheStoreNbr(c, slot, j, (static_cast<uint32_t>(idx[j]) - lo) |
-                                  (static_cast<uint32_t>(__ldg(c.ctrl_class + idx[j])) << kCacheRelBits));
+                                  (static_cast<uint32_t>(__ldg(c.ctrl_class + idx[j]) & 7u) << kCacheClassShift));
     cacheStoreWeight(c, slot, j, precision, weightFp64(d2[j], d_max_f, const_w),
                      weightFp32(d2[j], inv_dmax, const_w));
   }

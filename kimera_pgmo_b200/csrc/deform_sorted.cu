@@ -618,7 +618,7 @@ __device__ __forceinline__ void searchItem(const DeformArgs& a, const GridArgs& 
     uint32_t rel[KCAP];
 #pragma unroll
     for (int j = 0; j < KCAP; ++j) {
-      rel[j] = (j < n - 1) ? (static_cast<uint32_t>(nbr_idx[j]) - info.x) | (nbr_cls[j] << kCacheRelBits) : 0u;
+      rel[j] = (j < n - 1) ? (static_cast<uint32_t>(nbr_idx[j]) - info.x) | ((nbr_cls[j] & 7u) << kCacheClassShift) : 0u;
     }
     {
       uint4 rec0;

@@ -147,6 +147,20 @@ int reserveRecords(pgmo_delta* h, uint64_t n, cudaStream_t st) {
   PGMO_TRY(h->r_needs_archive.reserve(n, st, keep));
   PGMO_TRY(h->r_is_new.reserve(n, st, keep));
   PGMO_TRY(h->r_alive.reserve(n, st, keep));
+  // the compaction target set and its scratch grow with the primary set, inside the call that
+  // is slow anyway, not inside the first garbage collection of a stream
+  const uint64_t cap = h->r_key.cap;
+  PGMO_TRY(h->s_key.reserve(cap));
+  PGMO_TRY(h->s_stamp.reserve(cap));
+  PGMO_TRY(h->s_point.reserve(cap));
+  PGMO_TRY(h->s_label.reserve(cap));
+  PGMO_TRY(h->s_mesh_index.reserve(cap));
+  PGMO_TRY(h->s_seq.reserve(cap));
+  PGMO_TRY(h->s_refs.reserve(cap));
+  PGMO_TRY(h->s_needs_archive.reserve(cap));
+  PGMO_TRY(h->s_is_new.reserve(cap));
+  PGMO_TRY(h->s_alive.reserve(cap));
+  PGMO_TRY(h->new_id.reserve(cap + 1));
   return PGMO_OK;
 }
 
@@ -459,6 +473,51 @@ int archiveChosen(pgmo_delta* h, const std::vector<size_t>& chosen) {
 
 }  // namespace
 
+namespace {
+
+// Every buffer of the handle at its floor size, once, at creation: what a 50k-vertex / 10 s
+// horizon stream needs is then in place before the first message (first update 11 ms -> the
+// usual 0.4 ms; the first archive and the first garbage collections no longer allocate).
+int prewarm(pgmo_delta* h) {
+  cudaStream_t st = h->stream;
+  PGMO_TRY(reserveRecords(h, room(1), st));
+  PGMO_TRY(ensureTable(h, 1, st));
+  PGMO_TRY(h->f_pool.reserve(room(1)));
+  PGMO_TRY(h->x_pool.reserve(room(1)));
+  PGMO_TRY(h->f_spare.reserve(h->f_pool.cap));
+  PGMO_TRY(h->x_spare.reserve(h->x_pool.cap));
+  PGMO_TRY(h->o_p2c.reserve(room(1)));
+  PGMO_TRY(h->o_del.reserve(room(1)));
+  PGMO_TRY(h->o_new.reserve(room(1)));
+  PGMO_TRY(h->o_obs.reserve(room(1)));
+  PGMO_TRY(reserveOutVertices(h, room(1), st));
+  PGMO_TRY(reserveTiles(h, room(1)));
+  PGMO_TRY(roomy(h->e_keys, 1));
+  PGMO_TRY(roomy(h->e_minseq, 1));
+  PGMO_TRY(roomy(h->acc_a, 1));
+  PGMO_TRY(roomy(h->acc_b, 1));
+  PGMO_TRY(roomy(h->d_segs, 1));
+  PGMO_TRY(roomy(h->d_fblocks, 1));
+  PGMO_TRY(roomy(h->work_faces, 1));
+  PGMO_TRY(roomy(h->f1, 1));
+  PGMO_TRY(roomy(h->f2, 1));
+  PGMO_TRY(roomy(h->valid, 1));
+  PGMO_TRY(roomy(h->o_faces_arch, 1));
+  PGMO_TRY(roomy(h->o_faces_upd, 1));
+  PGMO_TRY(roomy(h->pending, 1));
+  PGMO_TRY(roomy(h->pending2, 1));
+  PGMO_TRY(roomy(h->d_xyz, 1));
+  PGMO_TRY(roomy(h->d_rgba, 1));
+  PGMO_TRY(roomy(h->tslot_of_vertex, 1));
+  PGMO_TRY(roomy(h->active_remapping, 1));
+  PGMO_TRY(roomy(h->d_remap, 1));
+  PGMO_TRY(roomy(h->blk_counts, 1));
+  PGMO_CUDA(cudaStreamSynchronize(st));
+  return PGMO_OK;
+}
+
+}  // namespace
+
 extern "C" {
 
 int pgmo_delta_create(double resolution, int device, pgmo_delta_t** out) {
@@ -481,6 +540,10 @@ int pgmo_delta_create(double resolution, int device, pgmo_delta_t** out) {
     return PGMO_ERR_CUDA;
   }
   cudaMemsetAsync(h->counters.ptr, 0, kDcCount * sizeof(unsigned long long), h->stream);
+  if (prewarm(h) != PGMO_OK) {
+    pgmo_delta_destroy(h);
+    return PGMO_ERR_CUDA;
+  }
   preloadDeltaKernels();
   preloadCommonKernels();
   *out = h;
@@ -580,6 +643,8 @@ int pgmo_delta_update_labeled(pgmo_delta_t* h, uint32_t n_blocks, const int32_t*
     const auto tr0 = std::chrono::steady_clock::now();
     if (h->f_used + n_b + 1 > h->f_pool.cap) PGMO_TRY(h->f_pool.reserve(room(h->f_used + n_b + 1), st, h->f_used));
     if (h->x_used + n_b + 1 > h->x_pool.cap) PGMO_TRY(h->x_pool.reserve(room(h->x_used + n_b + 1), st, h->x_used));
+    PGMO_TRY(h->f_spare.reserve(h->f_pool.cap));  // the garbage collection's target pair
+    PGMO_TRY(h->x_spare.reserve(h->x_pool.cap));
     if (timer.on) {
       const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tr0).count();
       if (ms > 5.0) fprintf(stderr, "pgmo debug: pool reserve %.1f ms (f_used %llu cap %zu, x_used %llu cap %zu)\n", ms,

@@ -80,6 +80,40 @@ def deformation_case(n_vertices: int, n_controls: int, ctrl_per_kf: int = 10, se
                 valid=valid, poses=poses)
 
 
+def deformation_case_with_ties(n_vertices: int, n_controls: int, tie_fraction: float,
+                               ctrl_per_kf: int = 10, seed: int = 42, lattice: float = 2.0 ** -5):
+    """deformation_case with exact float-distance ties planted at a chosen rate (VERDICT r1 #8:
+    voxblox vertices sit on a lattice, nobody knows what ties cost).  Control points are snapped
+    to a `lattice` grid (0.03125 m: sums of two coordinates stay exact in float); a fraction
+    `tie_fraction` of the vertices is moved to the exact midpoint of a control point of its own
+    keyframe and that point's nearest control point among the keyframes within +-5 s (both alive
+    at the vertex's stamp): dx, dy, dz to the two are equal and opposite, so the two float d^2
+    are bit-identical and they are the vertex's nearest two.  Returns (case, tied vertex indices)."""
+    from scipy.spatial import cKDTree
+    case = deformation_case(n_vertices, n_controls, ctrl_per_kf, seed)
+    cpos = np.round(case["ctrl_xyz"] / lattice) * lattice
+    case["poses"][:, 9:] += cpos - case["ctrl_xyz"]
+    case["ctrl_xyz"] = cpos
+    n_kf = max(n_controls // ctrl_per_kf, 1)
+    c_kf = np.minimum(np.arange(n_controls) // ctrl_per_kf, n_kf - 1)
+    _, nbr = cKDTree(cpos).query(cpos, k=9)
+    partner = np.full(n_controls, -1, dtype=np.int64)
+    for j in range(1, 9):  # nearest other control point within +-5 keyframes, not coincident
+        cand = nbr[:, j]
+        ok = (partner < 0) & (np.abs(c_kf[cand] - c_kf) <= 5) & (cpos[cand] != cpos).any(axis=1)
+        partner[ok] = cand[ok]
+    rng = np.random.default_rng([seed, 977])
+    per_kf = -(-n_vertices // n_kf)
+    tied = np.nonzero(rng.random(n_vertices) < tie_fraction)[0]
+    v_kf = np.minimum(tied // per_kf, n_kf - 1)
+    c1 = np.minimum(v_kf * ctrl_per_kf + rng.integers(0, ctrl_per_kf, tied.shape[0]), n_controls - 1)
+    keep = partner[c1] >= 0
+    tied, c1 = tied[keep], c1[keep]
+    mid = (0.5 * (cpos[c1] + cpos[partner[c1]])).astype(np.float32)
+    case["x"][tied], case["y"][tied], case["z"][tied] = mid[:, 0], mid[:, 1], mid[:, 2]
+    return case, tied
+
+
 def deformation_slab(n_vertices_total: int, n_controls: int, first: int, count: int,
                      ctrl_per_kf: int = 10, seed: int = 42, t0_ns: int = T0_NS,
                      vertex_spread: float = 6.0, ctrl_spread: float = 5.0):

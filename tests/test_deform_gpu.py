@@ -338,3 +338,31 @@ def test_appended_controls_extend_the_schedule(capi, oracle):
                                case["valid"], case["poses"], k=3, tol_t=10.0)
     _compare(gpu, ref)
     h.close()
+
+
+@pytest.mark.parametrize("tie_fraction", [1e-3, 1e-2, 0.2])
+def test_planted_ties_follow_the_reference_order(capi, oracle, tie_fraction):
+    """Exact float-distance ties at realistic and absurd rates (vertices on the midpoint of two
+    lattice-snapped control points: bit-identical d^2 for their two nearest neighbours).  Which of
+    the two comes first is PCL's visit order (K4); positions must not depend on it being rare.
+    The second deformation runs from the association records the resolver left behind."""
+    case, tied = synth.deformation_case_with_ties(200_000, 2_000, tie_fraction)
+    assert tied.size > 0.5 * tie_fraction * 200_000
+    h = capi.DeformHandle(0)
+    _set(h, case)
+    gpu = h.deform_points(case["x"], case["y"], case["z"], case["stamps"], k=4, tol_t=10.0,
+                          want_f64=True, want_assoc=True)
+    assert h.last_step_info()["resolved"] >= tied.size * 0.95  # the planted vertices went through K4
+    ref = oracle.deform_points(case["x"], case["y"], case["z"], case["stamps"], case["ctrl_xyz"],
+                               case["ctrl_stamps"], case["valid"], case["poses"], k=4, tol_t=10.0)
+    _compare(gpu, ref)
+    # pose-only update: blend from the records (incl. the resolver's), against a fresh oracle run
+    poses2 = case["poses"].copy()
+    poses2[:, 9:] += np.array([0.25, -0.5, 0.125])
+    h.update_poses(poses2)
+    gpu2 = h.deform_points(case["x"], case["y"], case["z"], case["stamps"], k=4, tol_t=10.0,
+                           want_f64=True, want_assoc=True)
+    ref2 = oracle.deform_points(case["x"], case["y"], case["z"], case["stamps"], case["ctrl_xyz"],
+                                case["ctrl_stamps"], case["valid"], poses2, k=4, tol_t=10.0)
+    _compare(gpu2, ref2)
+    h.close()
