@@ -71,8 +71,12 @@ struct pgmo_deform {
   DevBuf<WorkItem> d_items;
   std::vector<WorkItem> h_items;
   cudaStream_t s_in = nullptr, s_out = nullptr;  // copy streams of the pipelined host entry point
-  static constexpr int kPipe = 8;
-  cudaEvent_t ev_in[kPipe] = {}, ev_done[kPipe] = {};
+  static constexpr int kMaxPipe = 32;
+  // slabs / upload chunks of the pipelined host entry points (PGMO_PIPE).  Measured per 10 M
+  // vertices: 4 -> 3.52 ms, 8 -> 3.42, 12 -> 3.60, 16 -> 3.67, 32 -> 3.99 (every slab costs seven
+  // DMA transfers and ~8 launches; fewer slabs lengthen the fill and drain of the pipeline)
+  int pipe = 8;
+  cudaEvent_t ev_in[kMaxPipe] = {}, ev_done[kMaxPipe] = {};
   cudaEvent_t ev_stamps = nullptr;
   float r_scale = 1.0f, r_grow_mul = 1.5f, r_grow_add = 1.0f, far_mul = 3.0f;
   uint32_t n_items = 0;
@@ -510,7 +514,7 @@ int pgmo_deform_create(int device, pgmo_deform_t** out) {
   }
   cudaEventCreateWithFlags(&h->ev_stamps, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&h->ev_fp, cudaEventDisableTiming);
-  for (int i = 0; i < pgmo_deform::kPipe; ++i) {
+  for (int i = 0; i < pgmo_deform::kMaxPipe; ++i) {
     cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming);
   }
@@ -528,6 +532,9 @@ int pgmo_deform_create(int device, pgmo_deform_t** out) {
   preloadMeshMsgKernels();
   cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, device);
   if (const char* e = std::getenv("PGMO_ASSOC_CACHE")) h->cache_enabled = atoi(e) != 0;
+  if (const char* e = std::getenv("PGMO_PIPE")) {
+    h->pipe = std::max(1, std::min(static_cast<int>(pgmo_deform::kMaxPipe), atoi(e)));
+  }
   if (const char* e = std::getenv("PGMO_BLEND_COPIES")) h->blend_copies_override = static_cast<uint32_t>(atoi(e));
   *out = h;
   return PGMO_OK;
@@ -544,7 +551,7 @@ void pgmo_deform_destroy(pgmo_deform_t* h) {
   for (auto& e : h->ev) {
     if (e) cudaEventDestroy(e);
   }
-  for (int i = 0; i < pgmo_deform::kPipe; ++i) {
+  for (int i = 0; i < pgmo_deform::kMaxPipe; ++i) {
     if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
     if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
   }
@@ -1190,10 +1197,10 @@ static int runDeviceRange(pgmo_deform_t* h, uint64_t first_position, uint64_t n_
   return PGMO_OK;
 }
 
-// Vertex streams up in kPipe chunks on the copy stream, one event per chunk.
+// Vertex streams up in `pipe` chunks on the copy stream, one event per chunk.
 static int queueVertexUpload(pgmo_deform_t* h, uint64_t n_v, const float* x, const float* y,
                              const float* z, cudaStream_t up, uint64_t* chunk_end) {
-  const int n_chunks = pgmo_deform::kPipe;
+  const int n_chunks = h->pipe;
   for (int c = 0; c < n_chunks; ++c) {
     const uint64_t b = n_v * static_cast<uint64_t>(c) / n_chunks;
     const uint64_t e = n_v * static_cast<uint64_t>(c + 1) / n_chunks;
@@ -1216,10 +1223,10 @@ static int runPipelined(pgmo_deform_t* h, uint64_t first_position, uint64_t n_po
                         const uint64_t* chunk_end) {
   cudaStream_t st = h->stream;
   CallOrder call_order(h, st);
-  const int n_chunks = pgmo_deform::kPipe;
+  const int n_chunks = h->pipe;
   PGMO_TRY(h->d_status.reserve(n_pos));
   PGMO_TRY(ensureItems(h, first_position, n_pos, st));
-  const int n_slabs = pgmo_deform::kPipe;
+  const int n_slabs = h->pipe;
   uint64_t begin = 0;
   int waited = -1;  // chunks [0, waited] are known to the compute stream
   for (int sl = 0; sl < n_slabs && begin < n_pos; ++sl) {
@@ -1412,9 +1419,9 @@ int pgmo_deform_points(pgmo_deform_t* h, uint64_t n_v, const float* x, const flo
   }
 
   // Every upload is queued on the copy stream right away — stamps first (K1 and the host-side
-  // window schedule only need them), then the vertex streams in kPipe chunks, one event each —
+  // window schedule only need them), then the vertex streams in `pipe` chunks, one event each —
   // so that the H2D engine never idles while the schedule is looked up / built on the host.
-  const int n_chunks = pgmo_deform::kPipe;
+  const int n_chunks = h->pipe;
   const bool copy_stream = h->s_in != nullptr && h->s_out != nullptr;
   cudaStream_t up = copy_stream ? h->s_in : st;
   if (stamps_ns) {
@@ -1426,7 +1433,7 @@ int pgmo_deform_points(pgmo_deform_t* h, uint64_t n_v, const float* x, const flo
       PGMO_CUDA(cudaStreamWaitEvent(st, h->ev_stamps, 0));
     }
   }
-  uint64_t chunk_end[pgmo_deform::kPipe];
+  uint64_t chunk_end[pgmo_deform::kMaxPipe];
   if (copy_stream) {
     PGMO_TRY(queueVertexUpload(h, n_v, x, y, z, up, chunk_end));
   } else {
@@ -1547,7 +1554,7 @@ int pgmo_deform_run_host_slab(pgmo_deform_t* h, uint64_t first_position, uint64_
   PGMO_TRY(h->d_ox.reserve(n_local));
   PGMO_TRY(h->d_oy.reserve(n_local));
   PGMO_TRY(h->d_oz.reserve(n_local));
-  uint64_t chunk_end[pgmo_deform::kPipe];
+  uint64_t chunk_end[pgmo_deform::kMaxPipe];
   PGMO_TRY(queueVertexUpload(h, n_local, x, y, z, h->s_in, chunk_end));
   bool any_skip = false;
   for (const ScheduleRun& run : h->sched.runs) any_skip = any_skip || run.skip;
@@ -1555,7 +1562,7 @@ int pgmo_deform_run_host_slab(pgmo_deform_t* h, uint64_t first_position, uint64_
     // skipped vertices come back with their input coordinates (the reference's new_points starts
     // as a copy of the input cloud and `continue`s past them): seed the outputs, then one pass
     cudaStream_t st = h->stream;
-    PGMO_CUDA(cudaStreamWaitEvent(st, h->ev_in[pgmo_deform::kPipe - 1], 0));
+    PGMO_CUDA(cudaStreamWaitEvent(st, h->ev_in[h->pipe - 1], 0));
     PGMO_CUDA(cudaMemcpyAsync(h->d_ox.ptr, h->d_x.ptr, n_local * sizeof(float), cudaMemcpyDeviceToDevice, st));
     PGMO_CUDA(cudaMemcpyAsync(h->d_oy.ptr, h->d_y.ptr, n_local * sizeof(float), cudaMemcpyDeviceToDevice, st));
     PGMO_CUDA(cudaMemcpyAsync(h->d_oz.ptr, h->d_z.ptr, n_local * sizeof(float), cudaMemcpyDeviceToDevice, st));

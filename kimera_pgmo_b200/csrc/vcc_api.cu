@@ -496,6 +496,9 @@ int pgmo_vcc_create(double resolution, int device, pgmo_vcc_t** out) {
     pgmo_vcc_destroy(h);
     return rc;
   }
+  // polygons_ of the archived blocks grows by every pruned block's faces: reserved far ahead
+  // (virtual memory until touched) so that no prune call pays for moving the whole list
+  h->archived_polygons.reserve(size_t(1) << 26);
   preloadVccKernels();
   preloadMeshInterfaceKernels();
   preloadCommonKernels();

@@ -45,3 +45,38 @@ print(f"mean wavefronts per quarter warp and LDS.128: {tot / 5:.3f}")
 u = np.sort((nbr & 0x7FF).reshape(n // 32, 160), axis=1)
 print("distinct rows (union over slots) per group of 32 records: mean %.2f"
       % (1 + (u[:, 1:] != u[:, :-1]).sum(axis=1)).mean())
+
+
+# --- would another order of the 32 records of a group help?  (the search kernel is free to
+# choose it.)  Needs the vertex of every record: synth.deformation_case gives every keyframe
+# per_kf vertices = one head item of 1 vertex + one item with the rest.
+n_kf = max(n_c // 10, 1)
+per_kf = -(-n_v // n_kf)
+if per_kf <= 2049:
+    slot = np.arange(n)
+    within = slot % per_kf
+    item_start = slot - within + (within > 0)
+    vert = item_start + rec[:n, 0]
+    vx, vy, vz = case["x"][vert], case["y"][vert], case["z"][vert]
+    rank_in_item = slot - item_start
+    grp = (item_start.astype(np.int64) << 8) + rank_in_item // 32      # group id
+    full = np.bincount(np.unique(grp, return_inverse=True)[1])          # group sizes
+    gid = np.unique(grp, return_inverse=True)[1]
+    keep = full[gid] == 32
+    R5 = (nbr & 0x7FF)[keep]
+    g_of = gid[keep]
+    def morton(cell):
+        qx, qy, qz = (np.floor(c / cell).astype(np.int64) & 1023 for c in (vx[keep], vy[keep], vz[keep]))
+        m = np.zeros_like(qx)
+        for b in range(10):
+            m |= ((qx >> b) & 1) << (3 * b) | ((qy >> b) & 1) << (3 * b + 1) | ((qz >> b) & 1) << (3 * b + 2)
+        return m
+
+    for label, key in (("as recorded", rank_in_item[keep] % 32), ("by z", vz[keep]),
+                       ("by x", vx[keep]), ("by y", vy[keep]), ("by Morton code, 0.75 m cells", morton(0.75)),
+                       ("by Morton code, 0.4 m cells", morton(0.4))):
+        o = np.lexsort((key, g_of))
+        Rr = R5[o].reshape(-1, 8, 5)
+        srt = np.sort(Rr, axis=1)
+        d = 1 + (srt[:, 1:, :] != srt[:, :-1, :]).sum(axis=1)
+        print(f"records of a group ordered {label}: distinct rows per quarter warp and slot {d.mean():.2f}")
