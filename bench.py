@@ -266,10 +266,16 @@ def run_b200(args):
 
     case = synth.deformation_slab(n_total, n_ctrl, first, n_local)
     # host-side (pinned) copies of this rank's inputs: what an end-to-end caller owns
-    h_in = {k: torch.from_numpy(case[k]).pin_memory() for k in ("x", "y", "z")}
+    # x / y / z as planes of ONE page-locked allocation (and so the outputs): a chunk of all three
+    # then moves in one 3-row DMA operation (scripts/microbench/pcie_chunks.cu)
+    h_in_planes = torch.empty((3, n_local), dtype=torch.float32).pin_memory()
+    for i, k in enumerate(("x", "y", "z")):
+        h_in_planes[i].copy_(torch.from_numpy(case[k]))
+    h_in = {k: h_in_planes[i] for i, k in enumerate(("x", "y", "z"))}
     h_stamps = torch.from_numpy(case["stamps"].view(np.int64)).pin_memory()
     h_poses = torch.from_numpy(case["poses"]).pin_memory()
-    h_out = [torch.empty(n_local, dtype=torch.float32).pin_memory() for _ in range(3)]
+    h_out_planes = torch.empty((3, n_local), dtype=torch.float32).pin_memory()
+    h_out = [h_out_planes[0], h_out_planes[1], h_out_planes[2]]
 
     d = {k: h_in[k].to(dev) for k in h_in}
     d_stamps = h_stamps.to(dev)
@@ -511,7 +517,39 @@ def run_b200(args):
         e2e_ms = float(t.item())
         if world == 1:
             assert torch.equal(h_out[0], d_out[0].cpu()) and torch.equal(h_out[2], d_out[2].cpu())
+        # the floor under that number on this box: the same bytes moved by plain copies, up and
+        # down at once, no kernel, no pipeline (every rank at the same time: the ranks share the
+        # host's PCIe root complexes and memory)
+        d_floor_in = torch.empty((3, n_local), dtype=torch.float32, device=dev)
+        d_floor_out = torch.empty((3, n_local), dtype=torch.float32, device=dev)
+        s_up, s_down = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+        def copies_only():
+            with torch.cuda.stream(s_up):
+                d_floor_in.copy_(h_in_planes, non_blocking=True)
+            with torch.cuda.stream(s_down):
+                h_out_scratch.copy_(d_floor_out, non_blocking=True)
+
+        h_out_scratch = torch.empty((3, n_local), dtype=torch.float32).pin_memory()
+        for _ in range(2):
+            copies_only()
+        torch.cuda.synchronize(dev)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            copies_only()
+        torch.cuda.synchronize(dev)
+        barrier()
+        copy_ms = 1e3 * (time.perf_counter() - t0) / e2e_steps
+        t = torch.tensor([copy_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        copy_ms = float(t.item())
+        del d_floor_in, d_floor_out, h_out_scratch
         e2e = {"value": n_total / (e2e_ms * 1e-3), "unit": "vertices/s", "ms_per_step": e2e_ms,
+               "copies_only_ms": copy_ms,
+               "copies_only_note": "12 B/vertex up and 12 B/vertex down per rank as two plain page-locked copies "
+                                   "at once on every rank, nothing else: what the host's PCIe paths give N ranks",
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "api": e2e_api,
                "bytes_note": "per rank (rank 0 also uploads the pose table); the stamps went up with "
                              "the first deformMesh and are not sent again",

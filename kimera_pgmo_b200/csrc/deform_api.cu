@@ -13,6 +13,65 @@
 
 using namespace pgmo;
 
+namespace {
+struct PlaneSet;
+// one plane of a PlaneSet; reserve() grows all three planes of the set
+struct PlaneView {
+  float* ptr = nullptr;
+  size_t cap = 0;
+  PlaneSet* set = nullptr;
+  int reserve(size_t n);
+};
+struct PlaneSet {
+  pgmo::DevBuf<float> all;
+  PlaneView* view[3];
+  size_t pitch = 0;  // elements between planes
+  PlaneSet(PlaneView* a, PlaneView* b, PlaneView* c) : view{a, b, c} {
+    for (PlaneView* v : view) v->set = this;
+  }
+  int reserve(size_t n) {
+    if (n <= pitch) return PGMO_OK;
+    size_t want = pitch ? pitch : 256;
+    while (want < n) want += want / 2 + 256;
+    want = (want + 63) & ~static_cast<size_t>(63);  // planes stay 256-byte aligned
+    all.release();
+    pitch = 0;
+    for (PlaneView* v : view) {
+      v->ptr = nullptr;
+      v->cap = 0;
+    }
+    PGMO_TRY(all.reserve(3 * want));
+    pitch = want;
+    for (int i = 0; i < 3; ++i) {
+      view[i]->ptr = all.ptr + static_cast<size_t>(i) * pitch;
+      view[i]->cap = pitch;
+    }
+    return PGMO_OK;
+  }
+};
+inline int PlaneView::reserve(size_t n) { return n <= cap ? PGMO_OK : set->reserve(n); }
+
+// [b, b + count) of three planes in one direction: one 3-row operation when the planes are
+// equally spaced on both sides, three plain copies otherwise.
+inline cudaError_t copyPlanes(float* d0, float* d1, float* d2, const float* s0, const float* s1,
+                              const float* s2, uint64_t count, cudaMemcpyKind kind,
+                              cudaStream_t stream) {
+  if (count == 0) return cudaSuccess;
+  const ptrdiff_t dp = d1 - d0, sp = s1 - s0;
+  constexpr ptrdiff_t kMaxPitch = (ptrdiff_t(1) << 29) - 1;  // pitch in bytes stays below 2 GiB
+  if (d2 - d1 == dp && s2 - s1 == sp && dp >= static_cast<ptrdiff_t>(count) &&
+      sp >= static_cast<ptrdiff_t>(count) && dp <= kMaxPitch && sp <= kMaxPitch) {
+    return cudaMemcpy2DAsync(d0, static_cast<size_t>(dp) * sizeof(float), s0,
+                             static_cast<size_t>(sp) * sizeof(float), count * sizeof(float), 3, kind,
+                             stream);
+  }
+  cudaError_t e = cudaMemcpyAsync(d0, s0, count * sizeof(float), kind, stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d1, s1, count * sizeof(float), kind, stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d2, s2, count * sizeof(float), kind, stream);
+  return e;
+}
+}  // namespace
+
 struct pgmo_deform {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -76,7 +135,28 @@ struct pgmo_deform {
   // vertices: 4 -> 3.52 ms, 8 -> 3.42, 12 -> 3.60, 16 -> 3.67, 32 -> 3.99 (every slab costs seven
   // DMA transfers and ~8 launches; fewer slabs lengthen the fill and drain of the pipeline)
   int pipe = 8;
+  // slab sizes ramp up over the first `pipe_taper` slabs and down over the last ones (weights
+  // 1, 2, .., taper + 1, .., 2, 1): the upload of the first slab and the download of the last
+  // one overlap with nothing, so they are kept short (PGMO_PIPE_TAPER; 0 = equal slabs)
+  int pipe_taper = 0;
+  // run_host_slab on page-locked buffers with warm association records: the kernels read and
+  // write the host buffers themselves (PGMO_HOST_DIRECT=0 goes back to staged DMA copies)
+  int host_direct = 0;  // 0: staged copies, 1: reads and writes direct, 2: writes direct only
+  uint64_t pipeCut(uint64_t n, int c) const {  // positions before slab / chunk c
+    if (c <= 0) return 0;
+    if (c >= pipe) return n;
+    uint64_t before = 0, total = 0;
+    for (int i = 0; i < pipe; ++i) {
+      const uint64_t w = static_cast<uint64_t>(std::min(std::min(i + 1, pipe - i), pipe_taper + 1));
+      total += w;
+      if (i < c) before += w;
+    }
+    return static_cast<uint64_t>(static_cast<unsigned __int128>(n) * before / total);
+  }
   cudaEvent_t ev_in[kMaxPipe] = {}, ev_done[kMaxPipe] = {};
+  // PGMO_PIPE_TRACE=1: events carry time stamps and every pipelined call prints its timeline
+  bool pipe_trace = false;
+  cudaEvent_t ev_t0 = nullptr, ev_out[kMaxPipe] = {};
   cudaEvent_t ev_stamps = nullptr;
   float r_scale = 1.0f, r_grow_mul = 1.5f, r_grow_add = 1.0f, far_mul = 3.0f;
   uint32_t n_items = 0;
@@ -132,7 +212,11 @@ struct pgmo_deform {
   bool fp_pending = false;
 
   // staging for the host-buffer entry points
-  DevBuf<float> d_x, d_y, d_z, d_ox, d_oy, d_oz;
+  // staged vertex coordinates in / out: three planes of ONE allocation each, so that a chunk of
+  // all three moves in one 3-row DMA operation when the caller's x / y / z are equally spaced
+  // too (copyPlanes; PCIe duplex rate against the operation size: scripts/microbench/pcie_chunks.cu)
+  PlaneView d_x, d_y, d_z, d_ox, d_oy, d_oz;
+  PlaneSet in_planes{&d_x, &d_y, &d_z}, out_planes{&d_ox, &d_oy, &d_oz};
   DevBuf<uint64_t> d_vstamps, d_subset;
   DevBuf<double> d_of64;
   DevBuf<uint32_t> d_assoc;
@@ -514,10 +598,14 @@ int pgmo_deform_create(int device, pgmo_deform_t** out) {
   }
   cudaEventCreateWithFlags(&h->ev_stamps, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&h->ev_fp, cudaEventDisableTiming);
+  if (const char* e = std::getenv("PGMO_PIPE_TRACE")) h->pipe_trace = atoi(e) != 0;
+  const unsigned pipe_ev_flags = h->pipe_trace ? cudaEventDefault : cudaEventDisableTiming;
   for (int i = 0; i < pgmo_deform::kMaxPipe; ++i) {
-    cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_in[i], pipe_ev_flags);
+    cudaEventCreateWithFlags(&h->ev_done[i], pipe_ev_flags);
+    if (h->pipe_trace) cudaEventCreate(&h->ev_out[i]);
   }
+  if (h->pipe_trace) cudaEventCreate(&h->ev_t0);
   for (auto& e : h->ev) {
     if (cudaEventCreate(&e) != cudaSuccess) {
       setLastError("cudaEventCreate failed");
@@ -535,6 +623,8 @@ int pgmo_deform_create(int device, pgmo_deform_t** out) {
   if (const char* e = std::getenv("PGMO_PIPE")) {
     h->pipe = std::max(1, std::min(static_cast<int>(pgmo_deform::kMaxPipe), atoi(e)));
   }
+  if (const char* e = std::getenv("PGMO_HOST_DIRECT")) h->host_direct = atoi(e);
+  if (const char* e = std::getenv("PGMO_PIPE_TAPER")) h->pipe_taper = std::max(0, atoi(e));
   if (const char* e = std::getenv("PGMO_BLEND_COPIES")) h->blend_copies_override = static_cast<uint32_t>(atoi(e));
   *out = h;
   return PGMO_OK;
@@ -554,6 +644,7 @@ void pgmo_deform_destroy(pgmo_deform_t* h) {
   for (int i = 0; i < pgmo_deform::kMaxPipe; ++i) {
     if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
     if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
+    if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]);
   }
   if (h->ev_stamps) cudaEventDestroy(h->ev_stamps);
   if (h->ev_fp) cudaEventDestroy(h->ev_fp);
@@ -1197,18 +1288,39 @@ static int runDeviceRange(pgmo_deform_t* h, uint64_t first_position, uint64_t n_
   return PGMO_OK;
 }
 
+// Page-locked host memory the device can address (cudaHostAlloc / cudaHostRegister under unified
+// addressing): the device-side alias of [p, p + n) or false.
+template <typename T>
+static bool mappedHost(T* p, uint64_t n, T** dev_alias) {
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  if (attr.type != cudaMemoryTypeHost || attr.devicePointer == nullptr) return false;
+  // the last element must belong to a page-locked range too (one allocation in practice)
+  cudaPointerAttributes last;
+  if (cudaPointerGetAttributes(&last, p + (n ? n - 1 : 0)) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  if (last.type != cudaMemoryTypeHost || last.devicePointer == nullptr) return false;
+  *dev_alias = static_cast<T*>(attr.devicePointer);
+  return true;
+}
+
 // Vertex streams up in `pipe` chunks on the copy stream, one event per chunk.
 static int queueVertexUpload(pgmo_deform_t* h, uint64_t n_v, const float* x, const float* y,
                              const float* z, cudaStream_t up, uint64_t* chunk_end) {
   const int n_chunks = h->pipe;
+  if (h->pipe_trace) PGMO_CUDA(cudaEventRecord(h->ev_t0, up));
   for (int c = 0; c < n_chunks; ++c) {
-    const uint64_t b = n_v * static_cast<uint64_t>(c) / n_chunks;
-    const uint64_t e = n_v * static_cast<uint64_t>(c + 1) / n_chunks;
+    const uint64_t b = h->pipeCut(n_v, c);
+    const uint64_t e = h->pipeCut(n_v, c + 1);
     chunk_end[c] = e;
     if (e > b) {
-      PGMO_CUDA(cudaMemcpyAsync(h->d_x.ptr + b, x + b, (e - b) * sizeof(float), cudaMemcpyHostToDevice, up));
-      PGMO_CUDA(cudaMemcpyAsync(h->d_y.ptr + b, y + b, (e - b) * sizeof(float), cudaMemcpyHostToDevice, up));
-      PGMO_CUDA(cudaMemcpyAsync(h->d_z.ptr + b, z + b, (e - b) * sizeof(float), cudaMemcpyHostToDevice, up));
+      PGMO_CUDA(copyPlanes(h->d_x.ptr + b, h->d_y.ptr + b, h->d_z.ptr + b, x + b, y + b, z + b, e - b,
+                           cudaMemcpyHostToDevice, up));
     }
     PGMO_CUDA(cudaEventRecord(h->ev_in[c], up));
   }
@@ -1227,13 +1339,18 @@ static int runPipelined(pgmo_deform_t* h, uint64_t first_position, uint64_t n_po
   PGMO_TRY(h->d_status.reserve(n_pos));
   PGMO_TRY(ensureItems(h, first_position, n_pos, st));
   const int n_slabs = h->pipe;
+  // results written by the kernels straight into the caller's page-locked buffers (posted PCIe
+  // writes) instead of HBM + a download per slab
+  float *dox = nullptr, *doy = nullptr, *doz = nullptr;
+  const bool direct_out = h->host_direct == 2 && mappedHost(out_x, n_pos, &dox) &&
+                          mappedHost(out_y, n_pos, &doy) && mappedHost(out_z, n_pos, &doz);
   uint64_t begin = 0;
   int waited = -1;  // chunks [0, waited] are known to the compute stream
   for (int sl = 0; sl < n_slabs && begin < n_pos; ++sl) {
     uint64_t end = n_pos;
     if (sl + 1 < n_slabs) {
       // first item starting at or after the ideal cut
-      const uint64_t want = n_pos * static_cast<uint64_t>(sl + 1) / n_slabs;
+      const uint64_t want = h->pipeCut(n_pos, sl + 1);
       const auto it = std::lower_bound(h->h_items.begin(), h->h_items.end(), want,
                                        [](const WorkItem& w, uint64_t v) { return w.start < v; });
       end = it == h->h_items.end() ? n_pos : it->start;
@@ -1247,20 +1364,34 @@ static int runPipelined(pgmo_deform_t* h, uint64_t first_position, uint64_t n_po
       waited = need;
     }
     PGMO_TRY(runDeviceRange(h, first_position, n_pos, h->d_x.ptr, h->d_y.ptr, h->d_z.ptr, nullptr,
-                            precision, h->d_ox.ptr, h->d_oy.ptr, h->d_oz.ptr, nullptr, nullptr, 0,
+                            precision, direct_out ? dox : h->d_ox.ptr, direct_out ? doy : h->d_oy.ptr,
+                            direct_out ? doz : h->d_oz.ptr, nullptr, nullptr, 0,
                             nullptr, h->d_status.ptr, nullptr, st, begin, end));
     PGMO_CUDA(cudaEventRecord(h->ev_done[sl], st));
     PGMO_CUDA(cudaStreamWaitEvent(h->s_out, h->ev_done[sl], 0));
-    PGMO_CUDA(cudaMemcpyAsync(out_x + begin, h->d_ox.ptr + begin, cnt * sizeof(float), cudaMemcpyDeviceToHost, h->s_out));
-    PGMO_CUDA(cudaMemcpyAsync(out_y + begin, h->d_oy.ptr + begin, cnt * sizeof(float), cudaMemcpyDeviceToHost, h->s_out));
-    PGMO_CUDA(cudaMemcpyAsync(out_z + begin, h->d_oz.ptr + begin, cnt * sizeof(float), cudaMemcpyDeviceToHost, h->s_out));
+    if (!direct_out) {
+      PGMO_CUDA(copyPlanes(out_x + begin, out_y + begin, out_z + begin, h->d_ox.ptr + begin,
+                           h->d_oy.ptr + begin, h->d_oz.ptr + begin, cnt, cudaMemcpyDeviceToHost, h->s_out));
+    }
     if (processed) {
       PGMO_CUDA(cudaMemcpyAsync(processed + begin, h->d_status.ptr + begin, cnt, cudaMemcpyDeviceToHost, h->s_out));
     }
+    if (h->pipe_trace) PGMO_CUDA(cudaEventRecord(h->ev_out[sl], h->s_out));
     begin = end;
   }
   PGMO_CUDA(cudaStreamSynchronize(h->s_out));
   PGMO_CUDA(cudaStreamSynchronize(st));
+  if (h->pipe_trace) {
+    fprintf(stderr, "pgmo pipe trace (ms after the first upload was queued): slab: upload done | kernels done | download done\n");
+    for (int sl = 0; sl < n_slabs; ++sl) {
+      float a = -1.f, b = -1.f, c = -1.f;
+      cudaEventElapsedTime(&a, h->ev_t0, h->ev_in[sl]);
+      if (cudaEventElapsedTime(&b, h->ev_t0, h->ev_done[sl]) != cudaSuccess) b = -1.f;
+      if (cudaEventElapsedTime(&c, h->ev_t0, h->ev_out[sl]) != cudaSuccess) c = -1.f;
+      fprintf(stderr, "  %2d: %.3f | %.3f | %.3f\n", sl, a, b, c);
+    }
+    cudaGetLastError();
+  }
   return PGMO_OK;
 }
 
@@ -1548,6 +1679,34 @@ int pgmo_deform_run_host_slab(pgmo_deform_t* h, uint64_t first_position, uint64_
     return PGMO_ERR_CUDA;
   }
   CallOrder call_order(h, h->stream);
+  bool any_skip = false;
+  for (const ScheduleRun& run : h->sched.runs) any_skip = any_skip || run.skip;
+  if (h->host_direct == 1 && !any_skip && h->use_grid && h->grid_mode == 1 && h->cache_enabled) {
+    // Association records of an earlier call cover the slab (the usual re-deformation after a
+    // new solve): the blend kernel reads every vertex once and writes every result once, so it
+    // can do both straight on the caller's page-locked buffers over PCIe — no staging copy in
+    // HBM, no DMA descriptors, uploads / kernel / downloads overlap by themselves.  Items the
+    // kernel finds stale are searched again from the same pointers (second read over PCIe).
+    cudaStream_t st = h->stream;
+    PGMO_TRY(ensureItems(h, first_position, n_local, st));
+    const float *dx = nullptr, *dy = nullptr, *dz = nullptr;
+    float *dox = nullptr, *doy = nullptr, *doz = nullptr;
+    const bool records_apply = h->cache_items_first == h->items_first && h->cache_items_n == h->items_n &&
+                               h->cache_sched_builds == h->items_sched_builds && h->cache_precision == precision;
+    if (records_apply && h->n_items > 0 && h->cache_cold_lo == 0 && h->n_items <= h->cache_cold_hi &&
+        mappedHost(x, n_local, &dx) && mappedHost(y, n_local, &dy) && mappedHost(z, n_local, &dz) &&
+        mappedHost(out_x, n_local, &dox) && mappedHost(out_y, n_local, &doy) &&
+        mappedHost(out_z, n_local, &doz)) {
+      PGMO_TRY(h->d_status.reserve(n_local));
+      PGMO_TRY(runDeviceRange(h, first_position, n_local, dx, dy, dz, nullptr, precision, dox, doy, doz,
+                              nullptr, nullptr, 0, nullptr, h->d_status.ptr, nullptr, st, 0, n_local));
+      if (processed) {
+        PGMO_CUDA(cudaMemcpyAsync(processed, h->d_status.ptr, n_local, cudaMemcpyDeviceToHost, st));
+      }
+      PGMO_CUDA(cudaStreamSynchronize(st));
+      return PGMO_OK;
+    }
+  }
   PGMO_TRY(h->d_x.reserve(n_local));
   PGMO_TRY(h->d_y.reserve(n_local));
   PGMO_TRY(h->d_z.reserve(n_local));
@@ -1556,8 +1715,6 @@ int pgmo_deform_run_host_slab(pgmo_deform_t* h, uint64_t first_position, uint64_
   PGMO_TRY(h->d_oz.reserve(n_local));
   uint64_t chunk_end[pgmo_deform::kMaxPipe];
   PGMO_TRY(queueVertexUpload(h, n_local, x, y, z, h->s_in, chunk_end));
-  bool any_skip = false;
-  for (const ScheduleRun& run : h->sched.runs) any_skip = any_skip || run.skip;
   if (any_skip || !h->use_grid) {
     // skipped vertices come back with their input coordinates (the reference's new_points starts
     // as a copy of the input cloud and `continue`s past them): seed the outputs, then one pass
