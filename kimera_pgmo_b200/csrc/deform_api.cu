@@ -33,7 +33,7 @@ struct PlaneSet {
     if (n <= pitch) return PGMO_OK;
     size_t want = pitch ? pitch : 256;
     while (want < n) want += want / 2 + 256;
-    want = (want + 63) & ~static_cast<size_t>(63);  // planes stay 256-byte aligned
+    want = (want + 1023) & ~static_cast<size_t>(1023);  // planes stay 4 KB aligned
     all.release();
     pitch = 0;
     for (PlaneView* v : view) {
@@ -151,7 +151,11 @@ struct pgmo_deform {
       total += w;
       if (i < c) before += w;
     }
-    return static_cast<uint64_t>(static_cast<unsigned __int128>(n) * before / total);
+    // cuts on 4 KB boundaries: a DMA operation that starts at an odd address runs far below the
+    // link rate (scripts/microbench/pcie_chunks.cu: 6 or 12 equal chunks of 40 MB planes took
+    // 3.3 ms where 8 or 16 took 2.8)
+    const uint64_t cut = static_cast<uint64_t>(static_cast<unsigned __int128>(n) * before / total);
+    return std::min<uint64_t>(n, (cut + 512) & ~static_cast<uint64_t>(1023));
   }
   cudaEvent_t ev_in[kMaxPipe] = {}, ev_done[kMaxPipe] = {};
   // PGMO_PIPE_TRACE=1: events carry time stamps and every pipelined call prints its timeline
@@ -1344,7 +1348,7 @@ static int runPipelined(pgmo_deform_t* h, uint64_t first_position, uint64_t n_po
   float *dox = nullptr, *doy = nullptr, *doz = nullptr;
   const bool direct_out = h->host_direct == 2 && mappedHost(out_x, n_pos, &dox) &&
                           mappedHost(out_y, n_pos, &doy) && mappedHost(out_z, n_pos, &doz);
-  uint64_t begin = 0;
+  uint64_t begin = 0, down_begin = 0;
   int waited = -1;  // chunks [0, waited] are known to the compute stream
   for (int sl = 0; sl < n_slabs && begin < n_pos; ++sl) {
     uint64_t end = n_pos;
@@ -1369,13 +1373,20 @@ static int runPipelined(pgmo_deform_t* h, uint64_t first_position, uint64_t n_po
                             nullptr, h->d_status.ptr, nullptr, st, begin, end));
     PGMO_CUDA(cudaEventRecord(h->ev_done[sl], st));
     PGMO_CUDA(cudaStreamWaitEvent(h->s_out, h->ev_done[sl], 0));
-    if (!direct_out) {
-      PGMO_CUDA(copyPlanes(out_x + begin, out_y + begin, out_z + begin, h->d_ox.ptr + begin,
-                           h->d_oy.ptr + begin, h->d_oz.ptr + begin, cnt, cudaMemcpyDeviceToHost, h->s_out));
+    // slabs end on work-item boundaries, downloads on 4 KB boundaries inside what is finished
+    // (the odd tail travels with the next slab)
+    const uint64_t down_end = end == n_pos ? n_pos : std::max(down_begin, end & ~static_cast<uint64_t>(1023));
+    const uint64_t down_cnt = down_end - down_begin;
+    if (!direct_out && down_cnt) {
+      PGMO_CUDA(copyPlanes(out_x + down_begin, out_y + down_begin, out_z + down_begin,
+                           h->d_ox.ptr + down_begin, h->d_oy.ptr + down_begin, h->d_oz.ptr + down_begin,
+                           down_cnt, cudaMemcpyDeviceToHost, h->s_out));
     }
-    if (processed) {
-      PGMO_CUDA(cudaMemcpyAsync(processed + begin, h->d_status.ptr + begin, cnt, cudaMemcpyDeviceToHost, h->s_out));
+    if (processed && down_cnt) {
+      PGMO_CUDA(cudaMemcpyAsync(processed + down_begin, h->d_status.ptr + down_begin, down_cnt,
+                                cudaMemcpyDeviceToHost, h->s_out));
     }
+    down_begin = down_end;
     if (h->pipe_trace) PGMO_CUDA(cudaEventRecord(h->ev_out[sl], h->s_out));
     begin = end;
   }

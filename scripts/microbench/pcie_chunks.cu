@@ -6,6 +6,16 @@
 #include <cstdio>
 #include <cuda_runtime.h>
 
+// stands in for the deformation kernels of one slab: streams `n4` float4 through the SMs
+__global__ void busyKernel(const float4* __restrict__ in, float4* __restrict__ out, size_t n4, int rounds) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float4 v = in[i];
+    for (int r = 0; r < rounds; ++r) v.x = v.x * 1.0001f + v.y;
+    out[i] = v;
+  }
+}
+
 int main() {
   const size_t n = 120u << 20;
   char *h_in, *h_out, *d_in, *d_out;
@@ -48,6 +58,47 @@ int main() {
       const double bytes = (mode >= 2 ? 2.0 : 1.0) * n;
       printf("ops of %3zu MB, %-20s: %.3f ms = %.1f GB/s\n", mb, names[mode], ms, bytes / ms / 1e6);
     }
+  }
+  // The shape of the host-pointer deformation step without its kernels: chunk c goes up on one
+  // stream, a second stream waits for it (the kernels would run here), a third stream waits for
+  // that and brings chunk c of the results down.  n_chunks 3-row operations each way.
+  cudaStream_t mid;
+  cudaStreamCreateWithFlags(&mid, cudaStreamNonBlocking);
+  cudaEvent_t in_done[64], k_done[64];
+  for (int i = 0; i < 64; ++i) {
+    cudaEventCreateWithFlags(&in_done[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&k_done[i], cudaEventDisableTiming);
+  }
+  char *d_scratch_in, *d_scratch_out;
+  cudaMalloc(&d_scratch_in, n);
+  cudaMalloc(&d_scratch_out, n);
+  for (int with_kernel = 0; with_kernel < 3; ++with_kernel)
+  for (int n_chunks : {1, 2, 4, 6, 8, 12, 16}) {
+    double best = 1e9;
+    const size_t plane = n / 3, per = plane / n_chunks;
+    for (int rep = 0; rep < 6; ++rep) {
+      cudaDeviceSynchronize();
+      const auto t0 = std::chrono::steady_clock::now();
+      for (int c = 0; c < n_chunks; ++c) {
+        const size_t o = per * c, w = c + 1 == n_chunks ? plane - o : per;
+        cudaMemcpy2DAsync(d_in + o, plane, h_in + o, plane, w, 3, cudaMemcpyHostToDevice, up);
+        cudaEventRecord(in_done[c], up);
+        cudaStreamWaitEvent(mid, in_done[c], 0);
+        if (with_kernel) {  // 1: ~HBM-bound pass over 120 MB / n_chunks; 2: the same, 200 dependent FMAs per element
+          busyKernel<<<148 * 8, 256, 0, mid>>>(reinterpret_cast<const float4*>(d_scratch_in),
+                                               reinterpret_cast<float4*>(d_scratch_out), n / 16 / n_chunks,
+                                               with_kernel == 1 ? 1 : 200);
+        }
+        cudaEventRecord(k_done[c], mid);
+        cudaStreamWaitEvent(down, k_done[c], 0);
+        cudaMemcpy2DAsync(h_out + o, plane, d_out + o, plane, w, 3, cudaMemcpyDeviceToHost, down);
+      }
+      cudaDeviceSynchronize();
+      const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+      if (ms < best) best = ms;
+    }
+    printf("pipeline of %2d chunks (up -> %s -> down, 3-row operations): %.3f ms\n", n_chunks,
+           with_kernel == 0 ? "wait" : with_kernel == 1 ? "streaming kernel" : "compute-heavy kernel", best);
   }
   return 0;
 }

@@ -25,7 +25,7 @@ h_out3 = torch.empty((3, n_v), dtype=torch.float32).pin_memory()
 h_stamps = pin(case["stamps"].view(np.int64))
 h_out = [torch.empty(n_v, dtype=torch.float32).pin_memory() for _ in range(3)]
 h_poses = pin(case["poses"])
-combos = [(8, 0, 0, 0), (8, 0, 0, 1), (6, 1, 0, 1), (6, 0, 0, 1), (10, 0, 0, 1), (12, 0, 0, 1), (12, 2, 0, 1), (16, 0, 0, 1), (16, 3, 0, 1)]
+combos = [(8, 0, 0, 0), (8, 0, 0, 1), (6, 0, 0, 1), (12, 0, 0, 1), (16, 0, 0, 1), (24, 0, 0, 1), (12, 2, 0, 1), (16, 3, 0, 1), (16, 0, 0, 0)]
 for rep in range(2):
     for pipe, taper, direct, planes in combos:
         os.environ["PGMO_PIPE"], os.environ["PGMO_PIPE_TAPER"] = str(pipe), str(taper)
