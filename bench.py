@@ -630,8 +630,9 @@ def run_b200(args):
                     "bytes_per_vertex": blend_bytes, "achieved": own, "frac": own / peak,
                     "note": "what the blend-only kernel itself moves per vertex: xyz in, 16-byte "
                             "association record, k + 1 weights, xyz out, status (= `traffic`)"},
-                "limiter": "shared-memory data pipe (pose-row gather: 35 LDS.128 per vertex, "
-                           "l1tex__data_pipe_lsu_wavefronts 87 % of peak; DESIGN.md 2.4)",
+                "limiter": "shared-memory data pipe (pose-row gather: 35 LDS.128 + 5 LDS.64 per vertex, "
+                           "l1tex__data_pipe_lsu_wavefronts 83 % of peak, 42 % of the shared-memory "
+                           "wavefronts are bank-conflict replays; profiles/r02_blend_raw.csv, DESIGN.md 2.4)",
                 "search_ms": mean("search_ms", warm_infos),
                 "resolver_ms": mean("resolver_ms", warm_infos),
                 "stale_items": mean("stale_items", warm_infos),
@@ -647,7 +648,7 @@ def run_b200(args):
                     "achieved": f_achieved, "peak": peak, "unit": "GB/s", "frac": f_achieved / peak,
                     "bytes_per_vertex": BYTES_STEP_PER_VERTEX, "search_ms": f_search,
                     "blend_ms": f_blend, "resolver_ms": mean("resolver_ms", first_infos),
-                    "traffic": load_ncu_traffic("knn_traffic.json"),
+                    "traffic": load_ncu_traffic("first_deform_traffic.json"),
                     "step_frac": BYTES_STEP_PER_VERTEX * n_local / (first_ms * 1e-3) / 1e9 / peak,
                 },
             },
