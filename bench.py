@@ -303,11 +303,16 @@ def run_b200(args):
     # slab references straight from rank 0's memory over NVLink — no broadcast of the whole table
     pose_src = sharding.PoseSource(h, n_ctrl, rank, world, dev) if world > 1 else None
     sync_flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    flag_sync = os.environ.get("PGMO_POSE_SYNC", "flags") != "collective"
     ctrl_range = [0, n_ctrl]
 
     def new_poses(poses):
         """a new solve result (device tensor, or pinned host tensor on rank 0) reaches every GPU"""
-        if world > 1:
+        if world > 1 and flag_sync:
+            # ordering by sequence numbers inside the pose source (system-scope release / acquire
+            # over NVLink): no collective per solve
+            pose_src.publish_and_pull(poses, ctrl_range[0], ctrl_range[1], stream)
+        elif world > 1:
             pose_src.write(poses, stream)
             dist.all_reduce(sync_flag)
             pose_src.pull(ctrl_range[0], ctrl_range[1], stream)
@@ -337,6 +342,8 @@ def run_b200(args):
     state = {"valid": False}
     flag_group = dist.new_group(backend="gloo") if world > 1 else None
     flag = torch.zeros(1, dtype=torch.int32)
+    # experiment only (timing of the host-side flag all-reduce): the ranks then trust their own check
+    skip_flag_reduce = os.environ.get("PGMO_BENCH_SKIP_FLAG_REDUCE") == "1"
 
     def run_slab():
         h.run_device(first, n_local, d["x"], d["y"], d["z"], d_out[0], d_out[1], d_out[2],
@@ -353,7 +360,7 @@ def run_b200(args):
             h.stamp_check_begin(d_stamps, n_local, stream)
             run_slab()
             changed = h.stamp_check_finish()
-            if world > 1:
+            if world > 1 and not skip_flag_reduce:
                 flag[0] = int(changed)
                 dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=flag_group)
                 changed = bool(flag[0])
@@ -368,7 +375,9 @@ def run_b200(args):
             rc = h.build_schedule(ss, sl, n_total, K_NEIGHBOURS, TOL_T)
             assert rc == 0
             ctrl_range[:] = h.slab_control_range(first, n_local)
-            if world > 1:  # the tables outside the old range may be stale: one full pull
+            if world > 1 and flag_sync:  # the tables outside the old range may be stale: one full pull
+                pose_src.pull_again(0, n_ctrl, stream)
+            elif world > 1:
                 h.update_poses_from_source((pose_src.step - 1) % 2, 0, n_ctrl, stream)
             t0 = _mark("schedule", t0)
             run_slab()
@@ -591,6 +600,11 @@ def run_b200(args):
         hr.close()
         del cloud, d_cloud_out, h_cloud
 
+    pose_timeouts = 0
+    if world > 1:
+        t = torch.tensor([h.pose_source_timeouts()], dtype=torch.int64, device=dev)
+        dist.all_reduce(t)
+        pose_timeouts = int(t.item())
     config3 = None
     if not args.no_config3:
         h.close()
@@ -654,6 +668,12 @@ def run_b200(args):
             },
             "clocks": clocks.summary(),
             "e2e": e2e, "e2e_resident_mesh": resident, "config3": config3,
+            "pose_exchange": None if world == 1 else {
+                "how": ("rank 0 writes the solve result into its pose source once; every rank's "
+                        "table-build kernel pulls the rows its slab references over NVLink; ordered by "
+                        + ("sequence numbers in the source's memory (release / acquire, no collective)"
+                           if flag_sync else "a 1-element NCCL all-reduce")),
+                "waits_that_timed_out": pose_timeouts},
             # buildControlTables, K1, K3b (validating), K3a / K4 / K3b over the stale list, done
             "gpu_launches": 7 * args.steps,
             "resolved_by_tie_kernel": int(n_resolved),

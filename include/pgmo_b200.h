@@ -123,6 +123,22 @@ int pgmo_deform_pose_source_attach(pgmo_deform_t* h, uint64_t n_c, const void* i
 int pgmo_deform_pose_source_write(pgmo_deform_t* h, int buffer, const double* poses12, void* stream);
 int pgmo_deform_update_poses_from_source(pgmo_deform_t* h, int buffer, uint64_t row_begin,
                                          uint64_t row_end, void* stream);
+/* The same with the ordering inside the source: sequence numbers (1, 2, ...; buffer = seq & 1)
+ * kept in flag words of the source's own memory, written and polled with system-scope release /
+ * acquire over NVLink, so that no collective between the processes is needed per solve.
+ *   publish   owner: waits on the device until readers 0 .. n_readers - 1 have acknowledged
+ *             sequence seq - 2 (the buffer's previous content), copies poses12, marks the buffer
+ *             ready for seq.  Stream-ordered, the host does not wait.
+ *   update_poses_from_source_seq   reader `reader` (the owner too): a one-thread kernel waits
+ *             until the buffer is ready for seq, the table-build kernel pulls rows
+ *             [row_begin, row_end), a one-thread kernel acknowledges seq.
+ * A wait gives up after 2 s (the pull then reads whatever the buffer holds) and is counted:
+ * pgmo_deform_pose_source_timeouts synchronises the handle's stream and returns the count. */
+int pgmo_deform_pose_source_publish(pgmo_deform_t* h, uint64_t seq, uint32_t n_readers,
+                                    const double* poses12, void* stream);
+int pgmo_deform_update_poses_from_source_seq(pgmo_deform_t* h, uint64_t seq, uint32_t reader,
+                                             uint64_t row_begin, uint64_t row_end, void* stream);
+int pgmo_deform_pose_source_timeouts(pgmo_deform_t* h, uint64_t* n);
 /* Control-point rows the slab [first_position, first_position + n_local) can reference under the
  * current schedule: the union of its runs' windows. */
 int pgmo_deform_slab_control_range(pgmo_deform_t* h, uint64_t first_position, uint64_t n_local,

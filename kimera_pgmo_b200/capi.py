@@ -57,6 +57,9 @@ SIGNATURES = {
     "pgmo_deform_pose_source_attach": (C.c_int, [_vp, C.c_uint64, _vp, _vp, C.c_int]),
     "pgmo_deform_pose_source_write": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "pgmo_deform_update_poses_from_source": (C.c_int, [_vp, C.c_int, C.c_uint64, C.c_uint64, _vp]),
+    "pgmo_deform_pose_source_publish": (C.c_int, [_vp, C.c_uint64, C.c_uint32, _vp, _vp]),
+    "pgmo_deform_update_poses_from_source_seq": (C.c_int, [_vp, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, _vp]),
+    "pgmo_deform_pose_source_timeouts": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "pgmo_deform_slab_control_range": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _u64p, _u64p]),
     "pgmo_deform_run_host_slab": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _vp, _vp, _vp, C.c_int, _vp,
                                             _vp, _vp, _vp]),
@@ -249,6 +252,18 @@ class DeformHandle:
 
     def pose_source_write(self, buffer, poses12, stream=0):
         _check(self._lib.pgmo_deform_pose_source_write(self._h, buffer, _ptr(poses12), _vp(stream)))
+
+    def pose_source_publish(self, seq, n_readers, poses12, stream=0):
+        _check(self._lib.pgmo_deform_pose_source_publish(self._h, seq, n_readers, _ptr(poses12), _vp(stream)))
+
+    def update_poses_from_source_seq(self, seq, reader, row_begin, row_end, stream=0):
+        _check(self._lib.pgmo_deform_update_poses_from_source_seq(self._h, seq, reader, row_begin, row_end,
+                                                                  _vp(stream)))
+
+    def pose_source_timeouts(self):
+        n = C.c_uint64(0)
+        _check(self._lib.pgmo_deform_pose_source_timeouts(self._h, C.byref(n)))
+        return int(n.value)
 
     def update_poses_from_source(self, buffer, row_begin, row_end, stream=0):
         _check(self._lib.pgmo_deform_update_poses_from_source(self._h, buffer, row_begin, row_end, _vp(stream)))

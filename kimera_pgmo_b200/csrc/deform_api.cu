@@ -177,6 +177,8 @@ struct pgmo_deform {
   // pose source (multi-GPU): the table the solve result is written to once; every device pulls
   // the rows its slab references from it (2 buffers of n_c x 12 doubles, used alternately)
   double* pose_src = nullptr;
+  DevBuf<unsigned long long> d_pose_timeouts;  // waits of the sequenced protocol that gave up
+  bool pose_timeouts_zeroed = false;
   uint64_t pose_src_n = 0;
   bool pose_src_owned = false, pose_src_ipc = false;
 
@@ -799,7 +801,10 @@ int pgmo_deform_pose_source_create(pgmo_deform_t* h, uint64_t n_c, void* ipc_han
     setLastError("pose source already set on this handle");
     return PGMO_ERR_INVALID;
   }
-  PGMO_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->pose_src), 2 * 12 * n_c * sizeof(double)));
+  // two pose buffers, then the flag words of the sequenced protocol (ready[2], ack[64])
+  const size_t bytes = 2 * 12 * n_c * sizeof(double) + kPoseSrcFlagWords * sizeof(unsigned long long);
+  PGMO_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->pose_src), bytes));
+  PGMO_CUDA(cudaMemset(h->pose_src + 2 * 12 * n_c, 0, kPoseSrcFlagWords * sizeof(unsigned long long)));
   h->pose_src_n = n_c;
   h->pose_src_owned = true;
   if (ipc_handle64) {
@@ -880,6 +885,75 @@ int pgmo_deform_update_poses_from_source(pgmo_deform_t* h, int buffer, uint64_t 
                                       h->pose_src + static_cast<uint64_t>(buffer) * 12 * h->pose_src_n,
                                       h->d_poses.ptr, h->d_pos.ptr, h->d_pose_f32.ptr,
                                       h->d_pose_rows.ptr, h->d_class.ptr, st));
+  return PGMO_OK;
+}
+
+static unsigned long long* poseSourceFlags(pgmo_deform_t* h) {
+  return reinterpret_cast<unsigned long long*>(h->pose_src + 2 * 12 * h->pose_src_n);
+}
+
+int pgmo_deform_pose_source_publish(pgmo_deform_t* h, uint64_t seq, uint32_t n_readers,
+                                    const double* poses12, void* stream) {
+  PGMO_CHECK_ARG(h != nullptr && poses12 != nullptr && seq >= 1 && n_readers <= kPoseSrcMaxReaders);
+  PGMO_TRY(ensureDevice(h->device));
+  if (!h->pose_src || !h->pose_src_owned) {
+    setLastError("pose_source_publish: this handle does not own a pose source");
+    return PGMO_ERR_INVALID;
+  }
+  cudaStream_t st = pick(h, stream);
+  CallOrder call_order(h, st);
+  PGMO_TRY(h->d_pose_timeouts.reserve(1));
+  if (!h->pose_timeouts_zeroed) {
+    PGMO_CUDA(cudaMemsetAsync(h->d_pose_timeouts.ptr, 0, sizeof(unsigned long long), st));
+    h->pose_timeouts_zeroed = true;
+  }
+  unsigned long long* flags = poseSourceFlags(h);
+  const int buffer = static_cast<int>(seq & 1u);
+  // the buffer's previous content is sequence seq - 2: nobody may still be reading it
+  PGMO_CUDA(launchPoseSourceWaitAcks(flags + 2, n_readers, seq >= 2 ? seq - 2 : 0,
+                                     h->d_pose_timeouts.ptr, st));
+  PGMO_CUDA(cudaMemcpyAsync(h->pose_src + static_cast<uint64_t>(buffer) * 12 * h->pose_src_n, poses12,
+                            12 * h->pose_src_n * sizeof(double), cudaMemcpyDefault, st));
+  PGMO_CUDA(launchPoseSourceStore(flags + buffer, seq, st));
+  return PGMO_OK;
+}
+
+int pgmo_deform_update_poses_from_source_seq(pgmo_deform_t* h, uint64_t seq, uint32_t reader,
+                                             uint64_t row_begin, uint64_t row_end, void* stream) {
+  PGMO_CHECK_ARG(h != nullptr && seq >= 1 && reader < kPoseSrcMaxReaders);
+  PGMO_TRY(ensureDevice(h->device));
+  if (!h->pose_src || h->pose_src_n != h->n_c) {
+    setLastError("update_poses_from_source_seq: no pose source for %llu control points",
+                 static_cast<unsigned long long>(h->n_c));
+    return PGMO_ERR_INVALID;
+  }
+  cudaStream_t st = pick(h, stream);
+  {
+    CallOrder call_order(h, st);
+    PGMO_TRY(h->d_pose_timeouts.reserve(1));
+    if (!h->pose_timeouts_zeroed) {
+      PGMO_CUDA(cudaMemsetAsync(h->d_pose_timeouts.ptr, 0, sizeof(unsigned long long), st));
+      h->pose_timeouts_zeroed = true;
+    }
+    PGMO_CUDA(launchPoseSourceWaitReady(poseSourceFlags(h) + (seq & 1u), seq, h->d_pose_timeouts.ptr, st));
+  }
+  PGMO_TRY(pgmo_deform_update_poses_from_source(h, static_cast<int>(seq & 1u), row_begin, row_end, stream));
+  {
+    CallOrder call_order(h, st);
+    PGMO_CUDA(launchPoseSourceStore(poseSourceFlags(h) + 2 + reader, seq, st));
+  }
+  return PGMO_OK;
+}
+
+int pgmo_deform_pose_source_timeouts(pgmo_deform_t* h, uint64_t* n) {
+  PGMO_CHECK_ARG(h != nullptr && n != nullptr);
+  *n = 0;
+  if (!h->pose_timeouts_zeroed) return PGMO_OK;
+  PGMO_TRY(ensureDevice(h->device));
+  unsigned long long v = 0;
+  PGMO_CUDA(cudaStreamSynchronize(h->stream));
+  PGMO_CUDA(cudaMemcpy(&v, h->d_pose_timeouts.ptr, sizeof(v), cudaMemcpyDeviceToHost));
+  *n = v;
   return PGMO_OK;
 }
 

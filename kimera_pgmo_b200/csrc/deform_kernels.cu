@@ -372,6 +372,71 @@ cudaError_t launchBuildControlTables(uint64_t n_c, const double* ctrl_pos, const
   return cudaGetLastError();
 }
 
+// ---- sequenced pose source: the ordering between the writer of a solve result and the devices
+// that pull it is kept by flags inside the source's own memory (sequence numbers, system-scope
+// release / acquire over NVLink) instead of a collective between the processes.
+namespace {
+__device__ __forceinline__ unsigned long long loadAcquireSys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void storeReleaseSys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globalTimerNs() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// waits until *p >= need; gives up after kPoseWaitNs and counts the timeout (the caller's data is
+// then whatever the buffer holds: pgmo_deform_pose_source_timeouts reports it)
+constexpr unsigned long long kPoseWaitNs = 2000000000ull;
+__device__ __forceinline__ void waitAtLeast(const unsigned long long* p, unsigned long long need,
+                                            unsigned long long* timeouts) {
+  const unsigned long long t0 = globalTimerNs();
+  while (loadAcquireSys(p) < need) {
+    if (globalTimerNs() - t0 > kPoseWaitNs) {
+      atomicAdd(timeouts, 1ull);
+      return;
+    }
+    __nanosleep(100);
+  }
+}
+}  // namespace
+
+// writer, before it overwrites a buffer: every reader has acknowledged the buffer's old content
+__global__ void poseSourceWaitAcksKernel(const unsigned long long* __restrict__ acks, uint32_t n_readers,
+                                         unsigned long long need, unsigned long long* timeouts) {
+  if (threadIdx.x < n_readers) waitAtLeast(acks + threadIdx.x, need, timeouts);
+}
+__global__ void poseSourceStoreKernel(unsigned long long* flag, unsigned long long seq) {
+  __threadfence_system();
+  storeReleaseSys(flag, seq);
+}
+// reader, before it pulls: the buffer holds sequence number `seq` (or a later one)
+__global__ void poseSourceWaitReadyKernel(const unsigned long long* ready, unsigned long long seq,
+                                          unsigned long long* timeouts) {
+  waitAtLeast(ready, seq, timeouts);
+}
+
+cudaError_t launchPoseSourceWaitAcks(const unsigned long long* acks, uint32_t n_readers,
+                                     unsigned long long need, unsigned long long* timeouts,
+                                     cudaStream_t stream) {
+  if (n_readers == 0 || need == 0) return cudaSuccess;
+  poseSourceWaitAcksKernel<<<1, 64, 0, stream>>>(acks, n_readers, need, timeouts);
+  return cudaGetLastError();
+}
+cudaError_t launchPoseSourceStore(unsigned long long* flag, unsigned long long seq, cudaStream_t stream) {
+  poseSourceStoreKernel<<<1, 1, 0, stream>>>(flag, seq);
+  return cudaGetLastError();
+}
+cudaError_t launchPoseSourceWaitReady(const unsigned long long* ready, unsigned long long seq,
+                                      unsigned long long* timeouts, cudaStream_t stream) {
+  poseSourceWaitReadyKernel<<<1, 1, 0, stream>>>(ready, seq, timeouts);
+  return cudaGetLastError();
+}
+
 cudaError_t launchPullBuildPoseTables(uint64_t row_begin, uint64_t row_end, uint64_t n_c,
                                       const double* src, double* poses_local, const double* ctrl_pos,
                                       float* ctrl_pose_f32, double* pose_rows64,

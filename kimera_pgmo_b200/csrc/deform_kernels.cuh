@@ -241,6 +241,15 @@ cudaError_t launchBuildControlTables(uint64_t n_c, const double* ctrl_pos, const
                                      cudaStream_t stream);  // pose_rows64: kBlendCopies x n_c rows
 // Rows [row_begin, row_end) of the pose table `src` (local or a peer device's memory) -> this
 // device's f64 copy (poses_local, may be null or == src), f32 rows and swizzled f64 rows.
+// sequenced pose source (deform_kernels.cu): flags in the source's memory order writer and readers
+constexpr uint32_t kPoseSrcMaxReaders = 64;
+constexpr uint32_t kPoseSrcFlagWords = 2 + kPoseSrcMaxReaders;  // ready[2], ack[kPoseSrcMaxReaders]
+cudaError_t launchPoseSourceWaitAcks(const unsigned long long* acks, uint32_t n_readers,
+                                     unsigned long long need, unsigned long long* timeouts,
+                                     cudaStream_t stream);
+cudaError_t launchPoseSourceStore(unsigned long long* flag, unsigned long long seq, cudaStream_t stream);
+cudaError_t launchPoseSourceWaitReady(const unsigned long long* ready, unsigned long long seq,
+                                      unsigned long long* timeouts, cudaStream_t stream);
 cudaError_t launchPullBuildPoseTables(uint64_t row_begin, uint64_t row_end, uint64_t n_c,
                                       const double* src, double* poses_local, const double* ctrl_pos,
                                       float* ctrl_pose_f32, double* pose_rows64,

@@ -164,6 +164,19 @@ class PoseSource:
         self.h.update_poses_from_source(self.step % 2, row_begin, row_end, stream)
         self.step += 1
 
+    # The same exchange without a collective: sequence numbers in the source's own memory order
+    # the owner's write and everybody's pull (pgmo_deform_pose_source_publish /
+    # pgmo_deform_update_poses_from_source_seq); `seq` counts solves from 1.
+    def publish_and_pull(self, poses, row_begin: int, row_end: int, stream=0):
+        self.seq = getattr(self, "seq", 0) + 1
+        if self.rank == self.owner:
+            self.h.pose_source_publish(self.seq, self.world, poses, stream)
+        self.h.update_poses_from_source_seq(self.seq, self.rank, row_begin, row_end, stream)
+
+    def pull_again(self, row_begin: int, row_end: int, stream=0):
+        """other rows of the solve published last (e.g. after the slab's control range changed)"""
+        self.h.update_poses_from_source_seq(self.seq, self.rank, row_begin, row_end, stream)
+
 
 def gpu_numa_affinity(device_index: int):
     """Pins the calling process to the CPUs of the NUMA node the GPU hangs off (so that the
