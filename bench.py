@@ -764,6 +764,8 @@ def bench_config3(args, world, rank, local_rank, dev, stream, flag_group, peak):
         d["range"] = [0, n_c]
         segs.append((r, first, count, d))
     exchange = sharding.MultiRobotExchange(R, world, dev)
+    readers = {r: [rk for rk in range(world) if any(seg[0] == r for seg in plan[rk])] for r in range(R)}
+    flag_sync = os.environ.get("PGMO_POSE_SYNC", "flags") != "collective"
     state = {"valid": False, "step": 0}
     flag = torch.zeros(1, dtype=torch.int32)
     sync_flag = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -771,7 +773,17 @@ def bench_config3(args, world, rank, local_rank, dev, stream, flag_group, peak):
 
     def step():
         # a new solve for every robot
-        if world > 1:
+        if world > 1 and flag_sync:
+            # ordered by sequence numbers in the pose sources (no collective); the readers of
+            # robot r's source are the ranks that own a segment of robot r, in rank order
+            seq = state["step"] + 1
+            if rank == 0:
+                for r in range(R):
+                    handles[r].pose_source_publish(seq, len(readers[r]), poses[r], stream)
+            for r, first, count, d in segs:
+                handles[r].update_poses_from_source_seq(seq, readers[r].index(rank), d["range"][0],
+                                                        d["range"][1], stream)
+        elif world > 1:
             buf = state["step"] % 2
             if rank == 0:
                 for r in range(R):
