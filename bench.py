@@ -266,8 +266,8 @@ def run_b200(args):
 
     case = synth.deformation_slab(n_total, n_ctrl, first, n_local)
     # host-side (pinned) copies of this rank's inputs: what an end-to-end caller owns
-    # x / y / z as planes of ONE page-locked allocation (and so the outputs): a chunk of all three
-    # then moves in one 3-row DMA operation (scripts/microbench/pcie_chunks.cu)
+    # x / y / z as planes of ONE page-locked allocation (and so the outputs), as the C++ shim
+    # stages them
     h_in_planes = torch.empty((3, n_local), dtype=torch.float32).pin_memory()
     for i, k in enumerate(("x", "y", "z")):
         h_in_planes[i].copy_(torch.from_numpy(case[k]))

@@ -264,12 +264,14 @@ int pgmo_deform_schedule_info(pgmo_deform_t* h, uint64_t* n_runs, uint64_t capac
  * slab.  Only the coordinates cross PCIe (12 B per vertex each way instead of 20 + 12); uploads,
  * kernels and downloads are pipelined in slabs of work items.  x / y / z / out_* are local to the
  * slab.  Skipped vertices (mesh_deformation.h:184-186) come back with their input coordinates.
- * Page-locked buffers (pgmo_host_alloc) copy fastest; when y - x == z - y (the three arrays are
- * equally spaced planes of one allocation; likewise out_*) a chunk of all three moves in one DMA
- * operation instead of three.  Environment knobs, read at pgmo_deform_create: PGMO_PIPE (slabs
- * per call, default 8), PGMO_PIPE_TAPER (shorter first / last slabs), PGMO_HOST_DIRECT (1: the
- * kernels read and write page-locked buffers themselves, 2: write only; measured slower than the
- * staged copies on B200 / PCIe 5, default 0), PGMO_PIPE_TRACE (prints the timeline of a call). */
+ * Page-locked buffers (pgmo_host_alloc) copy fastest.  Every DMA operation starts on a 4 KB
+ * boundary of the arrays (slabs end on work-item boundaries, the copies do not).  Environment
+ * knobs, read at pgmo_deform_create: PGMO_PIPE (slabs per call, default 8), PGMO_PIPE_TAPER
+ * (shorter first / last slabs), PGMO_COPY_2D (1: when y - x == z - y, i.e. the three arrays are
+ * equally spaced planes of one allocation, a chunk of all three moves in one 3-row operation;
+ * measured slightly slower than three plain copies, default 0), PGMO_HOST_DIRECT (1: the kernels
+ * read and write page-locked buffers themselves, 2: write only; measured slower than the staged
+ * copies on B200 / PCIe 5, default 0), PGMO_PIPE_TRACE (prints the timeline of a call). */
 int pgmo_deform_run_host_slab(pgmo_deform_t* h, uint64_t first_position, uint64_t n_local,
                               const float* x, const float* y, const float* z, int precision,
                               float* out_x, float* out_y, float* out_z, uint8_t* processed);

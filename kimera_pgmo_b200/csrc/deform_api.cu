@@ -55,11 +55,11 @@ inline int PlaneView::reserve(size_t n) { return n <= cap ? PGMO_OK : set->reser
 // equally spaced on both sides, three plain copies otherwise.
 inline cudaError_t copyPlanes(float* d0, float* d1, float* d2, const float* s0, const float* s1,
                               const float* s2, uint64_t count, cudaMemcpyKind kind,
-                              cudaStream_t stream) {
+                              cudaStream_t stream, bool use_2d) {
   if (count == 0) return cudaSuccess;
   const ptrdiff_t dp = d1 - d0, sp = s1 - s0;
   constexpr ptrdiff_t kMaxPitch = (ptrdiff_t(1) << 29) - 1;  // pitch in bytes stays below 2 GiB
-  if (d2 - d1 == dp && s2 - s1 == sp && dp >= static_cast<ptrdiff_t>(count) &&
+  if (use_2d && d2 - d1 == dp && s2 - s1 == sp && dp >= static_cast<ptrdiff_t>(count) &&
       sp >= static_cast<ptrdiff_t>(count) && dp <= kMaxPitch && sp <= kMaxPitch) {
     return cudaMemcpy2DAsync(d0, static_cast<size_t>(dp) * sizeof(float), s0,
                              static_cast<size_t>(sp) * sizeof(float), count * sizeof(float), 3, kind,
@@ -141,6 +141,7 @@ struct pgmo_deform {
   int pipe_taper = 0;
   // run_host_slab on page-locked buffers with warm association records: the kernels read and
   // write the host buffers themselves (PGMO_HOST_DIRECT=0 goes back to staged DMA copies)
+  bool copy_2d = false;  // PGMO_COPY_2D=1: one 3-row operation per chunk for equally spaced planes
   int host_direct = 0;  // 0: staged copies, 1: reads and writes direct, 2: writes direct only
   uint64_t pipeCut(uint64_t n, int c) const {  // positions before slab / chunk c
     if (c <= 0) return 0;
@@ -218,9 +219,11 @@ struct pgmo_deform {
   bool fp_pending = false;
 
   // staging for the host-buffer entry points
-  // staged vertex coordinates in / out: three planes of ONE allocation each, so that a chunk of
-  // all three moves in one 3-row DMA operation when the caller's x / y / z are equally spaced
-  // too (copyPlanes; PCIe duplex rate against the operation size: scripts/microbench/pcie_chunks.cu)
+  // staged vertex coordinates in / out: three 4 KB-aligned planes of ONE allocation each.  A
+  // chunk of all three can move in one 3-row DMA operation when the caller's x / y / z are equally
+  // spaced too (copyPlanes, PGMO_COPY_2D=1) — measured 0.08 ms slower per 10 M vertices than three
+  // plain copies once every cut sits on a 4 KB boundary, so off by default
+  // (scripts/pipe_sweep.py, scripts/microbench/pcie_chunks.cu)
   PlaneView d_x, d_y, d_z, d_ox, d_oy, d_oz;
   PlaneSet in_planes{&d_x, &d_y, &d_z}, out_planes{&d_ox, &d_oy, &d_oz};
   DevBuf<uint64_t> d_vstamps, d_subset;
@@ -629,6 +632,7 @@ int pgmo_deform_create(int device, pgmo_deform_t** out) {
   if (const char* e = std::getenv("PGMO_PIPE")) {
     h->pipe = std::max(1, std::min(static_cast<int>(pgmo_deform::kMaxPipe), atoi(e)));
   }
+  if (const char* e = std::getenv("PGMO_COPY_2D")) h->copy_2d = atoi(e) != 0;
   if (const char* e = std::getenv("PGMO_HOST_DIRECT")) h->host_direct = atoi(e);
   if (const char* e = std::getenv("PGMO_PIPE_TAPER")) h->pipe_taper = std::max(0, atoi(e));
   if (const char* e = std::getenv("PGMO_BLEND_COPIES")) h->blend_copies_override = static_cast<uint32_t>(atoi(e));
@@ -1398,7 +1402,7 @@ static int queueVertexUpload(pgmo_deform_t* h, uint64_t n_v, const float* x, con
     chunk_end[c] = e;
     if (e > b) {
       PGMO_CUDA(copyPlanes(h->d_x.ptr + b, h->d_y.ptr + b, h->d_z.ptr + b, x + b, y + b, z + b, e - b,
-                           cudaMemcpyHostToDevice, up));
+                           cudaMemcpyHostToDevice, up, h->copy_2d));
     }
     PGMO_CUDA(cudaEventRecord(h->ev_in[c], up));
   }
@@ -1427,11 +1431,12 @@ static int runPipelined(pgmo_deform_t* h, uint64_t first_position, uint64_t n_po
   for (int sl = 0; sl < n_slabs && begin < n_pos; ++sl) {
     uint64_t end = n_pos;
     if (sl + 1 < n_slabs) {
-      // first item starting at or after the ideal cut
+      // last work-item boundary at or before the end of upload chunk sl: the slab then needs
+      // nothing of chunk sl + 1 (a slab that ends a few vertices later would wait for all of it)
       const uint64_t want = h->pipeCut(n_pos, sl + 1);
-      const auto it = std::lower_bound(h->h_items.begin(), h->h_items.end(), want,
-                                       [](const WorkItem& w, uint64_t v) { return w.start < v; });
-      end = it == h->h_items.end() ? n_pos : it->start;
+      const auto it = std::upper_bound(h->h_items.begin(), h->h_items.end(), want,
+                                       [](uint64_t v, const WorkItem& w) { return v < w.start; });
+      end = it == h->h_items.begin() ? begin : std::prev(it)->start;
     }
     if (end <= begin) continue;
     const uint64_t cnt = end - begin;
@@ -1454,7 +1459,7 @@ static int runPipelined(pgmo_deform_t* h, uint64_t first_position, uint64_t n_po
     if (!direct_out && down_cnt) {
       PGMO_CUDA(copyPlanes(out_x + down_begin, out_y + down_begin, out_z + down_begin,
                            h->d_ox.ptr + down_begin, h->d_oy.ptr + down_begin, h->d_oz.ptr + down_begin,
-                           down_cnt, cudaMemcpyDeviceToHost, h->s_out));
+                           down_cnt, cudaMemcpyDeviceToHost, h->s_out, h->copy_2d));
     }
     if (processed && down_cnt) {
       PGMO_CUDA(cudaMemcpyAsync(processed + down_begin, h->d_status.ptr + down_begin, down_cnt,

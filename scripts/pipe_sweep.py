@@ -22,14 +22,20 @@ h_in3 = torch.empty((3, n_v), dtype=torch.float32).pin_memory()
 for i, k in enumerate("xyz"):
     h_in3[i].copy_(h_in[k])
 h_out3 = torch.empty((3, n_v), dtype=torch.float32).pin_memory()
+n_pad = (n_v + 1023) // 1024 * 1024
+h_in3a = torch.empty((3, n_pad), dtype=torch.float32).pin_memory()
+for i, k in enumerate("xyz"):
+    h_in3a[i, :n_v].copy_(h_in[k])
+h_out3a = torch.empty((3, n_pad), dtype=torch.float32).pin_memory()
 h_stamps = pin(case["stamps"].view(np.int64))
 h_out = [torch.empty(n_v, dtype=torch.float32).pin_memory() for _ in range(3)]
 h_poses = pin(case["poses"])
-combos = [(8, 0, 0, 0), (8, 0, 0, 1), (6, 0, 0, 1), (12, 0, 0, 1), (16, 0, 0, 1), (24, 0, 0, 1), (12, 2, 0, 1), (16, 3, 0, 1), (16, 0, 0, 0)]
+combos = [(8, 0, 0, 0), (8, 0, 0, 1), (8, 0, 0, 2), (8, 0, 0, 3), (8, 0, 0, 4)]
 for rep in range(2):
     for pipe, taper, direct, planes in combos:
         os.environ["PGMO_PIPE"], os.environ["PGMO_PIPE_TAPER"] = str(pipe), str(taper)
         os.environ["PGMO_HOST_DIRECT"] = str(direct)
+        os.environ["PGMO_COPY_2D"] = "0" if planes in (2, 3) else "1"
         h = capi.DeformHandle(0)
         h.set_controls(case["ctrl_xyz"], case["ctrl_stamps"], case["valid"], case["poses"])
         capi._check(h._lib.pgmo_deform_points(
@@ -38,8 +44,13 @@ for rep in range(2):
             capi._ptr(h_out[2]), None, None, 0, None, None))
         ref = [o.clone() for o in h_out]
 
-        xin = [h_in3[0], h_in3[1], h_in3[2]] if planes else [h_in["x"], h_in["y"], h_in["z"]]
-        xout = [h_out3[0], h_out3[1], h_out3[2]] if planes else h_out
+        if planes in (3, 4):
+            xin = [h_in3a[0, :n_v], h_in3a[1, :n_v], h_in3a[2, :n_v]]
+            xout = [h_out3a[0, :n_v], h_out3a[1, :n_v], h_out3a[2, :n_v]]
+        elif planes:
+            xin, xout = [h_in3[0], h_in3[1], h_in3[2]], [h_out3[0], h_out3[1], h_out3[2]]
+        else:
+            xin, xout = [h_in["x"], h_in["y"], h_in["z"]], h_out
 
         def step():
             h.update_poses(h_poses.numpy())
@@ -53,5 +64,5 @@ for rep in range(2):
         torch.cuda.synchronize()
         ms = 1e3 * (time.perf_counter() - t0) / 10
         ok = all(torch.equal(a, b) for a, b in zip(ref, xout))
-        print(f"pipe {pipe:2d} taper {taper} direct {direct} planes-of-one-allocation {planes}: {ms:.3f} ms per step, outputs equal to the first deformMesh: {ok}", flush=True)
+        print(f"pipe {pipe:2d} taper {taper} direct {direct} planes-of-one-allocation {planes} (1: planes + 2D copies, 2: planes + plain copies, 3: 4 KB-aligned planes + plain copies, 4: aligned planes + 2D copies): {ms:.3f} ms per step, outputs equal to the first deformMesh: {ok}", flush=True)
         h.close()

@@ -5,8 +5,8 @@ After a first deformMesh (pgmo_deform_points: stamps up, schedule built, associa
 written) every further solve is pgmo_deform_update_poses + pgmo_deform_run_host_slab.  Checked
 against the oracle with the new poses (mesh_deformation.cpp:73-106), bit-exact floats, for
   * pageable arrays (three plain copies per chunk),
-  * x / y / z and the outputs as planes of ONE page-locked allocation each (one 3-row DMA
-    operation per chunk),
+  * x / y / z and the outputs as planes of ONE page-locked allocation each (with PGMO_COPY_2D=1:
+    one 3-row DMA operation per chunk),
   * PGMO_PIPE / PGMO_PIPE_TAPER slab layouts,
   * the kernels reading / writing the page-locked buffers themselves (PGMO_HOST_DIRECT = 1, 2),
   * vertices that moved since the records were written (stale items searched again).
@@ -54,7 +54,7 @@ def _as_numpy(a):
 
 @pytest.mark.parametrize("planes", [False, True])
 @pytest.mark.parametrize("env", [{}, {"PGMO_PIPE": "5", "PGMO_PIPE_TAPER": "1"}, {"PGMO_PIPE": "1"},
-                                 {"PGMO_HOST_DIRECT": "1"}, {"PGMO_HOST_DIRECT": "2"}])
+                                 {"PGMO_COPY_2D": "1"}, {"PGMO_HOST_DIRECT": "1"}, {"PGMO_HOST_DIRECT": "2"}])
 def test_pose_only_steps_through_host_pointers(capi, oracle, monkeypatch, planes, env):
     torch = pytest.importorskip("torch")
     for k, v in env.items():
