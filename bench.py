@@ -674,8 +674,10 @@ def run_b200(args):
                         + ("sequence numbers in the source's memory (release / acquire, no collective)"
                            if flag_sync else "a 1-element NCCL all-reduce")),
                 "waits_that_timed_out": pose_timeouts},
-            # buildControlTables, K1, K3b (validating), K3a / K4 / K3b over the stale list, done
-            "gpu_launches": 7 * args.steps,
+            # buildControlTables (N > 1: the pull + table-build kernel), K1, K3b (validating), K3a /
+            # K4 / K3b over the stale list, done; with the sequenced pose source rank 0 also
+            # launches wait-for-acks, publish, wait-for-ready and acknowledge (counted for rank 0)
+            "gpu_launches": (7 + (4 if world > 1 and flag_sync else 0)) * args.steps,
             "resolved_by_tie_kernel": int(n_resolved),
             "cold_step": {"ms_per_step": cold_ms, "value": n_total / (cold_ms * 1e-3), "unit": "vertices/s",
                           "what": "same step with the window schedule + per-run tables rebuilt "

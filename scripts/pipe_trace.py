@@ -17,7 +17,7 @@ h_in = {k: pin(case[k]) for k in "xyz"}
 h_stamps = pin(case["stamps"].view(np.int64))
 h_out = [torch.empty(n_v, dtype=torch.float32).pin_memory() for _ in range(3)]
 h_poses = pin(case["poses"])
-for pipe, taper in [(8, 0), (6, 1), (6, 0)]:
+for pipe, taper in [(8, 0), (12, 2)]:
     os.environ["PGMO_PIPE"], os.environ["PGMO_PIPE_TAPER"] = str(pipe), str(taper)
     h = capi.DeformHandle(0)
     h.set_controls(case["ctrl_xyz"], case["ctrl_stamps"], case["valid"], case["poses"])
