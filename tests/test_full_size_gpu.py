@@ -13,6 +13,9 @@ started mid-way gets wrong for the control points it bulk-inserts at its first v
 2 x tol_t = 20 stretches.  After that every alive point was inserted by the running sweep and
 the state is the full sweep's.
 
+Plus properties that hold for every vertex without an oracle (identity correction, a common
+rigid motion, first call == pose-only call).
+
 configs[1]: 50k-vertex messages, 24 of them, as 1 block and as 64 voxblox-like blocks per
 message, horizon pruning / archiving before each message, through VoxelClearing, Octree and
 Delta compression: every remap, every output list and the stored mesh against the oracle.
@@ -82,6 +85,74 @@ def test_config2_slices_over_the_whole_mesh(oracle, mesh10m, deformed10m):
             np.testing.assert_array_equal(gpu[ax][c:b], ref[ax][c - a:], err_msg=f"stretch {s}")
         checked += b - c
     assert checked > 150_000
+
+
+# ---- size-independent properties of interpPoint (mesh_deformation.cpp:73-106) on all 10 M
+# vertices: no oracle needed, the expected values follow from the formula
+#   out = sum_j w_j (R_j (v - g_j) + t_j) / sum_j w_j
+
+def _deform_with(capi, case, poses):
+    h = capi.DeformHandle(0)
+    h.set_controls(case["ctrl_xyz"], case["ctrl_stamps"], case["valid"], poses)
+    out = h.deform_points(case["x"], case["y"], case["z"], case["stamps"], k=4, tol_t=10.0)
+    assert out["rc"] == 0 and out["processed"].all()
+    h.close()
+    return out
+
+
+def test_config2_identity_correction_returns_the_mesh(capi, mesh10m):
+    """R_j = I, t_j = g_j: every term is (v - g_j) + g_j = v, the weighted mean of equal doubles is
+    within a few 1e-16 relative of v, and v is a float: bit-identical output for every vertex."""
+    case = mesh10m
+    poses = np.zeros((N_C, 12))
+    poses[:, [0, 4, 8]] = 1.0
+    poses[:, 9:] = case["ctrl_xyz"]
+    out = _deform_with(capi, case, poses)
+    for ax in "xyz":
+        # (v - g) + g is exact in double unless |v| is some 2^-29 of |g|: such a coordinate may move
+        # by a rounding of g's magnitude, nothing else may move at all
+        bad = out[ax] != case[ax]
+        assert bad.sum() <= 8, int(bad.sum())
+        assert (np.abs(case[ax][bad]) < 1e-4).all()
+        assert (np.abs(out[ax][bad].astype(np.float64) - case[ax][bad]) < 1e-11).all()
+
+
+def test_config2_common_rigid_motion(capi, mesh10m):
+    """the same rigid motion T = (R, d) on every node: R_j = R, t_j = R g_j + d gives
+    R (v - g_j) + R g_j + d = R v + d for every neighbour, so the blend is R v + d whatever the
+    neighbour sets and weights are — up to the rounding of the terms (1e-5 m at 1 km)."""
+    case = mesh10m
+    th = np.deg2rad(7.0)
+    R = np.array([[np.cos(th), -np.sin(th), 0.0], [np.sin(th), np.cos(th), 0.0], [0.0, 0.0, 1.0]])
+    d = np.array([0.5, -0.25, 0.125])
+    poses = np.empty((N_C, 12))
+    poses[:, :9] = R.reshape(-1)
+    poses[:, 9:] = case["ctrl_xyz"] @ R.T + d
+    out = _deform_with(capi, case, poses)
+    v = np.stack([case["x"], case["y"], case["z"]], axis=1).astype(np.float64)
+    want = v @ R.T + d
+    got = np.stack([out["x"], out["y"], out["z"]], axis=1).astype(np.float64)
+    scale = np.maximum(1.0, np.abs(want).max())
+    assert np.abs(got - want).max() <= 2.0 ** -22 * scale  # a float ulp at that magnitude + slack
+
+
+def test_config2_first_call_equals_pose_only_call(capi, mesh10m):
+    """search + blend (first deformMesh) and blend-from-records (after update_poses) are the same
+    function of (mesh, control table, poses): bit-identical on all vertices"""
+    case = mesh10m
+    poses2 = case["poses"].copy()
+    poses2[:, 9:] += np.random.default_rng(5).normal(0, 0.05, poses2[:, 9:].shape)
+    cold = _deform_with(capi, case, poses2)          # records do not exist yet
+    h = capi.DeformHandle(0)
+    h.set_controls(case["ctrl_xyz"], case["ctrl_stamps"], case["valid"], case["poses"])
+    assert h.deform_points(case["x"], case["y"], case["z"], case["stamps"], k=4, tol_t=10.0)["rc"] == 0
+    h.update_poses(poses2)
+    warm = h.deform_points(case["x"], case["y"], case["z"], case["stamps"], k=4, tol_t=10.0)
+    info = h.last_step_info()
+    assert warm["rc"] == 0 and info["warm"] and info["stale_items"] == 0, info
+    h.close()
+    for ax in "xyz":
+        np.testing.assert_array_equal(warm[ax], cold[ax])
 
 
 def _vcc_state(gpu, ora):
