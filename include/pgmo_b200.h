@@ -221,7 +221,10 @@ int pgmo_deform_stamp_stretches_device(pgmo_deform_t* h, uint64_t n_local,
  * _finish waits for that read-back only — work queued behind it (pgmo_deform_run_device on the
  * cached schedule) keeps running — and sets *changed = 0 iff the slab still has the stretch list
  * last returned by pgmo_deform_stamp_stretches_device.  On *changed = 1 the caller discards the
- * speculative result: stamp_stretches_device -> (exchange) -> build_schedule -> run_device. */
+ * speculative result: stamp_stretches_device -> (exchange) -> build_schedule -> run_device.
+ * The scan runs on a side stream of the handle forked off `stream` at the call (it sees what was
+ * queued on `stream` before, and overlaps with what is queued after): d_stamps_ns must not be
+ * written between _begin and the return of _finish. */
 int pgmo_deform_stamp_check_begin(pgmo_deform_t* h, uint64_t n_local, const uint64_t* d_stamps_ns,
                                   void* stream);
 int pgmo_deform_stamp_check_finish(pgmo_deform_t* h, int* changed);

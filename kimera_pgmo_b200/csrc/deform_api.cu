@@ -163,6 +163,8 @@ struct pgmo_deform {
   bool pipe_trace = false;
   cudaEvent_t ev_t0 = nullptr, ev_out[kMaxPipe] = {};
   cudaEvent_t ev_stamps = nullptr;
+  cudaStream_t s_scan = nullptr;  // side stream of the stamp scan (stampCheckBegin)
+  cudaEvent_t ev_scan = nullptr;
   float r_scale = 1.0f, r_grow_mul = 1.5f, r_grow_add = 1.0f, far_mul = 3.0f;
   uint32_t n_items = 0;
   uint64_t items_first = ~0ull, items_n = 0, items_sched_builds = ~0ull;
@@ -553,12 +555,22 @@ int stampCheckBegin(pgmo_deform_t* h, const uint64_t* d_stamps, uint64_t n_pos, 
   PGMO_TRY(h->d_fp.reserve(2));
   PGMO_TRY(h->h_fp.reserve(2));
   PGMO_TRY(h->d_bounds.reserve(std::max<uint64_t>(h->d_bounds.cap, 1u << 16)));
-  PGMO_CUDA(cudaMemsetAsync(h->d_fp.ptr, 0, 2 * sizeof(unsigned long long), st));
+  // The scan reads 8 B per vertex from HBM and nothing of it feeds the kernels queued behind it
+  // (they run on the cached schedule; the host decides afterwards whether to keep their result):
+  // it goes to a side stream forked off `st`, where it overlaps with the blend kernel, which is
+  // bound by shared memory, not by HBM.  The caller leaves the stamps alone until _finish.
+  cudaStream_t run = st;
+  if (h->s_scan && h->ev_scan) {
+    PGMO_CUDA(cudaEventRecord(h->ev_scan, st));
+    PGMO_CUDA(cudaStreamWaitEvent(h->s_scan, h->ev_scan, 0));
+    run = h->s_scan;
+  }
+  PGMO_CUDA(cudaMemsetAsync(h->d_fp.ptr, 0, 2 * sizeof(unsigned long long), run));
   PGMO_CUDA(launchStampStretches(d_stamps, nullptr, n_pos, h->d_bounds.ptr, h->d_bounds.cap,
-                                 h->d_fp.ptr, st));
+                                 h->d_fp.ptr, run));
   PGMO_CUDA(cudaMemcpyAsync(h->h_fp.ptr, h->d_fp.ptr, 2 * sizeof(unsigned long long),
-                            cudaMemcpyDeviceToHost, st));
-  PGMO_CUDA(cudaEventRecord(h->ev_fp, st));
+                            cudaMemcpyDeviceToHost, run));
+  PGMO_CUDA(cudaEventRecord(h->ev_fp, run));
   h->fp_n_pos = n_pos;
   h->fp_pending = true;
   return PGMO_OK;
@@ -606,6 +618,11 @@ int pgmo_deform_create(int device, pgmo_deform_t** out) {
     cudaGetLastError();
   }
   cudaEventCreateWithFlags(&h->ev_stamps, cudaEventDisableTiming);
+  if (!std::getenv("PGMO_SCAN_INLINE")) {
+    if (cudaStreamCreateWithFlags(&h->s_scan, cudaStreamNonBlocking) != cudaSuccess) h->s_scan = nullptr;
+    if (cudaEventCreateWithFlags(&h->ev_scan, cudaEventDisableTiming) != cudaSuccess) h->ev_scan = nullptr;
+    cudaGetLastError();
+  }
   cudaEventCreateWithFlags(&h->ev_fp, cudaEventDisableTiming);
   if (const char* e = std::getenv("PGMO_PIPE_TRACE")) h->pipe_trace = atoi(e) != 0;
   const unsigned pipe_ev_flags = h->pipe_trace ? cudaEventDefault : cudaEventDisableTiming;
@@ -657,6 +674,8 @@ void pgmo_deform_destroy(pgmo_deform_t* h) {
     if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]);
   }
   if (h->ev_stamps) cudaEventDestroy(h->ev_stamps);
+  if (h->ev_scan) cudaEventDestroy(h->ev_scan);
+  if (h->s_scan) cudaStreamDestroy(h->s_scan);
   if (h->ev_fp) cudaEventDestroy(h->ev_fp);
   if (h->order_ev) {
     cudaEventSynchronize(h->order_ev);  // work a call left on a caller's stream
