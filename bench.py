@@ -638,6 +638,8 @@ def run_b200(args):
                 "bound": "hbm", "kernel": "deformBlendCachedKernel", "achieved": achieved,
                 "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": load_ncu_traffic("blend_traffic.json"), "kernel_ms": blend_ms,
+                "kernel_ms_note": "CUDA events around the kernel inside the step, where the stamp scan (K1) "
+                                  "runs beside it on a side stream; alone it takes 0.42-0.43 ms",
                 "bytes_per_vertex": BYTES_STEP_PER_VERTEX,
                 "bytes_note": "SURVEY 8(d): 12 B xyz read + 8 B stamp read + 12 B xyz written per vertex",
                 "own_bytes": {
