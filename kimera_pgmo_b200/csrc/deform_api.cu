@@ -94,6 +94,7 @@ struct pgmo_deform {
   DevBuf<float4> d_ctrl_f4;
   DevBuf<float> d_pose_f32;
   DevBuf<double> d_pose_rows;  // blend kernel rows: 16 doubles per control, chunk-swizzled
+  uint32_t pose_planes_built = kBlendCopies;  // copy planes of d_pose_rows the last full build wrote
   DevBuf<int4> d_ctrl_key;
   DevBuf<int32_t> d_del_run, d_stable_key;
 
@@ -344,9 +345,17 @@ int finishControls(pgmo_deform_t* h, bool positions_changed, cudaStream_t st) {
   PGMO_TRY(h->d_pose_f32.reserve(16 * h->n_c + 16));
   PGMO_TRY(h->d_ctrl_key.reserve(h->n_c + 1));
   PGMO_TRY(h->d_pose_rows.reserve(16 * h->n_c * kBlendCopies + 16));
+  // copy planes of the blend table: all of them until a schedule says how many the blend kernel
+  // has room for (usually one), then only those
+  uint32_t n_planes = kBlendCopies;
+  if (h->sched_ready && !positions_changed) {
+    n_planes = blendCopiesFor(PGMO_PRECISION_FP64, h->widest_window);
+    if (h->blend_copies_override) n_planes = std::min<uint32_t>(n_planes, h->blend_copies_override);
+  }
+  h->pose_planes_built = n_planes;
   PGMO_CUDA(launchBuildControlTables(h->n_c, h->d_pos.ptr, h->has_poses ? h->d_poses.ptr : nullptr,
                                      h->d_ctrl_f4.ptr, h->d_pose_f32.ptr, h->d_pose_rows.ptr,
-                                     h->d_class.ptr, positions_changed, st));
+                                     h->d_class.ptr, positions_changed, static_cast<int>(n_planes), st));
   if (positions_changed) {
     ++h->control_version;
     h->sched_ready = false;
@@ -1217,6 +1226,7 @@ static int prepareCache(pgmo_deform_t* h, int precision, cudaStream_t st, AssocC
   c->plane_rows = h->n_c;
   c->n_copies = h->blend_copies_override ? std::min<uint32_t>(h->blend_copies_override, blendCopiesFor(precision, h->widest_window))
                                          : blendCopiesFor(precision, h->widest_window);
+  c->n_copies = std::max<uint32_t>(1u, std::min<uint32_t>(c->n_copies, h->pose_planes_built));
   c->ctrl_class = h->d_class.ptr;
   return PGMO_OK;
 }

@@ -178,42 +178,42 @@ __global__ void predeformKernel(uint64_t n_v, uint64_t start_idx, const float* _
   oz[i] = __double2float_rn(__dadd_rn(r2, T[11]));
 }
 
+// Eight threads per control point, one 16-byte chunk of its rows each: the 128-byte rows of the
+// blend table (and the 64-byte rows of the FP32 table) are written as whole, coalesced lines.
+// Only the first n_planes copy planes of the blend table are written (the ones the blend kernel
+// stages: deform_blend.cu blendCopiesFor).
 __global__ void buildControlTablesKernel(uint64_t n_c, const double* __restrict__ ctrl_pos,
                                          const double* __restrict__ poses,
                                          float4* __restrict__ ctrl_f4,
                                          float* __restrict__ pose_f32,
                                          double* __restrict__ pose_rows64,
                                          const uint8_t* __restrict__ ctrl_class,
-                                         int positions_changed) {
-  const uint64_t j = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+                                         int positions_changed, int n_planes) {
+  const uint64_t gid = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const uint64_t j = gid >> 3;
+  const int c = static_cast<int>(gid & 7u);
   if (j >= n_c) return;
-  const double gx = ctrl_pos[3 * j], gy = ctrl_pos[3 * j + 1], gz = ctrl_pos[3 * j + 2];
-  if (positions_changed) {
+  // row = R(9) t(3) g(3) pad; this thread's elements 2c and 2c + 1
+  auto element = [&](int i) -> double {
+    if (i < 12) return poses ? poses[12 * j + i] : 0.0;
+    if (i < 15) return ctrl_pos[3 * j + (i - 12)];
+    return 0.0;
+  };
+  const double e0 = element(2 * c), e1 = element(2 * c + 1);
+  if (positions_changed && c == 0) {
     // .w (the schedule's del_run) is rewritten by applyScheduleKernel after the next build
-    ctrl_f4[j] = make_float4(__double2float_rn(gx), __double2float_rn(gy), __double2float_rn(gz),
-                             __int_as_float(0));
+    ctrl_f4[j] = make_float4(__double2float_rn(ctrl_pos[3 * j]), __double2float_rn(ctrl_pos[3 * j + 1]),
+                             __double2float_rn(ctrl_pos[3 * j + 2]), __int_as_float(0));
   }
-  float* o = pose_f32 + 16 * j;
-  for (int i = 0; i < 12; ++i) o[i] = poses ? __double2float_rn(poses[12 * j + i]) : 0.f;
-  o[12] = __double2float_rn(gx);
-  o[13] = __double2float_rn(gy);
-  o[14] = __double2float_rn(gz);
-  o[15] = 0.f;
+  reinterpret_cast<float2*>(pose_f32 + 16 * j)[c] = make_float2(__double2float_rn(e0), __double2float_rn(e1));
   if (pose_rows64) {
-    // blend-kernel row: R(9) t(3) g(3) pad as eight 16-byte chunks, chunk c stored at
-    // c ^ class so that lanes reading the same chunk of the rows of control points that lie
-    // close together spread over the shared-memory banks
-    double row[16];
-    for (int i = 0; i < 12; ++i) row[i] = poses ? poses[12 * j + i] : 0.0;
-    row[12] = gx;
-    row[13] = gy;
-    row[14] = gz;
-    row[15] = 0.0;
+    // chunk c stored at c ^ class so that lanes reading the same chunk of the rows of control
+    // points that lie close together spread over the shared-memory banks
     const uint32_t class0 = ctrl_class ? (ctrl_class[j] & 7u) : 0u;
-    for (int m = 0; m < kBlendCopies; ++m) {  // one plane of n_c rows per copy
+    for (int m = 0; m < n_planes; ++m) {  // one plane of n_c rows per copy
       double2* dst = reinterpret_cast<double2*>(pose_rows64 + 16 * (static_cast<uint64_t>(m) * n_c + j));
       const int sw = static_cast<int>(dev::blendClass(class0, j, m));
-      for (int c = 0; c < 8; ++c) dst[c ^ sw] = make_double2(row[2 * c], row[2 * c + 1]);
+      dst[c ^ sw] = make_double2(e0, e1);
     }
   }
 }
@@ -363,12 +363,12 @@ cudaError_t launchPredeform(uint64_t n_v, uint64_t start_idx, const float* x, co
 cudaError_t launchBuildControlTables(uint64_t n_c, const double* ctrl_pos, const double* poses,
                                      float4* ctrl_f4, float* ctrl_pose_f32, double* pose_rows64,
                                      const uint8_t* ctrl_class, bool positions_changed,
-                                     cudaStream_t stream) {
+                                     int n_planes, cudaStream_t stream) {
   if (n_c == 0) return cudaSuccess;
   const unsigned threads = 256;
-  buildControlTablesKernel<<<static_cast<unsigned>((n_c + threads - 1) / threads), threads, 0,
+  buildControlTablesKernel<<<static_cast<unsigned>((8 * n_c + threads - 1) / threads), threads, 0,
                              stream>>>(n_c, ctrl_pos, poses, ctrl_f4, ctrl_pose_f32, pose_rows64,
-                                       ctrl_class, positions_changed ? 1 : 0);
+                                       ctrl_class, positions_changed ? 1 : 0, n_planes);
   return cudaGetLastError();
 }
 

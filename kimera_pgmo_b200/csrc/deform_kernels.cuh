@@ -238,7 +238,7 @@ cudaError_t launchPredeform(uint64_t n_v, uint64_t start_idx, const float* x, co
 cudaError_t launchBuildControlTables(uint64_t n_c, const double* ctrl_pos, const double* poses,
                                      float4* ctrl_f4, float* ctrl_pose_f32, double* pose_rows64,
                                      const uint8_t* ctrl_class, bool positions_changed,
-                                     cudaStream_t stream);  // pose_rows64: kBlendCopies x n_c rows
+                                     int n_planes, cudaStream_t stream);  // n_planes <= kBlendCopies  // pose_rows64: kBlendCopies x n_c rows
 // Rows [row_begin, row_end) of the pose table `src` (local or a peer device's memory) -> this
 // device's f64 copy (poses_local, may be null or == src), f32 rows and swizzled f64 rows.
 // sequenced pose source (deform_kernels.cu): flags in the source's memory order writer and readers
