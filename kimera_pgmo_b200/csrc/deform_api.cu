@@ -339,6 +339,14 @@ int uploadSchedule(pgmo_deform_t* h, cudaStream_t st) {
   return PGMO_OK;
 }
 
+// copy planes of the blend table the blend kernel stages under the current schedule
+static uint32_t planesInUse(const pgmo_deform_t* h) {
+  if (!h->sched_ready) return kBlendCopies;
+  uint32_t n = blendCopiesFor(PGMO_PRECISION_FP64, h->widest_window);
+  if (h->blend_copies_override) n = std::min<uint32_t>(n, h->blend_copies_override);
+  return std::max<uint32_t>(1u, std::min<uint32_t>(n, kBlendCopies));
+}
+
 // (Re)builds the derived device tables after d_pos / d_poses changed.
 int finishControls(pgmo_deform_t* h, bool positions_changed, cudaStream_t st) {
   PGMO_TRY(h->d_ctrl_f4.reserve(h->n_c + 1));
@@ -347,11 +355,7 @@ int finishControls(pgmo_deform_t* h, bool positions_changed, cudaStream_t st) {
   PGMO_TRY(h->d_pose_rows.reserve(16 * h->n_c * kBlendCopies + 16));
   // copy planes of the blend table: all of them until a schedule says how many the blend kernel
   // has room for (usually one), then only those
-  uint32_t n_planes = kBlendCopies;
-  if (h->sched_ready && !positions_changed) {
-    n_planes = blendCopiesFor(PGMO_PRECISION_FP64, h->widest_window);
-    if (h->blend_copies_override) n_planes = std::min<uint32_t>(n_planes, h->blend_copies_override);
-  }
+  const uint32_t n_planes = positions_changed ? static_cast<uint32_t>(kBlendCopies) : planesInUse(h);
   h->pose_planes_built = n_planes;
   PGMO_CUDA(launchBuildControlTables(h->n_c, h->d_pos.ptr, h->has_poses ? h->d_poses.ptr : nullptr,
                                      h->d_ctrl_f4.ptr, h->d_pose_f32.ptr, h->d_pose_rows.ptr,
@@ -913,10 +917,15 @@ int pgmo_deform_update_poses_from_source(pgmo_deform_t* h, int buffer, uint64_t 
   PGMO_TRY(h->d_poses.reserve(12 * h->n_c + 12));
   PGMO_TRY(h->d_pose_f32.reserve(16 * h->n_c + 16));
   PGMO_TRY(h->d_pose_rows.reserve(16 * h->n_c * kBlendCopies + 16));
+  // rows outside [row_begin, row_end) keep the planes of the last full build: the blend kernel
+  // may use what both have
+  const uint32_t pull_planes = planesInUse(h);
+  h->pose_planes_built = std::min(h->pose_planes_built, pull_planes);
   PGMO_CUDA(launchPullBuildPoseTables(row_begin, row_end, h->n_c,
                                       h->pose_src + static_cast<uint64_t>(buffer) * 12 * h->pose_src_n,
                                       h->d_poses.ptr, h->d_pos.ptr, h->d_pose_f32.ptr,
-                                      h->d_pose_rows.ptr, h->d_class.ptr, st));
+                                      h->d_pose_rows.ptr, h->d_class.ptr,
+                                      static_cast<int>(pull_planes), st));
   return PGMO_OK;
 }
 

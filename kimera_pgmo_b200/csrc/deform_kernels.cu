@@ -230,7 +230,7 @@ pullBuildPoseTablesKernel(uint64_t row_begin, uint64_t row_end, uint64_t n_c,
                           const double* __restrict__ src,
                           double* __restrict__ poses_local, const double* __restrict__ ctrl_pos,
                           float* __restrict__ pose_f32, double* __restrict__ pose_rows64,
-                          const uint8_t* __restrict__ ctrl_class) {
+                          const uint8_t* __restrict__ ctrl_class, int n_planes) {
   __shared__ double2 stage[kPullRows * 6];
   const uint64_t r0 = row_begin + static_cast<uint64_t>(blockIdx.x) * kPullRows;
   const uint64_t n_rows = row_end - r0 < static_cast<uint64_t>(kPullRows) ? row_end - r0 : kPullRows;
@@ -242,23 +242,25 @@ pullBuildPoseTablesKernel(uint64_t row_begin, uint64_t row_end, uint64_t n_c,
     if (l2 && l2 != s2) l2[e] = v;
   }
   __syncthreads();
-  if (threadIdx.x >= n_rows) return;
-  const uint64_t j = r0 + threadIdx.x;
-  double row[16];
-  const double* mine = reinterpret_cast<const double*>(stage) + 12 * threadIdx.x;
-  for (int i = 0; i < 12; ++i) row[i] = mine[i];
-  row[12] = ctrl_pos[3 * j];
-  row[13] = ctrl_pos[3 * j + 1];
-  row[14] = ctrl_pos[3 * j + 2];
-  row[15] = 0.0;
-  float* o = pose_f32 + 16 * j;
-  for (int i = 0; i < 15; ++i) o[i] = __double2float_rn(row[i]);
-  o[15] = 0.f;
-  const uint32_t class0 = ctrl_class ? (ctrl_class[j] & 7u) : 0u;
-  for (int m = 0; m < kBlendCopies; ++m) {
-    double2* dst = reinterpret_cast<double2*>(pose_rows64 + 16 * (static_cast<uint64_t>(m) * n_c + j));
-    const int sw = static_cast<int>(dev::blendClass(class0, j, m));
-    for (int c = 0; c < 8; ++c) dst[c ^ sw] = make_double2(row[2 * c], row[2 * c + 1]);
+  // one 16-byte chunk per thread and step: rows leave as whole, coalesced lines
+  const double* staged = reinterpret_cast<const double*>(stage);
+  for (uint32_t e = threadIdx.x; e < n_rows * 8; e += kPullRows) {
+    const uint32_t local = e >> 3;
+    const int c = static_cast<int>(e & 7u);
+    const uint64_t j = r0 + local;
+    auto element = [&](int i) -> double {
+      if (i < 12) return staged[12 * local + i];
+      if (i < 15) return ctrl_pos[3 * j + (i - 12)];
+      return 0.0;
+    };
+    const double e0 = element(2 * c), e1 = element(2 * c + 1);
+    reinterpret_cast<float2*>(pose_f32 + 16 * j)[c] = make_float2(__double2float_rn(e0), __double2float_rn(e1));
+    const uint32_t class0 = ctrl_class ? (ctrl_class[j] & 7u) : 0u;
+    for (int m = 0; m < n_planes; ++m) {
+      double2* dst = reinterpret_cast<double2*>(pose_rows64 + 16 * (static_cast<uint64_t>(m) * n_c + j));
+      const int sw = static_cast<int>(dev::blendClass(class0, j, m));
+      dst[c ^ sw] = make_double2(e0, e1);
+    }
   }
 }
 
@@ -440,11 +442,12 @@ cudaError_t launchPoseSourceWaitReady(const unsigned long long* ready, unsigned 
 cudaError_t launchPullBuildPoseTables(uint64_t row_begin, uint64_t row_end, uint64_t n_c,
                                       const double* src, double* poses_local, const double* ctrl_pos,
                                       float* ctrl_pose_f32, double* pose_rows64,
-                                      const uint8_t* ctrl_class, cudaStream_t stream) {
+                                      const uint8_t* ctrl_class, int n_planes, cudaStream_t stream) {
   if (row_end <= row_begin) return cudaSuccess;
   const uint64_t blocks = (row_end - row_begin + kPullRows - 1) / kPullRows;
   pullBuildPoseTablesKernel<<<static_cast<unsigned>(blocks), kPullRows, 0, stream>>>(
-      row_begin, row_end, n_c, src, poses_local, ctrl_pos, ctrl_pose_f32, pose_rows64, ctrl_class);
+      row_begin, row_end, n_c, src, poses_local, ctrl_pos, ctrl_pose_f32, pose_rows64, ctrl_class,
+      n_planes);
   return cudaGetLastError();
 }
 

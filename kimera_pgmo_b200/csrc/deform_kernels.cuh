@@ -253,7 +253,7 @@ cudaError_t launchPoseSourceWaitReady(const unsigned long long* ready, unsigned 
 cudaError_t launchPullBuildPoseTables(uint64_t row_begin, uint64_t row_end, uint64_t n_c,
                                       const double* src, double* poses_local, const double* ctrl_pos,
                                       float* ctrl_pose_f32, double* pose_rows64,
-                                      const uint8_t* ctrl_class, cudaStream_t stream);
+                                      const uint8_t* ctrl_class, int n_planes, cudaStream_t stream);
 // writes del_run into ctrl_f4[].w and the stable keys (after build_schedule)
 cudaError_t launchApplySchedule(uint64_t n_c, const int32_t* del_run, const int32_t* stable_key3,
                                 float4* ctrl_f4, int4* ctrl_key, cudaStream_t stream);
