@@ -516,8 +516,11 @@ def run_b200(args):
         barrier()
         e2e_steps = max(3, min(args.steps, 10))
         t0 = time.perf_counter()
+        e2e_each = []
         for _ in range(e2e_steps):
-            e2e_step()
+            t1 = time.perf_counter()
+            e2e_step()  # returns when the results are in the host buffers
+            e2e_each.append(1e3 * (time.perf_counter() - t1))
         barrier()
         e2e_ms = 1e3 * (time.perf_counter() - t0) / e2e_steps
         t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
@@ -556,6 +559,7 @@ def run_b200(args):
         copy_ms = float(t.item())
         del d_floor_in, d_floor_out, h_out_scratch
         e2e = {"value": n_total / (e2e_ms * 1e-3), "unit": "vertices/s", "ms_per_step": e2e_ms,
+               "ms_each_step_this_rank": [round(v, 3) for v in e2e_each],
                "copies_only_ms": copy_ms,
                "copies_only_note": "12 B/vertex up and 12 B/vertex down per rank as two plain page-locked copies "
                                    "at once on every rank, nothing else: what the host's PCIe paths give N ranks",
@@ -677,9 +681,9 @@ def run_b200(args):
                            if flag_sync else "a 1-element NCCL all-reduce")),
                 "waits_that_timed_out": pose_timeouts},
             # buildControlTables (N > 1: the pull + table-build kernel), K1, K3b (validating), K3a /
-            # K4 / K3b over the stale list, done; with the sequenced pose source rank 0 also
-            # launches wait-for-acks, publish, wait-for-ready and acknowledge (counted for rank 0)
-            "gpu_launches": (7 + (4 if world > 1 and flag_sync else 0)) * args.steps,
+            # K4 / K3b over the stale list; with the sequenced pose source rank 0 also launches
+            # wait-for-acks, publish, wait-for-ready and acknowledge (counted for rank 0)
+            "gpu_launches": (6 + (4 if world > 1 and flag_sync else 0)) * args.steps,
             "resolved_by_tie_kernel": int(n_resolved),
             "cold_step": {"ms_per_step": cold_ms, "value": n_total / (cold_ms * 1e-3), "unit": "vertices/s",
                           "what": "same step with the window schedule + per-run tables rebuilt "

@@ -1387,7 +1387,9 @@ static int runDeviceRange(pgmo_deform_t* h, uint64_t first_position, uint64_t n_
     PGMO_CUDA(launchDeformResolve(a, ra, nullptr, precision, st));
     if (h->profiling) PGMO_CUDA(cudaEventRecord(h->ev[3], st));
   }
-  PGMO_CUDA(launchDeformStepDone(h->d_counters.ptr, st));
+  // marks the resolver / stale lists consumed for the next range of the same call; after the last
+  // range nothing reads them again (a call's first range zeroes the counters)
+  if (range_end != n_local) PGMO_CUDA(launchDeformStepDone(h->d_counters.ptr, st));
   if (h->profiling) {
     PGMO_CUDA(cudaEventRecord(h->ev[4], st));
     h->ev_recorded = true;
