@@ -299,6 +299,20 @@ __device__ __forceinline__ void blendItem(const DeformArgs& a, const GridArgs& g
                n_rows * kRowBytes, &S.bar);
     }
   }
+  // Validating mode: an item without records is known at once (one flag); whether its vertices
+  // are still the ones the records were computed for is known only after all of them have been
+  // read — that comparison waits until the blend is done (the barrier before the results go out
+  // is there anyway), so that a valid item, the usual case, pays no barrier for being checked.
+  // A stale item's blend read valid records of other coordinates: its output is garbage that
+  // the stale-list pass overwrites.
+  if (MODE == 1 && t == 0) {
+    const bool missing = cache.item_ok[item_index] == 0u;
+    S.stale = missing ? 1u : 0u;
+    if (missing) {
+      const unsigned long long at = atomicAdd(a.counters + 2, 1ull);
+      cache.stale_items[at] = item_index;
+    }
+  }
   // ---- vertices in (coalesced), fingerprint
   unsigned long long fp = 0ull;
   for (int i = t; i < count; i += kBThreads) {
@@ -314,26 +328,12 @@ __device__ __forceinline__ void blendItem(const DeformArgs& a, const GridArgs& g
     if (lane == 0) S.fp_w[warp] = fp;
   }
   __syncthreads();
-  if (MODE == 1) {
-    if (t == 0) {
-      unsigned long long f = 0ull;
-#pragma unroll
-      for (int w = 0; w < kBWarps; ++w) f += S.fp_w[w];
-      const bool ok = cache.item_ok[item_index] != 0u && cache.item_fp[item_index] == f;
-      S.stale = ok ? 0u : 1u;
-      if (!ok) {
-        const unsigned long long at = atomicAdd(a.counters + 2, 1ull);
-        cache.stale_items[at] = item_index;
-      }
+  if (MODE == 1 && S.stale) {  // no records: nothing to blend from
+    if (!tiny) {  // the copy must have landed before the CTA may leave or reuse the rows
+      mbarWait(&S.bar, bar_phase);
+      bar_phase ^= 1u;
     }
-    __syncthreads();
-    if (S.stale) {
-      if (!tiny) {  // the copy must have landed before the CTA may leave or reuse the rows
-        mbarWait(&S.bar, bar_phase);
-        bar_phase ^= 1u;
-      }
-      return;
-    }
+    return;
   }
   if (!tiny) {
     mbarWait(&S.bar, bar_phase);
@@ -344,6 +344,15 @@ __device__ __forceinline__ void blendItem(const DeformArgs& a, const GridArgs& g
   else if (nb == 5) blendVertices<PREC, 5, false>(a, cache, S, rows, p_base, count, nb, lo, n_rows);
   else blendVertices<PREC, 0, false>(a, cache, S, rows, p_base, count, nb, lo, n_rows);
   __syncthreads();
+  if (MODE == 1 && t == 0) {
+    unsigned long long f = 0ull;
+#pragma unroll
+    for (int w = 0; w < kBWarps; ++w) f += S.fp_w[w];
+    if (cache.item_fp[item_index] != f) {
+      const unsigned long long at = atomicAdd(a.counters + 2, 1ull);
+      cache.stale_items[at] = item_index;
+    }
+  }
   // ---- results out (coalesced)
   for (int i = t; i < count; i += kBThreads) {
     const uint64_t ii = a.subset ? a.subset[p_base + i] : p_base + i;
