@@ -297,6 +297,9 @@ def run_b200(args):
     stream = torch.cuda.current_stream().cuda_stream
     h.set_controls_device(n_ctrl, d_cpos, d_cst, d_cvalid, d_poses, stream)
     h.set_profiling(True)
+    # N > 1: the ranks all-reduce the "stamps changed" flag on the host after stamp_check_finish;
+    # that must not wait for a scan that shares the GPU with the blend kernel (include/pgmo_b200.h)
+    h.set_scan_overlap(world == 1)
     exchange_stretches = sharding.StretchExchange(world, dev)
     # N > 1: a solve result is written once into rank 0's pose source; after one 1-element
     # all_reduce (ordering only) every rank's table-build kernel pulls the control-point rows its
@@ -748,6 +751,7 @@ def bench_config3(args, world, rank, local_rank, dev, stream, flag_group, peak):
         owns = any(seg[0] == r for seg in mine)
         if owns or rank == 0:
             hd = capi.DeformHandle(local_rank)
+            hd.set_scan_overlap(world == 1)  # see run_b200
             hd.set_controls_device(n_c, t[0], t[1], t[2], t[3], stream)
             handles[r] = hd
         poses[r] = t[3]

@@ -228,6 +228,15 @@ int pgmo_deform_stamp_stretches_device(pgmo_deform_t* h, uint64_t n_local,
 int pgmo_deform_stamp_check_begin(pgmo_deform_t* h, uint64_t n_local, const uint64_t* d_stamps_ns,
                                   void* stream);
 int pgmo_deform_stamp_check_finish(pgmo_deform_t* h, int* changed);
+/* enabled = 0: the scan is queued on `stream` itself, ahead of what follows (its result is then
+ * on the host a few tens of microseconds after _begin, whatever runs behind it).  What a caller
+ * wants whose host has work to do between _finish and the next step — e.g. the all-reduce of the
+ * flag between the ranks of a sharded job: with the overlapped scan (default, a side stream)
+ * _finish can return late in the step, and that work then delays the next step's launches
+ * (8 ranks: 0.75 ms per step against 0.54 ms).  PGMO_SCAN_PRIORITY=1 (environment, read at
+ * pgmo_deform_create) gives the side stream the highest priority instead: the result arrives
+ * early again and the step keeps most of the overlap (0.480 ms against 0.470 / 0.496 ms). */
+int pgmo_deform_set_scan_overlap(pgmo_deform_t* h, int enabled);
 
 /* Replays the reference's add/remove window state machine (mesh_deformation.h:159-212) over the
  * stamp stretches and uploads the resulting schedule.  stretch_stamp == NULL selects the

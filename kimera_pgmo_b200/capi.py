@@ -57,6 +57,7 @@ SIGNATURES = {
     "pgmo_deform_pose_source_attach": (C.c_int, [_vp, C.c_uint64, _vp, _vp, C.c_int]),
     "pgmo_deform_pose_source_write": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "pgmo_deform_update_poses_from_source": (C.c_int, [_vp, C.c_int, C.c_uint64, C.c_uint64, _vp]),
+    "pgmo_deform_set_scan_overlap": (C.c_int, [_vp, C.c_int]),
     "pgmo_deform_pose_source_publish": (C.c_int, [_vp, C.c_uint64, C.c_uint32, _vp, _vp]),
     "pgmo_deform_update_poses_from_source_seq": (C.c_int, [_vp, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, _vp]),
     "pgmo_deform_pose_source_timeouts": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
@@ -279,6 +280,9 @@ class DeformHandle:
         return _check(self._lib.pgmo_deform_run_host_slab(
             self._h, first_position, n_local, _ptr(x), _ptr(y), _ptr(z), precision, _ptr(ox), _ptr(oy),
             _ptr(oz), _ptr(processed)))
+
+    def set_scan_overlap(self, enabled=True):
+        _check(self._lib.pgmo_deform_set_scan_overlap(self._h, 1 if enabled else 0))
 
     def set_assoc_cache(self, enabled=True):
         _check(self._lib.pgmo_deform_set_assoc_cache(self._h, 1 if enabled else 0))
