@@ -12,24 +12,59 @@
 #include <set>
 #include <vector>
 
+#include <numeric>
+#include <optional>
+#include <stdexcept>
+#include <string>
+
 #include "kimera_pgmo_b200/compression.h"
 
 namespace kimera_pgmo_b200 {
 
-struct Face {  // mesh_delta.h:24-37
+struct Face {  // mesh_delta.h:24-37, mesh_delta.cpp:66-77
   Face() = default;
   Face(size_t a, size_t b, size_t c)
       : v1(static_cast<uint32_t>(a)), v2(static_cast<uint32_t>(b)), v3(static_cast<uint32_t>(c)) {}
+  Face(const std::vector<size_t>& indices, size_t i)
+      : Face(indices.at(i), indices.at(i + 1), indices.at(i + 2)) {}
   bool valid() const { return v1 != v2 && v1 != v3 && v2 != v3; }
+  void fill(std::vector<uint32_t>& other) const { other = {v1, v2, v3}; }
   uint32_t v1 = 0, v2 = 0, v3 = 0;
 };
 
 class MeshDelta {  // mesh_delta.h:65-150: what DeltaCompression::update produces
  public:
   using Ptr = std::shared_ptr<MeshDelta>;
+  MeshDelta() : MeshDelta(0, 0) {}  // mesh_delta.cpp:79
   MeshDelta(size_t vertex_start_, size_t face_start_)
       : vertex_start(vertex_start_), face_start(face_start_),
         vertex_updates(new pcl::PointCloud<pcl::PointXYZRGBA>()) {}
+  // a whole mesh as one delta (mesh_delta.cpp:86-106)
+  MeshDelta(const pcl::PointCloud<pcl::PointXYZRGBA>& vertices, const std::vector<Timestamp>& stamps,
+            const std::vector<pcl::Vertices>& faces,
+            std::optional<std::vector<uint32_t>> semantics = std::nullopt)
+      : vertex_updates(new pcl::PointCloud<pcl::PointXYZRGBA>(vertices)), stamp_updates(stamps) {
+    if (semantics) semantic_updates = *semantics;
+    face_updates.reserve(faces.size());
+    for (const auto& face : faces) {
+      face_updates.emplace_back(face.vertices[0], face.vertices[1], face.vertices[2]);
+    }
+  }
+
+  // mesh_delta.cpp:144-168: what DeltaCompression::update calls per vertex / face in the
+  // reference (here the device fills the vectors); kept for callers that build deltas by hand
+  size_t addVertex(Timestamp timestamp_ns, const pcl::PointXYZRGBA& point,
+                   std::optional<uint32_t> semantics = std::nullopt, bool archive = false) {
+    const size_t index = vertex_start + vertex_updates->size();
+    vertex_updates->push_back(point);
+    stamp_updates.push_back(timestamp_ns);
+    if (semantics) semantic_updates.push_back(*semantics);
+    if (archive) ++num_archived_vertices_;
+    return index;
+  }
+  void addFace(const Face& face, bool archive = false) {
+    (archive ? face_archive_updates : face_updates).push_back(face);
+  }
 
   size_t getNumArchivedVertices() const { return num_archived_vertices_; }
   size_t getNumArchivedFaces() const { return face_archive_updates.size(); }
@@ -42,16 +77,23 @@ class MeshDelta {  // mesh_delta.h:65-150: what DeltaCompression::update produce
   // mesh_delta.cpp:112-114
   bool hasSemantics() const { return semantic_updates.size() == vertex_updates->size(); }
 
-  // updateVertices / updateFaces (mesh_delta.h:171-215) for the PCL containers
-  void updateMesh(pcl::PointCloud<pcl::PointXYZRGBA>& vertices, std::vector<Timestamp>& stamps,
-                  std::vector<pcl::Vertices>& faces) const {
+  // updateVertices / updateFaces (mesh_delta.h:171-215, mesh_delta.cpp:116-142) for the PCL
+  // containers; stamps / semantics optional as in the reference (semantics are written only
+  // when the delta has a label for every vertex)
+  void updateVertices(pcl::PointCloud<pcl::PointXYZRGBA>& vertices, std::vector<Timestamp>* stamps,
+                      std::vector<uint32_t>* semantics = nullptr) const {
+    const bool semantics_valid = semantics && hasSemantics();
     const size_t total_vertices = vertex_start + vertex_updates->size();
     vertices.resize(total_vertices);
-    stamps.resize(total_vertices);
+    if (stamps) stamps->resize(total_vertices);
+    if (semantics_valid) semantics->resize(total_vertices);
     for (size_t i = 0; i < vertex_updates->size(); ++i) {
       vertices.at(i + vertex_start) = vertex_updates->at(i);
-      stamps.at(i + vertex_start) = stamp_updates.at(i);
+      if (stamps) stamps->at(i + vertex_start) = stamp_updates.at(i);
+      if (semantics_valid) semantics->at(i + vertex_start) = semantic_updates.at(i);
     }
+  }
+  void updateFaces(std::vector<pcl::Vertices>& faces) const {
     faces.resize(getTotalFaces());
     size_t face_idx = face_start;
     for (const auto* list : {&face_archive_updates, &face_updates}) {
@@ -60,6 +102,48 @@ class MeshDelta {  // mesh_delta.h:65-150: what DeltaCompression::update produce
         ++face_idx;
       }
     }
+  }
+  void updateMesh(pcl::PointCloud<pcl::PointXYZRGBA>& vertices, std::vector<Timestamp>& stamps,
+                  std::vector<pcl::Vertices>& faces, std::vector<uint32_t>* semantics = nullptr) const {
+    updateVertices(vertices, &stamps, semantics);
+    updateFaces(faces);
+  }
+  // mesh_delta.cpp:194-200: the vertices of this delta that were not archived
+  std::shared_ptr<std::vector<int>> getActiveIndices() const {
+    auto indices = std::make_shared<std::vector<int>>(vertex_updates->size() - num_archived_vertices_);
+    std::iota(indices->begin(), indices->end(), static_cast<int>(vertex_start + num_archived_vertices_));
+    return indices;
+  }
+  // mesh_delta.cpp:202-262
+  void checkFaces(const std::string& name) const {
+    const size_t total_archived = getTotalArchivedVertices();
+    for (const auto& face : face_archive_updates) {
+      if (!(face.v1 < total_archived && face.v2 < total_archived && face.v3 < total_archived)) {
+        throw std::runtime_error(name + " invalid archived face: (" + std::to_string(face.v1) + ", " +
+                                 std::to_string(face.v2) + ", " + std::to_string(face.v3) +
+                                 ") (total archived: " + std::to_string(total_archived) + ")");
+      }
+    }
+    const size_t total_vertices = vertex_start + vertex_updates->size();
+    for (const auto& face : face_updates) {
+      if (!(face.v1 < total_vertices && face.v2 < total_vertices && face.v3 < total_vertices)) {
+        throw std::runtime_error(name + " invalid face: (" + std::to_string(face.v1) + ", " +
+                                 std::to_string(face.v2) + ", " + std::to_string(face.v3) +
+                                 ") (total vertices: " + std::to_string(total_vertices) + ")");
+      }
+    }
+  }
+  void validate(pcl::PointCloud<pcl::PointXYZRGBA>& vertices, std::vector<Timestamp>& stamps,
+                std::vector<pcl::Vertices>& faces, std::vector<uint32_t>* semantics = nullptr) const {
+    auto fail = [](const char* what, size_t have, const char* start_name, size_t start) {
+      throw std::runtime_error(std::string("invalid update: ") + what + " size (" + std::to_string(have) +
+                               ") < " + start_name + " (" + std::to_string(start) + ")");
+    };
+    if (vertices.size() < vertex_start) fail("vertices", vertices.size(), "vertex start", vertex_start);
+    if (stamps.size() < vertex_start) fail("stamps", stamps.size(), "vertex start", vertex_start);
+    if (semantics && semantics->size() < vertex_start) fail("semantics", semantics->size(), "vertex start", vertex_start);
+    if (faces.size() < face_start) fail("faces", faces.size(), "faces start", face_start);
+    checkFaces("[validate]");
   }
 
   size_t vertex_start = 0;

@@ -325,18 +325,47 @@ void katSimpleMeshFlow(double res) {
   KAT_EQ(s.triangles.at(3)[2], 6u);
   KAT_EQ(c.getVertices().size(), 9u);
   KAT_EQ(c.getStoredPolygons().size(), 8u);
-  c.pruneStoredMesh(100.5);
+  c.pruneStoredMesh(100.5);  // test_block_compression.cpp:190-212
   KAT_EQ(c.getActiveVertices().size(), 5u);
   KAT_EQ(c.getStoredPolygons().size(), 8u);
+  KAT_EQ(c.getActiveVerticesTimestamps().size(), 5u);
   KAT_EQ(c.getVertices().size(), 9u);
   KAT_EQ(c.getActiveVertices()[1].x, 2.f);
+  KAT_EQ(c.getActiveVertices()[2].y, 2.f);
+  KAT_EQ(c.getActiveVertices()[4].z, 2.f);
+  KAT_EQ(c.getStoredPolygons().at(0)[0], 0u);
+  KAT_EQ(c.getStoredPolygons().at(3)[2], 2u);
+  KAT_EQ(c.getActiveVerticesTimestamps().at(4), 101.0);
   KAT_EQ(c.getActiveVerticesTimestamps().at(0), 101.0);
+  KAT_EQ(c.getVertices()[5].x, 2.f);
+  KAT_EQ(c.getVertices()[7].y, 2.f);
+  KAT_EQ(c.getVertices()[8].z, 2.f);
+  KAT_EQ(c.getStoredPolygons().at(4)[0], 0u);
+  KAT_EQ(c.getStoredPolygons().at(7)[2], 6u);
   s = Scratch();
   c.compressAndIntegrate(simpleMeshInterface(1.0), s.vertices, s.triangles, s.indices,
                          s.remappings, 102.0);
+  c.pruneStoredMesh(100.9);  // :214-258
+  KAT_EQ(c.getActiveVertices().size(), 9u);
+  KAT_EQ(c.getStoredPolygons().size(), 12u);
+  KAT_EQ(c.getActiveVerticesTimestamps().size(), 9u);
+  KAT_EQ(c.getVertices().size(), 13u);
+  KAT_EQ(c.getActiveVertices()[5].x, 1.f);
+  KAT_EQ(c.getActiveVertices()[7].y, 1.f);
+  KAT_EQ(c.getActiveVertices()[8].z, 1.f);
+  KAT_EQ(c.getStoredPolygons().at(4)[0], 0u);
+  KAT_EQ(c.getStoredPolygons().at(7)[2], 6u);
+  KAT_EQ(c.getStoredPolygons().at(8)[0], 0u);
+  KAT_EQ(c.getStoredPolygons().at(11)[2], 10u);
+  KAT_EQ(c.getActiveVerticesTimestamps().at(8), 102.0);
   KAT_EQ(s.vertices.size(), 4u);
   KAT_EQ(s.triangles.size(), 4u);
+  KAT_EQ(s.indices.size(), 5u);
   KAT_TRUE(s.indices == (V{0, 9, 10, 11, 12}));
+  KAT_EQ(s.vertices[0].x, 1.f);
+  KAT_EQ(s.vertices[2].y, 1.f);
+  KAT_EQ(s.vertices[3].z, 1.f);
+  KAT_EQ(s.triangles.at(0)[0], 0u);
   KAT_EQ(s.triangles.at(1)[1], 11u);
   KAT_EQ(s.triangles.at(3)[2], 10u);
 }
@@ -352,11 +381,25 @@ void katBlockCompression() {
   KAT_EQ(s.triangles.size(), 0u);
   KAT_EQ(s.indices.size(), 0u);
   KAT_EQ(c.getVertices().size(), 0u);
+  KAT_EQ(c.getActiveVertices().size(), 0u);          // :301-330 storedValuesCompressed
+  KAT_EQ(c.getStoredPolygons().size(), 0u);
+  KAT_EQ(c.getActiveVerticesTimestamps().size(), 0u);
   s = Scratch();
   c.compressAndIntegrate(simpleMeshInterface(2.0), s.vertices, s.triangles, s.indices,
                          s.remappings, 101.0);
   KAT_EQ(s.vertices.size(), 0u);
+  KAT_EQ(s.triangles.size(), 0u);
+  KAT_EQ(s.indices.size(), 0u);
+  KAT_EQ(c.getVertices().size(), 0u);                // :340-350
+  KAT_EQ(c.getActiveVertices().size(), 0u);
+  KAT_EQ(c.getActiveVerticesTimestamps().size(), 0u);
   KAT_EQ(c.getStoredPolygons().size(), 0u);
+  // :18-38 constructor
+  BlockCompression fresh(1.0);
+  KAT_EQ(fresh.getVertices().size(), 0u);
+  KAT_EQ(fresh.getActiveVertices().size(), 0u);
+  KAT_EQ(fresh.getStoredPolygons().size(), 0u);
+  KAT_EQ(fresh.getActiveVerticesTimestamps().size(), 0u);
 }
 
 void katOctreeFullCollapse() {

@@ -227,5 +227,31 @@ int runDeltaKats() {
     KAT_TRUE(info.shouldArchive());
   }
   for (const auto& config : configurations()) runConfig(config);
+  {
+    // kimera_pgmo/test/test_mesh_delta.cpp:39-43, :80-103 (constructor, archiveVerticesCorrect,
+    // archiveFacesCorrect; updateSimple is replayed through the shim's MeshDelta, tests/cpp/test_shim.cpp)
+    MeshDelta fresh(0, 0);
+    KAT_EQ(fresh.vertex_start, 0u);
+    KAT_EQ(fresh.face_start, 0u);
+    MeshDelta delta(1, 3);
+    PointXYZRGBA p;
+    p.x = 1.0f;
+    p.y = 2.0f;
+    p.z = 3.0f;
+    KAT_EQ(delta.addVertex(100, p, MeshInterface::kNoLabel, true), 1u);
+    KAT_EQ(delta.addVertex(100, p, MeshInterface::kNoLabel, true), 2u);
+    KAT_EQ(delta.addVertex(100, p, MeshInterface::kNoLabel, false), 3u);
+    KAT_EQ(delta.addVertex(100, p, MeshInterface::kNoLabel, false), 4u);
+    KAT_EQ(delta.getTotalArchivedVertices(), 3u);
+    KAT_EQ(delta.num_archived_vertices, 2u);
+    KAT_TRUE(!delta.hasSemantics());
+    MeshDelta faces(1, 3);
+    faces.addFace({0, 1, 2}, true);
+    faces.addFace({1, 2, 3}, true);
+    faces.addFace({0, 1, 2}, false);
+    faces.addFace({1, 2, 3}, false);
+    KAT_EQ(faces.getTotalArchivedFaces(), 5u);
+    KAT_EQ(faces.face_archive_updates.size(), 2u);
+  }
   return kat::failures();
 }

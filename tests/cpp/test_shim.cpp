@@ -1070,6 +1070,100 @@ static void testDeltaCompression() {
 // mesh_frontend_interface.cpp:100-115, :197-211.  The expected mesh_to_graph_idx_ is the
 // reference's own loop run on the host maps after every update, entries of a block taken in
 // ascending msg index (the order the device uses where the reference's is implementation-defined).
+// kimera_pgmo/test/test_traits.cpp:11-21 (stampTraitsCorrect): which clouds carry stamps is decided
+// at compile time by the same has_get_stamp dispatch (the start-index search of
+// test_traits.cpp:23-41 is findStartIndex's upper bound, exercised by testIncrementalWithPredeform)
+static_assert(!traits::has_get_stamp<pcl::PointCloud<pcl::PointXYZ>>::value, "pcl::PointXYZ get failed");
+static_assert(!traits::has_get_stamp<pcl::PointCloud<pcl::PointXYZRGBA>>::value, "pcl::PointXYZRGBA get failed");
+static_assert(traits::has_get_stamp<ConstStampedCloud<pcl::PointXYZ>>::value, "const stamped pcl::PointXYZ failed");
+static_assert(traits::has_get_stamp<ConstStampedCloud<pcl::PointXYZRGBA>>::value,
+              "const stamped pcl::PointXYZRGBA failed");
+
+// kimera_pgmo/test/test_mesh_delta.cpp:39-103, transcribed (host only: MeshDelta is what callers of
+// DeltaCompression consume)
+static void testMeshDelta() {
+  auto point = [](float x, float y, float z, int r, int g, int b) {
+    pcl::PointXYZRGBA p;
+    p.x = x;
+    p.y = y;
+    p.z = z;
+    p.r = static_cast<std::uint8_t>(r);
+    p.g = static_cast<std::uint8_t>(g);
+    p.b = static_cast<std::uint8_t>(b);
+    p.a = 255;
+    return p;
+  };
+  {  // constructor
+    MeshDelta mesh;
+    EXPECT_EQ(mesh.vertex_start, 0u);
+    EXPECT_EQ(mesh.face_start, 0u);
+  }
+  {  // updateSimple
+    MeshDelta delta1;
+    for (int r = 0; r < 4; ++r) delta1.addVertex(100, point(1.0f, 2.0f, 3.0f, r, 0, 0));
+    delta1.addFace({0, 1, 2});
+    delta1.addFace({1, 2, 3});
+    pcl::PointCloud<pcl::PointXYZRGBA> vertices;
+    std::vector<pcl::Vertices> faces;
+    std::vector<Timestamp> stamps;
+    delta1.updateMesh(vertices, stamps, faces);
+    EXPECT_EQ(stamps.size(), vertices.size());
+    EXPECT_EQ(vertices.size(), 4u);
+    for (size_t i = 0; i < vertices.size(); ++i) EXPECT_EQ(static_cast<size_t>(vertices.at(i).r), i);
+    EXPECT_EQ(faces.size(), 2u);
+    MeshDelta delta2(2, 1);
+    for (int r = 2; r < 6; ++r) delta2.addVertex(100, point(1.0f, 2.0f, 3.0f, r, 0, 0));
+    delta2.addFace({0, 1, 2});
+    delta2.addFace({1, 2, 3});
+    delta2.updateMesh(vertices, stamps, faces);
+    EXPECT_EQ(stamps.size(), vertices.size());
+    EXPECT_EQ(vertices.size(), 6u);
+    for (size_t i = 0; i < vertices.size(); ++i) EXPECT_EQ(static_cast<size_t>(vertices.at(i).r), i);
+    EXPECT_EQ(faces.size(), 3u);
+    // beyond the reference's test: indices of the unarchived vertices, validation, labels
+    EXPECT_EQ(delta2.getActiveIndices()->size(), 4u);
+    EXPECT_EQ(delta2.getActiveIndices()->front(), 2);
+    delta2.validate(vertices, stamps, faces);
+    MeshDelta bad(0, 0);
+    bad.addVertex(1, point(0, 0, 0, 0, 0, 0));
+    bad.addFace({0, 1, 2});
+    bool threw = false;
+    try {
+      bad.checkFaces("test");
+    } catch (const std::runtime_error&) {
+      threw = true;
+    }
+    EXPECT_TRUE(threw);
+    MeshDelta labelled;
+    labelled.addVertex(5, point(1, 1, 1, 0, 0, 0), 7u);
+    labelled.addVertex(6, point(2, 2, 2, 0, 0, 0), 9u);
+    EXPECT_TRUE(labelled.hasSemantics());
+    std::vector<uint32_t> labels;
+    labelled.updateMesh(vertices, stamps, faces, &labels);
+    EXPECT_EQ(labels.size(), 2u);
+    EXPECT_EQ(labels.at(1), 9u);
+    EXPECT_EQ(stamps.at(1), Timestamp(6));
+  }
+  {  // archiveVerticesCorrect
+    MeshDelta delta(1, 3);
+    EXPECT_EQ(delta.addVertex(100, point(1.0f, 2.0f, 3.0f, 0, 0, 0), std::nullopt, true), 1u);
+    EXPECT_EQ(delta.addVertex(100, point(1.0f, 2.0f, 3.0f, 0, 0, 0), std::nullopt, true), 2u);
+    EXPECT_EQ(delta.addVertex(100, point(1.0f, 2.0f, 3.0f, 0, 0, 0), std::nullopt, false), 3u);
+    EXPECT_EQ(delta.addVertex(100, point(1.0f, 2.0f, 3.0f, 0, 0, 0), std::nullopt, false), 4u);
+    EXPECT_EQ(delta.getTotalArchivedVertices(), 3u);
+    EXPECT_EQ(delta.getNumArchivedVertices(), 2u);
+  }
+  {  // archiveFacesCorrect
+    MeshDelta delta(1, 3);
+    delta.addFace({0, 1, 2}, true);
+    delta.addFace({1, 2, 3}, true);
+    delta.addFace({0, 1, 2}, false);
+    delta.addFace({1, 2, 3}, false);
+    EXPECT_EQ(delta.getTotalArchivedFaces(), 5u);
+    EXPECT_EQ(delta.getNumArchivedFaces(), 2u);
+  }
+}
+
 static void testMeshFrontend() {
   MeshFrontendInterface::Config config;
   config.full_compression_method = MeshFrontendInterface::FullCompressionMethod::VOXEL_CLEARING;
@@ -1151,6 +1245,7 @@ int main(int argc, char** argv) {
   testVoxelClearing();
   testVoxbloxInterface();
   testDeltaCompression();
+  testMeshDelta();
   testMeshFrontend();
   if (with_octree) testOctreeCompression();
   std::printf("shim tests: %d checks, %d failures\n", g_checks, g_failures);
