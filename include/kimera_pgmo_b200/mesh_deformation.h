@@ -49,6 +49,10 @@ namespace kimera_pgmo_b200 {
 
 // common_structs.cpp:21-24
 inline Timestamp stampFromSec(double sec) { return pgmo_stamp_from_sec(sec); }
+// utils/common_structs.cpp:26-29 (host only; nothing on the device path needs it)
+inline double stampToSec(Timestamp stamp) {
+  return std::chrono::duration<double>(std::chrono::nanoseconds(stamp)).count();
+}
 
 class PgmoB200Error : public std::runtime_error {
  public:

@@ -1093,6 +1093,9 @@ static void testMeshDelta() {
     p.a = 255;
     return p;
   };
+  // kimera_pgmo/test/test_common_structs.cpp:12-20
+  EXPECT_EQ(Timestamp(105867312345678), stampFromSec(105867.312345678));
+  EXPECT_EQ(105867.312345678, stampToSec(Timestamp(105867312345678)));
   {  // constructor
     MeshDelta mesh;
     EXPECT_EQ(mesh.vertex_start, 0u);
