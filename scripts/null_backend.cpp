@@ -49,4 +49,32 @@ int pgmo_deform_mesh_device(pgmo_deform_t*, uint64_t, const void*, const uint64_
                             double, int, void*, uint8_t*, uint64_t*, void*) {
   return PGMO_ERR_UNSUPPORTED;
 }
+// the multi-device backend of the shim (linked, not used by bench_shim's single-device run)
+struct pgmo_deform_group {};
+int pgmo_deform_group_create(int, const int*, pgmo_deform_group_t** out) {
+  *out = new pgmo_deform_group();
+  return PGMO_OK;
+}
+void pgmo_deform_group_destroy(pgmo_deform_group_t* g) { delete g; }
+int pgmo_deform_group_size(pgmo_deform_group_t*) { return 1; }
+int pgmo_deform_group_set_controls(pgmo_deform_group_t*, uint64_t, const double*, const uint64_t*,
+                                   const uint8_t*, const double*) {
+  return PGMO_OK;
+}
+int pgmo_deform_group_update_poses(pgmo_deform_group_t*, const double*) { return PGMO_OK; }
+int pgmo_deform_group_points(pgmo_deform_group_t*, uint64_t n_v, const float* x, const float* y,
+                             const float* z, const uint64_t*, uint32_t, double, int, float* out_x,
+                             float* out_y, float* out_z, uint8_t* processed) {
+  std::memcpy(out_x, x, n_v * sizeof(float));
+  std::memcpy(out_y, y, n_v * sizeof(float));
+  std::memcpy(out_z, z, n_v * sizeof(float));
+  if (processed) std::memset(processed, 1, n_v);
+  return PGMO_OK;
+}
+int pgmo_deform_group_repeat(pgmo_deform_group_t* g, uint64_t n_v, const float* x, const float* y,
+                             const float* z, int precision, float* out_x, float* out_y, float* out_z,
+                             uint8_t* processed) {
+  return pgmo_deform_group_points(g, n_v, x, y, z, nullptr, 0, 0.0, precision, out_x, out_y, out_z,
+                                  processed);
+}
 }
