@@ -54,6 +54,10 @@ def parse_args():
     ap.add_argument("--no-tie-sweep", action="store_true")
     ap.add_argument("--no-config3", action="store_true")
     ap.add_argument("--only-config3", action="store_true")
+    ap.add_argument("--no-config4", action="store_true")
+    ap.add_argument("--config4-keyframes", type=int, default=300,
+                    help="keyframes of the configs[4] scenario (BASELINE: 1000; bounded by default so "
+                         "that the whole bench stays within minutes)")
     ap.add_argument("--config3-vertices-per-robot", type=int, default=25_000_000)
     return ap.parse_args()
 
@@ -710,6 +714,11 @@ def run_b200(args):
             line["compression"] = bench_compression(local_rank, with_cpu=not args.no_cpu_baseline)
         if world == 1 and not args.no_tie_sweep:
             line["tie_sweep"] = bench_tie_sweep(local_rank, n_local, n_ctrl)
+        if world == 1 and not args.no_config4:
+            # BASELINE configs[4]: OctreeCompression with horizon eviction + full re-deformation per
+            # loop closure (kimera_pgmo_b200/scenarios.py; the full 1000 keyframes: scripts/config5.py)
+            from kimera_pgmo_b200 import scenarios
+            line["config4"] = scenarios.run_config4(args.config4_keyframes, 50, local_rank)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -57,6 +57,10 @@ template <typename T>
 struct DevBuf {
   T* ptr = nullptr;
   size_t cap = 0;
+  // a buffer that had to grow once will grow again (a mesh that gains vertices between loop
+  // closures): with this set, a regrowth allocates twice what is asked for, so that a steadily
+  // growing caller pays cudaMalloc + cudaFree (tens to hundreds of ms here) log2 times
+  bool regrow_double = false;
   ~DevBuf() { release(); }
   DevBuf() = default;
   DevBuf(const DevBuf&) = delete;
@@ -71,6 +75,7 @@ struct DevBuf {
     if (n <= cap) return PGMO_OK;
     size_t new_cap = cap ? cap : 256;
     while (new_cap < n) new_cap += new_cap / 2 + 256;
+    if (regrow_double && cap > 0 && new_cap < 2 * n) new_cap = 2 * n;
     T* fresh = nullptr;
     if (traceAlloc()) fprintf(stderr, "pgmo alloc: device %zu -> %zu bytes\n", cap * sizeof(T), new_cap * sizeof(T));
     PGMO_CUDA(cudaMalloc(&fresh, new_cap * sizeof(T)));

@@ -33,6 +33,7 @@ struct PlaneSet {
     if (n <= pitch) return PGMO_OK;
     size_t want = pitch ? pitch : 256;
     while (want < n) want += want / 2 + 256;
+    if (pitch > 0 && want < 2 * n) want = 2 * n;  // a regrowth: see DevBuf::regrow_double
     want = (want + 1023) & ~static_cast<size_t>(1023);  // planes stay 4 KB aligned
     all.release();
     pitch = 0;
@@ -645,6 +646,10 @@ int pgmo_deform_create(int device, pgmo_deform_t** out) {
     cudaGetLastError();
   }
   cudaEventCreateWithFlags(&h->ev_fp, cudaEventDisableTiming);
+  // per-vertex buffers: a mesh grows between loop closures (BASELINE configs[4])
+  h->d_status.regrow_double = h->d_tie_list.regrow_double = h->d_tie_slot.regrow_double = true;
+  h->d_cache_rec.regrow_double = h->d_cache_w.regrow_double = h->d_vstamps.regrow_double = true;
+  h->d_of64.regrow_double = h->d_assoc.regrow_double = true;
   if (const char* e = std::getenv("PGMO_PIPE_TRACE")) h->pipe_trace = atoi(e) != 0;
   const unsigned pipe_ev_flags = h->pipe_trace ? cudaEventDefault : cudaEventDisableTiming;
   for (int i = 0; i < pgmo_deform::kMaxPipe; ++i) {

@@ -12,77 +12,10 @@ and, per closure, mesh size, control count and deformation time.
 import json
 import os
 import sys
-import time
-
-import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from kimera_pgmo_b200 import capi, synth  # noqa: E402
+from kimera_pgmo_b200 import scenarios  # noqa: E402
 
 n_kf = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
 closure_every = int(sys.argv[2]) if len(sys.argv) > 2 else 50
-horizon, res, verts, ctrl_per_kf = 10.0, 0.05, 50_000, 10
-
-oc = capi.OctHandle(res, 0)
-dh = capi.DeformHandle(0)
-rng = np.random.default_rng(0)
-lat_ms, closures, rounds = [], [], []
-ctrl_xyz, ctrl_stamps = [], []
-for m, (blocks, offsets, xyz, rgba, t) in enumerate(synth.compression_stream(n_kf, verts, n_blocks=1)):
-    t0 = time.perf_counter()
-    oc.prune(t - horizon)
-    oc.integrate(blocks, offsets, xyz, rgba, t)
-    lat_ms.append(1e3 * (time.perf_counter() - t0))
-    rounds.append(oc.last_stats()[0])
-    # control points of this keyframe: a subsample of the message's vertices (float-representable)
-    pick = rng.choice(xyz.shape[0], ctrl_per_kf, replace=False)
-    ctrl_xyz.append(xyz[pick].astype(np.float64))
-    ctrl_stamps.append(np.full(ctrl_per_kf, capi.stamp_from_sec(t), dtype=np.uint64))
-    if (m + 1) % closure_every == 0:
-        snap = oc.snapshot()
-        v = snap["vertices"]
-        order = np.argsort(snap["stamps"], kind="stable")  # mesh vertices in stamp order
-        x, y, z = (np.ascontiguousarray(v[order, a]) for a in range(3))
-        st = np.ascontiguousarray(snap["stamps"][order])
-        cp = np.concatenate(ctrl_xyz)
-        cs = np.concatenate(ctrl_stamps)
-        ramp = np.linspace(0.0, 1.0, cp.shape[0])
-        poses = np.zeros((cp.shape[0], 12))
-        poses[:, [0, 4, 8]] = 1.0
-        poses[:, 9:] = cp + np.stack([0.6 * ramp, 0.8 * ramp, 0 * ramp], 1)
-        t1 = time.perf_counter()
-        dh.set_controls(cp, cs, None, poses)
-        r = dh.deform_points(x, y, z, st, k=4, tol_t=10.0)
-        t_first = 1e3 * (time.perf_counter() - t1)
-        t2 = time.perf_counter()
-        dh.update_poses(poses)
-        dh.deform_points(x, y, z, st, k=4, tol_t=10.0)
-        t_again = 1e3 * (time.perf_counter() - t2)
-        # the same re-deformation on the compressor's device-resident cloud (stored order; no
-        # vertex upload, deformed cloud stays in HBM)
-        import torch
-        d_v, d_st, n_res = oc.device_view()
-        d_out = torch.empty((n_res, 4), dtype=torch.float32, device="cuda:0")
-        dh.deform_mesh_device(n_res, d_v, d_st, d_out, k=4, tol_t=10.0)
-        torch.cuda.synchronize()
-        t3 = time.perf_counter()
-        dh.update_poses(poses)
-        dh.deform_mesh_device(n_res, d_v, d_st, d_out, k=4, tol_t=10.0)
-        torch.cuda.synchronize()
-        t_res = 1e3 * (time.perf_counter() - t3)
-        closures.append({"keyframe": m + 1, "mesh_vertices": int(x.shape[0]), "controls": int(cp.shape[0]),
-                         "deform_ms_new_controls": t_first, "deform_ms_same_controls": t_again,
-                         "deform_ms_resident_cloud": t_res,
-                         "rc": int(r["rc"])})
-lat = np.array(lat_ms[5:])
-print(json.dumps({
-    "scenario": f"configs[4]: {n_kf} keyframes x {verts}-vertex messages, OctreeCompression res {res} m, "
-                f"horizon {horizon} s, closure every {closure_every}",
-    "compression_ms_per_message": {"mean": float(lat.mean()), "p50": float(np.percentile(lat, 50)),
-                                   "p99": float(np.percentile(lat, 99))},
-    "compressed_vertices_per_s": verts / (lat.mean() * 1e-3),
-    "fixed_point_rounds": {"mean": float(np.mean(rounds)), "max": int(np.max(rounds))},
-    "slowest_messages": [(int(i), round(float(lat_ms[i]), 2), int(rounds[i])) for i in np.argsort(lat_ms)[-5:]],
-    "final_mesh_vertices": closures[-1]["mesh_vertices"] if closures else 0,
-    "closures": closures[:3] + closures[-3:],
-}))
+print(json.dumps(scenarios.run_config4(n_kf, closure_every)))

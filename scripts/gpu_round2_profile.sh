@@ -10,7 +10,7 @@ echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu.log
 tail -3 gpurun_out/pytest_gpu.log
 timeout 400 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err
 echo "bench rc=$?"
-B="python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-compression --no-e2e --no-tie-sweep --no-config3"
+B="python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-compression --no-e2e --no-tie-sweep --no-config3 --no-config4"
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
   --log-file gpurun_out/r02_launches.csv $B > gpurun_out/ncu_launches.log 2>&1
 echo "ncu launches rc=$?"
