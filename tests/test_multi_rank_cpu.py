@@ -179,3 +179,75 @@ def test_two_ranks_three_robots_exchange(tmp_path):
                         "29654", str(worker), ROOT], capture_output=True, text=True, env=env,
                        timeout=280)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
+
+
+POSE_WORKER = r'''
+import json, os, sys
+import numpy as np
+import torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from kimera_pgmo_b200 import sharding
+
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+
+
+class RecordingHandle:
+    """stands in for capi.DeformHandle: records what the pose-exchange protocol asks of the C ABI"""
+    def __init__(self):
+        self.calls = []
+    def pose_source_create(self, n_c):
+        self.calls.append(("create", n_c))
+        return np.arange(64, dtype=np.uint8), 0
+    def pose_source_attach(self, n_c, ipc_handle=None, d_base=None, owner_device=0):
+        self.calls.append(("attach", n_c, [int(b) for b in ipc_handle[:4]]))
+    def pose_source_publish(self, seq, n_readers, poses, stream=0):
+        self.calls.append(("publish", seq, n_readers))
+    def update_poses_from_source_seq(self, seq, reader, row_begin, row_end, stream=0):
+        self.calls.append(("pull", seq, reader, row_begin, row_end))
+    def pose_source_write(self, buffer, poses, stream=0):
+        self.calls.append(("write", buffer))
+    def update_poses_from_source(self, buffer, row_begin, row_end, stream=0):
+        self.calls.append(("pull_buffer", buffer, row_begin, row_end))
+
+
+h = RecordingHandle()
+src = sharding.PoseSource(h, 1000, rank, world, torch.device("cpu"))
+poses = np.zeros((1000, 12))
+lo, hi = 100 * rank, 600 + 100 * rank
+for _ in range(3):
+    src.publish_and_pull(poses, lo, hi)
+src.pull_again(0, 1000)
+# the caller-ordered variant keeps working next to it
+src.write(poses)
+src.pull(lo, hi)
+json.dump(h.calls, open(os.path.join(sys.argv[2], f"pose_rank{rank}.json"), "w"))
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+def test_two_ranks_pose_exchange_protocol(tmp_path):
+    """sharding.PoseSource on two gloo ranks with a recording handle: the owner creates the source
+    and publishes sequence numbers 1, 2, 3 for `world` readers, every rank attaches with the
+    owner's IPC handle and pulls its rows as reader `rank` with the same sequence numbers
+    (pgmo_deform_pose_source_publish / pgmo_deform_update_poses_from_source_seq)."""
+    import json
+    worker = tmp_path / "pose_worker.py"
+    worker.write_text(POSE_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                        "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port",
+                        "29655", str(worker), ROOT, str(tmp_path)], capture_output=True, text=True,
+                       env=env, timeout=280)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
+    c0 = json.load(open(tmp_path / "pose_rank0.json"))
+    c1 = json.load(open(tmp_path / "pose_rank1.json"))
+    assert c0[0] == ["create", 1000]
+    assert c1[0] == ["attach", 1000, [0, 1, 2, 3]]           # the owner's handle bytes arrived
+    assert [c for c in c0 if c[0] == "publish"] == [["publish", s, 2] for s in (1, 2, 3)]
+    assert not [c for c in c1 if c[0] == "publish"]            # only the owner writes
+    assert [c for c in c0 if c[0] == "pull"] == [["pull", s, 0, 0, 600] for s in (1, 2, 3)] + [["pull", 3, 0, 0, 1000]]
+    assert [c for c in c1 if c[0] == "pull"] == [["pull", s, 1, 100, 700] for s in (1, 2, 3)] + [["pull", 3, 1, 0, 1000]]
+    assert c0[-2:] == [["write", 0], ["pull_buffer", 0, 0, 600]]
+    assert c1[-1] == ["pull_buffer", 0, 100, 700]
