@@ -785,7 +785,7 @@ def bench_config3(args, world, rank, local_rank, dev, stream, flag_group, peak):
         d["range"] = [0, n_c]
         segs.append((r, first, count, d))
     exchange = sharding.MultiRobotExchange(R, world, dev)
-    readers = {r: [rk for rk in range(world) if any(seg[0] == r for seg in plan[rk])] for r in range(R)}
+    readers = sharding.robot_readers(plan, R)
     flag_sync = os.environ.get("PGMO_POSE_SYNC", "flags") != "collective"
     state = {"valid": False, "step": 0}
     flag = torch.zeros(1, dtype=torch.int32)

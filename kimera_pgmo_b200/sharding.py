@@ -120,6 +120,14 @@ def plan_segments(counts, world: int):
     return plan
 
 
+def robot_readers(plan, n_robots: int):
+    """Per robot, the ranks that own a segment of it, in rank order: the readers of that robot's
+    pose source (a rank's reader id = its position in the list, pgmo_deform_pose_source_publish
+    waits for that many acknowledgements)."""
+    return {r: [rank for rank, segs in enumerate(plan) if any(seg[0] == r for seg in segs)]
+            for r in range(n_robots)}
+
+
 class MultiRobotExchange:
     """One StretchExchange per robot: ranks that own no vertex of a robot contribute an empty
     list (the collectives stay world-wide, a few KB each, and only run when a list changed)."""

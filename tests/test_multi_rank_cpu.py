@@ -126,6 +126,21 @@ def test_plan_segments_cover_every_robot_once():
         assert max(sizes) - min(sizes) <= 1  # equal slabs over the concatenated robots
 
 
+def test_robot_readers_are_dense_and_cover_every_segment():
+    """readers of a robot's pose source = the ranks owning a segment of the robot, rank order"""
+    from kimera_pgmo_b200 import sharding
+    for world in (1, 2, 3, 4, 8):
+        plan = sharding.plan_segments([25_000_000] * 4, world)
+        readers = sharding.robot_readers(plan, 4)
+        for r in range(4):
+            assert readers[r] == sorted(readers[r]) and len(set(readers[r])) == len(readers[r])
+            assert readers[r], "every robot is deformed by somebody"
+            for rank, segs in enumerate(plan):
+                assert (rank in readers[r]) == any(seg[0] == r for seg in segs)
+    assert sharding.robot_readers(sharding.plan_segments([10, 10, 10, 10], 8), 4) == {
+        0: [0, 1], 1: [2, 3], 2: [4, 5], 3: [6, 7]}
+
+
 def test_range_generator_is_partition_invariant():
     from kimera_pgmo_b200 import synth
     n, n_c = 2_300_000, 2300
